@@ -1,0 +1,351 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Never imported by the product (image-preprocessing-pipeline_b200/).
+
+CPU restatement (numpy) of the reference's per-plane destripe/enhancement path, each function citing the
+reference lines it follows (paths relative to /root/reference).  Third-party arithmetic:
+  * PyWavelets  -> oracle/pywt_c.c + oracle/pywt_shim.py        (restated; PARITY UNPINNED, absent offline)
+  * scipy.fftpack.rfft/irfft (pocketfft), scipy.ndimage.zoom, cv2.GaussianBlur -> the real libraries (present)
+  * log1p / expm1 -> glibc log1pf / expm1f (what numexpr, the reference's default, calls; oracle/pywt_c.c)
+Pinned by tests/test_oracle_vs_reference.py, which executes the reference source verbatim (oracle/ref_runner.py)
+in the build container, and by the golden vectors under tests/golden/ made from that same verbatim run.
+
+Semantics switch `quirks`:
+  quirks=False (default, "intended"): flat-field division is float32 (`img.astype(float32) / flat`) and the 5x5
+      Gaussian is applied.  quirks=True ("as written"): uint16 `img /= flat` raises TypeError (core.py:1250) and the
+      GaussianBlur result is discarded (core.py:1284), exactly as the shipped code behaves.
+"""
+import ctypes
+from math import ceil, exp, log, sqrt
+
+import numpy as np
+from scipy.fftpack import irfft, rfft
+from scipy.ndimage import zoom as ndi_zoom
+
+from . import pywt_shim as pywt
+
+PAD_MODES = ('constant', 'edge', 'linear_ramp', 'maximum', 'mean', 'median', 'minimum', 'reflect',
+             'symmetric', 'wrap', 'empty')
+
+
+# ---- libm pins ---------------------------------------------------------------------------------
+def log1p_f32(x: np.ndarray) -> np.ndarray:
+    """core.py:190-197 log1p_jit (numexpr 'log1p(img)' on float32 -> libm log1pf)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    pywt.lib().orc_log1pf(ctypes.c_void_p(x.ctypes.data), ctypes.c_void_p(out.ctypes.data), ctypes.c_size_t(x.size))
+    return out
+
+
+def expm1_f32(x: np.ndarray) -> np.ndarray:
+    """core.py:180-187 expm1_jit."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    pywt.lib().orc_expm1f(ctypes.c_void_p(x.ctypes.data), ctypes.c_void_p(out.ctypes.data), ctypes.c_size_t(x.size))
+    return out
+
+
+# ---- scalars -----------------------------------------------------------------------------------
+def notch_rise_point(sigma, rise):
+    """core.py:670-678."""
+    return int(sqrt(-2 * sigma ** 2 * log(1 - rise)) + .5) // 2 * 2
+
+
+def calculate_pad_size(shape, sigma, rise=0.5):
+    """core.py:681-698 (the VRAM cap term uses c = 5e14)."""
+    if sigma == 0:
+        return 0
+    x = shape[1] + 1
+    y = shape[0] + 1
+    c = 5e14
+    root = sqrt(x ** 2 - 2 * x * y + y ** 2 + 4 * c)
+    rise = min(round(1 - exp((x + y - root) / (4 * sigma ** 2)), 2) - 0.01, rise)
+    return notch_rise_point(sigma, rise)
+
+
+def np_notch(length: int, sigma: float) -> np.ndarray:
+    """core.py:637-667, numpy branch (:663-666): float32 throughout."""
+    if length <= 0:
+        raise ValueError('np_notch: length must be positive')
+    if sigma <= 0:
+        raise ValueError('np_notch: sigma must be positive')
+    g = np.arange(length, dtype=np.float32)
+    g **= 2
+    g /= -np.float32(2) * sigma ** 2
+    g = np.exp(g)
+    return np.float32(1) - g
+
+
+def np_filter_coefficient(coef: np.ndarray, width_frac: float, axis=-1) -> np.ndarray:
+    """core.py:749-754 + :701-722.  sigma uses the OTHER axis' length (coef.shape[axis + 1]); the notch is
+    indexed by packed-rfft array position, not by frequency."""
+    sigma = coef.shape[axis + 1] * width_frac
+    spec = rfft(coef, axis=axis)
+    g = np_notch(coef.shape[axis], sigma)
+    if axis == -2:
+        g = g.reshape(-1, 1)
+    spec *= g
+    return irfft(spec, axis=axis)
+
+
+def filter_subband(img, sigma, level, wavelet, axes=-1):
+    """core.py:840-940, numpy branch :927-940."""
+    level = None if level == 0 else level
+    d_type = img.dtype
+    rows, cols = img.shape
+    if isinstance(axes, int):
+        axes = (axes,)
+    coeffs = pywt.wavedec2(img, wavelet, mode='symmetric', level=level, axes=(-2, -1))
+    for i in range(1, len(coeffs)):
+        ch, cv, cd = coeffs[i]
+        if -1 in axes:
+            ch = np_filter_coefficient(ch, sigma / rows, axis=-1)
+        if -2 in axes:
+            cv = np_filter_coefficient(cv, sigma / cols, axis=-2)
+        coeffs[i] = (ch, cv, cd)
+    return pywt.waverec2(coeffs, wavelet, mode='symmetric', axes=(-2, -1)).astype(d_type)
+
+
+def filter_streak_dual_band(img, sigma1, sigma2, level, wavelet, threshold=None, axes=-1):
+    """core.py:943-979 with use_thresholding=False (the only reachable variant)."""
+    if (sigma1 > 0 and sigma1 == sigma2) or (threshold is not None and threshold <= 0):
+        return filter_subband(img, sigma1, level, wavelet, axes=axes)
+    img = filter_subband(img, sigma1, level, wavelet, axes=axes)
+    return filter_subband(img, sigma2, level, wavelet, axes=axes)
+
+
+def padded_geometry(shape, sigma, padding_mode):
+    """core.py:1084-1096: returns base_pad, pad_y, pad_x."""
+    pad_y, pad_x = [s % 2 for s in shape]
+    if isinstance(padding_mode, str):
+        padding_mode = padding_mode.lower()
+    if padding_mode not in PAD_MODES:
+        raise RuntimeError(f"Unsupported padding mode: {padding_mode}")
+    base_pad = calculate_pad_size(shape=shape, sigma=max(sigma))
+    min_len = 34
+    if shape[0] + 2 * base_pad + pad_y < min_len:
+        pad_y = min_len - (shape[0] + 2 * base_pad)
+    if shape[1] + 2 * base_pad + pad_x < min_len:
+        pad_x = min_len - (shape[1] + 2 * base_pad)
+    return base_pad, pad_y, pad_x
+
+
+def filter_streaks(img, sigma=(250, 250), level=0, wavelet='db9', crossover=10, threshold=None,
+                   padding_mode="wrap", bidirectional=False, log1p_normalization_needed=True,
+                   return_log_domain=False):
+    """core.py:982-1159 without the bleach-correction / masking options (never enabled by a caller)."""
+    if not isinstance(sigma, (tuple, list)):
+        sigma = (sigma,) * 2
+    s1, s2 = sigma
+    if s1 == s2 == 0:
+        return img
+    d_type = img.dtype
+    if log1p_normalization_needed:
+        img = log1p_f32(img.astype(np.float32))
+    shape = img.shape
+    base_pad, pad_y, pad_x = padded_geometry(shape, sigma, padding_mode)
+    if pad_y > 0 or pad_x > 0 or base_pad > 0:
+        mode = padding_mode.lower() if padding_mode else 'reflect'
+        img = np.pad(img, ((base_pad, base_pad + pad_y), (base_pad, base_pad + pad_x)), mode=mode)
+    img = filter_streak_dual_band(img, s1, s2, level, wavelet, threshold, axes=(-1, -2) if bidirectional else -1)
+    if pad_y > 0 or pad_x > 0 or base_pad > 0:
+        img = img[base_pad: img.shape[0] - (base_pad + pad_y), base_pad: img.shape[1] - (base_pad + pad_x)]
+        assert img.shape == shape
+    if return_log_domain:
+        return np.ascontiguousarray(img)
+    if log1p_normalization_needed:
+        img = expm1_f32(img) if img.dtype == np.float32 else np.expm1(img).astype(np.float32)
+    if np.dtype(d_type).kind in "ui":
+        img = np.rint(img)
+        info = np.iinfo(d_type)
+        np.clip(img, info.min, info.max, out=img)
+    if img.dtype != d_type:
+        img = img.astype(d_type)
+    return img
+
+
+# ---- process_img pieces ------------------------------------------------------------------------
+def is_uniform_2d(arr):
+    """core.py:106-121."""
+    if arr.size == 0:
+        return None
+    return bool((arr == arr.flat[0]).all())
+
+
+def normalize_flat(flat):
+    """core.py:2047-2049."""
+    f = flat.astype(np.float32)
+    return f / f.max()
+
+
+def convert_to_16bit_fun(img):
+    """core.py:397-399 (clip then C-cast: truncation toward zero)."""
+    img = np.clip(img, 0, 65535)
+    return img.astype(np.uint16)
+
+
+def convert_to_8bit_fun(img, bit_shift_to_right=8):
+    """core.py:402-423."""
+    if img is None or img.dtype == np.uint8:
+        return img
+    if img.dtype != np.uint16:
+        img = convert_to_16bit_fun(img)
+    if bit_shift_to_right is None:
+        bit_shift_to_right = 8
+    if not 0 <= bit_shift_to_right < 9:
+        raise RuntimeError("right shift should be between 0 and 8")
+    lower = 2 ** bit_shift_to_right
+    img = np.where((0 < img) & (img < lower), 1, img >> bit_shift_to_right)
+    img = np.clip(img, 0, 255)
+    return img.astype(np.uint8)
+
+
+def block_reduce(img, block, method):
+    """skimage.measure.block_reduce(img, block_size=block, func=np.{max,min,mean,median}), cval=0 padding of the
+    trailing edges (core.py:1286-1300).  mean/median return float64 like numpy."""
+    func = {'max': np.max, 'min': np.min, 'mean': np.mean, 'median': np.median}[method]
+    by, bx = block
+    py, px = (-img.shape[0]) % by, (-img.shape[1]) % bx
+    if py or px:
+        img = np.pad(img, ((0, py), (0, px)), mode='constant', constant_values=0)
+    v = img.reshape(img.shape[0] // by, by, img.shape[1] // bx, bx)
+    return func(v, axis=(1, 3))
+
+
+def calculate_down_sampled_size(tile_size, down_sample):
+    """core.py:1162-1170."""
+    return tuple(ceil(s / d) if d is not None else s for s, d in zip(tile_size, down_sample))
+
+
+def gaussian_blur_5x5(img):
+    """cv2.GaussianBlur(img, ksize=(5,5), sigmaX=1, sigmaY=1) — core.py:1284 (intended semantics)."""
+    import cv2
+    return cv2.GaussianBlur(img, ksize=(5, 5), sigmaX=1, sigmaY=1)
+
+
+# ---- lightsheet_correct ------------------------------------------------------------------------
+def _percentile_numba(data, q):
+    """numba's np.percentile (numba/np/arraymath.py _collect_percentiles_inner): linear interpolation between
+    closest ranks, float64; called through pystripe/lightsheet_correct.py:240-242."""
+    n = data.size
+    if n == 0:
+        return 0
+    a = np.sort(data.astype(np.float64), axis=None)
+    if n == 1:
+        return a[0]
+    if q == 100:
+        return a[-1]
+    rank = 1 + (n - 1) * (q / 100.0)
+    f = int(np.floor(rank))
+    m = rank - f
+    lower = a[f - 1]
+    upper = a[min(f, n - 1)]
+    return lower * (1 - m) + upper * m
+
+
+def local_percentile(source, percentile, selem, spacing=None, step=None, interpolate=1, dtype=None):
+    """lightsheet_correct.py:245-312 -> apply_local_function :113-237 for a 2-D plane (the reshape to (H,W,1)
+    and the unit third axis are dropped: they do not change any number)."""
+    q = 100 * percentile
+    shape = source.shape
+    if spacing is None:
+        spacing = selem
+    if step is None:
+        step = (None, None)
+    n_centers = tuple(s // h for s, h in zip(shape, spacing))
+    left = tuple((s - (n - 1) * h) // 2 for s, n, h in zip(shape, n_centers, spacing))
+    cy = list(range(left[0], shape[0], spacing[0]))
+    cx = list(range(left[1], shape[1], spacing[1]))
+    rdtype = source.dtype if dtype is None else dtype
+    # NB: meshgrid over range(le, s, h) may yield MORE centres than n_centers when (s - le) > n*h is impossible
+    # by construction ((n-1)*h + le < s <= n*h + le), so len(range) == n.
+    assert len(cy) == n_centers[0] and len(cx) == n_centers[1]
+    results = np.zeros(n_centers, dtype=rdtype)
+    hl = tuple(h // 2 for h in selem)
+    hr = tuple(h - l for h, l in zip(selem, hl))
+    for iy, yy in enumerate(cy):
+        sy = slice(max(0, yy - hl[0]), min(yy + hr[0], shape[0]), step[0])
+        for ix, xx in enumerate(cx):
+            sx = slice(max(0, xx - hl[1]), min(xx + hr[1], shape[1]), step[1])
+            results[iy, ix] = _percentile_numba(source[sy, sx], q)   # float64 -> rdtype C cast (truncation)
+    if interpolate:
+        zoom = tuple(float(s) / float(r) for s, r in zip(shape, results.shape))
+        results = ndi_zoom(results, zoom=zoom, order=interpolate)
+    return results
+
+
+def correct_lightsheet(img, percentile=0.25, artifact_length=150, background_window_size=200,
+                       lightsheet_vs_background=2.0, d_type=None):
+    """lightsheet_correct.py:31-106 as called from core.py:1333-1348."""
+    if d_type is None:
+        d_type = img.dtype
+    ls = local_percentile(img, percentile, selem=(1, artifact_length), dtype=d_type)
+    bg = local_percentile(img, percentile, selem=(background_window_size,) * 2, spacing=(25, 25), step=(2, 2),
+                          interpolate=1, dtype=d_type)
+    img = img.copy()
+    if isinstance(lightsheet_vs_background, float) and all(
+            a.dtype in (np.uint8, np.uint16) for a in (img, ls, bg)):
+        img -= np.minimum(img, np.minimum(ls, bg * int(lightsheet_vs_background)))
+    else:
+        img -= np.minimum(img, np.minimum(ls, bg * lightsheet_vs_background)).astype(img.dtype)
+    return img
+
+
+# ---- process_img -------------------------------------------------------------------------------
+def process_img(img, flat=None, gaussian_filter_2d=False, down_sample=None, down_sample_method='max',
+                tile_size=None, new_size=None, sigma=(0, 0), level=0, wavelet='coif15', threshold=None,
+                padding_mode="wrap", bidirectional=False, log1p_normalization_needed=True, dark=0,
+                lightsheet=False, artifact_length=150, background_window_size=200, percentile=0.25,
+                lightsheet_vs_background=2.0, rotate=0, flip_upside_down=False, convert_to_16bit=False,
+                convert_to_8bit=False, bit_shift_to_right=8, d_type=None, quirks=False):
+    """core.py:1190-1381 (order of operations preserved; bleach / dark-edge options not restated)."""
+    if new_size is not None:
+        raise NotImplementedError("new_size (skimage.transform.resize) is a 'next' row (SURVEY §8f N3)")
+    if tile_size is None:
+        tile_size = img.shape
+    tile_size = tuple(tile_size)
+    if d_type is None:
+        d_type = img.dtype
+    d_type = np.dtype(d_type)
+
+    if is_uniform_2d(img):                                             # :1232-1246
+        if down_sample is not None:
+            tile_size = calculate_down_sampled_size(tile_size, down_sample)
+        if rotate in (90, 270):
+            tile_size = (tile_size[1], tile_size[0])
+        out_t = np.uint16 if convert_to_16bit else (np.uint8 if convert_to_8bit else d_type)
+        return np.zeros(tile_size, dtype=out_t)
+
+    if flat is not None:                                               # :1248-1254
+        if tile_size == flat.shape:
+            if quirks and img.dtype.kind in "ui":
+                raise TypeError("ufunc 'divide' output cannot be cast (uint16 /= float32), core.py:1250")
+            img = img.astype(np.float32) / flat.astype(np.float32)
+    if gaussian_filter_2d and not quirks:                              # :1280-1284 (result discarded as written)
+        img = gaussian_blur_5x5(img)
+    if down_sample is not None:                                        # :1286-1300
+        method = down_sample_method.lower()
+        if method not in ('min', 'max', 'mean', 'median'):
+            raise RuntimeError(f"unsupported down-sampling method: {down_sample_method}")
+        img = block_reduce(img, down_sample, method)
+        tile_size = calculate_down_sampled_size(tile_size, down_sample)
+    if tuple(sigma) > (0, 0):                                          # :1302-1320
+        img = filter_streaks(img, sigma=sigma, level=level, wavelet=wavelet, threshold=threshold,
+                             padding_mode=padding_mode, bidirectional=bidirectional,
+                             log1p_normalization_needed=log1p_normalization_needed)
+    if dark is not None and dark > 0:                                  # :1324-1330 (numpy branch)
+        img = np.where(img > dark, img - dark, 0)
+    if lightsheet:                                                     # :1333-1348
+        img = correct_lightsheet(img, percentile, artifact_length, background_window_size,
+                                 lightsheet_vs_background, d_type=d_type)
+    if convert_to_16bit and img.dtype != np.uint16:                    # :1361-1369
+        img = convert_to_16bit_fun(img)
+    elif convert_to_8bit and img.dtype != np.uint8:
+        img = convert_to_8bit_fun(img, bit_shift_to_right=bit_shift_to_right)
+    elif d_type.kind in "ui":
+        img = np.clip(img, np.iinfo(d_type).min, np.iinfo(d_type).max).astype(d_type)
+    else:
+        img = img.astype(d_type)
+    if flip_upside_down:                                               # :1371-1379
+        img = np.flipud(img)
+    if rotate in (90, 180, 270):
+        img = np.rot90(img, rotate // 90)
+    return np.ascontiguousarray(img)
