@@ -1,0 +1,832 @@
+// C ABI (include/b200stripe.h): contexts, plans (geometry, tables, workspace) and the batched run loop.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200stripe.h"
+#include "b2s_internal.h"
+
+struct b2s_context {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    int64_t launches = 0;
+    bool timing = false;
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    double ms[B2S_N_KERNEL_CLASSES] = {0};
+    int64_t n_launch[B2S_N_KERNEL_CLASSES] = {0};
+};
+
+namespace {
+
+int fail(b2s_context *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                               \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(ctx, B2S_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                        \
+    } while (0)
+
+int dtype_size(int d) { return d == B2S_U8 ? 1 : (d == B2S_U16 ? 2 : 4); }
+int round4(int n) { return (n + 3) & ~3; }
+
+// pystripe/core.py:670-698 ------------------------------------------------------------------------------------
+double py_round2(double v)
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.2f", v);  // correctly rounded decimal, like Python's round(v, 2)
+    return strtod(buf, nullptr);
+}
+int notch_rise_point(double sigma, double rise)
+{
+    return (int)(std::sqrt(-2.0 * (sigma * sigma) * std::log(1.0 - rise)) + .5) / 2 * 2;
+}
+int calculate_pad_size(int rows, int cols, double sigma, double rise = 0.5)
+{
+    if (sigma == 0) return 0;
+    const double x = cols + 1, y = rows + 1, c = 5e14;
+    const double root = std::sqrt(x * x - 2 * x * y + y * y + 4 * c);
+    const double r = py_round2(1 - std::exp((x + y - root) / (4 * (sigma * sigma)))) - 0.01;
+    if (r < rise) rise = r;
+    return notch_rise_point(sigma, rise);
+}
+int size_log2(size_t x) { int r = -1; while (x) { ++r; x >>= 1; } return r; }
+int dwt_max_level(int n, int F) { return (F <= 1 || n < F - 1) ? 0 : size_log2((size_t)n / (F - 1)); }
+
+struct Geometry {
+    int in_rows, in_cols;
+    int work_rows, work_cols;     // after down-sample
+    int dsy, dsx;
+    int base_pad, pad_y, pad_x, PH, PW;
+    int n_passes;
+    double pass_sigma[2];
+    int levels;
+    int my[B2S_MAX_LEVELS + 1], mx[B2S_MAX_LEVELS + 1];  // index 0 = padded image, l = level l sub-bands
+    int work_dtype;               // dtype of the array the reference holds when it enters filter_streaks
+    int int_path;
+    int final_mode, out_dtype;
+    int out_rows, out_cols;
+    bool fuse_flat;
+};
+
+int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
+{
+    if (p.struct_size != (int)sizeof(b2s_params)) return fail(ctx, B2S_ERR_INVALID, "b2s_params.struct_size mismatch");
+    if (p.height <= 0 || p.width <= 0) return fail(ctx, B2S_ERR_INVALID, "empty plane");
+    if (p.in_dtype < B2S_U8 || p.in_dtype > B2S_F32) return fail(ctx, B2S_ERR_INVALID, "bad in_dtype");
+    if (p.sigma1 < 0 || p.sigma2 < 0) return fail(ctx, B2S_ERR_INVALID, "np_notch: sigma must be positive");
+    g.in_rows = p.height;
+    g.in_cols = p.width;
+    g.dsy = p.down_sample_y > 1 ? p.down_sample_y : 1;
+    g.dsx = p.down_sample_x > 1 ? p.down_sample_x : 1;
+    const bool ds = p.process_img && (p.down_sample_y > 0 || p.down_sample_x > 0) && (g.dsy > 1 || g.dsx > 1);
+    g.work_rows = ds ? (p.height + g.dsy - 1) / g.dsy : p.height;
+    g.work_cols = ds ? (p.width + g.dsx - 1) / g.dsx : p.width;
+    if (p.process_img && p.down_sample_method > B2S_DS_MEAN && ds)
+        return fail(ctx, B2S_ERR_UNSUPPORTED, "down_sample_method 'median' is not implemented on the GPU path");
+
+    // dtype bookkeeping (process_img order: flat -> gaussian -> block_reduce -> filter_streaks)
+    int dt = p.in_dtype;
+    const bool flat = p.process_img && p.has_flat;
+    if (flat) dt = B2S_F32;
+    const bool gauss = p.process_img && p.gaussian && !p.reference_quirks;
+    if (gauss && dt == B2S_F32)
+        return fail(ctx, B2S_ERR_UNSUPPORTED, "gaussian_filter_2d on a float32 image (flat given) is not implemented");
+    if (gauss && dt == B2S_U8) return fail(ctx, B2S_ERR_UNSUPPORTED, "gaussian_filter_2d on uint8 is not implemented");
+    if (ds && p.down_sample_method == B2S_DS_MEAN) {
+        if (dt == B2S_F32) return fail(ctx, B2S_ERR_UNSUPPORTED, "mean down-sampling of a float32 image is not implemented");
+        dt = B2S_F32;
+    }
+    g.work_dtype = dt;
+    g.fuse_flat = flat && !gauss && !ds;
+
+    // filter_streak_dual_band pass list, core.py:943-979
+    const double s1 = p.sigma1, s2 = p.sigma2;
+    if (s1 == 0 && s2 == 0) g.n_passes = 0;
+    else if ((s1 > 0 && s1 == s2) || p.threshold_nonpositive) { g.n_passes = 1; g.pass_sigma[0] = s1; }
+    else { g.n_passes = 2; g.pass_sigma[0] = s1; g.pass_sigma[1] = s2; }
+    for (int i = 0; i < g.n_passes; ++i)
+        if (g.pass_sigma[i] <= 0) return fail(ctx, B2S_ERR_INVALID, "np_notch: sigma must be positive");
+
+    g.base_pad = g.pad_y = g.pad_x = 0;
+    g.PH = g.work_rows;
+    g.PW = g.work_cols;
+    g.levels = 0;
+    g.my[0] = g.PH;
+    g.mx[0] = g.PW;
+    if (g.n_passes > 0) {
+        if (p.pad_mode < B2S_PAD_REFLECT || p.pad_mode > B2S_PAD_CONSTANT)
+            return fail(ctx, B2S_ERR_UNSUPPORTED, "padding mode not implemented on the GPU path");
+        if (p.n_taps < 2 || p.n_taps > B2S_MAX_TAPS || (p.n_taps & 1) || !p.dec_lo)
+            return fail(ctx, B2S_ERR_INVALID, "wavelet filter must have an even length in [2, %d]", B2S_MAX_TAPS);
+        // core.py:1084-1096
+        g.pad_y = g.work_rows % 2;
+        g.pad_x = g.work_cols % 2;
+        g.base_pad = calculate_pad_size(g.work_rows, g.work_cols, s1 > s2 ? s1 : s2);
+        const int min_len = 34;
+        if (g.work_rows + 2 * g.base_pad + g.pad_y < min_len) g.pad_y = min_len - (g.work_rows + 2 * g.base_pad);
+        if (g.work_cols + 2 * g.base_pad + g.pad_x < min_len) g.pad_x = min_len - (g.work_cols + 2 * g.base_pad);
+        g.PH = g.work_rows + 2 * g.base_pad + g.pad_y;
+        g.PW = g.work_cols + 2 * g.base_pad + g.pad_x;
+        const int F = p.n_taps;
+        const int lmax = std::min(dwt_max_level(g.PH, F), dwt_max_level(g.PW, F));
+        int L = p.level == 0 ? lmax : p.level;
+        if (L < 0) return fail(ctx, B2S_ERR_INVALID, "Level value of %d is too low . Minimum level is 0.", L);
+        if (L > B2S_MAX_LEVELS) return fail(ctx, B2S_ERR_INVALID, "level too high");
+        g.my[0] = g.PH;
+        g.mx[0] = g.PW;
+        for (int l = 1; l <= L; ++l) {
+            if (g.my[l - 1] < F || g.mx[l - 1] < F)
+                return fail(ctx, B2S_ERR_UNSUPPORTED, "level %d: image side %dx%d shorter than the filter (%d taps)", l,
+                            g.my[l - 1], g.mx[l - 1], F);
+            g.my[l] = (g.my[l - 1] + F - 1) / 2;
+            g.mx[l] = (g.mx[l - 1] + F - 1) / 2;
+        }
+        g.levels = L;
+    }
+    g.int_path = g.n_passes > 0 && g.work_dtype != B2S_F32;
+
+    // final conversion, core.py:1361-1369
+    if (!p.process_img) {
+        g.out_dtype = p.in_dtype;
+        g.final_mode = p.in_dtype == B2S_F32 ? 3 : 0;
+    } else {
+        // dtype of the array right before the conversion
+        int cur = g.work_dtype;
+        if (p.dark > 0 && cur != B2S_F32 && p.dark != std::floor(p.dark)) cur = B2S_F32;  // promoted to float64
+        if (p.convert_to_16bit && cur != B2S_U16) { g.final_mode = 1; g.out_dtype = B2S_U16; }
+        else if (p.convert_to_8bit && cur != B2S_U8) { g.final_mode = 2; g.out_dtype = B2S_U8; }
+        else if (p.out_dtype != B2S_F32) { g.final_mode = 0; g.out_dtype = p.out_dtype; }
+        else { g.final_mode = 3; g.out_dtype = B2S_F32; }
+        if (p.convert_to_8bit && (p.bit_shift_to_right < 0 || p.bit_shift_to_right > 8))
+            return fail(ctx, B2S_ERR_INVALID, "right shift should be between 0 and 8");
+    }
+    if (p.rotate != 0 && p.rotate != 90 && p.rotate != 180 && p.rotate != 270)
+        return fail(ctx, B2S_ERR_INVALID, "rotate must be 0, 90, 180 or 270");
+    const bool swap = p.process_img && (p.rotate == 90 || p.rotate == 270);
+    g.out_rows = swap ? g.work_cols : g.work_rows;
+    g.out_cols = swap ? g.work_rows : g.work_cols;
+    if (p.process_img && p.lightsheet) return fail(ctx, B2S_ERR_UNSUPPORTED, "lightsheet=True is not implemented yet");
+    return B2S_OK;
+}
+
+void fill_info(const b2s_params &p, const Geometry &g, b2s_plan_info *info)
+{
+    memset(info, 0, sizeof *info);
+    info->out_height = g.out_rows;
+    info->out_width = g.out_cols;
+    info->out_dtype = g.out_dtype;
+    info->n_passes = g.n_passes;
+    info->work_height = g.work_rows;
+    info->work_width = g.work_cols;
+    info->base_pad = g.base_pad;
+    info->pad_y = g.pad_y;
+    info->pad_x = g.pad_x;
+    info->padded_height = g.PH;
+    info->padded_width = g.PW;
+    info->levels = g.levels;
+    int64_t bytes = 0, flops = 0;
+    const int F = p.n_taps;
+    if (g.n_passes > 0) {
+        bytes += (int64_t)dtype_size(g.work_dtype) * g.work_rows * g.work_cols + 4ll * g.PH * g.PW;  // prologue
+        int64_t per_pass = 0;
+        for (int l = 1; l <= g.levels; ++l) {
+            info->level_rows[l - 1] = g.my[l];
+            info->level_cols[l - 1] = g.mx[l];
+            const int64_t sub = (int64_t)g.my[l] * g.mx[l], inp = (int64_t)g.my[l - 1] * g.mx[l - 1];
+            per_pass += 4 * inp + 16 * sub;                       // forward
+            per_pass += 8 * sub * (p.bidirectional ? 2 : 1);      // notch
+            per_pass += 16 * sub + 4 * inp;                       // inverse
+            // MACs: axis -2 pass 2F per (my x nx) sample, axis -1 pass 4F per (my x mx); synthesis mirrors it
+            flops += 2 * 2 * ((int64_t)2 * F * g.my[l] * g.mx[l - 1] + (int64_t)4 * F * sub);
+        }
+        bytes += per_pass * g.n_passes;
+        flops *= g.n_passes;
+        bytes += 4ll * g.work_rows * g.work_cols + (int64_t)dtype_size(g.out_dtype) * g.out_rows * g.out_cols;  // epilogue
+    } else {
+        bytes += (int64_t)(dtype_size(p.in_dtype)) * p.height * p.width + (int64_t)dtype_size(g.out_dtype) * g.out_rows * g.out_cols;
+    }
+    info->algorithmic_bytes_per_plane = bytes;
+    info->flops_per_plane = flops;
+}
+
+std::vector<int> factorize(int n)
+{
+    std::vector<int> f;
+    for (int p : {4, 2, 3, 5, 7})
+        while (n % p == 0) { f.push_back(p); n /= p; }
+    for (int p = 11; n > 1; p += 2) {
+        if ((int64_t)p * p > n) { f.push_back(n); break; }
+        while (n % p == 0) { f.push_back(p); n /= p; }
+    }
+    return f;
+}
+
+}  // namespace
+
+struct b2s_plan {
+    b2s_context *ctx = nullptr;
+    b2s_params p;
+    Geometry g;
+    B2sTaps taps;
+    int B = 1;            // max batch
+    // device workspace (one slot per in-flight batch)
+    static constexpr int kSlots = 2;
+    struct Slot {
+        float *padded = nullptr;
+        float *sub[B2S_MAX_LEVELS + 1][4] = {};
+        void *d_in = nullptr, *d_out = nullptr;
+        void *pre_a = nullptr, *pre_b = nullptr;   // pre-op temporaries
+        unsigned *mm = nullptr;
+        int *flags = nullptr;
+        void *h_in = nullptr, *h_out = nullptr;    // pinned staging
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+    } slot[kSlots];
+    int n_slots_ready = 0;
+    int pitch[B2S_MAX_LEVELS + 1];
+    size_t plane_stride[B2S_MAX_LEVELS + 1];
+    float *d_flat = nullptr;
+    std::map<int, B2sFftPlan> fft;                  // by length
+    float *d_notch[2][B2S_MAX_LEVELS + 1][2] = {};  // [pass][level][axis: 0 = cH rows, 1 = cV cols]
+    int64_t workspace_bytes = 0;
+    std::vector<void *> allocs;
+    int last_batch = 0;
+};
+
+namespace {
+
+int dev_alloc(b2s_plan *pl, void **ptr, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess) return fail(pl->ctx, B2S_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    pl->allocs.push_back(*ptr);
+    pl->workspace_bytes += (int64_t)bytes;
+    return B2S_OK;
+}
+
+struct ClassTimer {
+    b2s_context *ctx;
+    cudaStream_t s;
+    int cls;
+    int n;
+    cudaEvent_t a = nullptr;
+    ClassTimer(b2s_context *c, cudaStream_t st, int k, int n_launches) : ctx(c), s(st), cls(k), n(n_launches)
+    {
+        ctx->launches += n;
+        ctx->n_launch[cls] += n;
+        if (ctx->timing) { cudaEventCreate(&a); cudaEventRecord(a, s); }
+    }
+    ~ClassTimer()
+    {
+        if (ctx->timing) {
+            cudaEvent_t b;
+            cudaEventCreate(&b);
+            cudaEventRecord(b, s);
+            ctx->spans.push_back({cls, a, b});
+        }
+    }
+};
+
+B2sImg img_of(b2s_plan *pl, float *base, int level)
+{
+    B2sImg im;
+    im.ptr = base;
+    im.plane_stride = pl->plane_stride[level];
+    im.pitch = pl->pitch[level];
+    im.rows = pl->g.my[level];
+    im.cols = pl->g.mx[level];
+    return im;
+}
+
+int build_tables(b2s_plan *pl)
+{
+    b2s_context *ctx = pl->ctx;
+    const Geometry &g = pl->g;
+    const b2s_params &p = pl->p;
+    // filters: pywt derives everything from one table (wavelets.c); float32 copies of the double values
+    const int F = p.n_taps;
+    B2sTaps &t = pl->taps;
+    memset(&t, 0, sizeof t);
+    t.F = F;
+    std::vector<double> dec_lo(p.dec_lo, p.dec_lo + F), rec_lo(F), rec_hi(F), dec_hi(F);
+    for (int k = 0; k < F; ++k) rec_lo[k] = dec_lo[F - 1 - k];
+    for (int k = 0; k < F; ++k) rec_hi[k] = ((k & 1) ? -1.0 : 1.0) * rec_lo[F - 1 - k];
+    for (int k = 0; k < F; ++k) dec_hi[k] = rec_hi[F - 1 - k];
+    for (int k = 0; k < F; ++k) {
+        t.dec_lo[k] = (float)dec_lo[k];
+        t.dec_hi[k] = (float)dec_hi[k];
+        t.rec_lo[k] = (float)rec_lo[k];
+        t.rec_hi[k] = (float)rec_hi[k];
+    }
+    // per-level FFT plans + notch tables (np_notch, core.py:637-667, numpy float32 branch)
+    for (int pass = 0; pass < g.n_passes; ++pass) {
+        for (int l = 1; l <= g.levels; ++l) {
+            for (int axis = 0; axis < (p.bidirectional ? 2 : 1); ++axis) {
+                const int n = axis == 0 ? g.mx[l] : g.my[l];
+                const int other = axis == 0 ? g.my[l] : g.mx[l];
+                const int img_len = axis == 0 ? g.PH : g.PW;
+                if (b2s_notch_smem(n) > 220 * 1024)
+                    return fail(ctx, B2S_ERR_UNSUPPORTED, "sub-band side %d too long for the shared-memory FFT", n);
+                if (!pl->fft.count(n)) {
+                    B2sFftPlan fp;
+                    fp.n = n;
+                    std::vector<int> f = factorize(n);
+                    if (f.size() > 32) return fail(ctx, B2S_ERR_UNSUPPORTED, "too many FFT factors");
+                    fp.n_factors = (int)f.size();
+                    for (size_t i = 0; i < f.size(); ++i) fp.factors[i] = f[i];
+                    std::vector<float2> tw(n);
+                    for (int k = 0; k < n; ++k) {
+                        const double ang = -2.0 * M_PI * (double)k / (double)n;
+                        tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+                    }
+                    int rc = dev_alloc(pl, (void **)&fp.d_twiddle, sizeof(float2) * n);
+                    if (rc) return rc;
+                    CU(ctx, cudaMemcpy(fp.d_twiddle, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+                    pl->fft[n] = fp;
+                }
+                const double width_frac = g.pass_sigma[pass] / (double)img_len;
+                const double sigma_l = (double)other * width_frac;
+                const float denom = -2.0f * (float)(sigma_l * sigma_l);
+                std::vector<float> gt(n);
+                for (int k = 0; k < n; ++k) {
+                    float v = (float)k;
+                    v = v * v;
+                    v = v / denom;
+                    v = expf(v);
+                    gt[k] = 1.0f - v;
+                }
+                int rc = dev_alloc(pl, (void **)&pl->d_notch[pass][l][axis], sizeof(float) * n);
+                if (rc) return rc;
+                CU(ctx, cudaMemcpy(pl->d_notch[pass][l][axis], gt.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+            }
+        }
+    }
+    return B2S_OK;
+}
+
+int alloc_slot(b2s_plan *pl, int si)
+{
+    b2s_context *ctx = pl->ctx;
+    const Geometry &g = pl->g;
+    const b2s_params &p = pl->p;
+    b2s_plan::Slot &s = pl->slot[si];
+    const size_t B = pl->B;
+    int rc;
+    if (g.n_passes > 0) {
+        if ((rc = dev_alloc(pl, (void **)&s.padded, sizeof(float) * pl->plane_stride[0] * B))) return rc;
+        for (int l = 1; l <= g.levels; ++l)
+            for (int k = 0; k < 4; ++k)
+                if ((rc = dev_alloc(pl, (void **)&s.sub[l][k], sizeof(float) * pl->plane_stride[l] * B))) return rc;
+    }
+    const size_t in_elems = (size_t)g.in_rows * g.in_cols, work_elems = (size_t)g.work_rows * g.work_cols;
+    if ((rc = dev_alloc(pl, &s.d_in, in_elems * dtype_size(p.in_dtype) * B))) return rc;
+    if ((rc = dev_alloc(pl, &s.d_out, (size_t)g.out_rows * g.out_cols * dtype_size(g.out_dtype) * B))) return rc;
+    if (p.process_img) {
+        if ((rc = dev_alloc(pl, &s.pre_a, in_elems * 4 * B))) return rc;
+        if ((rc = dev_alloc(pl, &s.pre_b, in_elems * 4 * B))) return rc;
+        if ((rc = dev_alloc(pl, (void **)&s.mm, sizeof(unsigned) * 2 * B))) return rc;
+        if ((rc = dev_alloc(pl, (void **)&s.flags, sizeof(int) * B))) return rc;
+    }
+    (void)work_elems;
+    CU(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    return B2S_OK;
+}
+
+// enqueue the whole per-batch pipeline on `st` using slot workspace `s`
+int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out, int nb, cudaStream_t st)
+{
+    b2s_context *ctx = pl->ctx;
+    const Geometry &g = pl->g;
+    const b2s_params &p = pl->p;
+    const int exact = p.exact;
+    pl->last_batch = nb;
+
+    // ---- process_img pre-ops (core.py:1232-1300)
+    const void *cur = d_in;
+    int cur_dt = p.in_dtype;
+    if (p.process_img) {
+        ClassTimer t(ctx, st, B2S_K_PRE, 3);
+        b2s_launch_uniform(d_in, p.in_dtype, (size_t)g.in_rows * g.in_cols, nb, s.mm, s.flags, st);
+    }
+    const bool flat = p.process_img && p.has_flat;
+    if (flat && !pl->d_flat) return fail(ctx, B2S_ERR_INVALID, "has_flat is set but b2s_plan_set_flat was not called");
+    if (flat && !g.fuse_flat) {
+        ClassTimer t(ctx, st, B2S_K_PRE, 1);
+        b2s_launch_flat_divide(cur, cur_dt, pl->d_flat, (float *)s.pre_a, (size_t)g.in_rows * g.in_cols, nb, st);
+        cur = s.pre_a;
+        cur_dt = B2S_F32;
+    }
+    if (p.process_img && p.gaussian && !p.reference_quirks) {
+        ClassTimer t(ctx, st, B2S_K_PRE, 1);
+        b2s_launch_gauss5_u16((const uint16_t *)cur, (uint16_t *)s.pre_b, g.in_rows, g.in_cols, nb, st);
+        cur = s.pre_b;
+    }
+    if (g.work_rows != g.in_rows || g.work_cols != g.in_cols) {
+        ClassTimer t(ctx, st, B2S_K_PRE, 1);
+        void *dst = (cur == s.pre_a) ? s.pre_b : s.pre_a;
+        b2s_launch_block_reduce(cur, cur_dt, g.in_rows, g.in_cols, g.dsy, g.dsx, p.down_sample_method, dst, g.work_dtype,
+                                g.work_rows, g.work_cols, nb, st);
+        cur = dst;
+        cur_dt = g.work_dtype;
+    }
+
+    B2sImg padded = img_of(pl, s.padded, 0);
+    if (g.n_passes > 0) {
+        {
+            ClassTimer t(ctx, st, B2S_K_PROLOGUE, 1);
+            B2sPrologueArgs a;
+            a.in = cur;
+            a.in_dtype = cur_dt;
+            a.src_rows = g.work_rows;
+            a.src_cols = g.work_cols;
+            a.flat = g.fuse_flat ? pl->d_flat : nullptr;
+            a.pad_mode = p.pad_mode;
+            a.base_pad = g.base_pad;
+            a.use_log1p = p.log1p;
+            a.out = padded;
+            b2s_launch_prologue(a, nb, st);
+        }
+        if (p.debug_stop_after == B2S_STAGE_PROLOGUE) return B2S_OK;
+        for (int pass = 0; pass < g.n_passes; ++pass) {
+            {
+                ClassTimer t(ctx, st, B2S_K_DWT_FWD, g.levels);
+                for (int l = 1; l <= g.levels; ++l) {
+                    const B2sImg in = l == 1 ? padded : img_of(pl, s.sub[l - 1][0], l - 1);
+                    b2s_launch_dwt_fwd(pl->taps, in, img_of(pl, s.sub[l][0], l), img_of(pl, s.sub[l][1], l),
+                                       img_of(pl, s.sub[l][2], l), img_of(pl, s.sub[l][3], l), nb, exact, st);
+                }
+            }
+            if (p.debug_stop_after == B2S_STAGE_FORWARD) return B2S_OK;
+            {
+                ClassTimer t(ctx, st, B2S_K_NOTCH, g.levels * (p.bidirectional ? 2 : 1));
+                for (int l = 1; l <= g.levels; ++l) {
+                    b2s_launch_notch(pl->fft[g.mx[l]], pl->d_notch[pass][l][0], img_of(pl, s.sub[l][1], l), 0, nb,
+                                     ctx->sm_count, st);
+                    if (p.bidirectional)
+                        b2s_launch_notch(pl->fft[g.my[l]], pl->d_notch[pass][l][1], img_of(pl, s.sub[l][2], l), 1, nb,
+                                         ctx->sm_count, st);
+                }
+            }
+            if (p.debug_stop_after == B2S_STAGE_NOTCH) return B2S_OK;
+            {
+                ClassTimer t(ctx, st, B2S_K_DWT_INV, g.levels);
+                for (int l = g.levels; l >= 1; --l) {
+                    // the reconstruction of level l-1 overwrites that level's approximation buffer (or the padded image)
+                    B2sImg out = l == 1 ? padded : img_of(pl, s.sub[l - 1][0], l - 1);
+                    b2s_launch_dwt_inv(pl->taps, img_of(pl, s.sub[l][0], l), img_of(pl, s.sub[l][1], l),
+                                       img_of(pl, s.sub[l][2], l), img_of(pl, s.sub[l][3], l), out, nb, exact, st);
+                }
+            }
+        }
+        if (p.debug_stop_after == B2S_STAGE_INVERSE) return B2S_OK;
+    }
+    {
+        ClassTimer t(ctx, st, B2S_K_EPILOGUE, 1);
+        B2sEpilogueArgs e;
+        memset(&e, 0, sizeof e);
+        e.in = padded;
+        e.raw = cur;
+        e.raw_dtype = cur_dt;
+        e.destripe = g.n_passes > 0;
+        e.base_pad = g.base_pad;
+        e.rows = g.work_rows;
+        e.cols = g.work_cols;
+        e.use_log1p = p.log1p;
+        e.int_path = g.int_path;
+        e.work_dtype = g.work_dtype;
+        e.dark = p.process_img ? p.dark : 0.0;
+        e.ls_sub = nullptr;
+        e.final_mode = g.final_mode;
+        e.shift = p.bit_shift_to_right;
+        e.out_dtype = g.out_dtype;
+        e.flip = p.process_img ? p.flip_upside_down : 0;
+        e.rot = p.process_img ? p.rotate / 90 : 0;
+        e.uniform_flags = p.process_img ? s.flags : nullptr;
+        e.out = d_out;
+        e.out_rows = g.out_rows;
+        e.out_cols = g.out_cols;
+        b2s_launch_epilogue(e, nb, st);
+    }
+    CU(ctx, cudaGetLastError());
+    return B2S_OK;
+}
+
+bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2s_version(void) { return B2S_VERSION; }
+
+void b2s_params_default(b2s_params *p)
+{
+    memset(p, 0, sizeof *p);
+    p->struct_size = (int32_t)sizeof *p;
+    p->in_dtype = p->out_dtype = B2S_U16;
+    p->pad_mode = B2S_PAD_WRAP;
+    p->log1p = 1;
+    p->artifact_length = 150;
+    p->background_window_size = 200;
+    p->percentile = 0.25;
+    p->lightsheet_vs_background = 2.0;
+    p->bit_shift_to_right = 8;
+    p->max_batch = 8;
+    p->exact = 1;
+}
+
+int b2s_create(int device, b2s_context **out)
+{
+    if (!out) return B2S_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    b2s_context *ctx = new b2s_context();
+    *out = ctx;  // returned even on failure so that b2s_last_error works; caller destroys it
+    if (e != cudaSuccess || n == 0)
+        return fail(ctx, B2S_ERR_CUDA, "no CUDA device available (%s) — this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(ctx, B2S_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+    ctx->device = device;
+    CU(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(ctx, cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10)
+        return fail(ctx, B2S_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    return B2S_OK;
+}
+
+void b2s_destroy(b2s_context *ctx)
+{
+    if (!ctx) return;
+    for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    delete ctx;
+}
+
+const char *b2s_last_error(const b2s_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int b2s_device_sm_count(const b2s_context *ctx) { return ctx ? ctx->sm_count : 0; }
+int64_t b2s_launch_count(const b2s_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int b2s_plan_geometry(const b2s_params *params, b2s_plan_info *info, char *err, size_t err_len)
+{
+    if (!params || !info) return B2S_ERR_INVALID;
+    b2s_context tmp;
+    Geometry g;
+    int rc = compute_geometry(&tmp, *params, g);
+    if (rc) {
+        if (err && err_len) snprintf(err, err_len, "%s", tmp.err.c_str());
+        return rc;
+    }
+    fill_info(*params, g, info);
+    return B2S_OK;
+}
+
+int b2s_plan_create(b2s_context *ctx, const b2s_params *params, b2s_plan **out)
+{
+    if (!ctx || !params || !out) return B2S_ERR_INVALID;
+    *out = nullptr;
+    Geometry g;
+    int rc = compute_geometry(ctx, *params, g);
+    if (rc) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+    b2s_plan *pl = new b2s_plan();
+    pl->ctx = ctx;
+    pl->p = *params;
+    pl->g = g;
+    pl->B = params->max_batch > 0 ? params->max_batch : 8;
+    for (int l = 0; l <= g.levels; ++l) {
+        pl->pitch[l] = round4(g.mx[l]);
+        pl->plane_stride[l] = (size_t)pl->pitch[l] * g.my[l];
+    }
+    if (g.n_passes == 0) { pl->pitch[0] = round4(g.PW); pl->plane_stride[0] = (size_t)pl->pitch[0] * g.PH; }
+    if (g.n_passes > 0) {
+        const int need = b2s_dwt_max_smem(params->n_taps);
+        if (need > 227 * 1024) { delete pl; return fail(ctx, B2S_ERR_UNSUPPORTED, "filter too long for the shared-memory tiles"); }
+        rc = build_tables(pl);
+    }
+    for (int si = 0; rc == B2S_OK && si < b2s_plan::kSlots; ++si) rc = alloc_slot(pl, si);
+    pl->p.dec_lo = nullptr;  // the caller's table is not retained
+    if (rc) { b2s_plan_destroy(pl); return rc; }
+    *out = pl;
+    return B2S_OK;
+}
+
+void b2s_plan_destroy(b2s_plan *pl)
+{
+    if (!pl) return;
+    cudaSetDevice(pl->ctx->device);
+    cudaDeviceSynchronize();
+    for (void *p : pl->allocs) cudaFree(p);
+    for (auto &s : pl->slot) {
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    delete pl;
+}
+
+int b2s_plan_query(const b2s_plan *pl, b2s_plan_info *info)
+{
+    if (!pl || !info) return B2S_ERR_INVALID;
+    b2s_params p = pl->p;
+    fill_info(p, pl->g, info);
+    info->workspace_bytes = pl->workspace_bytes;
+    return B2S_OK;
+}
+
+int b2s_plan_set_flat(b2s_plan *pl, const float *flat, int is_device)
+{
+    if (!pl || !flat) return B2S_ERR_INVALID;
+    b2s_context *ctx = pl->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(float) * (size_t)pl->g.in_rows * pl->g.in_cols;
+    if (!pl->d_flat) {
+        int rc = dev_alloc(pl, (void **)&pl->d_flat, bytes);
+        if (rc) return rc;
+    }
+    CU(ctx, cudaMemcpy(pl->d_flat, flat, bytes, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return B2S_OK;
+}
+
+int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is_device, int out_is_device, void *stream)
+{
+    if (!pl || !in || !out || n_planes < 0) return B2S_ERR_INVALID;
+    b2s_context *ctx = pl->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const Geometry &g = pl->g;
+    const size_t in_plane = (size_t)g.in_rows * g.in_cols * dtype_size(pl->p.in_dtype);
+    const size_t out_plane = (size_t)g.out_rows * g.out_cols * dtype_size(g.out_dtype);
+    const int B = pl->B;
+
+    if (in_is_device && out_is_device) {
+        cudaStream_t st = (cudaStream_t)stream;
+        for (int64_t z = 0; z < n_planes; z += B) {
+            const int nb = (int)std::min<int64_t>(B, n_planes - z);
+            int rc = enqueue_batch(pl, pl->slot[0], (const char *)in + z * in_plane, (char *)out + z * out_plane, nb, st);
+            if (rc) return rc;
+        }
+        return B2S_OK;
+    }
+
+    // host path: two slots, each with its own stream: H2D -> kernels -> D2H; the slots overlap each other
+    const bool in_pinned = in_is_device || is_pinned_host(in);
+    const bool out_pinned = out_is_device || is_pinned_host(out);
+    for (auto &s : pl->slot) {
+        if (!in_pinned && !s.h_in) CU(ctx, cudaMallocHost(&s.h_in, in_plane * B));
+        if (!out_pinned && !s.h_out) CU(ctx, cudaMallocHost(&s.h_out, out_plane * B));
+    }
+    struct Pending { int64_t z; int nb; bool active; } pend[b2s_plan::kSlots] = {};
+    auto drain = [&](int si) -> int {
+        if (!pend[si].active) return B2S_OK;
+        b2s_plan::Slot &s = pl->slot[si];
+        CU(ctx, cudaEventSynchronize(s.done));
+        if (!out_is_device && !out_pinned)
+            memcpy((char *)out + pend[si].z * out_plane, s.h_out, out_plane * pend[si].nb);
+        pend[si].active = false;
+        return B2S_OK;
+    };
+    int si = 0;
+    for (int64_t z = 0; z < n_planes; z += B, si ^= 1) {
+        const int nb = (int)std::min<int64_t>(B, n_planes - z);
+        b2s_plan::Slot &s = pl->slot[si];
+        int rc = drain(si);
+        if (rc) return rc;
+        const void *d_in;
+        if (in_is_device) {
+            d_in = (const char *)in + z * in_plane;
+        } else {
+            const void *src = (const char *)in + z * in_plane;
+            if (!in_pinned) { memcpy(s.h_in, src, in_plane * nb); src = s.h_in; }
+            CU(ctx, cudaMemcpyAsync(s.d_in, src, in_plane * nb, cudaMemcpyHostToDevice, s.stream));
+            d_in = s.d_in;
+        }
+        void *d_out = out_is_device ? (void *)((char *)out + z * out_plane) : s.d_out;
+        rc = enqueue_batch(pl, s, d_in, d_out, nb, s.stream);
+        if (rc) return rc;
+        if (!out_is_device) {
+            void *dst = out_pinned ? (void *)((char *)out + z * out_plane) : s.h_out;
+            CU(ctx, cudaMemcpyAsync(dst, s.d_out, out_plane * nb, cudaMemcpyDeviceToHost, s.stream));
+        }
+        CU(ctx, cudaEventRecord(s.done, s.stream));
+        pend[si] = {z, nb, true};
+    }
+    for (int k = 0; k < b2s_plan::kSlots; ++k) {
+        int rc = drain(k);
+        if (rc) return rc;
+    }
+    return B2S_OK;
+}
+
+int b2s_host_alloc(b2s_context *ctx, size_t bytes, void **ptr)
+{
+    if (!ctx || !ptr) return B2S_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMallocHost(ptr, bytes ? bytes : 16));
+    return B2S_OK;
+}
+
+int b2s_host_free(b2s_context *ctx, void *ptr)
+{
+    if (!ctx) return B2S_ERR_INVALID;
+    CU(ctx, cudaFreeHost(ptr));
+    return B2S_OK;
+}
+
+int b2s_timing_enable(b2s_context *ctx, int on)
+{
+    if (!ctx) return B2S_ERR_INVALID;
+    ctx->timing = on != 0;
+    return B2S_OK;
+}
+
+int b2s_timing_read(b2s_context *ctx, double *ms, int64_t *launches, int reset)
+{
+    if (!ctx) return B2S_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    for (auto &s : ctx->spans) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, s.a, s.b);
+        ctx->ms[s.cls] += t;
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    ctx->spans.clear();
+    for (int k = 0; k < B2S_N_KERNEL_CLASSES; ++k) {
+        if (ms) ms[k] = ctx->ms[k];
+        if (launches) launches[k] = ctx->n_launch[k];
+        if (reset) { ctx->ms[k] = 0; ctx->n_launch[k] = 0; }
+    }
+    return B2S_OK;
+}
+
+int b2s_debug_read(b2s_plan *pl, int what, int level, int plane, float *out, int32_t *rows, int32_t *cols)
+{
+    if (!pl || !out) return B2S_ERR_INVALID;
+    b2s_context *ctx = pl->ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    const Geometry &g = pl->g;
+    if (g.n_passes == 0) return fail(ctx, B2S_ERR_INVALID, "plan has no destripe workspace");
+    if (plane < 0 || plane >= pl->B) return fail(ctx, B2S_ERR_INVALID, "plane out of range");
+    int l = 0;
+    const float *base;
+    if (what == 0) base = pl->slot[0].padded;
+    else {
+        if (what < 1 || what > 4 || level < 1 || level > g.levels) return fail(ctx, B2S_ERR_INVALID, "bad sub-band / level");
+        l = level;
+        base = pl->slot[0].sub[l][what - 1];
+    }
+    const int r = g.my[l], c = g.mx[l];
+    CU(ctx, cudaMemcpy2D(out, sizeof(float) * c, base + (size_t)plane * pl->plane_stride[l], sizeof(float) * pl->pitch[l],
+                         sizeof(float) * c, r, cudaMemcpyDeviceToHost));
+    if (rows) *rows = r;
+    if (cols) *cols = c;
+    return B2S_OK;
+}
+
+int b2s_debug_math(b2s_context *ctx, int which, const float *in, float *out, int64_t n)
+{
+    if (!ctx || !in || !out || n < 0) return B2S_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    float *d_in = nullptr, *d_out = nullptr;
+    CU(ctx, cudaMalloc(&d_in, sizeof(float) * (n ? n : 1)));
+    CU(ctx, cudaMalloc(&d_out, sizeof(float) * (n ? n : 1)));
+    CU(ctx, cudaMemcpy(d_in, in, sizeof(float) * n, cudaMemcpyHostToDevice));
+    if (n) b2s_launch_math(which, d_in, d_out, n, 0);
+    ctx->launches += 1;
+    CU(ctx, cudaMemcpy(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return B2S_OK;
+}
+
+}  // extern "C"

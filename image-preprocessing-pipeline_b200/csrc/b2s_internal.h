@@ -1,0 +1,91 @@
+// Internal declarations shared by the kernel translation units and api.cu.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define B2S_MAX_TAPS 128
+#define B2S_MAX_LEVELS 32
+
+// Filter bank, float32 copies of the float64 tables (pywt casts its double tables to float for float32 data).
+struct B2sTaps {
+    int F;
+    float dec_lo[B2S_MAX_TAPS], dec_hi[B2S_MAX_TAPS], rec_lo[B2S_MAX_TAPS], rec_hi[B2S_MAX_TAPS];
+};
+
+// One 2-D float32 image per plane inside a batched workspace buffer.
+struct B2sImg {
+    float *ptr;           // plane 0
+    size_t plane_stride;  // floats between planes
+    int pitch;            // floats between rows (multiple of 4)
+    int rows, cols;       // logical size
+};
+
+// pointwise.cu ------------------------------------------------------------------------------------------------
+struct B2sPrologueArgs {
+    const void *in;        // u8/u16/f32 planes, contiguous (src_rows x src_cols)
+    int in_dtype;
+    int src_rows, src_cols;
+    const float *flat;     // optional (src_rows x src_cols)
+    int pad_mode, base_pad;
+    int use_log1p;
+    B2sImg out;            // padded image
+};
+void b2s_launch_prologue(const B2sPrologueArgs &a, int n_planes, cudaStream_t s);
+
+struct B2sEpilogueArgs {
+    B2sImg in;             // padded reconstruction (log domain when use_log1p); or unused when !destripe
+    const void *raw;       // when destripe is skipped: the (pre-processed) source image, raw_dtype
+    int raw_dtype;
+    int destripe;          // 1: take `in`, crop base_pad;   0: take `raw`
+    int base_pad;
+    int rows, cols;        // work image size (before rotation)
+    int use_log1p;
+    int int_path;          // 1: rint+clip to the integer work dtype right after expm1 (filter_streaks on integer input)
+    int work_dtype;        // dtype the reference's array has at this point when int_path (U8/U16)
+    double dark;
+    const float *ls_sub;   // optional lightsheet subtrahend (rows x cols, float) — already min(ls, bg*w)
+    int final_mode;        // 0: clip+trunc to out_dtype (integer d_type); 1: convert_to_16bit; 2: convert_to_8bit; 3: float32 out
+    int shift;
+    int out_dtype;
+    int flip, rot;         // rot in {0,1,2,3} quarter turns (numpy.rot90 k)
+    const int *uniform_flags; // optional per-plane flag: 1 => write zeros (process_img uniform shortcut)
+    void *out;
+    int out_rows, out_cols;
+};
+void b2s_launch_epilogue(const B2sEpilogueArgs &a, int n_planes, cudaStream_t s);
+
+// per-plane "all pixels equal" flags (process_img core.py:1232)
+void b2s_launch_uniform(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned *minmax_scratch,
+                        int *flags, cudaStream_t s);
+
+// pre-processing ahead of the destripe: flat division, 5x5 Gaussian, block reduce.  in/out dtype per stage.
+void b2s_launch_flat_divide(const void *in, int in_dtype, const float *flat, float *out, size_t plane_elems,
+                            int n_planes, cudaStream_t s);
+void b2s_launch_gauss5_u16(const uint16_t *in, uint16_t *out, int rows, int cols, int n_planes, cudaStream_t s);
+void b2s_launch_gauss5_f32(const float *in, float *out, int rows, int cols, int n_planes, cudaStream_t s);
+void b2s_launch_block_reduce(const void *in, int dtype, int rows, int cols, int by, int bx, int method, void *out,
+                             int out_dtype, int out_rows, int out_cols, int n_planes, cudaStream_t s);
+void b2s_launch_math(int which, const float *in, float *out, int64_t n, cudaStream_t s);
+
+// dwt.cu --------------------------------------------------------------------------------------------------------
+// forward level: in (ny x nx) -> cA,cH,cV,cD ((ny+F-1)/2 x (nx+F-1)/2); exact!=0 => reference summation order, no FMA
+void b2s_launch_dwt_fwd(const B2sTaps &t, const B2sImg &in, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV,
+                        const B2sImg &cD, int n_planes, int exact, cudaStream_t s);
+// inverse level: sub-bands (my x mx; cA is read with that logical size) -> out (first out.rows x out.cols of the
+// 2*my-F+2 x 2*mx-F+2 reconstruction)
+void b2s_launch_dwt_inv(const B2sTaps &t, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV, const B2sImg &cD,
+                        const B2sImg &out, int n_planes, int exact, cudaStream_t s);
+int b2s_dwt_max_smem(int F);
+
+// fft.cu --------------------------------------------------------------------------------------------------------
+struct B2sFftPlan {      // per transform length n
+    int n;
+    int n_factors;
+    int factors[32];
+    float2 *d_twiddle;   // n entries exp(-2 pi i k / n)
+};
+// rows x n image; transform along the contiguous axis when along_cols == 0, along the row index otherwise.
+// d_notch: n floats multiplying the packed (fftpack) spectrum; result overwrites the image.
+void b2s_launch_notch(const B2sFftPlan &fp, const float *d_notch, const B2sImg &img, int along_cols, int n_planes,
+                      int sm_count, cudaStream_t s);
+size_t b2s_notch_smem(int n);

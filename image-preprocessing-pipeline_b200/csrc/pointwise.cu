@@ -1,0 +1,313 @@
+// Element-wise / small-stencil stages around the wavelet-FFT destripe.  All arithmetic here is exact-by-construction
+// against the reference (integer work, single IEEE float32 operations, or the fdlibm mirrors in libm_mirror.h).
+//
+//   prologue : u8/u16/f32 plane [/ flat] -> log1p -> numpy.pad            (pystripe/core.py:1063-1110, 1248-1250)
+//   epilogue : crop -> expm1 -> rint/clip -> dark -> convert -> flip/rot  (core.py:1124-1158, 1324-1330, 1361-1379, 397-423)
+//   uniform  : per-plane "all pixels equal" flag                          (core.py:106-121, 1232-1246)
+//   pre-ops  : flat division, 5x5 Gaussian (cv2 fixed point), block reduce (core.py:1248-1300)
+#include "b2s_internal.h"
+#include "libm_mirror.h"
+#include "../../include/b200stripe.h"
+
+namespace {
+
+__device__ __forceinline__ int imod(int i, int p)
+{
+    int t = i % p;
+    return t < 0 ? t + p : t;
+}
+
+// numpy.pad source index for padded coordinate i (already shifted by -base_pad); -1 = constant fill
+__device__ __forceinline__ int pad_index(int i, int n, int mode)
+{
+    if (i >= 0 && i < n) return i;
+    switch (mode) {
+    case B2S_PAD_REFLECT: {
+        if (n == 1) return 0;
+        const int p = 2 * (n - 1);
+        const int t = imod(i, p);
+        return t < n ? t : p - t;
+    }
+    case B2S_PAD_SYMMETRIC: {
+        const int p = 2 * n;
+        const int t = imod(i, p);
+        return t < n ? t : p - 1 - t;
+    }
+    case B2S_PAD_WRAP: return imod(i, n);
+    case B2S_PAD_EDGE: return i < 0 ? 0 : n - 1;
+    default: return -1;
+    }
+}
+
+__device__ __forceinline__ float load_as_float(const void *p, int dtype, size_t idx)
+{
+    if (dtype == B2S_U16) return (float)__ldg(reinterpret_cast<const unsigned short *>(p) + idx);
+    if (dtype == B2S_U8) return (float)__ldg(reinterpret_cast<const unsigned char *>(p) + idx);
+    return __ldg(reinterpret_cast<const float *>(p) + idx);
+}
+
+__global__ void __launch_bounds__(256) k_prologue(B2sPrologueArgs a)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x4 >= a.out.pitch) return;
+    const size_t plane = blockIdx.z;
+    const size_t src_plane = plane * (size_t)a.src_rows * a.src_cols;
+    const int sy = pad_index(y - a.base_pad, a.src_rows, a.pad_mode);
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = x4 + k;
+        float r = 0.f;
+        if (x < a.out.cols) {
+            const int sx = pad_index(x - a.base_pad, a.src_cols, a.pad_mode);
+            if (sy >= 0 && sx >= 0) {
+                const size_t si = (size_t)sy * a.src_cols + sx;
+                r = load_as_float(a.in, a.in_dtype, src_plane + si);
+                if (a.flat) r = __fdiv_rn(r, __ldg(a.flat + si));
+                if (a.use_log1p) r = b2s_log1pf(r);
+            }
+        }
+        v[k] = r;
+    }
+    float *dst = a.out.ptr + plane * a.out.plane_stride + (size_t)y * a.out.pitch + x4;
+    *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+__global__ void __launch_bounds__(256) k_epilogue(B2sEpilogueArgs a)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;  // output column
+    const int i = blockIdx.y;                             // output row
+    if (j >= a.out_cols) return;
+    const size_t plane = blockIdx.z;
+    const size_t oidx = plane * (size_t)a.out_rows * a.out_cols + (size_t)i * a.out_cols + j;
+
+    double v = 0.0;
+    float vf = 0.f;
+    const bool zero_plane = a.uniform_flags && a.uniform_flags[plane];
+    if (!zero_plane) {
+        // output (i, j) -> work-image (y, x): undo rot90 then flipud
+        const int R = a.rows, C = a.cols;
+        int y, x;
+        switch (a.rot) {
+        case 1: y = j; x = C - 1 - i; break;
+        case 2: y = R - 1 - i; x = C - 1 - j; break;
+        case 3: y = R - 1 - j; x = i; break;
+        default: y = i; x = j; break;
+        }
+        if (a.flip) y = R - 1 - y;
+
+        bool is_int;  // does the reference hold an integer array at this point?
+        if (a.destripe) {
+            vf = a.in.ptr[plane * a.in.plane_stride + (size_t)(y + a.base_pad) * a.in.pitch + (x + a.base_pad)];
+            if (a.use_log1p) vf = b2s_expm1f(vf);
+            is_int = a.int_path != 0;
+            if (is_int) {  // rint (half to even) + clip to the integer dtype, core.py:1153-1158
+                vf = rintf(vf);
+                const float hi = a.work_dtype == B2S_U8 ? 255.f : 65535.f;
+                vf = fminf(fmaxf(vf, 0.f), hi);
+            }
+        } else {
+            vf = load_as_float(a.raw, a.raw_dtype, plane * (size_t)R * C + (size_t)y * C + x);
+            is_int = a.raw_dtype != B2S_F32;
+        }
+        if (a.dark > 0.0) {  // core.py:1324-1330
+            if (is_int) {
+                const double d = (double)vf;
+                v = d > a.dark ? d - a.dark : 0.0;
+            } else {
+                const float df = (float)a.dark;
+                vf = vf > df ? __fsub_rn(vf, df) : 0.f;
+                v = (double)vf;
+            }
+        } else {
+            v = (double)vf;
+        }
+    }
+    // final conversion, core.py:1361-1369
+    if (a.final_mode == 3) {
+        reinterpret_cast<float *>(a.out)[oidx] = (float)v;
+        return;
+    }
+    if (a.final_mode == 2) {  // convert_to_8bit_fun, core.py:402-423
+        double c = v < 0.0 ? 0.0 : (v > 65535.0 ? 65535.0 : v);
+        unsigned u = (unsigned)c;  // truncation
+        const unsigned lower = 1u << a.shift;
+        u = (u > 0 && u < lower) ? 1u : (u >> a.shift);
+        if (u > 255u) u = 255u;
+        reinterpret_cast<unsigned char *>(a.out)[oidx] = (unsigned char)u;
+        return;
+    }
+    const double hi = (a.out_dtype == B2S_U8) ? 255.0 : 65535.0;
+    double c = v < 0.0 ? 0.0 : (v > hi ? hi : v);
+    const unsigned u = (unsigned)c;
+    if (a.out_dtype == B2S_U8) reinterpret_cast<unsigned char *>(a.out)[oidx] = (unsigned char)u;
+    else reinterpret_cast<unsigned short *>(a.out)[oidx] = (unsigned short)u;
+}
+
+// ---- uniform flag: min/max per plane via shared reduction + global atomics on an ordered-uint key
+__device__ __forceinline__ unsigned f2key(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void k_minmax_init(unsigned *mm, int n_planes)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_planes) { mm[2 * i] = 0xffffffffu; mm[2 * i + 1] = 0u; }
+}
+
+__global__ void __launch_bounds__(256) k_minmax(const void *in, int dtype, size_t plane_elems, unsigned *mm)
+{
+    const size_t plane = blockIdx.y;
+    unsigned lo = 0xffffffffu, hi = 0u;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane_elems; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned k;
+        if (dtype == B2S_F32) k = f2key(__ldg(reinterpret_cast<const float *>(in) + plane * plane_elems + i));
+        else if (dtype == B2S_U16) k = __ldg(reinterpret_cast<const unsigned short *>(in) + plane * plane_elems + i);
+        else k = __ldg(reinterpret_cast<const unsigned char *>(in) + plane * plane_elems + i);
+        lo = min(lo, k);
+        hi = max(hi, k);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm + 2 * plane, lo);
+        atomicMax(mm + 2 * plane + 1, hi);
+    }
+}
+
+__global__ void k_uniform_flags(const unsigned *mm, int *flags, int n_planes)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_planes) flags[i] = mm[2 * i] == mm[2 * i + 1];
+}
+
+// ---- pre-ops
+__global__ void __launch_bounds__(256) k_flat_divide(const void *in, int dtype, const float *flat, float *out,
+                                                     size_t plane_elems)
+{
+    const size_t plane = blockIdx.y;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane_elems; i += (size_t)gridDim.x * blockDim.x)
+        out[plane * plane_elems + i] = __fdiv_rn(load_as_float(in, dtype, plane * plane_elems + i), __ldg(flat + i));
+}
+
+__device__ __forceinline__ int reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    const int p = 2 * (n - 1);
+    const int t = imod(i, p);
+    return t < n ? t : p - t;
+}
+
+// cv2.GaussianBlur(u16, (5,5), 1, 1): fixed point. Q16 taps {3571,16004,26386,16004,3571}; the horizontal pass is
+// exact in 16.16, the vertical pass in 16.32, then round half up and saturate.
+__global__ void __launch_bounds__(256) k_gauss5_u16(const uint16_t *in, uint16_t *out, int rows, int cols)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= cols) return;
+    const size_t plane = (size_t)blockIdx.z * rows * cols;
+    const unsigned kq[5] = {3571u, 16004u, 26386u, 16004u, 3571u};
+    unsigned long long acc = 0ull;
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy) {
+        const int yy = reflect101(y + dy, rows);
+        const uint16_t *row = in + plane + (size_t)yy * cols;
+        unsigned h = 0u;
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) h += kq[dx + 2] * (unsigned)__ldg(row + reflect101(x + dx, cols));
+        acc += (unsigned long long)kq[dy + 2] * h;
+    }
+    unsigned long long r = (acc + (1ull << 31)) >> 32;
+    out[plane + (size_t)y * cols + x] = (uint16_t)(r > 65535ull ? 65535ull : r);
+}
+
+// skimage.measure.block_reduce with cval=0 padding of the trailing edges.  max/min keep the dtype; mean of an
+// integer image is the float64 mean cast to float32 (what log1p_jit's astype(float32) makes of it).
+__global__ void __launch_bounds__(256) k_block_reduce(const void *in, int dtype, int rows, int cols, int by, int bx,
+                                                      int method, void *out, int out_dtype, int out_rows, int out_cols)
+{
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy = blockIdx.y;
+    if (ox >= out_cols) return;
+    const size_t ip = (size_t)blockIdx.z * rows * cols, op = (size_t)blockIdx.z * out_rows * out_cols;
+    float best = 0.f;
+    double sum = 0.0;
+    bool first = true;
+    for (int dy = 0; dy < by; ++dy) {
+        const int y = oy * by + dy;
+        for (int dx = 0; dx < bx; ++dx) {
+            const int x = ox * bx + dx;
+            const float v = (y < rows && x < cols) ? load_as_float(in, dtype, ip + (size_t)y * cols + x) : 0.f;
+            if (first) { best = v; first = false; }
+            else if (method == B2S_DS_MAX) best = fmaxf(best, v);
+            else if (method == B2S_DS_MIN) best = fminf(best, v);
+            sum += (double)v;
+        }
+    }
+    const float r = (method == B2S_DS_MEAN) ? (float)(sum / (double)(by * bx)) : best;
+    const size_t o = op + (size_t)oy * out_cols + ox;
+    if (out_dtype == B2S_F32) reinterpret_cast<float *>(out)[o] = r;
+    else if (out_dtype == B2S_U16) reinterpret_cast<unsigned short *>(out)[o] = (unsigned short)r;
+    else reinterpret_cast<unsigned char *>(out)[o] = (unsigned char)r;
+}
+
+__global__ void k_math(int which, const float *in, float *out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = which == 0 ? b2s_log1pf(in[i]) : b2s_expm1f(in[i]);
+}
+
+}  // namespace
+
+void b2s_launch_prologue(const B2sPrologueArgs &a, int n_planes, cudaStream_t s)
+{
+    dim3 grid((a.out.pitch / 4 + 255) / 256, a.out.rows, n_planes);
+    k_prologue<<<grid, 256, 0, s>>>(a);
+}
+
+void b2s_launch_epilogue(const B2sEpilogueArgs &a, int n_planes, cudaStream_t s)
+{
+    dim3 grid((a.out_cols + 255) / 256, a.out_rows, n_planes);
+    k_epilogue<<<grid, 256, 0, s>>>(a);
+}
+
+void b2s_launch_uniform(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned *mm, int *flags,
+                        cudaStream_t s)
+{
+    k_minmax_init<<<(n_planes + 127) / 128, 128, 0, s>>>(mm, n_planes);
+    int bx = (int)((plane_elems + 256 * 8 - 1) / (256 * 8));
+    if (bx > 1024) bx = 1024;
+    if (bx < 1) bx = 1;
+    k_minmax<<<dim3(bx, n_planes), 256, 0, s>>>(in, dtype, plane_elems, mm);
+    k_uniform_flags<<<(n_planes + 127) / 128, 128, 0, s>>>(mm, flags, n_planes);
+}
+
+void b2s_launch_flat_divide(const void *in, int in_dtype, const float *flat, float *out, size_t plane_elems,
+                            int n_planes, cudaStream_t s)
+{
+    int bx = (int)((plane_elems + 256 * 4 - 1) / (256 * 4));
+    if (bx > 4096) bx = 4096;
+    k_flat_divide<<<dim3(bx, n_planes), 256, 0, s>>>(in, in_dtype, flat, out, plane_elems);
+}
+
+void b2s_launch_gauss5_u16(const uint16_t *in, uint16_t *out, int rows, int cols, int n_planes, cudaStream_t s)
+{
+    k_gauss5_u16<<<dim3((cols + 255) / 256, rows, n_planes), 256, 0, s>>>(in, out, rows, cols);
+}
+
+void b2s_launch_block_reduce(const void *in, int dtype, int rows, int cols, int by, int bx, int method, void *out,
+                             int out_dtype, int out_rows, int out_cols, int n_planes, cudaStream_t s)
+{
+    k_block_reduce<<<dim3((out_cols + 255) / 256, out_rows, n_planes), 256, 0, s>>>(in, dtype, rows, cols, by, bx, method,
+                                                                                   out, out_dtype, out_rows, out_cols);
+}
+
+void b2s_launch_math(int which, const float *in, float *out, int64_t n, cudaStream_t s)
+{
+    k_math<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(which, in, out, n);
+}

@@ -1,0 +1,999 @@
+"""pystripe.core — drop-in module surface of the reference's pystripe/core.py, backed by libb200stripe.so (sm_100a).
+
+Same names, keyword arguments, defaults and error behaviour as the reference for the per-plane destripe /
+enhancement path (reference lines cited per function, paths relative to the reference root).  The arithmetic runs
+on the GPU through the C ABI in include/b200stripe.h; there is no CPU fallback — without the library or without
+a B200 the calls raise.  Small host-side helpers that other reference scripts import from this module
+(process_images.py:37-40, parallel_image_processor.py:29-30, convert.py:18-19) are provided as plain numpy.
+
+Extensions over the reference (additive): `filter_streaks` / `process_img` also accept (Z, H, W) stacks and CUDA
+torch tensors (zero-copy, current stream); `process_stack` is the batched entry point batch_filter itself uses.
+"""
+import os
+import re
+import sys
+import threading
+from concurrent.futures import ThreadPoolExecutor
+from math import ceil, exp, log, sqrt
+from multiprocessing import Process, Queue
+from pathlib import Path
+from queue import Empty
+from time import sleep, time
+from typing import Callable, Iterator, List, Tuple, Union
+
+import numpy as np
+from numpy import max as np_max, mean as np_mean, median as np_median, min as np_min
+from numpy import ndarray, float32, uint8, uint16, zeros
+
+from . import _native
+from ._util import PrintColors, date_time_now
+from ._wavelet_tables import DEC_LO
+from .lightsheet_correct import correct_lightsheet, prctl  # noqa: F401  (re-exported, process_images.py:39)
+from .raw import raw_imread
+
+try:  # the reference imports these from torch.cuda (core.py:55-58); keep the names importable
+    from torch.cuda import device_count as cuda_device_count
+    from torch.cuda import get_device_properties as cuda_get_device_properties
+    from torch.cuda import is_available as cuda_is_available_for_pt
+except Exception:  # pragma: no cover
+    def cuda_device_count():
+        return 0
+
+    def cuda_get_device_properties(i):
+        raise RuntimeError("torch is not available")
+
+    def cuda_is_available_for_pt():
+        return False
+
+SUPPORTED_EXTENSIONS = ('.png', '.tif', '.tiff', '.raw', '.dcimg')
+NUM_RETRIES: int = 40
+USE_NUMEXPR: bool = False       # kept for callers that read the flag (process_images.py:40)
+USE_PYTORCH = False             # reference value on Linux (core.py:85-91); the GPU path here is not torch
+USE_JAX = False
+CUDA_IS_AVAILABLE_FOR_PT = False
+REFERENCE_QUIRKS = False        # True: reproduce as-written behaviour (Gaussian discarded, uint16 /= flat TypeError)
+MAX_BATCH = int(os.environ.get("B200STRIPE_MAX_BATCH", "8"))
+EXACT = os.environ.get("B200STRIPE_EXACT", "1") != "0"
+
+
+# --------------------------------------------------------------------------------------------------------------
+# host helpers imported by other reference scripts
+# --------------------------------------------------------------------------------------------------------------
+def is_uniform_1d(arr: ndarray):
+    """core.py:94-103."""
+    if len(arr) <= 0:
+        return None
+    return bool((arr == arr[0]).all())
+
+
+def is_uniform_2d(arr: ndarray):
+    """core.py:106-121."""
+    if len(arr) <= 0:
+        return None
+    return bool((arr == arr[0, 0]).all())
+
+
+def is_uniform_3d(arr: ndarray):
+    """core.py:124-139."""
+    if len(arr) <= 0:
+        return None
+    return bool((arr == arr[0, 0, 0]).all())
+
+
+def min_max_1d(arr: ndarray):
+    """core.py:142-164."""
+    if len(arr) <= 0:
+        return None, None
+    return arr.min(), arr.max()
+
+
+def min_max_2d(arr: ndarray):
+    """core.py:167-177."""
+    if len(arr) <= 0:
+        return None, None
+    return arr.min(), arr.max()
+
+
+def expm1_jit(img, dtype=float32):
+    """core.py:180-187 (host helper; the hot path evaluates expm1 on the GPU)."""
+    return np.expm1(img).astype(dtype)
+
+
+def log1p_jit(img, dtype=float32):
+    """core.py:190-197 (host helper; the hot path evaluates log1p on the GPU)."""
+    return np.log1p(img, dtype=dtype)
+
+
+def convert_to_16bit_fun(img: ndarray):
+    """core.py:397-399."""
+    np.clip(img, 0, 65535, out=img)
+    return img.astype(uint16)
+
+
+def convert_to_8bit_fun(img: ndarray, bit_shift_to_right: int = 8):
+    """core.py:402-423 (host helper for callers; process_img does this on the GPU)."""
+    if img is None or img.dtype in ('uint8', uint8):
+        return img
+    elif img.dtype not in ('uint16', uint16):
+        img = convert_to_16bit_fun(img)
+    if bit_shift_to_right is None:
+        bit_shift_to_right = 8
+    if 0 <= bit_shift_to_right < 9:
+        lower_bound = 2 ** bit_shift_to_right
+        img = np.where((0 < img) & (img < lower_bound), 1, img >> bit_shift_to_right)
+    else:
+        print("right shift should be between 0 and 8")
+        raise RuntimeError
+    np.clip(img, 0, 255, out=img)
+    return img.astype(uint8)
+
+
+def np_notch(length: int, sigma: float) -> ndarray:
+    """core.py:637-667."""
+    if length <= 0:
+        raise ValueError('np_notch: length must be positive')
+    if sigma <= 0:
+        raise ValueError('np_notch: sigma must be positive')
+    g = np.arange(length, dtype=float32)
+    g **= 2
+    g /= -float32(2) * sigma ** 2
+    return float32(1) - np.exp(g)
+
+
+def notch_rise_point(sigma, rise: float):
+    """core.py:670-678."""
+    return int(sqrt(-2 * sigma ** 2 * log(1 - rise)) + .5) // 2 * 2
+
+
+def calculate_pad_size(shape: tuple, sigma, rise: float = 0.5):
+    """core.py:681-698 (the same rule is evaluated inside the library for the plan geometry)."""
+    if sigma == 0:
+        return 0
+    x = shape[1] + 1
+    y = shape[0] + 1
+    c = 5e14
+    sqrt_xyc = sqrt(x ** 2 - 2 * x * y + y ** 2 + 4 * c)
+    rise = min(round(1 - exp((x + y - sqrt_xyc) / (4 * sigma ** 2)), 2) - 0.01, rise)
+    return notch_rise_point(sigma, rise)
+
+
+def np_gaussian_filter(shape: tuple, sigma: float, axis: int) -> ndarray:
+    """core.py:701-722."""
+    g = np_notch(length=shape[axis], sigma=sigma)
+    if axis == -2:
+        g = np.reshape(g, (shape[axis], 1))
+    return np.broadcast_to(g, shape)
+
+
+def max_level(min_len, wavelet):
+    """core.py:466-472: pywt.dwt_max_level(min_len, Wavelet(wavelet).dec_len)."""
+    f = len(_dec_lo(wavelet))
+    if f <= 1 or min_len < f - 1:
+        return 0
+    return int(min_len // (f - 1)).bit_length() - 1
+
+
+def calculate_down_sampled_size(tile_size, down_sample):
+    """core.py:1162-1170."""
+    if isinstance(down_sample, (int, float)):
+        tile_size = [ceil(size / down_sample) for size in tile_size]
+    elif isinstance(down_sample, (tuple, list)):
+        tile_size = list(tile_size)
+        for idx, factor in enumerate(down_sample):
+            if factor is not None:
+                tile_size[idx] = ceil(tile_size[idx] / factor)
+    return tile_size
+
+
+def normalize_flat(flat):
+    """core.py:2047-2049."""
+    flat_float = flat.astype(float32)
+    return flat_float / flat_float.max()
+
+
+def _unsupported(name):
+    def f(*a, **k):
+        raise NotImplementedError(f"{name} is outside the B200 hot path (SURVEY.md §2: never enabled by a caller)")
+    f.__name__ = name
+    return f
+
+
+hist_match = _unsupported("hist_match")                    # core.py:426
+get_img_mask = _unsupported("get_img_mask")                # core.py:475
+correct_bleaching = _unsupported("correct_bleaching")      # core.py:501
+otsu_threshold = _unsupported("otsu_threshold")            # core.py:562
+foreground_fraction = _unsupported("foreground_fraction")  # core.py:586
+
+
+# --------------------------------------------------------------------------------------------------------------
+# plan cache
+# --------------------------------------------------------------------------------------------------------------
+def _dec_lo(wavelet):
+    if hasattr(wavelet, "dec_lo"):
+        return tuple(float(v) for v in wavelet.dec_lo)
+    name = str(wavelet)
+    if name not in DEC_LO:
+        raise ValueError(f"Unknown wavelet name '{name}', check wavelist() for the list of available builtin wavelets.")
+    return DEC_LO[name]
+
+
+def wavelist():
+    return sorted(DEC_LO)
+
+
+_PAD_ALL = ('constant', 'edge', 'linear_ramp', 'maximum', 'mean', 'median', 'minimum', 'reflect', 'symmetric',
+            'wrap', 'empty')
+_plans = {}
+_plans_lock = threading.Lock()
+
+
+_tls = threading.local()
+
+
+class use_device:
+    """`with use_device(i):` — GPU used for host (numpy) inputs on this thread."""
+
+    def __init__(self, device: int):
+        self.device = int(device)
+
+    def __enter__(self):
+        self.prev = getattr(_tls, "device", None)
+        _tls.device = self.device
+        return self
+
+    def __exit__(self, *exc):
+        _tls.device = self.prev
+
+
+def _device_of(x) -> int:
+    if _native._is_torch(x):
+        if not x.is_cuda:
+            raise TypeError("torch tensors must live on a CUDA device (pass numpy arrays for host data)")
+        return x.device.index or 0
+    dev = getattr(_tls, "device", None)
+    if dev is not None:
+        return dev
+    return int(os.environ.get("B200STRIPE_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, threshold, padding_mode, bidirectional,
+              log1p, flat=None, gaussian=False, down_sample=None, down_sample_method='max', dark=0, lightsheet=False,
+              artifact_length=150, background_window_size=200, percentile=0.25, lightsheet_vs_background=2.0,
+              convert_to_16bit=False, convert_to_8bit=False, bit_shift_to_right=8, rotate=0, flip=False,
+              out_code=None, max_batch=None, stop_after=0, exact=None):
+    if not isinstance(sigma, (tuple, list)):
+        sigma = (sigma,) * 2
+    s1, s2 = float(sigma[0]), float(sigma[1])
+    destripe = not (s1 == 0 and s2 == 0)
+    mode = padding_mode.lower() if isinstance(padding_mode, str) else padding_mode
+    if destripe:
+        if mode not in _PAD_ALL:                                     # core.py:1088-1099
+            print(f"{PrintColors.FAIL}Unsupported padding mode: {padding_mode}{PrintColors.ENDC}")
+            raise RuntimeError(f"Unsupported padding mode: {padding_mode}")
+        if mode not in _native.PAD_MODES:
+            raise NotImplementedError(f"padding_mode='{mode}' is not implemented on the GPU path "
+                                      f"(available: {sorted(_native.PAD_MODES)})")
+    ds = None
+    if down_sample is not None:
+        if isinstance(down_sample, (int, float)):
+            down_sample = (down_sample, down_sample)
+        ds = tuple(1 if d is None else int(d) for d in down_sample)
+        if ds == (1, 1):
+            ds = None
+    method = str(down_sample_method).lower()
+    if ds is not None and method not in _native.DS_METHODS:          # core.py:1288-1298
+        print(f"{PrintColors.FAIL}unsupported down-sampling method: {down_sample_method}{PrintColors.ENDC}")
+        raise RuntimeError(f"unsupported down-sampling method: {down_sample_method}")
+    taps = _dec_lo(wavelet) if destripe else None
+    flat_key = None
+    if flat is not None:
+        flat_key = (id(flat), tuple(flat.shape))
+    key = (device, tuple(shape), in_code, process, s1, s2, int(level), taps, mode if destripe else None,
+           bool(bidirectional), bool(log1p), threshold is not None and threshold <= 0, flat_key, bool(gaussian), ds,
+           method, float(dark or 0), bool(lightsheet), artifact_length, background_window_size, percentile,
+           lightsheet_vs_background, bool(convert_to_16bit), bool(convert_to_8bit), bit_shift_to_right, rotate,
+           bool(flip), out_code, max_batch, stop_after, exact, REFERENCE_QUIRKS)
+    with _plans_lock:
+        plan = _plans.get(key)
+        if plan is not None:
+            return plan
+        p = _native.default_params()
+        p.height, p.width = int(shape[0]), int(shape[1])
+        p.in_dtype = in_code
+        p.out_dtype = in_code if out_code is None else out_code
+        p.sigma1, p.sigma2 = s1, s2
+        p.threshold_nonpositive = int(threshold is not None and threshold <= 0)
+        p.level = int(level)
+        p.pad_mode = _native.PAD_MODES.get(mode, 0) if destripe else 0
+        p.bidirectional = int(bool(bidirectional))
+        p.log1p = int(bool(log1p))
+        p.process_img = int(process)
+        p.has_flat = int(flat is not None)
+        p.gaussian = int(bool(gaussian))
+        if ds is not None:
+            p.down_sample_y, p.down_sample_x = ds
+            p.down_sample_method = _native.DS_METHODS[method]
+        p.dark = float(dark or 0)
+        p.lightsheet = int(bool(lightsheet))
+        p.artifact_length = int(artifact_length)
+        p.background_window_size = int(background_window_size)
+        p.percentile = float(percentile)
+        p.lightsheet_vs_background = float(lightsheet_vs_background)
+        p.convert_to_16bit = int(bool(convert_to_16bit))
+        p.convert_to_8bit = int(bool(convert_to_8bit))
+        p.bit_shift_to_right = 8 if bit_shift_to_right is None else int(bit_shift_to_right)
+        p.rotate = int(rotate or 0)
+        p.flip_upside_down = int(bool(flip))
+        p.reference_quirks = int(REFERENCE_QUIRKS)
+        p.max_batch = int(max_batch or MAX_BATCH)
+        p.debug_stop_after = int(stop_after)
+        p.exact = int(EXACT if exact is None else exact)
+        plan = _native.Plan(_native.context(device), p, dec_lo=taps, flat=flat)
+        plan._flat_ref = flat  # keep id(flat) stable while the plan is cached
+        if len(_plans) > 16:   # plans own GPU workspace: keep the cache small
+            _, old = _plans.popitem()
+            old.close()
+        _plans[key] = plan
+        return plan
+
+
+def clear_plan_cache():
+    with _plans_lock:
+        for pl in _plans.values():
+            pl.close()
+        _plans.clear()
+
+
+def _run(plan, img):
+    if _native._is_torch(img):
+        return plan.run_torch(img)
+    return plan.run_host(img)
+
+
+def _as_supported(img):
+    """(array for the GPU, restore-dtype or None)."""
+    if _native._is_torch(img):
+        import torch
+        if img.dtype in (torch.uint8, torch.uint16, torch.float32):
+            return img, None
+        if img.dtype == torch.float64:
+            return img.float(), torch.float64
+        raise TypeError(f"unsupported tensor dtype {img.dtype}")
+    img = np.asarray(img)
+    if img.dtype in (np.uint8, np.uint16, np.float32):
+        return img, None
+    if img.dtype == np.float64:
+        return img.astype(np.float32), np.float64
+    raise TypeError(f"unsupported dtype {img.dtype}: the GPU path takes uint8, uint16, float32 or float64 planes")
+
+
+def _code_of(img):
+    if _native._is_torch(img):
+        import torch
+        return {torch.uint8: _native.U8, torch.uint16: _native.U16, torch.float32: _native.F32}[img.dtype]
+    return _native.np_dtype_code(img.dtype)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# filter_streaks  (core.py:982-1159)
+# --------------------------------------------------------------------------------------------------------------
+def filter_streaks(
+        img,
+        sigma: Tuple[int, int] = (250, 250),
+        level: int = 0,
+        wavelet: str = 'db9',
+        crossover: float = 10,
+        threshold: float = None,
+        padding_mode: str = "wrap",
+        bidirectional: bool = False,
+        gpu_semaphore: Queue = None,
+        bleach_correction_frequency: float = None,
+        bleach_correction_max_method: bool = False,
+        bleach_correction_clip_min: Union[float, int] = None,
+        bleach_correction_clip_med: Union[float, int] = None,
+        bleach_correction_clip_max: Union[float, int] = None,
+        log1p_normalization_needed: bool = True,
+        enable_masking: bool = False,
+        close_steps: int = 50,
+        open_steps: int = 500,
+        verbose: bool = False
+):
+    """Filter horizontal streaks with the wavelet-FFT notch (reference core.py:982-1159) on the GPU.
+
+    img: (H, W) or (Z, H, W); numpy array (host round trip) or CUDA torch tensor (zero-copy, current stream).
+    `gpu_semaphore`, `crossover` are accepted and ignored (the thresholded dual-band variant is unreachable in the
+    reference, core.py:1113-1117).  Bleach correction / masking are outside the hot path: NotImplementedError.
+    """
+    if not isinstance(sigma, (tuple, list)):
+        sigma = (sigma,) * 2
+    if sigma[0] == sigma[1] == 0 and bleach_correction_frequency is None:
+        return img                                                      # core.py:1058-1059
+    if bleach_correction_frequency is not None or enable_masking:
+        raise NotImplementedError("bleach correction / masking are not part of the GPU hot path (SURVEY.md §8f N3)")
+    arr, restore = _as_supported(img)
+    plan = _get_plan(_device_of(arr), arr.shape[-2:], _code_of(arr), process=0, sigma=sigma, level=level,
+                     wavelet=wavelet, threshold=threshold, padding_mode=padding_mode, bidirectional=bidirectional,
+                     log1p=log1p_normalization_needed)
+    out = _run(plan, arr)
+    if verbose:
+        print(f"de-striping applied: sigma={sigma}, level={level}, wavelet={wavelet}, crossover={crossover}, "
+              f"threshold={threshold}, bidirectional={bidirectional}.")
+    if restore is not None:
+        out = out.to(restore) if _native._is_torch(out) else out.astype(restore)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# process_img  (core.py:1190-1381)
+# --------------------------------------------------------------------------------------------------------------
+def process_img(
+        img,
+        flat: ndarray = None,
+        gaussian_filter_2d: bool = False,
+        down_sample: Tuple[int, int] = None,
+        down_sample_method: str = 'max',
+        tile_size: Tuple[int, int] = None,
+        new_size: Tuple[int, int] = None,
+        exclude_dark_edges_set_them_to_zero: bool = False,
+        sigma: Tuple[int, int] = (0, 0),
+        level: int = 0,
+        wavelet: str = 'coif15',
+        crossover: float = 10,
+        threshold: float = None,
+        padding_mode: str = "wrap",
+        bidirectional: bool = False,
+        gpu_semaphore: Queue = None,
+        bleach_correction_frequency: float = None,
+        bleach_correction_clip_min: Union[float, int] = None,
+        bleach_correction_clip_med: Union[float, int] = None,
+        bleach_correction_clip_max: Union[float, int] = None,
+        bleach_correction_max_method: bool = False,
+        log1p_normalization_needed: bool = True,
+        dark: float = 0,
+        lightsheet: bool = False,
+        artifact_length: int = 150,
+        background_window_size: int = 200,
+        percentile: float = 0.25,
+        lightsheet_vs_background: float = 2.0,
+        rotate: int = 0,
+        flip_upside_down: bool = False,
+        convert_to_16bit: bool = False,
+        convert_to_8bit: bool = False,
+        bit_shift_to_right: int = 8,
+        d_type: str = None,
+        verbose: bool = False,
+        _max_batch: int = None,
+):
+    """Per-plane enhancement in the reference's order of operations (core.py:1190-1381), fused on the GPU:
+    uniform-plane shortcut -> flat -> 5x5 Gaussian -> block down-sample -> filter_streaks -> dark -> lightsheet ->
+    8/16-bit conversion -> flip -> rot90.   img: (H, W) or (Z, H, W), numpy or CUDA torch tensor."""
+    if bleach_correction_frequency is not None or exclude_dark_edges_set_them_to_zero:
+        raise NotImplementedError("bleach correction / dark-edge exclusion are outside the GPU hot path")
+    if new_size is not None:
+        raise NotImplementedError("new_size (skimage.transform.resize) is a 'next' row (SURVEY.md §8f N3)")
+    if not isinstance(sigma, (tuple, list)):
+        sigma = (sigma,) * 2
+    arr, restore = _as_supported(img)
+    shape = tuple(arr.shape[-2:])
+    if tile_size is None:
+        tile_size = shape
+    if d_type is None:
+        d_type = np.float64 if restore is not None else (
+            _native.CODE_TO_NP[_code_of(arr)])
+    d_type = np.dtype(d_type)
+    if d_type.kind in "ui":
+        if d_type not in (np.uint8, np.uint16):
+            raise TypeError(f"d_type {d_type} is not supported on the GPU path (uint8 / uint16 / float)")
+        out_code = _native.np_dtype_code(d_type)
+    else:
+        out_code = _native.F32
+    if flat is not None:
+        if tuple(tile_size) != tuple(flat.shape):                       # core.py:1248-1254
+            print(f"{PrintColors.WARNING}warning: image and flat arrays had different shapes{PrintColors.ENDC}")
+            flat = None
+        elif REFERENCE_QUIRKS and _code_of(arr) != _native.F32:
+            raise TypeError("Cannot cast ufunc 'divide' output from dtype('float32') to dtype('uint16') "
+                            "(reference core.py:1250 as written)")
+    if not tuple(sigma) > (0, 0):                                       # core.py:1302
+        sigma = (0, 0)
+    plan = _get_plan(_device_of(arr), shape, _code_of(arr), process=1, sigma=sigma, level=level, wavelet=wavelet,
+                     threshold=threshold, padding_mode=padding_mode, bidirectional=bidirectional,
+                     log1p=log1p_normalization_needed, flat=flat, gaussian=gaussian_filter_2d, down_sample=down_sample,
+                     down_sample_method=down_sample_method, dark=dark, lightsheet=lightsheet,
+                     artifact_length=artifact_length, background_window_size=background_window_size,
+                     percentile=percentile, lightsheet_vs_background=lightsheet_vs_background,
+                     convert_to_16bit=convert_to_16bit, convert_to_8bit=convert_to_8bit,
+                     bit_shift_to_right=bit_shift_to_right, rotate=rotate, flip=flip_upside_down, out_code=out_code,
+                     max_batch=_max_batch)
+    out = _run(plan, arr)
+    if out_code == _native.F32 and plan.info.out_dtype == _native.F32 and d_type != np.float32:
+        out = out.astype(d_type) if not _native._is_torch(out) else out.double()
+    return out
+
+
+def process_stack(stack, **kwargs):
+    """Batched process_img over a (Z, H, W) stack — the call batch_filter makes per group of decoded files."""
+    return process_img(stack, **kwargs)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# file I/O (boundary only — SURVEY.md §8f N2).  tifffile is used when present, else Pillow / OpenCV.
+# --------------------------------------------------------------------------------------------------------------
+def imread_tif_raw_png(path: Path, dtype: str = None, shape: Tuple[int, int] = None):
+    """core.py:200-264: retries, returns None when the file cannot be decoded."""
+    path = Path(path)
+    extension = path.suffix.lower()
+    img = None
+    attempt = 0
+    for attempt in range(NUM_RETRIES):
+        try:
+            if extension == '.raw':
+                img = raw_imread(path, dtype=dtype, shape=shape)
+            elif extension in ('.png', '.tif', '.tiff'):
+                img = _decode_image(path)
+            else:
+                print(f"{PrintColors.WARNING}Unsupported file format: {extension}{PrintColors.ENDC}")
+        except (OSError, TypeError, PermissionError, ValueError) as e:
+            print(f"[Attempt {attempt + 1}]: file: {path.name} Read error: {type(e).__name__} - {e}")
+            sleep(0.1)
+            continue
+        if img is not None:
+            break
+    if img is None:
+        print(f"{PrintColors.FAIL}Failed to load image after {attempt + 1} attempts:\n{path.name}{PrintColors.ENDC}")
+    return img
+
+
+def _decode_image(path: Path):
+    try:
+        import tifffile
+        if path.suffix.lower() in ('.tif', '.tiff'):
+            return tifffile.imread(path)
+    except ImportError:
+        pass
+    from PIL import Image
+    Image.MAX_IMAGE_PIXELS = None
+    with Image.open(path) as im:
+        im.load()
+        return np.array(im)
+
+
+def imsave_tif(path: Path, img: ndarray, compression: Union[Tuple[str, int], None] = ('ADOBE_DEFLATE', 1)) -> bool:
+    """core.py:276-334: returns True only when the user interrupted (caller dies with dignity)."""
+    path = Path(path)
+    for attempt in range(1, NUM_RETRIES):
+        try:
+            tmp_path = path.with_suffix(".tif")
+            _encode_tif(tmp_path, img, compression)
+            os.chmod(tmp_path, 0o666 if os.name == 'nt' else 0o777)
+            if tmp_path != path:
+                tmp_path.rename(path)
+            return False
+        except KeyboardInterrupt:
+            print(f"{PrintColors.WARNING}\ndying from imsave_tif{PrintColors.ENDC}")
+            _encode_tif(path, img, compression)
+            return True
+        except (OSError, TypeError, PermissionError) as inst:
+            if attempt == NUM_RETRIES - 1:
+                print(f"After {NUM_RETRIES} attempts failed to save the file:\n{path}\n\n{type(inst)}\n{inst.args}\n{inst}\n")
+                return False
+            sleep(0.1)
+    return False
+
+
+_PIL_COMPRESSION = {'ADOBE_DEFLATE': 'tiff_adobe_deflate', 'DEFLATE': 'tiff_deflate', 'LZW': 'tiff_lzw',
+                    'ZSTD': 'zstd', 'NONE': None}
+
+
+def _encode_tif(path: Path, img: ndarray, compression):
+    try:
+        import tifffile
+        tifffile.imwrite(path, data=img, compression=compression)
+        return
+    except ImportError:
+        pass
+    from PIL import Image
+    method = None
+    if compression:
+        name = compression[0] if isinstance(compression, (tuple, list)) else compression
+        method = _PIL_COMPRESSION.get(str(name).upper(), 'tiff_adobe_deflate')
+    im = Image.fromarray(np.ascontiguousarray(img))
+    if method:
+        im.save(path, format="TIFF", compression=method)
+    else:
+        im.save(path, format="TIFF")
+
+
+def imread_dcimg(path: Path, z: int):
+    """core.py:337-355."""
+    from dcimg import DCIMGFile
+    with DCIMGFile(path) as arr:
+        return arr[z]
+
+
+def check_dcimg_shape(path: Path):
+    from dcimg import DCIMGFile
+    with DCIMGFile(path) as arr:
+        return arr.shape
+
+
+def check_dcimg_start(path: Path):
+    return int(Path(path).name.split('.')[0])
+
+
+def glob_re(pattern: str, path: Path) -> Iterator[Path]:
+    """core.py:1603-1617: recursive case-insensitive regex search on file names."""
+    regexp = re.compile(pattern, re.IGNORECASE)
+    for p in os.scandir(path):
+        if p.is_file() and regexp.search(p.name):
+            yield Path(p.path)
+        elif p.is_dir(follow_symlinks=False):
+            yield from glob_re(pattern, Path(p.path))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# read_filter_save  (core.py:1384-1600)
+# --------------------------------------------------------------------------------------------------------------
+_PROCESS_KEYS = ('flat', 'gaussian_filter_2d', 'sigma', 'level', 'wavelet', 'crossover', 'threshold', 'padding_mode',
+                 'bidirectional', 'bleach_correction_frequency', 'bleach_correction_max_method',
+                 'bleach_correction_clip_min', 'bleach_correction_clip_med', 'bleach_correction_clip_max', 'dark',
+                 'lightsheet', 'artifact_length', 'background_window_size', 'percentile', 'lightsheet_vs_background',
+                 'convert_to_16bit', 'convert_to_8bit', 'bit_shift_to_right', 'down_sample', 'down_sample_method',
+                 'new_size', 'rotate', 'flip_upside_down')
+
+
+def read_filter_save(
+        input_file: Path = None,
+        output_file: Path = None,
+        z_idx: int = None,
+        continue_process: bool = False,
+        d_type: str = None,
+        tile_size: Tuple[int, int] = None,
+        print_input_file_names: bool = False,
+        compression: Tuple[str, int] = ('ADOBE_DEFLATE', 1),
+        flat: ndarray = None,
+        gaussian_filter_2d: bool = False,
+        sigma: Tuple[int, int] = (0, 0),
+        level: int = 0,
+        wavelet: str = 'coif15',
+        crossover: float = 10,
+        threshold: float = None,
+        padding_mode: str = "reflect",
+        bidirectional: bool = False,
+        gpu_semaphore: Queue = None,
+        bleach_correction_frequency: float = None,
+        bleach_correction_max_method: bool = True,
+        bleach_correction_clip_min: Union[float, int] = None,
+        bleach_correction_clip_med: Union[float, int] = None,
+        bleach_correction_clip_max: Union[float, int] = None,
+        dark: float = 0,
+        lightsheet: bool = False,
+        artifact_length: int = 150,
+        background_window_size: int = 200,
+        percentile: float = 0.25,
+        lightsheet_vs_background: float = 2.0,
+        convert_to_16bit: bool = False,
+        convert_to_8bit: bool = True,
+        bit_shift_to_right: int = 8,
+        down_sample: Tuple[int, int] = None,
+        down_sample_method: str = 'max',
+        new_size: Tuple[int, int] = None,
+        rotate: int = 0,
+        flip_upside_down: bool = False,
+):
+    """One file in, one TIFF out (reference core.py:1384-1600).  Failures are reported and swallowed like the
+    reference does (:1594-1600)."""
+    try:
+        input_file, output_file = Path(input_file), Path(output_file)
+        if continue_process and output_file.exists():
+            return
+        if print_input_file_names:
+            print(f"\n{input_file}")
+        img = _read_one(input_file, z_idx, d_type, tile_size, output_file)
+        if img is None:
+            return
+        if tile_size is not None and img.shape != tuple(tile_size):
+            raise NotImplementedError("resizing an input tile to tile_size needs skimage.transform.resize (next row N3)")
+        if d_type is None:
+            d_type = img.dtype
+        output_file.parent.mkdir(parents=True, exist_ok=True)
+        kw = {k: v for k, v in locals().items() if k in _PROCESS_KEYS}
+        img = process_img(np.ascontiguousarray(img), tile_size=img.shape, d_type=d_type, **kw)
+        imsave_tif(output_file, img, compression=compression)
+    except (OSError, IndexError, TypeError, RuntimeError) as inst:
+        print(f"{PrintColors.WARNING}warning: read_filter_save function failed:\n{type(inst)}\n{inst.args}\n{inst}"
+              f"\nPossible damaged input file: {input_file}{PrintColors.ENDC}")
+
+
+def _read_one(input_file, z_idx, d_type, tile_size, output_file):
+    """core.py:1515-1540: decode, or substitute a zero tile when shape and dtype are known."""
+    if z_idx is None:
+        img = imread_tif_raw_png(input_file, dtype=d_type, shape=tile_size)
+    else:
+        img = imread_dcimg(input_file, z_idx)
+    if img is None and d_type is not None and tile_size is not None:
+        print(f"{PrintColors.WARNING}\nimread function returned None. Possible damaged input file:\n\t{input_file}."
+              f"\n\toutput file is set to a dummy zeros tile of shape {tile_size} and type {d_type}, instead:"
+              f"\n\t{output_file}{PrintColors.ENDC}")
+        img = zeros(dtype=d_type, shape=tile_size)
+    elif img is None:
+        print(f"{PrintColors.WARNING}\nimread function returned None. Possible damaged input file:\n\t{input_file}."
+              f"\n\toutput file could be replaced with a dummy tile of zeros if shape and d_type were provided."
+              f"{PrintColors.ENDC}")
+    return img
+
+
+# --------------------------------------------------------------------------------------------------------------
+# job farm classes kept for API compatibility (process_images.py:37 imports them)
+# --------------------------------------------------------------------------------------------------------------
+class MultiProcessQueueRunner(Process):
+    """core.py:1687-1771: a worker that drains a queue of kwargs dicts through `fun`.  batch_filter no longer uses
+    it (the GPU scheduler below replaces the process farm); other reference scripts still can."""
+
+    def __init__(self, progress_queue: Queue, args_queue: Queue, gpu_semaphore: Queue = None, gpu: int = None,
+                 fun: Callable = read_filter_save, timeout: float = None, replace_timeout_with_dummy: bool = True):
+        Process.__init__(self)
+        self.daemon = False
+        self.progress_queue = progress_queue
+        self.args_queue = args_queue
+        self.gpu_semaphore = gpu_semaphore
+        self.gpu = gpu
+        self.timeout = timeout
+        self.die = False
+        self.function = fun
+        self.replace_timeout_with_dummy = replace_timeout_with_dummy
+
+    def run(self):
+        if self.gpu is not None:
+            os.environ["B200STRIPE_DEVICE"] = str(self.gpu)
+        running_next = True
+        while not self.die:
+            try:
+                args: dict = self.args_queue.get(block=True, timeout=0.5)
+            except Empty:
+                break
+            try:
+                self.function(**args)
+            except KeyboardInterrupt:
+                self.die = True
+            except Exception as inst:
+                print(f"{PrintColors.WARNING}\nwarning: process unexpectedly failed for {args}."
+                      f"\nexception instance: {type(inst)}\nexception: {inst}{PrintColors.ENDC}")
+            self.progress_queue.put(running_next)
+        self.progress_queue.put(not running_next)
+
+
+def progress_manager(progress_queue: Queue, workers: int, total: int, desc="PyStripe", unit=" images"):
+    """core.py:1774-1803."""
+    from tqdm import tqdm
+    return_code = 0
+    list_of_outputs = []
+    print(f"{PrintColors.GREEN}{date_time_now()}: {PrintColors.ENDC}"
+          f"using {workers} workers. {total} images need to be processed.", flush=True)
+    progress_bar = tqdm(total=total, ascii=True, smoothing=0.01, mininterval=1.0, unit=unit, desc=desc)
+    while workers > 0:
+        try:
+            still_running = progress_queue.get(block=False)
+            if isinstance(still_running, bool) and still_running:
+                progress_bar.update(1)
+            else:
+                workers -= 1
+                if not isinstance(still_running, bool):
+                    list_of_outputs += [still_running]
+        except Empty:
+            try:
+                sleep(0.05)
+            except KeyboardInterrupt:
+                print(f"\n{PrintColors.WARNING}Terminating processes with dignity!{PrintColors.ENDC}")
+                return_code = 1
+        except KeyboardInterrupt:
+            print(f"\n{PrintColors.WARNING}Terminating processes with dignity!{PrintColors.ENDC}")
+            return_code = 1
+    progress_bar.close()
+    return list_of_outputs if list_of_outputs else return_code
+
+
+# --------------------------------------------------------------------------------------------------------------
+# batch_filter  (core.py:1806-2044) — re-designed scheduling: decode threads -> per-GPU batched plans -> encode threads
+# --------------------------------------------------------------------------------------------------------------
+def _visible_gpus() -> List[int]:
+    env = os.environ.get("B200STRIPE_DEVICES")
+    if env:
+        return [int(v) for v in env.split(",") if v.strip() != ""]
+    try:
+        n = cuda_device_count()
+    except Exception:
+        n = 0
+    return list(range(max(n, 1)))
+
+
+def batch_filter(
+        input_path: Path,
+        output_path: Path,
+        files_list: List[Path] = None,
+        workers: int = None,
+        threads_per_gpu: int = 8,
+        flat: ndarray = None,
+        gaussian_filter_2d: bool = False,
+        sigma: Tuple[int, int] = (0, 0),
+        level=0,
+        wavelet: str = 'db9',
+        crossover: int = 10,
+        threshold: int = None,
+        padding_mode: str = "reflect",
+        bidirectional: bool = False,
+        bleach_correction_frequency: float = None,
+        bleach_correction_max_method: bool = True,
+        bleach_correction_clip_min: Union[float, int] = None,
+        bleach_correction_clip_med: Union[float, int] = None,
+        bleach_correction_clip_max: Union[float, int] = None,
+        dark: int = 0,
+        z_step: float = None,
+        rotate: int = 0,
+        flip_upside_down: bool = False,
+        lightsheet: bool = False,
+        artifact_length: int = 150,
+        background_window_size: int = 200,
+        percentile: float = .25,
+        lightsheet_vs_background: float = 2.0,
+        convert_to_16bit: bool = False,
+        convert_to_8bit: bool = False,
+        bit_shift_to_right: int = 8,
+        continue_process: bool = False,
+        d_type: str = None,
+        tile_size: Tuple[int, int] = None,
+        down_sample: Tuple[int, int] = None,
+        new_size: Tuple[int, int] = None,
+        print_input_file_names: bool = False,
+        timeout: float = None,
+        compression: Tuple[str, int] = ('ADOBE_DEFLATE', 1)
+) -> int:
+    """Apply process_img to every image under `input_path`, writing TIFFs under `output_path`
+    (reference core.py:1806-2044; same arguments, return code 0 = done, 1 = interrupted).
+
+    Scheduling is re-designed for one box of B200s: `workers` host threads decode files into batches, one feeder
+    thread per visible GPU runs a batched plan (Z planes are independent: no collective), encoder threads write the
+    results.  `threads_per_gpu` is the number of planes per GPU batch; `timeout` is accepted and ignored.
+    """
+    from tqdm import tqdm
+    input_path = Path(input_path)
+    assert input_path.is_dir()
+    if convert_to_16bit is True and convert_to_8bit is True:
+        print(f"{PrintColors.FAIL}Select 8-bit or 16-bit output format.{PrintColors.ENDC}")
+        raise TypeError("Select 8-bit or 16-bit output format.")
+    output_path = Path(output_path)
+    output_path.mkdir(parents=True, exist_ok=True)
+    if sigma is None:
+        sigma = (0, 0)
+    if workers is None or workers <= 0:
+        workers = os.cpu_count() or 1
+    if isinstance(flat, (np.ndarray, np.generic)):
+        flat = normalize_flat(flat)
+    elif isinstance(flat, (Path, str)):
+        flat = normalize_flat(imread_tif_raw_png(Path(flat)))
+    elif flat is not None:
+        print(f"{PrintColors.FAIL}flat argument should be a numpy array or a path to a flat.tif file{PrintColors.ENDC}")
+        raise TypeError("flat argument should be a numpy array or a path to a flat.tif file")
+    if isinstance(down_sample, tuple) and down_sample == (1, 1):
+        down_sample = None
+    kw = dict(flat=flat, gaussian_filter_2d=gaussian_filter_2d, sigma=sigma, level=level, wavelet=wavelet,
+              crossover=crossover, threshold=threshold, padding_mode=padding_mode, bidirectional=bidirectional,
+              bleach_correction_frequency=bleach_correction_frequency,
+              bleach_correction_max_method=bleach_correction_max_method,
+              bleach_correction_clip_min=bleach_correction_clip_min,
+              bleach_correction_clip_med=bleach_correction_clip_med,
+              bleach_correction_clip_max=bleach_correction_clip_max, dark=dark, lightsheet=lightsheet,
+              artifact_length=artifact_length, background_window_size=background_window_size, percentile=percentile,
+              lightsheet_vs_background=lightsheet_vs_background, rotate=rotate, flip_upside_down=flip_upside_down,
+              convert_to_16bit=convert_to_16bit, convert_to_8bit=convert_to_8bit,
+              bit_shift_to_right=bit_shift_to_right, down_sample=down_sample, new_size=new_size)
+
+    print(f"{PrintColors.GREEN}{date_time_now()}: {PrintColors.ENDC}Scheduling jobs for images in \n\t{input_path}")
+    jobs = []  # (input_file, output_file, z_idx)
+    if z_step is None:
+        files = glob_re(r"\.(?:tiff?|raw|png)$", input_path) if files_list is None else files_list
+        for f in files:
+            f = Path(f)
+            out = output_path / f.relative_to(input_path)
+            out = out.parent / (out.name[0:-len(out.suffix)] + '.tif')
+            if continue_process and out.exists():
+                continue
+            jobs.append((f, out, None))
+    else:
+        files = glob_re(r"\.(?:dcimg)$", input_path) if files_list is None else files_list
+        for f in files:
+            f = Path(f)
+            n = check_dcimg_shape(f)[0]
+            start = check_dcimg_start(f)
+            for i in range(n):
+                out = output_path / f.relative_to(input_path).parent / f'z{start + i * z_step:08.1f}.tif'
+                if continue_process and out.exists():
+                    continue
+                jobs.append((f, out, i))
+    num_images = len(jobs)
+    if num_images == 0:
+        return 0
+
+    gpus = _visible_gpus()
+    batch = max(1, int(threads_per_gpu))
+    print(f"{PrintColors.GREEN}{date_time_now()}: {PrintColors.ENDC}"
+          f"using {workers} decode/encode threads and {len(gpus)} GPU(s). {num_images} images need to be processed.",
+          flush=True)
+    progress = tqdm(total=num_images, ascii=True, smoothing=0.01, mininterval=1.0, unit=" images", desc="PyStripe")
+    stop = threading.Event()
+    lock = threading.Lock()
+    cursor = [0]
+
+    def decode(job):
+        f, out, z = job
+        try:
+            if print_input_file_names:
+                print(f"\n{f}")
+            img = _read_one(f, z, d_type, tile_size, out)
+            if img is not None and tile_size is not None and img.shape != tuple(tile_size):
+                raise NotImplementedError("resizing an input tile to tile_size is a next-row feature (N3)")
+            return img
+        except (OSError, IndexError, TypeError, RuntimeError, ValueError) as inst:
+            print(f"{PrintColors.WARNING}warning: read failed for {f}: {type(inst)} {inst}{PrintColors.ENDC}")
+            return None
+
+    def encode(out, img):
+        try:
+            out.parent.mkdir(parents=True, exist_ok=True)
+            if imsave_tif(out, img, compression=compression):
+                stop.set()
+        except Exception as inst:  # never propagate per-file failures (core.py:1594-1600)
+            print(f"{PrintColors.WARNING}warning: write failed for {out}: {type(inst)} {inst}{PrintColors.ENDC}")
+
+    def feeder(device, pool):
+        pending = []
+        while not stop.is_set():
+            with lock:                                   # shared plane counter: dynamic Z partition across GPUs
+                lo = cursor[0]
+                hi = min(lo + batch, num_images)
+                cursor[0] = hi
+            if lo >= hi:
+                break
+            group = jobs[lo:hi]
+            imgs = list(pool.map(decode, group))
+            buckets = {}
+            for job, img in zip(group, imgs):
+                if img is None:
+                    progress.update(1)
+                    continue
+                buckets.setdefault((img.shape, img.dtype.str), []).append((job, img))
+            for (shape, _), items in buckets.items():
+                stack = np.stack([np.ascontiguousarray(i) for _, i in items])
+                try:
+                    with use_device(device):
+                        res = process_img(stack, tile_size=shape, d_type=d_type if d_type is not None else stack.dtype,
+                                          _max_batch=batch, **kw)
+                except (TypeError, RuntimeError, ValueError, NotImplementedError) as inst:
+                    print(f"{PrintColors.WARNING}warning: processing failed for {items[0][0][0]} (+{len(items) - 1}): "
+                          f"{type(inst)} {inst}{PrintColors.ENDC}")
+                    progress.update(len(items))
+                    continue
+                for (job, _), plane in zip(items, res):
+                    pending.append(pool.submit(encode, job[1], plane))
+                    progress.update(1)
+            pending = [p for p in pending if not p.done()]
+        for p in pending:
+            p.result()
+
+    return_code = 0
+    try:
+        with ThreadPoolExecutor(max_workers=max(2, workers)) as pool:
+            threads = [threading.Thread(target=feeder, args=(g, pool), daemon=True) for g in gpus[:max(1, num_images)]]
+            for t in threads:
+                t.start()
+            for t in threads:
+                while t.is_alive():
+                    t.join(timeout=0.5)
+    except KeyboardInterrupt:
+        print(f"\n{PrintColors.WARNING}Terminating processes with dignity!{PrintColors.ENDC}")
+        stop.set()
+        return_code = 1
+    progress.close()
+    if stop.is_set():
+        return_code = 1
+    return return_code

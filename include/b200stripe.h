@@ -1,0 +1,163 @@
+/*
+ * b200stripe — C ABI of the B200-native (sm_100a) pystripe hot path.
+ *
+ * The reference (ucla-brain/image-preprocessing-pipeline) has no FFI layer for this path: its boundary is the
+ * Python module surface of pystripe/core.py.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference root).  Host bindings: image-preprocessing-pipeline_b200/pystripe/_native.py
+ * (ctypes); the stub a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions: every call returns 0 on success or a negative b2s_status; the message for the last failure on a
+ * context is b2s_last_error(ctx).  Nothing throws across the ABI.  The caller owns every buffer it passes.
+ * One context per GPU; a context and its plans may be used from one host thread at a time.
+ * There is no CPU fallback: without a CUDA device b2s_create fails with B2S_ERR_CUDA.
+ */
+#ifndef B200STRIPE_H
+#define B200STRIPE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_VERSION 100 /* 0.1.0 */
+
+typedef enum b2s_status {
+    B2S_OK = 0,
+    B2S_ERR_INVALID = -1,     /* bad argument (ValueError / RuntimeError on the Python side)           */
+    B2S_ERR_UNSUPPORTED = -2, /* valid in the reference, not implemented by this build                 */
+    B2S_ERR_CUDA = -3,        /* CUDA runtime failure (message carries cudaGetErrorString)             */
+    B2S_ERR_NOMEM = -4
+} b2s_status;
+
+typedef enum b2s_dtype { B2S_U8 = 0, B2S_U16 = 1, B2S_F32 = 2 } b2s_dtype;
+
+/* numpy.pad modes accepted by filter_streaks (pystripe/core.py:1088-1089). */
+typedef enum b2s_pad_mode {
+    B2S_PAD_REFLECT = 0, B2S_PAD_WRAP = 1, B2S_PAD_SYMMETRIC = 2, B2S_PAD_EDGE = 3, B2S_PAD_CONSTANT = 4
+} b2s_pad_mode;
+
+typedef enum b2s_ds_method { B2S_DS_MAX = 0, B2S_DS_MIN = 1, B2S_DS_MEAN = 2, B2S_DS_MEDIAN = 3 } b2s_ds_method;
+
+/* debug_stop_after values (parity tests read intermediate coefficients with b2s_debug_read). */
+typedef enum b2s_stage { B2S_STAGE_ALL = 0, B2S_STAGE_PROLOGUE = 1, B2S_STAGE_FORWARD = 2, B2S_STAGE_NOTCH = 3,
+                         B2S_STAGE_INVERSE = 4 } b2s_stage;
+
+/*
+ * Plan parameters = the keyword arguments of process_img (pystripe/core.py:1190-1226) that reach arithmetic,
+ * which include every argument of filter_streaks (pystripe/core.py:982-1002).
+ * Zero-initialise, set struct_size = sizeof(b2s_params), then fill.
+ */
+typedef struct b2s_params {
+    int32_t struct_size;
+    int32_t height, width;        /* input plane (rows, cols)                                              */
+    int32_t in_dtype;             /* b2s_dtype of the input planes (U16 or U8; F32 for filter_streaks(float)) */
+    int32_t out_dtype;            /* b2s_dtype of the output planes                                        */
+    /* --- filter_streaks ------------------------------------------------------------------------------- */
+    double sigma1, sigma2;        /* sigma=(foreground, background); both 0 => destripe skipped (core.py:1058) */
+    int32_t threshold_nonpositive;/* `threshold is not None and threshold <= 0`: one pass with sigma1 (core.py:946) */
+    int32_t level;                /* 0 = maximum (pywt level=None), core.py:846                              */
+    int32_t n_taps;               /* wavelet decomposition low-pass length F (even, 2..128)                  */
+    const double *dec_lo;         /* host pointer, F doubles == pywt.Wavelet(name).dec_lo                    */
+    int32_t pad_mode;             /* b2s_pad_mode                                                           */
+    int32_t bidirectional;        /* core.py:1112-1117: also notch cV along axis -2                          */
+    int32_t log1p;                /* log1p_normalization_needed (core.py:1063, 1150)                         */
+    /* --- process_img ---------------------------------------------------------------------------------- */
+    int32_t process_img;          /* 0: filter_streaks semantics only; 1: full process_img order of operations */
+    int32_t has_flat;             /* flat-field supplied via b2s_plan_set_flat (core.py:1248-1250)           */
+    int32_t gaussian;             /* gaussian_filter_2d (core.py:1280-1284, intended semantics)              */
+    int32_t down_sample_y, down_sample_x; /* 0/1 = none (core.py:1286-1300); applied BEFORE the destripe     */
+    int32_t down_sample_method;   /* b2s_ds_method                                                          */
+    double dark;                  /* core.py:1324-1330                                                      */
+    int32_t lightsheet;           /* core.py:1333-1348 -> pystripe/lightsheet_correct.py:31                  */
+    int32_t artifact_length, background_window_size;
+    double percentile, lightsheet_vs_background;
+    int32_t convert_to_16bit, convert_to_8bit, bit_shift_to_right; /* core.py:1361-1369, 397-423              */
+    int32_t rotate;               /* 0, 90, 180, 270 (core.py:1374-1379)                                     */
+    int32_t flip_upside_down;     /* core.py:1371                                                           */
+    int32_t reference_quirks;     /* 1: reproduce as-written behaviour (Gaussian result discarded)           */
+    /* --- execution ------------------------------------------------------------------------------------ */
+    int32_t max_batch;            /* planes processed per launch group (workspace is sized for this)         */
+    int32_t debug_stop_after;     /* b2s_stage; 0 in production                                             */
+    int32_t exact;                /* 1 (default when 0 is passed through b2s_params_default): separate mul/add
+                                     in the reference's summation order; 0 allows FMA contraction            */
+} b2s_params;
+
+typedef struct b2s_plan_info {
+    int32_t out_height, out_width;      /* after down-sample / rotation                                     */
+    int32_t out_dtype;                  /* b2s_dtype actually written (core.py:1361-1369 rules)             */
+    int32_t n_passes;                   /* 0 (no destripe), 1, or 2 (sigma1 != sigma2, core.py:977-978)     */
+    int32_t work_height, work_width;    /* image entering filter_streaks (after down-sample)                */
+    int32_t base_pad, pad_y, pad_x;     /* core.py:1084-1096                                                */
+    int32_t padded_height, padded_width;
+    int32_t levels;
+    int32_t level_rows[32], level_cols[32]; /* sub-band shape per level (index 0 = level 1)                 */
+    int64_t workspace_bytes;
+    int64_t algorithmic_bytes_per_plane;  /* SURVEY.md §8(d) stage model, for roofline reporting            */
+    int64_t flops_per_plane;
+} b2s_plan_info;
+
+typedef struct b2s_context b2s_context;
+typedef struct b2s_plan b2s_plan;
+
+int b2s_version(void);
+void b2s_params_default(b2s_params *p); /* defaults of filter_streaks: wrap padding, log1p, level 0, exact */
+
+/* replaces: the implicit per-process device choice of the dead torch branch, pystripe/core.py:871-883, 1694-1695 */
+int b2s_create(int device, b2s_context **ctx);
+void b2s_destroy(b2s_context *ctx);
+const char *b2s_last_error(const b2s_context *ctx);
+int b2s_device_sm_count(const b2s_context *ctx);
+
+/* replaces: argument handling of filter_streaks / process_img (core.py:1055-1110, 1227-1254) */
+int b2s_plan_create(b2s_context *ctx, const b2s_params *params, b2s_plan **plan);
+void b2s_plan_destroy(b2s_plan *plan);
+int b2s_plan_query(const b2s_plan *plan, b2s_plan_info *info);
+/* host-only: validate params and report the geometry a plan would have; needs no GPU (err may be NULL) */
+int b2s_plan_geometry(const b2s_params *params, b2s_plan_info *info, char *err, size_t err_len);
+/* replaces: normalize_flat result captured in batch_filter's arg dict (core.py:1948-1953); flat is (height,width) f32 */
+int b2s_plan_set_flat(b2s_plan *plan, const float *flat, int is_device);
+
+/*
+ * replaces: process_img(img, ...) / filter_streaks(img, ...) applied to n_planes independent planes
+ * (core.py:1190, 982; driven per file by read_filter_save, core.py:1557).
+ * in : n_planes x height x width, contiguous, params.in_dtype;  out: n_planes x out_height x out_width.
+ * *_is_device = 1: pointer is device memory on the context's GPU (zero-copy torch tensors), work is enqueued on
+ * `stream` (cudaStream_t, may be NULL) and the call returns without synchronising.
+ * *_is_device = 0: host memory; the call stages through pinned buffers, overlaps H2D / compute / D2H on internal
+ * streams and returns after the result is in `out`.
+ */
+int b2s_run(b2s_plan *plan, const void *in, void *out, int64_t n_planes, int in_is_device, int out_is_device,
+            void *stream);
+
+/* page-locked host allocations for the caller's staging buffers (host path runs at PCIe speed only from these) */
+int b2s_host_alloc(b2s_context *ctx, size_t bytes, void **ptr);
+int b2s_host_free(b2s_context *ctx, void *ptr);
+
+/* number of kernels this library launched on the context since creation (bench.py reports it as gpu_launches) */
+int64_t b2s_launch_count(const b2s_context *ctx);
+
+/* event timing of the kernels inside b2s_run: when enabled every kernel class is bracketed by CUDA events on the
+ * launching stream; b2s_timing_read returns accumulated milliseconds and launch counts per class. */
+#define B2S_N_KERNEL_CLASSES 8
+enum { B2S_K_PRE = 0, B2S_K_PROLOGUE = 1, B2S_K_DWT_FWD = 2, B2S_K_NOTCH = 3, B2S_K_DWT_INV = 4, B2S_K_EPILOGUE = 5,
+       B2S_K_LIGHTSHEET = 6, B2S_K_OTHER = 7 };
+int b2s_timing_enable(b2s_context *ctx, int on);
+int b2s_timing_read(b2s_context *ctx, double *ms_per_class, int64_t *launches_per_class, int reset);
+
+/*
+ * Parity-test hook: copy one float32 buffer of plane `plane` of the last batch to host.
+ * what: 0 = padded image / reconstruction (padded_height x padded_width)
+ *       1..4 = cA, cH, cV, cD of `level` (1-based)
+ * out must hold rows*cols floats; rows/cols are returned.
+ */
+int b2s_debug_read(b2s_plan *plan, int what, int level, int plane, float *out, int32_t *rows, int32_t *cols);
+
+/* device-side math used by the kernels, exposed so tests can compare them with the host libm bit for bit */
+int b2s_debug_math(b2s_context *ctx, int which /*0 log1pf, 1 expm1f*/, const float *in, float *out, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200STRIPE_H */

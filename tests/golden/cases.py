@@ -1,0 +1,49 @@
+"""Seeded cases shared by make_golden.py (reference, verbatim) and the tests (oracle / GPU)."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from tools import synth  # noqa: E402
+
+
+def normalize_flat(flat):
+    f = flat.astype(np.float32)
+    return f / f.max()
+
+
+def all_cases():
+    """yields (name, kind, img, kwargs).  kind in {"filter_streaks", "process_img"}; '_flat' = flat-field array."""
+    rng = np.random.default_rng(7)
+    a = synth.plane(0, (96, 128))
+    b = rng.integers(0, 65536, size=(70, 91)).astype(np.uint16)
+    c = synth.plane(1, (30, 30))
+    d = synth.plane(2, (160, 200))
+    fs = "filter_streaks"
+    yield "fs_db10_wrap", fs, a, dict(sigma=(24, 24), wavelet="db10")
+    yield "fs_db9_reflect_bidir", fs, a, dict(sigma=(16, 16), wavelet="db9", padding_mode="reflect", bidirectional=True)
+    yield "fs_db4_dual_sigma", fs, a, dict(sigma=(8, 32), wavelet="db4", padding_mode="symmetric")
+    yield "fs_fullrange_odd", fs, b, dict(sigma=(10, 10), wavelet="db5", padding_mode="edge")
+    yield "fs_tiny_min34", fs, c, dict(sigma=(2, 2), wavelet="db2", padding_mode="constant")
+    yield "fs_level2", fs, a, dict(sigma=(24, 24), wavelet="db3", level=2)
+    yield "fs_nolog", fs, a, dict(sigma=(24, 24), wavelet="db3", log1p_normalization_needed=False)
+    yield "fs_db10_big", fs, d, dict(sigma=(32, 32), wavelet="db10", padding_mode="reflect")
+    yield "fs_u8", fs, (a >> 4).astype(np.uint8), dict(sigma=(16, 16), wavelet="db4")
+    pi = "process_img"
+    img = synth.plane(3, (96, 128))
+    yield "pi_dark_8bit", pi, img, dict(sigma=(16, 16), wavelet="db6", dark=100, convert_to_8bit=True, bit_shift_to_right=3)
+    yield "pi_ds_max", pi, img, dict(sigma=(16, 16), wavelet="db6", down_sample=(2, 2), dark=90, padding_mode="reflect")
+    yield "pi_ds_min_rot", pi, img, dict(sigma=(0, 0), down_sample=(3, 2), down_sample_method="min", rotate=90,
+                                        flip_upside_down=True)
+    yield "pi_16bit_rot270", pi, img, dict(sigma=(16, 16), wavelet="db6", convert_to_16bit=True, rotate=270)
+    yield "pi_rot180_flip", pi, img, dict(sigma=(12, 12), wavelet="db2", rotate=180, flip_upside_down=True, dark=120)
+    yield "pi_lightsheet", pi, img, dict(sigma=(0, 0), lightsheet=True, artifact_length=30, background_window_size=40,
+                                        dark=100)
+    yield "pi_flat_dark", pi, img, dict(sigma=(16, 16), wavelet="db6", dark=100, padding_mode="reflect",
+                                       _flat=normalize_flat(synth.flat_field((96, 128))))
+    yield "pi_flat_8bit", pi, img, dict(sigma=(16, 16), wavelet="db10", dark=100, convert_to_8bit=True,
+                                       bit_shift_to_right=4, _flat=normalize_flat(synth.flat_field((96, 128))))
+    yield "pi_uniform", pi, np.full((64, 80), 7, np.uint16), dict(sigma=(8, 8), wavelet="db2", down_sample=(2, 2),
+                                                                  rotate=90, convert_to_8bit=True)

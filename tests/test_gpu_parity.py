@@ -1,0 +1,254 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): integer outputs within +-1 LSB on every pixel and >= 99.99 % bit-exact where the
+whole chain is reproducible (everything except the row FFT, whose float32 rounding differs from pocketfft's: see
+DESIGN.md — the measured exact fraction is asserted against MIN_EXACT below); float intermediates within 1e-4 relative.
+Stages that are reproducible by construction (log1p, padding, analysis filter bank, expm1, integer epilogues) are
+asserted BIT-EXACT.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import pystripe_oracle as orc
+from oracle import pywt_shim as pw
+from tests.golden import cases
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+MIN_EXACT = 0.999          # fraction of bit-exact integer pixels required per case (measured: see profiles/parity_r01.json)
+REPORT = {}
+
+
+def _cmp_int(name, got, ref, min_exact=MIN_EXACT):
+    assert got.dtype == ref.dtype and got.shape == ref.shape, (name, got.dtype, ref.dtype, got.shape, ref.shape)
+    d = np.abs(got.astype(np.int64) - ref.astype(np.int64))
+    exact = float((d == 0).mean())
+    REPORT[name] = {"max_abs_diff": int(d.max()), "exact_fraction": exact, "pixels": int(d.size)}
+    assert d.max() <= 1, f"{name}: max |diff| = {d.max()}"
+    assert exact >= min_exact, f"{name}: only {exact:.5%} bit-exact"
+
+
+def test_device_math_is_bit_exact(gpu_ctx):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([np.arange(65536, dtype=np.float32),
+                        rng.uniform(0, 70000, 1 << 20).astype(np.float32),
+                        (np.arange(65536, dtype=np.float32) / rng.uniform(0.3, 1, 65536).astype(np.float32))])
+    assert np.array_equal(gpu_ctx.debug_math(0, x), orc.log1p_f32(x))
+    y = np.concatenate([rng.uniform(-2, 12, 1 << 20).astype(np.float32), orc.log1p_f32(x)])
+    assert np.array_equal(gpu_ctx.debug_math(1, y), orc.expm1_f32(y))
+
+
+def _plan(shape, code, **kw):
+    from pystripe import core
+    base = dict(process=0, sigma=(24, 24), level=0, wavelet="db10", threshold=None, padding_mode="wrap",
+                bidirectional=False, log1p=True)
+    base.update(kw)
+    return core._get_plan(0, shape, code, **base)
+
+
+@pytest.mark.parametrize("mode", ["reflect", "wrap", "symmetric", "edge", "constant"])
+def test_prologue_log1p_and_padding_bit_exact(mode):
+    img = synth.plane(5, (70, 91))
+    plan = _plan(img.shape, 1, sigma=(40, 40), padding_mode=mode, stop_after=1)
+    plan.run_host(img)
+    got = plan.debug_read(0)
+    base, py, px = orc.padded_geometry(img.shape, (40, 40), mode)
+    ref = np.pad(orc.log1p_f32(img.astype(np.float32)), ((base, base + py), (base, base + px)), mode=mode)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("shape,wavelet,sigma", [((96, 128), "db10", (24, 24)), ((70, 91), "db5", (10, 10)),
+                                                  ((160, 200), "db2", (64, 64)), ((128, 96), "db9", (16, 16)),
+                                                  ((200, 300), "db16", (30, 30))])
+def test_forward_dwt_bit_exact(shape, wavelet, sigma):
+    img = synth.plane(6, shape)
+    plan = _plan(shape, 1, sigma=sigma, wavelet=wavelet, stop_after=2)
+    plan.run_host(img)
+    base, py, px = orc.padded_geometry(shape, sigma, "wrap")
+    padded = np.pad(orc.log1p_f32(img.astype(np.float32)), ((base, base + py), (base, base + px)), mode="wrap")
+    coeffs = pw.wavedec2(padded, wavelet)
+    L = len(coeffs) - 1
+    assert plan.info.levels == L
+    for lvl in range(1, L + 1):
+        ch, cv, cd = coeffs[L - lvl + 1]
+        for what, ref in ((2, ch), (3, cv), (4, cd)):
+            got = plan.debug_read(what, lvl)
+            assert np.array_equal(got, ref), f"level {lvl} band {what}: {np.abs(got - ref).max()}"
+    assert np.array_equal(plan.debug_read(1, L), coeffs[0])
+
+
+def test_inverse_dwt_bit_exact_without_notch():
+    """sigma so large that... no: run forward+inverse only by stopping before the notch is not possible, so compare the
+    reconstruction after a run whose notch is the identity except DC (tiny sigma): oracle does the same steps."""
+    img = synth.plane(7, (96, 128))
+    plan = _plan(img.shape, 1, sigma=(24, 24), wavelet="db4", stop_after=4)
+    plan.run_host(img)
+    got = plan.debug_read(0)
+    base, py, px = orc.padded_geometry(img.shape, (24, 24), "wrap")
+    padded = np.pad(orc.log1p_f32(img.astype(np.float32)), ((base, base + py), (base, base + px)), mode="wrap")
+    ref = orc.filter_subband(padded, 24, 0, "db4")
+    rel = np.abs(got - ref).max() / np.abs(ref).max()
+    REPORT["log_domain_rel_err_db4"] = float(rel)
+    assert rel < 1e-4
+
+
+def test_notch_stage_close_to_pocketfft():
+    img = synth.plane(8, (96, 128))
+    plan = _plan(img.shape, 1, sigma=(24, 24), wavelet="db10", stop_after=3, bidirectional=True)
+    plan.run_host(img)
+    base, py, px = orc.padded_geometry(img.shape, (24, 24), "wrap")
+    padded = np.pad(orc.log1p_f32(img.astype(np.float32)), ((base, base + py), (base, base + px)), mode="wrap")
+    coeffs = pw.wavedec2(padded, "db10")
+    L = len(coeffs) - 1
+    for lvl in range(1, L + 1):
+        ch, cv, _ = coeffs[L - lvl + 1]
+        rh = orc.np_filter_coefficient(ch.copy(), 24 / padded.shape[0], axis=-1)
+        rv = orc.np_filter_coefficient(cv.copy(), 24 / padded.shape[1], axis=-2)
+        gh, gv = plan.debug_read(2, lvl), plan.debug_read(3, lvl)
+        for g, r in ((gh, rh), (gv, rv)):
+            assert np.abs(g - r).max() <= 1e-5 * max(1.0, float(np.abs(r).max()))
+
+
+def _gpu_case(kind, img, kw):
+    from pystripe import core
+    if kind == "filter_streaks":
+        return core.filter_streaks(img.copy(), **kw)
+    kw = dict(kw)
+    flat = kw.pop("_flat", None)
+    if flat is not None:
+        return core.process_img(img.copy(), flat=flat, d_type="uint16", **kw)
+    return core.process_img(img.copy(), **kw)
+
+
+def test_golden_vectors_from_the_reference():
+    gold = np.load(ROOT / "tests" / "golden" / "pystripe_golden.npz")
+    for name, kind, img, kw in cases.all_cases():
+        if kw.get("lightsheet"):
+            continue  # lightsheet has its own test module
+        if kw.get("log1p_normalization_needed") is False:
+            pass
+        got = _gpu_case(kind, img, kw)
+        _cmp_int("golden/" + name, np.asarray(got), gold[name])
+
+
+@pytest.mark.parametrize("kw", [
+    dict(sigma=(256, 256), wavelet="db10"),                                   # BASELINE config 1 (scaled plane)
+    dict(sigma=(128, 512), wavelet="db9", padding_mode="reflect", bidirectional=True),
+    dict(sigma=(100, 100), wavelet="db9", padding_mode="reflect", bidirectional=True),  # Step 3 as shipped
+    dict(sigma=(64, 64), wavelet="db20", level=3),
+])
+def test_filter_streaks_512(kw):
+    from pystripe import core
+    img = synth.plane(11, (512, 512))
+    got = core.filter_streaks(img, **kw)
+    ref = orc.filter_streaks(img, **kw)
+    _cmp_int(f"fs512/{kw}", got, ref)
+
+
+def test_filter_streaks_float_input_stays_float():
+    from pystripe import core
+    img = synth.plane(12, (128, 160)).astype(np.float32)
+    got = core.filter_streaks(img.copy(), sigma=(32, 32), wavelet="db6")
+    ref = orc.filter_streaks(img.copy(), sigma=(32, 32), wavelet="db6")
+    assert got.dtype == np.float32
+    assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_odd_ragged_and_tiny_shapes():
+    from pystripe import core
+    for shape, wavelet, sigma in [((255, 257), "db10", (64, 64)), ((30, 30), "db2", (2, 2)), ((64, 64), "db9", (1, 1)),
+                                  ((33, 301), "db3", (20, 20))]:
+        img = synth.plane(13, shape)
+        _cmp_int(f"ragged/{shape}", core.filter_streaks(img, sigma=sigma, wavelet=wavelet),
+                 orc.filter_streaks(img, sigma=sigma, wavelet=wavelet))
+
+
+def test_sigma_zero_is_identity_and_errors():
+    from pystripe import core
+    img = synth.plane(14, (64, 64))
+    assert core.filter_streaks(img, sigma=(0, 0)) is img
+    with pytest.raises(ValueError):
+        core.filter_streaks(img, sigma=(0, 8), wavelet="db2")
+
+
+def test_batch_equals_single_and_torch_zero_copy():
+    import torch
+    from pystripe import core
+    stack = synth.stack(5, (128, 160))
+    kw = dict(sigma=(32, 32), wavelet="db10", padding_mode="reflect")
+    whole = core.filter_streaks(stack, **kw)
+    for z in range(5):
+        assert np.array_equal(whole[z], core.filter_streaks(stack[z], **kw))
+    t = torch.from_numpy(stack).cuda()
+    out = core.filter_streaks(t, **kw)
+    assert out.is_cuda and out.dtype == torch.uint16
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), whole)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(sigma=(32, 32), wavelet="db10", dark=100, padding_mode="reflect"),
+    dict(sigma=(32, 32), wavelet="db10", dark=100, convert_to_8bit=True, bit_shift_to_right=4, down_sample=(2, 2)),
+    dict(sigma=(0, 0), dark=120.5, convert_to_8bit=True, bit_shift_to_right=0),
+    dict(sigma=(16, 16), wavelet="db4", down_sample=(2, 3), down_sample_method="mean"),
+    dict(sigma=(16, 16), wavelet="db4", gaussian_filter_2d=True, rotate=90),
+    dict(sigma=(0, 0), gaussian_filter_2d=True, flip_upside_down=True),
+])
+def test_process_img_variants(kw):
+    from pystripe import core
+    img = synth.plane(15, (130, 171))
+    got = core.process_img(img.copy(), **kw)
+    ref = orc.process_img(img.copy(), **kw)
+    _cmp_int(f"pi/{kw}", got, ref)
+
+
+def test_process_img_flat_field_float_path():
+    from pystripe import core
+    img = synth.plane(16, (128, 160))
+    flat = orc.normalize_flat(synth.flat_field((128, 160)))
+    kw = dict(sigma=(32, 32), wavelet="db10", dark=100, padding_mode="reflect")
+    got = core.process_img(img.copy(), flat=flat, **kw)
+    ref = orc.process_img(img.copy(), flat=flat, **kw)
+    _cmp_int("pi/flat", got, ref)
+
+
+def test_uniform_plane_shortcut():
+    from pystripe import core
+    stack = synth.stack(3, (64, 80))
+    stack[1] = 9
+    out = core.process_img(stack, sigma=(8, 8), wavelet="db2", convert_to_8bit=True, rotate=90)
+    assert out.shape == (3, 80, 64) and out.dtype == np.uint8
+    assert (out[1] == 0).all() and out[0].any()
+    for z in (0, 2):
+        assert np.array_equal(out[z], orc.process_img(stack[z], sigma=(8, 8), wavelet="db2", convert_to_8bit=True, rotate=90)) \
+            or np.abs(out[z].astype(int) - orc.process_img(stack[z], sigma=(8, 8), wavelet="db2", convert_to_8bit=True, rotate=90)).max() <= 1
+
+
+def test_full_size_plane_against_oracle():
+    """BASELINE config 1 at full size: one 2048x2048 plane, sigma=(256,256), db10, defaults."""
+    from pystripe import core
+    img = synth.plane(0, (2048, 2048))
+    got = core.filter_streaks(img, sigma=(256, 256), wavelet="db10")
+    ref = orc.filter_streaks(img, sigma=(256, 256), wavelet="db10")
+    _cmp_int("config1/2048", got, ref)
+
+
+def test_full_size_property_columns_only_image_is_a_fixed_point():
+    """size-independent property: an image that is constant along y has cH == 0 at every level, so the destripe must
+    return it unchanged (the float32 wavelet round trip is far below half an LSB)."""
+    from pystripe import core
+    rng = np.random.default_rng(5)
+    row = rng.integers(100, 4000, 2048).astype(np.uint16)
+    img = np.ascontiguousarray(np.broadcast_to(row, (2048, 2048)))
+    out = core.filter_streaks(img, sigma=(256, 256), wavelet="db10", padding_mode="reflect")
+    assert np.array_equal(out, img)
+
+
+def test_zz_write_parity_report():
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "parity_report.json").write_text(json.dumps(REPORT, indent=1, default=str))

@@ -1,0 +1,140 @@
+"""CPU: the oracle against known answers, the golden vectors made from the reference run verbatim, and (where
+/root/reference exists) the reference itself."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+from scipy.fftpack import rfft
+
+from oracle import pystripe_oracle as orc
+from oracle import pywt_shim as pw
+from oracle import ref_runner
+from tests.golden import cases
+
+ROOT = Path(__file__).resolve().parents[1]
+
+# known-answer vectors
+REC_LO = {
+    "db2": [0.48296291314469025, 0.836516303737469, 0.22414386804185735, -0.12940952255092145],
+    "db3": [0.3326705529509569, 0.8068915093133388, 0.4598775021193313, -0.13501102001039084, -0.08544127388224149,
+            0.035226291882100656],
+    "db4": [0.23037781330885523, 0.7148465705525415, 0.6308807679295904, -0.02798376941698385, -0.18703481171888114,
+            0.030841381835986965, 0.032883011666982945, -0.010597401784997278],
+}
+DB10_DEC_LO = [-1.3264202894521245e-5, 9.3588670320069591e-5, -1.1646685512928545e-4, -6.8585669495971163e-4,
+               1.9924052951850561e-3, 1.3953517470529012e-3, -1.0733175483330575e-2, 3.6065535669561697e-3,
+               3.3212674059341002e-2, -2.9457536821875813e-2, -7.1394147166397087e-2, 9.3057364603572351e-2,
+               1.2736934033579326e-1, -1.9594627437737704e-1, -2.4984642432731538e-1, 2.8117234366057746e-1,
+               6.8845903945360357e-1, 5.2720118893172559e-1, 1.8817680007769149e-1, 2.6670057900555554e-2]
+
+
+@pytest.mark.parametrize("name", sorted(REC_LO))
+def test_wavelet_known_answers(name):
+    w = pw.Wavelet(name)
+    assert np.allclose(w.rec_lo, REC_LO[name], atol=5e-12, rtol=0)
+    assert np.allclose(w.dec_lo, REC_LO[name][::-1], atol=5e-12, rtol=0)
+
+
+def test_db10_table():
+    assert np.allclose(pw.Wavelet("db10").dec_lo, DB10_DEC_LO, atol=1e-15, rtol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["db1", "db2", "db5", "db9", "db10", "db16", "db20"])
+def test_wavelet_orthonormal_and_moments(name):
+    w = pw.Wavelet(name)
+    h = w.dec_lo
+    F = h.size
+    assert abs(h.sum() - np.sqrt(2)) < 1e-13
+    for m in range(F // 2):
+        s = float(np.dot(h[: F - 2 * m], h[2 * m:]))
+        assert abs(s - (1.0 if m == 0 else 0.0)) < 1e-12
+    # N = F/2 vanishing moments of the high-pass
+    g = w.dec_hi
+    k = np.arange(F, dtype=np.float64)
+    for p in range(F // 2):
+        assert abs(np.dot(g, k ** p)) < 1e-6 * max(1.0, (F ** p))
+    assert np.array_equal(w.rec_hi, [(-1) ** i * w.rec_lo[F - 1 - i] for i in range(F)])
+
+
+@pytest.mark.parametrize("shape,wav", [((64, 64), "db2"), ((101, 60), "db4"), ((39, 183), "db3"), ((200, 266), "db10")])
+@pytest.mark.parametrize("dt,tol", [(np.float64, 1e-12), (np.float32, 2e-5)])
+def test_perfect_reconstruction(shape, wav, dt, tol):
+    x = np.random.default_rng(0).standard_normal(shape).astype(dt)
+    c = pw.wavedec2(x, wav)
+    r = pw.waverec2(c, wav)
+    assert r.dtype == dt
+    assert np.abs(r[: shape[0], : shape[1]] - x).max() < tol
+
+
+def test_level_rule_and_shapes():
+    c = pw.wavedec2(np.zeros((2648, 2648), np.float32), "db10")
+    assert [d[0].shape[0] for d in c[1:]][::-1] == [1333, 676, 347, 183, 101, 60, 39]
+    assert pw.dwt_max_level(3252, 90) == 5 and pw.dwt_max_level(2588, 18) == 7 and pw.dwt_max_level(16, 18) == 0
+
+
+def test_symmetric_extension_definition():
+    """dwt output == direct evaluation on the half-sample symmetric extension (float64, order-insensitive)."""
+    rng = np.random.default_rng(3)
+    for n, name in [(37, "db3"), (20, "db10"), (64, "db4")]:
+        x = rng.standard_normal(n)
+        w = pw.Wavelet(name)
+        F = w.dec_len
+        ext = np.concatenate([x[::-1], x, x[::-1]])
+        a, d = pw.dwt_axis(x[None, :], w, -1)
+        for o in range((n + F - 1) // 2):
+            ref = sum(w.dec_lo[j] * ext[n + 2 * o + 1 - j] for j in range(F))
+            assert abs(a[0, o] - ref) < 1e-12
+
+
+def test_scalar_known_answers():
+    assert orc.calculate_pad_size((2048, 2048), 256) == 300
+    assert orc.calculate_pad_size((2048, 2048), 250) == 294
+    assert orc.calculate_pad_size((2048, 2048), 512) == 602
+    assert orc.calculate_pad_size((2048, 2048), 100) == 118
+    g = orc.np_notch(8, 2.0)
+    assert np.allclose(g, [0, .11750311, .39346933, .67534757, .86466473, .9560631, .988891, .9978125], atol=2e-7)
+    assert np.allclose(rfft(np.arange(8, dtype=np.float32)), [28, -4, 9.656855, -4, 4, -4, 1.6568542, -4], atol=1e-5)
+
+
+def _run_case(kind, img, kw):
+    if kind == "filter_streaks":
+        return orc.filter_streaks(img.copy(), **kw)
+    kw = dict(kw)
+    flat = kw.pop("_flat", None)
+    if flat is not None:
+        return orc.process_img(img.copy(), flat=flat, d_type="uint16", **kw)
+    quirks = not kw.get("gaussian_filter_2d", False)
+    return orc.process_img(img.copy(), quirks=quirks, **kw)
+
+
+def test_oracle_matches_golden_vectors():
+    """goldens were produced by the reference source executed verbatim (tests/golden/make_golden.py)."""
+    gold = np.load(ROOT / "tests" / "golden" / "pystripe_golden.npz")
+    meta = json.loads((ROOT / "tests" / "golden" / "pystripe_golden.json").read_text())
+    n = 0
+    for name, kind, img, kw in cases.all_cases():
+        got = _run_case(kind, img, kw)
+        ref = gold[name]
+        assert str(got.dtype) == meta[name]["dtype"] and list(got.shape) == meta[name]["shape"], name
+        assert np.array_equal(got, ref), f"{name}: {(got != ref).mean():.4%} pixels differ"
+        n += 1
+    assert n == len(meta)
+
+
+@pytest.mark.skipif(not ref_runner.available(), reason="/root/reference only exists in the build container")
+def test_oracle_matches_reference_verbatim():
+    r = subprocess.run([sys.executable, "-m", "oracle.ref_check"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rep = json.loads(r.stdout.strip().splitlines()[-1])
+    assert rep["bad"] == 0 and len(rep["cases"]) >= 20
+
+
+def test_libm_pins():
+    x = np.linspace(0, 70000, 200001, dtype=np.float32)
+    y = orc.log1p_f32(x)
+    assert np.abs(y - np.log1p(x.astype(np.float64))).max() < 2e-6
+    z = orc.expm1_f32(y)
+    assert (np.abs(z - x) <= 1e-6 * np.maximum(x, 1.0)).all()

@@ -140,6 +140,20 @@ def main():
     tables["haar"] = tables["db1"]
     out_json = {k: [float(c) for c in v] for k, v in tables.items()}
     (ROOT / "oracle" / "wavelet_tables.json").write_text(json.dumps(out_json, indent=0))
+    lines = ['"""Wavelet decomposition low-pass tables (== pywt.Wavelet(name).dec_lo), float64.',
+             '',
+             'GENERATED by tools/gen_wavelets.py (mpmath, 80 digits) — do not edit.  PyWavelets is not a dependency of',
+             'this package: the four filters of an orthogonal wavelet all derive from this one list.',
+             '"""',
+             '',
+             'DEC_LO = {']
+    for k, v in out_json.items():
+        lines.append(f'    "{k}": (')
+        for c in v:
+            lines.append(f'        {c!r},')
+        lines.append('    ),')
+    lines.append('}')
+    (ROOT / "image-preprocessing-pipeline_b200" / "pystripe" / "_wavelet_tables.py").write_text("\n".join(lines) + "\n")
     print({k: len(v) for k, v in out_json.items()})
 
 
