@@ -17,10 +17,10 @@ struct b2s_context {
     std::string err;
     int64_t launches = 0;
     bool timing = false;
-    struct Span { int cls; cudaEvent_t a, b; };
+    struct Span { int cls, level, n; cudaEvent_t a, b; };
     std::vector<Span> spans;
-    double ms[B2S_N_KERNEL_CLASSES] = {0};
-    int64_t n_launch[B2S_N_KERNEL_CLASSES] = {0};
+    double ms[B2S_N_KERNEL_CLASSES][B2S_TIMING_LEVELS] = {{0}};
+    int64_t n_launch[B2S_N_KERNEL_CLASSES][B2S_TIMING_LEVELS] = {{0}};
 };
 
 namespace {
@@ -283,16 +283,17 @@ int dev_alloc(b2s_plan *pl, void **ptr, size_t bytes)
     return B2S_OK;
 }
 
+// brackets `n_launches` kernel launches of class `k` (level 0 = not level-specific) with CUDA events on the
+// launching stream when timing is enabled; always counts the launches
 struct ClassTimer {
     b2s_context *ctx;
     cudaStream_t s;
-    int cls;
-    int n;
+    int cls, level, n;
     cudaEvent_t a = nullptr;
-    ClassTimer(b2s_context *c, cudaStream_t st, int k, int n_launches) : ctx(c), s(st), cls(k), n(n_launches)
+    ClassTimer(b2s_context *c, cudaStream_t st, int k, int n_launches, int lvl = 0)
+        : ctx(c), s(st), cls(k), level(lvl), n(n_launches)
     {
         ctx->launches += n;
-        ctx->n_launch[cls] += n;
         if (ctx->timing) { cudaEventCreate(&a); cudaEventRecord(a, s); }
     }
     ~ClassTimer()
@@ -301,7 +302,7 @@ struct ClassTimer {
             cudaEvent_t b;
             cudaEventCreate(&b);
             cudaEventRecord(b, s);
-            ctx->spans.push_back({cls, a, b});
+            ctx->spans.push_back({cls, level, n, a, b});
         }
     }
 };
@@ -469,8 +470,8 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
         if (p.debug_stop_after == B2S_STAGE_PROLOGUE) return B2S_OK;
         for (int pass = 0; pass < g.n_passes; ++pass) {
             {
-                ClassTimer t(ctx, st, B2S_K_DWT_FWD, g.levels);
                 for (int l = 1; l <= g.levels; ++l) {
+                    ClassTimer t(ctx, st, B2S_K_DWT_FWD, 1, l);
                     const B2sImg in = l == 1 ? padded : img_of(pl, s.sub[l - 1][0], l - 1);
                     b2s_launch_dwt_fwd(pl->taps, in, img_of(pl, s.sub[l][0], l), img_of(pl, s.sub[l][1], l),
                                        img_of(pl, s.sub[l][2], l), img_of(pl, s.sub[l][3], l), nb, exact, st);
@@ -478,8 +479,8 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             }
             if (p.debug_stop_after == B2S_STAGE_FORWARD) return B2S_OK;
             {
-                ClassTimer t(ctx, st, B2S_K_NOTCH, g.levels * (p.bidirectional ? 2 : 1));
                 for (int l = 1; l <= g.levels; ++l) {
+                    ClassTimer t(ctx, st, B2S_K_NOTCH, p.bidirectional ? 2 : 1, l);
                     b2s_launch_notch(pl->fft[g.mx[l]], pl->d_notch[pass][l][0], img_of(pl, s.sub[l][1], l), 0, nb,
                                      ctx->sm_count, st);
                     if (p.bidirectional)
@@ -489,8 +490,8 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             }
             if (p.debug_stop_after == B2S_STAGE_NOTCH) return B2S_OK;
             {
-                ClassTimer t(ctx, st, B2S_K_DWT_INV, g.levels);
                 for (int l = g.levels; l >= 1; --l) {
+                    ClassTimer t(ctx, st, B2S_K_DWT_INV, 1, l);
                     // the reconstruction of level l-1 overwrites that level's approximation buffer (or the padded image)
                     B2sImg out = l == 1 ? padded : img_of(pl, s.sub[l - 1][0], l - 1);
                     b2s_launch_dwt_inv(pl->taps, img_of(pl, s.sub[l][0], l), img_of(pl, s.sub[l][1], l),
@@ -775,16 +776,19 @@ int b2s_timing_read(b2s_context *ctx, double *ms, int64_t *launches, int reset)
     for (auto &s : ctx->spans) {
         float t = 0.f;
         cudaEventElapsedTime(&t, s.a, s.b);
-        ctx->ms[s.cls] += t;
+        const int lv = s.level < B2S_TIMING_LEVELS ? s.level : 0;
+        ctx->ms[s.cls][lv] += t;
+        ctx->n_launch[s.cls][lv] += s.n;
         cudaEventDestroy(s.a);
         cudaEventDestroy(s.b);
     }
     ctx->spans.clear();
-    for (int k = 0; k < B2S_N_KERNEL_CLASSES; ++k) {
-        if (ms) ms[k] = ctx->ms[k];
-        if (launches) launches[k] = ctx->n_launch[k];
-        if (reset) { ctx->ms[k] = 0; ctx->n_launch[k] = 0; }
-    }
+    for (int k = 0; k < B2S_N_KERNEL_CLASSES; ++k)
+        for (int l = 0; l < B2S_TIMING_LEVELS; ++l) {
+            if (ms) ms[k * B2S_TIMING_LEVELS + l] = ctx->ms[k][l];
+            if (launches) launches[k * B2S_TIMING_LEVELS + l] = ctx->n_launch[k][l];
+            if (reset) { ctx->ms[k][l] = 0; ctx->n_launch[k][l] = 0; }
+        }
     return B2S_OK;
 }
 

