@@ -162,6 +162,9 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
         g.levels = L;
     }
     g.int_path = g.n_passes > 0 && g.work_dtype != B2S_F32;
+    if (g.int_path && !p.log1p)
+        return fail(ctx, B2S_ERR_UNSUPPORTED,
+                    "log1p_normalization_needed=False on an integer image runs in float64 in the reference; not implemented");
 
     // final conversion, core.py:1361-1369
     if (!p.process_img) {

@@ -29,6 +29,8 @@ def all_cases():
     yield "fs_tiny_min34", fs, c, dict(sigma=(2, 2), wavelet="db2", padding_mode="constant")
     yield "fs_level2", fs, a, dict(sigma=(24, 24), wavelet="db3", level=2)
     yield "fs_nolog", fs, a, dict(sigma=(24, 24), wavelet="db3", log1p_normalization_needed=False)
+    yield "fs_nolog_f32", fs, a.astype(np.float32), dict(sigma=(24, 24), wavelet="db3", log1p_normalization_needed=False)
+    yield "fs_f32", fs, a.astype(np.float32), dict(sigma=(24, 24), wavelet="db8", padding_mode="reflect")
     yield "fs_db10_big", fs, d, dict(sigma=(32, 32), wavelet="db10", padding_mode="reflect")
     yield "fs_u8", fs, (a >> 4).astype(np.uint8), dict(sigma=(16, 16), wavelet="db4")
     pi = "process_img"

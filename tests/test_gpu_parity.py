@@ -129,7 +129,17 @@ def test_golden_vectors_from_the_reference():
     for name, kind, img, kw in cases.all_cases():
         if kw.get("lightsheet"):
             continue  # lightsheet has its own test module
+        if kw.get("log1p_normalization_needed") is False and img.dtype.kind in "ui":
+            # the reference runs this combination in float64 and truncates inside filter_subband (core.py:939):
+            # declared unsupported by the GPU path rather than approximated
+            with pytest.raises(NotImplementedError):
+                _gpu_case(kind, img, kw)
+            continue
         got = _gpu_case(kind, img, kw)
+        if gold[name].dtype.kind == "f":
+            ref = gold[name]
+            assert got.dtype == ref.dtype and np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max(), name
+            continue
         # full-range random pixels (up to 65535): one float32 ulp in the log domain is ~100x larger in counts than for
         # camera-like data, so the row-FFT rounding difference shows on more pixels (still within 1 LSB)
         _cmp_int("golden/" + name, np.asarray(got), gold[name], min_exact=0.99 if "fullrange" in name else MIN_EXACT)
