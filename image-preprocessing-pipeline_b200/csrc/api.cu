@@ -230,18 +230,6 @@ void fill_info(const b2s_params &p, const Geometry &g, b2s_plan_info *info)
     info->flops_per_plane = flops;
 }
 
-std::vector<int> factorize(int n)
-{
-    std::vector<int> f;
-    for (int p : {4, 2, 3, 5, 7})
-        while (n % p == 0) { f.push_back(p); n /= p; }
-    for (int p = 11; n > 1; p += 2) {
-        if ((int64_t)p * p > n) { f.push_back(n); break; }
-        while (n % p == 0) { f.push_back(p); n /= p; }
-    }
-    return f;
-}
-
 }  // namespace
 
 struct b2s_plan {
@@ -352,11 +340,7 @@ int build_tables(b2s_plan *pl)
                     return fail(ctx, B2S_ERR_UNSUPPORTED, "sub-band side %d too long for the shared-memory FFT", n);
                 if (!pl->fft.count(n)) {
                     B2sFftPlan fp;
-                    fp.n = n;
-                    std::vector<int> f = factorize(n);
-                    if (f.size() > 32) return fail(ctx, B2S_ERR_UNSUPPORTED, "too many FFT factors");
-                    fp.n_factors = (int)f.size();
-                    for (size_t i = 0; i < f.size(); ++i) fp.factors[i] = f[i];
+                    b2s_fft_plan_init(&fp, n);
                     std::vector<float2> tw(n);
                     for (int k = 0; k < n; ++k) {
                         const double ang = -2.0 * M_PI * (double)k / (double)n;
@@ -477,7 +461,7 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
                     ClassTimer t(ctx, st, B2S_K_DWT_FWD, 1, l);
                     const B2sImg in = l == 1 ? padded : img_of(pl, s.sub[l - 1][0], l - 1);
                     b2s_launch_dwt_fwd(pl->taps, in, img_of(pl, s.sub[l][0], l), img_of(pl, s.sub[l][1], l),
-                                       img_of(pl, s.sub[l][2], l), img_of(pl, s.sub[l][3], l), nb, exact, st);
+                                       img_of(pl, s.sub[l][2], l), img_of(pl, s.sub[l][3], l), nb, exact, ctx->sm_count, st);
                 }
             }
             if (p.debug_stop_after == B2S_STAGE_FORWARD) return B2S_OK;
@@ -498,7 +482,7 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
                     // the reconstruction of level l-1 overwrites that level's approximation buffer (or the padded image)
                     B2sImg out = l == 1 ? padded : img_of(pl, s.sub[l - 1][0], l - 1);
                     b2s_launch_dwt_inv(pl->taps, img_of(pl, s.sub[l][0], l), img_of(pl, s.sub[l][1], l),
-                                       img_of(pl, s.sub[l][2], l), img_of(pl, s.sub[l][3], l), out, nb, exact, st);
+                                       img_of(pl, s.sub[l][2], l), img_of(pl, s.sub[l][3], l), out, nb, exact, ctx->sm_count, st);
                 }
             }
         }

@@ -70,11 +70,11 @@ void b2s_launch_math(int which, const float *in, float *out, int64_t n, cudaStre
 // dwt.cu --------------------------------------------------------------------------------------------------------
 // forward level: in (ny x nx) -> cA,cH,cV,cD ((ny+F-1)/2 x (nx+F-1)/2); exact!=0 => reference summation order, no FMA
 void b2s_launch_dwt_fwd(const B2sTaps &t, const B2sImg &in, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV,
-                        const B2sImg &cD, int n_planes, int exact, cudaStream_t s);
+                        const B2sImg &cD, int n_planes, int exact, int sm_count, cudaStream_t s);
 // inverse level: sub-bands (my x mx; cA is read with that logical size) -> out (first out.rows x out.cols of the
 // 2*my-F+2 x 2*mx-F+2 reconstruction)
 void b2s_launch_dwt_inv(const B2sTaps &t, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV, const B2sImg &cD,
-                        const B2sImg &out, int n_planes, int exact, cudaStream_t s);
+                        const B2sImg &out, int n_planes, int exact, int sm_count, cudaStream_t s);
 int b2s_dwt_max_smem(int F);
 
 // fft.cu --------------------------------------------------------------------------------------------------------
@@ -82,8 +82,11 @@ struct B2sFftPlan {      // per transform length n
     int n;
     int n_factors;
     int factors[32];
+    int group;           // sequence pairs transformed together by one CTA
+    int has_large;       // a prime factor > 43 is present
     float2 *d_twiddle;   // n entries exp(-2 pi i k / n)
 };
+void b2s_fft_plan_init(B2sFftPlan *fp, int n);   // factorisation + batching; d_twiddle is left to the caller
 // rows x n image; transform along the contiguous axis when along_cols == 0, along the row index otherwise.
 // d_notch: n floats multiplying the packed (fftpack) spectrum; result overwrites the image.
 void b2s_launch_notch(const B2sFftPlan &fp, const float *d_notch, const B2sImg &img, int along_cols, int n_planes,

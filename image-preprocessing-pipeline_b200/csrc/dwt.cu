@@ -8,258 +8,410 @@
 // for the low-pass branch, then the high-pass branch, then one add).  axis -2 (rows index) is analysed first and
 // synthesised last, as pywt's dwtn / idwtn do.
 //
-// One CTA computes a TY x TX tile of all four sub-bands: the (2TY+F-2) x (2TX+F-2) input window is staged in shared
-// memory with the half-sample symmetric extension resolved at load time, the axis -2 pass writes its two
-// half-height images to a second shared buffer, the axis -1 pass reads them with conflict-free 128-bit shared loads
-// and stores 128-bit coalesced rows.  No intermediate ever goes to HBM.
+// sm_100a design (the stage is FP32-issue bound, not HBM bound: 2F MACs per sample and pass)
+//   * one CTA computes a TY x TX tile of all four sub-bands: the (2TY+F-2) x (2TX+F-2) input window is staged in
+//     shared memory (128-bit coalesced loads; the half-sample symmetric extension is resolved at load time), the
+//     axis -2 pass writes its two half-height images to a second shared buffer, the axis -1 pass reads them with
+//     conflict-free 128-bit shared loads and stores 128-bit rows.  No intermediate goes to HBM.
+//   * every thread owns R consecutive outputs and keeps the 2R+J-2 samples they need in registers, so one shared
+//     load feeds ~6 MACs.
+//   * the two outputs that share an input sample — (low, high) in the analysis, (even, odd) in the synthesis — are
+//     computed together with packed f32x2 instructions (FFMA2 / FADD2 with a scalar-broadcast operand).  Packed
+//     instructions have the same MAC rate as scalar ones on sm_100 but need half the issue slots, which leaves the
+//     other half for the shared-memory loads, address arithmetic and stores: the FP32 pipe stays the only limiter.
+//   * exact mode: ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even under -fmad=false, so the unfused product is
+//     formed as fma(t, v, -0.0) with the -0.0 passed as a kernel argument (opaque to the compiler):
+//     round(t*v - 0) == round(t*v) for every input, signed zeros included.
+//   * filters longer than 20 taps (coif15 has 90) run the same code in chunks of J taps (taps are zero-padded to a
+//     multiple of J; adding an exact zero product never changes a float32 sum), so registers stay bounded.
+#include <cstdlib>
+
 #include "b2s_internal.h"
 
 namespace {
 
-constexpr int kNT = 256;
-// forward tile: TY x TX outputs per sub-band, each thread RY (axis -2 pass) / RX (axis -1 pass) consecutive outputs
-constexpr int kTY = 32, kTX = 64, kRY = 4, kRX = 4;
-// inverse tile: TQ x TP coefficient positions -> 2TQ x 2TP outputs
-constexpr int kTQ = 32, kTP = 64;
+constexpr int kR = 4;                 // consecutive outputs per thread and pass
+constexpr int kMaxFp = 160;           // padded analysis filter length bound (B2S_MAX_TAPS rounded up to a chunk)
+constexpr int kSmemPerSm = 227 * 1024;
 
-__host__ __device__ inline int pitch_mod8_is4(int n)  // >= n, multiple of 4, (p/4) odd
+// tile shapes.  Forward: TY x TX outputs per sub-band; inverse: TY x TX coefficient positions -> 2TY x 2TX outputs.
+template <int TY_, int TX_, int NT_, int STAGES_>
+struct Tile {
+    static constexpr int TY = TY_, TX = TX_, NT = NT_, NW = NT_ / 32, STAGES = STAGES_;
+    static_assert(TY_ % 4 == 0 && TX_ % 16 == 0 && NT_ % 32 == 0, "tile shape");
+};
+
+__host__ __device__ inline int round_up4(int n) { return (n + 3) & ~3; }
+__host__ __device__ inline int pitch_quads_odd(int n)  // >= n, multiple of 4, (p/4) odd
 {
-    int p = (n + 3) & ~3;
+    int p = round_up4(n);
     if (((p >> 2) & 1) == 0) p += 4;
     return p;
 }
-__host__ __device__ inline int pitch_mod32_is16(int n)  // >= n, multiple of 4, (p/4) % 8 == 4
+__host__ __device__ inline int pitch_quads_4mod8(int n)  // >= n, multiple of 4, (p/4) % 8 == 4
 {
-    int p = (n + 3) & ~3;
+    int p = round_up4(n);
     while (((p >> 2) & 7) != 4) p += 4;
     return p;
 }
 
+struct FwdTaps { float2 t[kMaxFp]; };                          // (dec_lo[j], dec_hi[j]), zero beyond F
+struct InvTaps { float2 lo[kMaxFp / 2], hi[kMaxFp / 2]; };     // (rec[2j], rec[2j+1]), zero beyond F/2
+
+// geometry of the shared-memory tiles for a padded filter length Fp (forward) / Hp = padded F/2 (inverse)
+// one or two input stages (two: the next tile is fetched while the current one is computed) + one intermediate buffer
 struct FwdGeom {
-    int rin_y, rin_x, pitch;
-    __host__ __device__ explicit FwdGeom(int F)
+    int rin_y, rin_x, pin, pmid, stage_floats, mid_floats;
+    __host__ __device__ FwdGeom(int Fp, int TY, int TX)
     {
-        rin_y = 2 * kTY + F - 2;
-        rin_x = 2 * kTX + F - 2;
-        pitch = pitch_mod8_is4(rin_x + 2);
+        rin_y = 2 * TY + Fp - 2;
+        rin_x = 2 * TX + Fp - 2;
+        pin = round_up4(rin_x + 2) + 4;        // + alignment offset (0 or 2) of the tile's first column
+        pmid = pitch_quads_odd(rin_x);
+        stage_floats = rin_y * pin;
+        mid_floats = 2 * TY * pmid;
     }
-    __host__ __device__ size_t smem_floats() const { return (size_t)(rin_y + 2 * kTY) * pitch + 8; }
+    __host__ __device__ size_t smem_bytes(int stages) const { return sizeof(float) * ((size_t)stages * stage_floats + mid_floats); }
 };
-
 struct InvGeom {
-    int H, rq, rp, ps, pm;
-    __host__ __device__ explicit InvGeom(int F)
+    int rq, rp, ps, pm, sub_floats, stage_floats, mid_floats;
+    __host__ __device__ InvGeom(int Hp, int TQ, int TP)
     {
-        H = F / 2;
-        rq = kTQ + H - 1;
-        rp = kTP + H - 1;
-        ps = pitch_mod32_is16(rp + 3);
-        pm = pitch_mod8_is4(2 * kTP);
+        rq = TQ + Hp - 1;
+        rp = TP + Hp - 1;
+        ps = pitch_quads_4mod8(rp);
+        pm = pitch_quads_odd(2 * TP);
+        sub_floats = rq * ps;
+        stage_floats = 4 * sub_floats;
+        mid_floats = 2 * rq * pm;
     }
-    __host__ __device__ size_t smem_floats() const { return (size_t)4 * rq * ps + (size_t)2 * rq * pm + 8; }
+    __host__ __device__ size_t smem_bytes(int stages) const { return sizeof(float) * ((size_t)stages * stage_floats + mid_floats); }
 };
 
-__device__ __forceinline__ int sym_ext(int i, int n)
+__device__ __forceinline__ int sym_ext(int i, int n)  // half-sample symmetric extension, any i
 {
+    if (i >= 0 && i < n) return i;
     const int p = 2 * n;
     int t = i % p;
     if (t < 0) t += p;
     return t < n ? t : p - 1 - t;
 }
 
-template <bool EXACT>
-__device__ __forceinline__ float mac(float acc, float a, float b)
+// asynchronous global -> shared copies (LDGSTS): a thread issues its whole share of the tile without waiting
+__device__ __forceinline__ void cp_async16(float *dst, const float *src)
 {
-    if (EXACT) return __fadd_rn(acc, __fmul_rn(a, b));  // never contracted into an FMA
-    return fmaf(a, b, acc);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float *dst, const float *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// (t.x, t.y) * v, rounded once per lane: see the header for why this is not __fmul2_rn
+__device__ __forceinline__ float2 mul2_exact(float2 t, float v, float2 nz) { return __ffma2_rn(t, make_float2(v, v), nz); }
+
+__device__ __forceinline__ float mac1_exact(float acc, float a, float b) { return __fadd_rn(acc, __fmul_rn(a, b)); }
+
+// "acc (+)= t * (v, v)" on an output pair.  Exact: unfused multiply then add (the reference's rounding); fast: one FMA.
+// (Measured on B200: scalar FMUL/FADD or FFMA variants of the same loops are no faster than the packed ones.)
+enum { kExact = 0, kFast = 1 };
+template <int MODE>
+__device__ __forceinline__ void mac_pair(float2 &acc, float2 t, float v, float2 nz, bool first)
+{
+    if (MODE == kExact) {
+        const float2 p = mul2_exact(t, v, nz);
+        acc = first ? p : __fadd2_rn(acc, p);
+    } else {
+        acc = first ? __fmul2_rn(t, make_float2(v, v)) : __ffma2_rn(t, make_float2(v, v), acc);
+    }
+}
+
+// ---- R consecutive analysis outputs from a register window -----------------------------------------------------
+// out[r] = sum_j taps[j] * x[2r + Fp-1 - j], j ascending; x = `base` with element stride `stride` (VEC: stride 1,
+// 16-byte aligned base, 128-bit loads).
+template <int J, bool MULTI, int MODE, bool VEC>
+__device__ __forceinline__ void analysis_run(const float *base, int stride, const float2 *__restrict__ taps, int nch,
+                                             int Fp, float2 nz, float2 (&acc)[kR])
+{
+    constexpr int W = 2 * kR + J - 2;
+    constexpr int W4 = (W + 3) / 4;
+    float w[W4 * 4];
+    if (!MULTI) {
+        if (VEC) {
+#pragma unroll
+            for (int k = 0; k < W4; ++k) {
+                const float4 v = *reinterpret_cast<const float4 *>(base + 4 * k);
+                w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < W; ++k) w[k] = base[k * stride];
+        }
+#pragma unroll
+        for (int jj = 0; jj < J; ++jj) {
+            const float2 t = taps[jj];
+#pragma unroll
+            for (int r = 0; r < kR; ++r) {
+                mac_pair<MODE>(acc[r], t, w[2 * r + J - 1 - jj], nz, jj == 0);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < kR; ++r) acc[r] = make_float2(0.f, 0.f);
+        for (int c = 0; c < nch; ++c) {
+            const float *b = base + (Fp - (c + 1) * J) * stride;   // multiple of 4 elements (J % 4 == 0)
+            if (VEC) {
+#pragma unroll
+                for (int k = 0; k < W4; ++k) {
+                    const float4 v = *reinterpret_cast<const float4 *>(b + 4 * k);
+                    w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < W; ++k) w[k] = b[k * stride];
+            }
+            const float2 *tc = taps + c * J;
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) {
+                const float2 t = tc[jj];
+#pragma unroll
+                for (int r = 0; r < kR; ++r) {
+                    mac_pair<MODE>(acc[r], t, w[2 * r + J - 1 - jj], nz, false);
+                }
+            }
+        }
+    }
 }
 
 // analysis output whose window overhangs the right edge (i = 2o+1 >= n): pywt visits the reflected part with the
-// filter index descending from i-n to 0, then the in-range part ascending.  `w` points at the extended sample that
-// pairs with tap 0 (stride between samples = step, towards lower indices for higher taps).
-template <bool EXACT>
-__device__ __forceinline__ float analysis_right_edge(const float *filt, int F, const float *w0, int step, int over)
+// filter index descending from i-n to 0, then the in-range part ascending.  `w0` points at the extended sample that
+// pairs with tap 0; higher taps pair with samples `step` floats lower.
+__device__ __forceinline__ float2 analysis_right_edge(const FwdTaps &taps, int F, const float *w0, int step, int over)
 {
-    float s = 0.f;
+    float lo = 0.f, hi = 0.f;
+#pragma unroll 1
     for (int t = 0; t < F; ++t) {
         const int j = (t <= over) ? (over - t) : t;
-        s = mac<EXACT>(s, filt[j], w0[-j * step]);
+        const float2 f = taps.t[j];
+        const float v = w0[-j * step];
+        lo = mac1_exact(lo, f.x, v);
+        hi = mac1_exact(hi, f.y, v);
     }
-    return s;
+    return make_float2(lo, hi);
+}
+
+// ---- R consecutive synthesis positions -> R (even, odd) output pairs ---------------------------------------------
+// pair[cc] = sum_j lo[j] * a[cc + Hp-1 - j]  (+)  sum_j hi[j] * d[cc + Hp-1 - j], each sum j ascending, one final add.
+template <int JH, bool MULTI, int MODE, bool VEC>
+__device__ __forceinline__ void synthesis_run(const float *pa, const float *pd, int stride, const float2 *__restrict__ tlo,
+                                              const float2 *__restrict__ thi, int nch, int Hp, float2 nz, float2 (&out)[kR])
+{
+    constexpr int W = kR + JH - 1;
+    constexpr int W4 = (W + 3) / 4;
+    float wa[W4 * 4], wd[W4 * 4];
+    float2 sl[kR], sh[kR];
+    if (!MULTI) {
+        if (VEC) {
+#pragma unroll
+            for (int k = 0; k < W4; ++k) {
+                const float4 v = *reinterpret_cast<const float4 *>(pa + 4 * k);
+                wa[4 * k] = v.x; wa[4 * k + 1] = v.y; wa[4 * k + 2] = v.z; wa[4 * k + 3] = v.w;
+                const float4 u = *reinterpret_cast<const float4 *>(pd + 4 * k);
+                wd[4 * k] = u.x; wd[4 * k + 1] = u.y; wd[4 * k + 2] = u.z; wd[4 * k + 3] = u.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < W; ++k) { wa[k] = pa[k * stride]; wd[k] = pd[k * stride]; }
+        }
+#pragma unroll
+        for (int jj = 0; jj < JH; ++jj) {
+            const float2 fl = tlo[jj], fh = thi[jj];
+#pragma unroll
+            for (int cc = 0; cc < kR; ++cc) {
+                mac_pair<MODE>(sl[cc], fl, wa[cc + JH - 1 - jj], nz, jj == 0);
+                mac_pair<MODE>(sh[cc], fh, wd[cc + JH - 1 - jj], nz, jj == 0);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int cc = 0; cc < kR; ++cc) { sl[cc] = make_float2(0.f, 0.f); sh[cc] = make_float2(0.f, 0.f); }
+        for (int c = 0; c < nch; ++c) {
+            const int b = (Hp - (c + 1) * JH) * stride;
+            if (VEC) {
+#pragma unroll
+                for (int k = 0; k < W4; ++k) {
+                    const float4 v = *reinterpret_cast<const float4 *>(pa + b + 4 * k);
+                    wa[4 * k] = v.x; wa[4 * k + 1] = v.y; wa[4 * k + 2] = v.z; wa[4 * k + 3] = v.w;
+                    const float4 u = *reinterpret_cast<const float4 *>(pd + b + 4 * k);
+                    wd[4 * k] = u.x; wd[4 * k + 1] = u.y; wd[4 * k + 2] = u.z; wd[4 * k + 3] = u.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < W; ++k) { wa[k] = pa[b + k * stride]; wd[k] = pd[b + k * stride]; }
+            }
+            const float2 *cl = tlo + c * JH, *ch = thi + c * JH;
+#pragma unroll
+            for (int jj = 0; jj < JH; ++jj) {
+                const float2 fl = cl[jj], fh = ch[jj];
+#pragma unroll
+                for (int cc = 0; cc < kR; ++cc) {
+                    mac_pair<MODE>(sl[cc], fl, wa[cc + JH - 1 - jj], nz, false);
+                    mac_pair<MODE>(sh[cc], fh, wd[cc + JH - 1 - jj], nz, false);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int cc = 0; cc < kR; ++cc) out[cc] = __fadd2_rn(sl[cc], sh[cc]);
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int F_, bool EXACT>
-__global__ void __launch_bounds__(kNT, 2)
-k_dwt_fwd(const B2sTaps taps, const B2sImg in, const B2sImg cA, const B2sImg cH, const B2sImg cV, const B2sImg cD)
+struct FwdArgs {
+    B2sImg in, cA, cH, cV, cD;
+    int F, Fp, nch;
+    int tiles_x, tiles_y, n_tiles;
+    float negzero;   // -0.0f, deliberately a run-time value (see mul2_exact)
+};
+
+// Persistent CTAs: each walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the window of the next tile is
+// copied (cp.async) into the other shared stage while the current tile is computed.
+template <class T, int J, bool MULTI, int MODE>
+__global__ void __launch_bounds__(T::NT) k_dwt_fwd(const __grid_constant__ FwdTaps taps, const FwdArgs a)
 {
     extern __shared__ __align__(16) float smem[];
-    const int F = F_ > 0 ? F_ : taps.F;
-    const FwdGeom g(F);
-    const int P = g.pitch;
-    float *s_in = smem;
-    float *s_mid = smem + (size_t)g.rin_y * P;
+    constexpr int TY = T::TY, TX = T::TX, NT = T::NT, NW = T::NW, STAGES = T::STAGES;
+    constexpr bool EXACT = MODE == kExact;
+    const int Fp = MULTI ? a.Fp : J;
+    const FwdGeom g(Fp, TY, TX);
+    const int PIN = g.pin, PM = g.pmid;
+    float *s_mid = smem + STAGES * g.stage_floats;
 
-    const int tid = threadIdx.x;
-    const int oy0 = blockIdx.y * kTY, ox0 = blockIdx.x * kTX;
-    const int ny = in.rows, nx = in.cols;
-    const int my = cA.rows, mx = cA.cols;
-    const float *src = in.ptr + (size_t)blockIdx.z * in.plane_stride;
-    const int gy0 = 2 * oy0 - F + 2, gx0 = 2 * ox0 - F + 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ny = a.in.rows, nx = a.in.cols;
+    const int my = a.cA.rows, mx = a.cA.cols;
+    const int off = (2 - Fp) & 3;             // tile column origin 2*ox0 + 2 - Fp modulo 4 (ox0 is a multiple of 16)
+    const int c4n = (g.rin_x + off + 3) >> 2;
+    const float2 nz = make_float2(a.negzero, a.negzero);
+    const int tiles_xy = a.tiles_x * a.tiles_y;
 
-    // ---- stage the extended input window
-    {
-        const bool x_inside = gx0 >= 0 && gx0 + g.rin_x <= nx;
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int ry = warp; ry < g.rin_y; ry += kNT / 32) {
-            const int sy = sym_ext(gy0 + ry, ny);
-            const float *srow = src + (size_t)sy * in.pitch;
-            float *drow = s_in + ry * P;
-            if (x_inside) {
-                for (int rx = lane; rx < g.rin_x; rx += 32) drow[rx] = __ldg(srow + gx0 + rx);
-            } else {
-                for (int rx = lane; rx < g.rin_x; rx += 32) drow[rx] = __ldg(srow + sym_ext(gx0 + rx, nx));
+    // stage the input window of tile t (symmetric extension resolved here); asynchronous, one commit group
+    auto issue_load = [&](int t, float *s_in) {
+        const int plane = t / tiles_xy;
+        const int r2 = t - plane * tiles_xy;
+        const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
+        const int gy0 = 2 * ty * TY + 2 - Fp;            // image row of shared row 0
+        const int gx0a = (2 * tx * TX + 2 - Fp) & ~3;    // 16-byte aligned image column of shared column 0
+        const float *src = a.in.ptr + (size_t)plane * a.in.plane_stride;
+        if (gy0 >= 0 && gy0 + g.rin_y <= ny && gx0a >= 0 && gx0a + 4 * c4n <= nx) {
+            // interior tile: every quad is one aligned 16-byte copy, no per-element tests
+            const float *src0 = src + (size_t)gy0 * a.in.pitch + gx0a;
+            const int nq = g.rin_y * c4n;
+#pragma unroll 4
+            for (int q = tid; q < nq; q += NT) {
+                const int r = q / c4n, c4 = q - r * c4n;
+                cp_async16(s_in + r * PIN + 4 * c4, src0 + (size_t)r * a.in.pitch + 4 * c4);
+            }
+        } else {
+            for (int r = warp; r < g.rin_y; r += NW) {
+                const float *srow = src + (size_t)sym_ext(gy0 + r, ny) * a.in.pitch;
+                float *drow = s_in + r * PIN;
+                for (int c4 = lane; c4 < c4n; c4 += 32) {
+                    const int gx = gx0a + 4 * c4;
+                    if (gx >= 0 && gx + 3 < nx) {
+                        cp_async16(drow + 4 * c4, srow + gx);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) cp_async4(drow + 4 * c4 + k, srow + sym_ext(gx + k, nx));
+                    }
+                }
             }
         }
-    }
-    __syncthreads();
+        cp_async_commit();
+    };
 
-    // ---- axis -2 (rows index) pass: s_in -> s_mid[0..TY) = low-pass rows, s_mid[TY..2TY) = high-pass rows
-    {
-        constexpr int NGY = kTY / kRY;
-        const int items = NGY * g.rin_x;
-        for (int it = tid; it < items; it += kNT) {
-            const int gy = it / g.rin_x;
-            const int rx = it - gy * g.rin_x;
-            const float *col = s_in + (2 * kRY * gy) * P + rx;
-            float lo[kRY], hi[kRY];
-            if (F_ > 0) {
-                constexpr int FW = F_ > 0 ? F_ : 2;
-                float w[2 * kRY + FW - 2];
+    int t = blockIdx.x;
+    if (STAGES == 2 && t < a.n_tiles) issue_load(t, smem);
+    for (int it = 0; t < a.n_tiles; t += gridDim.x, ++it) {
+        const float *s_in = smem + (STAGES == 2 ? (it & 1) : 0) * g.stage_floats;
+        const int tn = t + gridDim.x;
+        if (STAGES == 2 && tn < a.n_tiles) {
+            issue_load(tn, smem + ((it + 1) & 1) * g.stage_floats);   // that stage was last read before the previous barrier
+            cp_async_wait_group<1>();
+        } else {
+            if (STAGES == 1) issue_load(t, smem);   // the single stage was last read before the previous barrier
+            cp_async_wait_group<0>();
+        }
+        __syncthreads();   // tile t has landed; every warp is done with s_mid of the previous tile
+
+        const int plane = t / tiles_xy;
+        const int r2 = t - plane * tiles_xy;
+        const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
+        const int oy0 = ty * TY, ox0 = tx * TX;
+        // does this tile hold outputs whose window overhangs the bottom / right edge (the reference visits their taps
+        // in another order, see analysis_right_edge)?
+        const bool edge_y = 2 * (oy0 + TY) - 1 >= ny, edge_x = 2 * (ox0 + TX) - 1 >= nx;
+
+        // ---- axis -2 (rows index) pass: s_in -> s_mid[0..TY) = low-pass rows, s_mid[TY..2TY) = high-pass rows
+        {
+            const int ncg = (g.rin_x + 31) >> 5;
+            for (int wi = warp; wi < (TY / kR) * ncg; wi += NW) {
+                const int gy = wi / ncg;
+                const int c = (wi - gy * ncg) * 32 + lane;
+                if (c >= g.rin_x) continue;
+                const float *col = s_in + (2 * kR * gy) * PIN + c + off;
+                float2 acc[kR];
+                analysis_run<J, MULTI, MODE, false>(col, PIN, taps.t, a.nch, Fp, nz, acc);
+                if (EXACT && edge_y) {
 #pragma unroll
-                for (int t = 0; t < 2 * kRY + FW - 2; ++t) w[t] = col[t * P];
-#pragma unroll
-                for (int r = 0; r < kRY; ++r) {
-                    float a = 0.f, d = 0.f;
-#pragma unroll
-                    for (int j = 0; j < FW; ++j) {
-                        const float v = w[2 * r + FW - 1 - j];
-                        a = mac<EXACT>(a, taps.dec_lo[j], v);
-                        d = mac<EXACT>(d, taps.dec_hi[j], v);
-                    }
-                    lo[r] = a;
-                    hi[r] = d;
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < kRY; ++r) {
-                    float a = 0.f, d = 0.f;
-                    const float *w0 = col + (2 * r + F - 1) * P;
-                    for (int j = 0; j < F; ++j) {
-                        const float v = w0[-j * P];
-                        a = mac<EXACT>(a, taps.dec_lo[j], v);
-                        d = mac<EXACT>(d, taps.dec_hi[j], v);
-                    }
-                    lo[r] = a;
-                    hi[r] = d;
-                }
-            }
-            if (EXACT) {
-#pragma unroll
-                for (int r = 0; r < kRY; ++r) {
-                    const int i = 2 * (oy0 + kRY * gy + r) + 1;
-                    if (i >= ny && i - ny <= F - 2) {
-                        const float *w0 = col + (2 * r + F - 1) * P;
-                        lo[r] = analysis_right_edge<true>(taps.dec_lo, F, w0, P, i - ny);
-                        hi[r] = analysis_right_edge<true>(taps.dec_hi, F, w0, P, i - ny);
+                    for (int r = 0; r < kR; ++r) {
+                        const int i = 2 * (oy0 + kR * gy + r) + 1;
+                        if (i >= ny && i - ny <= a.F - 2)
+                            acc[r] = analysis_right_edge(taps, a.F, col + (2 * r + Fp - 1) * PIN, PIN, i - ny);
                     }
                 }
-            }
 #pragma unroll
-            for (int r = 0; r < kRY; ++r) {
-                s_mid[(kRY * gy + r) * P + rx] = lo[r];
-                s_mid[(kTY + kRY * gy + r) * P + rx] = hi[r];
+                for (int r = 0; r < kR; ++r) {
+                    s_mid[(kR * gy + r) * PM + c] = acc[r].x;
+                    s_mid[(TY + kR * gy + r) * PM + c] = acc[r].y;
+                }
             }
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // ---- axis -1 pass: each lane owns RX consecutive output columns of one s_mid row
-    {
-        const int warp = tid >> 5, lane = tid & 31;
-        const int gxl = lane & 3, rsub = lane >> 2;
-        constexpr int NGX = kTX / kRX;      // 16 column groups
-        constexpr int N_GB = NGX / 4;       // 4 group blocks
-        constexpr int N_RB = (2 * kTY) / 8; // 8 row blocks
-        float *pA = cA.ptr + (size_t)blockIdx.z * cA.plane_stride;
-        float *pH = cH.ptr + (size_t)blockIdx.z * cH.plane_stride;
-        float *pV = cV.ptr + (size_t)blockIdx.z * cV.plane_stride;
-        float *pD = cD.ptr + (size_t)blockIdx.z * cD.plane_stride;
-        for (int wi = warp; wi < N_RB * N_GB; wi += kNT / 32) {
-            const int rb = wi / N_GB, gb = wi - rb * N_GB;
-            const int rm = rb * 8 + rsub;
-            const int gx = gb * 4 + gxl;
-            const float *row = s_mid + rm * P + 2 * kRX * gx;
-            float a[kRX], d[kRX];
-            if (F_ > 0) {
-                constexpr int FW = F_ > 0 ? F_ : 2;
-                constexpr int NW = (2 * kRX + FW - 2 + 3) / 4;
-                float w[NW * 4];
+        // ---- axis -1 pass: a warp covers 8 rows x 4 column groups (conflict-free 128-bit window loads, PM/4 odd)
+        {
+            const int gxl = lane & 3, rsub = lane >> 2;
+            constexpr int N_GB = TX / kR / 4;
+            constexpr int N_RB = (2 * TY) / 8;
+            float *pA = a.cA.ptr + (size_t)plane * a.cA.plane_stride;
+            float *pH = a.cH.ptr + (size_t)plane * a.cH.plane_stride;
+            float *pV = a.cV.ptr + (size_t)plane * a.cV.plane_stride;
+            float *pD = a.cD.ptr + (size_t)plane * a.cD.plane_stride;
+            for (int wi = warp; wi < N_RB * N_GB; wi += NW) {
+                const int rb = wi / N_GB, gb = wi - rb * N_GB;
+                const int rm = rb * 8 + rsub;
+                const int gx = gb * 4 + gxl;
+                const float *row = s_mid + rm * PM + 2 * kR * gx;
+                float2 acc[kR];
+                analysis_run<J, MULTI, MODE, true>(row, 1, taps.t, a.nch, Fp, nz, acc);
+                const int oxb = ox0 + kR * gx;
+                if (EXACT && edge_x) {
 #pragma unroll
-                for (int t = 0; t < NW; ++t) {
-                    const float4 v = *reinterpret_cast<const float4 *>(row + 4 * t);
-                    w[4 * t] = v.x; w[4 * t + 1] = v.y; w[4 * t + 2] = v.z; w[4 * t + 3] = v.w;
-                }
-#pragma unroll
-                for (int c = 0; c < kRX; ++c) {
-                    float sa = 0.f, sd = 0.f;
-#pragma unroll
-                    for (int j = 0; j < FW; ++j) {
-                        const float v = w[2 * c + FW - 1 - j];
-                        sa = mac<EXACT>(sa, taps.dec_lo[j], v);
-                        sd = mac<EXACT>(sd, taps.dec_hi[j], v);
-                    }
-                    a[c] = sa;
-                    d[c] = sd;
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < kRX; ++c) {
-                    float sa = 0.f, sd = 0.f;
-                    const float *w0 = row + 2 * c + F - 1;
-                    for (int j = 0; j < F; ++j) {
-                        const float v = w0[-j];
-                        sa = mac<EXACT>(sa, taps.dec_lo[j], v);
-                        sd = mac<EXACT>(sd, taps.dec_hi[j], v);
-                    }
-                    a[c] = sa;
-                    d[c] = sd;
-                }
-            }
-            const int oxb = ox0 + kRX * gx;
-            if (EXACT) {
-#pragma unroll
-                for (int c = 0; c < kRX; ++c) {
-                    const int i = 2 * (oxb + c) + 1;
-                    if (i >= nx && i - nx <= F - 2) {
-                        const float *w0 = row + 2 * c + F - 1;
-                        a[c] = analysis_right_edge<true>(taps.dec_lo, F, w0, 1, i - nx);
-                        d[c] = analysis_right_edge<true>(taps.dec_hi, F, w0, 1, i - nx);
+                    for (int cc = 0; cc < kR; ++cc) {
+                        const int i = 2 * (oxb + cc) + 1;
+                        if (i >= nx && i - nx <= a.F - 2)
+                            acc[cc] = analysis_right_edge(taps, a.F, row + 2 * cc + Fp - 1, 1, i - nx);
                     }
                 }
-            }
-            const bool low_rows = rm < kTY;
-            const int oy = oy0 + (low_rows ? rm : rm - kTY);
-            if (oy < my && oxb < mx) {
-                float *da = (low_rows ? pA : pH) + (size_t)oy * cA.pitch + oxb;  // all four share pitch
-                float *dd = (low_rows ? pV : pD) + (size_t)oy * cA.pitch + oxb;
-                if (oxb + kRX <= mx) {
-                    *reinterpret_cast<float4 *>(da) = make_float4(a[0], a[1], a[2], a[3]);
-                    *reinterpret_cast<float4 *>(dd) = make_float4(d[0], d[1], d[2], d[3]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < kRX; ++c)
-                        if (oxb + c < mx) { da[c] = a[c]; dd[c] = d[c]; }
+                const bool low_rows = rm < TY;
+                const int oy = oy0 + (low_rows ? rm : rm - TY);
+                if (oy < my && oxb < mx) {   // pitch is a multiple of 4, so a whole float4 always fits
+                    const size_t o = (size_t)oy * a.cA.pitch + oxb;     // the four sub-bands share pitch
+                    *reinterpret_cast<float4 *>((low_rows ? pA : pH) + o) = make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
+                    *reinterpret_cast<float4 *>((low_rows ? pV : pD) + o) = make_float4(acc[0].y, acc[1].y, acc[2].y, acc[3].y);
                 }
             }
         }
@@ -267,211 +419,303 @@ k_dwt_fwd(const B2sTaps taps, const B2sImg in, const B2sImg cA, const B2sImg cH,
 }
 
 // ------------------------------------------------------------------------------------------------ inverse
-template <int F_, bool EXACT>
-__global__ void __launch_bounds__(kNT, 2)
-k_dwt_inv(const B2sTaps taps, const B2sImg cA, const B2sImg cH, const B2sImg cV, const B2sImg cD, const B2sImg out)
+struct InvArgs {
+    B2sImg cA, cH, cV, cD, out;
+    int H, Hp, nch;
+    int tiles_x, tiles_y, n_tiles;
+    float negzero;
+};
+
+template <class T, int JH, bool MULTI, int MODE>
+__global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTaps taps, const InvArgs a)
 {
     extern __shared__ __align__(16) float smem[];
-    const int F = F_ > 0 ? F_ : taps.F;
-    const InvGeom g(F);
-    const int H = g.H, PS = g.ps, PM = g.pm, RQ = g.rq, RP = g.rp;
-    float *s_sub = smem;                         // [4][RQ][PS] : 0 = cA, 1 = cV, 2 = cH, 3 = cD
-    float *s_mid = smem + (size_t)4 * RQ * PS;   // [2][RQ][PM] : 0 = a (from cA,cV), 1 = d (from cH,cD)
+    constexpr int TQ = T::TY, TP = T::TX, NT = T::NT, NW = T::NW, STAGES = T::STAGES;
+    const int Hp = MULTI ? a.Hp : JH;
+    const InvGeom g(Hp, TQ, TP);
+    const int PS = g.ps, PM = g.pm, RQ = g.rq;
+    const int sub_floats = g.sub_floats;
+    float *s_mid = smem + STAGES * g.stage_floats; // [2][RQ][PM]: a (from cA,cV), d (from cH,cD)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.y * kTQ, p0 = blockIdx.x * kTP;
-    const int my = cH.rows, mx = cH.cols;
+    const int my = a.cH.rows, mx = a.cH.cols;
+    const float2 nz = make_float2(a.negzero, a.negzero);
+    const int tiles_xy = a.tiles_x * a.tiles_y;
+    const int c4n = (g.rp + 3) >> 2;
 
-    // ---- stage the four sub-band windows (zero beyond the sub-band: only feeds outputs that are not stored)
-    {
-        const float *base[4] = {cA.ptr + (size_t)blockIdx.z * cA.plane_stride, cV.ptr + (size_t)blockIdx.z * cV.plane_stride,
-                                cH.ptr + (size_t)blockIdx.z * cH.plane_stride, cD.ptr + (size_t)blockIdx.z * cD.plane_stride};
-        const int pitch[4] = {cA.pitch, cV.pitch, cH.pitch, cD.pitch};
-        for (int r = warp; r < 4 * RQ; r += kNT / 32) {
-            const int sb = r / RQ, ry = r - sb * RQ;
-            const int y = q0 + ry;
-            float *drow = s_sub + (size_t)r * PS;
-            if (y < my) {
-                const float *srow = base[sb] + (size_t)y * pitch[sb] + p0;
-                for (int rx = lane; rx < PS; rx += 32) drow[rx] = (rx < RP && p0 + rx < mx) ? __ldg(srow + rx) : 0.f;
-            } else {
-                for (int rx = lane; rx < PS; rx += 32) drow[rx] = 0.f;
+    // stage the four coefficient windows of tile t as [cA, cV, cH, cD][RQ][PS]; everything outside the sub-band is
+    // zero (it only meets zero taps or outputs that are not stored)
+    auto issue_load = [&](int t, float *s_sub) {
+        const int plane = t / tiles_xy;
+        const int r2 = t - plane * tiles_xy;
+        const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
+        const int cy0 = ty * TQ + a.H - Hp, cx0 = tx * TP + a.H - Hp;   // coefficient coordinates of shared (0, 0)
+        const bool aligned = (cx0 & 3) == 0;
+        if (aligned && cy0 >= 0 && cy0 + RQ <= my && cx0 >= 0 && cx0 + 4 * c4n <= mx) {
+            const int nq = RQ * c4n;
+#pragma unroll
+            for (int sb = 0; sb < 4; ++sb) {
+                const B2sImg &im = sb == 0 ? a.cA : (sb == 1 ? a.cV : (sb == 2 ? a.cH : a.cD));
+                const float *src0 = im.ptr + (size_t)plane * im.plane_stride + (size_t)cy0 * im.pitch + cx0;
+                float *dst0 = s_sub + sb * sub_floats;
+#pragma unroll 2
+                for (int q = tid; q < nq; q += NT) {
+                    const int r = q / c4n, c4 = q - r * c4n;
+                    cp_async16(dst0 + r * PS + 4 * c4, src0 + (size_t)r * im.pitch + 4 * c4);
+                }
+            }
+        } else {
+            for (int r = warp; r < 4 * RQ; r += NW) {
+                const int sb = r / RQ, ry = r - sb * RQ;
+                const int y = cy0 + ry;
+                float *drow = s_sub + sb * sub_floats + ry * PS;
+                const bool row_ok = y >= 0 && y < my;
+                const B2sImg &im = sb == 0 ? a.cA : (sb == 1 ? a.cV : (sb == 2 ? a.cH : a.cD));
+                const float *srow = im.ptr + (size_t)plane * im.plane_stride + (size_t)(row_ok ? y : 0) * im.pitch;
+                for (int c4 = lane; c4 < c4n; c4 += 32) {
+                    const int x = cx0 + 4 * c4;
+                    if (row_ok && aligned && x >= 0 && x + 3 < mx) {
+                        cp_async16(drow + 4 * c4, srow + x);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (row_ok && x + k >= 0 && x + k < mx) cp_async4(drow + 4 * c4 + k, srow + x + k);
+                            else drow[4 * c4 + k] = 0.f;
+                        }
+                    }
+                }
             }
         }
-    }
-    __syncthreads();
+        cp_async_commit();
+    };
 
-    // ---- axis -1 synthesis: (cA,cV) -> a, (cH,cD) -> d   [idwtn handles the last axis first]
-    {
-        const int gxl = lane & 3, rsub = lane >> 2;
-        constexpr int N_GB = (kTP / kRX) / 4;  // 4
-        const int n_rb = (2 * RQ + 7) / 8;
-        for (int wi = warp; wi < n_rb * N_GB; wi += kNT / 32) {
-            const int rb = wi / N_GB, gb = wi - rb * N_GB;
-            const int rr = rb * 8 + rsub;
-            if (rr >= 2 * RQ) continue;
-            const int sel = rr >= RQ ? 1 : 0;
-            const int ry = rr - sel * RQ;
-            const int gx = gb * 4 + gxl;
-            const float *rl = s_sub + (size_t)((2 * sel) * RQ + ry) * PS + kRX * gx;
-            const float *rh = s_sub + (size_t)((2 * sel + 1) * RQ + ry) * PS + kRX * gx;
-            float o[2 * kRX];
-            if (F_ > 0) {
-                constexpr int HW = F_ > 0 ? F_ / 2 : 1;
-                constexpr int NW = (kRX + HW - 1 + 3) / 4;
-                float wl[NW * 4], wh[NW * 4];
-#pragma unroll
-                for (int t = 0; t < NW; ++t) {
-                    const float4 v = *reinterpret_cast<const float4 *>(rl + 4 * t);
-                    wl[4 * t] = v.x; wl[4 * t + 1] = v.y; wl[4 * t + 2] = v.z; wl[4 * t + 3] = v.w;
-                    const float4 u = *reinterpret_cast<const float4 *>(rh + 4 * t);
-                    wh[4 * t] = u.x; wh[4 * t + 1] = u.y; wh[4 * t + 2] = u.z; wh[4 * t + 3] = u.w;
-                }
-#pragma unroll
-                for (int c = 0; c < kRX; ++c) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        float sl = 0.f, sh = 0.f;
-#pragma unroll
-                        for (int j = 0; j < HW; ++j) sl = mac<EXACT>(sl, taps.rec_lo[2 * j + e], wl[c + HW - 1 - j]);
-#pragma unroll
-                        for (int j = 0; j < HW; ++j) sh = mac<EXACT>(sh, taps.rec_hi[2 * j + e], wh[c + HW - 1 - j]);
-                        o[2 * c + e] = __fadd_rn(sl, sh);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < kRX; ++c) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        float sl = 0.f, sh = 0.f;
-                        for (int j = 0; j < H; ++j) sl = mac<EXACT>(sl, taps.rec_lo[2 * j + e], rl[c + H - 1 - j]);
-                        for (int j = 0; j < H; ++j) sh = mac<EXACT>(sh, taps.rec_hi[2 * j + e], rh[c + H - 1 - j]);
-                        o[2 * c + e] = __fadd_rn(sl, sh);
-                    }
-                }
-            }
-            float *dst = s_mid + (size_t)(sel * RQ + ry) * PM + 2 * kRX * gx;
-            *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4 *>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    int t = blockIdx.x;
+    if (STAGES == 2 && t < a.n_tiles) issue_load(t, smem);
+    for (int it = 0; t < a.n_tiles; t += gridDim.x, ++it) {
+        const float *s_sub = smem + (STAGES == 2 ? (it & 1) : 0) * g.stage_floats;
+        const int tn = t + gridDim.x;
+        if (STAGES == 2 && tn < a.n_tiles) {
+            issue_load(tn, smem + ((it + 1) & 1) * g.stage_floats);
+            cp_async_wait_group<1>();
+        } else {
+            if (STAGES == 1) issue_load(t, smem);
+            cp_async_wait_group<0>();
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // ---- axis -2 synthesis: (a, d) -> out rows 2q, 2q+1
-    {
-        constexpr int NGQ = kTQ / kRY;
-        constexpr int OXW = 2 * kTP;
-        float *dst = out.ptr + (size_t)blockIdx.z * out.plane_stride;
-        for (int it = tid; it < NGQ * OXW; it += kNT) {
-            const int gq = it / OXW, x = it - gq * OXW;
-            const float *ca = s_mid + (size_t)(kRY * gq) * PM + x;
-            const float *cd = s_mid + (size_t)(RQ + kRY * gq) * PM + x;
-            float o[2 * kRY];
-            if (F_ > 0) {
-                constexpr int HW = F_ > 0 ? F_ / 2 : 1;
-                float wa[kRY + HW - 1], wd[kRY + HW - 1];
-#pragma unroll
-                for (int t = 0; t < kRY + HW - 1; ++t) { wa[t] = ca[t * PM]; wd[t] = cd[t * PM]; }
-#pragma unroll
-                for (int c = 0; c < kRY; ++c) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        float sl = 0.f, sh = 0.f;
-#pragma unroll
-                        for (int j = 0; j < HW; ++j) sl = mac<EXACT>(sl, taps.rec_lo[2 * j + e], wa[c + HW - 1 - j]);
-#pragma unroll
-                        for (int j = 0; j < HW; ++j) sh = mac<EXACT>(sh, taps.rec_hi[2 * j + e], wd[c + HW - 1 - j]);
-                        o[2 * c + e] = __fadd_rn(sl, sh);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < kRY; ++c) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        float sl = 0.f, sh = 0.f;
-                        for (int j = 0; j < H; ++j) sl = mac<EXACT>(sl, taps.rec_lo[2 * j + e], ca[(c + H - 1 - j) * PM]);
-                        for (int j = 0; j < H; ++j) sh = mac<EXACT>(sh, taps.rec_hi[2 * j + e], cd[(c + H - 1 - j) * PM]);
-                        o[2 * c + e] = __fadd_rn(sl, sh);
-                    }
-                }
-            }
-            const int ox = 2 * p0 + x;
-            if (ox < out.cols) {
-                const int oyb = 2 * (q0 + kRY * gq);
-#pragma unroll
-                for (int k = 0; k < 2 * kRY; ++k)
-                    if (oyb + k < out.rows) dst[(size_t)(oyb + k) * out.pitch + ox] = o[k];
+        const int plane = t / tiles_xy;
+        const int r2 = t - plane * tiles_xy;
+        const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
+        const int q0 = ty * TQ, p0 = tx * TP;
+
+        // ---- axis -1 synthesis: (cA,cV) -> a, (cH,cD) -> d   [idwtn handles the last axis first]
+        {
+            const int gxl = lane & 3, rsub = lane >> 2;
+            constexpr int N_GB = TP / kR / 4;
+            const int n_rb = (2 * RQ + 7) >> 3;
+            for (int wi = warp; wi < n_rb * N_GB; wi += NW) {
+                const int rb = wi / N_GB, gb = wi - rb * N_GB;
+                const int rr = rb * 8 + rsub;
+                if (rr >= 2 * RQ) continue;
+                const int sel = rr >= RQ ? 1 : 0;
+                const int ry = rr - sel * RQ;
+                const int gx = gb * 4 + gxl;
+                const float *rl = s_sub + (2 * sel) * sub_floats + ry * PS + kR * gx;
+                const float *rh = rl + sub_floats;
+                float2 o[kR];  // (even, odd) output pairs
+                synthesis_run<JH, MULTI, MODE, true>(rl, rh, 1, taps.lo, taps.hi, a.nch, Hp, nz, o);
+                float *dst = s_mid + (size_t)(sel * RQ + ry) * PM + 2 * kR * gx;
+                *reinterpret_cast<float4 *>(dst) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+                *reinterpret_cast<float4 *>(dst + 4) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
             }
         }
+        __syncthreads();
+
+        // ---- axis -2 synthesis: (a, d) -> out rows 2q, 2q+1
+        {
+            constexpr int NGQ = TQ / kR;
+            constexpr int NCG = (2 * TP) / 32;
+            float *dstp = a.out.ptr + (size_t)plane * a.out.plane_stride;
+            for (int wi = warp; wi < NGQ * NCG; wi += NW) {
+                const int gq = wi / NCG;
+                const int x = (wi - gq * NCG) * 32 + lane;
+                const float *ca = s_mid + (size_t)(kR * gq) * PM + x;
+                const float *cd = ca + (size_t)RQ * PM;
+                float2 o[kR];  // (row 2q, row 2q+1)
+                synthesis_run<JH, MULTI, MODE, false>(ca, cd, PM, taps.lo, taps.hi, a.nch, Hp, nz, o);
+                const int ox = 2 * p0 + x;
+                if (ox < a.out.cols) {
+                    const int oyb = 2 * (q0 + kR * gq);
+#pragma unroll
+                    for (int k = 0; k < kR; ++k) {
+                        if (oyb + 2 * k < a.out.rows) dstp[(size_t)(oyb + 2 * k) * a.out.pitch + ox] = o[k].x;
+                        if (oyb + 2 * k + 1 < a.out.rows) dstp[(size_t)(oyb + 2 * k + 1) * a.out.pitch + ox] = o[k].y;
+                    }
+                }
+            }
+        }
+        // the next iteration's barrier (after its wait) orders these s_mid reads before the next axis -1 pass
     }
 }
 
-template <typename K>
-void set_smem(K kernel, size_t bytes)
+// ---- chunk selection ----------------------------------------------------------------------------------------------
+// F <= 20: one chunk of J = F taps (everything compile-time).  Longer filters: chunks of J in {8,12,16,20} taps, the
+// choice that pads least (ties: the longer chunk).
+void pick_fwd_chunk(int F, int *J, int *nch)
 {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (F <= 20) { *J = F; *nch = 1; return; }
+    int best = 0, best_fp = 1 << 30;
+    for (int j : {8, 12, 16, 20}) {
+        const int fp = (F + j - 1) / j * j;
+        if (fp <= best_fp) { best_fp = fp; best = j; }
+    }
+    *J = best;
+    *nch = best_fp / best;
+}
+void pick_inv_chunk(int H, int *JH, int *nch)
+{
+    if (H <= 10) { *JH = H; *nch = 1; return; }
+    int best = 0, best_hp = 1 << 30;
+    for (int j : {4, 8, 12}) {
+        const int hp = (H + j - 1) / j * j;
+        if (hp <= best_hp) { best_hp = hp; best = j; }
+    }
+    *JH = best;
+    *nch = best_hp / best;
 }
 
-#define B2S_FOR_STATIC_F(X) X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20) X(24) X(30)
+// tile shapes.  Measured on B200 (db10, 2648^2, 8 planes): one tile per CTA with ~4 CTAs per SM (single stage) beats
+// persistent CTAs with two stages (2 CTAs per SM): 32 vs 42 us/plane for the level-1 analysis.  The two-stage variant
+// stays selectable (B2S_DWT_PERSIST=1) for tuning.
+typedef Tile<16, 64, 256, 2> FwdTileA;
+typedef Tile<32, 32, 256, 2> InvTileA;
+typedef Tile<16, 64, 256, 1> FwdTileS;
+typedef Tile<32, 32, 256, 1> InvTileS;
 
-template <int F, bool EXACT>
-void launch_fwd_t(const B2sTaps &t, const B2sImg &in, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV,
-                  const B2sImg &cD, int n_planes, cudaStream_t s)
+int dev_knob(const char *name, int dflt)
 {
-    const FwdGeom g(t.F);
-    const size_t bytes = g.smem_floats() * sizeof(float);
-    set_smem(k_dwt_fwd<F, EXACT>, bytes);
-    dim3 grid((cA.cols + kTX - 1) / kTX, (cA.rows + kTY - 1) / kTY, n_planes);
-    k_dwt_fwd<F, EXACT><<<grid, kNT, bytes, s>>>(t, in, cA, cH, cV, cD);
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
-template <int F, bool EXACT>
-void launch_inv_t(const B2sTaps &t, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV, const B2sImg &cD,
-                  const B2sImg &out, int n_planes, cudaStream_t s)
+template <class T, int J, bool MULTI, int MODE>
+void launch_fwd_t(const FwdTaps &ft, FwdArgs a, int n_planes, int sm_count, cudaStream_t s)
 {
-    const InvGeom g(t.F);
-    const size_t bytes = g.smem_floats() * sizeof(float);
-    set_smem(k_dwt_inv<F, EXACT>, bytes);
-    dim3 grid((out.cols + 2 * kTP - 1) / (2 * kTP), (out.rows + 2 * kTQ - 1) / (2 * kTQ), n_planes);
-    k_dwt_inv<F, EXACT><<<grid, kNT, bytes, s>>>(t, cA, cH, cV, cD, out);
+    const FwdGeom g(a.Fp, T::TY, T::TX);
+    const size_t bytes = g.smem_bytes(T::STAGES);
+    a.tiles_x = (a.cA.cols + T::TX - 1) / T::TX;
+    a.tiles_y = (a.cA.rows + T::TY - 1) / T::TY;
+    a.n_tiles = a.tiles_x * a.tiles_y * n_planes;
+    int per_sm = (int)(kSmemPerSm / (bytes + 1024));
+    if (per_sm > 2048 / T::NT) per_sm = 2048 / T::NT;
+    if (per_sm < 1) per_sm = 1;
+    const int grid = (T::STAGES == 1 || a.n_tiles < sm_count * per_sm) ? a.n_tiles : sm_count * per_sm;
+    cudaFuncSetAttribute(k_dwt_fwd<T, J, MULTI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    k_dwt_fwd<T, J, MULTI, MODE><<<grid, T::NT, bytes, s>>>(ft, a);
+}
+template <int J, bool MULTI>
+void launch_fwd_j(const FwdTaps &ft, const FwdArgs &a, int n_planes, int exact, int sm_count, cudaStream_t s)
+{
+    static const int persist = dev_knob("B2S_DWT_PERSIST", 0);
+    if (persist && FwdGeom(a.Fp, FwdTileA::TY, FwdTileA::TX).smem_bytes(FwdTileA::STAGES) <= (size_t)kSmemPerSm - 1024) {
+        if (exact) launch_fwd_t<FwdTileA, J, MULTI, kExact>(ft, a, n_planes, sm_count, s);
+        else launch_fwd_t<FwdTileA, J, MULTI, kFast>(ft, a, n_planes, sm_count, s);
+    } else {
+        if (exact) launch_fwd_t<FwdTileS, J, MULTI, kExact>(ft, a, n_planes, sm_count, s);
+        else launch_fwd_t<FwdTileS, J, MULTI, kFast>(ft, a, n_planes, sm_count, s);
+    }
+}
+
+template <class T, int JH, bool MULTI, int MODE>
+void launch_inv_t(const InvTaps &it, InvArgs a, int n_planes, int sm_count, cudaStream_t s)
+{
+    const InvGeom g(a.Hp, T::TY, T::TX);
+    const size_t bytes = g.smem_bytes(T::STAGES);
+    a.tiles_x = (a.out.cols + 2 * T::TX - 1) / (2 * T::TX);
+    a.tiles_y = (a.out.rows + 2 * T::TY - 1) / (2 * T::TY);
+    a.n_tiles = a.tiles_x * a.tiles_y * n_planes;
+    int per_sm = (int)(kSmemPerSm / (bytes + 1024));
+    if (per_sm > 2048 / T::NT) per_sm = 2048 / T::NT;
+    if (per_sm < 1) per_sm = 1;
+    const int grid = (T::STAGES == 1 || a.n_tiles < sm_count * per_sm) ? a.n_tiles : sm_count * per_sm;
+    cudaFuncSetAttribute(k_dwt_inv<T, JH, MULTI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    k_dwt_inv<T, JH, MULTI, MODE><<<grid, T::NT, bytes, s>>>(it, a);
+}
+template <int JH, bool MULTI>
+void launch_inv_j(const InvTaps &it, const InvArgs &a, int n_planes, int exact, int sm_count, cudaStream_t s)
+{
+    static const int persist = dev_knob("B2S_DWT_PERSIST", 0);
+    if (persist && InvGeom(a.Hp, InvTileA::TY, InvTileA::TX).smem_bytes(InvTileA::STAGES) <= (size_t)kSmemPerSm - 1024) {
+        if (exact) launch_inv_t<InvTileA, JH, MULTI, kExact>(it, a, n_planes, sm_count, s);
+        else launch_inv_t<InvTileA, JH, MULTI, kFast>(it, a, n_planes, sm_count, s);
+    } else {
+        if (exact) launch_inv_t<InvTileS, JH, MULTI, kExact>(it, a, n_planes, sm_count, s);
+        else launch_inv_t<InvTileS, JH, MULTI, kFast>(it, a, n_planes, sm_count, s);
+    }
 }
 
 }  // namespace
 
 int b2s_dwt_max_smem(int F)
 {
-    const size_t a = FwdGeom(F).smem_floats() * sizeof(float), b = InvGeom(F).smem_floats() * sizeof(float);
-    return (int)(a > b ? a : b);
+    int J, nch, JH, nchi;
+    pick_fwd_chunk(F, &J, &nch);
+    pick_inv_chunk(F / 2, &JH, &nchi);
+    const size_t a = FwdGeom(J * nch, FwdTileS::TY, FwdTileS::TX).smem_bytes(FwdTileS::STAGES);
+    const size_t b = InvGeom(JH * nchi, InvTileS::TY, InvTileS::TX).smem_bytes(InvTileS::STAGES);
+    return (int)((a > b ? a : b) + 1024);
 }
 
 void b2s_launch_dwt_fwd(const B2sTaps &t, const B2sImg &in, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV,
-                        const B2sImg &cD, int n_planes, int exact, cudaStream_t s)
+                        const B2sImg &cD, int n_planes, int exact, int sm_count, cudaStream_t s)
 {
-#define X(FF)                                                                                        \
-    if (t.F == FF) {                                                                                 \
-        if (exact) launch_fwd_t<FF, true>(t, in, cA, cH, cV, cD, n_planes, s);                       \
-        else launch_fwd_t<FF, false>(t, in, cA, cH, cV, cD, n_planes, s);                            \
-        return;                                                                                      \
-    }
-    B2S_FOR_STATIC_F(X)
+    int J, nch;
+    pick_fwd_chunk(t.F, &J, &nch);
+    FwdTaps ft;
+    for (int j = 0; j < kMaxFp; ++j) ft.t[j] = j < t.F ? make_float2(t.dec_lo[j], t.dec_hi[j]) : make_float2(0.f, 0.f);
+    FwdArgs a;
+    a.in = in; a.cA = cA; a.cH = cH; a.cV = cV; a.cD = cD;
+    a.F = t.F; a.Fp = J * nch; a.nch = nch;
+    a.negzero = -0.0f;
+    if (nch == 1) {
+        switch (J) {
+#define X(JJ) case JJ: launch_fwd_j<JJ, false>(ft, a, n_planes, exact, sm_count, s); return;
+            X(2) X(4) X(6) X(8) X(10) X(12) X(14) X(16) X(18) X(20)
 #undef X
-    if (exact) launch_fwd_t<0, true>(t, in, cA, cH, cV, cD, n_planes, s);
-    else launch_fwd_t<0, false>(t, in, cA, cH, cV, cD, n_planes, s);
+        }
+    }
+    switch (J) {
+#define X(JJ) case JJ: launch_fwd_j<JJ, true>(ft, a, n_planes, exact, sm_count, s); return;
+        X(8) X(12) X(16) X(20)
+#undef X
+    }
 }
 
 void b2s_launch_dwt_inv(const B2sTaps &t, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV, const B2sImg &cD,
-                        const B2sImg &out, int n_planes, int exact, cudaStream_t s)
+                        const B2sImg &out, int n_planes, int exact, int sm_count, cudaStream_t s)
 {
-#define X(FF)                                                                                        \
-    if (t.F == FF) {                                                                                 \
-        if (exact) launch_inv_t<FF, true>(t, cA, cH, cV, cD, out, n_planes, s);                      \
-        else launch_inv_t<FF, false>(t, cA, cH, cV, cD, out, n_planes, s);                           \
-        return;                                                                                      \
+    const int H = t.F / 2;
+    int JH, nch;
+    pick_inv_chunk(H, &JH, &nch);
+    InvTaps it;
+    for (int j = 0; j < kMaxFp / 2; ++j) {
+        it.lo[j] = j < H ? make_float2(t.rec_lo[2 * j], t.rec_lo[2 * j + 1]) : make_float2(0.f, 0.f);
+        it.hi[j] = j < H ? make_float2(t.rec_hi[2 * j], t.rec_hi[2 * j + 1]) : make_float2(0.f, 0.f);
     }
-    B2S_FOR_STATIC_F(X)
+    InvArgs a;
+    a.cA = cA; a.cH = cH; a.cV = cV; a.cD = cD; a.out = out;
+    a.H = H; a.Hp = JH * nch; a.nch = nch;
+    a.negzero = -0.0f;
+    if (nch == 1) {
+        switch (JH) {
+#define X(JJ) case JJ: launch_inv_j<JJ, false>(it, a, n_planes, exact, sm_count, s); return;
+            X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10)
 #undef X
-    if (exact) launch_inv_t<0, true>(t, cA, cH, cV, cD, out, n_planes, s);
-    else launch_inv_t<0, false>(t, cA, cH, cV, cD, out, n_planes, s);
+        }
+    }
+    switch (JH) {
+#define X(JJ) case JJ: launch_inv_j<JJ, true>(it, a, n_planes, exact, sm_count, s); return;
+        X(4) X(8) X(12)
+#undef X
+    }
 }

@@ -22,8 +22,11 @@ def main():
     ctx.timing_enable(True); ctx.timing_read(reset=True)
     for _ in range(3):
         plan.run_torch(stack, out)
+    tl = ctx.timing_read(reset=False, per_level=True)
     t = ctx.timing_read(reset=True)
     ctx.timing_enable(False)
+    for (k, l), (ms, cnt) in sorted(tl.items()):
+        if l: print(f"  {k}@L{l}: {ms / (3 * n) * 1e3:7.1f} us/plane")
     tot = sum(v[0] for v in t.values())
     for k, (ms, cnt) in t.items():
         if cnt: print(f"{k:10s} {ms / (3 * n) * 1e3:9.1f} us/plane  launches={cnt}")
