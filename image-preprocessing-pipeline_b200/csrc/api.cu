@@ -255,6 +255,10 @@ struct b2s_plan {
     int pitch[B2S_MAX_LEVELS + 1];
     size_t plane_stride[B2S_MAX_LEVELS + 1];
     float *d_flat = nullptr;
+    // numpy.pad tables for the prologue
+    int n_row_groups = 0;
+    int *d_row_src = nullptr, *d_row_start = nullptr, *d_row_targets = nullptr, *d_colmap = nullptr;
+    float *d_lut = nullptr;
     std::map<int, B2sFftPlan> fft;                  // by length
     float *d_notch[2][B2S_MAX_LEVELS + 1][2] = {};  // [pass][level][axis: 0 = cH rows, 1 = cV cols]
     int64_t workspace_bytes = 0;
@@ -329,6 +333,50 @@ int build_tables(b2s_plan *pl)
         t.rec_lo[k] = (float)rec_lo[k];
         t.rec_hi[k] = (float)rec_hi[k];
     }
+    // numpy.pad as index tables (core.py:1100-1110)
+    {
+        auto pad_index = [&](int i, int n) -> int {
+            if (i >= 0 && i < n) return i;
+            auto imod = [](int v, int m) { int t = v % m; return t < 0 ? t + m : t; };
+            switch (p.pad_mode) {
+            case B2S_PAD_REFLECT: { if (n == 1) return 0; const int q = 2 * (n - 1), t = imod(i, q); return t < n ? t : q - t; }
+            case B2S_PAD_SYMMETRIC: { const int q = 2 * n, t = imod(i, q); return t < n ? t : q - 1 - t; }
+            case B2S_PAD_WRAP: return imod(i, n);
+            case B2S_PAD_EDGE: return i < 0 ? 0 : n - 1;
+            default: return -1;
+            }
+        };
+        std::vector<int> colmap(pl->pitch[0], -1);
+        for (int c = 0; c < g.PW; ++c) colmap[c] = pad_index(c - g.base_pad, g.work_cols);
+        std::vector<std::vector<int>> targets(g.work_rows);
+        std::vector<int> orphan;
+        for (int i = 0; i < g.PH; ++i) {
+            const int sy = pad_index(i - g.base_pad, g.work_rows);
+            if (sy >= 0) targets[sy].push_back(i); else orphan.push_back(i);
+        }
+        std::vector<int> row_src, row_start(1, 0), row_targets;
+        for (int y = 0; y < g.work_rows; ++y) {
+            if (targets[y].empty()) continue;
+            row_src.push_back(y);
+            row_targets.insert(row_targets.end(), targets[y].begin(), targets[y].end());
+            row_start.push_back((int)row_targets.size());
+        }
+        for (int i : orphan) { row_src.push_back(-1); row_targets.push_back(i); row_start.push_back((int)row_targets.size()); }
+        pl->n_row_groups = (int)row_src.size();
+        struct { int **dst; std::vector<int> *src; } up[4] = {{&pl->d_row_src, &row_src}, {&pl->d_row_start, &row_start},
+                                                              {&pl->d_row_targets, &row_targets}, {&pl->d_colmap, &colmap}};
+        for (auto &u : up) {
+            int rc = dev_alloc(pl, (void **)u.dst, sizeof(int) * u.src->size());
+            if (rc) return rc;
+            CU(ctx, cudaMemcpy(*u.dst, u.src->data(), sizeof(int) * u.src->size(), cudaMemcpyHostToDevice));
+        }
+        if (g.work_dtype != B2S_F32 && p.log1p) {   // integer pixels enter filter_streaks: table look-up
+            int rc = dev_alloc(pl, (void **)&pl->d_lut, sizeof(float) * 65536);
+            if (rc) return rc;
+            b2s_launch_log1p_lut(pl->d_lut, 65536, 0);
+            CU(ctx, cudaDeviceSynchronize());
+        }
+    }
     // per-level FFT plans + notch tables (np_notch, core.py:637-667, numpy float32 branch)
     for (int pass = 0; pass < g.n_passes; ++pass) {
         for (int l = 1; l <= g.levels; ++l) {
@@ -340,15 +388,16 @@ int build_tables(b2s_plan *pl)
                     return fail(ctx, B2S_ERR_UNSUPPORTED, "sub-band side %d too long for the shared-memory FFT", n);
                 if (!pl->fft.count(n)) {
                     B2sFftPlan fp;
-                    b2s_fft_plan_init(&fp, n);
-                    std::vector<float2> tw(n);
-                    for (int k = 0; k < n; ++k) {
-                        const double ang = -2.0 * M_PI * (double)k / (double)n;
-                        tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+                    B2sFftHostTables ht;
+                    b2s_fft_plan_init(&fp, n, &ht);
+                    fp.d_twiddle = fp.d_chirp = fp.d_bf = nullptr;
+                    struct { float2 **dst; std::vector<float2> *src; } up[3] = {{&fp.d_twiddle, &ht.tw}, {&fp.d_chirp, &ht.chirp}, {&fp.d_bf, &ht.bf}};
+                    for (auto &u : up) {
+                        if (u.src->empty()) continue;
+                        int rc = dev_alloc(pl, (void **)u.dst, sizeof(float2) * u.src->size());
+                        if (rc) return rc;
+                        CU(ctx, cudaMemcpy(*u.dst, u.src->data(), sizeof(float2) * u.src->size(), cudaMemcpyHostToDevice));
                     }
-                    int rc = dev_alloc(pl, (void **)&fp.d_twiddle, sizeof(float2) * n);
-                    if (rc) return rc;
-                    CU(ctx, cudaMemcpy(fp.d_twiddle, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
                     pl->fft[n] = fp;
                 }
                 const double width_frac = g.pass_sigma[pass] / (double)img_len;
@@ -452,6 +501,12 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             a.base_pad = g.base_pad;
             a.use_log1p = p.log1p;
             a.out = padded;
+            a.n_groups = pl->n_row_groups;
+            a.row_src = pl->d_row_src;
+            a.row_start = pl->d_row_start;
+            a.row_targets = pl->d_row_targets;
+            a.colmap = pl->d_colmap;
+            a.lut = (cur_dt != B2S_F32 && !a.flat && p.log1p) ? pl->d_lut : nullptr;
             b2s_launch_prologue(a, nb, st);
         }
         if (p.debug_stop_after == B2S_STAGE_PROLOGUE) return B2S_OK;
@@ -503,6 +558,8 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
         e.int_path = g.int_path;
         e.work_dtype = g.work_dtype;
         e.dark = p.process_img ? p.dark : 0.0;
+        // float32 holds every intermediate exactly unless a fractional dark meets an integer image (float64 there)
+        e.f32_exact = !(e.dark > 0.0 && g.int_path && e.dark != std::floor(e.dark)) && e.dark < 16777216.0;
         e.ls_sub = nullptr;
         e.final_mode = g.final_mode;
         e.shift = p.bit_shift_to_right;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #define B2S_MAX_TAPS 128
 #define B2S_MAX_LEVELS 32
 
@@ -29,6 +31,13 @@ struct B2sPrologueArgs {
     int pad_mode, base_pad;
     int use_log1p;
     B2sImg out;            // padded image
+    // numpy.pad as tables (built once per plan): padded rows grouped by the source row they replicate
+    int n_groups;          // source rows + padded rows without a source (constant mode)
+    const int *row_src;    // [n_groups] source row, -1 => zero rows
+    const int *row_start;  // [n_groups + 1] CSR offsets into row_targets
+    const int *row_targets;// padded row indices
+    const int *colmap;     // [out.pitch] source column of each padded column, -1 => 0
+    const float *lut;      // optional: log1p of every integer pixel value (no flat, integer input)
 };
 void b2s_launch_prologue(const B2sPrologueArgs &a, int n_planes, cudaStream_t s);
 
@@ -48,6 +57,7 @@ struct B2sEpilogueArgs {
     int shift;
     int out_dtype;
     int flip, rot;         // rot in {0,1,2,3} quarter turns (numpy.rot90 k)
+    int f32_exact;         // every value of the final conversion is exact in float32 (no dark, or integral dark on integers)
     const int *uniform_flags; // optional per-plane flag: 1 => write zeros (process_img uniform shortcut)
     void *out;
     int out_rows, out_cols;
@@ -66,6 +76,7 @@ void b2s_launch_gauss5_f32(const float *in, float *out, int rows, int cols, int 
 void b2s_launch_block_reduce(const void *in, int dtype, int rows, int cols, int by, int bx, int method, void *out,
                              int out_dtype, int out_rows, int out_cols, int n_planes, cudaStream_t s);
 void b2s_launch_math(int which, const float *in, float *out, int64_t n, cudaStream_t s);
+void b2s_launch_log1p_lut(float *lut, int n, cudaStream_t s);
 
 // dwt.cu --------------------------------------------------------------------------------------------------------
 // forward level: in (ny x nx) -> cA,cH,cV,cD ((ny+F-1)/2 x (nx+F-1)/2); exact!=0 => reference summation order, no FMA
@@ -78,15 +89,21 @@ void b2s_launch_dwt_inv(const B2sTaps &t, const B2sImg &cA, const B2sImg &cH, co
 int b2s_dwt_max_smem(int F);
 
 // fft.cu --------------------------------------------------------------------------------------------------------
-struct B2sFftPlan {      // per transform length n
+struct B2sFftPlan {      // per sequence length n
     int n;
-    int n_factors;
+    int L;               // transform length: n, or the Bluestein convolution length (>= 2n-1, 13-smooth)
+    int bluestein;
+    int n_factors;       // factors of L
     int factors[32];
     int group;           // sequence pairs transformed together by one CTA
     int has_large;       // a prime factor > 43 is present
-    float2 *d_twiddle;   // n entries exp(-2 pi i k / n)
+    float2 *d_twiddle;   // L entries exp(-2 pi i k / L)
+    float2 *d_chirp;     // Bluestein: n entries exp(-i pi k^2 / n)
+    float2 *d_bf;        // Bluestein: L entries, spectrum of the wrapped conjugate chirp / L
 };
-void b2s_fft_plan_init(B2sFftPlan *fp, int n);   // factorisation + batching; d_twiddle is left to the caller
+struct B2sFftHostTables { std::vector<float2> tw, chirp, bf; };
+// factorisation, batching and (when host != NULL) the tables the caller uploads into d_twiddle / d_chirp / d_bf
+void b2s_fft_plan_init(B2sFftPlan *fp, int n, B2sFftHostTables *host);
 // rows x n image; transform along the contiguous axis when along_cols == 0, along the row index otherwise.
 // d_notch: n floats multiplying the packed (fftpack) spectrum; result overwrites the image.
 void b2s_launch_notch(const B2sFftPlan &fp, const float *d_notch, const B2sImg &img, int along_cols, int n_planes,

@@ -39,6 +39,17 @@ constexpr int kDftTableFloats = dft_table_offset(kMaxRegH + 1);
 // radix 2h+1, row r-1 (r = 1..h): cos(2 pi q r / R) for q = 1..h (padded to a multiple of 4), then sin(2 pi q r / R)
 __constant__ float c_dft[kDftTableFloats];
 
+// asynchronous global -> shared copies: the whole gather of a group is in flight at once
+__device__ __forceinline__ void cp_async4(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -48,13 +59,16 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 
 struct NotchArgs {
     B2sImg img;
-    const float2 *tw;   // exp(-2 pi i k / n)
-    const float *g;     // notch over packed positions
+    const float2 *tw;     // exp(-2 pi i k / L), L = transform length (n, or n2 for Bluestein)
+    const float *g;       // notch over packed positions
+    const float2 *chirp;  // Bluestein: exp(-i pi k^2 / n), k < n
+    const float2 *bf;     // Bluestein: FFT_L of the wrapped conjugate chirp, scaled by 1/L
     int n, nseq, along_cols;
-    int n_factors;
+    int L;                // transform length and per-sequence stride in shared memory
+    int n_factors;        // factors of L
     int factors[32];
-    int group;          // sequence pairs per CTA pass
-    int has_large;      // a factor > 43 is present (third buffer allocated)
+    int group;            // sequence pairs per CTA pass
+    int has_large;        // a factor > 43 is present (third buffer allocated)
     int groups_per_plane;
 };
 
@@ -238,17 +252,60 @@ __device__ __forceinline__ void fft_pass(int R, const float2 *in, float2 *out, f
     }
 }
 
+// all passes of one length-L transform over `ng` sequences; result ends in `cur`
+template <bool INV>
+__device__ __forceinline__ void run_passes(const NotchArgs &a, float2 *&cur, float2 *&nxt, float2 *tmp, const float2 *tw, int ng)
+{
+    int Ns = 1;
+    for (int f = 0; f < a.n_factors; ++f) {
+        const int R = a.factors[f];
+        fft_pass<INV>(R, cur, nxt, tmp, tw, a.L, Ns, ng);
+        Ns *= R;
+        __syncthreads();
+        float2 *t = cur; cur = nxt; nxt = t;
+    }
+}
+
+// unnormalised forward DFT of length n of every sequence in `cur` (stride L).  Direct when L == n, else Bluestein:
+// X_j = c_j * sum_k (z_k c_k) conj(c)_{j-k}, the convolution done cyclically at length L >= 2n-1.
+__device__ __forceinline__ void dft_n(const NotchArgs &a, float2 *&cur, float2 *&nxt, float2 *tmp, const float2 *tw, int ng)
+{
+    const int n = a.n, L = a.L;
+    if (L == n) { run_passes<false>(a, cur, nxt, tmp, tw, ng); return; }
+    for (int i = threadIdx.x; i < ng * L; i += kFT) {
+        const int gi = i / L, k = i - gi * L;
+        float2 *z = cur + gi * L;
+        z[k] = k < n ? cmul(z[k], __ldg(a.chirp + k)) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    run_passes<false>(a, cur, nxt, tmp, tw, ng);
+    for (int i = threadIdx.x; i < ng * L; i += kFT) {
+        const int gi = i / L, k = i - gi * L;
+        float2 *z = cur + gi * L;
+        z[k] = cmul(z[k], __ldg(a.bf + k));
+    }
+    __syncthreads();
+    run_passes<true>(a, cur, nxt, tmp, tw, ng);
+    for (int i = threadIdx.x; i < ng * n; i += kFT) {
+        const int gi = i / n, k = i - gi * n;
+        float2 *z = cur + gi * L;
+        z[k] = cmul(z[k], __ldg(a.chirp + k));
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kFT) k_notch(const NotchArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = a.n, G = a.group;
+    const int n = a.n, L = a.L, G = a.group;
     float2 *bufA = reinterpret_cast<float2 *>(smem_raw);
-    float2 *bufB = bufA + G * n;
-    float2 *tmp = bufB + G * n;
-    float2 *tw = tmp + (a.has_large ? G * n : 0);
-    float *g = reinterpret_cast<float *>(tw + n);
+    float2 *bufB = bufA + G * L;
+    float2 *tmp = bufB + G * L;
+    float2 *tw = tmp + (a.has_large ? G * L : 0);
+    float *g = reinterpret_cast<float *>(tw + L);
 
-    for (int i = threadIdx.x; i < n; i += kFT) { tw[i] = a.tw[i]; g[i] = a.g[i]; }
+    for (int i = threadIdx.x; i < L; i += kFT) tw[i] = a.tw[i];
+    for (int i = threadIdx.x; i < n; i += kFT) g[i] = a.g[i];
 
     const float inv_n = 1.0f / (float)n;
     float *plane = a.img.ptr + (size_t)blockIdx.y * a.img.plane_stride;
@@ -263,30 +320,31 @@ __global__ void __launch_bounds__(kFT) k_notch(const NotchArgs a)
                 const int gi = i / n, t = i - gi * n;
                 const int s0 = 2 * (pair0 + gi);
                 const float *r0 = plane + (size_t)s0 * a.img.pitch;
-                bufA[i] = make_float2(r0[t], s0 + 1 < a.nseq ? r0[a.img.pitch + t] : 0.f);
+                float2 *z = bufA + gi * L + t;
+                cp_async4(&z->x, r0 + t);
+                if (s0 + 1 < a.nseq) cp_async4(&z->y, r0 + a.img.pitch + t);
+                else z->y = 0.f;
             }
         } else {
             for (int i = threadIdx.x; i < ng * n; i += kFT) {
                 const int t = i / ng, gi = i - t * ng;   // neighbouring threads read neighbouring columns
                 const int s0 = 2 * (pair0 + gi);
                 const float *p = plane + (size_t)t * a.img.pitch + s0;
-                bufA[gi * n + t] = make_float2(p[0], s0 + 1 < a.nseq ? p[1] : 0.f);
+                float2 *z = bufA + gi * L + t;
+                if (s0 + 1 < a.nseq) cp_async8(z, p);
+                else { cp_async4(&z->x, p); z->y = 0.f; }
             }
         }
+        cp_async_wait_all();
         __syncthreads();
         float2 *cur = bufA, *nxt = bufB;
-        int Ns = 1;
-        for (int f = 0; f < a.n_factors; ++f) {
-            fft_pass<false>(a.factors[f], cur, nxt, tmp, tw, n, Ns, ng);
-            Ns *= a.factors[f];
-            __syncthreads();
-            float2 *t = cur; cur = nxt; nxt = t;
-        }
-        // ---- separate the two spectra, apply the notch on packed positions, recombine
+        dft_n(a, cur, nxt, tmp, tw, ng);
+        // ---- separate the two spectra, apply the notch on packed positions, recombine; the inverse transform is
+        //      conj(DFT(conj(.))), so the recombined spectrum is stored conjugated
         const int half = n / 2 + 1;
         for (int i = threadIdx.x; i < ng * half; i += kFT) {
             const int gi = i / half, k = i - gi * half;
-            float2 *z = cur + gi * n;
+            float2 *z = cur + gi * L;
             const int kp = k == 0 ? 0 : n - k;
             const float2 zk = z[k], zp = z[kp];
             float ar = 0.5f * (zk.x + zp.x), ai = 0.5f * (zk.y - zp.y);
@@ -294,35 +352,29 @@ __global__ void __launch_bounds__(kFT) k_notch(const NotchArgs a)
             const float gr = k == 0 ? g[0] : g[2 * k - 1];
             const float gim = (k == 0 || 2 * k == n) ? 0.f : g[2 * k];
             ar *= gr; br *= gr; ai *= gim; bi *= gim;
-            z[k] = make_float2(ar - bi, ai + br);
-            if (kp != k) z[kp] = make_float2(ar + bi, br - ai);
+            z[k] = make_float2(ar - bi, -(ai + br));
+            if (kp != k) z[kp] = make_float2(ar + bi, -(br - ai));
         }
         __syncthreads();
-        Ns = 1;
-        for (int f = 0; f < a.n_factors; ++f) {
-            fft_pass<true>(a.factors[f], cur, nxt, tmp, tw, n, Ns, ng);
-            Ns *= a.factors[f];
-            __syncthreads();
-            float2 *t = cur; cur = nxt; nxt = t;
-        }
-        // ---- scatter
+        dft_n(a, cur, nxt, tmp, tw, ng);
+        // ---- scatter (undo the conjugation: only the sign of the imaginary part, i.e. of the second sequence)
         if (!a.along_cols) {
             for (int i = threadIdx.x; i < ng * n; i += kFT) {
                 const int gi = i / n, t = i - gi * n;
                 const int s0 = 2 * (pair0 + gi);
                 float *r0 = plane + (size_t)s0 * a.img.pitch;
-                const float2 z = cur[i];
+                const float2 z = cur[gi * L + t];
                 r0[t] = z.x * inv_n;
-                if (s0 + 1 < a.nseq) r0[a.img.pitch + t] = z.y * inv_n;
+                if (s0 + 1 < a.nseq) r0[a.img.pitch + t] = -z.y * inv_n;
             }
         } else {
             for (int i = threadIdx.x; i < ng * n; i += kFT) {
                 const int t = i / ng, gi = i - t * ng;
                 const int s0 = 2 * (pair0 + gi);
                 float *p = plane + (size_t)t * a.img.pitch + s0;
-                const float2 z = cur[gi * n + t];
+                const float2 z = cur[gi * L + t];
                 p[0] = z.x * inv_n;
-                if (s0 + 1 < a.nseq) p[1] = z.y * inv_n;
+                if (s0 + 1 < a.nseq) p[1] = -z.y * inv_n;
             }
         }
     }
@@ -348,40 +400,104 @@ void upload_dft_tables()
     done[dev] = true;
 }
 
-size_t smem_for(int n, int group, int has_large)
+size_t smem_for(int n, int L, int group, int has_large)
 {
-    return (size_t)n * ((size_t)(has_large ? 3 : 2) * group * sizeof(float2) + sizeof(float2) + sizeof(float));
+    return (size_t)L * ((size_t)(has_large ? 3 : 2) * group * sizeof(float2) + sizeof(float2)) + (size_t)n * sizeof(float);
+}
+
+int largest_prime_factor(int n)
+{
+    int best = 1;
+    for (int p = 2; (long long)p * p <= n; ++p)
+        while (n % p == 0) { best = p; n /= p; }
+    return n > 1 ? n : best;
+}
+
+// factors of L in pass order: 4s, 2s, then odd primes ascending
+int factorize(int L, int *factors, int *has_large)
+{
+    int nf = 0, rem = L;
+    *has_large = 0;
+    while (rem % 4 == 0) { factors[nf++] = 4; rem /= 4; }
+    while (rem % 2 == 0) { factors[nf++] = 2; rem /= 2; }
+    for (int p = 3; rem > 1; p += 2) {
+        if ((long long)p * p > rem) p = rem;
+        while (rem % p == 0) {
+            factors[nf++] = p;
+            if (p > 2 * kMaxRegH + 1) *has_large = 1;
+            rem /= p;
+        }
+    }
+    return nf;
 }
 
 }  // namespace
 
-void b2s_fft_plan_init(B2sFftPlan *fp, int n)
+// pocketfft switches to Bluestein when a length has a large prime factor; so do we (threshold: a prime factor > 127;
+// primes 47..127 use the cooperative direct pass).  The convolution length is the smallest 13-smooth L >= 2n-1.
+void b2s_fft_plan_init(B2sFftPlan *fp, int n, B2sFftHostTables *host)
 {
     fp->n = n;
-    fp->n_factors = 0;
-    fp->has_large = 0;
-    int rem = n;
-    while (rem % 4 == 0) { fp->factors[fp->n_factors++] = 4; rem /= 4; }
-    while (rem % 2 == 0) { fp->factors[fp->n_factors++] = 2; rem /= 2; }
-    for (int p = 3; rem > 1; p += 2) {
-        if ((long long)p * p > rem) p = rem;
-        while (rem % p == 0) {
-            fp->factors[fp->n_factors++] = p;
-            if (p > 2 * kMaxRegH + 1) fp->has_large = 1;
-            rem /= p;
+    fp->L = n;
+    fp->bluestein = 0;
+    if (largest_prime_factor(n) > 127) {
+        int L = 2 * n - 1;
+        while (largest_prime_factor(L) > 13) ++L;
+        fp->L = L;
+        fp->bluestein = 1;
+    }
+    const int L = fp->L;
+    fp->n_factors = factorize(L, fp->factors, &fp->has_large);
+    // sequence pairs per CTA: as many as fit in ~110 KB (two CTAs per SM), at most 8
+    int g = 8;
+    while (g > 1 && smem_for(n, L, g, fp->has_large) > 110 * 1024) --g;
+    fp->group = g;
+    if (!host) return;
+    host->tw.resize(L);
+    for (int k = 0; k < L; ++k) {
+        const double ang = -2.0 * M_PI * (double)k / (double)L;
+        host->tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+    host->chirp.clear();
+    host->bf.clear();
+    if (fp->bluestein) {
+        // c_k = exp(-i pi k^2 / n); k^2 is reduced modulo 2n so the angle keeps full precision
+        std::vector<double> cr(n), ci(n);
+        host->chirp.resize(n);
+        for (int k = 0; k < n; ++k) {
+            const long long k2 = ((long long)k * k) % (2LL * n);
+            const double ang = -M_PI * (double)k2 / (double)n;
+            cr[k] = std::cos(ang); ci[k] = std::sin(ang);
+            host->chirp[k] = make_float2((float)cr[k], (float)ci[k]);
+        }
+        // B[t] = conj(c)_{|t|} wrapped to length L; BF = DFT_L(B) / L in double (O(L^2) once per plan is too slow for
+        // L ~ 3000, so use the recurrence-free split: direct sum over the 2n-1 non-zero taps)
+        std::vector<double> br(L, 0.0), bi(L, 0.0);
+        for (int t = 0; t < n; ++t) {
+            br[t] = cr[t]; bi[t] = -ci[t];
+            if (t) { br[L - t] = cr[t]; bi[L - t] = -ci[t]; }
+        }
+        host->bf.resize(L);
+        std::vector<double> wr(L), wi(L);
+        for (int k = 0; k < L; ++k) { const double ang = -2.0 * M_PI * (double)k / (double)L; wr[k] = std::cos(ang); wi[k] = std::sin(ang); }
+        for (int j = 0; j < L; ++j) {
+            double sr = 0.0, si = 0.0;
+            for (int t = 0; t < L; ++t) {
+                if (br[t] == 0.0 && bi[t] == 0.0) continue;
+                const int e = (int)(((long long)j * t) % L);
+                sr += br[t] * wr[e] - bi[t] * wi[e];
+                si += br[t] * wi[e] + bi[t] * wr[e];
+            }
+            host->bf[j] = make_float2((float)(sr / L), (float)(si / L));
         }
     }
-    // sequence pairs per CTA: as many as fit in ~100 KB (two CTAs per SM), at most 8
-    int g = 8;
-    while (g > 1 && smem_for(n, g, fp->has_large) > 100 * 1024) --g;
-    fp->group = g;
 }
 
 size_t b2s_notch_smem(int n)
 {
     B2sFftPlan fp;
-    b2s_fft_plan_init(&fp, n);
-    return smem_for(n, fp.group, fp.has_large);
+    b2s_fft_plan_init(&fp, n, nullptr);
+    return smem_for(n, fp.L, fp.group, fp.has_large);
 }
 
 void b2s_launch_notch(const B2sFftPlan &fp, const float *d_notch, const B2sImg &img, int along_cols, int n_planes,
@@ -392,7 +508,10 @@ void b2s_launch_notch(const B2sFftPlan &fp, const float *d_notch, const B2sImg &
     a.img = img;
     a.tw = fp.d_twiddle;
     a.g = d_notch;
+    a.chirp = fp.d_chirp;
+    a.bf = fp.d_bf;
     a.n = fp.n;
+    a.L = fp.L;
     a.along_cols = along_cols;
     a.nseq = along_cols ? img.cols : img.rows;
     a.n_factors = fp.n_factors;
@@ -401,7 +520,7 @@ void b2s_launch_notch(const B2sFftPlan &fp, const float *d_notch, const B2sImg &
     a.has_large = fp.has_large;
     const int pairs = (a.nseq + 1) / 2;
     a.groups_per_plane = (pairs + fp.group - 1) / fp.group;
-    const size_t bytes = smem_for(fp.n, fp.group, fp.has_large);
+    const size_t bytes = smem_for(fp.n, fp.L, fp.group, fp.has_large);
     cudaFuncSetAttribute(k_notch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     int bx = a.groups_per_plane;
     const int cap = (sm_count * 4 + n_planes - 1) / n_planes;

@@ -46,32 +46,145 @@ __device__ __forceinline__ float load_as_float(const void *p, int dtype, size_t 
     return __ldg(reinterpret_cast<const float *>(p) + idx);
 }
 
+// One CTA per group of padded rows that share a source row (numpy.pad replicates rows): the source row is converted
+// once ([/ flat], log1p) into shared memory, then every target row is assembled through the column map with 128-bit
+// stores.  Groups without a source row (constant padding) are zero rows.
 __global__ void __launch_bounds__(256) k_prologue(B2sPrologueArgs a)
 {
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
-    if (x4 >= a.out.pitch) return;
-    const size_t plane = blockIdx.z;
-    const size_t src_plane = plane * (size_t)a.src_rows * a.src_cols;
-    const int sy = pad_index(y - a.base_pad, a.src_rows, a.pad_mode);
-    float v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int x = x4 + k;
-        float r = 0.f;
-        if (x < a.out.cols) {
-            const int sx = pad_index(x - a.base_pad, a.src_cols, a.pad_mode);
-            if (sy >= 0 && sx >= 0) {
-                const size_t si = (size_t)sy * a.src_cols + sx;
-                r = load_as_float(a.in, a.in_dtype, src_plane + si);
-                if (a.flat) r = __fdiv_rn(r, __ldg(a.flat + si));
+    extern __shared__ __align__(16) float s_row[];
+    const int grp = blockIdx.x;
+    const size_t plane = blockIdx.y;
+    const int sy = a.row_src[grp];
+    if (sy >= 0) {
+        const size_t base = plane * (size_t)a.src_rows * a.src_cols + (size_t)sy * a.src_cols;
+        const float *flat = a.flat ? a.flat + (size_t)sy * a.src_cols : nullptr;
+#pragma unroll 8
+        for (int x = threadIdx.x; x < a.src_cols; x += 256) {
+            float r;
+            if (a.lut) {   // integer pixels, no flat: log1p through the 64 K-entry table (built with b2s_log1pf)
+                const unsigned v = a.in_dtype == B2S_U16 ? __ldg(reinterpret_cast<const unsigned short *>(a.in) + base + x)
+                                                         : __ldg(reinterpret_cast<const unsigned char *>(a.in) + base + x);
+                r = __ldg(a.lut + v);
+            } else {
+                r = load_as_float(a.in, a.in_dtype, base + x);
+                if (flat) r = __fdiv_rn(r, __ldg(flat + x));
                 if (a.use_log1p) r = b2s_log1pf(r);
             }
+            s_row[x] = r;
         }
-        v[k] = r;
     }
-    float *dst = a.out.ptr + plane * a.out.plane_stride + (size_t)y * a.out.pitch + x4;
-    *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    __syncthreads();
+    const int q4 = a.out.pitch >> 2;
+    const int4 *cm = reinterpret_cast<const int4 *>(a.colmap);
+    for (int t = a.row_start[grp]; t < a.row_start[grp + 1]; ++t) {
+        float *drow = a.out.ptr + plane * a.out.plane_stride + (size_t)a.row_targets[t] * a.out.pitch;
+#pragma unroll 4
+        for (int c4 = threadIdx.x; c4 < q4; c4 += 256) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (sy >= 0) {
+                const int4 m = __ldg(cm + c4);
+                if (m.x >= 0) o.x = s_row[m.x];
+                if (m.y >= 0) o.y = s_row[m.y];
+                if (m.z >= 0) o.z = s_row[m.z];
+                if (m.w >= 0) o.w = s_row[m.w];
+            }
+            *reinterpret_cast<float4 *>(drow + 4 * c4) = o;
+        }
+    }
+}
+
+// final conversion of one value: dark subtraction, convert_to_8bit / 16bit / clip+truncate (core.py:1324-1330, 1361-1369)
+struct EpiOut { unsigned u; float f; };
+__device__ __forceinline__ EpiOut epilogue_value(const B2sEpilogueArgs &a, float vf, bool is_int)
+{
+    EpiOut r;
+    double v;
+    if (a.dark > 0.0) {
+        if (is_int) {
+            const double d = (double)vf;
+            v = d > a.dark ? d - a.dark : 0.0;
+        } else {
+            const float df = (float)a.dark;
+            vf = vf > df ? __fsub_rn(vf, df) : 0.f;
+            v = (double)vf;
+        }
+    } else {
+        v = (double)vf;
+    }
+    r.f = (float)v;
+    if (a.final_mode == 2) {  // convert_to_8bit_fun, core.py:402-423
+        const double c = v < 0.0 ? 0.0 : (v > 65535.0 ? 65535.0 : v);
+        unsigned u = (unsigned)c;  // truncation
+        const unsigned lower = 1u << a.shift;
+        u = (u > 0 && u < lower) ? 1u : (u >> a.shift);
+        r.u = u > 255u ? 255u : u;
+    } else {
+        const double hi = (a.out_dtype == B2S_U8) ? 255.0 : 65535.0;
+        const double c = v < 0.0 ? 0.0 : (v > hi ? hi : v);
+        r.u = (unsigned)c;
+    }
+    return r;
+}
+
+// same thing when everything is exactly representable in float32: no dark, or an integral dark on an integer image
+__device__ __forceinline__ unsigned epilogue_value_f32(const B2sEpilogueArgs &a, float vf, bool is_int, float darkf)
+{
+    if (darkf > 0.f) vf = vf > darkf ? __fsub_rn(vf, darkf) : 0.f;
+    (void)is_int;
+    if (a.final_mode == 2) {
+        const float c = vf < 0.f ? 0.f : (vf > 65535.f ? 65535.f : vf);
+        unsigned u = (unsigned)c;
+        const unsigned lower = 1u << a.shift;
+        u = (u > 0 && u < lower) ? 1u : (u >> a.shift);
+        return u > 255u ? 255u : u;
+    }
+    const float hi = (a.out_dtype == B2S_U8) ? 255.f : 65535.f;
+    const float c = vf < 0.f ? 0.f : (vf > hi ? hi : vf);
+    return (unsigned)c;
+}
+
+// destripe epilogue without rotation, integer output: 4 pixels per thread, 64-bit loads (base_pad is even), packed stores
+__global__ void __launch_bounds__(256) k_epilogue_rows(B2sEpilogueArgs a)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int i = blockIdx.y;
+    if (x4 >= a.out_cols) return;
+    const size_t plane = blockIdx.z;
+    const size_t oidx = plane * (size_t)a.out_rows * a.out_cols + (size_t)i * a.out_cols + x4;
+    const int nvalid = min(4, a.out_cols - x4);
+    unsigned u[4] = {0u, 0u, 0u, 0u};
+    const bool zero_plane = a.uniform_flags && a.uniform_flags[plane];
+    if (!zero_plane) {
+        const int y = a.flip ? a.rows - 1 - i : i;
+        const float *src = a.in.ptr + plane * a.in.plane_stride + (size_t)(y + a.base_pad) * a.in.pitch + (x4 + a.base_pad);
+        float v[4];
+        if (nvalid == 4) {
+            const float2 p0 = __ldg(reinterpret_cast<const float2 *>(src)), p1 = __ldg(reinterpret_cast<const float2 *>(src + 2));
+            v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = k < nvalid ? __ldg(src + k) : 0.f;
+        }
+        const bool is_int = a.int_path != 0;
+        const float hi_w = a.work_dtype == B2S_U8 ? 255.f : 65535.f;
+        const float darkf = (float)a.dark;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float vf = v[k];
+            if (a.use_log1p) vf = b2s_expm1f(vf);
+            if (is_int) vf = fminf(fmaxf(rintf(vf), 0.f), hi_w);   // core.py:1153-1158
+            u[k] = a.f32_exact ? epilogue_value_f32(a, vf, is_int, darkf) : epilogue_value(a, vf, is_int).u;
+        }
+    }
+    if (a.out_dtype == B2S_U8) {
+        unsigned char *o = reinterpret_cast<unsigned char *>(a.out) + oidx;
+        if (nvalid == 4 && (oidx & 3) == 0) *reinterpret_cast<uchar4 *>(o) = make_uchar4(u[0], u[1], u[2], u[3]);
+        else for (int k = 0; k < nvalid; ++k) o[k] = (unsigned char)u[k];
+    } else {
+        unsigned short *o = reinterpret_cast<unsigned short *>(a.out) + oidx;
+        if (nvalid == 4 && (oidx & 3) == 0) *reinterpret_cast<ushort4 *>(o) = make_ushort4(u[0], u[1], u[2], u[3]);
+        else for (int k = 0; k < nvalid; ++k) o[k] = (unsigned short)u[k];
+    }
 }
 
 __global__ void __launch_bounds__(256) k_epilogue(B2sEpilogueArgs a)
@@ -82,8 +195,8 @@ __global__ void __launch_bounds__(256) k_epilogue(B2sEpilogueArgs a)
     const size_t plane = blockIdx.z;
     const size_t oidx = plane * (size_t)a.out_rows * a.out_cols + (size_t)i * a.out_cols + j;
 
-    double v = 0.0;
     float vf = 0.f;
+    bool is_int_g = false;
     const bool zero_plane = a.uniform_flags && a.uniform_flags[plane];
     if (!zero_plane) {
         // output (i, j) -> work-image (y, x): undo rot90 then flipud
@@ -97,50 +210,24 @@ __global__ void __launch_bounds__(256) k_epilogue(B2sEpilogueArgs a)
         }
         if (a.flip) y = R - 1 - y;
 
-        bool is_int;  // does the reference hold an integer array at this point?
+        // is_int_g: does the reference hold an integer array at this point?
         if (a.destripe) {
             vf = a.in.ptr[plane * a.in.plane_stride + (size_t)(y + a.base_pad) * a.in.pitch + (x + a.base_pad)];
             if (a.use_log1p) vf = b2s_expm1f(vf);
-            is_int = a.int_path != 0;
-            if (is_int) {  // rint (half to even) + clip to the integer dtype, core.py:1153-1158
+            is_int_g = a.int_path != 0;
+            if (is_int_g) {  // rint (half to even) + clip to the integer dtype, core.py:1153-1158
                 vf = rintf(vf);
                 const float hi = a.work_dtype == B2S_U8 ? 255.f : 65535.f;
                 vf = fminf(fmaxf(vf, 0.f), hi);
             }
         } else {
             vf = load_as_float(a.raw, a.raw_dtype, plane * (size_t)R * C + (size_t)y * C + x);
-            is_int = a.raw_dtype != B2S_F32;
-        }
-        if (a.dark > 0.0) {  // core.py:1324-1330
-            if (is_int) {
-                const double d = (double)vf;
-                v = d > a.dark ? d - a.dark : 0.0;
-            } else {
-                const float df = (float)a.dark;
-                vf = vf > df ? __fsub_rn(vf, df) : 0.f;
-                v = (double)vf;
-            }
-        } else {
-            v = (double)vf;
+            is_int_g = a.raw_dtype != B2S_F32;
         }
     }
-    // final conversion, core.py:1361-1369
-    if (a.final_mode == 3) {
-        reinterpret_cast<float *>(a.out)[oidx] = (float)v;
-        return;
-    }
-    if (a.final_mode == 2) {  // convert_to_8bit_fun, core.py:402-423
-        double c = v < 0.0 ? 0.0 : (v > 65535.0 ? 65535.0 : v);
-        unsigned u = (unsigned)c;  // truncation
-        const unsigned lower = 1u << a.shift;
-        u = (u > 0 && u < lower) ? 1u : (u >> a.shift);
-        if (u > 255u) u = 255u;
-        reinterpret_cast<unsigned char *>(a.out)[oidx] = (unsigned char)u;
-        return;
-    }
-    const double hi = (a.out_dtype == B2S_U8) ? 255.0 : 65535.0;
-    double c = v < 0.0 ? 0.0 : (v > hi ? hi : v);
-    const unsigned u = (unsigned)c;
+    const EpiOut r = epilogue_value(a, vf, is_int_g);
+    if (a.final_mode == 3) { reinterpret_cast<float *>(a.out)[oidx] = zero_plane ? 0.f : r.f; return; }
+    const unsigned u = zero_plane ? 0u : r.u;
     if (a.out_dtype == B2S_U8) reinterpret_cast<unsigned char *>(a.out)[oidx] = (unsigned char)u;
     else reinterpret_cast<unsigned short *>(a.out)[oidx] = (unsigned short)u;
 }
@@ -266,15 +353,29 @@ __global__ void k_math(int which, const float *in, float *out, int64_t n)
 
 void b2s_launch_prologue(const B2sPrologueArgs &a, int n_planes, cudaStream_t s)
 {
-    dim3 grid((a.out.pitch / 4 + 255) / 256, a.out.rows, n_planes);
-    k_prologue<<<grid, 256, 0, s>>>(a);
+    const size_t bytes = sizeof(float) * (size_t)a.src_cols;
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(k_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    k_prologue<<<dim3(a.n_groups, n_planes), 256, bytes, s>>>(a);
 }
 
 void b2s_launch_epilogue(const B2sEpilogueArgs &a, int n_planes, cudaStream_t s)
 {
+    if (a.destripe && a.rot == 0 && a.final_mode != 3) {
+        dim3 grid(((a.out_cols + 3) / 4 + 255) / 256, a.out_rows, n_planes);
+        k_epilogue_rows<<<grid, 256, 0, s>>>(a);
+        return;
+    }
     dim3 grid((a.out_cols + 255) / 256, a.out_rows, n_planes);
     k_epilogue<<<grid, 256, 0, s>>>(a);
 }
+
+// log1p table for integer pixels: lut[v] = b2s_log1pf((float)v), the function the non-table path evaluates
+__global__ void k_log1p_lut(float *lut, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lut[i] = b2s_log1pf((float)i);
+}
+void b2s_launch_log1p_lut(float *lut, int n, cudaStream_t s) { k_log1p_lut<<<(n + 255) / 256, 256, 0, s>>>(lut, n); }
 
 void b2s_launch_uniform(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned *mm, int *flags,
                         cudaStream_t s)
