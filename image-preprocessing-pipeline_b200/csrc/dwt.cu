@@ -30,15 +30,15 @@
 
 namespace {
 
-constexpr int kR = 4;                 // consecutive outputs per thread and pass
 constexpr int kMaxFp = 160;           // padded analysis filter length bound (B2S_MAX_TAPS rounded up to a chunk)
 constexpr int kSmemPerSm = 227 * 1024;
 
 // tile shapes.  Forward: TY x TX outputs per sub-band; inverse: TY x TX coefficient positions -> 2TY x 2TX outputs.
-template <int TY_, int TX_, int NT_, int STAGES_>
+// R1 / R2 = consecutive outputs a thread computes from one register window in the first / second pass.
+template <int TY_, int TX_, int NT_, int R1_, int R2_ = R1_>
 struct Tile {
-    static constexpr int TY = TY_, TX = TX_, NT = NT_, NW = NT_ / 32, STAGES = STAGES_;
-    static_assert(TY_ % 4 == 0 && TX_ % 16 == 0 && NT_ % 32 == 0, "tile shape");
+    static constexpr int TY = TY_, TX = TX_, NT = NT_, NW = NT_ / 32, R1 = R1_, R2 = R2_;
+    static_assert(TX_ % 32 == 0 && NT_ % 32 == 0 && (R1_ == 4 || R1_ == 8) && (R2_ == 4 || R2_ == 8), "tile shape");
 };
 
 __host__ __device__ inline int round_up4(int n) { return (n + 3) & ~3; }
@@ -48,6 +48,7 @@ __host__ __device__ inline int pitch_quads_odd(int n)  // >= n, multiple of 4, (
     if (((p >> 2) & 1) == 0) p += 4;
     return p;
 }
+
 __host__ __device__ inline int pitch_quads_4mod8(int n)  // >= n, multiple of 4, (p/4) % 8 == 4
 {
     int p = round_up4(n);
@@ -59,7 +60,8 @@ struct FwdTaps { float2 t[kMaxFp]; };                          // (dec_lo[j], de
 struct InvTaps { float2 lo[kMaxFp / 2], hi[kMaxFp / 2]; };     // (rec[2j], rec[2j+1]), zero beyond F/2
 
 // geometry of the shared-memory tiles for a padded filter length Fp (forward) / Hp = padded F/2 (inverse)
-// one or two input stages (two: the next tile is fetched while the current one is computed) + one intermediate buffer
+// shared-memory geometry: one input stage (the next tile is fetched into it while the second pass of the current tile
+// runs out of the intermediate buffer) + the intermediate buffer
 struct FwdGeom {
     int rin_y, rin_x, pin, pmid, stage_floats, mid_floats;
     __host__ __device__ FwdGeom(int Fp, int TY, int TX)
@@ -67,25 +69,26 @@ struct FwdGeom {
         rin_y = 2 * TY + Fp - 2;
         rin_x = 2 * TX + Fp - 2;
         pin = round_up4(rin_x + 2) + 4;        // + alignment offset (0 or 2) of the tile's first column
-        pmid = pitch_quads_odd(rin_x);
+        pmid = pitch_quads_odd(rin_x + 2);
         stage_floats = rin_y * pin;
         mid_floats = 2 * TY * pmid;
     }
-    __host__ __device__ size_t smem_bytes(int stages) const { return sizeof(float) * ((size_t)stages * stage_floats + mid_floats); }
+    __host__ __device__ size_t smem_bytes() const { return sizeof(float) * ((size_t)stage_floats + mid_floats); }
 };
 struct InvGeom {
     int rq, rp, ps, pm, sub_floats, stage_floats, mid_floats;
-    __host__ __device__ InvGeom(int Hp, int TQ, int TP)
+    __host__ __device__ InvGeom(int Hp, int TQ, int TP, int R)
     {
         rq = TQ + Hp - 1;
         rp = TP + Hp - 1;
-        ps = pitch_quads_4mod8(rp);
+        // a quarter warp of the axis -1 pass reads 4 column groups (R floats apart) x 2 rows with 128-bit loads
+        ps = R == 4 ? pitch_quads_4mod8(rp) : pitch_quads_odd(rp);
         pm = pitch_quads_odd(2 * TP);
         sub_floats = rq * ps;
         stage_floats = 4 * sub_floats;
-        mid_floats = 2 * rq * pm;
+        mid_floats = (2 * rq + 8) * pm;   // + slack rows: the last row group may look past TQ when TQ % R != 0
     }
-    __host__ __device__ size_t smem_bytes(int stages) const { return sizeof(float) * ((size_t)stages * stage_floats + mid_floats); }
+    __host__ __device__ size_t smem_bytes() const { return sizeof(float) * ((size_t)stage_floats + mid_floats); }
 };
 
 __device__ __forceinline__ int sym_ext(int i, int n)  // half-sample symmetric extension, any i
@@ -106,9 +109,7 @@ __device__ __forceinline__ void cp_async4(float *dst, const float *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // (t.x, t.y) * v, rounded once per lane: see the header for why this is not __fmul2_rn
 __device__ __forceinline__ float2 mul2_exact(float2 t, float v, float2 nz) { return __ffma2_rn(t, make_float2(v, v), nz); }
@@ -132,11 +133,11 @@ __device__ __forceinline__ void mac_pair(float2 &acc, float2 t, float v, float2 
 // ---- R consecutive analysis outputs from a register window -----------------------------------------------------
 // out[r] = sum_j taps[j] * x[2r + Fp-1 - j], j ascending; x = `base` with element stride `stride` (VEC: stride 1,
 // 16-byte aligned base, 128-bit loads).
-template <int J, bool MULTI, int MODE, bool VEC>
+template <int R, int J, bool MULTI, int MODE, bool VEC>
 __device__ __forceinline__ void analysis_run(const float *base, int stride, const float2 *__restrict__ taps, int nch,
-                                             int Fp, float2 nz, float2 (&acc)[kR])
+                                             int Fp, float2 nz, float2 (&acc)[R])
 {
-    constexpr int W = 2 * kR + J - 2;
+    constexpr int W = 2 * R + J - 2;
     constexpr int W4 = (W + 3) / 4;
     float w[W4 * 4];
     if (!MULTI) {
@@ -154,13 +155,13 @@ __device__ __forceinline__ void analysis_run(const float *base, int stride, cons
         for (int jj = 0; jj < J; ++jj) {
             const float2 t = taps[jj];
 #pragma unroll
-            for (int r = 0; r < kR; ++r) {
+            for (int r = 0; r < R; ++r) {
                 mac_pair<MODE>(acc[r], t, w[2 * r + J - 1 - jj], nz, jj == 0);
             }
         }
     } else {
 #pragma unroll
-        for (int r = 0; r < kR; ++r) acc[r] = make_float2(0.f, 0.f);
+        for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
         for (int c = 0; c < nch; ++c) {
             const float *b = base + (Fp - (c + 1) * J) * stride;   // multiple of 4 elements (J % 4 == 0)
             if (VEC) {
@@ -178,7 +179,7 @@ __device__ __forceinline__ void analysis_run(const float *base, int stride, cons
             for (int jj = 0; jj < J; ++jj) {
                 const float2 t = tc[jj];
 #pragma unroll
-                for (int r = 0; r < kR; ++r) {
+                for (int r = 0; r < R; ++r) {
                     mac_pair<MODE>(acc[r], t, w[2 * r + J - 1 - jj], nz, false);
                 }
             }
@@ -205,14 +206,14 @@ __device__ __forceinline__ float2 analysis_right_edge(const FwdTaps &taps, int F
 
 // ---- R consecutive synthesis positions -> R (even, odd) output pairs ---------------------------------------------
 // pair[cc] = sum_j lo[j] * a[cc + Hp-1 - j]  (+)  sum_j hi[j] * d[cc + Hp-1 - j], each sum j ascending, one final add.
-template <int JH, bool MULTI, int MODE, bool VEC>
+template <int R, int JH, bool MULTI, int MODE, bool VEC>
 __device__ __forceinline__ void synthesis_run(const float *pa, const float *pd, int stride, const float2 *__restrict__ tlo,
-                                              const float2 *__restrict__ thi, int nch, int Hp, float2 nz, float2 (&out)[kR])
+                                              const float2 *__restrict__ thi, int nch, int Hp, float2 nz, float2 (&out)[R])
 {
-    constexpr int W = kR + JH - 1;
+    constexpr int W = R + JH - 1;
     constexpr int W4 = (W + 3) / 4;
     float wa[W4 * 4], wd[W4 * 4];
-    float2 sl[kR], sh[kR];
+    float2 sl[R], sh[R];
     if (!MULTI) {
         if (VEC) {
 #pragma unroll
@@ -230,14 +231,14 @@ __device__ __forceinline__ void synthesis_run(const float *pa, const float *pd, 
         for (int jj = 0; jj < JH; ++jj) {
             const float2 fl = tlo[jj], fh = thi[jj];
 #pragma unroll
-            for (int cc = 0; cc < kR; ++cc) {
+            for (int cc = 0; cc < R; ++cc) {
                 mac_pair<MODE>(sl[cc], fl, wa[cc + JH - 1 - jj], nz, jj == 0);
                 mac_pair<MODE>(sh[cc], fh, wd[cc + JH - 1 - jj], nz, jj == 0);
             }
         }
     } else {
 #pragma unroll
-        for (int cc = 0; cc < kR; ++cc) { sl[cc] = make_float2(0.f, 0.f); sh[cc] = make_float2(0.f, 0.f); }
+        for (int cc = 0; cc < R; ++cc) { sl[cc] = make_float2(0.f, 0.f); sh[cc] = make_float2(0.f, 0.f); }
         for (int c = 0; c < nch; ++c) {
             const int b = (Hp - (c + 1) * JH) * stride;
             if (VEC) {
@@ -257,7 +258,7 @@ __device__ __forceinline__ void synthesis_run(const float *pa, const float *pd, 
             for (int jj = 0; jj < JH; ++jj) {
                 const float2 fl = cl[jj], fh = ch[jj];
 #pragma unroll
-                for (int cc = 0; cc < kR; ++cc) {
+                for (int cc = 0; cc < R; ++cc) {
                     mac_pair<MODE>(sl[cc], fl, wa[cc + JH - 1 - jj], nz, false);
                     mac_pair<MODE>(sh[cc], fh, wd[cc + JH - 1 - jj], nz, false);
                 }
@@ -265,7 +266,7 @@ __device__ __forceinline__ void synthesis_run(const float *pa, const float *pd, 
         }
     }
 #pragma unroll
-    for (int cc = 0; cc < kR; ++cc) out[cc] = __fadd2_rn(sl[cc], sh[cc]);
+    for (int cc = 0; cc < R; ++cc) out[cc] = __fadd2_rn(sl[cc], sh[cc]);
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -276,80 +277,88 @@ struct FwdArgs {
     float negzero;   // -0.0f, deliberately a run-time value (see mul2_exact)
 };
 
-// Persistent CTAs: each walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the window of the next tile is
-// copied (cp.async) into the other shared stage while the current tile is computed.
+struct TileCoord { int plane, ty, tx; };
+__device__ __forceinline__ TileCoord tile_of(int t, int tiles_x, int tiles_xy)
+{
+    TileCoord c;
+    c.plane = t / tiles_xy;
+    const int r2 = t - c.plane * tiles_xy;
+    c.ty = r2 / tiles_x;
+    c.tx = r2 - c.ty * tiles_x;
+    return c;
+}
+
+// Persistent CTAs: each walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The input window of the next tile is
+// copied (cp.async) into the input stage while the axis -1 pass of the current tile runs out of the intermediate buffer.
 template <class T, int J, bool MULTI, int MODE>
 __global__ void __launch_bounds__(T::NT) k_dwt_fwd(const __grid_constant__ FwdTaps taps, const FwdArgs a)
 {
     extern __shared__ __align__(16) float smem[];
-    constexpr int TY = T::TY, TX = T::TX, NT = T::NT, NW = T::NW, STAGES = T::STAGES;
+    constexpr int TY = T::TY, TX = T::TX, NT = T::NT, NW = T::NW, RY = T::R1, RX = T::R2;
     constexpr bool EXACT = MODE == kExact;
     const int Fp = MULTI ? a.Fp : J;
     const FwdGeom g(Fp, TY, TX);
     const int PIN = g.pin, PM = g.pmid;
-    float *s_mid = smem + STAGES * g.stage_floats;
+    float *s_in = smem;
+    float *s_mid = smem + g.stage_floats;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ny = a.in.rows, nx = a.in.cols;
     const int my = a.cA.rows, mx = a.cA.cols;
-    const int off = (2 - Fp) & 3;             // tile column origin 2*ox0 + 2 - Fp modulo 4 (ox0 is a multiple of 16)
+    const int off = (2 - Fp) & 3;             // tile column origin 2*ox0 + 2 - Fp modulo 4 (ox0 is a multiple of 32)
     const int c4n = (g.rin_x + off + 3) >> 2;
     const float2 nz = make_float2(a.negzero, a.negzero);
     const int tiles_xy = a.tiles_x * a.tiles_y;
 
-    // stage the input window of tile t (symmetric extension resolved here); asynchronous, one commit group
-    auto issue_load = [&](int t, float *s_in) {
-        const int plane = t / tiles_xy;
-        const int r2 = t - plane * tiles_xy;
-        const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
-        const int gy0 = 2 * ty * TY + 2 - Fp;            // image row of shared row 0
-        const int gx0a = (2 * tx * TX + 2 - Fp) & ~3;    // 16-byte aligned image column of shared column 0
-        const float *src = a.in.ptr + (size_t)plane * a.in.plane_stride;
+    // stage the input window of tile t (half-sample symmetric extension resolved here); asynchronous
+    auto issue_load = [&](int t) {
+        const TileCoord c = tile_of(t, a.tiles_x, tiles_xy);
+        const int gy0 = 2 * c.ty * TY + 2 - Fp;            // image row of shared row 0
+        const int gx0a = (2 * c.tx * TX + 2 - Fp) & ~3;    // 16-byte aligned image column of shared column 0
+        const float *src = a.in.ptr + (size_t)c.plane * a.in.plane_stride;
         if (gy0 >= 0 && gy0 + g.rin_y <= ny && gx0a >= 0 && gx0a + 4 * c4n <= nx) {
-            // interior tile: every quad is one aligned 16-byte copy, no per-element tests
-            const float *src0 = src + (size_t)gy0 * a.in.pitch + gx0a;
+            // interior tile: every quad is one aligned 16-byte copy; (row, quad) advance incrementally
             const int nq = g.rin_y * c4n;
-#pragma unroll 4
+            int r = tid / c4n, c4 = tid - r * c4n;
+            const int dr = NT / c4n, dc = NT - dr * c4n;
+            const float *sp = src + (size_t)(gy0 + r) * a.in.pitch + gx0a + 4 * c4;
+            float *dp = s_in + r * PIN + 4 * c4;
+            const int s_step = dr * a.in.pitch + 4 * dc, d_step = dr * PIN + 4 * dc;
+            const int s_wrap = a.in.pitch - 4 * c4n, d_wrap = PIN - 4 * c4n;
             for (int q = tid; q < nq; q += NT) {
-                const int r = q / c4n, c4 = q - r * c4n;
-                cp_async16(s_in + r * PIN + 4 * c4, src0 + (size_t)r * a.in.pitch + 4 * c4);
+                cp_async16(dp, sp);
+                sp += s_step; dp += d_step; c4 += dc;
+                if (c4 >= c4n) { c4 -= c4n; sp += s_wrap; dp += d_wrap; }
             }
         } else {
+            // edge tile: only samples within Fp of the image can reach a stored output; the rest of the window is left
+            // as it is (it only feeds outputs beyond the sub-band, which are never stored)
             for (int r = warp; r < g.rin_y; r += NW) {
-                const float *srow = src + (size_t)sym_ext(gy0 + r, ny) * a.in.pitch;
+                const int gy = gy0 + r;
+                if (gy < -Fp || gy >= ny + Fp) continue;
+                const float *srow = src + (size_t)sym_ext(gy, ny) * a.in.pitch;
                 float *drow = s_in + r * PIN;
                 for (int c4 = lane; c4 < c4n; c4 += 32) {
                     const int gx = gx0a + 4 * c4;
                     if (gx >= 0 && gx + 3 < nx) {
                         cp_async16(drow + 4 * c4, srow + gx);
-                    } else {
+                    } else if (gx + 3 >= -Fp && gx < nx + Fp) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) cp_async4(drow + 4 * c4 + k, srow + sym_ext(gx + k, nx));
                     }
                 }
             }
         }
-        cp_async_commit();
     };
 
     int t = blockIdx.x;
-    if (STAGES == 2 && t < a.n_tiles) issue_load(t, smem);
-    for (int it = 0; t < a.n_tiles; t += gridDim.x, ++it) {
-        const float *s_in = smem + (STAGES == 2 ? (it & 1) : 0) * g.stage_floats;
-        const int tn = t + gridDim.x;
-        if (STAGES == 2 && tn < a.n_tiles) {
-            issue_load(tn, smem + ((it + 1) & 1) * g.stage_floats);   // that stage was last read before the previous barrier
-            cp_async_wait_group<1>();
-        } else {
-            if (STAGES == 1) issue_load(t, smem);   // the single stage was last read before the previous barrier
-            cp_async_wait_group<0>();
-        }
+    if (t < a.n_tiles) issue_load(t);
+    while (t < a.n_tiles) {
+        cp_async_wait_all();
         __syncthreads();   // tile t has landed; every warp is done with s_mid of the previous tile
 
-        const int plane = t / tiles_xy;
-        const int r2 = t - plane * tiles_xy;
-        const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
-        const int oy0 = ty * TY, ox0 = tx * TX;
+        const TileCoord c = tile_of(t, a.tiles_x, tiles_xy);
+        const int oy0 = c.ty * TY, ox0 = c.tx * TX;
         // does this tile hold outputs whose window overhangs the bottom / right edge (the reference visits their taps
         // in another order, see analysis_right_edge)?
         const bool edge_y = 2 * (oy0 + TY) - 1 >= ny, edge_x = 2 * (ox0 + TX) - 1 >= nx;
@@ -357,50 +366,60 @@ __global__ void __launch_bounds__(T::NT) k_dwt_fwd(const __grid_constant__ FwdTa
         // ---- axis -2 (rows index) pass: s_in -> s_mid[0..TY) = low-pass rows, s_mid[TY..2TY) = high-pass rows
         {
             const int ncg = (g.rin_x + 31) >> 5;
-            for (int wi = warp; wi < (TY / kR) * ncg; wi += NW) {
+            constexpr int NGY = (TY + RY - 1) / RY;
+            for (int wi = warp; wi < NGY * ncg; wi += NW) {
                 const int gy = wi / ncg;
-                const int c = (wi - gy * ncg) * 32 + lane;
-                if (c >= g.rin_x) continue;
-                const float *col = s_in + (2 * kR * gy) * PIN + c + off;
-                float2 acc[kR];
-                analysis_run<J, MULTI, MODE, false>(col, PIN, taps.t, a.nch, Fp, nz, acc);
+                const int col_idx = (wi - gy * ncg) * 32 + lane;
+                if (col_idx >= g.rin_x) continue;
+                const float *col = s_in + (2 * RY * gy) * PIN + col_idx + off;
+                float2 acc[RY];
+                analysis_run<RY, J, MULTI, MODE, false>(col, PIN, taps.t, a.nch, Fp, nz, acc);
                 if (EXACT && edge_y) {
 #pragma unroll
-                    for (int r = 0; r < kR; ++r) {
-                        const int i = 2 * (oy0 + kR * gy + r) + 1;
+                    for (int r = 0; r < RY; ++r) {
+                        const int i = 2 * (oy0 + RY * gy + r) + 1;
                         if (i >= ny && i - ny <= a.F - 2)
                             acc[r] = analysis_right_edge(taps, a.F, col + (2 * r + Fp - 1) * PIN, PIN, i - ny);
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < kR; ++r) {
-                    s_mid[(kR * gy + r) * PM + c] = acc[r].x;
-                    s_mid[(TY + kR * gy + r) * PM + c] = acc[r].y;
+                for (int r = 0; r < RY; ++r) {
+                    if (TY % RY == 0 || RY * gy + r < TY) {
+                        s_mid[(RY * gy + r) * PM + col_idx] = acc[r].x;
+                        s_mid[(TY + RY * gy + r) * PM + col_idx] = acc[r].y;
+                    }
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();   // s_mid complete; s_in is free again
 
-        // ---- axis -1 pass: a warp covers 8 rows x 4 column groups (conflict-free 128-bit window loads, PM/4 odd)
+        const int tn = t + gridDim.x;
+        if (tn < a.n_tiles) issue_load(tn);
+
+        // ---- axis -1 pass.  RX = 4: a warp covers 8 rows x 4 column groups; RX = 8: 16 rows x 2 column groups.  Either way
+        //      the 128-bit window loads of a quarter warp hit 8 different bank quads (PM/4 odd).
         {
-            const int gxl = lane & 3, rsub = lane >> 2;
-            constexpr int N_GB = TX / kR / 4;
-            constexpr int N_RB = (2 * TY) / 8;
-            float *pA = a.cA.ptr + (size_t)plane * a.cA.plane_stride;
-            float *pH = a.cH.ptr + (size_t)plane * a.cH.plane_stride;
-            float *pV = a.cV.ptr + (size_t)plane * a.cV.plane_stride;
-            float *pD = a.cD.ptr + (size_t)plane * a.cD.plane_stride;
+            constexpr int GPW = RX == 4 ? 4 : 2;          // column groups per warp
+            constexpr int RPW = 32 / GPW;                // rows per warp
+            const int gxl = lane % GPW, rsub = lane / GPW;
+            constexpr int N_GB = TX / RX / GPW;
+            constexpr int N_RB = (2 * TY + RPW - 1) / RPW;
+            float *pA = a.cA.ptr + (size_t)c.plane * a.cA.plane_stride;
+            float *pH = a.cH.ptr + (size_t)c.plane * a.cH.plane_stride;
+            float *pV = a.cV.ptr + (size_t)c.plane * a.cV.plane_stride;
+            float *pD = a.cD.ptr + (size_t)c.plane * a.cD.plane_stride;
             for (int wi = warp; wi < N_RB * N_GB; wi += NW) {
                 const int rb = wi / N_GB, gb = wi - rb * N_GB;
-                const int rm = rb * 8 + rsub;
-                const int gx = gb * 4 + gxl;
-                const float *row = s_mid + rm * PM + 2 * kR * gx;
-                float2 acc[kR];
-                analysis_run<J, MULTI, MODE, true>(row, 1, taps.t, a.nch, Fp, nz, acc);
-                const int oxb = ox0 + kR * gx;
+                const int rm = rb * RPW + rsub;
+                if ((2 * TY) % RPW != 0 && rm >= 2 * TY) continue;
+                const int gx = gb * GPW + gxl;
+                const float *row = s_mid + rm * PM + 2 * RX * gx;
+                float2 acc[RX];
+                analysis_run<RX, J, MULTI, MODE, true>(row, 1, taps.t, a.nch, Fp, nz, acc);
+                const int oxb = ox0 + RX * gx;
                 if (EXACT && edge_x) {
 #pragma unroll
-                    for (int cc = 0; cc < kR; ++cc) {
+                    for (int cc = 0; cc < RX; ++cc) {
                         const int i = 2 * (oxb + cc) + 1;
                         if (i >= nx && i - nx <= a.F - 2)
                             acc[cc] = analysis_right_edge(taps, a.F, row + 2 * cc + Fp - 1, 1, i - nx);
@@ -408,13 +427,22 @@ __global__ void __launch_bounds__(T::NT) k_dwt_fwd(const __grid_constant__ FwdTa
                 }
                 const bool low_rows = rm < TY;
                 const int oy = oy0 + (low_rows ? rm : rm - TY);
-                if (oy < my && oxb < mx) {   // pitch is a multiple of 4, so a whole float4 always fits
+                if (oy < my) {   // pitch is a multiple of 4, so a whole float4 always fits when its first column does
                     const size_t o = (size_t)oy * a.cA.pitch + oxb;     // the four sub-bands share pitch
-                    *reinterpret_cast<float4 *>((low_rows ? pA : pH) + o) = make_float4(acc[0].x, acc[1].x, acc[2].x, acc[3].x);
-                    *reinterpret_cast<float4 *>((low_rows ? pV : pD) + o) = make_float4(acc[0].y, acc[1].y, acc[2].y, acc[3].y);
+                    float *d0 = (low_rows ? pA : pH) + o, *d1 = (low_rows ? pV : pD) + o;
+#pragma unroll
+                    for (int h = 0; h < RX / 4; ++h) {
+                        if (oxb + 4 * h < mx) {
+                            *reinterpret_cast<float4 *>(d0 + 4 * h) =
+                                make_float4(acc[4 * h].x, acc[4 * h + 1].x, acc[4 * h + 2].x, acc[4 * h + 3].x);
+                            *reinterpret_cast<float4 *>(d1 + 4 * h) =
+                                make_float4(acc[4 * h].y, acc[4 * h + 1].y, acc[4 * h + 2].y, acc[4 * h + 3].y);
+                        }
+                    }
                 }
             }
         }
+        t = tn;
     }
 }
 
@@ -430,12 +458,13 @@ template <class T, int JH, bool MULTI, int MODE>
 __global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTaps taps, const InvArgs a)
 {
     extern __shared__ __align__(16) float smem[];
-    constexpr int TQ = T::TY, TP = T::TX, NT = T::NT, NW = T::NW, STAGES = T::STAGES;
+    constexpr int TQ = T::TY, TP = T::TX, NT = T::NT, NW = T::NW, RX = T::R1, RY = T::R2;
     const int Hp = MULTI ? a.Hp : JH;
-    const InvGeom g(Hp, TQ, TP);
+    const InvGeom g(Hp, TQ, TP, RX);
     const int PS = g.ps, PM = g.pm, RQ = g.rq;
     const int sub_floats = g.sub_floats;
-    float *s_mid = smem + STAGES * g.stage_floats; // [2][RQ][PM]: a (from cA,cV), d (from cH,cD)
+    float *s_sub = smem;                       // [cA, cV, cH, cD][RQ][PS]
+    float *s_mid = smem + g.stage_floats;      // [2][RQ][PM]: a (from cA,cV), d (from cH,cD)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int my = a.cH.rows, mx = a.cH.cols;
@@ -443,25 +472,28 @@ __global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTa
     const int tiles_xy = a.tiles_x * a.tiles_y;
     const int c4n = (g.rp + 3) >> 2;
 
-    // stage the four coefficient windows of tile t as [cA, cV, cH, cD][RQ][PS]; everything outside the sub-band is
-    // zero (it only meets zero taps or outputs that are not stored)
-    auto issue_load = [&](int t, float *s_sub) {
-        const int plane = t / tiles_xy;
-        const int r2 = t - plane * tiles_xy;
-        const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
-        const int cy0 = ty * TQ + a.H - Hp, cx0 = tx * TP + a.H - Hp;   // coefficient coordinates of shared (0, 0)
+    // stage the four coefficient windows of tile t; everything outside the sub-band is zero (it only meets zero taps
+    // or outputs that are not stored)
+    auto issue_load = [&](int t) {
+        const TileCoord c = tile_of(t, a.tiles_x, tiles_xy);
+        const int cy0 = c.ty * TQ + a.H - Hp, cx0 = c.tx * TP + a.H - Hp;   // coefficient coordinates of shared (0, 0)
         const bool aligned = (cx0 & 3) == 0;
         if (aligned && cy0 >= 0 && cy0 + RQ <= my && cx0 >= 0 && cx0 + 4 * c4n <= mx) {
             const int nq = RQ * c4n;
+            const int r0 = tid / c4n, c40 = tid - r0 * c4n;
+            const int dr = NT / c4n, dc = NT - dr * c4n;
 #pragma unroll
             for (int sb = 0; sb < 4; ++sb) {
                 const B2sImg &im = sb == 0 ? a.cA : (sb == 1 ? a.cV : (sb == 2 ? a.cH : a.cD));
-                const float *src0 = im.ptr + (size_t)plane * im.plane_stride + (size_t)cy0 * im.pitch + cx0;
-                float *dst0 = s_sub + sb * sub_floats;
-#pragma unroll 2
+                const float *sp = im.ptr + (size_t)c.plane * im.plane_stride + (size_t)(cy0 + r0) * im.pitch + cx0 + 4 * c40;
+                float *dp = s_sub + sb * sub_floats + r0 * PS + 4 * c40;
+                const int s_step = dr * im.pitch + 4 * dc, d_step = dr * PS + 4 * dc;
+                const int s_wrap = im.pitch - 4 * c4n, d_wrap = PS - 4 * c4n;
+                int c4 = c40;
                 for (int q = tid; q < nq; q += NT) {
-                    const int r = q / c4n, c4 = q - r * c4n;
-                    cp_async16(dst0 + r * PS + 4 * c4, src0 + (size_t)r * im.pitch + 4 * c4);
+                    cp_async16(dp, sp);
+                    sp += s_step; dp += d_step; c4 += dc;
+                    if (c4 >= c4n) { c4 -= c4n; sp += s_wrap; dp += d_wrap; }
                 }
             }
         } else {
@@ -471,7 +503,7 @@ __global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTa
                 float *drow = s_sub + sb * sub_floats + ry * PS;
                 const bool row_ok = y >= 0 && y < my;
                 const B2sImg &im = sb == 0 ? a.cA : (sb == 1 ? a.cV : (sb == 2 ? a.cH : a.cD));
-                const float *srow = im.ptr + (size_t)plane * im.plane_stride + (size_t)(row_ok ? y : 0) * im.pitch;
+                const float *srow = im.ptr + (size_t)c.plane * im.plane_stride + (size_t)(row_ok ? y : 0) * im.pitch;
                 for (int c4 = lane; c4 < c4n; c4 += 32) {
                     const int x = cx0 + 4 * c4;
                     if (row_ok && aligned && x >= 0 && x + 3 < mx) {
@@ -486,32 +518,22 @@ __global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTa
                 }
             }
         }
-        cp_async_commit();
     };
 
     int t = blockIdx.x;
-    if (STAGES == 2 && t < a.n_tiles) issue_load(t, smem);
-    for (int it = 0; t < a.n_tiles; t += gridDim.x, ++it) {
-        const float *s_sub = smem + (STAGES == 2 ? (it & 1) : 0) * g.stage_floats;
-        const int tn = t + gridDim.x;
-        if (STAGES == 2 && tn < a.n_tiles) {
-            issue_load(tn, smem + ((it + 1) & 1) * g.stage_floats);
-            cp_async_wait_group<1>();
-        } else {
-            if (STAGES == 1) issue_load(t, smem);
-            cp_async_wait_group<0>();
-        }
-        __syncthreads();
+    if (t < a.n_tiles) issue_load(t);
+    while (t < a.n_tiles) {
+        cp_async_wait_all();
+        __syncthreads();   // tile t has landed; every warp is done with s_mid of the previous tile
 
-        const int plane = t / tiles_xy;
-        const int r2 = t - plane * tiles_xy;
-        const int ty = r2 / a.tiles_x, tx = r2 - ty * a.tiles_x;
-        const int q0 = ty * TQ, p0 = tx * TP;
+        const TileCoord c = tile_of(t, a.tiles_x, tiles_xy);
+        const int q0 = c.ty * TQ, p0 = c.tx * TP;
 
         // ---- axis -1 synthesis: (cA,cV) -> a, (cH,cD) -> d   [idwtn handles the last axis first]
+        //      a warp covers 8 rows x 4 groups of RX coefficient positions (PS/4 odd: conflict-free 128-bit loads)
         {
             const int gxl = lane & 3, rsub = lane >> 2;
-            constexpr int N_GB = TP / kR / 4;
+            constexpr int N_GB = TP / RX / 4;
             const int n_rb = (2 * RQ + 7) >> 3;
             for (int wi = warp; wi < n_rb * N_GB; wi += NW) {
                 const int rb = wi / N_GB, gb = wi - rb * N_GB;
@@ -520,41 +542,46 @@ __global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTa
                 const int sel = rr >= RQ ? 1 : 0;
                 const int ry = rr - sel * RQ;
                 const int gx = gb * 4 + gxl;
-                const float *rl = s_sub + (2 * sel) * sub_floats + ry * PS + kR * gx;
+                const float *rl = s_sub + (2 * sel) * sub_floats + ry * PS + RX * gx;
                 const float *rh = rl + sub_floats;
-                float2 o[kR];  // (even, odd) output pairs
-                synthesis_run<JH, MULTI, MODE, true>(rl, rh, 1, taps.lo, taps.hi, a.nch, Hp, nz, o);
-                float *dst = s_mid + (size_t)(sel * RQ + ry) * PM + 2 * kR * gx;
-                *reinterpret_cast<float4 *>(dst) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
-                *reinterpret_cast<float4 *>(dst + 4) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+                float2 o[RX];  // (even, odd) output pairs
+                synthesis_run<RX, JH, MULTI, MODE, true>(rl, rh, 1, taps.lo, taps.hi, a.nch, Hp, nz, o);
+                float *dst = s_mid + (size_t)(sel * RQ + ry) * PM + 2 * RX * gx;
+#pragma unroll
+                for (int h = 0; h < RX / 2; ++h)
+                    *reinterpret_cast<float4 *>(dst + 4 * h) = make_float4(o[2 * h].x, o[2 * h].y, o[2 * h + 1].x, o[2 * h + 1].y);
             }
         }
-        __syncthreads();
+        __syncthreads();   // s_mid complete; s_sub is free again
+
+        const int tn = t + gridDim.x;
+        if (tn < a.n_tiles) issue_load(tn);
 
         // ---- axis -2 synthesis: (a, d) -> out rows 2q, 2q+1
         {
-            constexpr int NGQ = TQ / kR;
+            constexpr int NGQ = (TQ + RY - 1) / RY;
             constexpr int NCG = (2 * TP) / 32;
-            float *dstp = a.out.ptr + (size_t)plane * a.out.plane_stride;
+            float *dstp = a.out.ptr + (size_t)c.plane * a.out.plane_stride;
             for (int wi = warp; wi < NGQ * NCG; wi += NW) {
                 const int gq = wi / NCG;
                 const int x = (wi - gq * NCG) * 32 + lane;
-                const float *ca = s_mid + (size_t)(kR * gq) * PM + x;
+                const float *ca = s_mid + (size_t)(RY * gq) * PM + x;
                 const float *cd = ca + (size_t)RQ * PM;
-                float2 o[kR];  // (row 2q, row 2q+1)
-                synthesis_run<JH, MULTI, MODE, false>(ca, cd, PM, taps.lo, taps.hi, a.nch, Hp, nz, o);
+                float2 o[RY];  // (row 2q, row 2q+1)
+                synthesis_run<RY, JH, MULTI, MODE, false>(ca, cd, PM, taps.lo, taps.hi, a.nch, Hp, nz, o);
                 const int ox = 2 * p0 + x;
                 if (ox < a.out.cols) {
-                    const int oyb = 2 * (q0 + kR * gq);
+                    const int oyb = 2 * (q0 + RY * gq);
 #pragma unroll
-                    for (int k = 0; k < kR; ++k) {
+                    for (int k = 0; k < RY; ++k) {
+                        if (TQ % RY != 0 && RY * gq + k >= TQ) continue;
                         if (oyb + 2 * k < a.out.rows) dstp[(size_t)(oyb + 2 * k) * a.out.pitch + ox] = o[k].x;
                         if (oyb + 2 * k + 1 < a.out.rows) dstp[(size_t)(oyb + 2 * k + 1) * a.out.pitch + ox] = o[k].y;
                     }
                 }
             }
         }
-        // the next iteration's barrier (after its wait) orders these s_mid reads before the next axis -1 pass
+        t = tn;
     }
 }
 
@@ -584,13 +611,13 @@ void pick_inv_chunk(int H, int *JH, int *nch)
     *nch = best_hp / best;
 }
 
-// tile shapes.  Measured on B200 (db10, 2648^2, 8 planes): one tile per CTA with ~4 CTAs per SM (single stage) beats
-// persistent CTAs with two stages (2 CTAs per SM): 32 vs 42 us/plane for the level-1 analysis.  The two-stage variant
-// stays selectable (B2S_DWT_PERSIST=1) for tuning.
-typedef Tile<16, 64, 256, 2> FwdTileA;
-typedef Tile<32, 32, 256, 2> InvTileA;
-typedef Tile<16, 64, 256, 1> FwdTileS;
-typedef Tile<32, 32, 256, 1> InvTileS;
+// tile shapes (selectable with B2S_DWT_CFG for tuning): 0 = R 4, 256 threads; 1 = R 8, 128 threads
+typedef Tile<16, 64, 256, 4> FwdTile0;
+typedef Tile<32, 32, 256, 4> InvTile0;
+typedef Tile<32, 64, 256, 4, 8> FwdTile1;   // y-pass 40 warp items, x-pass 16
+typedef Tile<31, 64, 256, 8, 4> InvTile1;   // x-pass 20 warp items, y-pass 32
+typedef Tile<32, 64, 256, 8, 8> FwdTile2;
+typedef Tile<31, 64, 256, 8, 8> InvTile2;
 
 int dev_knob(const char *name, int dflt)
 {
@@ -602,56 +629,73 @@ template <class T, int J, bool MULTI, int MODE>
 void launch_fwd_t(const FwdTaps &ft, FwdArgs a, int n_planes, int sm_count, cudaStream_t s)
 {
     const FwdGeom g(a.Fp, T::TY, T::TX);
-    const size_t bytes = g.smem_bytes(T::STAGES);
+    const size_t bytes = g.smem_bytes();
     a.tiles_x = (a.cA.cols + T::TX - 1) / T::TX;
     a.tiles_y = (a.cA.rows + T::TY - 1) / T::TY;
     a.n_tiles = a.tiles_x * a.tiles_y * n_planes;
     int per_sm = (int)(kSmemPerSm / (bytes + 1024));
     if (per_sm > 2048 / T::NT) per_sm = 2048 / T::NT;
     if (per_sm < 1) per_sm = 1;
-    const int grid = (T::STAGES == 1 || a.n_tiles < sm_count * per_sm) ? a.n_tiles : sm_count * per_sm;
+    static const int persist = dev_knob("B2S_DWT_PERSIST", 0);
+    const int grid = (!persist || a.n_tiles < sm_count * per_sm) ? a.n_tiles : sm_count * per_sm;
     cudaFuncSetAttribute(k_dwt_fwd<T, J, MULTI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     k_dwt_fwd<T, J, MULTI, MODE><<<grid, T::NT, bytes, s>>>(ft, a);
 }
 template <int J, bool MULTI>
 void launch_fwd_j(const FwdTaps &ft, const FwdArgs &a, int n_planes, int exact, int sm_count, cudaStream_t s)
 {
-    static const int persist = dev_knob("B2S_DWT_PERSIST", 0);
-    if (persist && FwdGeom(a.Fp, FwdTileA::TY, FwdTileA::TX).smem_bytes(FwdTileA::STAGES) <= (size_t)kSmemPerSm - 1024) {
-        if (exact) launch_fwd_t<FwdTileA, J, MULTI, kExact>(ft, a, n_planes, sm_count, s);
-        else launch_fwd_t<FwdTileA, J, MULTI, kFast>(ft, a, n_planes, sm_count, s);
-    } else {
-        if (exact) launch_fwd_t<FwdTileS, J, MULTI, kExact>(ft, a, n_planes, sm_count, s);
-        else launch_fwd_t<FwdTileS, J, MULTI, kFast>(ft, a, n_planes, sm_count, s);
+    static const int cfg = dev_knob("B2S_DWT_CFG", 0);
+    const bool fits1 = FwdGeom(a.Fp, FwdTile1::TY, FwdTile1::TX).smem_bytes() <= (size_t)kSmemPerSm - 1024;
+    if (cfg == 1 && fits1 && J == 20 && !MULTI) {
+        constexpr int JJ = (J == 20 && !MULTI) ? J : 2;   // R = 8 is instantiated for the headline filter length only
+        if (exact) launch_fwd_t<FwdTile1, JJ, false, kExact>(ft, a, n_planes, sm_count, s);
+        else launch_fwd_t<FwdTile1, JJ, false, kFast>(ft, a, n_planes, sm_count, s);
+        return;
     }
+    if (cfg == 2 && J == 20 && !MULTI) {
+        constexpr int JJ = (J == 20 && !MULTI) ? J : 2;
+        if (exact) launch_fwd_t<FwdTile2, JJ, false, kExact>(ft, a, n_planes, sm_count, s);
+        else launch_fwd_t<FwdTile2, JJ, false, kFast>(ft, a, n_planes, sm_count, s);
+        return;
+    }
+    if (exact) launch_fwd_t<FwdTile0, J, MULTI, kExact>(ft, a, n_planes, sm_count, s);
+    else launch_fwd_t<FwdTile0, J, MULTI, kFast>(ft, a, n_planes, sm_count, s);
 }
 
 template <class T, int JH, bool MULTI, int MODE>
 void launch_inv_t(const InvTaps &it, InvArgs a, int n_planes, int sm_count, cudaStream_t s)
 {
-    const InvGeom g(a.Hp, T::TY, T::TX);
-    const size_t bytes = g.smem_bytes(T::STAGES);
+    const InvGeom g(a.Hp, T::TY, T::TX, T::R1);
+    const size_t bytes = g.smem_bytes();
     a.tiles_x = (a.out.cols + 2 * T::TX - 1) / (2 * T::TX);
     a.tiles_y = (a.out.rows + 2 * T::TY - 1) / (2 * T::TY);
     a.n_tiles = a.tiles_x * a.tiles_y * n_planes;
     int per_sm = (int)(kSmemPerSm / (bytes + 1024));
     if (per_sm > 2048 / T::NT) per_sm = 2048 / T::NT;
     if (per_sm < 1) per_sm = 1;
-    const int grid = (T::STAGES == 1 || a.n_tiles < sm_count * per_sm) ? a.n_tiles : sm_count * per_sm;
+    static const int persist = dev_knob("B2S_DWT_PERSIST", 0);
+    const int grid = (!persist || a.n_tiles < sm_count * per_sm) ? a.n_tiles : sm_count * per_sm;
     cudaFuncSetAttribute(k_dwt_inv<T, JH, MULTI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     k_dwt_inv<T, JH, MULTI, MODE><<<grid, T::NT, bytes, s>>>(it, a);
 }
 template <int JH, bool MULTI>
 void launch_inv_j(const InvTaps &it, const InvArgs &a, int n_planes, int exact, int sm_count, cudaStream_t s)
 {
-    static const int persist = dev_knob("B2S_DWT_PERSIST", 0);
-    if (persist && InvGeom(a.Hp, InvTileA::TY, InvTileA::TX).smem_bytes(InvTileA::STAGES) <= (size_t)kSmemPerSm - 1024) {
-        if (exact) launch_inv_t<InvTileA, JH, MULTI, kExact>(it, a, n_planes, sm_count, s);
-        else launch_inv_t<InvTileA, JH, MULTI, kFast>(it, a, n_planes, sm_count, s);
-    } else {
-        if (exact) launch_inv_t<InvTileS, JH, MULTI, kExact>(it, a, n_planes, sm_count, s);
-        else launch_inv_t<InvTileS, JH, MULTI, kFast>(it, a, n_planes, sm_count, s);
+    static const int cfg = dev_knob("B2S_DWT_CFG", 0);
+    if (cfg == 1 && JH == 10 && !MULTI) {
+        constexpr int JJ = (JH == 10 && !MULTI) ? JH : 1;
+        if (exact) launch_inv_t<InvTile1, JJ, false, kExact>(it, a, n_planes, sm_count, s);
+        else launch_inv_t<InvTile1, JJ, false, kFast>(it, a, n_planes, sm_count, s);
+        return;
     }
+    if (cfg == 2 && JH == 10 && !MULTI) {
+        constexpr int JJ = (JH == 10 && !MULTI) ? JH : 1;
+        if (exact) launch_inv_t<InvTile2, JJ, false, kExact>(it, a, n_planes, sm_count, s);
+        else launch_inv_t<InvTile2, JJ, false, kFast>(it, a, n_planes, sm_count, s);
+        return;
+    }
+    if (exact) launch_inv_t<InvTile0, JH, MULTI, kExact>(it, a, n_planes, sm_count, s);
+    else launch_inv_t<InvTile0, JH, MULTI, kFast>(it, a, n_planes, sm_count, s);
 }
 
 }  // namespace
@@ -661,8 +705,8 @@ int b2s_dwt_max_smem(int F)
     int J, nch, JH, nchi;
     pick_fwd_chunk(F, &J, &nch);
     pick_inv_chunk(F / 2, &JH, &nchi);
-    const size_t a = FwdGeom(J * nch, FwdTileS::TY, FwdTileS::TX).smem_bytes(FwdTileS::STAGES);
-    const size_t b = InvGeom(JH * nchi, InvTileS::TY, InvTileS::TX).smem_bytes(InvTileS::STAGES);
+    const size_t a = FwdGeom(J * nch, FwdTile0::TY, FwdTile0::TX).smem_bytes();
+    const size_t b = InvGeom(JH * nchi, InvTile0::TY, InvTile0::TX, InvTile0::R1).smem_bytes();
     return (int)((a > b ? a : b) + 1024);
 }
 
