@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--planes", type=int, default=250, help="planes per step per GPU")
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("B200STRIPE_MAX_BATCH", "8")))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("B200STRIPE_MAX_BATCH", "32")))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic planes (tiled to --planes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

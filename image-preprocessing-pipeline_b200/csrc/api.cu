@@ -239,7 +239,7 @@ struct b2s_plan {
     B2sTaps taps;
     int B = 1;            // max batch
     // device workspace (one slot per in-flight batch)
-    static constexpr int kSlots = 2;
+    static constexpr int kSlots = 3;
     struct Slot {
         float *padded = nullptr;
         float *sub[B2S_MAX_LEVELS + 1][4] = {};
@@ -758,9 +758,16 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
         pend[si].active = false;
         return B2S_OK;
     };
+    // batch sizes ramp up from 4 planes and down again at the end of the call: the first kernels start after a short
+    // copy and the last device-to-host copy is short, so the pipeline fill / drain costs little
     int si = 0;
-    for (int64_t z = 0; z < n_planes; z += B, si ^= 1) {
-        const int nb = (int)std::min<int64_t>(B, n_planes - z);
+    int64_t z = 0;
+    int nb_next = B < 4 ? B : 4;
+    while (z < n_planes) {
+        const int64_t left = n_planes - z;
+        int nb = (int)std::min<int64_t>(nb_next, left);
+        if (left > 4 && nb > left / 2) nb = (int)std::max<int64_t>(4, left / 2);   // ramp down: halve what is left
+        nb_next = std::min(B, nb_next * 2);
         b2s_plan::Slot &s = pl->slot[si];
         int rc = drain(si);
         if (rc) return rc;
@@ -782,6 +789,8 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
         }
         CU(ctx, cudaEventRecord(s.done, s.stream));
         pend[si] = {z, nb, true};
+        z += nb;
+        si = (si + 1) % b2s_plan::kSlots;
     }
     for (int k = 0; k < b2s_plan::kSlots; ++k) {
         int rc = drain(k);
