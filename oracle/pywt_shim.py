@@ -22,7 +22,7 @@ _LIB = None
 
 def build(force: bool = False) -> Path:
     so = _HERE / "_build" / "liboracle.so"
-    if force or not so.exists() or so.stat().st_mtime < (_HERE / "pywt_c.c").stat().st_mtime:
+    if force or not so.exists() or so.stat().st_mtime < max((_HERE / f).stat().st_mtime for f in ("pywt_c.c", "pocketfft_c.c")):
         subprocess.check_call(["make", "-s", "-C", str(_HERE)])
     return so
 
