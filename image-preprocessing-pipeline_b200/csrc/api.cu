@@ -260,6 +260,7 @@ struct b2s_plan {
     int *d_row_src = nullptr, *d_row_start = nullptr, *d_row_targets = nullptr, *d_colmap = nullptr;
     float *d_lut = nullptr;
     std::map<int, B2sFftPlan> fft;                  // by length
+    std::map<int, B2sXfftPlan *> xfft;              // by length: rounding-exact transform (exact mode, covered lengths)
     float *d_notch[2][B2S_MAX_LEVELS + 1][2] = {};  // [pass][level][axis: 0 = cH rows, 1 = cV cols]
     int64_t workspace_bytes = 0;
     std::vector<void *> allocs;
@@ -399,6 +400,12 @@ int build_tables(b2s_plan *pl)
                         CU(ctx, cudaMemcpy(*u.dst, u.src->data(), sizeof(float2) * u.src->size(), cudaMemcpyHostToDevice));
                     }
                     pl->fft[n] = fp;
+                    static const bool no_xfft = getenv("B2S_NO_XFFT") != nullptr;
+                    if (p.exact && !no_xfft) {
+                        B2sXfftPlan *xp = b2s_xfft_create(n);
+                        if (xp) pl->xfft[n] = xp;
+                        CU(ctx, cudaGetLastError());
+                    }
                 }
                 const double width_frac = g.pass_sigma[pass] / (double)img_len;
                 const double sigma_l = (double)other * width_frac;
@@ -523,11 +530,15 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             {
                 for (int l = 1; l <= g.levels; ++l) {
                     ClassTimer t(ctx, st, B2S_K_NOTCH, p.bidirectional ? 2 : 1, l);
-                    b2s_launch_notch(pl->fft[g.mx[l]], pl->d_notch[pass][l][0], img_of(pl, s.sub[l][1], l), 0, nb,
-                                     ctx->sm_count, st);
-                    if (p.bidirectional)
-                        b2s_launch_notch(pl->fft[g.my[l]], pl->d_notch[pass][l][1], img_of(pl, s.sub[l][2], l), 1, nb,
-                                         ctx->sm_count, st);
+                    auto notch = [&](int n, const float *gt, float *band, int along_cols) {
+                        auto it = pl->xfft.find(n);
+                        if (it != pl->xfft.end())
+                            b2s_launch_notch_exact(it->second, gt, img_of(pl, band, l), along_cols, nb, ctx->sm_count, st);
+                        else
+                            b2s_launch_notch(pl->fft[n], gt, img_of(pl, band, l), along_cols, nb, ctx->sm_count, st);
+                    };
+                    notch(g.mx[l], pl->d_notch[pass][l][0], s.sub[l][1], 0);
+                    if (p.bidirectional) notch(g.my[l], pl->d_notch[pass][l][1], s.sub[l][2], 1);
                 }
             }
             if (p.debug_stop_after == B2S_STAGE_NOTCH) return B2S_OK;
@@ -689,6 +700,7 @@ void b2s_plan_destroy(b2s_plan *pl)
     cudaSetDevice(pl->ctx->device);
     cudaDeviceSynchronize();
     for (void *p : pl->allocs) cudaFree(p);
+    for (auto &kv : pl->xfft) b2s_xfft_destroy(kv.second);
     for (auto &s : pl->slot) {
         if (s.h_in) cudaFreeHost(s.h_in);
         if (s.h_out) cudaFreeHost(s.h_out);
@@ -718,6 +730,21 @@ int b2s_plan_set_flat(b2s_plan *pl, const float *flat, int is_device)
         if (rc) return rc;
     }
     CU(ctx, cudaMemcpy(pl->d_flat, flat, bytes, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return B2S_OK;
+}
+
+int b2s_plan_set_notch(b2s_plan *pl, int pass, int level, int axis, const float *g, int n)
+{
+    if (!pl || !g) return B2S_ERR_INVALID;
+    b2s_context *ctx = pl->ctx;
+    const Geometry &gm = pl->g;
+    if (pass < 0 || pass >= gm.n_passes || level < 1 || level > gm.levels || axis < 0 || axis > (pl->p.bidirectional ? 1 : 0))
+        return fail(ctx, B2S_ERR_INVALID, "b2s_plan_set_notch: no such table (pass %d, level %d, axis %d)", pass, level, axis);
+    const int len = axis == 0 ? gm.mx[level] : gm.my[level];
+    if (n != len) return fail(ctx, B2S_ERR_INVALID, "b2s_plan_set_notch: table has %d entries, sub-band side is %d", n, len);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    CU(ctx, cudaMemcpy(pl->d_notch[pass][level][axis], g, sizeof(float) * n, cudaMemcpyHostToDevice));
     return B2S_OK;
 }
 

@@ -109,3 +109,12 @@ void b2s_fft_plan_init(B2sFftPlan *fp, int n, B2sFftHostTables *host);
 void b2s_launch_notch(const B2sFftPlan &fp, const float *d_notch, const B2sImg &img, int along_cols, int n_planes,
                       int sm_count, cudaStream_t s);
 size_t b2s_notch_smem(int n);
+
+// rfft_exact.cu -------------------------------------------------------------------------------------------------
+// rounding-exact mirror of scipy.fftpack.rfft / irfft (float32); nullptr when the length class is not covered
+struct B2sXfftPlan;
+int b2s_xfft_supported(int n);
+B2sXfftPlan *b2s_xfft_create(int n);
+void b2s_xfft_destroy(B2sXfftPlan *pl);
+void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B2sImg &img, int along_cols, int n_planes,
+                            int sm_count, cudaStream_t s);

@@ -53,7 +53,7 @@ class PlanInfo(C.Structure):
 
 EXPORTS = (
     "b2s_version", "b2s_params_default", "b2s_create", "b2s_destroy", "b2s_last_error", "b2s_device_sm_count",
-    "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_plan_set_flat", "b2s_run",
+    "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_run",
     "b2s_host_alloc", "b2s_host_free", "b2s_launch_count", "b2s_timing_enable", "b2s_timing_read",
     "b2s_debug_read", "b2s_debug_math",
 )
@@ -92,6 +92,7 @@ def lib():
             L.b2s_plan_query.argtypes = [vp, C.POINTER(PlanInfo)]
             L.b2s_plan_geometry.argtypes = [C.POINTER(Params), C.POINTER(PlanInfo), C.c_char_p, C.c_size_t]
             L.b2s_plan_set_flat.argtypes = [vp, vp, i32]
+            L.b2s_plan_set_notch.argtypes = [vp, i32, i32, i32, vp, i32]
             L.b2s_run.argtypes = [vp, vp, vp, i64, i32, i32, vp]
             L.b2s_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
             L.b2s_host_free.argtypes = [vp, vp]
@@ -281,6 +282,11 @@ class Plan:
         else:
             f = np.ascontiguousarray(flat, dtype=np.float32)
             self.ctx.check(lib().b2s_plan_set_flat(self._h, f.ctypes.data, 0))
+
+    def set_notch(self, pass_idx: int, level: int, axis: int, g: np.ndarray):
+        """upload a host-evaluated np_notch table (float32) for (pass, 1-based level, axis 0 = cH / 1 = cV)."""
+        g = np.ascontiguousarray(g, dtype=np.float32)
+        self.ctx.check(lib().b2s_plan_set_notch(self._h, pass_idx, level, axis, C.c_void_p(g.ctypes.data), int(g.size)))
 
     def run_host(self, src: np.ndarray, dst: np.ndarray = None) -> np.ndarray:
         """src: (n, H, W) or (H, W) numpy array in host memory (pinned or pageable)."""

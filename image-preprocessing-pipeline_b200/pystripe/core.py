@@ -330,11 +330,28 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
         p.exact = int(EXACT if exact is None else exact)
         plan = _native.Plan(_native.context(device), p, dec_lo=taps, flat=flat)
         plan._flat_ref = flat  # keep id(flat) stable while the plan is cached
+        _upload_numpy_notch_tables(plan, s1, s2)
         if len(_plans) > 16:   # plans own GPU workspace: keep the cache small
             _, old = _plans.popitem()
             old.close()
         _plans[key] = plan
         return plan
+
+
+def _upload_numpy_notch_tables(plan, s1, s2):
+    """np_notch (core.py:637-667) is numpy arithmetic in the reference; numpy's float32 exp is not libm's expf, so the
+    tables are evaluated here, by numpy, exactly as np_filter_coefficient (core.py:749-754) does, and handed to the
+    library.  sigma of a level = (length of the OTHER sub-band axis) * sigma / (padded image rows or cols)."""
+    info = plan.info
+    if info.n_passes == 0:
+        return
+    sigmas = (s1,) if info.n_passes == 1 else (s1, s2)
+    for pi, sg in enumerate(sigmas):
+        for lvl in range(1, info.levels + 1):
+            rows, cols = info.level_rows[lvl - 1], info.level_cols[lvl - 1]
+            plan.set_notch(pi, lvl, 0, np_notch(cols, rows * (sg / info.padded_height)))
+            if plan.params.bidirectional:
+                plan.set_notch(pi, lvl, 1, np_notch(rows, cols * (sg / info.padded_width)))
 
 
 def clear_plan_cache():

@@ -119,6 +119,12 @@ int b2s_plan_geometry(const b2s_params *params, b2s_plan_info *info, char *err, 
 /* replaces: normalize_flat result captured in batch_filter's arg dict (core.py:1948-1953); flat is (height,width) f32 */
 int b2s_plan_set_flat(b2s_plan *plan, const float *flat, int is_device);
 
+/* replaces: np_notch (core.py:637-667) as evaluated by the host's numpy.  The plan builds its own float32 tables with
+ * libm expf; numpy's float32 exp is a SIMD routine whose last bit differs from libm on ~40 % of arguments, so a host
+ * that wants the reference's numpy values bit for bit uploads them here.  pass: 0 or 1 (sigma1 / sigma2 pass),
+ * level: 1-based, axis: 0 = cH filtered along axis -1, 1 = cV along axis -2 (bidirectional); g: n host floats. */
+int b2s_plan_set_notch(b2s_plan *plan, int pass, int level, int axis, const float *g, int n);
+
 /*
  * replaces: process_img(img, ...) / filter_streaks(img, ...) applied to n_planes independent planes
  * (core.py:1190, 982; driven per file by read_filter_save, core.py:1557).

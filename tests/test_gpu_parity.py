@@ -113,6 +113,44 @@ def test_notch_stage_close_to_pocketfft():
             assert np.abs(g - r).max() <= 1e-5 * max(1.0, float(np.abs(r).max()))
 
 
+def _mirrored(n):
+    # length classes whose scipy.fftpack float32 transform the GPU reproduces rounding for rounding (rfft_exact.cu)
+    return n >= 2 and not (n > 1000 and n % 2 == 0)
+
+
+@pytest.mark.parametrize("shape,wavelet,sigma", [
+    ((96, 128), "db10", (24, 24)),      # small radices 2,3,4,5 and generic 7..31
+    ((300, 274), "db2", (8, 8)),        # 149 / 157 primes >= 135: Bluestein passes
+    ((538, 560), "db3", (6, 6)),        # 2*137 = 274, 3*... composites with a Bluestein factor
+    ((700, 650), "db4", (20, 20)),
+    ((1290, 40), "db2", (4, 4)),        # odd length > 1000 along axis -2 (bidirectional)
+])
+def test_notch_stage_bit_exact_vs_scipy_fftpack(shape, wavelet, sigma):
+    img = synth.plane(9, shape)
+    plan = _plan(shape, 1, sigma=sigma, wavelet=wavelet, stop_after=3, bidirectional=True)
+    plan.run_host(img)
+    base, py, px = orc.padded_geometry(shape, sigma, "wrap")
+    padded = np.pad(orc.log1p_f32(img.astype(np.float32)), ((base, base + py), (base, base + px)), mode="wrap")
+    coeffs = pw.wavedec2(padded, wavelet)
+    L = len(coeffs) - 1
+    checked = 0
+    lengths = []
+    for lvl in range(1, L + 1):
+        ch, cv, _ = coeffs[L - lvl + 1]
+        rh = orc.np_filter_coefficient(ch.copy(), sigma[0] / padded.shape[0], axis=-1)
+        rv = orc.np_filter_coefficient(cv.copy(), sigma[0] / padded.shape[1], axis=-2)
+        gh, gv = plan.debug_read(2, lvl), plan.debug_read(3, lvl)
+        for g, r, n in ((gh, rh, ch.shape[1]), (gv, rv, cv.shape[0])):
+            lengths.append(n)
+            if _mirrored(n):
+                assert np.array_equal(g, r), f"level {lvl} n={n}: {np.abs(g - r).max()} ({(g != r).mean():.3%} differ)"
+                checked += 1
+            else:
+                assert np.abs(g - r).max() <= 1e-5 * max(1.0, float(np.abs(r).max()))
+    REPORT[f"notch_exact_lengths/{shape}/{wavelet}"] = lengths
+    assert checked > 0
+
+
 def _gpu_case(kind, img, kw):
     from pystripe import core
     if kind == "filter_streaks":
