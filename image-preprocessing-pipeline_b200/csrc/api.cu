@@ -99,21 +99,18 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
     const bool ds = p.process_img && (p.down_sample_y > 0 || p.down_sample_x > 0) && (g.dsy > 1 || g.dsx > 1);
     g.work_rows = ds ? (p.height + g.dsy - 1) / g.dsy : p.height;
     g.work_cols = ds ? (p.width + g.dsx - 1) / g.dsx : p.width;
-    if (p.process_img && p.down_sample_method > B2S_DS_MEAN && ds)
-        return fail(ctx, B2S_ERR_UNSUPPORTED, "down_sample_method 'median' is not implemented on the GPU path");
+    if (p.process_img && ds && (p.down_sample_method < B2S_DS_MAX || p.down_sample_method > B2S_DS_MEDIAN))
+        return fail(ctx, B2S_ERR_INVALID, "unsupported down-sampling method");
+    if (p.process_img && ds && p.down_sample_method == B2S_DS_MEDIAN && g.dsy * g.dsx > 64)
+        return fail(ctx, B2S_ERR_UNSUPPORTED, "median down-sampling over more than 64 samples per block is not implemented");
 
     // dtype bookkeeping (process_img order: flat -> gaussian -> block_reduce -> filter_streaks)
     int dt = p.in_dtype;
     const bool flat = p.process_img && p.has_flat;
     if (flat) dt = B2S_F32;
     const bool gauss = p.process_img && p.gaussian && !p.reference_quirks;
-    if (gauss && dt == B2S_F32)
-        return fail(ctx, B2S_ERR_UNSUPPORTED, "gaussian_filter_2d on a float32 image (flat given) is not implemented");
     if (gauss && dt == B2S_U8) return fail(ctx, B2S_ERR_UNSUPPORTED, "gaussian_filter_2d on uint8 is not implemented");
-    if (ds && p.down_sample_method == B2S_DS_MEAN) {
-        if (dt == B2S_F32) return fail(ctx, B2S_ERR_UNSUPPORTED, "mean down-sampling of a float32 image is not implemented");
-        dt = B2S_F32;
-    }
+    if (ds && p.down_sample_method >= B2S_DS_MEAN) dt = B2S_F32;   // float64 in the reference; float32 holds what reaches log1p
     g.work_dtype = dt;
     g.fuse_flat = flat && !gauss && !ds;
 
@@ -482,7 +479,8 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
     }
     if (p.process_img && p.gaussian && !p.reference_quirks) {
         ClassTimer t(ctx, st, B2S_K_PRE, 1);
-        b2s_launch_gauss5_u16((const uint16_t *)cur, (uint16_t *)s.pre_b, g.in_rows, g.in_cols, nb, st);
+        if (cur_dt == B2S_F32) b2s_launch_gauss5_f32((const float *)cur, (float *)s.pre_b, g.in_rows, g.in_cols, nb, st);
+        else b2s_launch_gauss5_u16((const uint16_t *)cur, (uint16_t *)s.pre_b, g.in_rows, g.in_cols, nb, st);
         cur = s.pre_b;
     }
     if (g.work_rows != g.in_rows || g.work_cols != g.in_cols) {

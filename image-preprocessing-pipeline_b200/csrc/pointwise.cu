@@ -249,11 +249,42 @@ __global__ void __launch_bounds__(256) k_minmax(const void *in, int dtype, size_
 {
     const size_t plane = blockIdx.y;
     unsigned lo = 0xffffffffu, hi = 0u;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane_elems; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    const int esz = dtype == B2S_F32 ? 4 : (dtype == B2S_U16 ? 2 : 1);
+    const char *base = reinterpret_cast<const char *>(in) + plane * plane_elems * esz;
+    // 128-bit loads over the aligned body (16 bytes = 8 u16 / 16 u8 / 4 f32 per thread and trip), scalar tail
+    size_t body = 0;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+        const size_t per = 16 / esz, nvec = plane_elems / per;
+        body = nvec * per;
+        const uint4 *v = reinterpret_cast<const uint4 *>(base);
+#pragma unroll 4
+        for (size_t i = tid; i < nvec; i += nthr) {
+            const uint4 q = __ldg(v + i);
+            const unsigned w[4] = {q.x, q.y, q.z, q.w};
+            if (dtype == B2S_U16) {
+                unsigned mn = __vminu2(__vminu2(w[0], w[1]), __vminu2(w[2], w[3]));
+                unsigned mx = __vmaxu2(__vmaxu2(w[0], w[1]), __vmaxu2(w[2], w[3]));
+                lo = min(lo, min(mn & 0xffffu, mn >> 16));
+                hi = max(hi, max(mx & 0xffffu, mx >> 16));
+            } else if (dtype == B2S_U8) {
+                unsigned mn = __vminu4(__vminu4(w[0], w[1]), __vminu4(w[2], w[3]));
+                unsigned mx = __vmaxu4(__vmaxu4(w[0], w[1]), __vmaxu4(w[2], w[3]));
+                mn = __vminu2(mn & 0x00ff00ffu, (mn >> 8) & 0x00ff00ffu);
+                mx = __vmaxu2(mx & 0x00ff00ffu, (mx >> 8) & 0x00ff00ffu);
+                lo = min(lo, min(mn & 0xffffu, mn >> 16));
+                hi = max(hi, max(mx & 0xffffu, mx >> 16));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const unsigned key = f2key(__uint_as_float(w[k])); lo = min(lo, key); hi = max(hi, key); }
+            }
+        }
+    }
+    for (size_t i = body + tid; i < plane_elems; i += nthr) {
         unsigned k;
-        if (dtype == B2S_F32) k = f2key(__ldg(reinterpret_cast<const float *>(in) + plane * plane_elems + i));
-        else if (dtype == B2S_U16) k = __ldg(reinterpret_cast<const unsigned short *>(in) + plane * plane_elems + i);
-        else k = __ldg(reinterpret_cast<const unsigned char *>(in) + plane * plane_elems + i);
+        if (dtype == B2S_F32) k = f2key(__ldg(reinterpret_cast<const float *>(base) + i));
+        else if (dtype == B2S_U16) k = __ldg(reinterpret_cast<const unsigned short *>(base) + i);
+        else k = __ldg(reinterpret_cast<const unsigned char *>(base) + i);
         lo = min(lo, k);
         hi = max(hi, k);
     }
@@ -313,6 +344,36 @@ __global__ void __launch_bounds__(256) k_gauss5_u16(const uint16_t *in, uint16_t
     out[plane + (size_t)y * cols + x] = (uint16_t)(r > 65535ull ? 65535ull : r);
 }
 
+// cv2.GaussianBlur(float32, (5,5), 1, 1): separable, BORDER_REFLECT_101, float32 taps getGaussianKernel(5, 1, CV_32F).
+// OpenCV's vector body evaluates both passes as  k0*x0, then fma(k1, x[-1]+x[1], .), then fma(k2, x[-2]+x[2], .)
+// (SymmRowSmallVec_32f / SymmColumnVec_32f); its scalar tail columns and non-FMA builds round differently, so cv2's
+// own float output is position- and CPU-dependent in the last bit.  This kernel is the vector-body formula everywhere:
+// within 2.4e-7 relative of cv2 (tests assert 1e-6), not bit-pinned.
+__global__ void __launch_bounds__(256) k_gauss5_f32(const float *in, float *out, int rows, int cols)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= cols) return;
+    const size_t plane = (size_t)blockIdx.z * rows * cols;
+    const float k0 = 0.40261996f, k1 = 0.24420135f, k2 = 0.05448868f;
+    int xs[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) xs[d] = reflect101(x + d - 2, cols);
+    float h[5];
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) {
+        const float *row = in + plane + (size_t)reflect101(y + dy - 2, rows) * cols;
+        float s = __fmul_rn(k0, __ldg(row + xs[2]));
+        s = __fmaf_rn(k1, __fadd_rn(__ldg(row + xs[1]), __ldg(row + xs[3])), s);
+        s = __fmaf_rn(k2, __fadd_rn(__ldg(row + xs[0]), __ldg(row + xs[4])), s);
+        h[dy] = s;
+    }
+    float v = __fmul_rn(k0, h[2]);
+    v = __fmaf_rn(k1, __fadd_rn(h[1], h[3]), v);
+    v = __fmaf_rn(k2, __fadd_rn(h[0], h[4]), v);
+    out[plane + (size_t)y * cols + x] = v;
+}
+
 // skimage.measure.block_reduce with cval=0 padding of the trailing edges.  max/min keep the dtype; mean of an
 // integer image is the float64 mean cast to float32 (what log1p_jit's astype(float32) makes of it).
 __global__ void __launch_bounds__(256) k_block_reduce(const void *in, int dtype, int rows, int cols, int by, int bx,
@@ -322,6 +383,21 @@ __global__ void __launch_bounds__(256) k_block_reduce(const void *in, int dtype,
     const int oy = blockIdx.y;
     if (ox >= out_cols) return;
     const size_t ip = (size_t)blockIdx.z * rows * cols, op = (size_t)blockIdx.z * out_rows * out_cols;
+    if (method == B2S_DS_MEDIAN) {   // numpy.median over the block (<= 64 samples): sort, mean of the middle pair in float64
+        float v[64];
+        int n = 0;
+        for (int dy = 0; dy < by; ++dy)
+            for (int dx = 0; dx < bx; ++dx) {
+                const int y = oy * by + dy, x = ox * bx + dx;
+                const float t = (y < rows && x < cols) ? load_as_float(in, dtype, ip + (size_t)y * cols + x) : 0.f;
+                int i = n++;
+                while (i > 0 && v[i - 1] > t) { v[i] = v[i - 1]; --i; }
+                v[i] = t;
+            }
+        const double m = (n & 1) ? (double)v[n / 2] : ((double)v[n / 2 - 1] + (double)v[n / 2]) / 2.0;
+        reinterpret_cast<float *>(out)[op + (size_t)oy * out_cols + ox] = (float)m;
+        return;
+    }
     float best = 0.f;
     double sum = 0.0;
     bool first = true;
@@ -381,8 +457,10 @@ void b2s_launch_uniform(const void *in, int dtype, size_t plane_elems, int n_pla
                         cudaStream_t s)
 {
     k_minmax_init<<<(n_planes + 127) / 128, 128, 0, s>>>(mm, n_planes);
-    int bx = (int)((plane_elems + 256 * 8 - 1) / (256 * 8));
-    if (bx > 1024) bx = 1024;
+    // 16 bytes per thread and trip, four trips in flight; at most ~4 CTAs per SM over the batch
+    const size_t bytes = plane_elems * (dtype == B2S_F32 ? 4 : (dtype == B2S_U16 ? 2 : 1));
+    int bx = (int)((bytes + 256 * 64 - 1) / (256 * 64));
+    if (bx > 512) bx = 512;
     if (bx < 1) bx = 1;
     k_minmax<<<dim3(bx, n_planes), 256, 0, s>>>(in, dtype, plane_elems, mm);
     k_uniform_flags<<<(n_planes + 127) / 128, 128, 0, s>>>(mm, flags, n_planes);
@@ -399,6 +477,11 @@ void b2s_launch_flat_divide(const void *in, int in_dtype, const float *flat, flo
 void b2s_launch_gauss5_u16(const uint16_t *in, uint16_t *out, int rows, int cols, int n_planes, cudaStream_t s)
 {
     k_gauss5_u16<<<dim3((cols + 255) / 256, rows, n_planes), 256, 0, s>>>(in, out, rows, cols);
+}
+
+void b2s_launch_gauss5_f32(const float *in, float *out, int rows, int cols, int n_planes, cudaStream_t s)
+{
+    k_gauss5_f32<<<dim3((cols + 255) / 256, rows, n_planes), 256, 0, s>>>(in, out, rows, cols);
 }
 
 void b2s_launch_block_reduce(const void *in, int dtype, int rows, int cols, int by, int bx, int method, void *out,

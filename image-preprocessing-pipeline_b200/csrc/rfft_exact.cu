@@ -22,7 +22,7 @@
 
 namespace {
 
-constexpr int kXT = 256;   // threads per CTA
+constexpr int kXT = 512;   // threads per CTA
 
 struct Ctx { int r, item0, istride, GP; };
 #define IDX(e) ((e) * c.GP + c.r)
@@ -170,50 +170,85 @@ __device__ void radf5(const Ctx &c, int ido, int l1, const float *cc, float *ch,
 #undef CC
 }
 
-// accumulate the generic-radix DFT rows: acc_l / acc_lc over j = 3.. in pocketfft's 4 / 2 / 1 grouping
-#define GENERIC_SUM(SRC, a, b)                                                                                         \
+// The O(ip^2) part of a generic-radix pass: for every l in [1, ipph) and every ik
+//   DST(ik, l)    = SRC(ik,0) + sum_j cos(2 pi l j / ip) SRC(ik, j)        (pocketfft's 4 / 2 / 1 grouping of j >= 3)
+//   DST(ik, ip-l) =             sum_j sin(2 pi l j / ip) SRC(ik, ip - j)
+// One thread owns LB consecutive l for one ik, so every SRC value it loads from shared memory feeds LB output pairs;
+// the (cos, sin) pairs come from a per-pass table T[l-1][j-1] (global, L1-resident, warp-uniform 128-bit loads) that
+// holds csarr[2*((l*j) mod ip)] — the values pocketfft walks with its iang counter.
+constexpr int LB = 4;
+// src / dst: the buffers behind SRC / DST; element (ik, j) lives at ((ik + idl1 * j) * GP + r)
+#define GENERIC_BLOCK(src, dst)                                                                                        \
     {                                                                                                                  \
-        int iang = 2 * l;                                                                                              \
-        int j = 3, jc = ip - 3;                                                                                        \
-        for (; j + 3 < ipph; j += 4, jc -= 4) {                                                                        \
-            iang += l; if (iang >= ip) iang -= ip;                                                                     \
-            const float ar1 = cs[2 * iang], ai1 = cs[2 * iang + 1];                                                    \
-            iang += l; if (iang >= ip) iang -= ip;                                                                     \
-            const float ar2 = cs[2 * iang], ai2 = cs[2 * iang + 1];                                                    \
-            iang += l; if (iang >= ip) iang -= ip;                                                                     \
-            const float ar3 = cs[2 * iang], ai3 = cs[2 * iang + 1];                                                    \
-            iang += l; if (iang >= ip) iang -= ip;                                                                     \
-            const float ar4 = cs[2 * iang], ai4 = cs[2 * iang + 1];                                                    \
-            a += ar1 * SRC(ik, j) + ar2 * SRC(ik, j + 1) + ar3 * SRC(ik, j + 2) + ar4 * SRC(ik, j + 3);                \
-            b += ai1 * SRC(ik, jc) + ai2 * SRC(ik, jc - 1) + ai3 * SRC(ik, jc - 2) + ai4 * SRC(ik, jc - 3);            \
+        const int l0 = 1 + LB * lb, nl = min(LB, ipph - l0);                                                           \
+        const int st = idl1 * c.GP;                                                                                    \
+        const float *pf = (src) + ik * c.GP + c.r;                                                                     \
+        const float *pb = pf + (ip - 1) * st;                                                                          \
+        float a_[LB], b_[LB];                                                                                          \
+        const float2 *trow[LB];                                                                                        \
+        _Pragma("unroll") for (int q = 0; q < LB; ++q) trow[q] = gt + (size_t)(min(l0 + q, ipph - 1) - 1) * JP;        \
+        {                                                                                                              \
+            const float x0 = pf[0], x1 = pf[st], x2 = pf[2 * st], y1 = pb[0], y2 = pb[-st];                            \
+            _Pragma("unroll") for (int q = 0; q < LB; ++q) {                                                           \
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(trow[q]));                                     \
+                a_[q] = x0 + t.x * x1 + t.z * x2;                                                                      \
+                b_[q] = t.y * y1 + t.w * y2;                                                                           \
+                trow[q] += 2;                                                                                          \
+            }                                                                                                          \
         }                                                                                                              \
-        for (; j + 1 < ipph; j += 2, jc -= 2) {                                                                        \
-            iang += l; if (iang >= ip) iang -= ip;                                                                     \
-            const float ar1 = cs[2 * iang], ai1 = cs[2 * iang + 1];                                                    \
-            iang += l; if (iang >= ip) iang -= ip;                                                                     \
-            const float ar2 = cs[2 * iang], ai2 = cs[2 * iang + 1];                                                    \
-            a += ar1 * SRC(ik, j) + ar2 * SRC(ik, j + 1);                                                              \
-            b += ai1 * SRC(ik, jc) + ai2 * SRC(ik, jc - 1);                                                            \
+        pf += 3 * st;                                                                                                  \
+        pb -= 2 * st;                                                                                                  \
+        int j = 3;                                                                                                     \
+        for (; j + 3 < ipph; j += 4) {                                                                                 \
+            const float x0 = pf[0], x1 = pf[st], x2 = pf[2 * st], x3 = pf[3 * st];                                     \
+            const float y0 = pb[0], y1 = pb[-st], y2 = pb[-2 * st], y3 = pb[-3 * st];                                  \
+            pf += 4 * st;                                                                                              \
+            pb -= 4 * st;                                                                                              \
+            _Pragma("unroll") for (int q = 0; q < LB; ++q) {                                                           \
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(trow[q]));                                     \
+                const float4 u = __ldg(reinterpret_cast<const float4 *>(trow[q] + 2));                                 \
+                trow[q] += 4;                                                                                          \
+                a_[q] += t.x * x0 + t.z * x1 + u.x * x2 + u.z * x3;                                                    \
+                b_[q] += t.y * y0 + t.w * y1 + u.y * y2 + u.w * y3;                                                    \
+            }                                                                                                          \
         }                                                                                                              \
-        for (; j < ipph; ++j, --jc) {                                                                                  \
-            iang += l; if (iang >= ip) iang -= ip;                                                                     \
-            const float ar = cs[2 * iang], ai = cs[2 * iang + 1];                                                      \
-            a += ar * SRC(ik, j);                                                                                      \
-            b += ai * SRC(ik, jc);                                                                                     \
+        for (; j + 1 < ipph; j += 2) {                                                                                 \
+            const float x0 = pf[0], x1 = pf[st], y0 = pb[0], y1 = pb[-st];                                             \
+            pf += 2 * st;                                                                                              \
+            pb -= 2 * st;                                                                                              \
+            _Pragma("unroll") for (int q = 0; q < LB; ++q) {                                                           \
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(trow[q]));                                     \
+                trow[q] += 2;                                                                                          \
+                a_[q] += t.x * x0 + t.z * x1;                                                                          \
+                b_[q] += t.y * y0 + t.w * y1;                                                                          \
+            }                                                                                                          \
         }                                                                                                              \
+        for (; j < ipph; ++j) {                                                                                        \
+            const float x0 = pf[0], y0 = pb[0];                                                                        \
+            pf += st;                                                                                                  \
+            pb -= st;                                                                                                  \
+            _Pragma("unroll") for (int q = 0; q < LB; ++q) {                                                           \
+                const float2 t = __ldg(trow[q]);                                                                       \
+                trow[q] += 1;                                                                                          \
+                a_[q] += t.x * x0;                                                                                     \
+                b_[q] += t.y * y0;                                                                                     \
+            }                                                                                                          \
+        }                                                                                                              \
+        float *pd = (dst) + ik * c.GP + c.r;                                                                           \
+        _Pragma("unroll") for (int q = 0; q < LB; ++q)                                                                 \
+            if (q < nl) { pd[(l0 + q) * st] = a_[q]; pd[(ip - l0 - q) * st] = b_[q]; }                                 \
     }
 
 // generic odd radix, forward; the result ends in cc.  `cs` is a shared-memory copy of csarr (2*ip floats).
-__device__ void radfg(const Ctx &c, int ido, int ip, int l1, float *cc, float *ch, const float *wa, const float *csarr,
-                      float *cs)
+__device__ void radfg(const Ctx &c, int ido, int ip, int l1, float *cc, float *ch, const float *wa, const float2 *gt)
 {
     const int cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
+    const int JP = (ipph - 1 + 3) & ~3, nlb = (ipph - 1 + LB - 1) / LB;
 #define CC(a, b, k_) cc[IDX((a) + ido * ((b) + cdim * (k_)))]
 #define CH(a, b, k_) ch[IDX((a) + ido * ((b) + l1 * (k_)))]
 #define C1(a, b, k_) cc[IDX((a) + ido * ((b) + l1 * (k_)))]
 #define C2(a, b) cc[IDX((a) + idl1 * (b))]
 #define CH2(a, b) ch[IDX((a) + idl1 * (b))]
-    for (int i = threadIdx.x; i < 2 * ip; i += kXT) cs[i] = __ldg(csarr + i);
     if (ido > 1) {
         const int ni = (ido - 1) >> 1;
         FOR_ITEMS(it, (ipph - 1) * l1 * ni) {
@@ -234,20 +269,13 @@ __device__ void radfg(const Ctx &c, int ido, int ip, int l1, float *cc, float *c
         PM(C1(0, k, j), C1(0, k, jc), t2, t1)
     }
     __syncthreads();
-    FOR_ITEMS(it, ipph * idl1) {
-        const int l = it / idl1, ik = it - l * idl1;
-        if (l == 0) {
+    FOR_ITEMS(it, (nlb + 1) * idl1) {
+        const int lb = it / idl1, ik = it - lb * idl1;
+        if (lb == nlb) {
             float s = C2(ik, 0);
             for (int j = 1; j < ipph; ++j) s += C2(ik, j);
             CH2(ik, 0) = s;
-        } else {
-            const int lc = ip - l;
-            float a = C2(ik, 0) + cs[2 * l] * C2(ik, 1) + cs[4 * l] * C2(ik, 2);
-            float b = cs[2 * l + 1] * C2(ik, ip - 1) + cs[4 * l + 1] * C2(ik, ip - 2);
-            GENERIC_SUM(C2, a, b)
-            CH2(ik, l) = a;
-            CH2(ik, lc) = b;
-        }
+        } else GENERIC_BLOCK(cc, ch)
     }
     __syncthreads();
     FOR_ITEMS(it, l1 * ido) {
@@ -423,13 +451,12 @@ __device__ void radb5(const Ctx &c, int ido, int l1, const float *cc, float *ch,
 }
 
 // generic odd radix, backward; the result ends in ch
-__device__ void radbg(const Ctx &c, int ido, int ip, int l1, float *cc, float *ch, const float *wa, const float *csarr,
-                      float *cs)
+__device__ void radbg(const Ctx &c, int ido, int ip, int l1, float *cc, float *ch, const float *wa, const float2 *gt)
 {
     const int cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
+    const int JP = (ipph - 1 + 3) & ~3, nlb = (ipph - 1 + LB - 1) / LB;
 #define CC(a, b, k_) cc[IDX((a) + ido * ((b) + cdim * (k_)))]
 #define CH(a, b, k_) ch[IDX((a) + ido * ((b) + l1 * (k_)))]
-    for (int i = threadIdx.x; i < 2 * ip; i += kXT) cs[i] = __ldg(csarr + i);
     FOR_ITEMS(it, l1 * ido) {
         const int k = it / ido, i = it - k * ido;
         CH(i, k, 0) = CC(i, 0, k);
@@ -454,20 +481,13 @@ __device__ void radbg(const Ctx &c, int ido, int ip, int l1, float *cc, float *c
     __syncthreads();
     // C2(ik, l >= 1) from CH2; the l == 0 item forms CH2(ik,0) + sum_j CH2(ik,j) and parks it in C2(ik,0) (cc's slot 0
     // is free) because the other items of this phase still read the old CH2(ik,0)
-    FOR_ITEMS(it, ipph * idl1) {
-        const int l = it / idl1, ik = it - l * idl1;
-        if (l == 0) {
+    FOR_ITEMS(it, (nlb + 1) * idl1) {
+        const int lb = it / idl1, ik = it - lb * idl1;
+        if (lb == nlb) {
             float s = CH2(ik, 0);
             for (int j = 1; j < ipph; ++j) s += CH2(ik, j);
             C2(ik, 0) = s;
-        } else {
-            const int lc = ip - l;
-            float a = CH2(ik, 0) + cs[2 * l] * CH2(ik, 1) + cs[4 * l] * CH2(ik, 2);
-            float b = cs[2 * l + 1] * CH2(ik, ip - 1) + cs[4 * l + 1] * CH2(ik, ip - 2);
-            GENERIC_SUM(CH2, a, b)
-            C2(ik, l) = a;
-            C2(ik, lc) = b;
-        }
+        } else GENERIC_BLOCK(ch, cc)
     }
     __syncthreads();
     FOR_ITEMS(ik, idl1) CH2(ik, 0) = C2(ik, 0);
@@ -831,13 +851,12 @@ __device__ void rblue(const Ctx &c, const XBlue &b, const float *tab, int ido, i
 #undef WA
 }
 
-__global__ void __launch_bounds__(kXT) k_notch_exact(const __grid_constant__ XArgs a)
+__global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ XArgs a)
 {
     extern __shared__ __align__(16) float xs[];
-    const int n = a.n, G = a.G, GP = G + 1;
+    const int n = a.n, G = a.G, GP = G;   // unpadded: 32/G consecutive elements x G rows hit 32 different banks
     float *A = xs, *B = A + n * GP;
-    float *cs = B + n * GP;                              // 2 * 136 floats
-    float2 *X0 = reinterpret_cast<float2 *>(cs + 272);   // Bluestein work buffers
+    float2 *X0 = reinterpret_cast<float2 *>(B + n * GP);   // Bluestein work buffers (offset 2*n*GP floats: 8-byte aligned)
     float2 *X1 = X0 + (size_t)a.blue.inst * a.blue.n2 * GP;
 
     Ctx c;
@@ -852,15 +871,16 @@ __global__ void __launch_bounds__(kXT) k_notch_exact(const __grid_constant__ XAr
         const int ns = min(G, a.nseq - s0);
         __syncthreads();
         // ---- gather (rows beyond the sub-band are zero sequences)
+        // a warp covers 32/G consecutive elements of G rows: each row contributes one 16..128-byte run
         if (!a.along_cols) {
             for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
-                const int rr = idx / n, e = idx - rr * n;
-                A[e * GP + rr] = rr < ns ? plane[(size_t)(s0 + rr) * a.img.pitch + e] : 0.f;
+                const int e = idx >> a.lgG, rr = idx & (G - 1);
+                A[idx] = rr < ns ? plane[(size_t)(s0 + rr) * a.img.pitch + e] : 0.f;
             }
         } else {
             for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
                 const int e = idx >> a.lgG, rr = idx & (G - 1);
-                A[e * GP + rr] = rr < ns ? plane[(size_t)e * a.img.pitch + s0 + rr] : 0.f;
+                A[idx] = rr < ns ? plane[(size_t)e * a.img.pitch + s0 + rr] : 0.f;
             }
         }
         __syncthreads();
@@ -875,7 +895,7 @@ __global__ void __launch_bounds__(kXT) k_notch_exact(const __grid_constant__ XAr
             case 3: radf3(c, p.ido, p.l1, p1, p2, wa); break;
             case 4: radf4(c, p.ido, p.l1, p1, p2, wa); break;
             case 5: radf5(c, p.ido, p.l1, p1, p2, wa); break;
-            case 6: radfg(c, p.ido, p.ip, p.l1, p1, p2, wa, a.tab + p.cs, cs); swap = false; break;
+            case 6: radfg(c, p.ido, p.ip, p.l1, p1, p2, wa, reinterpret_cast<const float2 *>(a.tab + p.cs)); swap = false; break;
             default: rblue<true>(c, a.blue, a.tab, p.ido, p.l1, p1, p2, wa, X0, X1); break;
             }
             __syncthreads();
@@ -884,7 +904,7 @@ __global__ void __launch_bounds__(kXT) k_notch_exact(const __grid_constant__ XAr
         // ---- notch on packed positions (core.py:752: spec *= g)
         for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
             const int e = idx >> a.lgG, rr = idx & (G - 1);
-            p1[e * GP + rr] = p1[e * GP + rr] * __ldg(a.g + e);
+            p1[idx] = p1[idx] * __ldg(a.g + e);
         }
         __syncthreads();
         // ---- backward: rfftp::exec(r2hc = false)
@@ -896,7 +916,7 @@ __global__ void __launch_bounds__(kXT) k_notch_exact(const __grid_constant__ XAr
             case 3: radb3(c, p.ido, p.l1, p1, p2, wa); break;
             case 4: radb4(c, p.ido, p.l1, p1, p2, wa); break;
             case 5: radb5(c, p.ido, p.l1, p1, p2, wa); break;
-            case 6: radbg(c, p.ido, p.ip, p.l1, p1, p2, wa, a.tab + p.cs, cs); break;
+            case 6: radbg(c, p.ido, p.ip, p.l1, p1, p2, wa, reinterpret_cast<const float2 *>(a.tab + p.cs)); break;
             default: rblue<false>(c, a.blue, a.tab, p.ido, p.l1, p1, p2, wa, X0, X1); break;
             }
             __syncthreads();
@@ -905,13 +925,13 @@ __global__ void __launch_bounds__(kXT) k_notch_exact(const __grid_constant__ XAr
         // ---- scale by 1/n (copy_and_norm) and scatter
         if (!a.along_cols) {
             for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
-                const int rr = idx / n, e = idx - rr * n;
-                if (rr < ns) plane[(size_t)(s0 + rr) * a.img.pitch + e] = a.fct * p1[e * GP + rr];
+                const int e = idx >> a.lgG, rr = idx & (G - 1);
+                if (rr < ns) plane[(size_t)(s0 + rr) * a.img.pitch + e] = a.fct * p1[idx];
             }
         } else {
             for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
                 const int e = idx >> a.lgG, rr = idx & (G - 1);
-                if (rr < ns) plane[(size_t)e * a.img.pitch + s0 + rr] = a.fct * p1[e * GP + rr];
+                if (rr < ns) plane[(size_t)e * a.img.pitch + s0 + rr] = a.fct * p1[idx];
             }
         }
     }
@@ -921,14 +941,14 @@ __global__ void __launch_bounds__(kXT) k_notch_exact(const __grid_constant__ XAr
 __global__ void __launch_bounds__(kXT) k_blue_setup(XBlue b, const float *tab, const float2 *tbkf, float2 *out)
 {
     extern __shared__ __align__(16) float xs[];
-    float2 *X0 = reinterpret_cast<float2 *>(xs), *X1 = X0 + 2 * b.n2;
+    float2 *X0 = reinterpret_cast<float2 *>(xs), *X1 = X0 + b.n2;
     Ctx c;
-    c.r = 0; c.item0 = threadIdx.x; c.istride = kXT; c.GP = 2;
-    for (int m = threadIdx.x; m < b.n2; m += kXT) X0[m * 2] = tbkf[m];
+    c.r = 0; c.item0 = threadIdx.x; c.istride = kXT; c.GP = 1;
+    for (int m = threadIdx.x; m < b.n2; m += kXT) X0[m] = tbkf[m];
     __syncthreads();
     float2 *cur = X0, *nxt = X1;
     cfft_all<true>(c, b, tab, cur, nxt, 1);
-    for (int m = threadIdx.x; m < b.n2 / 2 + 1; m += kXT) out[m] = cur[m * 2];
+    for (int m = threadIdx.x; m < b.n2 / 2 + 1; m += kXT) out[m] = cur[m];
 }
 
 // ================================================================ host: plan + tables
@@ -1008,8 +1028,8 @@ size_t good_size_cmplx(size_t n)
 
 size_t xfft_smem(int n, int G, const XBlue &b)
 {
-    const size_t GP = G + 1;
-    return sizeof(float) * (2 * (size_t)n * GP + 272) + sizeof(float2) * 2 * (size_t)b.inst * b.n2 * GP;
+    const size_t GP = G;
+    return sizeof(float) * (2 * (size_t)n * GP + 2) + sizeof(float2) * 2 * (size_t)b.inst * b.n2 * GP;
 }
 
 }  // namespace
@@ -1059,15 +1079,24 @@ B2sXfftPlan *b2s_xfft_create(int n)
                     twid.get((size_t)j * l1 * i, &tab[tw_off[k] + (j - 1) * (ido - 1) + 2 * i - 2],
                              &tab[tw_off[k] + (j - 1) * (ido - 1) + 2 * i - 1]);
             if (ip > 5 && ip < 135) {
-                cs_off[k] = (int)tab.size();
-                tab.resize(tab.size() + 2 * (size_t)ip, 0.f);
-                float *tws = &tab[cs_off[k]];
+                // csarr (rfftp::comp_twiddle, "extra factors required by *g functions"), expanded to T[l-1][j-1]
+                std::vector<float> tws(2 * (size_t)ip);
                 tws[0] = 1.f; tws[1] = 0.f;
                 for (int i = 2, ic = 2 * ip - 2; i <= ic; i += 2, ic -= 2) {
                     float re, im;
                     twid.get((size_t)(i / 2) * (n / ip), &re, &im);
                     tws[i] = re; tws[i + 1] = im; tws[ic] = re; tws[ic + 1] = -im;
                 }
+                const int ipph = (ip + 1) / 2, JP = (ipph - 1 + 3) & ~3;
+                while (tab.size() & 3) tab.push_back(0.f);
+                cs_off[k] = (int)tab.size();
+                tab.resize(tab.size() + 2 * (size_t)(ipph - 1) * JP, 0.f);
+                for (int l = 1; l < ipph; ++l)
+                    for (int j = 1; j < ipph; ++j) {
+                        const int iang = (int)(((long long)l * j) % ip);
+                        tab[cs_off[k] + 2 * ((size_t)(l - 1) * JP + (j - 1))] = tws[2 * iang];
+                        tab[cs_off[k] + 2 * ((size_t)(l - 1) * JP + (j - 1)) + 1] = tws[2 * iang + 1];
+                    }
             }
             if (ip >= 135) { ++n_blue; blue_ip = ip; }
             l1 *= ip;

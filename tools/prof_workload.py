@@ -1,0 +1,23 @@
+"""One batch of the bench workload (configs[1]: process_img with flat + dark, 2048^2 u16, db10, sigma 256) for ncu."""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path[:0] = [str(ROOT), str(ROOT / "image-preprocessing-pipeline_b200")]
+import numpy as np
+import torch
+from pystripe import core, _native
+from tools import synth
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+base = synth.stack(4, (2048, 2048))
+stack = torch.from_numpy(np.concatenate([base] * (n // 4))).cuda()
+flat = core.normalize_flat(synth.flat_field((2048, 2048)))
+plan = core._get_plan(0, (2048, 2048), _native.U16, process=1, sigma=(256, 256), level=0, wavelet="db10", threshold=None,
+                      padding_mode="reflect", bidirectional=False, log1p=True, flat=flat, dark=100, out_code=_native.U16,
+                      max_batch=n)
+out = None
+for _ in range(reps):
+    out = plan.run_torch(stack, out)
+torch.cuda.synchronize()
+print("ok", int(out[0, ::256, ::256].sum()))
