@@ -112,7 +112,6 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
     if (gauss && dt == B2S_U8) return fail(ctx, B2S_ERR_UNSUPPORTED, "gaussian_filter_2d on uint8 is not implemented");
     if (ds && p.down_sample_method >= B2S_DS_MEAN) dt = B2S_F32;   // float64 in the reference; float32 holds what reaches log1p
     g.work_dtype = dt;
-    g.fuse_flat = flat && !gauss && !ds;
 
     // filter_streak_dual_band pass list, core.py:943-979
     const double s1 = p.sigma1, s2 = p.sigma2;
@@ -121,6 +120,7 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
     else { g.n_passes = 2; g.pass_sigma[0] = s1; g.pass_sigma[1] = s2; }
     for (int i = 0; i < g.n_passes; ++i)
         if (g.pass_sigma[i] <= 0) return fail(ctx, B2S_ERR_INVALID, "np_notch: sigma must be positive");
+    g.fuse_flat = flat && !gauss && !ds && g.n_passes > 0;   // the prologue divides by flat; without a destripe it is a pre-op
 
     g.base_pad = g.pad_y = g.pad_x = 0;
     g.PH = g.work_rows;
@@ -183,7 +183,15 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
     const bool swap = p.process_img && (p.rotate == 90 || p.rotate == 270);
     g.out_rows = swap ? g.work_cols : g.work_rows;
     g.out_cols = swap ? g.work_rows : g.work_cols;
-    if (p.process_img && p.lightsheet) return fail(ctx, B2S_ERR_UNSUPPORTED, "lightsheet=True is not implemented yet");
+    if (p.process_img && p.lightsheet) {
+        if (const char *why = b2s_lightsheet_check(g.work_rows, g.work_cols, p.artifact_length, p.background_window_size))
+            return fail(ctx, B2S_ERR_UNSUPPORTED, "%s", why);
+        if (!(p.out_dtype == B2S_U16 || (p.out_dtype == B2S_U8 && g.work_dtype == B2S_U8)))
+            return fail(ctx, B2S_ERR_UNSUPPORTED, "lightsheet: d_type must be uint16 (or uint8 for uint8 input)");
+        if (g.work_dtype != B2S_F32 && p.dark > 0 && p.dark != std::floor(p.dark))
+            return fail(ctx, B2S_ERR_UNSUPPORTED, "lightsheet after a fractional dark on an integer image (float64 in the reference) is not implemented");
+        if (p.percentile < 0 || p.percentile > 1) return fail(ctx, B2S_ERR_INVALID, "percentile must be in [0, 1]");
+    }
     return B2S_OK;
 }
 
@@ -242,6 +250,8 @@ struct b2s_plan {
         float *sub[B2S_MAX_LEVELS + 1][4] = {};
         void *d_in = nullptr, *d_out = nullptr;
         void *pre_a = nullptr, *pre_b = nullptr;   // pre-op temporaries
+        void *mid = nullptr;                       // lightsheet: post-dark image
+        unsigned short *ls_grid = nullptr, *bg_grid = nullptr;
         unsigned *mm = nullptr;
         int *flags = nullptr;
         void *h_in = nullptr, *h_out = nullptr;    // pinned staging
@@ -257,6 +267,7 @@ struct b2s_plan {
     int *d_row_src = nullptr, *d_row_start = nullptr, *d_row_targets = nullptr, *d_colmap = nullptr;
     float *d_lut = nullptr;
     std::map<int, B2sFftPlan> fft;                  // by length
+    B2sLightsheet *ls = nullptr;
     std::map<int, B2sXfftPlan *> xfft;              // by length: rounding-exact transform (exact mode, covered lengths)
     float *d_notch[2][B2S_MAX_LEVELS + 1][2] = {};  // [pass][level][axis: 0 = cH rows, 1 = cV cols]
     int64_t workspace_bytes = 0;
@@ -447,7 +458,11 @@ int alloc_slot(b2s_plan *pl, int si)
         if ((rc = dev_alloc(pl, (void **)&s.mm, sizeof(unsigned) * 2 * B))) return rc;
         if ((rc = dev_alloc(pl, (void **)&s.flags, sizeof(int) * B))) return rc;
     }
-    (void)work_elems;
+    if (pl->ls) {
+        if ((rc = dev_alloc(pl, &s.mid, work_elems * 4 * B))) return rc;
+        if ((rc = dev_alloc(pl, (void **)&s.ls_grid, sizeof(unsigned short) * b2s_lightsheet_grid_elems(pl->ls, 0) * B))) return rc;
+        if ((rc = dev_alloc(pl, (void **)&s.bg_grid, sizeof(unsigned short) * b2s_lightsheet_grid_elems(pl->ls, 1) * B))) return rc;
+    }
     CU(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     return B2S_OK;
@@ -579,7 +594,21 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
         e.out = d_out;
         e.out_rows = g.out_rows;
         e.out_cols = g.out_cols;
-        b2s_launch_epilogue(e, nb, st);
+        if (!pl->ls) {
+            b2s_launch_epilogue(e, nb, st);
+        } else {
+            // stage 1: the image as the reference holds it after the dark subtraction (same dtype), unrotated
+            B2sEpilogueArgs m = e;
+            const bool mid_int = g.work_dtype != B2S_F32;
+            m.final_mode = mid_int ? 0 : 3;
+            m.out_dtype = mid_int ? g.work_dtype : B2S_F32;
+            m.flip = 0; m.rot = 0; m.uniform_flags = nullptr;
+            m.out = s.mid; m.out_rows = g.work_rows; m.out_cols = g.work_cols;
+            b2s_launch_epilogue(m, nb, st);
+            // stage 2: percentile grids, zoom, subtraction, final conversion
+            ClassTimer t2(ctx, st, B2S_K_LIGHTSHEET, 3);
+            b2s_launch_lightsheet(pl->ls, s.mid, s.ls_grid, s.bg_grid, e, nb, st);
+        }
     }
     CU(ctx, cudaGetLastError());
     return B2S_OK;
@@ -685,6 +714,12 @@ int b2s_plan_create(b2s_context *ctx, const b2s_params *params, b2s_plan **out)
         if (need > 227 * 1024) { delete pl; return fail(ctx, B2S_ERR_UNSUPPORTED, "filter too long for the shared-memory tiles"); }
         rc = build_tables(pl);
     }
+    if (rc == B2S_OK && params->process_img && params->lightsheet) {
+        pl->ls = b2s_lightsheet_create(g.work_rows, g.work_cols, g.work_dtype, params->artifact_length,
+                                       params->background_window_size, params->percentile,
+                                       params->lightsheet_vs_background, 1);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B2S_ERR_CUDA, "lightsheet table setup failed");
+    }
     for (int si = 0; rc == B2S_OK && si < b2s_plan::kSlots; ++si) rc = alloc_slot(pl, si);
     pl->p.dec_lo = nullptr;  // the caller's table is not retained
     if (rc) { b2s_plan_destroy(pl); return rc; }
@@ -699,6 +734,7 @@ void b2s_plan_destroy(b2s_plan *pl)
     cudaDeviceSynchronize();
     for (void *p : pl->allocs) cudaFree(p);
     for (auto &kv : pl->xfft) b2s_xfft_destroy(kv.second);
+    b2s_lightsheet_destroy(pl->ls);
     for (auto &s : pl->slot) {
         if (s.h_in) cudaFreeHost(s.h_in);
         if (s.h_out) cudaFreeHost(s.h_out);

@@ -118,3 +118,14 @@ B2sXfftPlan *b2s_xfft_create(int n);
 void b2s_xfft_destroy(B2sXfftPlan *pl);
 void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B2sImg &img, int along_cols, int n_planes,
                             int sm_count, cudaStream_t s);
+
+// lightsheet.cu -------------------------------------------------------------------------------------------------
+struct B2sLightsheet;
+const char *b2s_lightsheet_check(int rows, int cols, int artifact_length, int window);
+B2sLightsheet *b2s_lightsheet_create(int rows, int cols, int dtype, int artifact_length, int window, double percentile,
+                                     double weight, int weight_is_float);
+void b2s_lightsheet_destroy(B2sLightsheet *L);
+size_t b2s_lightsheet_grid_elems(const B2sLightsheet *L, int which /*0 ls, 1 bg*/);
+// mid: post-dark image in the lightsheet plan's dtype; e carries the final conversion / orientation / output
+void b2s_launch_lightsheet(const B2sLightsheet *L, const void *mid, unsigned short *ls_grid, unsigned short *bg_grid,
+                           const B2sEpilogueArgs &e, int n_planes, cudaStream_t s);

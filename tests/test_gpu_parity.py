@@ -165,8 +165,6 @@ def _gpu_case(kind, img, kw):
 def test_golden_vectors_from_the_reference():
     gold = np.load(ROOT / "tests" / "golden" / "pystripe_golden.npz")
     for name, kind, img, kw in cases.all_cases():
-        if kw.get("lightsheet"):
-            continue  # lightsheet has its own test module
         if kw.get("log1p_normalization_needed") is False and img.dtype.kind in "ui":
             # the reference runs this combination in float64 and truncates inside filter_subband (core.py:939):
             # declared unsupported by the GPU path rather than approximated
@@ -283,6 +281,45 @@ def test_process_img_median_downsample():
     img = synth.plane(18, (130, 171))
     kw = dict(sigma=(16, 16), wavelet="db4", down_sample=(2, 3), down_sample_method="median")
     _cmp_int("pi/median", core.process_img(img.copy(), **kw), orc.process_img(img.copy(), **kw))
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((300, 340), dict(sigma=(0, 0), lightsheet=True)),                                   # defaults: 150 / 200 / 0.25 / 2.0
+    ((256, 512), dict(sigma=(0, 0), lightsheet=True, dark=110, artifact_length=64, background_window_size=100,
+                      percentile=0.4, lightsheet_vs_background=3.0, rotate=90, flip_upside_down=True)),
+    ((200, 260), dict(sigma=(24, 24), wavelet="db6", lightsheet=True, dark=100, convert_to_8bit=True,
+                      bit_shift_to_right=2, padding_mode="reflect")),
+    ((131, 177), dict(sigma=(0, 0), lightsheet=True, artifact_length=50, background_window_size=75, percentile=1.0)),
+])
+def test_lightsheet_clean_bit_exact(shape, kw):
+    """lightsheet_correct (numba percentile + scipy zoom + wrap-around uint16 arithmetic) is integer/float64 work:
+    bit-exact, including scipy's zero column when the last zoom coordinate rounds above the grid."""
+    from pystripe import core
+    rng = np.random.default_rng(21)
+    img = synth.plane(19, shape)
+    img[:: 7] += rng.integers(0, 300, img[::7].shape).astype(np.uint16)     # row artefacts
+    got = core.process_img(img.copy(), **kw)
+    ref = orc.process_img(img.copy(), **kw)
+    _cmp_int(f"lightsheet/{shape}", got, ref, min_exact=1.0 if tuple(kw["sigma"]) == (0, 0) else MIN_EXACT)
+
+
+def test_lightsheet_on_flat_fielded_float_image():
+    from pystripe import core
+    img = synth.plane(20, (160, 200))
+    flat = orc.normalize_flat(synth.flat_field((160, 200)))
+    kw = dict(sigma=(0, 0), lightsheet=True, dark=90, artifact_length=40, background_window_size=60)
+    got = core.process_img(img.copy(), flat=flat, **kw)
+    ref = orc.process_img(img.copy(), flat=flat, **kw)
+    _cmp_int("lightsheet/flat", got, ref, min_exact=1.0)
+
+
+def test_flat_field_without_destripe():
+    from pystripe import core
+    img = synth.plane(22, (96, 130))
+    flat = orc.normalize_flat(synth.flat_field((96, 130)))
+    kw = dict(sigma=(0, 0), dark=50, convert_to_8bit=True, bit_shift_to_right=3)
+    _cmp_int("pi/flat_nodestripe", core.process_img(img.copy(), flat=flat, **kw), orc.process_img(img.copy(), flat=flat, **kw),
+             min_exact=1.0)
 
 
 def test_uniform_plane_shortcut():
