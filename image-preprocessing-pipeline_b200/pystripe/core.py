@@ -813,6 +813,28 @@ def progress_manager(progress_queue: Queue, workers: int, total: int, desc="PySt
 # --------------------------------------------------------------------------------------------------------------
 # batch_filter  (core.py:1806-2044) — re-designed scheduling: decode threads -> per-GPU batched plans -> encode threads
 # --------------------------------------------------------------------------------------------------------------
+def z_shard(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous Z partition: rank r of `world_size` owns items [lo, hi); the first
+    n_items % world_size ranks hold one extra item.  Planes are independent, so this is the only multi-GPU exchange:
+    no collective on the data path."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of size {world_size}")
+    base, extra = divmod(max(int(n_items), 0), world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _process_group() -> Tuple[int, int, int]:
+    """(world_size, rank, local_rank) when launched one process per GPU (torchrun / torch.distributed env), else (1, 0, 0)."""
+    try:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        rank = int(os.environ.get("RANK", "0"))
+        local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    except ValueError:
+        return 1, 0, 0
+    return (world, rank, local) if world > 1 else (1, 0, 0)
+
+
 def _visible_gpus() -> List[int]:
     env = os.environ.get("B200STRIPE_DEVICES")
     if env:
@@ -927,11 +949,17 @@ def batch_filter(
                 if continue_process and out.exists():
                     continue
                 jobs.append((f, out, i))
+    # one process per GPU (torchrun): this process takes its contiguous share of the job list on its own device
+    world, rank, local_rank = _process_group()
+    if world > 1:
+        jobs.sort(key=lambda j: (str(j[0]), -1 if j[2] is None else j[2]))   # every rank must see the same order
+        lo, hi = z_shard(len(jobs), world, rank)
+        jobs = jobs[lo:hi]
     num_images = len(jobs)
     if num_images == 0:
         return 0
 
-    gpus = _visible_gpus()
+    gpus = [local_rank] if world > 1 and not os.environ.get("B200STRIPE_DEVICES") else _visible_gpus()
     batch = max(1, int(threads_per_gpu))
     print(f"{PrintColors.GREEN}{date_time_now()}: {PrintColors.ENDC}"
           f"using {workers} decode/encode threads and {len(gpus)} GPU(s). {num_images} images need to be processed.",

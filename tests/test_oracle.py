@@ -138,3 +138,30 @@ def test_libm_pins():
     assert np.abs(y - np.log1p(x.astype(np.float64))).max() < 2e-6
     z = orc.expm1_f32(y)
     assert (np.abs(z - x) <= 1e-6 * np.maximum(x, 1.0)).all()
+
+
+def _fft_lib():
+    import ctypes
+    L = pw.lib()
+    L.orc_fftpack_r2r_f32.restype = ctypes.c_int
+    return L
+
+
+@pytest.mark.parametrize("lengths", [list(range(1, 140)), [143, 149, 169, 183, 256, 274, 289, 347, 411, 625, 676, 821, 1000],
+                                     [1001, 1029, 1327, 1333, 1337, 1341, 2047, 2187, 3251]])
+def test_fft_restatement_is_bit_identical_to_scipy_fftpack(lengths):
+    """oracle/pocketfft_c.c (the pass structure the GPU mirrors) against the scipy.fftpack the reference calls
+    (core.py:751,753): every bit, forward and inverse, rows vectorised and not; even lengths > 1000 are declared
+    outside the restatement (return code 1)."""
+    import ctypes
+    from scipy.fftpack import irfft, rfft
+    L = _fft_lib()
+    rng = np.random.default_rng(5)
+    for n in lengths:
+        x = rng.standard_normal((6, n)).astype(np.float32) * 100
+        for fwd, ref in ((1, rfft(x, axis=-1)), (0, irfft(x, axis=-1))):
+            y = x.copy()
+            rc = L.orc_fftpack_r2r_f32(ctypes.c_void_p(y.ctypes.data), ctypes.c_size_t(6), ctypes.c_size_t(n), ctypes.c_int(fwd))
+            assert rc == 0 and np.array_equal(ref.view(np.uint32), y.view(np.uint32)), (n, fwd)
+    y = np.zeros((1, 1024 + 2), np.float32)
+    assert L.orc_fftpack_r2r_f32(ctypes.c_void_p(y.ctypes.data), ctypes.c_size_t(1), ctypes.c_size_t(1026), ctypes.c_int(1)) == 1
