@@ -25,6 +25,9 @@ namespace {
 constexpr int kXT = 512;   // threads per CTA
 
 struct Ctx { int r, item0, istride, GP; };
+// one pass of the real transform.  kind: 2,3,4,5 = radix, 6 = generic, 7 = Bluestein; m_*: fdiv magics for l1, ni = (ido-1)/2,
+// l1*ni, ido, ido*l1
+struct XPass { int kind, ip, l1, ido, tw, cs; unsigned m_l1, m_ni, m_l1ni, m_ido, m_idl1; };
 #define IDX(e) ((e) * c.GP + c.r)
 #define FOR_ITEMS(it, count) for (int it = c.item0, cnt__ = (count); it < cnt__; it += c.istride)
 #define PM(a, b, cc_, d) { a = (cc_) + (d); b = (cc_) - (d); }
@@ -173,77 +176,86 @@ __device__ void radf5(const Ctx &c, int ido, int l1, const float *cc, float *ch,
 // The O(ip^2) part of a generic-radix pass: for every l in [1, ipph) and every ik
 //   DST(ik, l)    = SRC(ik,0) + sum_j cos(2 pi l j / ip) SRC(ik, j)        (pocketfft's 4 / 2 / 1 grouping of j >= 3)
 //   DST(ik, ip-l) =             sum_j sin(2 pi l j / ip) SRC(ik, ip - j)
-// One thread owns LB consecutive l for one ik, so every SRC value it loads from shared memory feeds LB output pairs;
-// the (cos, sin) pairs come from a per-pass table T[l-1][j-1] (global, L1-resident, warp-uniform 128-bit loads) that
-// holds csarr[2*((l*j) mod ip)] — the values pocketfft walks with its iang counter.
-constexpr int LB = 4;
-// src / dst: the buffers behind SRC / DST; element (ik, j) lives at ((ik + idl1 * j) * GP + r)
-#define GENERIC_BLOCK(src, dst)                                                                                        \
-    {                                                                                                                  \
-        const int l0 = 1 + LB * lb, nl = min(LB, ipph - l0);                                                           \
-        const int st = idl1 * c.GP;                                                                                    \
-        const float *pf = (src) + ik * c.GP + c.r;                                                                     \
-        const float *pb = pf + (ip - 1) * st;                                                                          \
-        float a_[LB], b_[LB];                                                                                          \
-        const float2 *trow[LB];                                                                                        \
-        _Pragma("unroll") for (int q = 0; q < LB; ++q) trow[q] = gt + (size_t)(min(l0 + q, ipph - 1) - 1) * JP;        \
-        {                                                                                                              \
-            const float x0 = pf[0], x1 = pf[st], x2 = pf[2 * st], y1 = pb[0], y2 = pb[-st];                            \
-            _Pragma("unroll") for (int q = 0; q < LB; ++q) {                                                           \
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(trow[q]));                                     \
-                a_[q] = x0 + t.x * x1 + t.z * x2;                                                                      \
-                b_[q] = t.y * y1 + t.w * y2;                                                                           \
-                trow[q] += 2;                                                                                          \
-            }                                                                                                          \
-        }                                                                                                              \
-        pf += 3 * st;                                                                                                  \
-        pb -= 2 * st;                                                                                                  \
-        int j = 3;                                                                                                     \
-        for (; j + 3 < ipph; j += 4) {                                                                                 \
-            const float x0 = pf[0], x1 = pf[st], x2 = pf[2 * st], x3 = pf[3 * st];                                     \
-            const float y0 = pb[0], y1 = pb[-st], y2 = pb[-2 * st], y3 = pb[-3 * st];                                  \
-            pf += 4 * st;                                                                                              \
-            pb -= 4 * st;                                                                                              \
-            _Pragma("unroll") for (int q = 0; q < LB; ++q) {                                                           \
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(trow[q]));                                     \
-                const float4 u = __ldg(reinterpret_cast<const float4 *>(trow[q] + 2));                                 \
-                trow[q] += 4;                                                                                          \
-                a_[q] += t.x * x0 + t.z * x1 + u.x * x2 + u.z * x3;                                                    \
-                b_[q] += t.y * y0 + t.w * y1 + u.y * y2 + u.w * y3;                                                    \
-            }                                                                                                          \
-        }                                                                                                              \
-        for (; j + 1 < ipph; j += 2) {                                                                                 \
-            const float x0 = pf[0], x1 = pf[st], y0 = pb[0], y1 = pb[-st];                                             \
-            pf += 2 * st;                                                                                              \
-            pb -= 2 * st;                                                                                              \
-            _Pragma("unroll") for (int q = 0; q < LB; ++q) {                                                           \
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(trow[q]));                                     \
-                trow[q] += 2;                                                                                          \
-                a_[q] += t.x * x0 + t.z * x1;                                                                          \
-                b_[q] += t.y * y0 + t.w * y1;                                                                          \
-            }                                                                                                          \
-        }                                                                                                              \
-        for (; j < ipph; ++j) {                                                                                        \
-            const float x0 = pf[0], y0 = pb[0];                                                                        \
-            pf += st;                                                                                                  \
-            pb -= st;                                                                                                  \
-            _Pragma("unroll") for (int q = 0; q < LB; ++q) {                                                           \
-                const float2 t = __ldg(trow[q]);                                                                       \
-                trow[q] += 1;                                                                                          \
-                a_[q] += t.x * x0;                                                                                     \
-                b_[q] += t.y * y0;                                                                                     \
-            }                                                                                                          \
-        }                                                                                                              \
-        float *pd = (dst) + ik * c.GP + c.r;                                                                           \
-        _Pragma("unroll") for (int q = 0; q < LB; ++q)                                                                 \
-            if (q < nl) { pd[(l0 + q) * st] = a_[q]; pd[(ip - l0 - q) * st] = b_[q]; }                                 \
+// One thread owns LB consecutive l for one ik, so every SRC value it loads from shared memory feeds LB output pairs.
+// The (cos, sin) pairs come from a per-pass table T[l-1][j-1] staged in shared memory (warp-uniform 128-bit loads) that
+// holds csarr[2*((l*j) mod ip)] — the values pocketfft walks with its iang counter.  The cos-sum and the sin-sum of one l
+// advance in lock step, so they share packed f32x2 instructions: products as fma(t, v, -0.0) (an exactly rounded
+// product that ptxas cannot re-contract with the following add; -0.0 arrives as a kernel argument), sums as FADD2 in
+// the reference's association order.
+constexpr int LB = 8;
+__device__ __forceinline__ float2 mul2x(float2 t, float2 v, float2 nz) { return __ffma2_rn(t, v, nz); }
+__device__ __forceinline__ void generic_block(const Ctx &c, const float *src, float *dst, const float2 *sgt, int JP, int ip,
+                                              int ipph, int idl1, int lb, int ik, float2 nz)
+{
+    const int l0 = 1 + LB * lb, nl = min(LB, ipph - l0);
+    const int st = idl1 * c.GP;
+    const float *pf = src + ik * c.GP + c.r;
+    const float *pb = pf + (ip - 1) * st;
+    float2 A[LB];
+    const float4 *trow[LB];
+#pragma unroll
+    for (int q = 0; q < LB; ++q) trow[q] = reinterpret_cast<const float4 *>(sgt + (min(l0 + q, ipph - 1) - 1) * JP);
+    {
+        const float2 x0 = make_float2(pf[0], 0.f);
+        const float2 v1 = make_float2(pf[st], pb[0]), v2 = make_float2(pf[2 * st], pb[-st]);
+#pragma unroll
+        for (int q = 0; q < LB; ++q) {
+            const float4 t = trow[q][0];
+            A[q] = __fadd2_rn(__fadd2_rn(x0, mul2x(make_float2(t.x, t.y), v1, nz)), mul2x(make_float2(t.z, t.w), v2, nz));
+        }
     }
+    pf += 3 * st;
+    pb -= 2 * st;
+    int j = 3, h = 1;   // h: float4 index of column j-1 in the table row
+    for (; j + 3 < ipph; j += 4, h += 2) {
+        const float2 v0 = make_float2(pf[0], pb[0]), v1 = make_float2(pf[st], pb[-st]);
+        const float2 v2 = make_float2(pf[2 * st], pb[-2 * st]), v3 = make_float2(pf[3 * st], pb[-3 * st]);
+        pf += 4 * st;
+        pb -= 4 * st;
+#pragma unroll
+        for (int q = 0; q < LB; ++q) {
+            const float4 t = trow[q][h], u = trow[q][h + 1];
+            float2 sacc = __fadd2_rn(mul2x(make_float2(t.x, t.y), v0, nz), mul2x(make_float2(t.z, t.w), v1, nz));
+            sacc = __fadd2_rn(sacc, mul2x(make_float2(u.x, u.y), v2, nz));
+            sacc = __fadd2_rn(sacc, mul2x(make_float2(u.z, u.w), v3, nz));
+            A[q] = __fadd2_rn(A[q], sacc);
+        }
+    }
+    for (; j + 1 < ipph; j += 2, h += 1) {
+        const float2 v0 = make_float2(pf[0], pb[0]), v1 = make_float2(pf[st], pb[-st]);
+        pf += 2 * st;
+        pb -= 2 * st;
+#pragma unroll
+        for (int q = 0; q < LB; ++q) {
+            const float4 t = trow[q][h];
+            A[q] = __fadd2_rn(A[q], __fadd2_rn(mul2x(make_float2(t.x, t.y), v0, nz), mul2x(make_float2(t.z, t.w), v1, nz)));
+        }
+    }
+    if (j < ipph) {
+        const float2 v0 = make_float2(pf[0], pb[0]);
+#pragma unroll
+        for (int q = 0; q < LB; ++q) {
+            const float2 t = reinterpret_cast<const float2 *>(trow[q])[2 * h];
+            A[q] = __fadd2_rn(A[q], mul2x(t, v0, nz));
+        }
+    }
+    float *pd = dst + ik * c.GP + c.r;
+#pragma unroll
+    for (int q = 0; q < LB; ++q)
+        if (q < nl) { pd[(l0 + q) * st] = A[q].x; pd[(ip - l0 - q) * st] = A[q].y; }
+}
+
+// exact integer division by a per-pass constant: q = umulhi(it, magic), magic = floor(2^32 / d) + 1 (0 encodes d == 1);
+// valid while it * d < 2^32, which the plan builder checks
+__device__ __forceinline__ int fdiv(int it, unsigned magic) { return magic ? (int)__umulhi((unsigned)it, magic) : it; }
 
 // generic odd radix, forward; the result ends in cc.  `cs` is a shared-memory copy of csarr (2*ip floats).
-__device__ void radfg(const Ctx &c, int ido, int ip, int l1, float *cc, float *ch, const float *wa, const float2 *gt)
+__device__ void radfg(const Ctx &c, const XPass &P, float *cc, float *ch, const float *wa, const float2 *gt, float2 *sgt, float2 nz)
 {
+    const int ido = P.ido, ip = P.ip, l1 = P.l1;
     const int cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
     const int JP = (ipph - 1 + 3) & ~3, nlb = (ipph - 1 + LB - 1) / LB;
+    for (int i = threadIdx.x; i < (ipph - 1) * JP; i += kXT) sgt[i] = __ldg(gt + i);   // visible after the next barrier
 #define CC(a, b, k_) cc[IDX((a) + ido * ((b) + cdim * (k_)))]
 #define CH(a, b, k_) ch[IDX((a) + ido * ((b) + l1 * (k_)))]
 #define C1(a, b, k_) cc[IDX((a) + ido * ((b) + l1 * (k_)))]
@@ -252,8 +264,8 @@ __device__ void radfg(const Ctx &c, int ido, int ip, int l1, float *cc, float *c
     if (ido > 1) {
         const int ni = (ido - 1) >> 1;
         FOR_ITEMS(it, (ipph - 1) * l1 * ni) {
-            const int jj = it / (l1 * ni), rem = it - jj * (l1 * ni);
-            const int k = rem / ni, i = 1 + 2 * (rem - k * ni);
+            const int jj = fdiv(it, P.m_l1ni), rem = it - jj * (l1 * ni);
+            const int k = fdiv(rem, P.m_ni), i = 1 + 2 * (rem - k * ni);
             const int j = jj + 1, jc = ip - j;
             const int idij = (j - 1) * (ido - 1) + (i - 1), idij2 = (jc - 1) * (ido - 1) + (i - 1);
             const float t1 = C1(i, k, j), t2 = C1(i + 1, k, j), t3 = C1(i, k, jc), t4 = C1(i + 1, k, jc);
@@ -264,34 +276,34 @@ __device__ void radfg(const Ctx &c, int ido, int ip, int l1, float *cc, float *c
         }
     }
     FOR_ITEMS(it, (ipph - 1) * l1) {
-        const int jj = it / l1, k = it - jj * l1, j = jj + 1, jc = ip - j;
+        const int jj = fdiv(it, P.m_l1), k = it - jj * l1, j = jj + 1, jc = ip - j;
         const float t1 = C1(0, k, j), t2 = C1(0, k, jc);
         PM(C1(0, k, j), C1(0, k, jc), t2, t1)
     }
     __syncthreads();
     FOR_ITEMS(it, (nlb + 1) * idl1) {
-        const int lb = it / idl1, ik = it - lb * idl1;
+        const int lb = fdiv(it, P.m_idl1), ik = it - lb * idl1;
         if (lb == nlb) {
             float s = C2(ik, 0);
             for (int j = 1; j < ipph; ++j) s += C2(ik, j);
             CH2(ik, 0) = s;
-        } else GENERIC_BLOCK(cc, ch)
+        } else generic_block(c, cc, ch, sgt, JP, ip, ipph, idl1, lb, ik, nz);
     }
     __syncthreads();
     FOR_ITEMS(it, l1 * ido) {
-        const int k = it / ido, i = it - k * ido;
+        const int k = fdiv(it, P.m_ido), i = it - k * ido;
         CC(i, 0, k) = CH(i, k, 0);
     }
     FOR_ITEMS(it, (ipph - 1) * l1) {
-        const int jj = it / l1, k = it - jj * l1, j = jj + 1, jc = ip - j, j2 = 2 * j - 1;
+        const int jj = fdiv(it, P.m_l1), k = it - jj * l1, j = jj + 1, jc = ip - j, j2 = 2 * j - 1;
         CC(ido - 1, j2, k) = CH(0, k, j);
         CC(0, j2 + 1, k) = CH(0, k, jc);
     }
     if (ido > 1) {
         const int ni = (ido - 1) >> 1;
         FOR_ITEMS(it, (ipph - 1) * l1 * ni) {
-            const int jj = it / (l1 * ni), rem = it - jj * (l1 * ni);
-            const int k = rem / ni, i = 1 + 2 * (rem - k * ni), ic = ido - i - 2;
+            const int jj = fdiv(it, P.m_l1ni), rem = it - jj * (l1 * ni);
+            const int k = fdiv(rem, P.m_ni), i = 1 + 2 * (rem - k * ni), ic = ido - i - 2;
             const int j = jj + 1, jc = ip - j, j2 = 2 * j - 1;
             CC(i, j2 + 1, k) = CH(i, k, j) + CH(i, k, jc);
             CC(ic, j2, k) = CH(i, k, j) - CH(i, k, jc);
@@ -451,26 +463,28 @@ __device__ void radb5(const Ctx &c, int ido, int l1, const float *cc, float *ch,
 }
 
 // generic odd radix, backward; the result ends in ch
-__device__ void radbg(const Ctx &c, int ido, int ip, int l1, float *cc, float *ch, const float *wa, const float2 *gt)
+__device__ void radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const float *wa, const float2 *gt, float2 *sgt, float2 nz)
 {
+    const int ido = P.ido, ip = P.ip, l1 = P.l1;
     const int cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
     const int JP = (ipph - 1 + 3) & ~3, nlb = (ipph - 1 + LB - 1) / LB;
+    for (int i = threadIdx.x; i < (ipph - 1) * JP; i += kXT) sgt[i] = __ldg(gt + i);   // visible after the next barrier
 #define CC(a, b, k_) cc[IDX((a) + ido * ((b) + cdim * (k_)))]
 #define CH(a, b, k_) ch[IDX((a) + ido * ((b) + l1 * (k_)))]
     FOR_ITEMS(it, l1 * ido) {
-        const int k = it / ido, i = it - k * ido;
+        const int k = fdiv(it, P.m_ido), i = it - k * ido;
         CH(i, k, 0) = CC(i, 0, k);
     }
     FOR_ITEMS(it, (ipph - 1) * l1) {
-        const int jj = it / l1, k = it - jj * l1, j = jj + 1, jc = ip - j, j2 = 2 * j - 1;
+        const int jj = fdiv(it, P.m_l1), k = it - jj * l1, j = jj + 1, jc = ip - j, j2 = 2 * j - 1;
         CH(0, k, j) = 2 * CC(ido - 1, j2, k);
         CH(0, k, jc) = 2 * CC(0, j2 + 1, k);
     }
     if (ido != 1) {
         const int ni = (ido - 1) >> 1;
         FOR_ITEMS(it, (ipph - 1) * l1 * ni) {
-            const int jj = it / (l1 * ni), rem = it - jj * (l1 * ni);
-            const int k = rem / ni, i = 1 + 2 * (rem - k * ni), ic = ido - i - 2;
+            const int jj = fdiv(it, P.m_l1ni), rem = it - jj * (l1 * ni);
+            const int k = fdiv(rem, P.m_ni), i = 1 + 2 * (rem - k * ni), ic = ido - i - 2;
             const int j = jj + 1, jc = ip - j, j2 = 2 * j - 1;
             CH(i, k, j) = CC(i, j2 + 1, k) + CC(ic, j2, k);
             CH(i, k, jc) = CC(i, j2 + 1, k) - CC(ic, j2, k);
@@ -482,24 +496,24 @@ __device__ void radbg(const Ctx &c, int ido, int ip, int l1, float *cc, float *c
     // C2(ik, l >= 1) from CH2; the l == 0 item forms CH2(ik,0) + sum_j CH2(ik,j) and parks it in C2(ik,0) (cc's slot 0
     // is free) because the other items of this phase still read the old CH2(ik,0)
     FOR_ITEMS(it, (nlb + 1) * idl1) {
-        const int lb = it / idl1, ik = it - lb * idl1;
+        const int lb = fdiv(it, P.m_idl1), ik = it - lb * idl1;
         if (lb == nlb) {
             float s = CH2(ik, 0);
             for (int j = 1; j < ipph; ++j) s += CH2(ik, j);
             C2(ik, 0) = s;
-        } else GENERIC_BLOCK(ch, cc)
+        } else generic_block(c, ch, cc, sgt, JP, ip, ipph, idl1, lb, ik, nz);
     }
     __syncthreads();
     FOR_ITEMS(ik, idl1) CH2(ik, 0) = C2(ik, 0);
     FOR_ITEMS(it, (ipph - 1) * l1) {
-        const int jj = it / l1, k = it - jj * l1, j = jj + 1, jc = ip - j;
+        const int jj = fdiv(it, P.m_l1), k = it - jj * l1, j = jj + 1, jc = ip - j;
         PM(CH(0, k, jc), CH(0, k, j), C1(0, k, j), C1(0, k, jc))
     }
     if (ido != 1) {
         const int ni = (ido - 1) >> 1;
         FOR_ITEMS(it, (ipph - 1) * l1 * ni) {
-            const int jj = it / (l1 * ni), rem = it - jj * (l1 * ni);
-            const int k = rem / ni, i = 1 + 2 * (rem - k * ni);
+            const int jj = fdiv(it, P.m_l1ni), rem = it - jj * (l1 * ni);
+            const int k = fdiv(rem, P.m_ni), i = 1 + 2 * (rem - k * ni);
             const int j = jj + 1, jc = ip - j;
             const float a0 = C1(i, k, j) - C1(i + 1, k, jc);      // CH(i  ,k,j )
             const float a1 = C1(i, k, j) + C1(i + 1, k, jc);      // CH(i  ,k,jc)
@@ -721,7 +735,6 @@ __device__ void cpass(const Ctx &c, int ido, int l1, const float2 *cc0, float2 *
     }
 }
 
-struct XPass { int kind, ip, l1, ido, tw, cs; };   // kind: 2,3,4,5 = radix, 6 = generic, 7 = Bluestein
 struct XBlue {
     int ip, n2, nf;
     int fct[12], tw[12];   // complex sub-plan: factors in pass order, twiddle offsets (floats) into the table
@@ -738,6 +751,8 @@ struct XArgs {
     XPass fwd[12], bwd[12];
     XBlue blue;
     float fct;           // 1/n
+    float negzero;       // -0.0f, deliberately a run-time value (see mul2x)
+    int gt_max;          // float2 entries reserved for the generic-radix table
     int groups_per_plane;
 };
 
@@ -856,7 +871,9 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
     extern __shared__ __align__(16) float xs[];
     const int n = a.n, G = a.G, GP = G;   // unpadded: 32/G consecutive elements x G rows hit 32 different banks
     float *A = xs, *B = A + n * GP;
-    float2 *X0 = reinterpret_cast<float2 *>(B + n * GP);   // Bluestein work buffers (offset 2*n*GP floats: 8-byte aligned)
+    float2 *sgt = reinterpret_cast<float2 *>(xs + ((2 * n * GP + 3) & ~3));   // generic-radix (cos, sin) table of the running pass
+    float2 *X0 = sgt + a.gt_max;                            // Bluestein work buffers
+    const float2 nz = make_float2(a.negzero, a.negzero);
     float2 *X1 = X0 + (size_t)a.blue.inst * a.blue.n2 * GP;
 
     Ctx c;
@@ -895,7 +912,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
             case 3: radf3(c, p.ido, p.l1, p1, p2, wa); break;
             case 4: radf4(c, p.ido, p.l1, p1, p2, wa); break;
             case 5: radf5(c, p.ido, p.l1, p1, p2, wa); break;
-            case 6: radfg(c, p.ido, p.ip, p.l1, p1, p2, wa, reinterpret_cast<const float2 *>(a.tab + p.cs)); swap = false; break;
+            case 6: radfg(c, p, p1, p2, wa, reinterpret_cast<const float2 *>(a.tab + p.cs), sgt, nz); swap = false; break;
             default: rblue<true>(c, a.blue, a.tab, p.ido, p.l1, p1, p2, wa, X0, X1); break;
             }
             __syncthreads();
@@ -916,7 +933,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
             case 3: radb3(c, p.ido, p.l1, p1, p2, wa); break;
             case 4: radb4(c, p.ido, p.l1, p1, p2, wa); break;
             case 5: radb5(c, p.ido, p.l1, p1, p2, wa); break;
-            case 6: radbg(c, p.ido, p.ip, p.l1, p1, p2, wa, reinterpret_cast<const float2 *>(a.tab + p.cs)); break;
+            case 6: radbg(c, p, p1, p2, wa, reinterpret_cast<const float2 *>(a.tab + p.cs), sgt, nz); break;
             default: rblue<false>(c, a.blue, a.tab, p.ido, p.l1, p1, p2, wa, X0, X1); break;
             }
             __syncthreads();
@@ -1026,10 +1043,11 @@ size_t good_size_cmplx(size_t n)
     return bestfac;
 }
 
-size_t xfft_smem(int n, int G, const XBlue &b)
+size_t xfft_smem(int n, int G, const XBlue &b, int gt_max)
 {
     const size_t GP = G;
-    return sizeof(float) * (2 * (size_t)n * GP + 2) + sizeof(float2) * 2 * (size_t)b.inst * b.n2 * GP;
+    const size_t ab = (2 * (size_t)n * GP + 3) & ~(size_t)3;   // keeps the table 16-byte aligned
+    return sizeof(float) * ab + sizeof(float2) * ((size_t)gt_max + 2 * (size_t)b.inst * b.n2 * GP);
 }
 
 }  // namespace
@@ -1104,20 +1122,37 @@ B2sXfftPlan *b2s_xfft_create(int n)
     }
     if (n_blue > 1) { delete pl; return nullptr; }
     a.nf = nf;
+    a.negzero = -0.0f;
+    a.gt_max = 0;
+    bool magic_ok = true;
+    auto magic = [&](int d, long long max_it) -> unsigned {
+        if (d <= 1) return 0u;
+        if (max_it * d >= (1LL << 32)) magic_ok = false;
+        return (unsigned)((1ULL << 32) / (unsigned)d) + 1u;
+    };
+    auto make_pass = [&](int k, int l1, int ido) {
+        const int ip = fct[k], ni = (ido - 1) / 2, ipph = (ip + 1) / 2;
+        const long long max_it = (long long)n * 2 + 64;     // every item loop of a pass runs over fewer than 2n items
+        XPass p{ip <= 5 ? ip : (ip < 135 ? 6 : 7), ip, l1, ido, tw_off[k], cs_off[k],
+                magic(l1, max_it), magic(ni, max_it), magic(l1 * ni, max_it), magic(ido, max_it), magic(ido * l1, max_it)};
+        if (p.kind == 6) a.gt_max = std::max(a.gt_max, (ipph - 1) * ((ipph - 1 + 3) & ~3));
+        return p;
+    };
     {
         int l1 = n;
         for (int k1 = 0; k1 < nf; ++k1) {   // forward: last factor first
             const int k = nf - 1 - k1, ip = fct[k], ido = n / l1;
             l1 /= ip;
-            a.fwd[k1] = XPass{ip <= 5 ? ip : (ip < 135 ? 6 : 7), ip, l1, ido, tw_off[k], cs_off[k]};
+            a.fwd[k1] = make_pass(k, l1, ido);
         }
         l1 = 1;
         for (int k = 0; k < nf; ++k) {
             const int ip = fct[k], ido = n / (ip * l1);
-            a.bwd[k] = XPass{ip <= 5 ? ip : (ip < 135 ? 6 : 7), ip, l1, ido, tw_off[k], cs_off[k]};
+            a.bwd[k] = make_pass(k, l1, ido);
             l1 *= ip;
         }
     }
+    if (!magic_ok) { delete pl; return nullptr; }
     XBlue &b = a.blue;
     std::vector<float2> tbkf;
     if (n_blue) {
@@ -1196,9 +1231,9 @@ B2sXfftPlan *b2s_xfft_create(int n)
                     if (a.fwd[f].kind == 7) need = a.fwd[f].l1 * (1 + (a.fwd[f].ido - 1) / 2);
                 for (int inst = need < 8 ? need : 8; inst >= 1; --inst) {
                     b.inst = inst;
-                    if (xfft_smem(n, g, b) <= (size_t)budget) { G = g; break; }
+                    if (xfft_smem(n, g, b, a.gt_max) <= (size_t)budget) { G = g; break; }
                 }
-            } else if (xfft_smem(n, g, b) <= (size_t)budget) G = g;
+            } else if (xfft_smem(n, g, b, a.gt_max) <= (size_t)budget) G = g;
         }
         if (G) break;
     }
@@ -1206,7 +1241,7 @@ B2sXfftPlan *b2s_xfft_create(int n)
     a.G = G;
     a.lgG = 0;
     while ((1 << a.lgG) < G) ++a.lgG;
-    pl->smem = xfft_smem(n, G, b);
+    pl->smem = xfft_smem(n, G, b, a.gt_max);
     return pl;
 }
 
