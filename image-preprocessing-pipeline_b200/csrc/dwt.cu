@@ -274,6 +274,7 @@ struct FwdArgs {
     B2sImg in, cA, cH, cV, cD;
     int F, Fp, nch;
     int tiles_x, tiles_y, n_tiles;
+    int grid3d;      // launched as (tiles_x, tiles_y, planes): one tile per CTA
     float negzero;   // -0.0f, deliberately a run-time value (see mul2_exact)
 };
 
@@ -311,8 +312,14 @@ __global__ void __launch_bounds__(T::NT) k_dwt_fwd(const __grid_constant__ FwdTa
     const int tiles_xy = a.tiles_x * a.tiles_y;
 
     // stage the input window of tile t (half-sample symmetric extension resolved here); asynchronous
+    // 3-D launch (one tile per CTA): coordinates come from blockIdx, no integer division on the critical path
+    const bool grid3d = gridDim.y > 1 || gridDim.z > 1 || a.grid3d;
+    auto coord_of = [&](int t) -> TileCoord {
+        if (grid3d) { TileCoord c; c.plane = blockIdx.z; c.ty = blockIdx.y; c.tx = blockIdx.x; return c; }
+        return tile_of(t, a.tiles_x, tiles_xy);
+    };
     auto issue_load = [&](int t) {
-        const TileCoord c = tile_of(t, a.tiles_x, tiles_xy);
+        const TileCoord c = coord_of(t);
         const int gy0 = 2 * c.ty * TY + 2 - Fp;            // image row of shared row 0
         const int gx0a = (2 * c.tx * TX + 2 - Fp) & ~3;    // 16-byte aligned image column of shared column 0
         const float *src = a.in.ptr + (size_t)c.plane * a.in.plane_stride;
@@ -351,13 +358,14 @@ __global__ void __launch_bounds__(T::NT) k_dwt_fwd(const __grid_constant__ FwdTa
         }
     };
 
-    int t = blockIdx.x;
-    if (t < a.n_tiles) issue_load(t);
-    while (t < a.n_tiles) {
+    int t = grid3d ? 0 : blockIdx.x;
+    const int t_end = grid3d ? 1 : a.n_tiles, t_step = grid3d ? 1 : gridDim.x;
+    if (t < t_end) issue_load(t);
+    while (t < t_end) {
         cp_async_wait_all();
         __syncthreads();   // tile t has landed; every warp is done with s_mid of the previous tile
 
-        const TileCoord c = tile_of(t, a.tiles_x, tiles_xy);
+        const TileCoord c = coord_of(t);
         const int oy0 = c.ty * TY, ox0 = c.tx * TX;
         // does this tile hold outputs whose window overhangs the bottom / right edge (the reference visits their taps
         // in another order, see analysis_right_edge)?
@@ -393,8 +401,8 @@ __global__ void __launch_bounds__(T::NT) k_dwt_fwd(const __grid_constant__ FwdTa
         }
         __syncthreads();   // s_mid complete; s_in is free again
 
-        const int tn = t + gridDim.x;
-        if (tn < a.n_tiles) issue_load(tn);
+        const int tn = t + t_step;
+        if (tn < t_end) issue_load(tn);
 
         // ---- axis -1 pass.  RX = 4: a warp covers 8 rows x 4 column groups; RX = 8: 16 rows x 2 column groups.  Either way
         //      the 128-bit window loads of a quarter warp hit 8 different bank quads (PM/4 odd).
@@ -451,6 +459,7 @@ struct InvArgs {
     B2sImg cA, cH, cV, cD, out;
     int H, Hp, nch;
     int tiles_x, tiles_y, n_tiles;
+    int grid3d;
     float negzero;
 };
 
@@ -474,8 +483,13 @@ __global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTa
 
     // stage the four coefficient windows of tile t; everything outside the sub-band is zero (it only meets zero taps
     // or outputs that are not stored)
+    const bool grid3d = gridDim.y > 1 || gridDim.z > 1 || a.grid3d;
+    auto coord_of = [&](int t) -> TileCoord {
+        if (grid3d) { TileCoord c; c.plane = blockIdx.z; c.ty = blockIdx.y; c.tx = blockIdx.x; return c; }
+        return tile_of(t, a.tiles_x, tiles_xy);
+    };
     auto issue_load = [&](int t) {
-        const TileCoord c = tile_of(t, a.tiles_x, tiles_xy);
+        const TileCoord c = coord_of(t);
         const int cy0 = c.ty * TQ + a.H - Hp, cx0 = c.tx * TP + a.H - Hp;   // coefficient coordinates of shared (0, 0)
         const bool aligned = (cx0 & 3) == 0;
         if (aligned && cy0 >= 0 && cy0 + RQ <= my && cx0 >= 0 && cx0 + 4 * c4n <= mx) {
@@ -520,13 +534,14 @@ __global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTa
         }
     };
 
-    int t = blockIdx.x;
-    if (t < a.n_tiles) issue_load(t);
-    while (t < a.n_tiles) {
+    int t = grid3d ? 0 : blockIdx.x;
+    const int t_end = grid3d ? 1 : a.n_tiles, t_step = grid3d ? 1 : gridDim.x;
+    if (t < t_end) issue_load(t);
+    while (t < t_end) {
         cp_async_wait_all();
         __syncthreads();   // tile t has landed; every warp is done with s_mid of the previous tile
 
-        const TileCoord c = tile_of(t, a.tiles_x, tiles_xy);
+        const TileCoord c = coord_of(t);
         const int q0 = c.ty * TQ, p0 = c.tx * TP;
 
         // ---- axis -1 synthesis: (cA,cV) -> a, (cH,cD) -> d   [idwtn handles the last axis first]
@@ -554,8 +569,8 @@ __global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTa
         }
         __syncthreads();   // s_mid complete; s_sub is free again
 
-        const int tn = t + gridDim.x;
-        if (tn < a.n_tiles) issue_load(tn);
+        const int tn = t + t_step;
+        if (tn < t_end) issue_load(tn);
 
         // ---- axis -2 synthesis: (a, d) -> out rows 2q, 2q+1
         {
@@ -637,7 +652,9 @@ void launch_fwd_t(const FwdTaps &ft, FwdArgs a, int n_planes, int sm_count, cuda
     if (per_sm > 2048 / T::NT) per_sm = 2048 / T::NT;
     if (per_sm < 1) per_sm = 1;
     static const int persist = dev_knob("B2S_DWT_PERSIST", 0);
-    const int grid = (!persist || a.n_tiles < sm_count * per_sm) ? a.n_tiles : sm_count * per_sm;
+    const bool one_per_cta = !persist || a.n_tiles < sm_count * per_sm;
+    a.grid3d = one_per_cta && n_planes <= 65535 && a.tiles_y <= 65535;
+    const dim3 grid = a.grid3d ? dim3(a.tiles_x, a.tiles_y, n_planes) : dim3(one_per_cta ? a.n_tiles : sm_count * per_sm);
     cudaFuncSetAttribute(k_dwt_fwd<T, J, MULTI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     k_dwt_fwd<T, J, MULTI, MODE><<<grid, T::NT, bytes, s>>>(ft, a);
 }
@@ -674,7 +691,9 @@ void launch_inv_t(const InvTaps &it, InvArgs a, int n_planes, int sm_count, cuda
     if (per_sm > 2048 / T::NT) per_sm = 2048 / T::NT;
     if (per_sm < 1) per_sm = 1;
     static const int persist = dev_knob("B2S_DWT_PERSIST", 0);
-    const int grid = (!persist || a.n_tiles < sm_count * per_sm) ? a.n_tiles : sm_count * per_sm;
+    const bool one_per_cta = !persist || a.n_tiles < sm_count * per_sm;
+    a.grid3d = one_per_cta && n_planes <= 65535 && a.tiles_y <= 65535;
+    const dim3 grid = a.grid3d ? dim3(a.tiles_x, a.tiles_y, n_planes) : dim3(one_per_cta ? a.n_tiles : sm_count * per_sm);
     cudaFuncSetAttribute(k_dwt_inv<T, JH, MULTI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     k_dwt_inv<T, JH, MULTI, MODE><<<grid, T::NT, bytes, s>>>(it, a);
 }

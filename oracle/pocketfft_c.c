@@ -1207,10 +1207,60 @@ static void rfftp_exec(const rfftp_t *p, float *c, float fct, int r2hc)
     free(ch);
 }
 
+/* ---- ducc0 rfftp_complexify<float>: even lengths > 1000 run as one complex transform of half the length */
+static int complexify_exec(float *c, size_t N, float fct, int fwd)
+{
+    size_t h = N / 2;
+    cfftp_t plan;
+    if (cfftp_init(&plan, h)) return -2;
+    sincos_t roots; sc_init(&roots, N);
+    cf *res = (cf *)malloc(sizeof(cf) * h);
+    if (fwd) {
+        memcpy(res, c, sizeof(cf) * h);
+        cfftp_exec(&plan, res, 1.f, 1);
+        float *r = (float *)malloc(sizeof(float) * N);
+        r[0] = res[0].r + res[0].i;
+        for (size_t i = 1, xi = h - 1; i <= xi; ++i, --xi) {
+            cf xe = {res[i].r + res[xi].r, res[i].i - res[xi].i};          /* res[i] + conj(res[xi]) */
+            cf t = {res[i].i + res[xi].i, res[xi].r - res[i].r};
+            cf w = sc_get(&roots, i);                                       /* conj applied in the product */
+            cf xo = {t.r * w.r + t.i * w.i, t.i * w.r - t.r * w.i};
+            r[2 * i - 1] = 0.5f * (xe.r + xo.r);
+            r[2 * i] = 0.5f * (xe.i + xo.i);
+            r[2 * xi - 1] = 0.5f * (xe.r - xo.r);
+            r[2 * xi] = 0.5f * (xo.i - xe.i);
+        }
+        r[N - 1] = res[0].r - res[0].i;
+        for (size_t i = 0; i < N; ++i) c[i] = fct != 1.f ? r[i] * fct : r[i];
+        free(r);
+    } else {
+        res[0].r = c[0] + c[N - 1]; res[0].i = c[0] - c[N - 1];
+        for (size_t i = 1, xi = h - 1; i <= xi; ++i, --xi) {
+            cf t1 = {c[2 * i - 1], c[2 * i]};
+            cf t2 = {c[2 * xi - 1], -c[2 * xi]};
+            cf xe = {t1.r + t2.r, t1.i + t2.i};
+            cf d = {t1.r - t2.r, t1.i - t2.i};
+            cf w = sc_get(&roots, i);
+            cf xo = {d.r * w.r - d.i * w.i, d.r * w.i + d.i * w.r};
+            res[i].r = xe.r - xo.i; res[i].i = xe.i + xo.r;
+            res[xi].r = xe.r + xo.i; res[xi].i = -xe.i + xo.r;
+        }
+        cfftp_exec(&plan, res, 1.f, 0);
+        float *r = (float *)res;
+        for (size_t i = 0; i < N; ++i) c[i] = fct != 1.f ? r[i] * fct : r[i];
+    }
+    free(res);
+    sc_free(&roots);
+    cfftp_free(&plan);
+    return 0;
+}
+
 /* ================================================================ pocketfft_r<float> + r2r_fftpack */
 /* 1 when this restatement covers length n: ducc0 switches even lengths > 1000 to a half-length complex transform
  * (rfftp_complexify), which is not restated here. */
-int orc_fft_mirrored(size_t n) { return n >= 1 && !(n > 1000 && (n & 1) == 0); }
+static int orc_allow_all = 0;
+void orc_fft_allow_all(int v) { orc_allow_all = v; }
+int orc_fft_mirrored(size_t n) { return n >= 1 && (orc_allow_all || !(n > 1000 && (n & 1) == 0)); }
 
 /* scipy.fftpack.rfft (forward != 0) / irfft (forward == 0, scaled by 1/n) on `rows` contiguous rows of length n.
  * Returns 0, or 1 when the length class is not restated (data untouched). */
@@ -1219,6 +1269,10 @@ int orc_fftpack_r2r_f32(float *data, size_t rows, size_t n, int forward)
     if (n == 0) return -1;
     if (!orc_fft_mirrored(n)) return 1;
     float fct = forward ? 1.f : (float)(1.0L / (long double)n);
+    if (n > 1000 && (n & 1) == 0) {
+        for (size_t r = 0; r < rows; ++r) { int rc = complexify_exec(data + r * n, n, fct, forward); if (rc) return rc; }
+        return 0;
+    }
     rfftp_t p;
     rfftp_init(&p, n);
     for (size_t r = 0; r < rows; ++r) rfftp_exec(&p, data + r * n, fct, forward);
