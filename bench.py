@@ -263,8 +263,22 @@ def run_b200(a):
         launches_per_plane = kn / planes_timed
         alg_bytes_per_launch = per_plane / launches_per_plane
         achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
+        # DRAM traffic of that kernel from the committed `ncu --set full` capture (dram__bytes_read+write per launch)
+        traffic, traffic_src = None, None
+        tf = ROOT / "profiles" / "r01_traffic.json"
+        if tf.exists():
+            tj = json.loads(tf.read_text())
+            ent = tj["kernels"].get(f"{kname}@L{lvl}" if lvl else kname)
+            if ent:
+                traffic = ent["dram_bytes_per_plane"] / launches_per_plane
+                traffic_src = tj["source"]
+        # the competing ceiling: FP32 lane-ops (exact mode issues a separate multiply and add per tap)
+        fp32_peak = 148 * 128 * 1.965e9
+        fp32 = {"flops_per_plane_model": int(info.flops_per_plane), "peak_lane_ops_per_s": fp32_peak,
+                "whole_pipeline_frac": info.flops_per_plane * a.steps * P / (ms_max * 1e-3) / fp32_peak,
+                "note": "DWT multiply-adds only (2 lane-ops per MAC in exact mode); FFT, log1p/expm1 and index work come on top"}
         roof = {"bound": "hbm", "kernel": f"{kname}@level{lvl}" if lvl else kname, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "fp32": fp32,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
                 "planes_per_launch": nb_per_launch, "share_of_step": round(kms / total, 4),

@@ -170,3 +170,68 @@ B2S_HD float b2s_expm1f(float x)
     }
     return y;
 }
+
+
+// ---- device hot paths ---------------------------------------------------------------------------------------------
+// The same operations as above, in the same order, for the argument range pixel data lives in; everything else falls
+// back to the general routine.  (One range test replaces the chain of special-case branches the general routines walk
+// for every pixel; tests/test_gpu_parity.py::test_device_math_is_bit_exact covers both paths against the host libm.)
+#if defined(__CUDACC__)
+__device__ __forceinline__ float b2s_expm1f_dev(float x)
+{
+    if (!(x >= 1.1f && x < 38.0f)) return b2s_expm1f(x);      // here 2 <= k <= 55
+    const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f, invln2 = 1.4426950216e+00f;
+    const float Q1 = -3.3333335072e-02f, Q2 = 1.5873016091e-03f, Q3 = -7.9365076090e-05f,
+                Q4 = 4.0082177293e-06f, Q5 = -2.0109921195e-07f;
+    const int32_t k = (int32_t)(invln2 * x + 0.5f);
+    const float t = (float)k;
+    const float hi = x - t * ln2_hi, lo = t * ln2_lo;
+    const float xr = hi - lo;
+    const float c = (hi - xr) - lo;
+    const float hfx = 0.5f * xr;
+    const float hxs = xr * hfx;
+    const float r1 = 1.0f + hxs * (Q1 + hxs * (Q2 + hxs * (Q3 + hxs * (Q4 + hxs * Q5))));
+    const float tt = 3.0f - r1 * hfx;
+    float e = hxs * ((r1 - tt) / (6.0f - xr * tt));
+    e = (xr * (e - c) - c);
+    e -= hxs;
+    float y;
+    if (k < 23) {
+        y = b2s_i2f(0x3f800000 - (0x1000000 >> k)) - (e - xr);
+    } else {
+        y = xr - (e + b2s_i2f((0x7f - k) << 23));
+        y += 1.0f;
+    }
+    return b2s_i2f(b2s_f2i(y) + (k << 23));
+}
+
+__device__ __forceinline__ float b2s_log1pf_dev(float x)
+{
+    if (!(x >= 0.5f && x < 1.0e9f)) return b2s_log1pf(x);     // here k != 0 and hx < 0x5a000000
+    const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f;
+    const float Lp1 = 6.6666668653e-01f, Lp2 = 4.0000000596e-01f, Lp3 = 2.8571429849e-01f,
+                Lp4 = 2.2222198546e-01f, Lp5 = 1.8183572590e-01f, Lp6 = 1.5313838422e-01f,
+                Lp7 = 1.4798198640e-01f;
+    float u = 1.0f + x;
+    int32_t hu = b2s_f2i(u);
+    int32_t k = (hu >> 23) - 127;
+    float c = (k > 0) ? 1.0f - (u - x) : x - (u - 1.0f);
+    c /= u;
+    hu &= 0x007fffff;
+    if (hu < 0x3504f7) {
+        u = b2s_i2f(hu | 0x3f800000);
+    } else {
+        k += 1;
+        u = b2s_i2f(hu | 0x3f000000);
+        hu = (0x00800000 - hu) >> 2;
+    }
+    if (hu == 0) return b2s_log1pf(x);                          // |f| < 2^-20: rare, general routine
+    const float f = u - 1.0f;
+    const float hfsq = 0.5f * f * f;
+    const float s = f / (2.0f + f);
+    const float z = s * s;
+    const float R = z * (Lp1 + z * (Lp2 + z * (Lp3 + z * (Lp4 + z * (Lp5 + z * (Lp6 + z * Lp7))))));
+    const float kf = (float)k;
+    return kf * ln2_hi - ((hfsq - (s * (hfsq + R) + (kf * ln2_lo + c))) - f);
+}
+#endif

@@ -153,6 +153,110 @@ __global__ void __launch_bounds__(NT == 32 ? 256 : NT) k_window_percentile(const
         a.grid[(size_t)blockIdx.y * n_win + win] = (unsigned short)(long long)value;   // C cast: truncation
 }
 
+// Integer pixels (uint8 / uint16), one CTA per window: two 16-bit keys per register, compared two at a time with the SIMD
+// video instructions (__vsetltu2 yields 0/1 per half-word), sample coordinates advanced incrementally (no division per
+// sample), the search started at the highest bit set in the window's maximum.  Missing samples are padded with 0xffff,
+// which is never below a probe.
+template <int NT, int KP>   // KP packed registers per thread: up to 2*KP*NT samples
+__global__ void __launch_bounds__(NT) k_window_percentile_u16(const GridArgs a)
+{
+    __shared__ unsigned scratch[32];
+    const int win = blockIdx.x;
+    const int n_win = a.gy.n * a.gx.n;
+    const int iy = win / a.gx.n, ix = win - iy * a.gx.n;
+    const int cy = a.gy.left + iy * a.gy.spacing, cx = a.gx.left + ix * a.gx.spacing;
+    const int y0 = max(0, cy - a.gy.hl), y1 = min(cy + a.gy.hr, a.gy.size);
+    const int x0 = max(0, cx - a.gx.hl), x1 = min(cx + a.gx.hr, a.gx.size);
+    const int ny = (y1 - y0 + a.gy.step - 1) / a.gy.step, nx = (x1 - x0 + a.gx.step - 1) / a.gx.step;
+    const int n = ny * nx;
+    const size_t plane_off = (size_t)blockIdx.y * a.rows * a.cols;
+    const unsigned short *p16 = reinterpret_cast<const unsigned short *>(a.img) + plane_off;
+    const unsigned char *p8 = reinterpret_cast<const unsigned char *>(a.img) + plane_off;
+    // sample t = tid + s*NT -> (ty, tx); advancing t by NT moves (ty, tx) by (dq, dr) with carry
+    const int dq = NT / nx, dr = NT - dq * nx;
+    int ty = threadIdx.x / nx, tx = threadIdx.x - ty * nx;
+    unsigned key[KP];
+    unsigned vmax = 0;
+#pragma unroll
+    for (int s = 0; s < KP; ++s) {
+        unsigned w = 0;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+            unsigned v = 0xffffu;
+            if (ty < ny) {
+                const size_t idx = (size_t)(y0 + ty * a.gy.step) * a.cols + (x0 + tx * a.gx.step);
+                v = a.dtype == B2S_U16 ? __ldg(p16 + idx) : __ldg(p8 + idx);
+                vmax = max(vmax, v);
+            }
+            w |= v << (16 * hlf);
+            ty += dq; tx += dr;
+            if (tx >= nx) { tx -= nx; ++ty; }
+        }
+        key[s] = w;
+    }
+    double value = 0.0;
+    if (n > 0) {
+        int k0, k1;
+        double m = 0.0;
+        if (n == 1) { k0 = k1 = 0; }
+        else if (a.q_is_100) { k0 = k1 = n - 1; }
+        else {
+            const double rank = 1.0 + (double)(n - 1) * a.qfrac;
+            const double f = floor(rank);
+            m = rank - f;
+            k0 = (int)f - 1;
+            k1 = min((int)f, n - 1);
+        }
+        // window maximum bounds the search
+        vmax = __reduce_max_sync(0xffffffffu, vmax);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = vmax;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) vmax = max(vmax, scratch[w]);
+        const int top = vmax ? 31 - __clz(vmax) : 0;
+        unsigned t = 0;
+        for (int b = top; b >= 0; --b) {
+            const unsigned p = t | (1u << b);
+            const unsigned pp = p | (p << 16);
+            unsigned c2 = 0;
+#pragma unroll
+            for (int s = 0; s < KP; ++s) c2 += __vsetltu2(key[s], pp);
+            unsigned c = (c2 & 0xffffu) + (c2 >> 16);
+            c = group_sum<NT>(c, scratch);
+            if (c <= (unsigned)k0) t = p;
+        }
+        unsigned v0 = t, v1 = t;
+        if (k1 != k0) {
+            // keys <= v0 and the smallest key above v0
+            unsigned le;
+            if (v0 >= 0xffffu) le = (unsigned)n;
+            else {
+                const unsigned q = v0 + 1, qq = q | (q << 16);
+                unsigned c2 = 0;
+#pragma unroll
+                for (int s = 0; s < KP; ++s) c2 += __vsetltu2(key[s], qq);
+                le = group_sum<NT>((c2 & 0xffffu) + (c2 >> 16), scratch);
+            }
+            if (le <= (unsigned)k1) {
+                unsigned nxt = 0xffffffffu;
+                int cnt = 0;   // only real samples: padding is 0xffff and may coincide with a real 0xffff, which is fine (same value)
+#pragma unroll
+                for (int s = 0; s < KP; ++s) {
+                    const unsigned lo = key[s] & 0xffffu, hi = key[s] >> 16;
+                    if (lo > v0) nxt = min(nxt, lo);
+                    if (hi > v0) nxt = min(nxt, hi);
+                }
+                (void)cnt;
+                v1 = group_min<NT>(nxt, scratch);
+            }
+        }
+        const double lower = (double)v0, upper = (double)v1;
+        value = (n == 1 || a.q_is_100) ? lower : lower * (1.0 - m) + upper * m;
+    }
+    if (threadIdx.x == 0) a.grid[(size_t)blockIdx.y * n_win + win] = (unsigned short)(long long)value;
+}
+
 // ---- scipy.ndimage.zoom axis tables -------------------------------------------------------------------------------
 struct ZoomAxis { const int *i0, *i1; const double *w0, *w1; const unsigned char *zero; };
 
@@ -379,7 +483,9 @@ void b2s_launch_lightsheet(const B2sLightsheet *L, const void *mid, unsigned sho
         const int n_win = g.gy.n * g.gx.n;
         const int side = (L->bg_x.hl + L->bg_x.hr + 1) / 2;
         dim3 grid(n_win, n_planes);
-        if (side * side <= 256 * 40) k_window_percentile<256, 40><<<grid, 256, 0, s>>>(g);
+        if (L->dtype != B2S_F32 && side * side <= 256 * 40) k_window_percentile_u16<256, 20><<<grid, 256, 0, s>>>(g);
+        else if (L->dtype != B2S_F32) k_window_percentile_u16<512, 24><<<grid, 512, 0, s>>>(g);
+        else if (side * side <= 256 * 40) k_window_percentile<256, 40><<<grid, 256, 0, s>>>(g);
         else k_window_percentile<512, 48><<<grid, 512, 0, s>>>(g);
     }
     FinalArgs f;

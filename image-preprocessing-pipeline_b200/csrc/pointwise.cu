@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) k_prologue(B2sPrologueArgs a)
             } else {
                 r = load_as_float(a.in, a.in_dtype, base + x);
                 if (flat) r = __fdiv_rn(r, __ldg(flat + x));
-                if (a.use_log1p) r = b2s_log1pf(r);
+                if (a.use_log1p) r = b2s_log1pf_dev(r);
             }
             s_row[x] = r;
         }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) k_epilogue_rows(B2sEpilogueArgs a)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float vf = v[k];
-            if (a.use_log1p) vf = b2s_expm1f(vf);
+            if (a.use_log1p) vf = b2s_expm1f_dev(vf);
             if (is_int) vf = fminf(fmaxf(rintf(vf), 0.f), hi_w);   // core.py:1153-1158
             u[k] = a.f32_exact ? epilogue_value_f32(a, vf, is_int, darkf) : epilogue_value(a, vf, is_int).u;
         }
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) k_epilogue(B2sEpilogueArgs a)
         // is_int_g: does the reference hold an integer array at this point?
         if (a.destripe) {
             vf = a.in.ptr[plane * a.in.plane_stride + (size_t)(y + a.base_pad) * a.in.pitch + (x + a.base_pad)];
-            if (a.use_log1p) vf = b2s_expm1f(vf);
+            if (a.use_log1p) vf = b2s_expm1f_dev(vf);
             is_int_g = a.int_path != 0;
             if (is_int_g) {  // rint (half to even) + clip to the integer dtype, core.py:1153-1158
                 vf = rintf(vf);
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256) k_block_reduce(const void *in, int dtype,
 __global__ void k_math(int which, const float *in, float *out, int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = which == 0 ? b2s_log1pf(in[i]) : b2s_expm1f(in[i]);
+    if (i < n) out[i] = which == 0 ? b2s_log1pf_dev(in[i]) : b2s_expm1f_dev(in[i]);
 }
 
 }  // namespace
@@ -449,7 +449,7 @@ void b2s_launch_epilogue(const B2sEpilogueArgs &a, int n_planes, cudaStream_t s)
 __global__ void k_log1p_lut(float *lut, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) lut[i] = b2s_log1pf((float)i);
+    if (i < n) lut[i] = b2s_log1pf_dev((float)i);
 }
 void b2s_launch_log1p_lut(float *lut, int n, cudaStream_t s) { k_log1p_lut<<<(n + 255) / 256, 256, 0, s>>>(lut, n); }
 

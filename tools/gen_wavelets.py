@@ -106,27 +106,12 @@ def symlet(N):
     return best[1]
 
 
-def coiflet(N):
-    """Coiflet of order N (6N taps): 2N vanishing wavelet moments, 2N-1 vanishing scaling moments.
-
-    Unknowns h[0..6N-1] with support offset -2N; solved with Newton iterations started from a
-    coarse solution (continuation on the previous order is not needed for N<=17 at 80 digits).
-    """
-    F = 6 * N
-    off = 2 * N  # index of the 'origin' tap
-    ks = [k - off for k in range(F)]
-
-    def eqs(*h):
-        out = []
-        # orthonormality (double-shift)
-        for m in range(F // 2):
-            s = mp.fsum(h[k] * h[k + 2 * m] for k in range(F - 2 * m))
-            out.append(s - (1 if m == 0 else 0))
-        # vanishing moments of the wavelet: sum (-1)^k k^p h_k = 0, p < 2N  (gives 2N eqs, some redundant)
-        # scaling-function moments: sum k^p h_k = 0 for 1 <= p < 2N
-        return out
-
-    raise NotImplementedError
+def coiflets():
+    """coifN tables solved by tools/gen_coiflets.py (slow: run separately), dec_lo as mpf."""
+    f = ROOT / "tools" / "coiflet_tables.json"
+    if not f.exists():
+        return {}
+    return {k: [mp.mpf(x) for x in v] for k, v in json.loads(f.read_text()).items()}
 
 
 def fmt(c):
@@ -135,9 +120,12 @@ def fmt(c):
 
 def main():
     tables = {}
-    for N in range(1, 21):
+    for N in range(1, 39):                      # pywt: db1 .. db38
         tables[f"db{N}"] = daubechies(N)
     tables["haar"] = tables["db1"]
+    for N in range(2, 21):                      # pywt: sym2 .. sym20
+        tables[f"sym{N}"] = symlet(N)
+    tables.update(coiflets())                   # pywt: coif1 .. coif17
     out_json = {k: [float(c) for c in v] for k, v in tables.items()}
     (ROOT / "oracle" / "wavelet_tables.json").write_text(json.dumps(out_json, indent=0))
     lines = ['"""Wavelet decomposition low-pass tables (== pywt.Wavelet(name).dec_lo), float64.',

@@ -1,0 +1,65 @@
+"""BASELINE.json configs[2..4] at full plane size on one GPU: parity against the oracle on one plane + device throughput."""
+import json
+import sys
+import time
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path[:0] = [str(ROOT), str(ROOT / "image-preprocessing-pipeline_b200")]
+import numpy as np
+import torch
+from oracle import pystripe_oracle as orc
+from pystripe import core
+from tools import synth
+
+H = W = 2048
+flat = core.normalize_flat(synth.flat_field((H, W)))
+CONFIGS = {
+    "config3_flat_gauss_ds2_8bit": dict(kw=dict(sigma=(256, 256), wavelet="db10", padding_mode="reflect", dark=100, gaussian_filter_2d=True,
+                                                down_sample=(2, 2), convert_to_8bit=True, bit_shift_to_right=8), flat=True),
+    "config4_lightsheet_destripe": dict(kw=dict(sigma=(256, 256), wavelet="db10", padding_mode="wrap", lightsheet=True), flat=False),
+    "config5_coif15_dual_sigma": dict(kw=dict(sigma=(128, 512), wavelet="coif15", padding_mode="reflect"), flat=False),
+    "step3_db9_sigma250_bidirectional": dict(kw=dict(sigma=(250, 250), wavelet="db9", padding_mode="reflect", bidirectional=True), flat=False),
+}
+if __name__ != "__main__":
+    which = []
+else:
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or list(CONFIGS)
+TIMING = "--timing" in sys.argv
+n = 16
+stack = synth.stack(4, (H, W))
+stack = np.concatenate([stack] * (n // 4))
+out = {}
+for name in which:
+    c = CONFIGS[name]
+    kw = dict(c["kw"])
+    fl = flat if c["flat"] else None
+    t0 = time.perf_counter()
+    got = core.process_img(stack[:1].copy(), flat=fl, **kw)[0]
+    t_first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ref = orc.process_img(stack[0].copy(), flat=None if fl is None else orc.normalize_flat(synth.flat_field((H, W))), **kw)
+    t_cpu = time.perf_counter() - t0
+    d = np.abs(got.astype(np.int64) - ref.astype(np.int64))
+    d_in = torch.from_numpy(stack).cuda()
+    res = core.process_img(d_in, flat=fl, **kw)          # warm-up (plan for batch)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        res = core.process_img(d_in, flat=fl, **kw)
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 3 / n * 1e3
+    if TIMING:
+        from pystripe import _native
+        ctx = _native.context(0)
+        ctx.timing_enable(True); ctx.timing_read(reset=True)
+        res = core.process_img(d_in, flat=fl, **kw)
+        tm = ctx.timing_read(reset=True)
+        ctx.timing_enable(False)
+        print("   ", {k: round(v[0] / n * 1e3, 1) for k, v in tm.items() if v[1]}, "us/plane")
+    out[name] = dict(max_abs_diff=int(d.max()), exact_fraction=float((d == 0).mean()), out_shape=list(got.shape), out_dtype=str(got.dtype),
+                     gpu_us_per_plane=round(us, 1), gpu_mpixel_per_s=round(H * W / us, 1), oracle_cpu_s_per_plane=round(t_cpu, 2),
+                     first_call_s=round(t_first, 2))
+    print(name, json.dumps(out[name]), flush=True)
+(ROOT / "gpurun_out").mkdir(exist_ok=True)
+(ROOT / "gpurun_out" / "configs_report.json").write_text(json.dumps(out, indent=1))
