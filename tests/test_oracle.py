@@ -24,6 +24,24 @@ REC_LO = {
     "db4": [0.23037781330885523, 0.7148465705525415, 0.6308807679295904, -0.02798376941698385, -0.18703481171888114,
             0.030841381835986965, 0.032883011666982945, -0.010597401784997278],
 }
+# published PyWavelets tables (dec_lo): sym4 from SURVEY.md section 8c, coif1-3 as printed by pywt.Wavelet(name).dec_lo
+DEC_LO_KAT = {
+    "sym7": [0.002681814568257878, -0.0010473848886829163, -0.01263630340325193, 0.03051551316596357, 0.0678926935013727,
+             -0.049552834937127255, 0.017441255086855827, 0.5361019170917628, 0.767764317003164, 0.2886296317515146,
+             -0.14004724044296152, -0.10780823770381774, 0.004010244871533663, 0.010268176708511255],
+    "sym4": [-0.07576571478927333, -0.02963552764599851, 0.49761866763201545, 0.8037387518059161, 0.29785779560527736,
+             -0.09921954357684722, -0.012603967262037833, 0.0322231006040427],
+    "coif1": [-0.01565572813546454, -0.0727326195128539, 0.38486484686420286, 0.8525720202122554, 0.3378976624578092,
+              -0.0727326195128539],
+    "coif2": [-0.0007205494453645122, -0.0018232088707029932, 0.0056114348193944995, 0.023680171946334084,
+              -0.0594344186464569, -0.0764885990783064, 0.41700518442169254, 0.8127236354455423, 0.3861100668211622,
+              -0.06737255472196302, -0.04146493678175915, 0.016387336463522112],
+    "coif3": [-3.459977283621256e-05, -7.098330313814125e-05, 0.0004662169601128863, 0.0011175187708906016,
+              -0.0025745176887502236, -0.00900797613666158, 0.015880544863615904, 0.03455502757306163,
+              -0.08230192710688598, -0.07179982161931202, 0.42848347637761874, 0.7937772226256206, 0.4051769024096169,
+              -0.06112339000267287, -0.0657719112818555, 0.023452696141836267, 0.007782596427325418,
+              -0.003793512864491014],
+}
 DB10_DEC_LO = [-1.3264202894521245e-5, 9.3588670320069591e-5, -1.1646685512928545e-4, -6.8585669495971163e-4,
                1.9924052951850561e-3, 1.3953517470529012e-3, -1.0733175483330575e-2, 3.6065535669561697e-3,
                3.3212674059341002e-2, -2.9457536821875813e-2, -7.1394147166397087e-2, 9.3057364603572351e-2,
@@ -38,15 +56,35 @@ def test_wavelet_known_answers(name):
     assert np.allclose(w.dec_lo, REC_LO[name][::-1], atol=5e-12, rtol=0)
 
 
+@pytest.mark.parametrize("name", sorted(DEC_LO_KAT))
+def test_sym_coif_known_answers(name):
+    assert np.allclose(pw.Wavelet(name).dec_lo, DEC_LO_KAT[name], atol=1e-11, rtol=0)
+    assert np.array_equal(pw.Wavelet("sym2").dec_lo, pw.Wavelet("db2").dec_lo)
+    assert np.array_equal(pw.Wavelet("sym3").dec_lo, pw.Wavelet("db3").dec_lo)
+
+
 def test_db10_table():
     assert np.allclose(pw.Wavelet("db10").dec_lo, DB10_DEC_LO, atol=1e-15, rtol=1e-13)
 
 
-@pytest.mark.parametrize("name", ["db1", "db2", "db5", "db9", "db10", "db16", "db20"])
+@pytest.mark.parametrize("name", ["db1", "db2", "db5", "db9", "db10", "db16", "db20", "db38", "sym5", "sym8", "sym13", "sym20",
+                                  "coif1", "coif5", "coif8", "coif12", "coif15", "coif17"])
 def test_wavelet_orthonormal_and_moments(name):
     w = pw.Wavelet(name)
     h = w.dec_lo
     F = h.size
+    if name.startswith("coif"):      # 6N taps: 2N vanishing wavelet moments, scaling moments 1..2N-1 vanish about tap 2N
+        N = F // 6
+        assert abs(h.sum() - np.sqrt(2)) < 1e-12
+        for m in range(F // 2):
+            assert abs(float(np.dot(h[: F - 2 * m], h[2 * m:])) - (1.0 if m == 0 else 0.0)) < 1e-12
+        kc = (np.arange(F) - 2 * N) / (2.0 * N)
+        r = w.rec_lo
+        for p in range(2 * N):
+            assert abs(np.dot(((-1.0) ** np.arange(F)) * kc ** p, r)) < 1e-9 * 2.0 ** p, (name, p)
+        for p in range(1, 2 * N):
+            assert abs(np.dot(kc ** p, r)) < 1e-9 * 2.0 ** p, (name, p)
+        return
     assert abs(h.sum() - np.sqrt(2)) < 1e-13
     for m in range(F // 2):
         s = float(np.dot(h[: F - 2 * m], h[2 * m:]))

@@ -88,22 +88,56 @@ def _phase_nonlinearity(h):
     return float(np.sum(res ** 2))
 
 
+# published PyWavelets dec_lo tables used to pin the root subset and the orientation of the low orders
+SYM_KAT = {
+    2: [-0.12940952255092145, 0.22414386804185735, 0.836516303737469, 0.48296291314469025],
+    3: [0.035226291882100656, -0.08544127388224149, -0.13501102001039084, 0.4598775021193313, 0.8068915093133388,
+        0.3326705529509569],
+    4: [-0.07576571478927333, -0.02963552764599851, 0.49761866763201545, 0.8037387518059161, 0.29785779560527736,
+        -0.09921954357684722, -0.012603967262037833, 0.0322231006040427],
+    5: [0.027333068345077982, 0.029519490925774643, -0.039134249302383094, 0.1993975339773936, 0.7234076904024206,
+        0.6339789634582119, 0.01660210576452232, -0.17532808990845047, -0.021101834024758855, 0.019538882735286728],
+    6: [0.015404109327027373, 0.0034907120842174702, -0.11799011114819057, -0.048311742585633, 0.4910559419267466,
+        0.787641141030194, 0.3379294217276218, -0.07263752278646252, -0.021060292512300564, 0.04472490177066578,
+        0.0017677118642428036, -0.007800708325034148],
+    7: [0.002681814568257878, -0.0010473848886829163, -0.01263630340325193, 0.03051551316596357, 0.0678926935013727,
+        -0.049552834937127255, 0.017441255086855827, 0.5361019170917628, 0.767764317003164, 0.2886296317515146,
+        -0.14004724044296152, -0.10780823770381774, 0.004010244871533663, 0.010268176708511255],
+    8: [-0.0033824159510061256, -0.0005421323317911481, 0.03169508781149298, 0.007607487324917605, -0.1432942383508097,
+        -0.061273359067658524, 0.4813596512583722, 0.7771857517005235, 0.3644418948353314, -0.05194583810770904,
+        -0.027219029917056003, 0.049137179673607506, 0.003808752013890615, -0.01495225833704823,
+        -0.0003029205147213668, 0.0018899503327594609],
+}
+
+
 def symlet(N):
-    """least-asymmetric Daubechies filter: enumerate inside/outside choices per conjugate group."""
+    """Symlet: one inside/outside choice per conjugate root group of the Daubechies half-band polynomial.
+    N <= 8: the subset and orientation that reproduce the published PyWavelets table (SYM_KAT; sym7 is NOT the subset a
+    phase-linearity score picks).  N >= 9: least phase non-linearity, orientation with the centre of mass below the
+    middle tap as in sym4/6/8 — agreement with PyWavelets UNVERIFIED offline."""
     pairs = _halfband_roots(N)
     groups = _group_conjugates(pairs)
-    best = None
+    cands = []
     for mask in range(1 << len(groups)):
         roots = []
         for g, grp in enumerate(groups):
             pick = (mask >> g) & 1
             roots.extend(p[pick] for p in grp)
-        h = _poly_from_roots(N, roots)
-        score = _phase_nonlinearity(h)
-        # canonical orientation tie-break between a filter and its mirror: handled after selection
-        if best is None or score < best[0] - 1e-12:
-            best = (score, h)
-    return best[1]
+        cands.append(_poly_from_roots(N, roots))
+    if N in SYM_KAT:
+        ref = [mp.mpf(v) for v in SYM_KAT[N]]
+        best = None
+        for h in cands:
+            for hh in (h, h[::-1]):
+                d = max(abs(a - b) for a, b in zip(hh, ref))
+                if best is None or d < best[0]:
+                    best = (d, hh)
+        assert best[0] < mp.mpf(10) ** (-9), (N, best[0])
+        return best[1]
+    h = min(cands, key=_phase_nonlinearity)
+    F = len(h)
+    com = mp.fsum(k * h[k] * h[k] for k in range(F)) / mp.fsum(x * x for x in h)
+    return h if com < mp.mpf(F - 1) / 2 else h[::-1]
 
 
 def coiflets():
