@@ -253,7 +253,6 @@ struct b2s_plan {
         void *mid = nullptr;                       // lightsheet: post-dark image
         unsigned short *ls_grid = nullptr, *bg_grid = nullptr;
         unsigned *mm = nullptr;
-        int *flags = nullptr;
         void *h_in = nullptr, *h_out = nullptr;    // pinned staging
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
@@ -456,7 +455,6 @@ int alloc_slot(b2s_plan *pl, int si)
         if ((rc = dev_alloc(pl, &s.pre_a, in_elems * 4 * B))) return rc;
         if ((rc = dev_alloc(pl, &s.pre_b, in_elems * 4 * B))) return rc;
         if ((rc = dev_alloc(pl, (void **)&s.mm, sizeof(unsigned) * 2 * B))) return rc;
-        if ((rc = dev_alloc(pl, (void **)&s.flags, sizeof(int) * B))) return rc;
     }
     if (pl->ls) {
         if ((rc = dev_alloc(pl, &s.mid, work_elems * 4 * B))) return rc;
@@ -480,9 +478,16 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
     // ---- process_img pre-ops (core.py:1232-1300)
     const void *cur = d_in;
     int cur_dt = p.in_dtype;
+    // uniform-plane check (core.py:1232): min / max keys of the raw input.  When the prologue reads the raw input itself
+    // (no pre-op in between) it accumulates them on the way; otherwise one vectorised pass does.
+    const bool fuse_minmax = p.process_img && g.n_passes > 0 && !(p.gaussian && !p.reference_quirks) &&
+                             g.work_rows == g.in_rows && g.work_cols == g.in_cols && (!(p.process_img && p.has_flat) || g.fuse_flat);
     if (p.process_img) {
-        ClassTimer t(ctx, st, B2S_K_PRE, 3);
-        b2s_launch_uniform(d_in, p.in_dtype, (size_t)g.in_rows * g.in_cols, nb, s.mm, s.flags, st);
+        CU(ctx, cudaMemsetAsync(s.mm, 0xff, sizeof(unsigned) * 2 * nb, st));
+        if (!fuse_minmax) {
+            ClassTimer t(ctx, st, B2S_K_PRE, 1);
+            b2s_launch_minmax(d_in, p.in_dtype, (size_t)g.in_rows * g.in_cols, nb, s.mm, st);
+        }
     }
     const bool flat = p.process_img && p.has_flat;
     if (flat && !pl->d_flat) return fail(ctx, B2S_ERR_INVALID, "has_flat is set but b2s_plan_set_flat was not called");
@@ -527,6 +532,7 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             a.row_targets = pl->d_row_targets;
             a.colmap = pl->d_colmap;
             a.lut = (cur_dt != B2S_F32 && !a.flat && p.log1p) ? pl->d_lut : nullptr;
+            a.minmax = fuse_minmax ? s.mm : nullptr;
             b2s_launch_prologue(a, nb, st);
         }
         if (p.debug_stop_after == B2S_STAGE_PROLOGUE) return B2S_OK;
@@ -590,7 +596,7 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
         e.out_dtype = g.out_dtype;
         e.flip = p.process_img ? p.flip_upside_down : 0;
         e.rot = p.process_img ? p.rotate / 90 : 0;
-        e.uniform_flags = p.process_img ? s.flags : nullptr;
+        e.uniform_mm = p.process_img ? s.mm : nullptr;
         e.out = d_out;
         e.out_rows = g.out_rows;
         e.out_cols = g.out_cols;
@@ -602,7 +608,7 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             const bool mid_int = g.work_dtype != B2S_F32;
             m.final_mode = mid_int ? 0 : 3;
             m.out_dtype = mid_int ? g.work_dtype : B2S_F32;
-            m.flip = 0; m.rot = 0; m.uniform_flags = nullptr;
+            m.flip = 0; m.rot = 0; m.uniform_mm = nullptr;
             m.out = s.mid; m.out_rows = g.work_rows; m.out_cols = g.work_cols;
             b2s_launch_epilogue(m, nb, st);
             // stage 2: percentile grids, zoom, subtraction, final conversion

@@ -38,6 +38,7 @@ struct B2sPrologueArgs {
     const int *row_targets;// padded row indices
     const int *colmap;     // [out.pitch] source column of each padded column, -1 => 0
     const float *lut;      // optional: log1p of every integer pixel value (no flat, integer input)
+    unsigned *minmax;      // optional: per-plane {min key, ~max key} of the raw input, accumulated here (uniform check fused)
 };
 void b2s_launch_prologue(const B2sPrologueArgs &a, int n_planes, cudaStream_t s);
 
@@ -58,15 +59,15 @@ struct B2sEpilogueArgs {
     int out_dtype;
     int flip, rot;         // rot in {0,1,2,3} quarter turns (numpy.rot90 k)
     int f32_exact;         // every value of the final conversion is exact in float32 (no dark, or integral dark on integers)
-    const int *uniform_flags; // optional per-plane flag: 1 => write zeros (process_img uniform shortcut)
+    const unsigned *uniform_mm; // optional per-plane {min key, ~max key}: equal => all pixels equal => write zeros (core.py:1232)
     void *out;
     int out_rows, out_cols;
 };
 void b2s_launch_epilogue(const B2sEpilogueArgs &a, int n_planes, cudaStream_t s);
 
 // per-plane "all pixels equal" flags (process_img core.py:1232)
-void b2s_launch_uniform(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned *minmax_scratch,
-                        int *flags, cudaStream_t s);
+// mm[2p] = min key, mm[2p+1] = ~max key (both initialised to 0xffffffff by a memset); standalone pass over the input
+void b2s_launch_minmax(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned *mm, cudaStream_t s);
 
 // pre-processing ahead of the destripe: flat division, 5x5 Gaussian, block reduce.  in/out dtype per stage.
 void b2s_launch_flat_divide(const void *in, int in_dtype, const float *flat, float *out, size_t plane_elems,

@@ -316,7 +316,7 @@ struct FinalArgs {
     double weight;
     int weight_is_int;    // isinstance(w, float) and integral handling: see below
     int final_mode, shift, out_dtype, flip, rot;
-    const int *uniform_flags;
+    const unsigned *uniform_mm;
     void *out;
     int out_rows, out_cols;
 };
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256) k_lightsheet_final(const FinalArgs a)
     if (j >= a.out_cols) return;
     const size_t plane = blockIdx.z;
     const size_t oidx = plane * (size_t)a.out_rows * a.out_cols + (size_t)i * a.out_cols + j;
-    const bool zero_plane = a.uniform_flags && a.uniform_flags[plane];
+    const bool zero_plane = a.uniform_mm && a.uniform_mm[2 * plane] == ~a.uniform_mm[2 * plane + 1];
     double v = 0.0;
     if (!zero_plane) {
         const int R = a.rows, C = a.cols;
@@ -498,6 +498,6 @@ void b2s_launch_lightsheet(const B2sLightsheet *L, const void *mid, unsigned sho
     f.ls_y = za[0]; f.ls_x = za[1]; f.bg_y = za[2]; f.bg_x = za[3];
     f.weight = L->weight; f.weight_is_int = L->weight_is_int;
     f.final_mode = e.final_mode; f.shift = e.shift; f.out_dtype = e.out_dtype; f.flip = e.flip; f.rot = e.rot;
-    f.uniform_flags = e.uniform_flags; f.out = e.out; f.out_rows = e.out_rows; f.out_cols = e.out_cols;
+    f.uniform_mm = e.uniform_mm; f.out = e.out; f.out_rows = e.out_rows; f.out_cols = e.out_cols;
     k_lightsheet_final<<<dim3((e.out_cols + 255) / 256, e.out_rows, n_planes), 256, 0, s>>>(f);
 }

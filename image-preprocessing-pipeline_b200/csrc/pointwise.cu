@@ -39,6 +39,13 @@ __device__ __forceinline__ int pad_index(int i, int n, int mode)
     }
 }
 
+// order-preserving unsigned key of a float (uniform check on float32 input)
+__device__ __forceinline__ unsigned f2key(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 __device__ __forceinline__ float load_as_float(const void *p, int dtype, size_t idx)
 {
     if (dtype == B2S_U16) return (float)__ldg(reinterpret_cast<const unsigned short *>(p) + idx);
@@ -52,9 +59,11 @@ __device__ __forceinline__ float load_as_float(const void *p, int dtype, size_t 
 __global__ void __launch_bounds__(256) k_prologue(B2sPrologueArgs a)
 {
     extern __shared__ __align__(16) float s_row[];
+    __shared__ unsigned s_mm[16];
     const int grp = blockIdx.x;
     const size_t plane = blockIdx.y;
     const int sy = a.row_src[grp];
+    unsigned klo = 0xffffffffu, khi = 0u;
     if (sy >= 0) {
         const size_t base = plane * (size_t)a.src_rows * a.src_cols + (size_t)sy * a.src_cols;
         const float *flat = a.flat ? a.flat + (size_t)sy * a.src_cols : nullptr;
@@ -65,15 +74,29 @@ __global__ void __launch_bounds__(256) k_prologue(B2sPrologueArgs a)
                 const unsigned v = a.in_dtype == B2S_U16 ? __ldg(reinterpret_cast<const unsigned short *>(a.in) + base + x)
                                                          : __ldg(reinterpret_cast<const unsigned char *>(a.in) + base + x);
                 r = __ldg(a.lut + v);
+                klo = min(klo, v); khi = max(khi, v);
             } else {
                 r = load_as_float(a.in, a.in_dtype, base + x);
+                if (a.minmax) { const unsigned key = a.in_dtype == B2S_F32 ? f2key(r) : (unsigned)r; klo = min(klo, key); khi = max(khi, key); }
                 if (flat) r = __fdiv_rn(r, __ldg(flat + x));
                 if (a.use_log1p) r = b2s_log1pf_dev(r);
             }
             s_row[x] = r;
         }
+        if (a.minmax) {   // every source row is read by exactly one CTA: the uniform check costs no extra pass
+            klo = __reduce_min_sync(0xffffffffu, klo);
+            khi = __reduce_max_sync(0xffffffffu, khi);
+            if ((threadIdx.x & 31) == 0) { s_mm[2 * (threadIdx.x >> 5)] = klo; s_mm[2 * (threadIdx.x >> 5) + 1] = khi; }
+        }
     }
     __syncthreads();
+    if (a.minmax && sy >= 0 && threadIdx.x == 0) {   // one atomic pair per CTA
+        unsigned lo = s_mm[0], hi = s_mm[1];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { lo = min(lo, s_mm[2 * w]); hi = max(hi, s_mm[2 * w + 1]); }
+        atomicMin(a.minmax + 2 * plane, lo);
+        atomicMin(a.minmax + 2 * plane + 1, ~hi);
+    }
     const int q4 = a.out.pitch >> 2;
     const int4 *cm = reinterpret_cast<const int4 *>(a.colmap);
     for (int t = a.row_start[grp]; t < a.row_start[grp + 1]; ++t) {
@@ -153,7 +176,7 @@ __global__ void __launch_bounds__(256) k_epilogue_rows(B2sEpilogueArgs a)
     const size_t oidx = plane * (size_t)a.out_rows * a.out_cols + (size_t)i * a.out_cols + x4;
     const int nvalid = min(4, a.out_cols - x4);
     unsigned u[4] = {0u, 0u, 0u, 0u};
-    const bool zero_plane = a.uniform_flags && a.uniform_flags[plane];
+    const bool zero_plane = a.uniform_mm && a.uniform_mm[2 * plane] == ~a.uniform_mm[2 * plane + 1];
     if (!zero_plane) {
         const int y = a.flip ? a.rows - 1 - i : i;
         const float *src = a.in.ptr + plane * a.in.plane_stride + (size_t)(y + a.base_pad) * a.in.pitch + (x4 + a.base_pad);
@@ -197,7 +220,7 @@ __global__ void __launch_bounds__(256) k_epilogue(B2sEpilogueArgs a)
 
     float vf = 0.f;
     bool is_int_g = false;
-    const bool zero_plane = a.uniform_flags && a.uniform_flags[plane];
+    const bool zero_plane = a.uniform_mm && a.uniform_mm[2 * plane] == ~a.uniform_mm[2 * plane + 1];
     if (!zero_plane) {
         // output (i, j) -> work-image (y, x): undo rot90 then flipud
         const int R = a.rows, C = a.cols;
@@ -232,18 +255,7 @@ __global__ void __launch_bounds__(256) k_epilogue(B2sEpilogueArgs a)
     else reinterpret_cast<unsigned short *>(a.out)[oidx] = (unsigned short)u;
 }
 
-// ---- uniform flag: min/max per plane via shared reduction + global atomics on an ordered-uint key
-__device__ __forceinline__ unsigned f2key(float f)
-{
-    const unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-__global__ void k_minmax_init(unsigned *mm, int n_planes)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_planes) { mm[2 * i] = 0xffffffffu; mm[2 * i + 1] = 0u; }
-}
+// ---- uniform check: min / max per plane via warp reduction + global atomics on an ordered-uint key
 
 __global__ void __launch_bounds__(256) k_minmax(const void *in, int dtype, size_t plane_elems, unsigned *mm)
 {
@@ -294,14 +306,8 @@ __global__ void __launch_bounds__(256) k_minmax(const void *in, int dtype, size_
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMin(mm + 2 * plane, lo);
-        atomicMax(mm + 2 * plane + 1, hi);
+        atomicMin(mm + 2 * plane + 1, ~hi);
     }
-}
-
-__global__ void k_uniform_flags(const unsigned *mm, int *flags, int n_planes)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_planes) flags[i] = mm[2 * i] == mm[2 * i + 1];
 }
 
 // ---- pre-ops
@@ -453,17 +459,14 @@ __global__ void k_log1p_lut(float *lut, int n)
 }
 void b2s_launch_log1p_lut(float *lut, int n, cudaStream_t s) { k_log1p_lut<<<(n + 255) / 256, 256, 0, s>>>(lut, n); }
 
-void b2s_launch_uniform(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned *mm, int *flags,
-                        cudaStream_t s)
+void b2s_launch_minmax(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned *mm, cudaStream_t s)
 {
-    k_minmax_init<<<(n_planes + 127) / 128, 128, 0, s>>>(mm, n_planes);
-    // 16 bytes per thread and trip, four trips in flight; at most ~4 CTAs per SM over the batch
+    // 16 bytes per thread and trip, four trips in flight
     const size_t bytes = plane_elems * (dtype == B2S_F32 ? 4 : (dtype == B2S_U16 ? 2 : 1));
     int bx = (int)((bytes + 256 * 64 - 1) / (256 * 64));
     if (bx > 512) bx = 512;
     if (bx < 1) bx = 1;
     k_minmax<<<dim3(bx, n_planes), 256, 0, s>>>(in, dtype, plane_elems, mm);
-    k_uniform_flags<<<(n_planes + 127) / 128, 128, 0, s>>>(mm, flags, n_planes);
 }
 
 void b2s_launch_flat_divide(const void *in, int in_dtype, const float *flat, float *out, size_t plane_elems,
