@@ -177,6 +177,21 @@ B2S_HD float b2s_expm1f(float x)
 // back to the general routine.  (One range test replaces the chain of special-case branches the general routines walk
 // for every pixel; tests/test_gpu_parity.py::test_device_math_is_bit_exact covers both paths against the host libm.)
 #if defined(__CUDACC__)
+// Correctly rounded a / b without the IEEE-division subroutine, for finite operands whose quotient is zero or a normal
+// number far from overflow (true for every division in the two hot paths: |quotient| in [2^-60, 2^20] or exactly 0):
+// reciprocal estimate, one Newton step, quotient, two exact-residual corrections (Markstein).  The residual a - b*q is
+// exactly representable once q is within an ulp, so the last fma rounds the true quotient once.
+__device__ __forceinline__ float b2s_div_hot(float a, float b)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    r = fmaf(fmaf(-b, r, 1.0f), r, r);
+    float q = __fmul_rn(a, r);
+    q = fmaf(fmaf(-b, q, a), r, q);
+    q = fmaf(fmaf(-b, q, a), r, q);
+    return q;
+}
+
 __device__ __forceinline__ float b2s_expm1f_dev(float x)
 {
     if (!(x >= 1.1f && x < 38.0f)) return b2s_expm1f(x);      // here 2 <= k <= 55
@@ -192,7 +207,7 @@ __device__ __forceinline__ float b2s_expm1f_dev(float x)
     const float hxs = xr * hfx;
     const float r1 = 1.0f + hxs * (Q1 + hxs * (Q2 + hxs * (Q3 + hxs * (Q4 + hxs * Q5))));
     const float tt = 3.0f - r1 * hfx;
-    float e = hxs * ((r1 - tt) / (6.0f - xr * tt));
+    float e = hxs * b2s_div_hot(r1 - tt, 6.0f - xr * tt);
     e = (xr * (e - c) - c);
     e -= hxs;
     float y;
@@ -216,7 +231,7 @@ __device__ __forceinline__ float b2s_log1pf_dev(float x)
     int32_t hu = b2s_f2i(u);
     int32_t k = (hu >> 23) - 127;
     float c = (k > 0) ? 1.0f - (u - x) : x - (u - 1.0f);
-    c /= u;
+    c = b2s_div_hot(c, u);
     hu &= 0x007fffff;
     if (hu < 0x3504f7) {
         u = b2s_i2f(hu | 0x3f800000);
@@ -228,7 +243,7 @@ __device__ __forceinline__ float b2s_log1pf_dev(float x)
     if (hu == 0) return b2s_log1pf(x);                          // |f| < 2^-20: rare, general routine
     const float f = u - 1.0f;
     const float hfsq = 0.5f * f * f;
-    const float s = f / (2.0f + f);
+    const float s = b2s_div_hot(f, 2.0f + f);
     const float z = s * s;
     const float R = z * (Lp1 + z * (Lp2 + z * (Lp3 + z * (Lp4 + z * (Lp5 + z * (Lp6 + z * Lp7))))));
     const float kf = (float)k;

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) k_prologue(B2sPrologueArgs a)
             } else {
                 r = load_as_float(a.in, a.in_dtype, base + x);
                 if (a.minmax) { const unsigned key = a.in_dtype == B2S_F32 ? f2key(r) : (unsigned)r; klo = min(klo, key); khi = max(khi, key); }
-                if (flat) r = __fdiv_rn(r, __ldg(flat + x));
+                if (flat) { const float fl = __ldg(flat + x); r = (fl > 1.0e-18f && fl < 1.0e18f) ? b2s_div_hot(r, fl) : __fdiv_rn(r, fl); }
                 if (a.use_log1p) r = b2s_log1pf_dev(r);
             }
             s_row[x] = r;
