@@ -315,8 +315,16 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """keep fd 1 for the single JSON line: libraries (NCCL prints its version banner on stdout) write to stderr instead."""
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 def main():
     a = parse()
+    _claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

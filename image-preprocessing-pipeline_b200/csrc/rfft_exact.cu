@@ -183,8 +183,10 @@ __device__ void radf5(const Ctx &c, int ido, int l1, const float *cc, float *ch,
 // product that ptxas cannot re-contract with the following add; -0.0 arrives as a kernel argument), sums as FADD2 in
 // the reference's association order.
 constexpr int LB = 8;
+constexpr int kRow = 68;   // float2 entries per table row (radix < 135 => at most 66 columns); compile-time so that the LB rows
+                          // a thread reads sit at immediate offsets from one running pointer
 __device__ __forceinline__ float2 mul2x(float2 t, float2 v, float2 nz) { return __ffma2_rn(t, v, nz); }
-__device__ __forceinline__ void generic_block(const Ctx &c, const float *src, float *dst, const float2 *sgt, int JP, int ip,
+__device__ __forceinline__ void generic_block(const Ctx &c, const float *src, float *dst, const float2 *sgt, int ip,
                                               int ipph, int idl1, int lb, int ik, float2 nz)
 {
     const int l0 = 1 + LB * lb, nl = min(LB, ipph - l0);
@@ -192,50 +194,53 @@ __device__ __forceinline__ void generic_block(const Ctx &c, const float *src, fl
     const float *pf = src + ik * c.GP + c.r;
     const float *pb = pf + (ip - 1) * st;
     float2 A[LB];
-    const float4 *trow[LB];
-#pragma unroll
-    for (int q = 0; q < LB; ++q) trow[q] = reinterpret_cast<const float4 *>(sgt + (min(l0 + q, ipph - 1) - 1) * JP);
+    // rows l0 .. l0+LB-1 of the table (rows past ipph-1 are zero padding: their results are not stored)
+    const float4 *tb = reinterpret_cast<const float4 *>(sgt + (l0 - 1) * kRow);
+    constexpr int RQ = kRow / 2;   // float4 per row
     {
         const float2 x0 = make_float2(pf[0], 0.f);
         const float2 v1 = make_float2(pf[st], pb[0]), v2 = make_float2(pf[2 * st], pb[-st]);
 #pragma unroll
         for (int q = 0; q < LB; ++q) {
-            const float4 t = trow[q][0];
+            const float4 t = tb[q * RQ];
             A[q] = __fadd2_rn(__fadd2_rn(x0, mul2x(make_float2(t.x, t.y), v1, nz)), mul2x(make_float2(t.z, t.w), v2, nz));
         }
     }
     pf += 3 * st;
     pb -= 2 * st;
-    int j = 3, h = 1;   // h: float4 index of column j-1 in the table row
-    for (; j + 3 < ipph; j += 4, h += 2) {
+    tb += 1;
+    int j = 3;
+    for (; j + 3 < ipph; j += 4) {
         const float2 v0 = make_float2(pf[0], pb[0]), v1 = make_float2(pf[st], pb[-st]);
         const float2 v2 = make_float2(pf[2 * st], pb[-2 * st]), v3 = make_float2(pf[3 * st], pb[-3 * st]);
         pf += 4 * st;
         pb -= 4 * st;
 #pragma unroll
         for (int q = 0; q < LB; ++q) {
-            const float4 t = trow[q][h], u = trow[q][h + 1];
+            const float4 t = tb[q * RQ], u = tb[q * RQ + 1];
             float2 sacc = __fadd2_rn(mul2x(make_float2(t.x, t.y), v0, nz), mul2x(make_float2(t.z, t.w), v1, nz));
             sacc = __fadd2_rn(sacc, mul2x(make_float2(u.x, u.y), v2, nz));
             sacc = __fadd2_rn(sacc, mul2x(make_float2(u.z, u.w), v3, nz));
             A[q] = __fadd2_rn(A[q], sacc);
         }
+        tb += 2;
     }
-    for (; j + 1 < ipph; j += 2, h += 1) {
+    for (; j + 1 < ipph; j += 2) {
         const float2 v0 = make_float2(pf[0], pb[0]), v1 = make_float2(pf[st], pb[-st]);
         pf += 2 * st;
         pb -= 2 * st;
 #pragma unroll
         for (int q = 0; q < LB; ++q) {
-            const float4 t = trow[q][h];
+            const float4 t = tb[q * RQ];
             A[q] = __fadd2_rn(A[q], __fadd2_rn(mul2x(make_float2(t.x, t.y), v0, nz), mul2x(make_float2(t.z, t.w), v1, nz)));
         }
+        tb += 1;
     }
     if (j < ipph) {
         const float2 v0 = make_float2(pf[0], pb[0]);
 #pragma unroll
         for (int q = 0; q < LB; ++q) {
-            const float2 t = reinterpret_cast<const float2 *>(trow[q])[2 * h];
+            const float2 t = reinterpret_cast<const float2 *>(tb + q * RQ)[0];
             A[q] = __fadd2_rn(A[q], mul2x(t, v0, nz));
         }
     }
@@ -254,8 +259,9 @@ __device__ void radfg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
 {
     const int ido = P.ido, ip = P.ip, l1 = P.l1;
     const int cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
-    const int JP = (ipph - 1 + 3) & ~3, nlb = (ipph - 1 + LB - 1) / LB;
-    for (int i = threadIdx.x; i < (ipph - 1) * JP; i += kXT) sgt[i] = __ldg(gt + i);   // visible after the next barrier
+    const int nlb = (ipph - 1 + LB - 1) / LB;
+    for (int i = threadIdx.x; i < nlb * LB * (kRow / 2); i += kXT)   // visible after the next barrier
+        reinterpret_cast<float4 *>(sgt)[i] = __ldg(reinterpret_cast<const float4 *>(gt) + i);
 #define CC(a, b, k_) cc[IDX((a) + ido * ((b) + cdim * (k_)))]
 #define CH(a, b, k_) ch[IDX((a) + ido * ((b) + l1 * (k_)))]
 #define C1(a, b, k_) cc[IDX((a) + ido * ((b) + l1 * (k_)))]
@@ -287,7 +293,7 @@ __device__ void radfg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
             float s = C2(ik, 0);
             for (int j = 1; j < ipph; ++j) s += C2(ik, j);
             CH2(ik, 0) = s;
-        } else generic_block(c, cc, ch, sgt, JP, ip, ipph, idl1, lb, ik, nz);
+        } else generic_block(c, cc, ch, sgt, ip, ipph, idl1, lb, ik, nz);
     }
     __syncthreads();
     FOR_ITEMS(it, l1 * ido) {
@@ -467,8 +473,9 @@ __device__ void radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
 {
     const int ido = P.ido, ip = P.ip, l1 = P.l1;
     const int cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
-    const int JP = (ipph - 1 + 3) & ~3, nlb = (ipph - 1 + LB - 1) / LB;
-    for (int i = threadIdx.x; i < (ipph - 1) * JP; i += kXT) sgt[i] = __ldg(gt + i);   // visible after the next barrier
+    const int nlb = (ipph - 1 + LB - 1) / LB;
+    for (int i = threadIdx.x; i < nlb * LB * (kRow / 2); i += kXT)   // visible after the next barrier
+        reinterpret_cast<float4 *>(sgt)[i] = __ldg(reinterpret_cast<const float4 *>(gt) + i);
 #define CC(a, b, k_) cc[IDX((a) + ido * ((b) + cdim * (k_)))]
 #define CH(a, b, k_) ch[IDX((a) + ido * ((b) + l1 * (k_)))]
     FOR_ITEMS(it, l1 * ido) {
@@ -501,7 +508,7 @@ __device__ void radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
             float s = CH2(ik, 0);
             for (int j = 1; j < ipph; ++j) s += CH2(ik, j);
             C2(ik, 0) = s;
-        } else generic_block(c, ch, cc, sgt, JP, ip, ipph, idl1, lb, ik, nz);
+        } else generic_block(c, ch, cc, sgt, ip, ipph, idl1, lb, ik, nz);
     }
     __syncthreads();
     FOR_ITEMS(ik, idl1) CH2(ik, 0) = C2(ik, 0);
@@ -1105,10 +1112,10 @@ B2sXfftPlan *b2s_xfft_create(int n)
                     twid.get((size_t)(i / 2) * (n / ip), &re, &im);
                     tws[i] = re; tws[i + 1] = im; tws[ic] = re; tws[ic + 1] = -im;
                 }
-                const int ipph = (ip + 1) / 2, JP = (ipph - 1 + 3) & ~3;
+                const int ipph = (ip + 1) / 2, JP = kRow, rows = (ipph - 1 + LB - 1) / LB * LB;   // zero rows pad the last block
                 while (tab.size() & 3) tab.push_back(0.f);
                 cs_off[k] = (int)tab.size();
-                tab.resize(tab.size() + 2 * (size_t)(ipph - 1) * JP, 0.f);
+                tab.resize(tab.size() + 2 * (size_t)rows * JP, 0.f);
                 for (int l = 1; l < ipph; ++l)
                     for (int j = 1; j < ipph; ++j) {
                         const int iang = (int)(((long long)l * j) % ip);
@@ -1135,7 +1142,7 @@ B2sXfftPlan *b2s_xfft_create(int n)
         const long long max_it = (long long)n * 2 + 64;     // every item loop of a pass runs over fewer than 2n items
         XPass p{ip <= 5 ? ip : (ip < 135 ? 6 : 7), ip, l1, ido, tw_off[k], cs_off[k],
                 magic(l1, max_it), magic(ni, max_it), magic(l1 * ni, max_it), magic(ido, max_it), magic(ido * l1, max_it)};
-        if (p.kind == 6) a.gt_max = std::max(a.gt_max, (ipph - 1) * ((ipph - 1 + 3) & ~3));
+        if (p.kind == 6) a.gt_max = std::max(a.gt_max, (ipph - 1 + LB - 1) / LB * LB * kRow);
         return p;
     };
     {
