@@ -244,7 +244,7 @@ struct b2s_plan {
     B2sTaps taps;
     int B = 1;            // max batch
     // device workspace (one slot per in-flight batch)
-    static constexpr int kSlots = 3;
+    static constexpr int kSlots = 5;
     struct Slot {
         float *padded = nullptr;
         float *sub[B2S_MAX_LEVELS + 1][4] = {};
@@ -808,7 +808,7 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
         return B2S_OK;
     }
 
-    // host path: two slots, each with its own stream: H2D -> kernels -> D2H; the slots overlap each other
+    // host path: kSlots slots, each with its own stream: H2D -> kernels -> D2H; the slots overlap each other
     const bool in_pinned = in_is_device || is_pinned_host(in);
     const bool out_pinned = out_is_device || is_pinned_host(out);
     for (auto &s : pl->slot) {
@@ -827,14 +827,18 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
     };
     // batch sizes ramp up from 4 planes and down again at the end of the call: the first kernels start after a short
     // copy and the last device-to-host copy is short, so the pipeline fill / drain costs little
+    // the host path runs shorter batches than the workspace allows: finer pipelining of H2D / kernels / D2H across the
+    // slots hides more of the PCIe time (measured at 2048^2: 8 planes per batch, 21.5 Gpx/s end to end vs 17.7 with 32)
+    static const int host_cap = getenv("B2S_HOST_BATCH") ? atoi(getenv("B2S_HOST_BATCH")) : 8;
+    const int Bh = std::max(1, std::min(B, host_cap));
     int si = 0;
     int64_t z = 0;
-    int nb_next = B < 4 ? B : 4;
+    int nb_next = Bh < 4 ? Bh : 4;
     while (z < n_planes) {
         const int64_t left = n_planes - z;
         int nb = (int)std::min<int64_t>(nb_next, left);
         if (left > 4 && nb > left / 2) nb = (int)std::max<int64_t>(4, left / 2);   // ramp down: halve what is left
-        nb_next = std::min(B, nb_next * 2);
+        nb_next = std::min(Bh, nb_next * 2);
         b2s_plan::Slot &s = pl->slot[si];
         int rc = drain(si);
         if (rc) return rc;

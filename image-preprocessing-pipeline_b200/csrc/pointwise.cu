@@ -336,15 +336,21 @@ __global__ void __launch_bounds__(256) k_gauss5_u16(const uint16_t *in, uint16_t
     if (x >= cols) return;
     const size_t plane = (size_t)blockIdx.z * rows * cols;
     const unsigned kq[5] = {3571u, 16004u, 26386u, 16004u, 3571u};
+    const bool interior = x >= 2 && x + 2 < cols && y >= 2 && y + 2 < rows;   // no index reflection needed
+    int xs[5], ys[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+        xs[d] = interior ? x + d - 2 : reflect101(x + d - 2, cols);
+        ys[d] = interior ? y + d - 2 : reflect101(y + d - 2, rows);
+    }
     unsigned long long acc = 0ull;
 #pragma unroll
-    for (int dy = -2; dy <= 2; ++dy) {
-        const int yy = reflect101(y + dy, rows);
-        const uint16_t *row = in + plane + (size_t)yy * cols;
+    for (int dy = 0; dy < 5; ++dy) {
+        const uint16_t *row = in + plane + (size_t)ys[dy] * cols;
         unsigned h = 0u;
 #pragma unroll
-        for (int dx = -2; dx <= 2; ++dx) h += kq[dx + 2] * (unsigned)__ldg(row + reflect101(x + dx, cols));
-        acc += (unsigned long long)kq[dy + 2] * h;
+        for (int dx = 0; dx < 5; ++dx) h += kq[dx] * (unsigned)__ldg(row + xs[dx]);
+        acc += (unsigned long long)kq[dy] * h;
     }
     unsigned long long r = (acc + (1ull << 31)) >> 32;
     out[plane + (size_t)y * cols + x] = (uint16_t)(r > 65535ull ? 65535ull : r);
@@ -362,13 +368,17 @@ __global__ void __launch_bounds__(256) k_gauss5_f32(const float *in, float *out,
     if (x >= cols) return;
     const size_t plane = (size_t)blockIdx.z * rows * cols;
     const float k0 = 0.40261996f, k1 = 0.24420135f, k2 = 0.05448868f;
-    int xs[5];
+    const bool interior = x >= 2 && x + 2 < cols && y >= 2 && y + 2 < rows;   // no index reflection needed
+    int xs[5], ys[5];
 #pragma unroll
-    for (int d = 0; d < 5; ++d) xs[d] = reflect101(x + d - 2, cols);
+    for (int d = 0; d < 5; ++d) {
+        xs[d] = interior ? x + d - 2 : reflect101(x + d - 2, cols);
+        ys[d] = interior ? y + d - 2 : reflect101(y + d - 2, rows);
+    }
     float h[5];
 #pragma unroll
     for (int dy = 0; dy < 5; ++dy) {
-        const float *row = in + plane + (size_t)reflect101(y + dy - 2, rows) * cols;
+        const float *row = in + plane + (size_t)ys[dy] * cols;
         float s = __fmul_rn(k0, __ldg(row + xs[2]));
         s = __fmaf_rn(k1, __fadd_rn(__ldg(row + xs[1]), __ldg(row + xs[3])), s);
         s = __fmaf_rn(k2, __fadd_rn(__ldg(row + xs[0]), __ldg(row + xs[4])), s);
