@@ -632,6 +632,9 @@ typedef Tile<32, 32, 256, 4> InvTile0;
 typedef Tile<32, 64, 256, 4, 8> FwdTile1;   // y-pass 40 warp items, x-pass 16
 typedef Tile<31, 64, 256, 8, 4> InvTile1;   // x-pass 20 warp items, y-pass 32
 typedef Tile<32, 64, 256, 8, 8> FwdTile2;
+// long filters (chunked taps): one CTA per SM fits, so it carries 16 warps to cover the FADD2 dependency chains
+typedef Tile<16, 64, 512, 4> FwdTileL;
+typedef Tile<32, 32, 512, 4> InvTileL;
 typedef Tile<31, 64, 256, 8, 8> InvTile2;
 
 int dev_knob(const char *name, int dflt)
@@ -675,6 +678,12 @@ void launch_fwd_j(const FwdTaps &ft, const FwdArgs &a, int n_planes, int exact, 
         else launch_fwd_t<FwdTile2, JJ, false, kFast>(ft, a, n_planes, sm_count, s);
         return;
     }
+    if (MULTI) {
+        constexpr bool M = MULTI;   // instantiate the wide tile for the chunked variants only
+        if (exact) launch_fwd_t<FwdTileL, J, M, kExact>(ft, a, n_planes, sm_count, s);
+        else launch_fwd_t<FwdTileL, J, M, kFast>(ft, a, n_planes, sm_count, s);
+        return;
+    }
     if (exact) launch_fwd_t<FwdTile0, J, MULTI, kExact>(ft, a, n_planes, sm_count, s);
     else launch_fwd_t<FwdTile0, J, MULTI, kFast>(ft, a, n_planes, sm_count, s);
 }
@@ -711,6 +720,12 @@ void launch_inv_j(const InvTaps &it, const InvArgs &a, int n_planes, int exact, 
         constexpr int JJ = (JH == 10 && !MULTI) ? JH : 1;
         if (exact) launch_inv_t<InvTile2, JJ, false, kExact>(it, a, n_planes, sm_count, s);
         else launch_inv_t<InvTile2, JJ, false, kFast>(it, a, n_planes, sm_count, s);
+        return;
+    }
+    if (MULTI) {
+        constexpr bool M = MULTI;
+        if (exact) launch_inv_t<InvTileL, JH, M, kExact>(it, a, n_planes, sm_count, s);
+        else launch_inv_t<InvTileL, JH, M, kFast>(it, a, n_planes, sm_count, s);
         return;
     }
     if (exact) launch_inv_t<InvTile0, JH, MULTI, kExact>(it, a, n_planes, sm_count, s);
