@@ -688,7 +688,7 @@ static void radbg(size_t ido, size_t ip, size_t l1, float *cc, float *ch, const 
 #undef WA
 
 /* ================================================================ cfftp<float> */
-typedef struct { size_t fct; cf *tw; } cfct;
+typedef struct { size_t fct; cf *tw, *tws; } cfct;
 typedef struct { size_t length, nfct; cfct fct[MAXFACT]; cf *mem; } cfftp_t;
 
 static int cfftp_init(cfftp_t *p, size_t length)
@@ -711,8 +711,9 @@ static int cfftp_init(cfftp_t *p, size_t length)
     size_t twsz = 0, l1 = 1;
     for (size_t k = 0; k < p->nfct; ++k) {
         size_t ip = p->fct[k].fct, ido = length / (l1 * ip);
-        if (ip > 11) return -1; /* passg: not needed (Bluestein lengths are 11-smooth) */
+        if (ip >= 110) return -1; /* complex Bluestein pass inside a multipass: not restated */
         twsz += (ip - 1) * (ido - 1);
+        if (ip > 11) twsz += ip;
         l1 *= ip;
     }
     p->mem = (cf *)calloc(twsz + 1, sizeof(cf));
@@ -725,6 +726,12 @@ static int cfftp_init(cfftp_t *p, size_t length)
         memofs += (ip - 1) * (ido - 1);
         for (size_t j = 1; j < ip; ++j)
             for (size_t i = 1; i < ido; ++i) p->fct[k].tw[(j - 1) * (ido - 1) + i - 1] = sc_get(&comp, j * l1 * i);
+        p->fct[k].tws = NULL;
+        if (ip > 11) {
+            p->fct[k].tws = p->mem + memofs;
+            memofs += ip;
+            for (size_t j = 0; j < ip; ++j) p->fct[k].tws[j] = sc_get(&comp, j * l1 * ido);
+        }
         l1 *= ip;
     }
     sc_free(&comp);
@@ -982,6 +989,85 @@ static void pass11(size_t ido, size_t l1, const cf *cc, cf *ch, const cf *wa, in
 #undef CCC
 }
 
+/* generic complex radix (cfftp::passg / ducc0 cfftpg); the result ends in cc */
+static void passg(size_t ido, size_t ip, size_t l1, cf *cc, cf *ch, const cf *wa, const cf *csarr, int fwd)
+{
+    const size_t cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
+#define GCH(a, b, c) ch[(a) + ido * ((b) + l1 * (c))]
+#define GCC(a, b, c) cc[(a) + ido * ((b) + cdim * (c))]
+#define GCX(a, b, c) cc[(a) + ido * ((b) + l1 * (c))]
+#define GCX2(a, b) cc[(a) + idl1 * (b)]
+#define GCH2(a, b) ch[(a) + idl1 * (b)]
+    cf *wal = (cf *)malloc(sizeof(cf) * ip);
+    wal[0].r = 1.f; wal[0].i = 0.f;
+    for (size_t i = 1; i < ip; ++i) { wal[i].r = csarr[i].r; wal[i].i = fwd ? -csarr[i].i : csarr[i].i; }
+    for (size_t k = 0; k < l1; ++k)
+        for (size_t i = 0; i < ido; ++i) GCH(i, k, 0) = GCC(i, 0, k);
+    for (size_t j = 1, jc = ip - 1; j < ipph; ++j, --jc)
+        for (size_t k = 0; k < l1; ++k)
+            for (size_t i = 0; i < ido; ++i) CPM(GCH(i, k, j), GCH(i, k, jc), GCC(i, j, k), GCC(i, jc, k))
+    for (size_t k = 0; k < l1; ++k)
+        for (size_t i = 0; i < ido; ++i) {
+            cf tmp = GCH(i, k, 0);
+            for (size_t j = 1; j < ipph; ++j) { tmp.r += GCH(i, k, j).r; tmp.i += GCH(i, k, j).i; }
+            GCX(i, k, 0) = tmp;
+        }
+    for (size_t l = 1, lc = ip - 1; l < ipph; ++l, --lc) {
+        for (size_t ik = 0; ik < idl1; ++ik) {
+            GCX2(ik, l).r = GCH2(ik, 0).r + wal[l].r * GCH2(ik, 1).r + wal[2 * l].r * GCH2(ik, 2).r;
+            GCX2(ik, l).i = GCH2(ik, 0).i + wal[l].r * GCH2(ik, 1).i + wal[2 * l].r * GCH2(ik, 2).i;
+            GCX2(ik, lc).r = -(wal[l].i * GCH2(ik, ip - 1).i + wal[2 * l].i * GCH2(ik, ip - 2).i);
+            GCX2(ik, lc).i = wal[l].i * GCH2(ik, ip - 1).r + wal[2 * l].i * GCH2(ik, ip - 2).r;
+        }
+        size_t iwal = 2 * l;
+        size_t j = 3, jc = ip - 3;
+        for (; j + 1 < ipph; j += 2, jc -= 2) {
+            iwal += l; if (iwal > ip) iwal -= ip;
+            cf xwal = wal[iwal];
+            iwal += l; if (iwal > ip) iwal -= ip;
+            cf xwal2 = wal[iwal];
+            for (size_t ik = 0; ik < idl1; ++ik) {
+                GCX2(ik, l).r += GCH2(ik, j).r * xwal.r + GCH2(ik, j + 1).r * xwal2.r;
+                GCX2(ik, l).i += GCH2(ik, j).i * xwal.r + GCH2(ik, j + 1).i * xwal2.r;
+                GCX2(ik, lc).r -= GCH2(ik, jc).i * xwal.i + GCH2(ik, jc - 1).i * xwal2.i;
+                GCX2(ik, lc).i += GCH2(ik, jc).r * xwal.i + GCH2(ik, jc - 1).r * xwal2.i;
+            }
+        }
+        for (; j < ipph; ++j, --jc) {
+            iwal += l; if (iwal > ip) iwal -= ip;
+            cf xwal = wal[iwal];
+            for (size_t ik = 0; ik < idl1; ++ik) {
+                GCX2(ik, l).r += GCH2(ik, j).r * xwal.r;
+                GCX2(ik, l).i += GCH2(ik, j).i * xwal.r;
+                GCX2(ik, lc).r -= GCH2(ik, jc).i * xwal.i;
+                GCX2(ik, lc).i += GCH2(ik, jc).r * xwal.i;
+            }
+        }
+    }
+    if (ido == 1) {
+        for (size_t j = 1, jc = ip - 1; j < ipph; ++j, --jc)
+            for (size_t ik = 0; ik < idl1; ++ik) {
+                cf t1 = GCX2(ik, j), t2 = GCX2(ik, jc);
+                CPM(GCX2(ik, j), GCX2(ik, jc), t1, t2)
+            }
+    } else {
+        for (size_t j = 1, jc = ip - 1; j < ipph; ++j, --jc)
+            for (size_t k = 0; k < l1; ++k) {
+                cf t1 = GCX(0, k, j), t2 = GCX(0, k, jc);
+                CPM(GCX(0, k, j), GCX(0, k, jc), t1, t2)
+                for (size_t i = 1; i < ido; ++i) {
+                    cf x1, x2;
+                    CPM(x1, x2, GCX(i, k, j), GCX(i, k, jc))
+                    size_t idij = (j - 1) * (ido - 1) + i - 1;
+                    GCX(i, k, j) = smul(x1, wa[idij], fwd);
+                    idij = (jc - 1) * (ido - 1) + i - 1;
+                    GCX(i, k, jc) = smul(x2, wa[idij], fwd);
+                }
+            }
+    }
+    free(wal);
+}
+
 static void cfftp_exec(const cfftp_t *p, cf *c, float fct, int fwd)
 {
     size_t length = p->length;
@@ -1000,11 +1086,12 @@ static void cfftp_exec(const cfftp_t *p, cf *c, float fct, int fwd)
         else if (ip == 5) pass5(ido, l1, p1, p2, p->fct[k1].tw, fwd);
         else if (ip == 7) pass7(ido, l1, p1, p2, p->fct[k1].tw, fwd);
         else if (ip == 11) pass11(ido, l1, p1, p2, p->fct[k1].tw, fwd);
+        else { passg(ido, ip, l1, p1, p2, p->fct[k1].tw, p->fct[k1].tws, fwd); t = p1; p1 = p2; p2 = t; }
         t = p1; p1 = p2; p2 = t;
         l1 = l2;
     }
     if (p1 != c) {
-        if (fct != 1.f) for (size_t i = 0; i < length; ++i) { c[i].r = ch[i].r * fct; c[i].i = ch[i].i * fct; }
+        if (fct != 1.f) for (size_t i = 0; i < length; ++i) { c[i].r = p1[i].r * fct; c[i].i = p1[i].i * fct; }
         else memcpy(c, p1, sizeof(cf) * length);
     } else if (fct != 1.f)
         for (size_t i = 0; i < length; ++i) { c[i].r *= fct; c[i].i *= fct; }
