@@ -763,13 +763,102 @@ struct XArgs {
     int groups_per_plane;
 };
 
+// generic complex radix (cfftp::passg / ducc0 cfftpg), one transform per row; the result ends in cc.
+// wal: shared-memory copy of csarr with the direction's sign (ip entries)
 template <bool FWD>
-__device__ void cfft_all(const Ctx &c, const XBlue &b, const float *tab, float2 *&cur, float2 *&nxt, int ninst)
+__device__ void cpassg(const Ctx &c, int ido, int ip, int l1, float2 *cc, float2 *ch, const float2 *wa, const float2 *csarr,
+                       float2 *wal)
+{
+    const int cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
+#define GCH(a, b, k_) ch[IDX((a) + ido * ((b) + l1 * (k_)))]
+#define GCC(a, b, k_) cc[IDX((a) + ido * ((b) + cdim * (k_)))]
+#define GCX(a, b, k_) cc[IDX((a) + ido * ((b) + l1 * (k_)))]
+#define GCX2(a, b) cc[IDX((a) + idl1 * (b))]
+#define GCH2(a, b) ch[IDX((a) + idl1 * (b))]
+    for (int i = threadIdx.x; i < ip; i += kXT) {
+        const float2 w = __ldg(csarr + i);
+        wal[i] = i == 0 ? make_float2(1.f, 0.f) : make_float2(w.x, FWD ? -w.y : w.y);
+    }
+    FOR_ITEMS(it, ipph * idl1) {
+        const int j = it / idl1, rem = it - j * idl1;
+        const int k = rem / ido, i = rem - k * ido;
+        if (j == 0) GCH(i, k, 0) = GCC(i, 0, k);
+        else { const int jc = ip - j; CPM(GCH(i, k, j), GCH(i, k, jc), GCC(i, j, k), GCC(i, jc, k)) }
+    }
+    __syncthreads();
+    FOR_ITEMS(it, ipph * idl1) {
+        const int l = it / idl1, ik = it - l * idl1;
+        if (l == 0) {
+            float2 tmp = GCH2(ik, 0);
+            for (int j = 1; j < ipph; ++j) { const float2 v = GCH2(ik, j); tmp.x += v.x; tmp.y += v.y; }
+            GCX2(ik, 0) = tmp;
+        } else {
+            const int lc = ip - l;
+            const float2 h0 = GCH2(ik, 0), h1 = GCH2(ik, 1), h2 = GCH2(ik, 2), g1 = GCH2(ik, ip - 1), g2 = GCH2(ik, ip - 2);
+            const float2 w1 = wal[l], w2 = wal[2 * l];
+            float2 a, b;
+            a.x = h0.x + w1.x * h1.x + w2.x * h2.x;
+            a.y = h0.y + w1.x * h1.y + w2.x * h2.y;
+            b.x = -(w1.y * g1.y + w2.y * g2.y);
+            b.y = w1.y * g1.x + w2.y * g2.x;
+            int iwal = 2 * l;
+            int j = 3, jc = ip - 3;
+            for (; j + 1 < ipph; j += 2, jc -= 2) {
+                iwal += l; if (iwal > ip) iwal -= ip;
+                const float2 xw = wal[iwal];
+                iwal += l; if (iwal > ip) iwal -= ip;
+                const float2 xw2 = wal[iwal];
+                const float2 p0 = GCH2(ik, j), p1 = GCH2(ik, j + 1), q0 = GCH2(ik, jc), q1 = GCH2(ik, jc - 1);
+                a.x += p0.x * xw.x + p1.x * xw2.x;
+                a.y += p0.y * xw.x + p1.y * xw2.x;
+                b.x -= q0.y * xw.y + q1.y * xw2.y;
+                b.y += q0.x * xw.y + q1.x * xw2.y;
+            }
+            for (; j < ipph; ++j, --jc) {
+                iwal += l; if (iwal > ip) iwal -= ip;
+                const float2 xw = wal[iwal];
+                const float2 p0 = GCH2(ik, j), q0 = GCH2(ik, jc);
+                a.x += p0.x * xw.x;
+                a.y += p0.y * xw.x;
+                b.x -= q0.y * xw.y;
+                b.y += q0.x * xw.y;
+            }
+            GCX2(ik, l) = a;
+            GCX2(ik, lc) = b;
+        }
+    }
+    __syncthreads();
+    // shuffling and twiddling, in place
+    FOR_ITEMS(it, (ipph - 1) * idl1) {
+        const int jj = it / idl1, rem = it - jj * idl1;
+        const int k = rem / ido, i = rem - k * ido;
+        const int j = jj + 1, jc = ip - j;
+        const float2 t1 = GCX(i, k, j), t2 = GCX(i, k, jc);
+        float2 x1, x2;
+        CPM(x1, x2, t1, t2)
+        if (i == 0) { GCX(i, k, j) = x1; GCX(i, k, jc) = x2; }
+        else {
+            GCX(i, k, j) = smul<FWD>(x1, __ldg(wa + (j - 1) * (ido - 1) + i - 1));
+            GCX(i, k, jc) = smul<FWD>(x2, __ldg(wa + (jc - 1) * (ido - 1) + i - 1));
+        }
+    }
+#undef GCH
+#undef GCC
+#undef GCX
+#undef GCX2
+#undef GCH2
+}
+
+// cs: per-factor offsets (floats) of csarr for generic radices (may be null when every factor is hard-coded)
+template <bool FWD>
+__device__ void cfft_all(const Ctx &c, const XBlue &b, const float *tab, float2 *&cur, float2 *&nxt, int ninst,
+                         const int *cs = nullptr, float2 *wal = nullptr)
 {
     int l1 = 1;
     for (int f = 0; f < b.nf; ++f) {
         const int ip = b.fct[f], ido = b.n2 / (l1 * ip);
         const float2 *wa = reinterpret_cast<const float2 *>(tab + b.tw[f]);
+        bool swap = true;
         switch (ip) {
         case 2: cpass<2, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
         case 3: cpass<3, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
@@ -777,10 +866,11 @@ __device__ void cfft_all(const Ctx &c, const XBlue &b, const float *tab, float2 
         case 5: cpass<5, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
         case 7: cpass<7, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
         case 8: cpass<8, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
-        default: cpass<11, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
+        case 11: cpass<11, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
+        default: cpassg<FWD>(c, ido, ip, l1, cur, nxt, wa, reinterpret_cast<const float2 *>(tab + cs[f]), wal); swap = false; break;
         }
         __syncthreads();
-        float2 *t = cur; cur = nxt; nxt = t;
+        if (swap) { float2 *t = cur; cur = nxt; nxt = t; }
         l1 *= ip;
     }
 }
@@ -961,6 +1051,93 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
     }
 }
 
+// ---- even lengths > 1000: ducc0 rfftp_complexify -------------------------------------------------------------------
+// The real transform of length N runs as one complex transform of length N/2 on (x[2m], x[2m+1]) plus a butterfly with
+// the N-point roots; the inverse undoes it.  The post-processing of the forward transform, the notch and the
+// pre-processing of the inverse touch the same four packed positions per (i, N/2-i) pair, so they are one fused step
+// here and the packed spectrum never exists in memory.
+struct XCArgs {
+    B2sImg img;
+    const float *g;
+    const float *tab;
+    int n, nseq, along_cols;
+    int G, lgG;
+    XBlue cp;            // complex plan of length n/2 (ip / bk / bkf / inst unused)
+    int cs[12];          // csarr offsets of generic factors
+    int roots;           // offset (floats) of exp(2 pi i k / n), k <= n/4
+    int wal_max;         // largest generic radix
+    float fct;
+    int groups_per_plane;
+};
+
+__global__ void __launch_bounds__(kXT, 2) k_notch_cplx(const __grid_constant__ XCArgs a)
+{
+    extern __shared__ __align__(16) float xs[];
+    const int n = a.n, h = n >> 1, G = a.G;
+    float2 *X0 = reinterpret_cast<float2 *>(xs), *X1 = X0 + (size_t)h * G;
+    float2 *wal = X1 + (size_t)h * G;
+    Ctx c;
+    c.r = threadIdx.x & (G - 1);
+    c.item0 = threadIdx.x >> a.lgG;
+    c.istride = kXT >> a.lgG;
+    c.GP = G;
+    const float2 *roots = reinterpret_cast<const float2 *>(a.tab + a.roots);
+    float *plane = a.img.ptr + (size_t)blockIdx.y * a.img.plane_stride;
+    for (int grp = blockIdx.x; grp < a.groups_per_plane; grp += gridDim.x) {
+        const int s0 = grp * G;
+        const int ns = min(G, a.nseq - s0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < G * h; idx += kXT) {
+            const int m = idx >> a.lgG, rr = idx & (G - 1);
+            float2 v = make_float2(0.f, 0.f);
+            if (rr < ns) {
+                if (!a.along_cols) v = *reinterpret_cast<const float2 *>(plane + (size_t)(s0 + rr) * a.img.pitch + 2 * m);
+                else v = make_float2(plane[(size_t)(2 * m) * a.img.pitch + s0 + rr], plane[(size_t)(2 * m + 1) * a.img.pitch + s0 + rr]);
+            }
+            X0[idx] = v;
+        }
+        __syncthreads();
+        float2 *cur = X0, *nxt = X1;
+        cfft_all<true>(c, a.cp, a.tab, cur, nxt, 1, a.cs, wal);
+        // ---- forward post-processing -> notch on the four packed positions -> inverse pre-processing
+        FOR_ITEMS(i, h / 2 + 1) {
+            const int xi = h - i;
+            if (i == 0) {
+                const float2 r0 = cur[IDX(0)];
+                const float c0 = (r0.x + r0.y) * __ldg(a.g), cn = (r0.x - r0.y) * __ldg(a.g + n - 1);
+                cur[IDX(0)] = make_float2(c0 + cn, c0 - cn);
+                continue;
+            }
+            const float2 ri = cur[IDX(i)], rx = cur[IDX(xi)];
+            const float2 w = __ldg(roots + i);
+            const float2 xe = make_float2(ri.x + rx.x, ri.y - rx.y);
+            const float2 t = make_float2(ri.y + rx.y, rx.x - ri.x);
+            const float2 xo = make_float2(t.x * w.x + t.y * w.y, t.y * w.x - t.x * w.y);
+            float ca = 0.5f * (xe.x + xo.x), cb = 0.5f * (xe.y + xo.y);        // packed 2i-1, 2i
+            const float cc_ = 0.5f * (xe.x - xo.x), cd = 0.5f * (xo.y - xe.y);  // packed 2xi-1, 2xi
+            if (i == xi) { ca = cc_; cb = cd; }                                // the later assignment wins in the reference loop
+            const float g1 = __ldg(a.g + 2 * i - 1), g2 = __ldg(a.g + 2 * i), g3 = __ldg(a.g + 2 * xi - 1), g4 = __ldg(a.g + 2 * xi);
+            const float2 t1 = make_float2(ca * g1, cb * g2);
+            const float2 t2 = make_float2(cc_ * g3, -(cd * g4));
+            const float2 ye = make_float2(t1.x + t2.x, t1.y + t2.y);
+            const float2 d = make_float2(t1.x - t2.x, t1.y - t2.y);
+            const float2 yo = make_float2(d.x * w.x - d.y * w.y, d.x * w.y + d.y * w.x);
+            if (i != xi) cur[IDX(i)] = make_float2(ye.x - yo.y, ye.y + yo.x);
+            cur[IDX(xi)] = make_float2(ye.x + yo.y, -ye.y + yo.x);
+        }
+        __syncthreads();
+        cfft_all<false>(c, a.cp, a.tab, cur, nxt, 1, a.cs, wal);
+        for (int idx = threadIdx.x; idx < G * h; idx += kXT) {
+            const int m = idx >> a.lgG, rr = idx & (G - 1);
+            if (rr >= ns) continue;
+            const float2 v = cur[idx];
+            const float o0 = v.x * a.fct, o1 = v.y * a.fct;
+            if (!a.along_cols) *reinterpret_cast<float2 *>(plane + (size_t)(s0 + rr) * a.img.pitch + 2 * m) = make_float2(o0, o1);
+            else { plane[(size_t)(2 * m) * a.img.pitch + s0 + rr] = o0; plane[(size_t)(2 * m + 1) * a.img.pitch + s0 + rr] = o1; }
+        }
+    }
+}
+
 // one-row complex forward transform used once per plan to build bkf on the device with the same passes
 __global__ void __launch_bounds__(kXT) k_blue_setup(XBlue b, const float *tab, const float2 *tbkf, float2 *out)
 {
@@ -1061,18 +1238,110 @@ size_t xfft_smem(int n, int G, const XBlue &b, int gt_max)
 
 struct B2sXfftPlan {
     XArgs a;            // img, g, tab, along_cols, nseq, groups_per_plane are filled per launch
+    XCArgs ca;          // complexify variant (even lengths > 1000)
+    int cplx;
     size_t smem;
     float *d_tab;
 };
 
-int b2s_xfft_supported(int n) { return n >= 2 && !(n > 1000 && (n & 1) == 0); }
+namespace {
+std::vector<int> prime_factors(int n)
+{
+    std::vector<int> f;
+    for (int p = 2; (long long)p * p <= n; ++p)
+        while (n % p == 0) { f.push_back(p); n /= p; }
+    if (n > 1) f.push_back(n);
+    return f;
+}
+// how scipy's (ducc0) float32 r2r transform of length n is evaluated: 0 = real passes (rfftp, Bluestein passes for prime
+// factors >= 135), 1 = half-length complex transform (rfftp_complexify), -1 = a variant that is not mirrored here.
+// Classification pinned empirically against scipy 1.18 for every even length in (1000, 3400): tests/test_oracle.py.
+int xfft_class(int n)
+{
+    if (n < 2) return -1;
+    if (n <= 1000 || (n & 1)) return 0;
+    const std::vector<int> f = prime_factors(n / 2);
+    int big = 0;
+    for (int p : f) big = std::max(big, p);
+    if (big <= 5) return (n % 8) ? 0 : -1;      // 5-smooth half length: plain real passes unless 8 | n (unknown variant)
+    return big < 110 ? 1 : -1;                   // a complex Bluestein pass inside the half-length plan is not mirrored
+}
+}  // namespace
+
+int b2s_xfft_supported(int n) { return xfft_class(n) >= 0; }
+
+static B2sXfftPlan *xfft_create_cplx(int n)
+{
+    B2sXfftPlan *pl = new B2sXfftPlan();
+    pl->cplx = 1;
+    XCArgs &a = pl->ca;
+    memset(&a, 0, sizeof a);
+    a.n = n;
+    const int h = n / 2;
+    XBlue &b = a.cp;
+    b.n2 = h;
+    std::vector<int> cf;
+    int len = h;
+    while ((len & 7) == 0) { cf.push_back(8); len >>= 3; }
+    while ((len & 3) == 0) { cf.push_back(4); len >>= 2; }
+    if ((len & 1) == 0) { len >>= 1; cf.push_back(2); std::swap(cf[0], cf.back()); }
+    for (int d = 3; d * d <= len; d += 2)
+        while ((len % d) == 0) { cf.push_back(d); len /= d; }
+    if (len > 1) cf.push_back(len);
+    if (cf.size() > 12) { delete pl; return nullptr; }
+    b.nf = (int)cf.size();
+    std::vector<float> tab;
+    SinCos comp(h);
+    int l1 = 1;
+    for (int k = 0; k < b.nf; ++k) {
+        const int ip = cf[k], ido = h / (l1 * ip);
+        b.fct[k] = ip;
+        while (tab.size() & 1) tab.push_back(0.f);
+        b.tw[k] = (int)tab.size();
+        tab.resize(tab.size() + 2 * (size_t)(ip - 1) * (ido - 1), 0.f);
+        for (int j = 1; j < ip; ++j)
+            for (int i = 1; i < ido; ++i)
+                comp.get((size_t)j * l1 * i, &tab[b.tw[k] + 2 * ((j - 1) * (ido - 1) + i - 1)],
+                         &tab[b.tw[k] + 2 * ((j - 1) * (ido - 1) + i - 1) + 1]);
+        if (ip > 11) {
+            a.cs[k] = (int)tab.size();
+            tab.resize(tab.size() + 2 * (size_t)ip, 0.f);
+            for (int j = 0; j < ip; ++j) comp.get((size_t)j * l1 * ido, &tab[a.cs[k] + 2 * j], &tab[a.cs[k] + 2 * j + 1]);
+            a.wal_max = std::max(a.wal_max, ip);
+        }
+        l1 *= ip;
+    }
+    while (tab.size() & 1) tab.push_back(0.f);
+    a.roots = (int)tab.size();
+    tab.resize(tab.size() + 2 * (size_t)(h / 2 + 1), 0.f);
+    SinCos rt(n);
+    for (int i = 0; i <= h / 2; ++i) rt.get(i, &tab[a.roots + 2 * i], &tab[a.roots + 2 * i + 1]);
+    a.fct = (float)(1.0L / (long double)n);
+    auto smem_of = [&](int g) { return sizeof(float2) * (2 * (size_t)h * g + (size_t)a.wal_max + 2); };
+    int G = 0;
+    for (int budget : {110 * 1024, 220 * 1024}) {
+        for (int g = 16; g >= 1 && !G; g >>= 1)
+            if (smem_of(g) <= (size_t)budget) G = g;
+        if (G) break;
+    }
+    if (!G || cudaMalloc(&pl->d_tab, sizeof(float) * (tab.size() + 2)) != cudaSuccess) { delete pl; return nullptr; }
+    cudaMemcpy(pl->d_tab, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice);
+    a.tab = pl->d_tab;
+    a.G = G;
+    while ((1 << a.lgG) < G) ++a.lgG;
+    pl->smem = smem_of(G);
+    return pl;
+}
 
 // builds the plan for length n (tables uploaded to the current device); returns nullptr when the length class is not
 // covered or the work set does not fit in shared memory
 B2sXfftPlan *b2s_xfft_create(int n)
 {
-    if (!b2s_xfft_supported(n)) return nullptr;
+    const int cls = xfft_class(n);
+    if (cls < 0) return nullptr;
+    if (cls == 1) return xfft_create_cplx(n);
     B2sXfftPlan *pl = new B2sXfftPlan();
+    pl->cplx = 0;
     XArgs &a = pl->a;
     memset(&a, 0, sizeof a);
     a.n = n;
@@ -1262,6 +1531,20 @@ void b2s_xfft_destroy(B2sXfftPlan *pl)
 void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B2sImg &img, int along_cols, int n_planes,
                             int sm_count, cudaStream_t s)
 {
+    if (pl->cplx) {
+        XCArgs a = pl->ca;
+        a.img = img;
+        a.g = d_notch;
+        a.along_cols = along_cols;
+        a.nseq = along_cols ? img.cols : img.rows;
+        a.groups_per_plane = (a.nseq + a.G - 1) / a.G;
+        cudaFuncSetAttribute(k_notch_cplx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
+        int bx = a.groups_per_plane;
+        const int cap = (sm_count * 8 + n_planes - 1) / n_planes;
+        if (bx > cap) bx = cap > 0 ? cap : 1;
+        k_notch_cplx<<<dim3(bx, n_planes), kXT, pl->smem, s>>>(a);
+        return;
+    }
     XArgs a = pl->a;
     a.img = img;
     a.g = d_notch;

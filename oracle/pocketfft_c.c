@@ -1343,20 +1343,40 @@ static int complexify_exec(float *c, size_t N, float fct, int fwd)
 }
 
 /* ================================================================ pocketfft_r<float> + r2r_fftpack */
-/* 1 when this restatement covers length n: ducc0 switches even lengths > 1000 to a half-length complex transform
- * (rfftp_complexify), which is not restated here. */
+/* How scipy (ducc0) evaluates the float32 r2r transform of length n, as far as it is restated here:
+ *   0  real passes (rfftp; Bluestein passes for prime factors >= 135): every odd or <= 1000 length, and even lengths
+ *      > 1000 whose half is 5-smooth when 8 does not divide n;
+ *   1  half-length complex transform (rfftp_complexify): even lengths > 1000 whose half length has a prime factor in
+ *      [7, 109];
+ *  -1  not restated: half length with a prime factor >= 110 (complex Bluestein pass inside the plan) or 5-smooth with
+ *      8 | n (unknown variant).
+ * Pinned against the installed scipy for every even length in (1000, 3400) by tests/test_oracle.py.  One known gap inside
+ * class 1: when 8 divides the half length, the rows scipy processes outside its 4-wide SIMD batches (the last rows % 4
+ * rows of an array) round differently from the SIMD rows; this file (and the GPU) reproduce the SIMD rows. */
 static int orc_allow_all = 0;
 void orc_fft_allow_all(int v) { orc_allow_all = v; }
-int orc_fft_mirrored(size_t n) { return n >= 1 && (orc_allow_all || !(n > 1000 && (n & 1) == 0)); }
+int orc_fft_class(size_t n)
+{
+    if (n < 1) return -1;
+    if (n <= 1000 || (n & 1)) return 0;
+    size_t h = n / 2, big = 1;
+    for (size_t p = 2; p * p <= h; ++p)
+        while (h % p == 0) { if (p > big) big = p; h /= p; }
+    if (h > 1 && h > big) big = h;
+    if (big <= 5) return (n % 8) ? 0 : (orc_allow_all ? 1 : -1);
+    return big < 110 ? 1 : -1;
+}
+int orc_fft_mirrored(size_t n) { return orc_fft_class(n) >= 0; }
 
 /* scipy.fftpack.rfft (forward != 0) / irfft (forward == 0, scaled by 1/n) on `rows` contiguous rows of length n.
  * Returns 0, or 1 when the length class is not restated (data untouched). */
 int orc_fftpack_r2r_f32(float *data, size_t rows, size_t n, int forward)
 {
     if (n == 0) return -1;
-    if (!orc_fft_mirrored(n)) return 1;
+    const int cls = orc_fft_class(n);
+    if (cls < 0) return 1;
     float fct = forward ? 1.f : (float)(1.0L / (long double)n);
-    if (n > 1000 && (n & 1) == 0) {
+    if (cls == 1) {
         for (size_t r = 0; r < rows; ++r) { int rc = complexify_exec(data + r * n, n, fct, forward); if (rc) return rc; }
         return 0;
     }

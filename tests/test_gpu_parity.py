@@ -114,8 +114,23 @@ def test_notch_stage_close_to_pocketfft():
 
 
 def _mirrored(n):
-    # length classes whose scipy.fftpack float32 transform the GPU reproduces rounding for rounding (rfft_exact.cu)
-    return n >= 2 and not (n > 1000 and n % 2 == 0)
+    """length classes whose scipy.fftpack float32 transform the GPU reproduces rounding for rounding (rfft_exact.cu):
+    every odd or <= 1000 length; even lengths > 1000 when the half length has a prime factor in [7, 109] (half-length
+    complex transform) or is 5-smooth with 8 not dividing n."""
+    if n < 2:
+        return False
+    if n <= 1000 or n % 2:
+        return True
+    h, f, p = n // 2, [], 2
+    while p * p <= h:
+        while h % p == 0:
+            f.append(p); h //= p
+        p += 1
+    if h > 1:
+        f.append(h)
+    if max(f) <= 5:
+        return n % 8 != 0
+    return max(f) < 110
 
 
 @pytest.mark.parametrize("shape,wavelet,sigma", [
@@ -124,6 +139,11 @@ def _mirrored(n):
     ((538, 560), "db3", (6, 6)),        # 2*137 = 274, 3*... composites with a Bluestein factor
     ((700, 650), "db4", (20, 20)),
     ((1290, 40), "db2", (4, 4)),        # odd length > 1000 along axis -2 (bidirectional)
+    ((2628, 44), "db9", (4, 4)),        # 1326 = 2*3*13*17 along axis -2: half-length complex transform, generic radices
+    ((44, 2276), "db9", (4, 4)),        # 1150 = 2*5*5*23 along axis -1
+    ((2640, 44), "db9", (4, 4)),        # 1332 = 4*9*37
+    ((44, 2580), "db9", (4, 4)),        # 1302 = 2*3*7*31
+    ((44, 2492), "db9", (4, 4)),        # 1258 = 2*17*37
 ])
 def test_notch_stage_bit_exact_vs_scipy_fftpack(shape, wavelet, sigma):
     img = synth.plane(9, shape)

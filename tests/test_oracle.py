@@ -201,5 +201,38 @@ def test_fft_restatement_is_bit_identical_to_scipy_fftpack(lengths):
             y = x.copy()
             rc = L.orc_fftpack_r2r_f32(ctypes.c_void_p(y.ctypes.data), ctypes.c_size_t(6), ctypes.c_size_t(n), ctypes.c_int(fwd))
             assert rc == 0 and np.array_equal(ref.view(np.uint32), y.view(np.uint32)), (n, fwd)
-    y = np.zeros((1, 1024 + 2), np.float32)
-    assert L.orc_fftpack_r2r_f32(ctypes.c_void_p(y.ctypes.data), ctypes.c_size_t(1), ctypes.c_size_t(1026), ctypes.c_int(1)) == 1
+    y = np.zeros((1, 1024), np.float32)        # 5-smooth half length with 8 | n: declared outside the restatement
+    assert L.orc_fftpack_r2r_f32(ctypes.c_void_p(y.ctypes.data), ctypes.c_size_t(1), ctypes.c_size_t(1024), ctypes.c_int(1)) == 1
+
+
+def test_fft_restatement_even_lengths_above_1000():
+    """ducc0 runs even lengths > 1000 as a half-length complex transform; the restatement (and the GPU mirror of it)
+    covers the half lengths with a prime factor in [7, 109].  Pinned on the 4-wide SIMD rows scipy processes (8 rows),
+    which is what a sub-band with > 1000 rows consists of; the production db9 lengths are checked on leftover rows too."""
+    import ctypes
+    from scipy.fftpack import irfft, rfft
+    L = _fft_lib()
+    L.orc_fft_class.restype = ctypes.c_int
+    L.orc_fft_class.argtypes = [ctypes.c_size_t]
+    rng = np.random.default_rng(6)
+    covered = 0
+    for n in list(range(1002, 1500, 2)) + [1670, 2048, 2636, 2648, 3252]:
+        cls = L.orc_fft_class(n)
+        x = rng.standard_normal((8, n)).astype(np.float32) * 50
+        y = x.copy()
+        rc = L.orc_fftpack_r2r_f32(ctypes.c_void_p(y.ctypes.data), ctypes.c_size_t(8), ctypes.c_size_t(n), ctypes.c_int(1))
+        if cls < 0:
+            assert rc == 1
+            continue
+        covered += 1
+        z = x.copy()
+        L.orc_fftpack_r2r_f32(ctypes.c_void_p(z.ctypes.data), ctypes.c_size_t(8), ctypes.c_size_t(n), ctypes.c_int(0))
+        assert np.array_equal(rfft(x, axis=-1).view(np.uint32), y.view(np.uint32)), n
+        assert np.array_equal(irfft(x, axis=-1).view(np.uint32), z.view(np.uint32)), n
+    assert covered > 100
+    for n in (1326, 1150, 1332, 1302):           # db9 on 2048^2 tiles, sigma 250 / 100 / 256, and 2000^2: any row count
+        for rows in (1, 6):
+            x = rng.standard_normal((rows, n)).astype(np.float32)
+            y = x.copy()
+            L.orc_fftpack_r2r_f32(ctypes.c_void_p(y.ctypes.data), ctypes.c_size_t(rows), ctypes.c_size_t(n), ctypes.c_int(1))
+            assert np.array_equal(rfft(x, axis=-1).view(np.uint32), y.view(np.uint32)), (n, rows)
