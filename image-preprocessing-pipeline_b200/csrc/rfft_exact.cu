@@ -849,10 +849,18 @@ __device__ void cpassg(const Ctx &c, int ido, int ip, int l1, float2 *cc, float2
 #undef GCH2
 }
 
-// cs: per-factor offsets (floats) of csarr for generic radices (may be null when every factor is hard-coded)
 template <bool FWD>
-__device__ void cfft_all(const Ctx &c, const XBlue &b, const float *tab, float2 *&cur, float2 *&nxt, int ninst,
-                         const int *cs = nullptr, float2 *wal = nullptr)
+__device__ void cblue(const Ctx &c, const XBlue &b, const float *tab, int ido, int l1, float2 *cc, float2 *ch,
+                      const float2 *wa, float2 *X0, float2 *X1);
+
+// cs: per-factor offsets (floats) of csarr for generic radices (may be null when every factor is hard-coded);
+// blue / BX0 / BX1: Bluestein sub-plan and work buffers for a prime factor >= 110 (complexify plans only)
+// OUTER: the plan may contain generic / Bluestein factors (complexify plans); the inner 11-smooth plans of a Bluestein
+// convolution are instantiated with OUTER = false, which also keeps the call graph free of recursion (everything inlines)
+template <bool FWD, bool OUTER = false>
+__device__ __forceinline__ void cfft_all(const Ctx &c, const XBlue &b, const float *tab, float2 *&cur, float2 *&nxt, int ninst,
+                                         const int *cs = nullptr, float2 *wal = nullptr, const XBlue *blue = nullptr,
+                                         float2 *BX0 = nullptr, float2 *BX1 = nullptr)
 {
     int l1 = 1;
     for (int f = 0; f < b.nf; ++f) {
@@ -867,12 +875,65 @@ __device__ void cfft_all(const Ctx &c, const XBlue &b, const float *tab, float2 
         case 7: cpass<7, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
         case 8: cpass<8, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
         case 11: cpass<11, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
-        default: cpassg<FWD>(c, ido, ip, l1, cur, nxt, wa, reinterpret_cast<const float2 *>(tab + cs[f]), wal); swap = false; break;
+        default:
+            if (OUTER) {
+                if (ip >= 110) { cblue<FWD>(c, *blue, tab, ido, l1, cur, nxt, wa, BX0, BX1); swap = l1 > 1; }
+                else { cpassg<FWD>(c, ido, ip, l1, cur, nxt, wa, reinterpret_cast<const float2 *>(tab + cs[f]), wal); swap = false; }
+            }
+            break;
         }
         __syncthreads();
         if (swap) { float2 *t = cur; cur = nxt; nxt = t; }
         l1 *= ip;
     }
+}
+
+// Bluestein pass of a complex plan (ducc0 cfftpblue, prime radix >= 110): every (k, i) column is one transform of length
+// ip evaluated as a cyclic convolution of length n2; the inter-pass twiddle is merged into the final multiplication by
+// b_k.  l1 > 1: result in ch; l1 == 1: written back into cc.
+template <bool FWD>
+__device__ void cblue(const Ctx &c, const XBlue &b, const float *tab, int ido, int l1, float2 *cc, float2 *ch,
+                      const float2 *wa, float2 *X0, float2 *X1)
+{
+    const int ip = b.ip, n2 = b.n2;
+    const float2 *bk = reinterpret_cast<const float2 *>(tab + b.bk);
+    const float2 *bkf = reinterpret_cast<const float2 *>(tab + b.bkf);
+    const int total = l1 * ido;
+#define BCC(a, m_, k_) cc[IDX((a) + ido * ((m_) + ip * (k_)))]
+#define BCH(a, k_, m_) ch[IDX((a) + ido * ((k_) + l1 * (m_)))]
+    for (int base = 0; base < total; base += b.inst) {
+        const int ninst = min(b.inst, total - base);
+        FOR_ITEMS(it, ninst * n2) {
+            const int q = it / n2, m = it - q * n2;
+            const int inst = base + q, k = inst / ido, i = inst - k * ido;
+            const float2 a0 = smul<FWD>(BCC(i, 0, k), __ldg(bk));
+            X0[IDX(q * n2 + m)] = m < ip ? smul<FWD>(BCC(i, m, k), __ldg(bk + m)) : make_float2(a0.x * 0.f, a0.y * 0.f);
+        }
+        __syncthreads();
+        float2 *cur = X0, *nxt = X1;
+        cfft_all<true>(c, b, tab, cur, nxt, ninst);
+        FOR_ITEMS(it, ninst * n2) {
+            const int q = it / n2, m = it - q * n2;
+            const int mb = 2 * m <= n2 ? m : n2 - m;
+            cur[IDX(q * n2 + m)] = smul<!FWD>(cur[IDX(q * n2 + m)], __ldg(bkf + mb));
+        }
+        __syncthreads();
+        cfft_all<false>(c, b, tab, cur, nxt, ninst);
+        FOR_ITEMS(it, ninst * ip) {
+            const int q = it / ip, m = it - q * ip;
+            const int inst = base + q, k = inst / ido, i = inst - k * ido;
+            float2 w = __ldg(bk + m);
+            if (i != 0 && m != 0) {
+                const float2 t = __ldg(wa + (i - 1) + (m - 1) * (ido - 1));
+                w = make_float2(w.x * t.x - w.y * t.y, w.x * t.y + w.y * t.x);
+            }
+            const float2 v = smul<FWD>(cur[IDX(q * n2 + m)], w);
+            if (l1 > 1) BCH(i, k, m) = v; else BCC(i, m, 0) = v;
+        }
+        __syncthreads();
+    }
+#undef BCC
+#undef BCH
 }
 
 // Bluestein pass of the real transform (ducc0 rfftpblue): every (k) and (k, i) column set is one complex transform of
@@ -1063,6 +1124,7 @@ struct XCArgs {
     int n, nseq, along_cols;
     int G, lgG;
     XBlue cp;            // complex plan of length n/2 (ip / bk / bkf / inst unused)
+    XBlue blue;          // Bluestein sub-plan of the (single) prime factor >= 110 of n/2, if any
     int cs[12];          // csarr offsets of generic factors
     int roots;           // offset (floats) of exp(2 pi i k / n), k <= n/4
     int wal_max;         // largest generic radix
@@ -1076,6 +1138,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_cplx(const __grid_constant__ X
     const int n = a.n, h = n >> 1, G = a.G;
     float2 *X0 = reinterpret_cast<float2 *>(xs), *X1 = X0 + (size_t)h * G;
     float2 *wal = X1 + (size_t)h * G;
+    float2 *BX0 = wal + a.wal_max + 2, *BX1 = BX0 + (size_t)a.blue.inst * a.blue.n2 * G;
     Ctx c;
     c.r = threadIdx.x & (G - 1);
     c.item0 = threadIdx.x >> a.lgG;
@@ -1098,7 +1161,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_cplx(const __grid_constant__ X
         }
         __syncthreads();
         float2 *cur = X0, *nxt = X1;
-        cfft_all<true>(c, a.cp, a.tab, cur, nxt, 1, a.cs, wal);
+        cfft_all<true, true>(c, a.cp, a.tab, cur, nxt, 1, a.cs, wal, &a.blue, BX0, BX1);
         // ---- forward post-processing -> notch on the four packed positions -> inverse pre-processing
         FOR_ITEMS(i, h / 2 + 1) {
             const int xi = h - i;
@@ -1126,7 +1189,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_cplx(const __grid_constant__ X
             cur[IDX(xi)] = make_float2(ye.x + yo.y, -ye.y + yo.x);
         }
         __syncthreads();
-        cfft_all<false>(c, a.cp, a.tab, cur, nxt, 1, a.cs, wal);
+        cfft_all<false, true>(c, a.cp, a.tab, cur, nxt, 1, a.cs, wal, &a.blue, BX0, BX1);
         for (int idx = threadIdx.x; idx < G * h; idx += kXT) {
             const int m = idx >> a.lgG, rr = idx & (G - 1);
             if (rr >= ns) continue;
@@ -1264,7 +1327,9 @@ int xfft_class(int n)
     int big = 0;
     for (int p : f) big = std::max(big, p);
     if (big <= 5) return (n % 8) ? 0 : -1;      // 5-smooth half length: plain real passes unless 8 | n (unknown variant)
-    return big < 110 ? 1 : -1;                   // a complex Bluestein pass inside the half-length plan is not mirrored
+    int n_blue = 0;
+    for (int p : f) n_blue += p >= 110;          // prime factors >= 110 run as complex Bluestein passes (one supported)
+    return n_blue <= 1 ? 1 : -1;
 }
 }  // namespace
 
@@ -1292,7 +1357,7 @@ static B2sXfftPlan *xfft_create_cplx(int n)
     b.nf = (int)cf.size();
     std::vector<float> tab;
     SinCos comp(h);
-    int l1 = 1;
+    int l1 = 1, blue_ip = 0, blue_need = 1;
     for (int k = 0; k < b.nf; ++k) {
         const int ip = cf[k], ido = h / (l1 * ip);
         b.fct[k] = ip;
@@ -1303,7 +1368,10 @@ static B2sXfftPlan *xfft_create_cplx(int n)
             for (int i = 1; i < ido; ++i)
                 comp.get((size_t)j * l1 * i, &tab[b.tw[k] + 2 * ((j - 1) * (ido - 1) + i - 1)],
                          &tab[b.tw[k] + 2 * ((j - 1) * (ido - 1) + i - 1) + 1]);
-        if (ip > 11) {
+        if (ip >= 110) {
+            blue_ip = ip;
+            blue_need = l1 * ido;
+        } else if (ip > 11) {
             a.cs[k] = (int)tab.size();
             tab.resize(tab.size() + 2 * (size_t)ip, 0.f);
             for (int j = 0; j < ip; ++j) comp.get((size_t)j * l1 * ido, &tab[a.cs[k] + 2 * j], &tab[a.cs[k] + 2 * j + 1]);
@@ -1311,21 +1379,89 @@ static B2sXfftPlan *xfft_create_cplx(int n)
         }
         l1 *= ip;
     }
+    std::vector<float2> tbkf;
+    XBlue &bl = a.blue;
+    if (blue_ip) {   // Bluestein sub-plan: same construction as for the real passes (b2s_xfft_create)
+        bl.ip = blue_ip;
+        bl.n2 = (int)good_size_cmplx((size_t)blue_ip * 2 - 1);
+        std::vector<int> bf;
+        int ln = bl.n2;
+        while ((ln & 7) == 0) { bf.push_back(8); ln >>= 3; }
+        while ((ln & 3) == 0) { bf.push_back(4); ln >>= 2; }
+        if ((ln & 1) == 0) { ln >>= 1; bf.push_back(2); std::swap(bf[0], bf.back()); }
+        for (int d = 3; d * d <= ln; d += 2)
+            while ((ln % d) == 0) { bf.push_back(d); ln /= d; }
+        if (ln > 1) bf.push_back(ln);
+        if (bf.size() > 12) { delete pl; return nullptr; }
+        bl.nf = (int)bf.size();
+        SinCos c2(bl.n2);
+        int m1 = 1;
+        for (int k = 0; k < bl.nf; ++k) {
+            const int ip = bf[k], ido = bl.n2 / (m1 * ip);
+            bl.fct[k] = ip;
+            while (tab.size() & 1) tab.push_back(0.f);
+            bl.tw[k] = (int)tab.size();
+            tab.resize(tab.size() + 2 * (size_t)(ip - 1) * (ido - 1), 0.f);
+            for (int j = 1; j < ip; ++j)
+                for (int i = 1; i < ido; ++i)
+                    c2.get((size_t)j * m1 * i, &tab[bl.tw[k] + 2 * ((j - 1) * (ido - 1) + i - 1)],
+                           &tab[bl.tw[k] + 2 * ((j - 1) * (ido - 1) + i - 1) + 1]);
+            m1 *= ip;
+        }
+        while (tab.size() & 1) tab.push_back(0.f);
+        bl.bk = (int)tab.size();
+        tab.resize(tab.size() + 2 * (size_t)blue_ip, 0.f);
+        SinCos tmp(2 * (size_t)blue_ip);
+        tab[bl.bk] = 1.f; tab[bl.bk + 1] = 0.f;
+        size_t coeff = 0;
+        for (int m = 1; m < blue_ip; ++m) {
+            coeff += 2 * (size_t)m - 1;
+            if (coeff >= 2 * (size_t)blue_ip) coeff -= 2 * (size_t)blue_ip;
+            tmp.get(coeff, &tab[bl.bk + 2 * m], &tab[bl.bk + 2 * m + 1]);
+        }
+        bl.bkf = (int)tab.size();
+        tab.resize(tab.size() + 2 * (size_t)(bl.n2 / 2 + 1), 0.f);
+        tbkf.assign(bl.n2, make_float2(0.f, 0.f));
+        volatile float xn2 = 1.f / (float)bl.n2;
+        for (int m = 0; m < blue_ip; ++m) {
+            volatile float re = tab[bl.bk + 2 * m] * xn2, im = tab[bl.bk + 2 * m + 1] * xn2;
+            tbkf[m] = make_float2(re, im);
+            if (m) tbkf[bl.n2 - m] = tbkf[m];
+        }
+    }
     while (tab.size() & 1) tab.push_back(0.f);
     a.roots = (int)tab.size();
     tab.resize(tab.size() + 2 * (size_t)(h / 2 + 1), 0.f);
     SinCos rt(n);
     for (int i = 0; i <= h / 2; ++i) rt.get(i, &tab[a.roots + 2 * i], &tab[a.roots + 2 * i + 1]);
     a.fct = (float)(1.0L / (long double)n);
-    auto smem_of = [&](int g) { return sizeof(float2) * (2 * (size_t)h * g + (size_t)a.wal_max + 2); };
+    auto smem_of = [&](int g) {
+        return sizeof(float2) * (2 * (size_t)h * g + (size_t)a.wal_max + 2 + 2 * (size_t)bl.inst * bl.n2 * g);
+    };
     int G = 0;
     for (int budget : {110 * 1024, 220 * 1024}) {
-        for (int g = 16; g >= 1 && !G; g >>= 1)
-            if (smem_of(g) <= (size_t)budget) G = g;
+        for (int g = 16; g >= 1 && !G; g >>= 1) {
+            if (blue_ip) {
+                for (int inst = blue_need < 8 ? blue_need : 8; inst >= 1; --inst) {
+                    bl.inst = inst;
+                    if (smem_of(g) <= (size_t)budget) { G = g; break; }
+                }
+            } else if (smem_of(g) <= (size_t)budget) G = g;
+        }
         if (G) break;
     }
     if (!G || cudaMalloc(&pl->d_tab, sizeof(float) * (tab.size() + 2)) != cudaSuccess) { delete pl; return nullptr; }
     cudaMemcpy(pl->d_tab, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice);
+    if (blue_ip) {
+        float2 *d_t = nullptr;
+        cudaMalloc(&d_t, sizeof(float2) * bl.n2);
+        cudaMemcpy(d_t, tbkf.data(), sizeof(float2) * bl.n2, cudaMemcpyHostToDevice);
+        const size_t sm = sizeof(float2) * 4 * (size_t)bl.n2;
+        cudaFuncSetAttribute(k_blue_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        k_blue_setup<<<1, kXT, sm>>>(bl, pl->d_tab, d_t, reinterpret_cast<float2 *>(pl->d_tab + bl.bkf));
+        cudaDeviceSynchronize();
+        cudaFree(d_t);
+    }
     a.tab = pl->d_tab;
     a.G = G;
     while ((1 << a.lgG) < G) ++a.lgG;

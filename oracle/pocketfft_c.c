@@ -690,6 +690,8 @@ static void radbg(size_t ido, size_t ip, size_t l1, float *cc, float *ch, const 
 /* ================================================================ cfftp<float> */
 typedef struct { size_t fct; cf *tw, *tws; } cfct;
 typedef struct { size_t length, nfct; cfct fct[MAXFACT]; cf *mem; } cfftp_t;
+/* complex Bluestein pass (ducc0 cfftpblue), defined after fftblue below */
+static void cblue_pass(size_t ido, size_t ip, size_t l1, cf *cc, cf *ch, const cf *wa, int fwd);
 
 static int cfftp_init(cfftp_t *p, size_t length)
 {
@@ -711,7 +713,6 @@ static int cfftp_init(cfftp_t *p, size_t length)
     size_t twsz = 0, l1 = 1;
     for (size_t k = 0; k < p->nfct; ++k) {
         size_t ip = p->fct[k].fct, ido = length / (l1 * ip);
-        if (ip >= 110) return -1; /* complex Bluestein pass inside a multipass: not restated */
         twsz += (ip - 1) * (ido - 1);
         if (ip > 11) twsz += ip;
         l1 *= ip;
@@ -1086,6 +1087,7 @@ static void cfftp_exec(const cfftp_t *p, cf *c, float fct, int fwd)
         else if (ip == 5) pass5(ido, l1, p1, p2, p->fct[k1].tw, fwd);
         else if (ip == 7) pass7(ido, l1, p1, p2, p->fct[k1].tw, fwd);
         else if (ip == 11) pass11(ido, l1, p1, p2, p->fct[k1].tw, fwd);
+        else if (ip >= 110) { cblue_pass(ido, ip, l1, p1, p2, p->fct[k1].tw, fwd); if (l1 == 1) { t = p1; p1 = p2; p2 = t; } }
         else { passg(ido, ip, l1, p1, p2, p->fct[k1].tw, p->fct[k1].tws, fwd); t = p1; p1 = p2; p2 = t; }
         t = p1; p1 = p2; p2 = t;
         l1 = l2;
@@ -1176,6 +1178,49 @@ __attribute__((unused)) static void fftblue_exec_r(const fftblue_t *b, float *c,
     free(tmp);
 }
 
+
+/* ---- ducc0 cfftpblue<float> as a pass of a complex plan (prime radix >= 110): every (k, i) column is one Bluestein
+ * transform of length ip; the inter-pass twiddle is merged into the final multiplication by b_k.  l1 > 1: result in ch;
+ * l1 == 1: written back into cc. */
+static void cblue_pass(size_t ido, size_t ip, size_t l1, cf *cc, cf *ch, const cf *wa, int fwd)
+{
+    fftblue_t b;
+    if (fftblue_init(&b, ip)) return;
+    size_t n2 = b.n2;
+    cf *akf = (cf *)malloc(sizeof(cf) * n2);
+#define BCC(a, b_, c) cc[(a) + ido * ((b_) + ip * (c))]
+#define BCH(a, b_, c) ch[(a) + ido * ((b_) + l1 * (c))]
+#define BWA(x, i) wa[(i) - 1 + (x) * (ido - 1)]
+    for (size_t k = 0; k < l1; ++k)
+        for (size_t i = 0; i < ido; ++i) {
+            for (size_t m = 0; m < ip; ++m) akf[m] = smul(BCC(i, m, k), b.bk[m], fwd);
+            cf zero = {akf[0].r * 0.f, akf[0].i * 0.f};
+            for (size_t m = ip; m < n2; ++m) akf[m] = zero;
+            cfftp_exec(&b.plan, akf, 1.f, 1);
+            akf[0] = smul(akf[0], b.bkf[0], !fwd);
+            for (size_t m = 1; m < (n2 + 1) / 2; ++m) {
+                akf[m] = smul(akf[m], b.bkf[m], !fwd);
+                akf[n2 - m] = smul(akf[n2 - m], b.bkf[m], !fwd);
+            }
+            if ((n2 & 1) == 0) akf[n2 / 2] = smul(akf[n2 / 2], b.bkf[n2 / 2], !fwd);
+            cfftp_exec(&b.plan, akf, 1.f, 0);
+            for (size_t m = 0; m < ip; ++m) {
+                cf w = b.bk[m];
+                if (i != 0 && m != 0) {
+                    cf t = BWA(m - 1, i);
+                    cf p = {b.bk[m].r * t.r - b.bk[m].i * t.i, b.bk[m].r * t.i + b.bk[m].i * t.r};
+                    w = p;
+                }
+                cf v = smul(akf[m], w, fwd);
+                if (l1 > 1) BCH(i, k, m) = v; else BCC(i, m, 0) = v;
+            }
+        }
+#undef BCC
+#undef BCH
+#undef BWA
+    free(akf);
+    fftblue_free(&b);
+}
 
 /* ---- ducc0 rfftpblue<float>: one real-FFT pass of prime radix ip >= 135 evaluated with complex Bluestein transforms
  * (scipy >= 1.15 vendors ducc0, whose rfftpass::make_pass uses rfftpg for ip < 135 and rfftpblue above) */
@@ -1346,10 +1391,9 @@ static int complexify_exec(float *c, size_t N, float fct, int fwd)
 /* How scipy (ducc0) evaluates the float32 r2r transform of length n, as far as it is restated here:
  *   0  real passes (rfftp; Bluestein passes for prime factors >= 135): every odd or <= 1000 length, and even lengths
  *      > 1000 whose half is 5-smooth when 8 does not divide n;
- *   1  half-length complex transform (rfftp_complexify): even lengths > 1000 whose half length has a prime factor in
- *      [7, 109];
- *  -1  not restated: half length with a prime factor >= 110 (complex Bluestein pass inside the plan) or 5-smooth with
- *      8 | n (unknown variant).
+ *   1  half-length complex transform (rfftp_complexify): even lengths > 1000 whose half length has a prime factor >= 7
+ *      (generic complex radices below 110, a complex Bluestein pass for a prime factor >= 110);
+ *  -1  not restated: 5-smooth half length with 8 | n (unknown variant), or two Bluestein factors.
  * Pinned against the installed scipy for every even length in (1000, 3400) by tests/test_oracle.py.  One known gap inside
  * class 1: when 8 divides the half length, the rows scipy processes outside its 4-wide SIMD batches (the last rows % 4
  * rows of an array) round differently from the SIMD rows; this file (and the GPU) reproduce the SIMD rows. */
@@ -1359,12 +1403,12 @@ int orc_fft_class(size_t n)
 {
     if (n < 1) return -1;
     if (n <= 1000 || (n & 1)) return 0;
-    size_t h = n / 2, big = 1;
+    size_t h = n / 2, big = 1, n_blue = 0;
     for (size_t p = 2; p * p <= h; ++p)
-        while (h % p == 0) { if (p > big) big = p; h /= p; }
-    if (h > 1 && h > big) big = h;
+        while (h % p == 0) { if (p > big) big = p; if (p >= 110) ++n_blue; h /= p; }
+    if (h > 1) { if (h > big) big = h; if (h >= 110) ++n_blue; }
     if (big <= 5) return (n % 8) ? 0 : (orc_allow_all ? 1 : -1);
-    return big < 110 ? 1 : -1;
+    return (n_blue <= 1 || orc_allow_all) ? 1 : -1;
 }
 int orc_fft_mirrored(size_t n) { return orc_fft_class(n) >= 0; }
 

@@ -207,7 +207,7 @@ def test_fft_restatement_is_bit_identical_to_scipy_fftpack(lengths):
 
 def test_fft_restatement_even_lengths_above_1000():
     """ducc0 runs even lengths > 1000 as a half-length complex transform; the restatement (and the GPU mirror of it)
-    covers the half lengths with a prime factor in [7, 109].  Pinned on the 4-wide SIMD rows scipy processes (8 rows),
+    covers every half length with a prime factor >= 7 (generic radices, Bluestein pass for factors >= 110).  Pinned on the 4-wide SIMD rows scipy processes (8 rows),
     which is what a sub-band with > 1000 rows consists of; the production db9 lengths are checked on leftover rows too."""
     import ctypes
     from scipy.fftpack import irfft, rfft
