@@ -12,8 +12,8 @@
 // Layout: a CTA holds G sequences ("rows") in shared memory, element e of row r at (e * GP + r), GP = G + 1, so
 //   * the global gather/scatter (consecutive e) and the passes (consecutive r) are both bank-conflict free,
 //   * a warp works on 32/G butterflies x G rows: index arithmetic and twiddle loads are (nearly) warp-uniform.
-// Even lengths > 1000 (ducc0 switches to a half-length complex transform there) are not covered; the caller falls
-// back to k_notch (fft.cu), which is within 1 LSB but not rounding-identical.
+// Even lengths > 1000 whose half length has a prime factor >= 7 run, as in ducc0, as a half-length complex transform
+// (k_notch_cplx below: complex radices 2,3,4,5,7,8,11, generic, Bluestein).  k_notch (fft.cu) remains for exact=0.
 #include <cmath>
 #include <cstdio>
 #include <vector>
@@ -1316,9 +1316,12 @@ std::vector<int> prime_factors(int n)
     if (n > 1) f.push_back(n);
     return f;
 }
-// how scipy's (ducc0) float32 r2r transform of length n is evaluated: 0 = real passes (rfftp, Bluestein passes for prime
-// factors >= 135), 1 = half-length complex transform (rfftp_complexify), -1 = a variant that is not mirrored here.
+// how scipy's (ducc0) float32 r2r transform of length n is evaluated on the rows of its 4-wide SIMD batches: 0 = real
+// passes (rfftp, Bluestein passes for prime factors >= 135), 1 = half-length complex transform (rfftp_complexify, even
+// lengths > 1000 whose half length has a prime factor >= 7), -1 = not mirrored (two Bluestein factors).
 // Classification pinned empirically against scipy 1.18 for every even length in (1000, 3400): tests/test_oracle.py.
+// The at most 3 rows of a sub-band that scipy processes outside its SIMD batches round differently when 8 divides the
+// half length; they are evaluated like the others here (oracle/pocketfft_c.c header).
 int xfft_class(int n)
 {
     if (n < 2) return -1;
@@ -1326,7 +1329,7 @@ int xfft_class(int n)
     const std::vector<int> f = prime_factors(n / 2);
     int big = 0;
     for (int p : f) big = std::max(big, p);
-    if (big <= 5) return (n % 8) ? 0 : -1;      // 5-smooth half length: plain real passes unless 8 | n (unknown variant)
+    if (big <= 5) return 0;                      // 5-smooth half length: plain real passes
     int n_blue = 0;
     for (int p : f) n_blue += p >= 110;          // prime factors >= 110 run as complex Bluestein passes (one supported)
     return n_blue <= 1 ? 1 : -1;

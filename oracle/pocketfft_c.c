@@ -141,6 +141,8 @@ size_t orc_pf_good_size(size_t n) { return good_size_cmplx(n); }
 typedef struct { size_t fct; float *tw, *tws; } rfct;
 typedef struct { size_t length, nfct; rfct fct[MAXFACT]; float *mem; } rfftp_t;
 
+static size_t orc_ovr_r[MAXFACT], orc_ovr_rn = 0, orc_ovr_c[MAXFACT], orc_ovr_cn = 0;
+void orc_override_factors(int real, const size_t *f, size_t nf) { if (real) { orc_ovr_rn = nf; for (size_t i = 0; i < nf; ++i) orc_ovr_r[i] = f[i]; } else { orc_ovr_cn = nf; for (size_t i = 0; i < nf; ++i) orc_ovr_c[i] = f[i]; } }
 static void rfftp_init(rfftp_t *p, size_t length)
 {
     p->length = length;
@@ -157,6 +159,7 @@ static void rfftp_init(rfftp_t *p, size_t length)
     for (size_t divisor = 3; divisor * divisor <= len; divisor += 2)
         while ((len % divisor) == 0) { p->fct[p->nfct++].fct = divisor; len /= divisor; }
     if (len > 1) p->fct[p->nfct++].fct = len;
+    if (orc_ovr_rn) { p->nfct = orc_ovr_rn; for (size_t i = 0; i < orc_ovr_rn; ++i) p->fct[i].fct = orc_ovr_r[i]; }
     /* twiddles */
     size_t twsz = 0, l1 = 1;
     for (size_t k = 0; k < p->nfct; ++k) {
@@ -710,6 +713,7 @@ static int cfftp_init(cfftp_t *p, size_t length)
     for (size_t divisor = 3; divisor * divisor <= len; divisor += 2)
         while ((len % divisor) == 0) { p->fct[p->nfct++].fct = divisor; len /= divisor; }
     if (len > 1) p->fct[p->nfct++].fct = len;
+    if (orc_ovr_cn) { size_t pr = 1; for (size_t i = 0; i < orc_ovr_cn; ++i) pr *= orc_ovr_c[i]; if (pr == length) { p->nfct = orc_ovr_cn; for (size_t i = 0; i < orc_ovr_cn; ++i) p->fct[i].fct = orc_ovr_c[i]; } }
     size_t twsz = 0, l1 = 1;
     for (size_t k = 0; k < p->nfct; ++k) {
         size_t ip = p->fct[k].fct, ido = length / (l1 * ip);
@@ -1388,26 +1392,29 @@ static int complexify_exec(float *c, size_t N, float fct, int fwd)
 }
 
 /* ================================================================ pocketfft_r<float> + r2r_fftpack */
-/* How scipy (ducc0) evaluates the float32 r2r transform of length n, as far as it is restated here:
+/* How scipy (ducc0) evaluates the float32 r2r transform of length n (rows processed in its 4-wide SIMD batches):
  *   0  real passes (rfftp; Bluestein passes for prime factors >= 135): every odd or <= 1000 length, and even lengths
- *      > 1000 whose half is 5-smooth when 8 does not divide n;
+ *      > 1000 whose half length is 5-smooth;
  *   1  half-length complex transform (rfftp_complexify): even lengths > 1000 whose half length has a prime factor >= 7
  *      (generic complex radices below 110, a complex Bluestein pass for a prime factor >= 110);
- *  -1  not restated: 5-smooth half length with 8 | n (unknown variant), or two Bluestein factors.
- * Pinned against the installed scipy for every even length in (1000, 3400) by tests/test_oracle.py.  One known gap inside
- * class 1: when 8 divides the half length, the rows scipy processes outside its 4-wide SIMD batches (the last rows % 4
- * rows of an array) round differently from the SIMD rows; this file (and the GPU) reproduce the SIMD rows. */
-static int orc_allow_all = 0;
+ *  -1  not restated: two Bluestein factors (lengths beyond 36 000).
+ * Pinned against the installed scipy for every even length in (1000, 3400) by tests/test_oracle.py.  Known gap: the rows
+ * scipy processes outside its SIMD batches (the last rows % 4 rows of an array) take another route when 8 divides the
+ * half length (class 1) or the length (5-smooth, class 0) and round differently; this file and the GPU reproduce the
+ * SIMD rows, i.e. all but at most 3 rows of a sub-band. */
+static int orc_allow_all = 0, orc_force_class = -2;
+void orc_fft_force_class(int c) { orc_force_class = c; }
 void orc_fft_allow_all(int v) { orc_allow_all = v; }
 int orc_fft_class(size_t n)
 {
+    if (orc_force_class > -2) return orc_force_class;
     if (n < 1) return -1;
     if (n <= 1000 || (n & 1)) return 0;
     size_t h = n / 2, big = 1, n_blue = 0;
     for (size_t p = 2; p * p <= h; ++p)
         while (h % p == 0) { if (p > big) big = p; if (p >= 110) ++n_blue; h /= p; }
     if (h > 1) { if (h > big) big = h; if (h >= 110) ++n_blue; }
-    if (big <= 5) return (n % 8) ? 0 : (orc_allow_all ? 1 : -1);
+    if (big <= 5) return 0;
     return (n_blue <= 1 || orc_allow_all) ? 1 : -1;
 }
 int orc_fft_mirrored(size_t n) { return orc_fft_class(n) >= 0; }

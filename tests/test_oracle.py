@@ -189,8 +189,7 @@ def _fft_lib():
                                      [1001, 1029, 1327, 1333, 1337, 1341, 2047, 2187, 3251]])
 def test_fft_restatement_is_bit_identical_to_scipy_fftpack(lengths):
     """oracle/pocketfft_c.c (the pass structure the GPU mirrors) against the scipy.fftpack the reference calls
-    (core.py:751,753): every bit, forward and inverse, rows vectorised and not; even lengths > 1000 are declared
-    outside the restatement (return code 1)."""
+    (core.py:751,753): every bit, forward and inverse, rows vectorised and not."""
     import ctypes
     from scipy.fftpack import irfft, rfft
     L = _fft_lib()
@@ -201,8 +200,6 @@ def test_fft_restatement_is_bit_identical_to_scipy_fftpack(lengths):
             y = x.copy()
             rc = L.orc_fftpack_r2r_f32(ctypes.c_void_p(y.ctypes.data), ctypes.c_size_t(6), ctypes.c_size_t(n), ctypes.c_int(fwd))
             assert rc == 0 and np.array_equal(ref.view(np.uint32), y.view(np.uint32)), (n, fwd)
-    y = np.zeros((1, 1024), np.float32)        # 5-smooth half length with 8 | n: declared outside the restatement
-    assert L.orc_fftpack_r2r_f32(ctypes.c_void_p(y.ctypes.data), ctypes.c_size_t(1), ctypes.c_size_t(1024), ctypes.c_int(1)) == 1
 
 
 def test_fft_restatement_even_lengths_above_1000():
