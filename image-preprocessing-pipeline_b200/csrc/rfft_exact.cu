@@ -1321,7 +1321,7 @@ std::vector<int> prime_factors(int n)
 // lengths > 1000 whose half length has a prime factor >= 7), -1 = not mirrored (two Bluestein factors).
 // Classification pinned empirically against scipy 1.18 for every even length in (1000, 3400): tests/test_oracle.py.
 // The at most 3 rows of a sub-band that scipy processes outside its SIMD batches round differently when 8 divides the
-// half length; they are evaluated like the others here (oracle/pocketfft_c.c header).
+// half length; they are evaluated like the others here.
 int xfft_class(int n)
 {
     if (n < 2) return -1;
