@@ -251,7 +251,7 @@ struct b2s_plan {
         void *d_in = nullptr, *d_out = nullptr;
         void *pre_a = nullptr, *pre_b = nullptr;   // pre-op temporaries
         void *mid = nullptr;                       // lightsheet: post-dark image
-        unsigned short *ls_grid = nullptr, *bg_grid = nullptr;
+        unsigned short *ls_grid = nullptr, *bg_grid = nullptr, *ls_cells = nullptr;
         unsigned *mm = nullptr;
         void *h_in = nullptr, *h_out = nullptr;    // pinned staging
         cudaStream_t stream = nullptr;
@@ -460,6 +460,8 @@ int alloc_slot(b2s_plan *pl, int si)
         if ((rc = dev_alloc(pl, &s.mid, work_elems * 4 * B))) return rc;
         if ((rc = dev_alloc(pl, (void **)&s.ls_grid, sizeof(unsigned short) * b2s_lightsheet_grid_elems(pl->ls, 0) * B))) return rc;
         if ((rc = dev_alloc(pl, (void **)&s.bg_grid, sizeof(unsigned short) * b2s_lightsheet_grid_elems(pl->ls, 1) * B))) return rc;
+        if (b2s_lightsheet_grid_elems(pl->ls, 2) &&
+            (rc = dev_alloc(pl, (void **)&s.ls_cells, sizeof(unsigned short) * b2s_lightsheet_grid_elems(pl->ls, 2) * B))) return rc;
     }
     CU(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -612,8 +614,8 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             m.out = s.mid; m.out_rows = g.work_rows; m.out_cols = g.work_cols;
             b2s_launch_epilogue(m, nb, st);
             // stage 2: percentile grids, zoom, subtraction, final conversion
-            ClassTimer t2(ctx, st, B2S_K_LIGHTSHEET, 3);
-            b2s_launch_lightsheet(pl->ls, s.mid, s.ls_grid, s.bg_grid, e, nb, st);
+            ClassTimer t2(ctx, st, B2S_K_LIGHTSHEET, s.ls_cells ? 4 : 3);
+            b2s_launch_lightsheet(pl->ls, s.mid, s.ls_grid, s.bg_grid, s.ls_cells, e, nb, st);
         }
     }
     CU(ctx, cudaGetLastError());

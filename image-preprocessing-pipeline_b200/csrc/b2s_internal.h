@@ -126,7 +126,7 @@ const char *b2s_lightsheet_check(int rows, int cols, int artifact_length, int wi
 B2sLightsheet *b2s_lightsheet_create(int rows, int cols, int dtype, int artifact_length, int window, double percentile,
                                      double weight, int weight_is_float);
 void b2s_lightsheet_destroy(B2sLightsheet *L);
-size_t b2s_lightsheet_grid_elems(const B2sLightsheet *L, int which /*0 ls, 1 bg*/);
+size_t b2s_lightsheet_grid_elems(const B2sLightsheet *L, int which /*0 ls grid, 1 bg grid, 2 sorted cell lists*/);
 // mid: post-dark image in the lightsheet plan's dtype; e carries the final conversion / orientation / output
 void b2s_launch_lightsheet(const B2sLightsheet *L, const void *mid, unsigned short *ls_grid, unsigned short *bg_grid,
-                           const B2sEpilogueArgs &e, int n_planes, cudaStream_t s);
+                           unsigned short *cell_lists, const B2sEpilogueArgs &e, int n_planes, cudaStream_t s);
