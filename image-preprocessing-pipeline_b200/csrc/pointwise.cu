@@ -361,33 +361,41 @@ __global__ void __launch_bounds__(256) k_gauss5_u16(const uint16_t *in, uint16_t
 // (SymmRowSmallVec_32f / SymmColumnVec_32f); its scalar tail columns and non-FMA builds round differently, so cv2's
 // own float output is position- and CPU-dependent in the last bit.  This kernel is the vector-body formula everywhere:
 // within 2.4e-7 relative of cv2 (tests assert 1e-6), not bit-pinned.
+// tile: 32 x 64 outputs per CTA; the horizontal pass of the 36 rows it needs goes to shared memory, the vertical pass reads it
 __global__ void __launch_bounds__(256) k_gauss5_f32(const float *in, float *out, int rows, int cols)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    if (x >= cols) return;
+    __shared__ float sh[36][64];
+    const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 32;
     const size_t plane = (size_t)blockIdx.z * rows * cols;
     const float k0 = 0.40261996f, k1 = 0.24420135f, k2 = 0.05448868f;
-    const bool interior = x >= 2 && x + 2 < cols && y >= 2 && y + 2 < rows;   // no index reflection needed
-    int xs[5], ys[5];
-#pragma unroll
-    for (int d = 0; d < 5; ++d) {
-        xs[d] = interior ? x + d - 2 : reflect101(x + d - 2, cols);
-        ys[d] = interior ? y + d - 2 : reflect101(y + d - 2, rows);
+    const int tx = threadIdx.x & 63, tr = threadIdx.x >> 6;   // 4 row lanes
+    const int x = x0 + tx;
+    if (x < cols) {
+        const bool xin = x >= 2 && x + 2 < cols;
+        const int xm2 = xin ? x - 2 : reflect101(x - 2, cols), xm1 = xin ? x - 1 : reflect101(x - 1, cols);
+        const int xp1 = xin ? x + 1 : reflect101(x + 1, cols), xp2 = xin ? x + 2 : reflect101(x + 2, cols);
+#pragma unroll 3
+        for (int r = tr; r < 36; r += 4) {
+            int y = y0 + r - 2;
+            if (y < 0 || y >= rows) y = reflect101(y, rows);
+            const float *row = in + plane + (size_t)y * cols;
+            float s = __fmul_rn(k0, __ldg(row + x));
+            s = __fmaf_rn(k1, __fadd_rn(__ldg(row + xm1), __ldg(row + xp1)), s);
+            s = __fmaf_rn(k2, __fadd_rn(__ldg(row + xm2), __ldg(row + xp2)), s);
+            sh[r][tx] = s;
+        }
     }
-    float h[5];
-#pragma unroll
-    for (int dy = 0; dy < 5; ++dy) {
-        const float *row = in + plane + (size_t)ys[dy] * cols;
-        float s = __fmul_rn(k0, __ldg(row + xs[2]));
-        s = __fmaf_rn(k1, __fadd_rn(__ldg(row + xs[1]), __ldg(row + xs[3])), s);
-        s = __fmaf_rn(k2, __fadd_rn(__ldg(row + xs[0]), __ldg(row + xs[4])), s);
-        h[dy] = s;
+    __syncthreads();
+    if (x >= cols) return;
+#pragma unroll 2
+    for (int r = tr; r < 32; r += 4) {
+        const int y = y0 + r;
+        if (y >= rows) break;
+        float v = __fmul_rn(k0, sh[r + 2][tx]);
+        v = __fmaf_rn(k1, __fadd_rn(sh[r + 1][tx], sh[r + 3][tx]), v);
+        v = __fmaf_rn(k2, __fadd_rn(sh[r][tx], sh[r + 4][tx]), v);
+        out[plane + (size_t)y * cols + x] = v;
     }
-    float v = __fmul_rn(k0, h[2]);
-    v = __fmaf_rn(k1, __fadd_rn(h[1], h[3]), v);
-    v = __fmaf_rn(k2, __fadd_rn(h[0], h[4]), v);
-    out[plane + (size_t)y * cols + x] = v;
 }
 
 // skimage.measure.block_reduce with cval=0 padding of the trailing edges.  max/min keep the dtype; mean of an
@@ -494,7 +502,7 @@ void b2s_launch_gauss5_u16(const uint16_t *in, uint16_t *out, int rows, int cols
 
 void b2s_launch_gauss5_f32(const float *in, float *out, int rows, int cols, int n_planes, cudaStream_t s)
 {
-    k_gauss5_f32<<<dim3((cols + 255) / 256, rows, n_planes), 256, 0, s>>>(in, out, rows, cols);
+    k_gauss5_f32<<<dim3((cols + 63) / 64, (rows + 31) / 32, n_planes), 256, 0, s>>>(in, out, rows, cols);
 }
 
 void b2s_launch_block_reduce(const void *in, int dtype, int rows, int cols, int by, int bx, int method, void *out,
