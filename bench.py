@@ -282,9 +282,18 @@ def run_b200(a):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
                 "planes_per_launch": nb_per_launch, "share_of_step": round(kms / total, 4),
+                "largest_mover": None,
                 "whole_pipeline": {"algorithmic_bytes_per_plane": int(info.algorithmic_bytes_per_plane),
                                    "achieved_GBps": info.algorithmic_bytes_per_plane * a.steps * P / (ms_max * 1e-3) / 1e9,
                                    "frac": info.algorithmic_bytes_per_plane * a.steps * P / (ms_max * 1e-3) / 1e9 / peak}}
+
+    # the kernel that moves the most bytes (forward DWT level 1), for the HBM view of the same run
+    if roof is not None and ("dwt_fwd", 1) in tm:
+        kms1, kn1 = tm[("dwt_fwd", 1)]
+        per_plane1 = 4 * rows[0] * cols[0] + 16 * rows[1] * cols[1]
+        ach1 = per_plane1 * (2 * P) / (kms1 * 1e-3) / 1e9
+        roof["largest_mover"] = {"kernel": "dwt_fwd@level1", "achieved": ach1, "frac": ach1 / peak,
+                                 "algorithmic_bytes_per_plane": per_plane1, "share_of_step": round(kms1 / total, 4)}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample
     cpu = None

@@ -380,6 +380,32 @@ def test_full_size_property_columns_only_image_is_a_fixed_point():
     assert np.array_equal(out, img)
 
 
+def test_batch_filter_step3_call_on_tiff_files(tmp_path):
+    """the call process_images.py:420 makes (db9, reflect, bidirectional, uint16 out) on a small tile directory, plus
+    dark and flat: files in, files out, every plane identical to the oracle's process_img."""
+    from pystripe import core
+    src, dst = tmp_path / "in", tmp_path / "out"
+    (src / "ch0").mkdir(parents=True)
+    flat = synth.flat_field((96, 120))
+    planes = {}
+    for z in range(11):
+        img = synth.plane(30 + z, (96, 120))
+        if z == 4:
+            img[:] = 123                                    # uniform plane -> zeros
+        core.imsave_tif(src / "ch0" / f"img_{z:05d}.tif", img, compression=None)
+        planes[f"ch0/img_{z:05d}.tif"] = img
+    kw = dict(sigma=(16, 16), level=0, wavelet="db9", padding_mode="reflect", bidirectional=True, dark=105)
+    rc = core.batch_filter(src, dst, workers=4, threads_per_gpu=4, flat=flat, d_type="uint16", compression=None, **kw)
+    assert rc == 0
+    nflat = orc.normalize_flat(flat)
+    for name, img in planes.items():
+        got = core.imread_tif_raw_png(dst / name)
+        ref = orc.process_img(img.copy(), flat=nflat, d_type=np.dtype("uint16"), **kw)
+        assert got.dtype == np.uint16 and np.array_equal(got, ref), name
+    # continue_process skips what exists
+    assert core.batch_filter(src, dst, workers=2, flat=flat, d_type="uint16", continue_process=True, **kw) == 0
+
+
 def test_zz_write_parity_report():
     out = ROOT / "gpurun_out"
     out.mkdir(exist_ok=True)
