@@ -369,6 +369,17 @@ def test_full_size_plane_against_oracle():
     _cmp_int("config1/2048", got, ref)
 
 
+def test_large_non_square_plane_against_oracle():
+    """beyond the benchmark size: 3000 x 4096, the production wavelet, both axes filtered (sub-band sides 1655 x 2203,
+    i.e. a Bluestein factor 331 and the prime 2203), batch of two planes."""
+    from pystripe import core
+    stack = np.stack([synth.plane(40, (3000, 4096)), synth.plane(41, (3000, 4096))])
+    kw = dict(sigma=(250, 250), wavelet="db9", padding_mode="reflect", bidirectional=True)
+    got = core.filter_streaks(stack, **kw)
+    ref = orc.filter_streaks(stack[1], **kw)
+    _cmp_int("large/3000x4096", got[1], ref)
+
+
 def test_full_size_property_columns_only_image_is_a_fixed_point():
     """size-independent property: an image that is constant along y has cH == 0 at every level, so the destripe must
     return it unchanged (the float32 wavelet round trip is far below half an LSB)."""
