@@ -82,12 +82,17 @@ void b2s_launch_log1p_lut(float *lut, int n, cudaStream_t s);
 // dwt.cu --------------------------------------------------------------------------------------------------------
 // forward level: in (ny x nx) -> cA,cH,cV,cD ((ny+F-1)/2 x (nx+F-1)/2); exact!=0 => reference summation order, no FMA
 void b2s_launch_dwt_fwd(const B2sTaps &t, const B2sImg &in, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV,
-                        const B2sImg &cD, int n_planes, int exact, int sm_count, cudaStream_t s);
+                        const B2sImg &cD, int n_planes, int exact, int sm_count, cudaStream_t s, float *scratch = nullptr,
+                        size_t scratch_plane_stride = 0);
 // inverse level: sub-bands (my x mx; cA is read with that logical size) -> out (first out.rows x out.cols of the
 // 2*my-F+2 x 2*mx-F+2 reconstruction)
 void b2s_launch_dwt_inv(const B2sTaps &t, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV, const B2sImg &cD,
-                        const B2sImg &out, int n_planes, int exact, int sm_count, cudaStream_t s);
+                        const B2sImg &out, int n_planes, int exact, int sm_count, cudaStream_t s, float *scratch = nullptr,
+                        size_t scratch_plane_stride = 0);
 int b2s_dwt_max_smem(int F);
+// long filters (F >= 42) run one kernel per axis through a scratch buffer: floats per plane for a level whose input is
+// ny x nx (0: the fused kernels are used); the level-1 figure covers every level
+size_t b2s_dwt_scratch_floats(int F, int ny, int nx);
 
 // fft.cu --------------------------------------------------------------------------------------------------------
 struct B2sFftPlan {      // per sequence length n

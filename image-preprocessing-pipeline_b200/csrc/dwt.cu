@@ -600,6 +600,282 @@ __global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTa
     }
 }
 
+// ================================================================================================ long filters
+// F > 40 (coif7..17, db21..38, sym21+): the fused 2-D tile above would carry a (2TX+F-2)/(2TX) halo through its first
+// pass and fit one CTA per SM.  Here each axis is its own kernel: no output is computed twice, three CTAs fit an SM, and
+// the half-height / half-width intermediates (lo, hi / a, d) go through a per-slot scratch buffer (L2 / HBM), which
+// is cheap next to the 2F multiply-adds per sample.  Arithmetic is the chunked exact path of analysis_run /
+// synthesis_run.  The zero taps that pad the filter to a whole number of chunks sit in FRONT of the real taps (a sum
+// that starts at +0 is unchanged by adding +-0 products first), chosen so that every tile window starts on a 16-byte
+// boundary of the source rows.
+struct FwdLongArgs {
+    B2sImg in, lo, hi, cA, cH, cV, cD;
+    int F, Fp, nch, shift;   // shift = number of leading zero taps
+    float negzero;
+};
+struct InvLongArgs {
+    B2sImg cA, cH, cV, cD, a, d, out;
+    int H, Hp, nch, shift;
+    float negzero;
+};
+
+__device__ __forceinline__ float2 analysis_right_edge_p(const float2 *__restrict__ taps, int F, const float *w0, int step, int over)
+{
+    float lo = 0.f, hi = 0.f;
+#pragma unroll 1
+    for (int t = 0; t < F; ++t) {
+        const int j = (t <= over) ? (over - t) : t;
+        const float2 f = taps[j];
+        const float v = w0[-j * step];
+        lo = mac1_exact(lo, f.x, v);
+        hi = mac1_exact(hi, f.y, v);
+    }
+    return make_float2(lo, hi);
+}
+
+constexpr int kLongNT = 256;
+// forward, axis -2: TY output rows x TC columns per CTA; a thread owns RY consecutive output rows of one column
+constexpr int kFyTY = 64, kFyTC = 64, kFyR = 8;
+// forward, axis -1: TR rows of lo and of hi x TX outputs per CTA
+constexpr int kFxTR = 16, kFxTX = 128, kFxR = 8;
+// inverse, axis -1: TR coefficient rows (both pairs) x TP coefficient columns -> 2 TP outputs
+constexpr int kIxTR = 8, kIxTP = 128, kIxR = 4;
+// inverse, axis -2: TQ coefficient rows x TC columns -> 2 TQ output rows
+constexpr int kIyTQ = 64, kIyTC = 64, kIyR = 4;
+
+template <int J, int MODE>
+__global__ void __launch_bounds__(kLongNT) k_dwt_fwd_y_long(const __grid_constant__ FwdTaps taps, const FwdLongArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    constexpr int TY = kFyTY, TC = kFyTC, RY = kFyR, NT = kLongNT, NW = NT / 32;
+    const int Fp = a.Fp;
+    const int rin_y = 2 * TY + Fp - 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ny = a.in.rows, nx = a.in.cols, my = a.lo.rows;
+    const int plane = blockIdx.z, oy0 = blockIdx.y * TY, x0 = blockIdx.x * TC;
+    const int gy0 = 2 * oy0 + 2 - Fp + a.shift;
+    const float2 nz = make_float2(a.negzero, a.negzero);
+    const float *src = a.in.ptr + (size_t)plane * a.in.plane_stride;
+    for (int idx = tid; idx < rin_y * (TC / 4); idx += NT) {
+        const int r = idx / (TC / 4), q = idx % (TC / 4);
+        const int gx = x0 + 4 * q;
+        if (gx < a.in.pitch) cp_async16(smem + r * TC + 4 * q, src + (size_t)sym_ext(gy0 + r, ny) * a.in.pitch + gx);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const bool edge_y = 2 * (oy0 + TY) - 1 >= ny;
+    float *plo = a.lo.ptr + (size_t)plane * a.lo.plane_stride, *phi = a.hi.ptr + (size_t)plane * a.hi.plane_stride;
+    constexpr int NCG = TC / 32;
+    for (int wi = warp; wi < (TY / RY) * NCG; wi += NW) {
+        const int gy = wi / NCG, col_idx = (wi % NCG) * 32 + lane;
+        const float *col = smem + (2 * RY * gy) * TC + col_idx;
+        float2 acc[RY];
+        analysis_run<RY, J, true, MODE, false>(col, TC, taps.t, a.nch, Fp, nz, acc);
+        if (MODE == kExact && edge_y) {
+#pragma unroll
+            for (int r = 0; r < RY; ++r) {
+                const int i = 2 * (oy0 + RY * gy + r) + 1;
+                if (i >= ny && i - ny <= a.F - 2)
+                    acc[r] = analysis_right_edge_p(taps.t + a.shift, a.F, col + (2 * r + Fp - 1 - a.shift) * TC, TC, i - ny);
+            }
+        }
+        const int x = x0 + col_idx;
+        if (x < nx) {
+#pragma unroll
+            for (int r = 0; r < RY; ++r) {
+                const int oy = oy0 + RY * gy + r;
+                if (oy < my) {
+                    plo[(size_t)oy * a.lo.pitch + x] = acc[r].x;
+                    phi[(size_t)oy * a.hi.pitch + x] = acc[r].y;
+                }
+            }
+        }
+    }
+}
+
+template <int J, int MODE>
+__global__ void __launch_bounds__(kLongNT) k_dwt_fwd_x_long(const __grid_constant__ FwdTaps taps, const FwdLongArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    constexpr int TR = kFxTR, TX = kFxTX, RX = kFxR, NT = kLongNT, NW = NT / 32;
+    const int Fp = a.Fp;
+    const int rin_x = 2 * TX + Fp - 2;
+    const int PM = pitch_quads_odd(rin_x + 2);
+    const int c4n = (rin_x + 3) >> 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nx = a.lo.cols, my = a.cA.rows, mx = a.cA.cols;
+    const int plane = blockIdx.z, oy0 = blockIdx.y * TR, ox0 = blockIdx.x * TX;
+    const int gx0 = 2 * ox0 + 2 - Fp + a.shift;
+    const bool aligned = (gx0 & 3) == 0;
+    const float2 nz = make_float2(a.negzero, a.negzero);
+    const float *slo = a.lo.ptr + (size_t)plane * a.lo.plane_stride, *shi = a.hi.ptr + (size_t)plane * a.hi.plane_stride;
+    for (int idx = tid; idx < 2 * TR * c4n; idx += NT) {
+        const int rm = idx / c4n, c4 = idx - rm * c4n;
+        const int oy = oy0 + (rm % TR);
+        if (oy >= my) continue;   // rows beyond the sub-band only feed outputs that are not stored
+        const float *srow = (rm < TR ? slo : shi) + (size_t)oy * a.lo.pitch;
+        const int gx = gx0 + 4 * c4;
+        float *dst = smem + rm * PM + 4 * c4;
+        if (aligned && gx >= 0 && gx + 3 < nx) {
+            cp_async16(dst, srow + gx);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cp_async4(dst + k, srow + sym_ext(gx + k, nx));
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const bool edge_x = 2 * (ox0 + TX) - 1 >= nx;
+    constexpr int GPW = 2, RPW = 16;           // RX = 8: a warp covers 16 rows x 2 column groups (PM/4 odd: conflict-free)
+    const int gxl = lane % GPW, rsub = lane / GPW;
+    constexpr int N_GB = TX / RX / GPW;
+    constexpr int N_RB = (2 * TR) / RPW;
+    float *pA = a.cA.ptr + (size_t)plane * a.cA.plane_stride;
+    float *pH = a.cH.ptr + (size_t)plane * a.cH.plane_stride;
+    float *pV = a.cV.ptr + (size_t)plane * a.cV.plane_stride;
+    float *pD = a.cD.ptr + (size_t)plane * a.cD.plane_stride;
+    for (int wi = warp; wi < N_RB * N_GB; wi += NW) {
+        const int rb = wi / N_GB, gb = wi - rb * N_GB;
+        const int rm = rb * RPW + rsub;
+        const int gx = gb * GPW + gxl;
+        const float *row = smem + rm * PM + 2 * RX * gx;
+        float2 acc[RX];
+        analysis_run<RX, J, true, MODE, true>(row, 1, taps.t, a.nch, Fp, nz, acc);
+        const int oxb = ox0 + RX * gx;
+        if (MODE == kExact && edge_x) {
+#pragma unroll
+            for (int cc = 0; cc < RX; ++cc) {
+                const int i = 2 * (oxb + cc) + 1;
+                if (i >= nx && i - nx <= a.F - 2)
+                    acc[cc] = analysis_right_edge_p(taps.t + a.shift, a.F, row + 2 * cc + Fp - 1 - a.shift, 1, i - nx);
+            }
+        }
+        const bool low_rows = rm < TR;
+        const int oy = oy0 + (low_rows ? rm : rm - TR);
+        if (oy < my) {
+            const size_t o = (size_t)oy * a.cA.pitch + oxb;
+            float *d0 = (low_rows ? pA : pH) + o, *d1 = (low_rows ? pV : pD) + o;
+#pragma unroll
+            for (int h = 0; h < RX / 4; ++h) {
+                if (oxb + 4 * h < mx) {
+                    *reinterpret_cast<float4 *>(d0 + 4 * h) =
+                        make_float4(acc[4 * h].x, acc[4 * h + 1].x, acc[4 * h + 2].x, acc[4 * h + 3].x);
+                    *reinterpret_cast<float4 *>(d1 + 4 * h) =
+                        make_float4(acc[4 * h].y, acc[4 * h + 1].y, acc[4 * h + 2].y, acc[4 * h + 3].y);
+                }
+            }
+        }
+    }
+}
+
+template <int JH, int MODE>
+__global__ void __launch_bounds__(kLongNT) k_dwt_inv_x_long(const __grid_constant__ InvTaps taps, const InvLongArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    constexpr int TR = kIxTR, TP = kIxTP, RX = kIxR, NT = kLongNT, NW = NT / 32;
+    const int Hp = a.Hp;
+    const int rp = TP + Hp - 1;
+    const int PS = pitch_quads_4mod8(rp);
+    const int c4n = (rp + 3) >> 2;
+    const int sub_floats = TR * PS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int my = a.cH.rows, mx = a.cH.cols;
+    const int plane = blockIdx.z, q0 = blockIdx.y * TR, p0 = blockIdx.x * TP;
+    const int cx0 = p0 + a.H - Hp + a.shift;
+    const bool aligned = (cx0 & 3) == 0;
+    const float2 nz = make_float2(a.negzero, a.negzero);
+    // [cA, cV, cH, cD][TR][PS]; everything outside the sub-band is zero
+    for (int idx = tid; idx < 4 * TR * c4n; idx += NT) {
+        const int row = idx / c4n, c4 = idx - row * c4n;
+        const int sb = row / TR, ry = row - sb * TR;
+        const int y = q0 + ry;
+        const B2sImg &im = sb == 0 ? a.cA : (sb == 1 ? a.cV : (sb == 2 ? a.cH : a.cD));
+        float *dst = smem + sb * sub_floats + ry * PS + 4 * c4;
+        const bool row_ok = y < my;
+        const float *srow = im.ptr + (size_t)plane * im.plane_stride + (size_t)(row_ok ? y : 0) * im.pitch;
+        const int x = cx0 + 4 * c4;
+        if (row_ok && aligned && x >= 0 && x + 3 < mx) {
+            cp_async16(dst, srow + x);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (row_ok && x + k >= 0 && x + k < mx) cp_async4(dst + k, srow + x + k);
+                else dst[k] = 0.f;
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int gxl = lane & 3, rsub = lane >> 2;
+    constexpr int N_GB = TP / RX / 4;
+    constexpr int N_RB = (2 * TR) / 8;
+    for (int wi = warp; wi < N_RB * N_GB; wi += NW) {
+        const int rb = wi / N_GB, gb = wi - rb * N_GB;
+        const int rr = rb * 8 + rsub;
+        const int sel = rr >= TR ? 1 : 0;
+        const int ry = rr - sel * TR;
+        const int gx = gb * 4 + gxl;
+        const float *rl = smem + (2 * sel) * sub_floats + ry * PS + RX * gx;
+        const float *rh = rl + sub_floats;
+        float2 o[RX];
+        synthesis_run<RX, JH, true, MODE, true>(rl, rh, 1, taps.lo, taps.hi, a.nch, Hp, nz, o);
+        const int y = q0 + ry, xo = 2 * (p0 + RX * gx);
+        if (y < my) {
+            const B2sImg &dimg = sel ? a.d : a.a;
+            float *dst = dimg.ptr + (size_t)plane * dimg.plane_stride + (size_t)y * dimg.pitch + xo;
+#pragma unroll
+            for (int h = 0; h < RX / 2; ++h)
+                if (xo + 4 * h < dimg.pitch)
+                    *reinterpret_cast<float4 *>(dst + 4 * h) = make_float4(o[2 * h].x, o[2 * h].y, o[2 * h + 1].x, o[2 * h + 1].y);
+        }
+    }
+}
+
+template <int JH, int MODE>
+__global__ void __launch_bounds__(kLongNT) k_dwt_inv_y_long(const __grid_constant__ InvTaps taps, const InvLongArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    constexpr int TQ = kIyTQ, TC = kIyTC, RY = kIyR, NT = kLongNT, NW = NT / 32;
+    const int Hp = a.Hp;
+    const int rq = TQ + Hp - 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int my = a.a.rows;
+    const int plane = blockIdx.z, q0 = blockIdx.y * TQ, x0 = blockIdx.x * TC;
+    const int cy0 = q0 + a.H - Hp + a.shift;
+    const float2 nz = make_float2(a.negzero, a.negzero);
+    float *s_a = smem, *s_d = smem + rq * TC;
+    const float *ga = a.a.ptr + (size_t)plane * a.a.plane_stride, *gd = a.d.ptr + (size_t)plane * a.d.plane_stride;
+    for (int idx = tid; idx < 2 * rq * (TC / 4); idx += NT) {
+        const int row = idx / (TC / 4), q = idx % (TC / 4);
+        const int sel = row >= rq ? 1 : 0, r = row - sel * rq;
+        const int y = cy0 + r, gx = x0 + 4 * q;
+        float *dst = (sel ? s_d : s_a) + r * TC + 4 * q;
+        if (y >= 0 && y < my && gx < a.a.pitch) cp_async16(dst, (sel ? gd : ga) + (size_t)y * a.a.pitch + gx);
+        else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    constexpr int NGQ = TQ / RY, NCG = TC / 32;
+    float *dstp = a.out.ptr + (size_t)plane * a.out.plane_stride;
+    for (int wi = warp; wi < NGQ * NCG; wi += NW) {
+        const int gq = wi / NCG;
+        const int x = (wi - gq * NCG) * 32 + lane;
+        const float *ca = s_a + (RY * gq) * TC + x;
+        const float *cd = s_d + (RY * gq) * TC + x;
+        float2 o[RY];
+        synthesis_run<RY, JH, true, MODE, false>(ca, cd, TC, taps.lo, taps.hi, a.nch, Hp, nz, o);
+        const int ox = x0 + x;
+        if (ox < a.out.cols) {
+            const int oyb = 2 * (q0 + RY * gq);
+#pragma unroll
+            for (int k = 0; k < RY; ++k) {
+                if (oyb + 2 * k < a.out.rows) dstp[(size_t)(oyb + 2 * k) * a.out.pitch + ox] = o[k].x;
+                if (oyb + 2 * k + 1 < a.out.rows) dstp[(size_t)(oyb + 2 * k + 1) * a.out.pitch + ox] = o[k].y;
+            }
+        }
+    }
+}
+
 // ---- chunk selection ----------------------------------------------------------------------------------------------
 // F <= 20: one chunk of J = F taps (everything compile-time).  Longer filters: chunks of J in {8,12,16,20} taps, the
 // choice that pads least (ties: the longer chunk).
@@ -732,6 +1008,82 @@ void launch_inv_j(const InvTaps &it, const InvArgs &a, int n_planes, int exact, 
     else launch_inv_t<InvTile0, JH, MULTI, kFast>(it, a, n_planes, sm_count, s);
 }
 
+
+constexpr int kLongMinF = 42;   // filters at least this long take the per-axis kernels when a scratch buffer is given
+
+template <int J>
+void launch_fwd_long(const B2sTaps &t, FwdLongArgs a, int nch, int n_planes, int exact, cudaStream_t s)
+{
+    a.F = t.F; a.Fp = J * nch; a.nch = nch; a.negzero = -0.0f;
+    // leading zero taps: the axis -1 windows start at column 2*ox0 + 2 - Fp + shift, which must be a multiple of 4
+    a.shift = 0;
+    for (int sh = 0; sh <= a.Fp - t.F; ++sh)
+        if (((2 - a.Fp + sh) & 3) == 0) { a.shift = sh; break; }
+    FwdTaps ft;
+    for (int j = 0; j < kMaxFp; ++j) {
+        const int k = j - a.shift;
+        ft.t[j] = (k >= 0 && k < t.F) ? make_float2(t.dec_lo[k], t.dec_hi[k]) : make_float2(0.f, 0.f);
+    }
+    const int my = a.cA.rows, mx = a.cA.cols, nx = a.in.cols;
+    const size_t smem_y = sizeof(float) * (size_t)(2 * kFyTY + a.Fp - 2) * kFyTC;
+    const size_t smem_x = sizeof(float) * (size_t)(2 * kFxTR) * pitch_quads_odd(2 * kFxTX + a.Fp - 2 + 2);
+    const dim3 gy((nx + kFyTC - 1) / kFyTC, (my + kFyTY - 1) / kFyTY, n_planes);
+    const dim3 gx((mx + kFxTX - 1) / kFxTX, (my + kFxTR - 1) / kFxTR, n_planes);
+    if (exact) {
+        cudaFuncSetAttribute(k_dwt_fwd_y_long<J, kExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_y);
+        cudaFuncSetAttribute(k_dwt_fwd_x_long<J, kExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
+        k_dwt_fwd_y_long<J, kExact><<<gy, kLongNT, smem_y, s>>>(ft, a);
+        k_dwt_fwd_x_long<J, kExact><<<gx, kLongNT, smem_x, s>>>(ft, a);
+    } else {
+        cudaFuncSetAttribute(k_dwt_fwd_y_long<J, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_y);
+        cudaFuncSetAttribute(k_dwt_fwd_x_long<J, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
+        k_dwt_fwd_y_long<J, kFast><<<gy, kLongNT, smem_y, s>>>(ft, a);
+        k_dwt_fwd_x_long<J, kFast><<<gx, kLongNT, smem_x, s>>>(ft, a);
+    }
+}
+
+template <int JH>
+void launch_inv_long(const B2sTaps &t, InvLongArgs a, int nch, int n_planes, int exact, cudaStream_t s)
+{
+    const int H = t.F / 2;
+    a.H = H; a.Hp = JH * nch; a.nch = nch; a.negzero = -0.0f;
+    a.shift = a.Hp - H;   // all padding in front: the coefficient windows start at the tile origin
+    InvTaps it;
+    for (int j = 0; j < kMaxFp / 2; ++j) {
+        const int k = j - a.shift;
+        const bool ok = k >= 0 && k < H;
+        it.lo[j] = ok ? make_float2(t.rec_lo[2 * k], t.rec_lo[2 * k + 1]) : make_float2(0.f, 0.f);
+        it.hi[j] = ok ? make_float2(t.rec_hi[2 * k], t.rec_hi[2 * k + 1]) : make_float2(0.f, 0.f);
+    }
+    const int my = a.cH.rows;
+    const size_t smem_x = sizeof(float) * 4 * (size_t)kIxTR * pitch_quads_4mod8(kIxTP + a.Hp - 1);
+    const size_t smem_y = sizeof(float) * 2 * (size_t)(kIyTQ + a.Hp - 1) * kIyTC;
+    const dim3 gx((a.out.cols + 2 * kIxTP - 1) / (2 * kIxTP), (my + kIxTR - 1) / kIxTR, n_planes);
+    const dim3 gy((a.out.cols + kIyTC - 1) / kIyTC, (a.out.rows + 2 * kIyTQ - 1) / (2 * kIyTQ), n_planes);
+    if (exact) {
+        cudaFuncSetAttribute(k_dwt_inv_x_long<JH, kExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
+        cudaFuncSetAttribute(k_dwt_inv_y_long<JH, kExact>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_y);
+        k_dwt_inv_x_long<JH, kExact><<<gx, kLongNT, smem_x, s>>>(it, a);
+        k_dwt_inv_y_long<JH, kExact><<<gy, kLongNT, smem_y, s>>>(it, a);
+    } else {
+        cudaFuncSetAttribute(k_dwt_inv_x_long<JH, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
+        cudaFuncSetAttribute(k_dwt_inv_y_long<JH, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_y);
+        k_dwt_inv_x_long<JH, kFast><<<gx, kLongNT, smem_x, s>>>(it, a);
+        k_dwt_inv_y_long<JH, kFast><<<gy, kLongNT, smem_y, s>>>(it, a);
+    }
+}
+
+B2sImg scratch_img(float *base, size_t plane_stride, int half, int rows, int cols, int pitch)
+{
+    B2sImg im;
+    im.ptr = base + (size_t)half * rows * pitch;
+    im.plane_stride = plane_stride;
+    im.pitch = pitch;
+    im.rows = rows;
+    im.cols = cols;
+    return im;
+}
+
 }  // namespace
 
 int b2s_dwt_max_smem(int F)
@@ -744,11 +1096,31 @@ int b2s_dwt_max_smem(int F)
     return (int)((a > b ? a : b) + 1024);
 }
 
+size_t b2s_dwt_scratch_floats(int F, int ny, int nx)
+{
+    static const int off = dev_knob("B2S_DWT_NO_LONG", 0);
+    if (F < kLongMinF || off) return 0;
+    return 2 * (size_t)((ny + F - 1) / 2) * round_up4(nx);
+}
+
 void b2s_launch_dwt_fwd(const B2sTaps &t, const B2sImg &in, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV,
-                        const B2sImg &cD, int n_planes, int exact, int sm_count, cudaStream_t s)
+                        const B2sImg &cD, int n_planes, int exact, int sm_count, cudaStream_t s, float *scratch,
+                        size_t scratch_plane_stride)
 {
     int J, nch;
     pick_fwd_chunk(t.F, &J, &nch);
+    if (scratch && t.F >= kLongMinF) {
+        FwdLongArgs a;
+        a.in = in; a.cA = cA; a.cH = cH; a.cV = cV; a.cD = cD;
+        const int pitch = round_up4(in.cols);
+        a.lo = scratch_img(scratch, scratch_plane_stride, 0, cA.rows, in.cols, pitch);
+        a.hi = scratch_img(scratch, scratch_plane_stride, 1, cA.rows, in.cols, pitch);
+        switch (J) {
+#define X(JJ) case JJ: launch_fwd_long<JJ>(t, a, nch, n_planes, exact, s); return;
+            X(8) X(12) X(16) X(20)
+#undef X
+        }
+    }
     FwdTaps ft;
     for (int j = 0; j < kMaxFp; ++j) ft.t[j] = j < t.F ? make_float2(t.dec_lo[j], t.dec_hi[j]) : make_float2(0.f, 0.f);
     FwdArgs a;
@@ -770,11 +1142,24 @@ void b2s_launch_dwt_fwd(const B2sTaps &t, const B2sImg &in, const B2sImg &cA, co
 }
 
 void b2s_launch_dwt_inv(const B2sTaps &t, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV, const B2sImg &cD,
-                        const B2sImg &out, int n_planes, int exact, int sm_count, cudaStream_t s)
+                        const B2sImg &out, int n_planes, int exact, int sm_count, cudaStream_t s, float *scratch,
+                        size_t scratch_plane_stride)
 {
     const int H = t.F / 2;
     int JH, nch;
     pick_inv_chunk(H, &JH, &nch);
+    if (scratch && t.F >= kLongMinF) {
+        InvLongArgs a;
+        a.cA = cA; a.cH = cH; a.cV = cV; a.cD = cD; a.out = out;
+        const int pitch = round_up4(out.cols);
+        a.a = scratch_img(scratch, scratch_plane_stride, 0, cH.rows, out.cols, pitch);
+        a.d = scratch_img(scratch, scratch_plane_stride, 1, cH.rows, out.cols, pitch);
+        switch (JH) {
+#define X(JJ) case JJ: launch_inv_long<JJ>(t, a, nch, n_planes, exact, s); return;
+            X(4) X(8) X(12)
+#undef X
+        }
+    }
     InvTaps it;
     for (int j = 0; j < kMaxFp / 2; ++j) {
         it.lo[j] = j < H ? make_float2(t.rec_lo[2 * j], t.rec_lo[2 * j + 1]) : make_float2(0.f, 0.f);

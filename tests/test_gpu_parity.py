@@ -63,7 +63,11 @@ def test_prologue_log1p_and_padding_bit_exact(mode):
 
 @pytest.mark.parametrize("shape,wavelet,sigma", [((96, 128), "db10", (24, 24)), ((70, 91), "db5", (10, 10)),
                                                   ((160, 200), "db2", (64, 64)), ((128, 96), "db9", (16, 16)),
-                                                  ((200, 300), "db16", (30, 30))])
+                                                  ((200, 300), "db16", (30, 30)),
+                                                  # long filters (F >= 42): one kernel per axis through the scratch buffer
+                                                  ((300, 410), "coif15", (20, 20)), ((257, 391), "coif8", (12, 12)),
+                                                  ((333, 250), "db38", (16, 16)), ((520, 700), "sym20", (40, 40)),
+                                                  ((300, 300), "coif7", (8, 8))])
 def test_forward_dwt_bit_exact(shape, wavelet, sigma):
     img = synth.plane(6, shape)
     plan = _plan(shape, 1, sigma=sigma, wavelet=wavelet, stop_after=2)
@@ -212,6 +216,9 @@ def test_golden_vectors_from_the_reference():
     dict(sigma=(128, 512), wavelet="db9", padding_mode="reflect", bidirectional=True),
     dict(sigma=(100, 100), wavelet="db9", padding_mode="reflect", bidirectional=True),  # Step 3 as shipped
     dict(sigma=(64, 64), wavelet="db20", level=3),
+    dict(sigma=(128, 512), wavelet="coif15", padding_mode="reflect"),         # BASELINE config 5 (scaled plane), two passes
+    dict(sigma=(64, 64), wavelet="coif15", padding_mode="reflect", bidirectional=True),   # post-stitch defaults
+    dict(sigma=(32, 32), wavelet="db30", level=2),
 ])
 def test_filter_streaks_512(kw):
     from pystripe import core

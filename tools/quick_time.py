@@ -15,8 +15,11 @@ def main():
     exact = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     base = synth.stack(4, (2048, 2048))
     stack = torch.from_numpy(np.concatenate([base] * (n // 4))).cuda()
-    plan = core._get_plan(0, (2048, 2048), 1, process=0, sigma=(256, 256), level=0, wavelet=wavelet, threshold=None,
-                          padding_mode="wrap", bidirectional=False, log1p=True, max_batch=batch, exact=exact)
+    import os
+    sigma = tuple(int(v) for v in os.environ.get("QT_SIGMA", "256,256").split(","))
+    plan = core._get_plan(0, (2048, 2048), 1, process=0, sigma=sigma, level=0, wavelet=wavelet, threshold=None,
+                          padding_mode=os.environ.get("QT_PAD", "wrap"), bidirectional=bool(int(os.environ.get("QT_BIDIR", "0"))),
+                          log1p=True, max_batch=batch, exact=exact)
     ctx = plan.ctx
     out = plan.run_torch(stack); torch.cuda.synchronize()
     ctx.timing_enable(True); ctx.timing_read(reset=True)
