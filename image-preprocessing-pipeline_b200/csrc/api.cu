@@ -84,6 +84,9 @@ struct Geometry {
     int final_mode, out_dtype;
     int out_rows, out_cols;
     bool fuse_flat;
+    bool resize;                  // new_size differs from the work image: order-1 zoom before the final conversion
+    int new_rows, new_cols;
+    int mid_dtype;                // dtype of the image the resize reads (after dark / lightsheet)
 };
 
 int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
@@ -158,6 +161,24 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
         }
         g.levels = L;
     }
+    // new_size, core.py:1356-1359: `tile_size < new_size` / `>` compare (rows, cols) tuples lexicographically
+    g.resize = false;
+    g.new_rows = g.work_rows;
+    g.new_cols = g.work_cols;
+    g.mid_dtype = g.work_dtype;
+    if (p.process_img && p.new_height > 0 && p.new_width > 0 && (p.new_height != g.work_rows || p.new_width != g.work_cols)) {
+        const bool up = g.work_rows < p.new_height || (g.work_rows == p.new_height && g.work_cols < p.new_width);
+        // anti_aliasing=True filters with sigma = max(0, (in/out - 1) / 2) per axis: only the sigma == 0 case is built
+        if (up && (g.work_rows > p.new_height || g.work_cols > p.new_width))
+            return fail(ctx, B2S_ERR_UNSUPPORTED,
+                        "new_size larger along one axis and smaller along the other (anti-aliasing Gaussian of skimage.transform.resize) is not implemented");
+        if (g.work_dtype != B2S_F32 && p.dark > 0 && p.dark != std::floor(p.dark))
+            return fail(ctx, B2S_ERR_UNSUPPORTED, "new_size after a fractional dark on an integer image (float64 in the reference) is not implemented");
+        g.resize = true;
+        g.new_rows = p.new_height;
+        g.new_cols = p.new_width;
+        if (p.lightsheet) g.mid_dtype = p.out_dtype;   // correct_lightsheet returns d_type
+    }
     g.int_path = g.n_passes > 0 && g.work_dtype != B2S_F32;
     if (g.int_path && !p.log1p)
         return fail(ctx, B2S_ERR_UNSUPPORTED,
@@ -171,6 +192,7 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
         // dtype of the array right before the conversion
         int cur = g.work_dtype;
         if (p.dark > 0 && cur != B2S_F32 && p.dark != std::floor(p.dark)) cur = B2S_F32;  // promoted to float64
+        if (g.resize) cur = B2S_F32;   // skimage.transform.resize returns float64 (float32 for a float32 image)
         if (p.convert_to_16bit && cur != B2S_U16) { g.final_mode = 1; g.out_dtype = B2S_U16; }
         else if (p.convert_to_8bit && cur != B2S_U8) { g.final_mode = 2; g.out_dtype = B2S_U8; }
         else if (p.out_dtype != B2S_F32) { g.final_mode = 0; g.out_dtype = p.out_dtype; }
@@ -181,8 +203,8 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
     if (p.rotate != 0 && p.rotate != 90 && p.rotate != 180 && p.rotate != 270)
         return fail(ctx, B2S_ERR_INVALID, "rotate must be 0, 90, 180 or 270");
     const bool swap = p.process_img && (p.rotate == 90 || p.rotate == 270);
-    g.out_rows = swap ? g.work_cols : g.work_rows;
-    g.out_cols = swap ? g.work_rows : g.work_cols;
+    g.out_rows = swap ? g.new_cols : g.new_rows;
+    g.out_cols = swap ? g.new_rows : g.new_cols;
     if (p.process_img && p.lightsheet) {
         if (const char *why = b2s_lightsheet_check(g.work_rows, g.work_cols, p.artifact_length, p.background_window_size))
             return fail(ctx, B2S_ERR_UNSUPPORTED, "%s", why);
@@ -251,7 +273,9 @@ struct b2s_plan {
         void *d_in = nullptr, *d_out = nullptr;
         void *pre_a = nullptr, *pre_b = nullptr;   // pre-op temporaries
         float *dwt_scratch = nullptr;              // long filters: per-axis intermediates (b2s_dwt_scratch_floats per plane)
-        void *mid = nullptr;                       // lightsheet: post-dark image
+        void *mid = nullptr;                       // lightsheet / resize: post-dark image
+        void *mid2 = nullptr;                      // lightsheet followed by resize: the cleaned image
+        unsigned *mm2 = nullptr;                   // resize: per-plane min / max keys of the image it reads
         unsigned short *ls_grid = nullptr, *bg_grid = nullptr, *ls_cells = nullptr;
         unsigned *mm = nullptr;
         void *h_in = nullptr, *h_out = nullptr;    // pinned staging
@@ -267,6 +291,8 @@ struct b2s_plan {
     int n_row_groups = 0;
     int *d_row_src = nullptr, *d_row_start = nullptr, *d_row_targets = nullptr, *d_colmap = nullptr;
     float *d_lut = nullptr;
+    int *d_rz_idx = nullptr;                        // new_size: [iy0 | iy1 | ix0 | ix1]
+    double *d_rz_w = nullptr;                       //           [wy0 | wy1 | wx0 | wx1]
     std::map<int, B2sFftPlan> fft;                  // by length
     B2sLightsheet *ls = nullptr;
     std::map<int, B2sXfftPlan *> xfft;              // by length: rounding-exact transform (exact mode, covered lengths)
@@ -321,6 +347,25 @@ B2sImg img_of(b2s_plan *pl, float *base, int level)
     im.rows = pl->g.my[level];
     im.cols = pl->g.mx[level];
     return im;
+}
+
+int build_resize_tables(b2s_plan *pl)
+{
+    b2s_context *ctx = pl->ctx;
+    const Geometry &g = pl->g;
+    if (g.resize) {   // axis tables of the order-1 zoom (scipy.ndimage NI_ZoomShift, grid_mode, mirror)
+        const int nr = g.new_rows, nc = g.new_cols;
+        std::vector<int> idx(2 * (size_t)(nr + nc));
+        std::vector<double> w(2 * (size_t)(nr + nc));
+        b2s_resize_axis_table(g.work_rows, nr, idx.data(), idx.data() + nr, w.data(), w.data() + nr);
+        b2s_resize_axis_table(g.work_cols, nc, idx.data() + 2 * nr, idx.data() + 2 * nr + nc, w.data() + 2 * nr, w.data() + 2 * nr + nc);
+        int rc = dev_alloc(pl, (void **)&pl->d_rz_idx, sizeof(int) * idx.size());
+        if (rc) return rc;
+        if ((rc = dev_alloc(pl, (void **)&pl->d_rz_w, sizeof(double) * w.size()))) return rc;
+        CU(ctx, cudaMemcpy(pl->d_rz_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(pl->d_rz_w, w.data(), sizeof(double) * w.size(), cudaMemcpyHostToDevice));
+    }
+    return B2S_OK;
 }
 
 int build_tables(b2s_plan *pl)
@@ -460,6 +505,11 @@ int alloc_slot(b2s_plan *pl, int si)
         if ((rc = dev_alloc(pl, &s.pre_a, in_elems * 4 * B))) return rc;
         if ((rc = dev_alloc(pl, &s.pre_b, in_elems * 4 * B))) return rc;
         if ((rc = dev_alloc(pl, (void **)&s.mm, sizeof(unsigned) * 2 * B))) return rc;
+    }
+    if (g.resize) {
+        if (!pl->ls && (rc = dev_alloc(pl, &s.mid, work_elems * 4 * B))) return rc;
+        if (pl->ls && (rc = dev_alloc(pl, &s.mid2, work_elems * 4 * B))) return rc;
+        if ((rc = dev_alloc(pl, (void **)&s.mm2, sizeof(unsigned) * 2 * B))) return rc;
     }
     if (pl->ls) {
         if ((rc = dev_alloc(pl, &s.mid, work_elems * 4 * B))) return rc;
@@ -608,17 +658,42 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
         e.out = d_out;
         e.out_rows = g.out_rows;
         e.out_cols = g.out_cols;
-        if (!pl->ls) {
+        // the image as the reference holds it after the dark subtraction (same dtype), unrotated
+        B2sEpilogueArgs m = e;
+        const bool mid_int = g.work_dtype != B2S_F32;
+        m.final_mode = mid_int ? 0 : 3;
+        m.out_dtype = mid_int ? g.work_dtype : B2S_F32;
+        m.flip = 0; m.rot = 0; m.uniform_mm = nullptr;
+        m.out = s.mid; m.out_rows = g.work_rows; m.out_cols = g.work_cols;
+        if (g.resize) {
+            {
+                ClassTimer t(ctx, st, B2S_K_EPILOGUE, 1);
+                b2s_launch_epilogue(m, nb, st);
+            }
+            const void *src = s.mid;
+            if (pl->ls) {   // lightsheet clean into a second work-size image of d_type, then resize that
+                ClassTimer t2(ctx, st, B2S_K_LIGHTSHEET, s.ls_cells ? 4 : 3);
+                B2sEpilogueArgs le = e;
+                le.final_mode = 0; le.out_dtype = g.mid_dtype; le.flip = 0; le.rot = 0;
+                le.out = s.mid2; le.out_rows = g.work_rows; le.out_cols = g.work_cols;
+                b2s_launch_lightsheet(pl->ls, s.mid, s.ls_grid, s.bg_grid, s.ls_cells, le, nb, st);
+                src = s.mid2;
+            }
+            ClassTimer t3(ctx, st, B2S_K_EPILOGUE, 2);
+            CU(ctx, cudaMemsetAsync(s.mm2, 0xff, sizeof(unsigned) * 2 * nb, st));
+            b2s_launch_minmax(src, g.mid_dtype, (size_t)g.work_rows * g.work_cols, nb, s.mm2, st);
+            B2sResizeArgs r;
+            r.src = src; r.dtype = g.mid_dtype; r.rows = g.work_rows; r.cols = g.work_cols;
+            r.new_rows = g.new_rows; r.new_cols = g.new_cols;
+            r.iy0 = pl->d_rz_idx; r.iy1 = r.iy0 + g.new_rows; r.ix0 = r.iy1 + g.new_rows; r.ix1 = r.ix0 + g.new_cols;
+            r.wy0 = pl->d_rz_w; r.wy1 = r.wy0 + g.new_rows; r.wx0 = r.wy1 + g.new_rows; r.wx1 = r.wx0 + g.new_cols;
+            r.mm = s.mm2;
+            b2s_launch_resize_final(r, e, nb, st);
+        } else if (!pl->ls) {
             ClassTimer t(ctx, st, B2S_K_EPILOGUE, 1);
             b2s_launch_epilogue(e, nb, st);
         } else {
-            // stage 1: the image as the reference holds it after the dark subtraction (same dtype), unrotated
-            B2sEpilogueArgs m = e;
-            const bool mid_int = g.work_dtype != B2S_F32;
-            m.final_mode = mid_int ? 0 : 3;
-            m.out_dtype = mid_int ? g.work_dtype : B2S_F32;
-            m.flip = 0; m.rot = 0; m.uniform_mm = nullptr;
-            m.out = s.mid; m.out_rows = g.work_rows; m.out_cols = g.work_cols;
+            // stage 1: the post-dark image
             {
                 ClassTimer t(ctx, st, B2S_K_EPILOGUE, 1);
                 b2s_launch_epilogue(m, nb, st);
@@ -709,6 +784,13 @@ int b2s_plan_geometry(const b2s_params *params, b2s_plan_info *info, char *err, 
     return B2S_OK;
 }
 
+int b2s_resize_table(int n_in, int n_out, int32_t *idx0, int32_t *idx1, double *w0, double *w1)
+{
+    if (n_in <= 0 || n_out <= 0 || !idx0 || !idx1 || !w0 || !w1) return B2S_ERR_INVALID;
+    b2s_resize_axis_table(n_in, n_out, idx0, idx1, w0, w1);
+    return B2S_OK;
+}
+
 int b2s_plan_create(b2s_context *ctx, const b2s_params *params, b2s_plan **out)
 {
     if (!ctx || !params || !out) return B2S_ERR_INVALID;
@@ -732,6 +814,7 @@ int b2s_plan_create(b2s_context *ctx, const b2s_params *params, b2s_plan **out)
         if (need > 227 * 1024) { delete pl; return fail(ctx, B2S_ERR_UNSUPPORTED, "filter too long for the shared-memory tiles"); }
         rc = build_tables(pl);
     }
+    if (rc == B2S_OK) rc = build_resize_tables(pl);
     if (rc == B2S_OK && params->process_img && params->lightsheet) {
         pl->ls = b2s_lightsheet_create(g.work_rows, g.work_cols, g.work_dtype, params->artifact_length,
                                        params->background_window_size, params->percentile,

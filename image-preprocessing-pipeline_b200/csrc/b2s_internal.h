@@ -65,6 +65,18 @@ struct B2sEpilogueArgs {
 };
 void b2s_launch_epilogue(const B2sEpilogueArgs &a, int n_planes, cudaStream_t s);
 
+// new_size (skimage.transform.resize, order 1, core.py:1356-1359) fused with the final conversion / orientation
+struct B2sResizeArgs {
+    const void *src;       // image after dark / lightsheet, `dtype`, rows x cols per plane, contiguous
+    int dtype, rows, cols;
+    int new_rows, new_cols;
+    const int *iy0, *iy1, *ix0, *ix1;            // per output row / column: the two source indices
+    const double *wy0, *wy1, *wx0, *wx1;         // and their float64 weights
+    const unsigned *mm;    // per-plane {min key, ~max key} of src (the clip range)
+};
+void b2s_resize_axis_table(int n_in, int n_out, int *idx0, int *idx1, double *w0, double *w1);   // host
+void b2s_launch_resize_final(const B2sResizeArgs &r, const B2sEpilogueArgs &a, int n_planes, cudaStream_t s);
+
 // per-plane "all pixels equal" flags (process_img core.py:1232)
 // mm[2p] = min key, mm[2p+1] = ~max key (both initialised to 0xffffffff by a memset); standalone pass over the input
 void b2s_launch_minmax(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned *mm, cudaStream_t s);

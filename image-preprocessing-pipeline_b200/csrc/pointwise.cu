@@ -469,6 +469,140 @@ void b2s_launch_epilogue(const B2sEpilogueArgs &a, int n_planes, cudaStream_t s)
     k_epilogue<<<grid, 256, 0, s>>>(a);
 }
 
+// ---- new_size: skimage.transform.resize(img, new_size, preserve_range=True, anti_aliasing=...) (core.py:1356-1359)
+// skimage (>= 0.19) evaluates an order-1 resize as scipy.ndimage.zoom(img, out/in, order=1, mode='mirror',
+// grid_mode=True) on a float64 copy of an integer image (a float32 image stays float32: the float64 sum is rounded to
+// float32 on store), then clips to [min(img), max(img)].  NI_ZoomShift: per axis and output index k the coordinate is
+// cc = (k + 0.5) * (in / out) - 0.5, mirrored about 0 when negative (never above: cc < in), start = floor(cc), weights
+// w0 = 1 - (cc - start), w1 = 1 - w0; the value is ((v00*wy0)*wx0 + (v01*wy0)*wx1) + (v10*wy1)*wx0 + (v11*wy1)*wx1 summed
+// left to right from 0.0 in float64, no contraction.  The per-axis tables are built on the host by b2s_resize_axis_table
+// (pinned bit-for-bit against scipy in tests/test_host_api.py).
+void b2s_resize_axis_table(int n_in, int n_out, int *idx0, int *idx1, double *w0, double *w1)
+{
+    const double zoom = (double)n_in / (double)n_out;
+    auto mirror = [n_in](long long i) -> int {
+        if (n_in <= 1) return 0;
+        const long long s2 = 2ll * n_in - 2;
+        if (i < 0) {
+            i = s2 * (long long)(-i / s2) + i;
+            i = i <= 1 - n_in ? i + s2 : -i;
+        } else if (i >= n_in) {
+            i -= s2 * (long long)(i / s2);
+            if (i >= n_in) i = s2 - i;
+        }
+        return (int)i;
+    };
+    for (int k = 0; k < n_out; ++k) {
+        double cc = (double)k;
+        cc += 0.5;
+        cc *= zoom;
+        cc -= 0.5;
+        if (cc < 0) {
+            if (n_in <= 1) cc = 0;
+            else {
+                const long long sz2 = 2ll * n_in - 2;
+                cc = (double)(sz2 * (long long)(-cc / (double)sz2)) + cc;
+                cc = cc <= 1 - n_in ? cc + (double)sz2 : -cc;
+            }
+        } else if (cc > n_in - 1) {
+            if (n_in <= 1) cc = 0;
+            else {
+                const long long sz2 = 2ll * n_in - 2;
+                cc -= (double)(sz2 * (long long)(cc / (double)sz2));
+                if (cc >= n_in) cc = (double)sz2 - cc;
+            }
+        }
+        const double fl = floor(cc);
+        const long long start = (long long)fl;
+        const double x = cc - fl;
+        w0[k] = 1.0 - x;
+        w1[k] = 1.0 - w0[k];
+        idx0[k] = mirror(start);
+        idx1[k] = mirror(start + 1);
+    }
+}
+
+__device__ __forceinline__ float key2f(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(256) k_resize_final(B2sResizeArgs r, B2sEpilogueArgs a)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;  // output column
+    const int i = blockIdx.y;                             // output row
+    if (j >= a.out_cols) return;
+    const size_t plane = blockIdx.z;
+    const size_t oidx = plane * (size_t)a.out_rows * a.out_cols + (size_t)i * a.out_cols + j;
+    const bool zero_plane = a.uniform_mm && a.uniform_mm[2 * plane] == ~a.uniform_mm[2 * plane + 1];
+    double v = 0.0;
+    if (!zero_plane) {
+        // output (i, j) -> resized image (y, x): undo rot90 then flipud
+        const int R = r.new_rows, Cn = r.new_cols;
+        int y, x;
+        switch (a.rot) {
+        case 1: y = j; x = Cn - 1 - i; break;
+        case 2: y = R - 1 - i; x = Cn - 1 - j; break;
+        case 3: y = R - 1 - j; x = i; break;
+        default: y = i; x = j; break;
+        }
+        if (a.flip) y = R - 1 - y;
+        const int y0 = __ldg(r.iy0 + y), y1 = __ldg(r.iy1 + y), x0 = __ldg(r.ix0 + x), x1 = __ldg(r.ix1 + x);
+        const double wy0 = __ldg(r.wy0 + y), wy1 = __ldg(r.wy1 + y), wx0 = __ldg(r.wx0 + x), wx1 = __ldg(r.wx1 + x);
+        const size_t base = plane * (size_t)r.rows * r.cols;
+        double v00, v01, v10, v11;
+        if (r.dtype == B2S_F32) {
+            const float *s = reinterpret_cast<const float *>(r.src) + base;
+            v00 = s[(size_t)y0 * r.cols + x0]; v01 = s[(size_t)y0 * r.cols + x1];
+            v10 = s[(size_t)y1 * r.cols + x0]; v11 = s[(size_t)y1 * r.cols + x1];
+        } else if (r.dtype == B2S_U16) {
+            const unsigned short *s = reinterpret_cast<const unsigned short *>(r.src) + base;
+            v00 = s[(size_t)y0 * r.cols + x0]; v01 = s[(size_t)y0 * r.cols + x1];
+            v10 = s[(size_t)y1 * r.cols + x0]; v11 = s[(size_t)y1 * r.cols + x1];
+        } else {
+            const unsigned char *s = reinterpret_cast<const unsigned char *>(r.src) + base;
+            v00 = s[(size_t)y0 * r.cols + x0]; v01 = s[(size_t)y0 * r.cols + x1];
+            v10 = s[(size_t)y1 * r.cols + x0]; v11 = s[(size_t)y1 * r.cols + x1];
+        }
+        double t = 0.0;
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(v00, wy0), wx0));
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(v01, wy0), wx1));
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(v10, wy1), wx0));
+        t = __dadd_rn(t, __dmul_rn(__dmul_rn(v11, wy1), wx1));
+        const unsigned klo = r.mm[2 * plane], khi = ~r.mm[2 * plane + 1];
+        if (r.dtype == B2S_F32) {
+            float tf = (float)t;
+            const float lo = key2f(klo), hi = key2f(khi);
+            tf = fminf(fmaxf(tf, lo), hi);
+            v = (double)tf;
+        } else {
+            const double lo = (double)klo, hi = (double)khi;
+            v = t < lo ? lo : (t > hi ? hi : t);
+        }
+    }
+    if (a.final_mode == 3) { reinterpret_cast<float *>(a.out)[oidx] = (float)v; return; }
+    unsigned u;
+    if (a.final_mode == 2) {  // convert_to_8bit_fun on a float image: clip, truncate to uint16, shift (core.py:402-423)
+        const double c = v < 0.0 ? 0.0 : (v > 65535.0 ? 65535.0 : v);
+        u = (unsigned)c;
+        const unsigned lower = 1u << a.shift;
+        u = (u > 0 && u < lower) ? 1u : (u >> a.shift);
+        u = u > 255u ? 255u : u;
+    } else {
+        const double hi = (a.out_dtype == B2S_U8) ? 255.0 : 65535.0;
+        const double c = v < 0.0 ? 0.0 : (v > hi ? hi : v);
+        u = (unsigned)c;
+    }
+    if (a.out_dtype == B2S_U8) reinterpret_cast<unsigned char *>(a.out)[oidx] = (unsigned char)u;
+    else reinterpret_cast<unsigned short *>(a.out)[oidx] = (unsigned short)u;
+}
+
+void b2s_launch_resize_final(const B2sResizeArgs &r, const B2sEpilogueArgs &a, int n_planes, cudaStream_t s)
+{
+    dim3 grid((a.out_cols + 255) / 256, a.out_rows, n_planes);
+    k_resize_final<<<grid, 256, 0, s>>>(r, a);
+}
+
 // log1p table for integer pixels: lut[v] = b2s_log1pf((float)v), the function the non-table path evaluates
 __global__ void k_log1p_lut(float *lut, int n)
 {

@@ -36,6 +36,7 @@ class Params(C.Structure):
         ("percentile", C.c_double), ("lightsheet_vs_background", C.c_double),
         ("convert_to_16bit", C.c_int32), ("convert_to_8bit", C.c_int32), ("bit_shift_to_right", C.c_int32),
         ("rotate", C.c_int32), ("flip_upside_down", C.c_int32), ("reference_quirks", C.c_int32),
+        ("new_height", C.c_int32), ("new_width", C.c_int32),
         ("max_batch", C.c_int32), ("debug_stop_after", C.c_int32), ("exact", C.c_int32),
     ]
 
@@ -53,7 +54,7 @@ class PlanInfo(C.Structure):
 
 EXPORTS = (
     "b2s_version", "b2s_params_default", "b2s_create", "b2s_destroy", "b2s_last_error", "b2s_device_sm_count",
-    "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_run",
+    "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_run",
     "b2s_host_alloc", "b2s_host_free", "b2s_launch_count", "b2s_timing_enable", "b2s_timing_read",
     "b2s_debug_read", "b2s_debug_math",
 )

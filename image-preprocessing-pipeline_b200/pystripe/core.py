@@ -260,7 +260,7 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
               log1p, flat=None, gaussian=False, down_sample=None, down_sample_method='max', dark=0, lightsheet=False,
               artifact_length=150, background_window_size=200, percentile=0.25, lightsheet_vs_background=2.0,
               convert_to_16bit=False, convert_to_8bit=False, bit_shift_to_right=8, rotate=0, flip=False,
-              out_code=None, max_batch=None, stop_after=0, exact=None):
+              out_code=None, max_batch=None, stop_after=0, exact=None, new_size=None):
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
     s1, s2 = float(sigma[0]), float(sigma[1])
@@ -292,7 +292,7 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
            bool(bidirectional), bool(log1p), threshold is not None and threshold <= 0, flat_key, bool(gaussian), ds,
            method, float(dark or 0), bool(lightsheet), artifact_length, background_window_size, percentile,
            lightsheet_vs_background, bool(convert_to_16bit), bool(convert_to_8bit), bit_shift_to_right, rotate,
-           bool(flip), out_code, max_batch, stop_after, exact, REFERENCE_QUIRKS)
+           bool(flip), out_code, max_batch, stop_after, exact, REFERENCE_QUIRKS, new_size)
     with _plans_lock:
         plan = _plans.get(key)
         if plan is not None:
@@ -325,6 +325,8 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
         p.rotate = int(rotate or 0)
         p.flip_upside_down = int(bool(flip))
         p.reference_quirks = int(REFERENCE_QUIRKS)
+        if new_size is not None:
+            p.new_height, p.new_width = int(new_size[0]), int(new_size[1])
         p.max_batch = int(max_batch or MAX_BATCH)
         p.debug_stop_after = int(stop_after)
         p.exact = int(EXACT if exact is None else exact)
@@ -443,6 +445,26 @@ def filter_streaks(
 # --------------------------------------------------------------------------------------------------------------
 # process_img  (core.py:1190-1381)
 # --------------------------------------------------------------------------------------------------------------
+def _resize_target(shape, tile_size, down_sample, new_size):
+    """core.py:1356-1359: `resize(img, new_size, preserve_range=True, anti_aliasing=tile_size < new_size)` unless the
+    (down-sampled) tile_size equals new_size.  Returns the (rows, cols) the GPU plan resizes to, or None."""
+    if new_size is None:
+        return None
+    new_size = tuple(int(v) for v in new_size)
+    ts, work = tuple(int(v) for v in tile_size), tuple(shape)
+    if down_sample is not None:
+        ts = tuple(calculate_down_sampled_size(ts, down_sample))        # core.py:1300
+        work = tuple(calculate_down_sampled_size(work, down_sample))
+    if ts == new_size:
+        return None
+    if work == new_size or (ts < new_size) != (work < new_size):
+        raise NotImplementedError("new_size with a tile_size that differs from the image shape is not implemented")
+    for n_in, n_out in zip(work, new_size):                             # the shape scipy.ndimage.zoom derives from the factors
+        if int(round(n_in * (1 / np.divide(n_in, n_out)))) != n_out:
+            raise NotImplementedError(f"new_size {new_size}: skimage's zoom factor rounds to another output shape")
+    return new_size
+
+
 def process_img(
         img,
         flat: ndarray = None,
@@ -486,14 +508,13 @@ def process_img(
     8/16-bit conversion -> flip -> rot90.   img: (H, W) or (Z, H, W), numpy or CUDA torch tensor."""
     if bleach_correction_frequency is not None or exclude_dark_edges_set_them_to_zero:
         raise NotImplementedError("bleach correction / dark-edge exclusion are outside the GPU hot path")
-    if new_size is not None:
-        raise NotImplementedError("new_size (skimage.transform.resize) is a 'next' row (SURVEY.md §8f N3)")
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
     arr, restore = _as_supported(img)
     shape = tuple(arr.shape[-2:])
     if tile_size is None:
         tile_size = shape
+    resize_to = _resize_target(shape, tile_size, down_sample, new_size)
     if d_type is None:
         d_type = np.float64 if restore is not None else (
             _native.CODE_TO_NP[_code_of(arr)])
@@ -521,7 +542,7 @@ def process_img(
                      percentile=percentile, lightsheet_vs_background=lightsheet_vs_background,
                      convert_to_16bit=convert_to_16bit, convert_to_8bit=convert_to_8bit,
                      bit_shift_to_right=bit_shift_to_right, rotate=rotate, flip=flip_upside_down, out_code=out_code,
-                     max_batch=_max_batch)
+                     max_batch=_max_batch, new_size=resize_to)
     out = _run(plan, arr)
     if out_code == _native.F32 and plan.info.out_dtype == _native.F32 and d_type != np.float32:
         out = out.astype(d_type) if not _native._is_torch(out) else out.double()

@@ -77,6 +77,9 @@ typedef struct b2s_params {
     int32_t rotate;               /* 0, 90, 180, 270 (core.py:1374-1379)                                     */
     int32_t flip_upside_down;     /* core.py:1371                                                           */
     int32_t reference_quirks;     /* 1: reproduce as-written behaviour (Gaussian result discarded)           */
+    int32_t new_height, new_width;/* new_size (core.py:1356-1359): skimage.transform.resize(order 1) after the
+                                     lightsheet stage, before the 8/16-bit conversion; 0 = none.  Pure up-sizing
+                                     (anti_aliasing with sigma 0) and down-sizing (anti_aliasing=False) only     */
     /* --- execution ------------------------------------------------------------------------------------ */
     int32_t max_batch;            /* planes processed per launch group (workspace is sized for this)         */
     int32_t debug_stop_after;     /* b2s_stage; 0 in production                                             */
@@ -116,6 +119,11 @@ void b2s_plan_destroy(b2s_plan *plan);
 int b2s_plan_query(const b2s_plan *plan, b2s_plan_info *info);
 /* host-only: validate params and report the geometry a plan would have; needs no GPU (err may be NULL) */
 int b2s_plan_geometry(const b2s_params *params, b2s_plan_info *info, char *err, size_t err_len);
+
+/* GPU-free: the per-axis index / weight tables of the order-1 resize behind `new_size` (replaces the coordinate
+ * set-up of scipy.ndimage.zoom(order=1, mode='mirror', grid_mode=True) that skimage.transform.resize reaches from
+ * pystripe/core.py:1356-1359).  Output k reads source indices idx0[k], idx1[k] with float64 weights w0[k], w1[k]. */
+int b2s_resize_table(int n_in, int n_out, int32_t *idx0, int32_t *idx1, double *w0, double *w1);
 /* replaces: normalize_flat result captured in batch_filter's arg dict (core.py:1948-1953); flat is (height,width) f32 */
 int b2s_plan_set_flat(b2s_plan *plan, const float *flat, int is_device);
 

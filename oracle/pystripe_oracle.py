@@ -289,6 +289,35 @@ def correct_lightsheet(img, percentile=0.25, artifact_length=150, background_win
     return img
 
 
+# ---- skimage.transform.resize (absent here; restated) -------------------------------------------
+def skimage_resize(image, output_shape, preserve_range=True, anti_aliasing=True, order=1, mode='reflect', cval=0,
+                   clip=True):
+    """skimage.transform.resize as pystripe calls it (core.py:1356-1359), restated from skimage/transform/_warps.py
+    (0.19 ... 0.25: `resize` -> scipy.ndimage.zoom(grid_mode=True), `_clip_warp_output`).  skimage is not installed and
+    not pinned by the reference: wrapper parity is UNPINNED; the interpolation itself is the real scipy.ndimage.zoom."""
+    from scipy import ndimage as ndi
+    image = np.asarray(image)
+    output_shape = tuple(int(v) for v in output_shape)
+    assert image.ndim == len(output_shape) == 2 and preserve_range and order == 1
+    if image.dtype == np.float16:
+        image = image.astype(np.float32)
+    if image.dtype.char not in 'df':                       # convert_to_float(image, preserve_range=True)
+        image = image.astype(np.float64)
+    factors = np.divide(image.shape, output_shape)
+    ndi_mode = {'constant': 'constant', 'edge': 'nearest', 'symmetric': 'reflect', 'reflect': 'mirror', 'wrap': 'wrap'}[mode]
+    if anti_aliasing:
+        sigma = np.maximum(0, (factors - 1) / 2)
+        filtered = ndi.gaussian_filter(image, sigma, cval=cval, mode=ndi_mode)
+    else:
+        filtered = image
+    zoom_factors = [1 / f for f in factors]
+    out = ndi.zoom(filtered, zoom_factors, order=order, mode=ndi_mode, cval=cval, grid_mode=True)
+    if clip:                                               # _clip_warp_output (mode != 'constant': cval plays no part)
+        min_val, max_val = np.min(image), np.max(image)
+        np.clip(out, min_val, max_val, out=out)
+    return out
+
+
 # ---- process_img -------------------------------------------------------------------------------
 def process_img(img, flat=None, gaussian_filter_2d=False, down_sample=None, down_sample_method='max',
                 tile_size=None, new_size=None, sigma=(0, 0), level=0, wavelet='coif15', threshold=None,
@@ -297,17 +326,19 @@ def process_img(img, flat=None, gaussian_filter_2d=False, down_sample=None, down
                 lightsheet_vs_background=2.0, rotate=0, flip_upside_down=False, convert_to_16bit=False,
                 convert_to_8bit=False, bit_shift_to_right=8, d_type=None, quirks=False):
     """core.py:1190-1381 (order of operations preserved; bleach / dark-edge options not restated)."""
-    if new_size is not None:
-        raise NotImplementedError("new_size (skimage.transform.resize) is a 'next' row (SURVEY §8f N3)")
     if tile_size is None:
         tile_size = img.shape
     tile_size = tuple(tile_size)
+    if new_size is not None:
+        new_size = tuple(int(v) for v in new_size)
     if d_type is None:
         d_type = img.dtype
     d_type = np.dtype(d_type)
 
     if is_uniform_2d(img):                                             # :1232-1246
-        if down_sample is not None:
+        if new_size is not None:
+            tile_size = new_size
+        elif down_sample is not None:
             tile_size = calculate_down_sampled_size(tile_size, down_sample)
         if rotate in (90, 270):
             tile_size = (tile_size[1], tile_size[0])
@@ -326,7 +357,7 @@ def process_img(img, flat=None, gaussian_filter_2d=False, down_sample=None, down
         if method not in ('min', 'max', 'mean', 'median'):
             raise RuntimeError(f"unsupported down-sampling method: {down_sample_method}")
         img = block_reduce(img, down_sample, method)
-        tile_size = calculate_down_sampled_size(tile_size, down_sample)
+        tile_size = tuple(calculate_down_sampled_size(tile_size, down_sample))
     if tuple(sigma) > (0, 0):                                          # :1302-1320
         img = filter_streaks(img, sigma=sigma, level=level, wavelet=wavelet, threshold=threshold,
                              padding_mode=padding_mode, bidirectional=bidirectional,
@@ -336,6 +367,10 @@ def process_img(img, flat=None, gaussian_filter_2d=False, down_sample=None, down
     if lightsheet:                                                     # :1333-1348
         img = correct_lightsheet(img, percentile, artifact_length, background_window_size,
                                  lightsheet_vs_background, d_type=d_type)
+    if new_size is not None and tile_size < new_size:                  # :1356-1359 (tuple comparison)
+        img = skimage_resize(img, new_size, preserve_range=True, anti_aliasing=True)
+    elif new_size is not None and tile_size > new_size:
+        img = skimage_resize(img, new_size, preserve_range=True, anti_aliasing=False)
     if convert_to_16bit and img.dtype != np.uint16:                    # :1361-1369
         img = convert_to_16bit_fun(img)
     elif convert_to_8bit and img.dtype != np.uint8:

@@ -62,6 +62,9 @@ def main():
         ("pi_ds_min_rot", dict(sigma=(0, 0), down_sample=(3, 2), down_sample_method="min", rotate=90, flip_upside_down=True)),
         ("pi_16bit", dict(sigma=(16, 16), wavelet="db6", convert_to_16bit=True, rotate=270)),
         ("pi_lightsheet", dict(sigma=(0, 0), lightsheet=True, artifact_length=30, background_window_size=40, dark=100)),
+        ("pi_resize_down", dict(sigma=(16, 16), wavelet="db6", dark=100, new_size=(81, 108), convert_to_8bit=True, bit_shift_to_right=3)),
+        ("pi_resize_up", dict(sigma=(12, 12), wavelet="db4", new_size=(130, 171), rotate=90, flip_upside_down=True)),
+        ("pi_resize_ls", dict(sigma=(0, 0), lightsheet=True, artifact_length=30, background_window_size=40, dark=100, new_size=(120, 160))),
     ]:
         ref = core.process_img(img.copy(), **kw)
         got = orc.process_img(img.copy(), quirks=True, **kw)

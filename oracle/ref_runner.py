@@ -59,6 +59,12 @@ def _not_available(what):
     return f
 
 
+def _resize(image, output_shape, **kw):
+    """skimage.transform.resize restated (oracle.pystripe_oracle.skimage_resize): skimage is absent here."""
+    from oracle.pystripe_oracle import skimage_resize
+    return skimage_resize(image, output_shape, **kw)
+
+
 def _block_reduce(image, block_size=2, func=None, cval=0, func_kwargs=None):
     """skimage.measure.block_reduce restated: pad trailing edges with cval up to a block multiple,
     view as blocks, reduce over the block axes (skimage/measure/block.py)."""
@@ -105,7 +111,7 @@ def load():
         "skimage.filters": _stub("skimage.filters", threshold_otsu=_not_available("skimage"),
                                  threshold_multiotsu=_not_available("skimage")),
         "skimage.measure": _stub("skimage.measure", block_reduce=_block_reduce),
-        "skimage.transform": _stub("skimage.transform", resize=_not_available("skimage.transform.resize")),
+        "skimage.transform": _stub("skimage.transform", resize=_resize),
         "tifffile": _stub("tifffile", imwrite=_not_available("tifffile")),
         "tifffile.tifffile": _stub("tifffile.tifffile", TiffFileError=type("TiffFileError", (Exception,), {})),
     }

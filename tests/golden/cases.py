@@ -47,5 +47,15 @@ def all_cases():
                                        _flat=normalize_flat(synth.flat_field((96, 128))))
     yield "pi_flat_8bit", pi, img, dict(sigma=(16, 16), wavelet="db10", dark=100, convert_to_8bit=True,
                                        bit_shift_to_right=4, _flat=normalize_flat(synth.flat_field((96, 128))))
+    # new_size (core.py:1356-1359): skimage.transform.resize restated over the real scipy.ndimage.zoom
+    yield "pi_resize_down_8bit", pi, img, dict(sigma=(16, 16), wavelet="db6", dark=100, new_size=(81, 108),
+                                              convert_to_8bit=True, bit_shift_to_right=3)
+    yield "pi_resize_up_rot", pi, img, dict(sigma=(12, 12), wavelet="db4", new_size=(130, 171), rotate=90,
+                                           flip_upside_down=True)
+    yield "pi_resize_down_nodestripe", pi, img, dict(sigma=(0, 0), new_size=(50, 127), dark=105)
+    yield "pi_resize_lightsheet", pi, img, dict(sigma=(0, 0), lightsheet=True, artifact_length=30,
+                                               background_window_size=40, dark=100, new_size=(120, 160))
+    yield "pi_resize_flat", pi, img, dict(sigma=(16, 16), wavelet="db6", dark=100, padding_mode="reflect", new_size=(77, 99),
+                                         _flat=normalize_flat(synth.flat_field((96, 128))))
     yield "pi_uniform", pi, np.full((64, 80), 7, np.uint16), dict(sigma=(8, 8), wavelet="db2", down_sample=(2, 2),
                                                                   rotate=90, convert_to_8bit=True)

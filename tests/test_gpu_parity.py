@@ -428,3 +428,34 @@ def test_zz_write_parity_report():
     out = ROOT / "gpurun_out"
     out.mkdir(exist_ok=True)
     (out / "parity_report.json").write_text(json.dumps(REPORT, indent=1, default=str))
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((200, 260), dict(sigma=(24, 24), wavelet="db6", dark=100, new_size=(173, 211), convert_to_8bit=True, bit_shift_to_right=4)),
+    ((200, 260), dict(sigma=(24, 24), wavelet="db6", new_size=(333, 401))),
+    ((256, 256), dict(sigma=(32, 32), wavelet="db10", padding_mode="reflect", dark=100, down_sample=(2, 2), new_size=(108, 108),
+                      convert_to_8bit=True, bit_shift_to_right=8, rotate=270)),          # config 3 with its optional resize
+    ((200, 260), dict(sigma=(0, 0), new_size=(77, 300 - 41), flip_upside_down=True, convert_to_16bit=True)),
+    ((200, 260), dict(sigma=(24, 24), wavelet="db6", lightsheet=True, artifact_length=40, background_window_size=50,
+                      dark=100, new_size=(150, 195), rotate=180)),
+])
+def test_process_img_new_size(shape, kw):
+    """new_size: order-1 resize (skimage.transform.resize restated over the real scipy.ndimage.zoom in the oracle)
+    between the lightsheet stage and the final conversion; float64 arithmetic in scipy's order => bit-exact."""
+    from pystripe import core
+    stack = np.stack([synth.plane(50, shape), synth.plane(51, shape), np.full(shape, 9, np.uint16)])
+    got = core.process_img(stack, **kw)
+    for z in range(len(stack)):
+        ref = orc.process_img(stack[z].copy(), **kw)
+        assert got[z].shape == ref.shape and got[z].dtype == ref.dtype
+        _cmp_int(f"new_size/{kw}/{z}", got[z], ref)
+
+
+def test_process_img_new_size_after_flat_is_float32_zoom():
+    from pystripe import core
+    img = synth.plane(52, (160, 200))
+    flat = core.normalize_flat(synth.flat_field((160, 200)))
+    kw = dict(sigma=(16, 16), wavelet="db6", dark=100, padding_mode="reflect", new_size=(131, 163), d_type="uint16")
+    got = core.process_img(img, flat=flat, **kw)
+    ref = orc.process_img(img.copy(), flat=orc.normalize_flat(synth.flat_field((160, 200))), **kw)
+    _cmp_int("new_size/flat", got, ref)

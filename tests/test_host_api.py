@@ -171,3 +171,52 @@ def test_product_does_not_import_oracle():
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.h")):
         txt = f.read_text()
         assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("the oracle", ""), f
+
+
+@pytest.mark.parametrize("ins,outs", [((100, 130), (87, 111)), ((64, 64), (150, 97)), ((33, 47), (33, 90)),
+                                      ((1024, 1024), (864, 864)), ((2, 3), (7, 9)), ((1, 5), (4, 11)),
+                                      ((300, 200), (301, 199)), ((17, 19), (171, 23))])
+def test_resize_tables_reproduce_scipy_zoom_bit_for_bit(ins, outs):
+    """new_size (core.py:1356-1359 -> skimage.transform.resize -> scipy.ndimage.zoom(order=1, mode='mirror',
+    grid_mode=True)): the index / weight tables the library builds on the host (b2s_resize_table, GPU-free), evaluated
+    with the kernel's expression in numpy float64, equal the real scipy.ndimage.zoom in every bit."""
+    import ctypes as C
+    from scipy import ndimage as ndi
+    from pystripe import _native
+    L = _native.lib()
+
+    def table(n_in, n_out):
+        i0, i1 = np.zeros(n_out, np.int32), np.zeros(n_out, np.int32)
+        w0, w1 = np.zeros(n_out, np.float64), np.zeros(n_out, np.float64)
+        L.b2s_resize_table.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        assert L.b2s_resize_table(n_in, n_out, i0.ctypes.data, i1.ctypes.data, w0.ctypes.data, w1.ctypes.data) == 0
+        return i0, i1, w0, w1
+
+    img = np.random.default_rng(5).integers(0, 65536, ins).astype(np.uint16)
+    ref = ndi.zoom(img.astype(np.float64), [1 / f for f in np.divide(ins, outs)], order=1, mode="mirror", cval=0, grid_mode=True)
+    assert ref.shape == outs
+    iy0, iy1, wy0, wy1 = table(ins[0], outs[0])
+    ix0, ix1, wx0, wx1 = table(ins[1], outs[1])
+    v = img.astype(np.float64)
+    t = np.zeros(outs)
+    t = t + (v[iy0][:, ix0] * wy0[:, None]) * wx0[None, :]
+    t = t + (v[iy0][:, ix1] * wy0[:, None]) * wx1[None, :]
+    t = t + (v[iy1][:, ix0] * wy1[:, None]) * wx0[None, :]
+    t = t + (v[iy1][:, ix1] * wy1[:, None]) * wx1[None, :]
+    assert np.array_equal(t, ref)
+
+
+def test_new_size_geometry_and_rejections():
+    from pystripe import _native, core
+    p = _native.default_params()
+    p.height, p.width, p.in_dtype, p.out_dtype = 96, 128, _native.U16, _native.U16
+    p.process_img, p.rotate = 1, 90
+    p.new_height, p.new_width = 81, 108
+    info = _native.plan_geometry(p)
+    assert (info.out_height, info.out_width) == (108, 81)
+    p.new_height, p.new_width = 120, 100          # up along y, down along x: skimage's anti-aliasing Gaussian
+    with pytest.raises(NotImplementedError):
+        _native.plan_geometry(p)
+    assert core._resize_target((96, 128), (96, 128), None, (96, 128)) is None
+    assert core._resize_target((96, 128), (96, 128), (2, 2), (48, 64)) is None
+    assert core._resize_target((96, 128), (96, 128), (2, 2), (40, 50)) == (40, 50)
