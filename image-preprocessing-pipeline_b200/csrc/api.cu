@@ -284,6 +284,7 @@ struct b2s_plan {
     } slot[kSlots];
     int n_slots_ready = 0;
     size_t dwt_scratch_stride = 0;   // floats per plane of Slot::dwt_scratch (0: fused DWT kernels)
+    cudaEvent_t fork = nullptr;      // device-resident runs: the caller's stream position the slot streams wait for
     int pitch[B2S_MAX_LEVELS + 1];
     size_t plane_stride[B2S_MAX_LEVELS + 1];
     float *d_flat = nullptr;
@@ -822,6 +823,7 @@ int b2s_plan_create(b2s_context *ctx, const b2s_params *params, b2s_plan **out)
         if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B2S_ERR_CUDA, "lightsheet table setup failed");
     }
     for (int si = 0; rc == B2S_OK && si < b2s_plan::kSlots; ++si) rc = alloc_slot(pl, si);
+    if (rc == B2S_OK && cudaEventCreateWithFlags(&pl->fork, cudaEventDisableTiming) != cudaSuccess) rc = fail(ctx, B2S_ERR_CUDA, "cudaEventCreate failed");
     pl->p.dec_lo = nullptr;  // the caller's table is not retained
     if (rc) { b2s_plan_destroy(pl); return rc; }
     *out = pl;
@@ -836,6 +838,7 @@ void b2s_plan_destroy(b2s_plan *pl)
     for (void *p : pl->allocs) cudaFree(p);
     for (auto &kv : pl->xfft) b2s_xfft_destroy(kv.second);
     b2s_lightsheet_destroy(pl->ls);
+    if (pl->fork) cudaEventDestroy(pl->fork);
     for (auto &s : pl->slot) {
         if (s.h_in) cudaFreeHost(s.h_in);
         if (s.h_out) cudaFreeHost(s.h_out);
@@ -895,10 +898,29 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
 
     if (in_is_device && out_is_device) {
         cudaStream_t st = (cudaStream_t)stream;
+        // more than one batch: consecutive batches alternate between slots on the slots' own streams, forked from and
+        // joined back into the caller's stream, so the small launches of the deep levels of one batch (grids below one
+        // wave) overlap the large launches of the next.  Per-kernel timing keeps everything on the caller's stream.
+        static const int dev_slots_env = getenv("B2S_DEV_SLOTS") ? atoi(getenv("B2S_DEV_SLOTS")) : 3;
+        const int n_batches = (int)((n_planes + B - 1) / B);
+        const int ns = ctx->timing ? 1 : std::max(1, std::min(std::min(dev_slots_env, (int)b2s_plan::kSlots), n_batches));
+        if (ns > 1) {
+            CU(ctx, cudaEventRecord(pl->fork, st));
+            for (int k = 0; k < ns; ++k) CU(ctx, cudaStreamWaitEvent(pl->slot[k].stream, pl->fork, 0));
+        }
+        int si = 0;
         for (int64_t z = 0; z < n_planes; z += B) {
             const int nb = (int)std::min<int64_t>(B, n_planes - z);
-            int rc = enqueue_batch(pl, pl->slot[0], (const char *)in + z * in_plane, (char *)out + z * out_plane, nb, st);
+            b2s_plan::Slot &s = pl->slot[si];
+            int rc = enqueue_batch(pl, s, (const char *)in + z * in_plane, (char *)out + z * out_plane, nb, ns > 1 ? s.stream : st);
             if (rc) return rc;
+            si = (si + 1) % ns;
+        }
+        if (ns > 1) {
+            for (int k = 0; k < ns; ++k) {
+                CU(ctx, cudaEventRecord(pl->slot[k].done, pl->slot[k].stream));
+                CU(ctx, cudaStreamWaitEvent(st, pl->slot[k].done, 0));
+            }
         }
         return B2S_OK;
     }
