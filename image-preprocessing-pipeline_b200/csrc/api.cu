@@ -1,4 +1,7 @@
 // C ABI (include/b200stripe.h): contexts, plans (geometry, tables, workspace) and the batched run loop.
+#include <sched.h>
+
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -708,6 +711,47 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
     return B2S_OK;
 }
 
+// Page-locked host memory on the NUMA node the GPU hangs off: the pages are faulted in by the calling thread, so the
+// thread is confined to the GPU's local CPUs (sysfs local_cpulist of its PCI function) for the duration of the
+// allocation and its affinity restored afterwards.  With several GPUs per box (one process each) this keeps every
+// H2D / D2H stream on its own socket's memory controllers.  B2S_NUMA=0 disables it; any failure falls back to a plain
+// cudaMallocHost.
+cudaError_t numa_local_malloc_host(b2s_context *ctx, void **ptr, size_t bytes)
+{
+    static const int enabled = getenv("B2S_NUMA") ? atoi(getenv("B2S_NUMA")) : 1;
+    cpu_set_t saved, local;
+    bool bound = false;
+    if (enabled && sched_getaffinity(0, sizeof saved, &saved) == 0) {
+        char bus[32] = {0}, path[128];
+        if (cudaDeviceGetPCIBusId(bus, sizeof bus, ctx->device) == cudaSuccess) {
+            for (char *c = bus; *c; ++c) *c = (char)tolower(*c);
+            snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+            if (FILE *f = fopen(path, "r")) {
+                char line[4096] = {0};
+                if (fgets(line, sizeof line, f)) {
+                    CPU_ZERO(&local);
+                    int n_local = 0;
+                    for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+                        int a = 0, b = 0;
+                        const int k = sscanf(tok, "%d-%d", &a, &b);
+                        if (k == 1) b = a;
+                        if (k >= 1)
+                            for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+                                if (CPU_ISSET(c, &saved)) { CPU_SET(c, &local); ++n_local; }
+                    }
+                    if (n_local > 0 && sched_setaffinity(0, sizeof local, &local) == 0) bound = true;
+                }
+                fclose(f);
+            }
+        } else {
+            cudaGetLastError();
+        }
+    }
+    const cudaError_t e = cudaMallocHost(ptr, bytes);
+    if (bound) sched_setaffinity(0, sizeof saved, &saved);
+    return e;
+}
+
 bool is_pinned_host(const void *p)
 {
     cudaPointerAttributes at;
@@ -929,8 +973,8 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
     const bool in_pinned = in_is_device || is_pinned_host(in);
     const bool out_pinned = out_is_device || is_pinned_host(out);
     for (auto &s : pl->slot) {
-        if (!in_pinned && !s.h_in) CU(ctx, cudaMallocHost(&s.h_in, in_plane * B));
-        if (!out_pinned && !s.h_out) CU(ctx, cudaMallocHost(&s.h_out, out_plane * B));
+        if (!in_pinned && !s.h_in) CU(ctx, numa_local_malloc_host(ctx, &s.h_in, in_plane * B));
+        if (!out_pinned && !s.h_out) CU(ctx, numa_local_malloc_host(ctx, &s.h_out, out_plane * B));
     }
     struct Pending { int64_t z; int nb; bool active; } pend[b2s_plan::kSlots] = {};
     auto drain = [&](int si) -> int {
@@ -991,7 +1035,8 @@ int b2s_host_alloc(b2s_context *ctx, size_t bytes, void **ptr)
 {
     if (!ctx || !ptr) return B2S_ERR_INVALID;
     CU(ctx, cudaSetDevice(ctx->device));
-    CU(ctx, cudaMallocHost(ptr, bytes ? bytes : 16));
+    cudaError_t e = numa_local_malloc_host(ctx, ptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) return fail(ctx, B2S_ERR_CUDA, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
     return B2S_OK;
 }
 
