@@ -312,6 +312,7 @@ def run_b200(a):
             "config": {"workload": WORKLOAD, "planes_per_step_per_gpu": P, "planes_per_launch": min(a.batch, P),
                        "exact_summation_order": not a.fast,
                        "l2": "inputs larger than L2 (each step streams %d MB of uint16 input per GPU)" % (P * H * W * 2 // 2 ** 20),
+                       "device_resident_streams": int(os.environ.get("B2S_DEV_SLOTS", "3")),
                        "parallelism": f"z-shard x{world}, no collective"},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(P * H * W * 2),
                     "d2h_bytes_per_step": int(P * plan.out_shape[0] * plan.out_shape[1] * np.dtype(plan.out_dtype).itemsize),

@@ -12,10 +12,12 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 base = synth.stack(4, (2048, 2048))
 stack = torch.from_numpy(np.concatenate([base] * (n // 4))).cuda()
+import os
 flat = core.normalize_flat(synth.flat_field((2048, 2048)))
-plan = core._get_plan(0, (2048, 2048), _native.U16, process=1, sigma=(256, 256), level=0, wavelet="db10", threshold=None,
-                      padding_mode="reflect", bidirectional=False, log1p=True, flat=flat, dark=100, out_code=_native.U16,
-                      max_batch=n)
+sigma = tuple(int(v) for v in os.environ.get("PW_SIGMA", "256,256").split(","))      # PW_SIGMA=128,512 PW_WAVELET=coif15: config 5
+plan = core._get_plan(0, (2048, 2048), _native.U16, process=1, sigma=sigma, level=0, wavelet=os.environ.get("PW_WAVELET", "db10"),
+                      threshold=None, padding_mode="reflect", bidirectional=False, log1p=True,
+                      flat=None if os.environ.get("PW_NOFLAT") else flat, dark=100, out_code=_native.U16, max_batch=n)
 out = None
 for _ in range(reps):
     out = plan.run_torch(stack, out)
