@@ -227,6 +227,31 @@ def run_b200(a):
     e2e_v = world * a.steps * P * H * W / float(t.item()) / 1e6
     checksum = int(h_out[:: max(1, P // 4), ::128, ::128].astype(np.int64).sum())
 
+    # ---- the platform's ceiling for e2e: one step's host<->device bytes with NO kernels, both directions at once, all
+    # ranks at the same time (pinned buffers of the e2e leg, one stream per direction).  Not a bench value.
+    copy_only = None
+    try:
+        th_in, th_out = torch.from_numpy(h_in), torch.from_numpy(h_out)
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copies():
+            with torch.cuda.stream(s_up):
+                d_in.copy_(th_in, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                th_out.copy_(d_out, non_blocking=True)
+        copies()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            copies()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        copy_only = world * 3 * P * H * W / float(t.item()) / 1e6
+    except Exception as e:                                      # the probe must never cost the bench line
+        print(f"copy-only probe failed: {type(e).__name__}: {e}", file=sys.stderr)
+
     # ---- roofline: per-launch CUDA events around every kernel (separate pass so `value` is not perturbed)
     roof = None
     shares = {}
@@ -316,7 +341,10 @@ def run_b200(a):
                        "parallelism": f"z-shard x{world}, no collective"},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(P * H * W * 2),
                     "d2h_bytes_per_step": int(P * plan.out_shape[0] * plan.out_shape[1] * np.dtype(plan.out_dtype).itemsize),
-                    "timer": "host wall clock around the synchronous C-ABI call (internal streams), max over ranks"},
+                    "timer": "host wall clock around the synchronous C-ABI call (internal streams), max over ranks",
+                    "copy_only_ceiling": copy_only,
+                    "copy_only_note": "same bytes per step moved H2D + D2H with no kernels, all ranks at once (PCIe / host "
+                                      "memory ceiling of this box, in the metric's unit); e2e / ceiling is the overlap achieved"},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
             "kernel_time_shares": shares, "checksum": checksum,
         }

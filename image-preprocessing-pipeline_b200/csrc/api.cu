@@ -285,7 +285,9 @@ struct b2s_plan {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
     } slot[kSlots];
-    int n_slots_ready = 0;
+    int n_slots = kSlots;            // slots in use: fewer when kSlots x B planes of workspace do not fit the device
+    bool dry = false;                // sizing pass: dev_alloc only adds up
+    size_t dry_bytes = 0;
     size_t dwt_scratch_stride = 0;   // floats per plane of Slot::dwt_scratch (0: fused DWT kernels)
     cudaEvent_t fork = nullptr;      // device-resident runs: the caller's stream position the slot streams wait for
     int pitch[B2S_MAX_LEVELS + 1];
@@ -311,6 +313,7 @@ namespace {
 int dev_alloc(b2s_plan *pl, void **ptr, size_t bytes)
 {
     if (bytes == 0) bytes = 16;
+    if (pl->dry) { pl->dry_bytes += (bytes + 511) & ~(size_t)511; return B2S_OK; }
     cudaError_t e = cudaMalloc(ptr, bytes);
     if (e != cudaSuccess) return fail(pl->ctx, B2S_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
     pl->allocs.push_back(*ptr);
@@ -443,9 +446,17 @@ int build_tables(b2s_plan *pl)
                 const int n = axis == 0 ? g.mx[l] : g.my[l];
                 const int other = axis == 0 ? g.my[l] : g.mx[l];
                 const int img_len = axis == 0 ? g.PH : g.PW;
-                if (b2s_notch_smem(n) > 220 * 1024)
-                    return fail(ctx, B2S_ERR_UNSUPPORTED, "sub-band side %d too long for the shared-memory FFT", n);
-                if (!pl->fft.count(n)) {
+                static const bool no_xfft = getenv("B2S_NO_XFFT") != nullptr;
+                if (!pl->fft.count(n) && !pl->xfft.count(n) && p.exact && !no_xfft) {
+                    // exact mode: the scipy.fftpack mirror serves every covered length (whole stitched slices: 5000+
+                    // points); the FMA transform of fft.cu is only built for lengths the mirror does not cover
+                    B2sXfftPlan *xp = b2s_xfft_create(n);
+                    if (xp) pl->xfft[n] = xp;
+                    CU(ctx, cudaGetLastError());
+                }
+                if (!pl->fft.count(n) && !pl->xfft.count(n)) {
+                    if (b2s_notch_smem(n) > 220 * 1024)
+                        return fail(ctx, B2S_ERR_UNSUPPORTED, "sub-band side %d too long for the shared-memory FFT", n);
                     B2sFftPlan fp;
                     B2sFftHostTables ht;
                     b2s_fft_plan_init(&fp, n, &ht);
@@ -458,12 +469,6 @@ int build_tables(b2s_plan *pl)
                         CU(ctx, cudaMemcpy(*u.dst, u.src->data(), sizeof(float2) * u.src->size(), cudaMemcpyHostToDevice));
                     }
                     pl->fft[n] = fp;
-                    static const bool no_xfft = getenv("B2S_NO_XFFT") != nullptr;
-                    if (p.exact && !no_xfft) {
-                        B2sXfftPlan *xp = b2s_xfft_create(n);
-                        if (xp) pl->xfft[n] = xp;
-                        CU(ctx, cudaGetLastError());
-                    }
                 }
                 const double width_frac = g.pass_sigma[pass] / (double)img_len;
                 const double sigma_l = (double)other * width_frac;
@@ -522,8 +527,42 @@ int alloc_slot(b2s_plan *pl, int si)
         if (b2s_lightsheet_grid_elems(pl->ls, 2) &&
             (rc = dev_alloc(pl, (void **)&s.ls_cells, sizeof(unsigned short) * b2s_lightsheet_grid_elems(pl->ls, 2) * B))) return rc;
     }
+    if (pl->dry) return B2S_OK;
     CU(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    return B2S_OK;
+}
+
+// Whole stitched slices (20k x 15k planes, ~7 GB of workspace each) do not fit kSlots x max_batch times:
+// the batch is halved, then slots are dropped, until the workspace fits B2S_WORKSPACE_FRACTION (default 0.7) of the
+// free device memory.  The caller's max_batch is a ceiling, b2s_run loops over whatever batch the plan ended up with.
+int fit_workspace(b2s_plan *pl)
+{
+    b2s_context *ctx = pl->ctx;
+    size_t free_b = 0, total_b = 0;
+    CU(ctx, cudaMemGetInfo(&free_b, &total_b));
+    const char *fe = getenv("B2S_WORKSPACE_FRACTION");
+    double frac = fe ? atof(fe) : 0.7;
+    if (!(frac > 0.0 && frac <= 1.0)) frac = 0.7;
+    const double budget = frac * (double)free_b;
+    auto slot_bytes = [&](int B) {
+        const int keep = pl->B;
+        pl->B = B; pl->dry = true; pl->dry_bytes = 0;
+        alloc_slot(pl, 0);
+        pl->slot[0] = b2s_plan::Slot();
+        pl->dry = false; pl->B = keep;
+        return (double)pl->dry_bytes;
+    };
+    int B = pl->B;
+    while (B > 1 && b2s_plan::kSlots * slot_bytes(B) > budget) B = (B + 1) / 2;
+    int ns = b2s_plan::kSlots;
+    const double per_slot = slot_bytes(B);
+    while (ns > 1 && ns * per_slot > budget) --ns;
+    if (ns * per_slot > budget)
+        return fail(ctx, B2S_ERR_NOMEM, "one plane needs %.1f GB of workspace, %.1f GB of device memory are free",
+                    per_slot / 1e9, (double)free_b / 1e9);
+    pl->B = B;
+    pl->n_slots = ns;
     return B2S_OK;
 }
 
@@ -866,7 +905,8 @@ int b2s_plan_create(b2s_context *ctx, const b2s_params *params, b2s_plan **out)
                                        params->lightsheet_vs_background, 1);
         if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, B2S_ERR_CUDA, "lightsheet table setup failed");
     }
-    for (int si = 0; rc == B2S_OK && si < b2s_plan::kSlots; ++si) rc = alloc_slot(pl, si);
+    if (rc == B2S_OK) rc = fit_workspace(pl);
+    for (int si = 0; rc == B2S_OK && si < pl->n_slots; ++si) rc = alloc_slot(pl, si);
     if (rc == B2S_OK && cudaEventCreateWithFlags(&pl->fork, cudaEventDisableTiming) != cudaSuccess) rc = fail(ctx, B2S_ERR_CUDA, "cudaEventCreate failed");
     pl->p.dec_lo = nullptr;  // the caller's table is not retained
     if (rc) { b2s_plan_destroy(pl); return rc; }
@@ -947,7 +987,7 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
         // wave) overlap the large launches of the next.  Per-kernel timing keeps everything on the caller's stream.
         static const int dev_slots_env = getenv("B2S_DEV_SLOTS") ? atoi(getenv("B2S_DEV_SLOTS")) : 3;
         const int n_batches = (int)((n_planes + B - 1) / B);
-        const int ns = ctx->timing ? 1 : std::max(1, std::min(std::min(dev_slots_env, (int)b2s_plan::kSlots), n_batches));
+        const int ns = ctx->timing ? 1 : std::max(1, std::min(std::min(dev_slots_env, pl->n_slots), n_batches));
         if (ns > 1) {
             CU(ctx, cudaEventRecord(pl->fork, st));
             for (int k = 0; k < ns; ++k) CU(ctx, cudaStreamWaitEvent(pl->slot[k].stream, pl->fork, 0));
@@ -972,7 +1012,8 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
     // host path: kSlots slots, each with its own stream: H2D -> kernels -> D2H; the slots overlap each other
     const bool in_pinned = in_is_device || is_pinned_host(in);
     const bool out_pinned = out_is_device || is_pinned_host(out);
-    for (auto &s : pl->slot) {
+    for (int k = 0; k < pl->n_slots; ++k) {
+        b2s_plan::Slot &s = pl->slot[k];
         if (!in_pinned && !s.h_in) CU(ctx, numa_local_malloc_host(ctx, &s.h_in, in_plane * B));
         if (!out_pinned && !s.h_out) CU(ctx, numa_local_malloc_host(ctx, &s.h_out, out_plane * B));
     }
@@ -992,6 +1033,8 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
     // slots hides more of the PCIe time (measured at 2048^2: 8 planes per batch, 21.5 Gpx/s end to end vs 17.7 with 32)
     static const int host_cap = getenv("B2S_HOST_BATCH") ? atoi(getenv("B2S_HOST_BATCH")) : 8;
     const int Bh = std::max(1, std::min(B, host_cap));
+    static const int host_slots_env = getenv("B2S_HOST_SLOTS") ? atoi(getenv("B2S_HOST_SLOTS")) : b2s_plan::kSlots;
+    const int nsh = std::max(1, std::min(pl->n_slots, host_slots_env));
     int si = 0;
     int64_t z = 0;
     int nb_next = Bh < 4 ? Bh : 4;
@@ -1022,9 +1065,9 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
         CU(ctx, cudaEventRecord(s.done, s.stream));
         pend[si] = {z, nb, true};
         z += nb;
-        si = (si + 1) % b2s_plan::kSlots;
+        si = (si + 1) % nsh;
     }
-    for (int k = 0; k < b2s_plan::kSlots; ++k) {
+    for (int k = 0; k < pl->n_slots; ++k) {
         int rc = drain(k);
         if (rc) return rc;
     }
