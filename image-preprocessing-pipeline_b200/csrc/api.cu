@@ -126,6 +126,14 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
     else { g.n_passes = 2; g.pass_sigma[0] = s1; g.pass_sigma[1] = s2; }
     for (int i = 0; i < g.n_passes; ++i)
         if (g.pass_sigma[i] <= 0) return fail(ctx, B2S_ERR_INVALID, "np_notch: sigma must be positive");
+    if (p.bleach) {   // correct_bleaching, core.py:501-559 (non-max method) — runs on the cropped reconstruction
+        if (g.n_passes == 0)
+            return fail(ctx, B2S_ERR_UNSUPPORTED, "bleach correction without a destripe pass (sigma = (0, 0)) is not implemented");
+        if (!p.log1p)
+            return fail(ctx, B2S_ERR_UNSUPPORTED, "bleach correction needs log1p_normalization_needed=True (the reference's clip levels are log-domain)");
+        if (g.work_cols <= 6)
+            return fail(ctx, B2S_ERR_INVALID, "The length of the input vector x must be greater than padlen, which is 6.");
+    }
     g.fuse_flat = flat && !gauss && !ds && g.n_passes > 0;   // the prologue divides by flat; without a destripe it is a pre-op
 
     g.base_pad = g.pad_y = g.pad_x = 0;
@@ -281,6 +289,9 @@ struct b2s_plan {
         unsigned *mm2 = nullptr;                   // resize: per-plane min / max keys of the image it reads
         unsigned short *ls_grid = nullptr, *bg_grid = nullptr, *ls_cells = nullptr;
         unsigned *mm = nullptr;
+        double *bleach_scratch = nullptr;          // bleach correction: forward low-pass output, rows x (cols + 12) per plane
+        float *bleach_filt = nullptr;              //                    img_filter, rows x cols per plane
+        unsigned *bleach_max = nullptr;            //                    per-plane key of max(img_filter)
         void *h_in = nullptr, *h_out = nullptr;    // pinned staging
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
@@ -508,6 +519,11 @@ int alloc_slot(b2s_plan *pl, int si)
             (rc = dev_alloc(pl, (void **)&s.dwt_scratch, sizeof(float) * pl->dwt_scratch_stride * B))) return rc;
     }
     const size_t in_elems = (size_t)g.in_rows * g.in_cols, work_elems = (size_t)g.work_rows * g.work_cols;
+    if (p.bleach) {
+        if ((rc = dev_alloc(pl, (void **)&s.bleach_scratch, sizeof(double) * (size_t)g.work_rows * (g.work_cols + 12) * B))) return rc;
+        if ((rc = dev_alloc(pl, (void **)&s.bleach_filt, sizeof(float) * work_elems * B))) return rc;
+        if ((rc = dev_alloc(pl, (void **)&s.bleach_max, sizeof(unsigned) * B))) return rc;
+    }
     if ((rc = dev_alloc(pl, &s.d_in, in_elems * dtype_size(p.in_dtype) * B))) return rc;
     if ((rc = dev_alloc(pl, &s.d_out, (size_t)g.out_rows * g.out_cols * dtype_size(g.out_dtype) * B))) return rc;
     if (p.process_img) {
@@ -625,6 +641,7 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             a.pad_mode = p.pad_mode;
             a.base_pad = g.base_pad;
             a.use_log1p = p.log1p;
+            a.pad_value = p.pad_mode == B2S_PAD_CONSTANT ? (float)p.pad_constant : 0.f;
             a.out = padded;
             a.n_groups = pl->n_row_groups;
             a.row_src = pl->d_row_src;
@@ -674,6 +691,19 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             }
         }
         if (p.debug_stop_after == B2S_STAGE_INVERSE) return B2S_OK;
+        if (p.bleach) {   // core.py:1131-1139: after the crop, before expm1
+            ClassTimer t(ctx, st, B2S_K_OTHER, 3);
+            B2sBleachArgs b;
+            b.img = padded;
+            b.base_pad = g.base_pad; b.rows = g.work_rows; b.cols = g.work_cols;
+            b.b0 = p.bleach_b0; b.b1 = p.bleach_b1; b.a1 = p.bleach_a1; b.zi = p.bleach_zi;
+            b.clip_min = p.bleach_clip_min; b.clip_med = p.bleach_clip_med; b.clip_max = p.bleach_clip_max;
+            b.scratch = s.bleach_scratch;
+            b.scratch_plane_stride = (size_t)g.work_rows * (g.work_cols + 12);
+            b.filt = s.bleach_filt;
+            b.maxkey = s.bleach_max;
+            b2s_launch_bleach(b, nb, st);
+        }
     }
     {
         B2sEpilogueArgs e;

@@ -30,6 +30,7 @@ struct B2sPrologueArgs {
     const float *flat;     // optional (src_rows x src_cols)
     int pad_mode, base_pad;
     int use_log1p;
+    float pad_value;       // constant padding: the fill value (core.py:1101-1105), 0 otherwise
     B2sImg out;            // padded image
     // numpy.pad as tables (built once per plan): padded rows grouped by the source row they replicate
     int n_groups;          // source rows + padded rows without a source (constant mode)
@@ -136,6 +137,20 @@ B2sXfftPlan *b2s_xfft_create(int n);
 void b2s_xfft_destroy(B2sXfftPlan *pl);
 void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B2sImg &img, int along_cols, int n_planes,
                             int sm_count, cudaStream_t s);
+
+// bleach.cu ----------------------------------------------------------------------------------------------------
+struct B2sBleachArgs {
+    B2sImg img;                    // padded log-domain image; the rows x cols window starts at (base_pad, base_pad)
+    int base_pad, rows, cols;
+    double b0, b1, a1, zi;         // butter(1, f, output='sos') = [b0, b1, 0, 1, a1, 0]; sosfilt_zi(sos)[0, 0]
+    double clip_min, clip_med, clip_max;
+    double *scratch;               // forward-pass output, rows x (cols + 12) doubles per plane
+    size_t scratch_plane_stride;   // doubles
+    float *filt;                   // img_filter, rows x cols per plane
+    unsigned *maxkey;              // per plane: order-preserving key of max(img_filter)
+};
+// correct_bleaching (core.py:501-559, non-max method) in place on the cropped window
+void b2s_launch_bleach(const B2sBleachArgs &a, int n_planes, cudaStream_t s);
 
 // lightsheet.cu -------------------------------------------------------------------------------------------------
 struct B2sLightsheet;

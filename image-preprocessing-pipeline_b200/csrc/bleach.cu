@@ -1,0 +1,158 @@
+// correct_bleaching (reference pystripe/core.py:501-559, non-max method) and butter_lowpass_filter (core.py:493-499) on
+// the cropped log-domain image, between the reconstruction and expm1 (core.py:1131-1148).
+//
+//   img_filter = img.copy(); img_filter[img_filter == 0] = clip_med; clip(img_filter, clip_min, clip_max)
+//   img_filter = sosfiltfilt(butter(1, frequency, output='sos'), img_filter).astype(float32)     # along each row
+//   img = img / img_filter * max(img_filter)                                                      # float32
+//
+// scipy.signal.sosfiltfilt, restated operation for operation (checked bit-for-bit against scipy on the CPU by
+// tests/test_oracle.py::test_sosfiltfilt_restatement and on the GPU against the reference run verbatim):
+//   * odd extension by edge = 6 samples per side, evaluated in the image's float32 (2*x[0] - x[6-j], 2*x[n-1] - x[n-2-k]);
+//   * one second-order section [b0, b1, 0, 1, a1, 0] in float64, direct form II transposed as _sosfilt.pyx runs it:
+//       y = b0*x + z;  z = (b1*x - a1*y) [+ 0]        (separate multiplies and adds: file compiled with -fmad=false)
+//     started at z = zi * x_ext[0]; the output is reversed and filtered again from z = zi * y[last]; the edges are
+//     dropped and the result is cast to float32.
+// The recurrence is sequential along a row, rows are independent: one thread per row, 64 rows per CTA, the row segments
+// pass through shared-memory tiles so that global loads/stores stay coalesced (a warp moves 128 / 256 contiguous bytes
+// of one row).  The forward output (float64) goes through a per-slot scratch buffer that the same CTA reads back.
+#include "b2s_internal.h"
+
+namespace {
+
+constexpr int kRows = 64;      // rows (= threads) per CTA
+constexpr int kChunk = 32;     // samples per tile
+constexpr int kEdge = 6;       // sosfiltfilt: ntaps = 2*1 + 1 - min(#(b2 == 0), #(a2 == 0)) = 2; edge = 3 * ntaps
+
+__device__ __forceinline__ unsigned f2key(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// the value the low-pass filter sees at column c of a row (float32): zero -> clip_med, then numpy.clip
+__device__ __forceinline__ float filt_input(const float *row, int c, const B2sBleachArgs &a)
+{
+    float v = row[c];
+    if (v == 0.0f) v = (float)a.clip_med;
+    double d = (double)v;
+    d = d < a.clip_min ? a.clip_min : d;      // numpy.clip = minimum(maximum(x, lo), hi)
+    d = d > a.clip_max ? a.clip_max : d;
+    return (float)d;
+}
+
+// sample j of the odd-extended row (float32 arithmetic, scipy.signal._arraytools.odd_ext)
+__device__ __forceinline__ float ext_sample(const float *row, int j, int n, const B2sBleachArgs &a)
+{
+    if (j < kEdge) return __fsub_rn(2.0f * filt_input(row, 0, a), filt_input(row, kEdge - j, a));
+    if (j < kEdge + n) return filt_input(row, j - kEdge, a);
+    return __fsub_rn(2.0f * filt_input(row, n - 1, a), filt_input(row, n - 2 - (j - kEdge - n), a));
+}
+
+__global__ void __launch_bounds__(kRows) k_bleach_lowpass(B2sBleachArgs a)
+{
+    __shared__ float s_in[kRows][kChunk + 1];
+    __shared__ double s_y[kRows][kChunk + 1];
+    __shared__ float s_red[kRows / 32];
+    const int tid = threadIdx.x;
+    const size_t plane = blockIdx.y;
+    const int r0 = blockIdx.x * kRows;
+    const int n = a.cols, N = n + 2 * kEdge;
+    const float *img = a.img.ptr + plane * a.img.plane_stride + (size_t)a.base_pad * a.img.pitch + a.base_pad;
+    double *scr = a.scratch + plane * a.scratch_plane_stride;
+    float *filt = a.filt + plane * (size_t)a.rows * n;
+    const bool live = r0 + tid < a.rows;
+    const double b0 = a.b0, b1 = a.b1, a1 = a.a1;
+    double z = 0.0, last = 0.0;
+
+    // forward over the extended row
+    for (int j0 = 0; j0 < N; j0 += kChunk) {
+        for (int e = tid; e < kRows * kChunk; e += kRows) {
+            const int rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = j0 + jj;
+            if (r < a.rows && j < N) s_in[rr][jj] = ext_sample(img + (size_t)r * a.img.pitch, j, n, a);
+        }
+        __syncthreads();
+        if (live) {
+            if (j0 == 0) z = a.zi * (double)s_in[tid][0];
+            const int m = min(kChunk, N - j0);
+            for (int jj = 0; jj < m; ++jj) {
+                const double x = (double)s_in[tid][jj];
+                const double y = __dadd_rn(__dmul_rn(b0, x), z);
+                z = __dsub_rn(__dmul_rn(b1, x), __dmul_rn(a1, y));
+                s_y[tid][jj] = y;
+                last = y;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < kRows * kChunk; e += kRows) {
+            const int rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = j0 + jj;
+            if (r < a.rows && j < N) scr[(size_t)r * N + j] = s_y[rr][jj];
+        }
+        __syncthreads();     // also orders this CTA's scratch writes before its own reads below
+    }
+
+    // backward: the reversed forward output through the same section, started from zi * y[last]
+    z = a.zi * last;
+    float mx = -INFINITY;
+    for (int j0 = ((N - 1) / kChunk) * kChunk; j0 >= 0; j0 -= kChunk) {
+        for (int e = tid; e < kRows * kChunk; e += kRows) {
+            const int rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = j0 + jj;
+            if (r < a.rows && j < N) s_y[rr][jj] = scr[(size_t)r * N + j];
+        }
+        __syncthreads();
+        if (live) {
+            const int m = min(kChunk, N - j0);
+            for (int jj = m - 1; jj >= 0; --jj) {
+                const double x = s_y[tid][jj];
+                const double y = __dadd_rn(__dmul_rn(b0, x), z);
+                z = __dsub_rn(__dmul_rn(b1, x), __dmul_rn(a1, y));
+                const float f = (float)y;
+                s_in[tid][jj] = f;
+                const int j = j0 + jj;
+                if (j >= kEdge && j < kEdge + n) mx = fmaxf(mx, f);
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < kRows * kChunk; e += kRows) {
+            const int rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = j0 + jj;
+            if (r < a.rows && j >= kEdge && j < kEdge + n) filt[(size_t)r * n + (j - kEdge)] = s_in[rr][jj];
+        }
+        __syncthreads();
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kRows / 32; ++w) mx = fmaxf(mx, s_red[w]);
+        atomicMax(a.maxkey + plane, f2key(mx));
+    }
+}
+
+// img = img / img_filter * max(img_filter), float32, in place on the cropped window of the padded image
+__global__ void __launch_bounds__(256) k_bleach_apply(B2sBleachArgs a)
+{
+    const size_t plane = blockIdx.z;
+    const int r = blockIdx.y;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= a.cols) return;
+    float *p = a.img.ptr + plane * a.img.plane_stride + (size_t)(a.base_pad + r) * a.img.pitch + a.base_pad + c;
+    const float f = a.filt[plane * (size_t)a.rows * a.cols + (size_t)r * a.cols + c];
+    const float mx = key2f(a.maxkey[plane]);
+    *p = __fmul_rn(__fdiv_rn(*p, f), mx);
+}
+
+}  // namespace
+
+void b2s_launch_bleach(const B2sBleachArgs &a, int n_planes, cudaStream_t s)
+{
+    cudaMemsetAsync(a.maxkey, 0, sizeof(unsigned) * n_planes, s);
+    k_bleach_lowpass<<<dim3((a.rows + kRows - 1) / kRows, n_planes), kRows, 0, s>>>(a);
+    k_bleach_apply<<<dim3((a.cols + 255) / 256, a.rows, n_planes), 256, 0, s>>>(a);
+}

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) k_prologue(B2sPrologueArgs a)
         float *drow = a.out.ptr + plane * a.out.plane_stride + (size_t)a.row_targets[t] * a.out.pitch;
 #pragma unroll 4
         for (int c4 = threadIdx.x; c4 < q4; c4 += 256) {
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 o = make_float4(a.pad_value, a.pad_value, a.pad_value, a.pad_value);
             if (sy >= 0) {
                 const int4 m = __ldg(cm + c4);
                 if (m.x >= 0) o.x = s_row[m.x];

@@ -37,6 +37,10 @@ class Params(C.Structure):
         ("convert_to_16bit", C.c_int32), ("convert_to_8bit", C.c_int32), ("bit_shift_to_right", C.c_int32),
         ("rotate", C.c_int32), ("flip_upside_down", C.c_int32), ("reference_quirks", C.c_int32),
         ("new_height", C.c_int32), ("new_width", C.c_int32),
+        ("bleach", C.c_int32), ("bleach_reserved", C.c_int32),
+        ("bleach_b0", C.c_double), ("bleach_b1", C.c_double), ("bleach_a1", C.c_double), ("bleach_zi", C.c_double),
+        ("bleach_clip_min", C.c_double), ("bleach_clip_med", C.c_double), ("bleach_clip_max", C.c_double),
+        ("pad_constant", C.c_double),
         ("max_batch", C.c_int32), ("debug_stop_after", C.c_int32), ("exact", C.c_int32),
     ]
 

@@ -260,7 +260,7 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
               log1p, flat=None, gaussian=False, down_sample=None, down_sample_method='max', dark=0, lightsheet=False,
               artifact_length=150, background_window_size=200, percentile=0.25, lightsheet_vs_background=2.0,
               convert_to_16bit=False, convert_to_8bit=False, bit_shift_to_right=8, rotate=0, flip=False,
-              out_code=None, max_batch=None, stop_after=0, exact=None, new_size=None):
+              out_code=None, max_batch=None, stop_after=0, exact=None, new_size=None, bleach=None, pad_constant=0.0):
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
     s1, s2 = float(sigma[0]), float(sigma[1])
@@ -292,7 +292,8 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
            bool(bidirectional), bool(log1p), threshold is not None and threshold <= 0, flat_key, bool(gaussian), ds,
            method, float(dark or 0), bool(lightsheet), artifact_length, background_window_size, percentile,
            lightsheet_vs_background, bool(convert_to_16bit), bool(convert_to_8bit), bit_shift_to_right, rotate,
-           bool(flip), out_code, max_batch, stop_after, exact, REFERENCE_QUIRKS, new_size)
+           bool(flip), out_code, max_batch, stop_after, exact, REFERENCE_QUIRKS, new_size, bleach,
+           float(pad_constant) if (destripe and mode == 'constant') else 0.0)
     with _plans_lock:
         plan = _plans.get(key)
         if plan is not None:
@@ -327,6 +328,11 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
         p.reference_quirks = int(REFERENCE_QUIRKS)
         if new_size is not None:
             p.new_height, p.new_width = int(new_size[0]), int(new_size[1])
+        if bleach is not None:
+            (p.bleach_b0, p.bleach_b1, p.bleach_a1, p.bleach_zi,
+             p.bleach_clip_min, p.bleach_clip_med, p.bleach_clip_max) = bleach
+            p.bleach = 1
+        p.pad_constant = float(pad_constant)
         p.max_batch = int(max_batch or MAX_BATCH)
         p.debug_stop_after = int(stop_after)
         p.exact = int(EXACT if exact is None else exact)
@@ -396,6 +402,44 @@ def _code_of(img):
 # --------------------------------------------------------------------------------------------------------------
 # filter_streaks  (core.py:982-1159)
 # --------------------------------------------------------------------------------------------------------------
+def _bleach_plan_args(frequency, clip_min, clip_med, clip_max, max_method, enable_masking):
+    """Host side of correct_bleaching (core.py:501-559) and butter_lowpass_filter (core.py:493-499): the reference's
+    argument checks, the first-order Butterworth section and its steady-state start value from scipy.signal (filter
+    design, a handful of scalars), and the clip levels in the precision numpy.clip compares them in.  Returns
+    (bleach tuple for the plan | None, constant-padding value)."""
+    pad_constant = 0.0
+    if clip_min is not None:                                            # core.py:1101-1105
+        pad_constant = float(np.float32(np.log1p(clip_min)))
+    if enable_masking:
+        raise NotImplementedError("enable_masking (get_img_mask: morphology + flood fill, core.py:475-490) is not part "
+                                  "of the GPU hot path (SURVEY.md §8f N3)")
+    if frequency is None:
+        return None, pad_constant
+    if clip_min is None or clip_med is None or clip_max is None:
+        raise NotImplementedError("bleach correction with clip levels left to threshold_multiotsu (core.py:1066-1077) is "
+                                  "not implemented: pass bleach_correction_clip_min / _med / _max")
+    if max_method:
+        raise NotImplementedError("bleach_correction_max_method=True is not implemented on the GPU path")
+    ok = (float, float32, np.float64)
+    assert isinstance(frequency, ok) and frequency > 0                   # core.py:521-527
+    assert isinstance(clip_min, ok) and clip_min >= 0
+    assert isinstance(clip_med, ok) and clip_med > clip_min
+    assert isinstance(clip_max, ok) and clip_max > clip_min
+    assert clip_max > clip_med
+    clip_min_lb = np.log1p(1)                                           # numpy float64 scalar (core.py:529-531)
+    if clip_min < clip_min_lb:
+        clip_min = clip_min_lb
+
+    def as_clip_sees(v):      # numpy.clip(float32 array, bound): a Python float is weak (-> float32), numpy.float64 is not
+        return float(v) if isinstance(v, np.float64) else float(np.float32(v))
+    from scipy.signal import butter, sosfilt_zi
+    sos = butter(1, frequency, output='sos')                            # core.py:495: [[b0, b1, 0, 1, a1, 0]]
+    zi = sosfilt_zi(sos)
+    assert sos.shape == (1, 6) and sos[0, 2] == 0 and sos[0, 5] == 0 and sos[0, 3] == 1 and zi[0, 1] == 0
+    return (float(sos[0, 0]), float(sos[0, 1]), float(sos[0, 4]), float(zi[0, 0]),
+            as_clip_sees(clip_min), float(np.float32(clip_med)), as_clip_sees(clip_max)), pad_constant
+
+
 def filter_streaks(
         img,
         sigma: Tuple[int, int] = (250, 250),
@@ -421,18 +465,20 @@ def filter_streaks(
 
     img: (H, W) or (Z, H, W); numpy array (host round trip) or CUDA torch tensor (zero-copy, current stream).
     `gpu_semaphore`, `crossover` are accepted and ignored (the thresholded dual-band variant is unreachable in the
-    reference, core.py:1113-1117).  Bleach correction / masking are outside the hot path: NotImplementedError.
+    reference, core.py:1113-1117).  Bleach correction (core.py:501-559) runs on the GPU for explicit clip levels and the
+    non-max method; masking and multi-Otsu clip levels raise NotImplementedError.
     """
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
     if sigma[0] == sigma[1] == 0 and bleach_correction_frequency is None:
         return img                                                      # core.py:1058-1059
-    if bleach_correction_frequency is not None or enable_masking:
-        raise NotImplementedError("bleach correction / masking are not part of the GPU hot path (SURVEY.md §8f N3)")
+    bleach, pad_constant = _bleach_plan_args(bleach_correction_frequency, bleach_correction_clip_min,
+                                             bleach_correction_clip_med, bleach_correction_clip_max,
+                                             bleach_correction_max_method, enable_masking)
     arr, restore = _as_supported(img)
     plan = _get_plan(_device_of(arr), arr.shape[-2:], _code_of(arr), process=0, sigma=sigma, level=level,
                      wavelet=wavelet, threshold=threshold, padding_mode=padding_mode, bidirectional=bidirectional,
-                     log1p=log1p_normalization_needed)
+                     log1p=log1p_normalization_needed, bleach=bleach, pad_constant=pad_constant)
     out = _run(plan, arr)
     if verbose:
         print(f"de-striping applied: sigma={sigma}, level={level}, wavelet={wavelet}, crossover={crossover}, "
@@ -506,8 +552,11 @@ def process_img(
     """Per-plane enhancement in the reference's order of operations (core.py:1190-1381), fused on the GPU:
     uniform-plane shortcut -> flat -> 5x5 Gaussian -> block down-sample -> filter_streaks -> dark -> lightsheet ->
     8/16-bit conversion -> flip -> rot90.   img: (H, W) or (Z, H, W), numpy or CUDA torch tensor."""
-    if bleach_correction_frequency is not None or exclude_dark_edges_set_them_to_zero:
-        raise NotImplementedError("bleach correction / dark-edge exclusion are outside the GPU hot path")
+    if exclude_dark_edges_set_them_to_zero:
+        raise NotImplementedError("dark-edge exclusion is outside the GPU hot path")
+    bleach, pad_constant = _bleach_plan_args(bleach_correction_frequency, bleach_correction_clip_min,
+                                             bleach_correction_clip_med, bleach_correction_clip_max,
+                                             bleach_correction_max_method, False)
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
     arr, restore = _as_supported(img)
@@ -534,6 +583,8 @@ def process_img(
                             "(reference core.py:1250 as written)")
     if not tuple(sigma) > (0, 0):                                       # core.py:1302
         sigma = (0, 0)
+        if bleach is not None:
+            raise NotImplementedError("bleach correction without a destripe pass (sigma = (0, 0)) is not implemented")
     plan = _get_plan(_device_of(arr), shape, _code_of(arr), process=1, sigma=sigma, level=level, wavelet=wavelet,
                      threshold=threshold, padding_mode=padding_mode, bidirectional=bidirectional,
                      log1p=log1p_normalization_needed, flat=flat, gaussian=gaussian_filter_2d, down_sample=down_sample,
@@ -542,7 +593,7 @@ def process_img(
                      percentile=percentile, lightsheet_vs_background=lightsheet_vs_background,
                      convert_to_16bit=convert_to_16bit, convert_to_8bit=convert_to_8bit,
                      bit_shift_to_right=bit_shift_to_right, rotate=rotate, flip=flip_upside_down, out_code=out_code,
-                     max_batch=_max_batch, new_size=resize_to)
+                     max_batch=_max_batch, new_size=resize_to, bleach=bleach, pad_constant=pad_constant)
     out = _run(plan, arr)
     if out_code == _native.F32 and plan.info.out_dtype == _native.F32 and d_type != np.float32:
         out = out.astype(d_type) if not _native._is_torch(out) else out.double()

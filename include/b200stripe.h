@@ -80,6 +80,18 @@ typedef struct b2s_params {
     int32_t new_height, new_width;/* new_size (core.py:1356-1359): skimage.transform.resize(order 1) after the
                                      lightsheet stage, before the 8/16-bit conversion; 0 = none.  Pure up-sizing
                                      (anti_aliasing with sigma 0) and down-sizing (anti_aliasing=False) only     */
+    /* --- bleach correction inside filter_streaks (core.py:501-559, 1131-1148) -------------------------- */
+    int32_t bleach;               /* 1: correct_bleaching (non-max method) on the cropped log image, before expm1:
+                                     filter = sosfiltfilt(butter(1, frequency), clip(img with 0 -> clip_med)) along each
+                                     row in float64 (scipy.signal, odd extension of 6 samples, sosfilt_zi start), cast to
+                                     float32; img = img / filter * max(filter)                                    */
+    int32_t bleach_reserved;
+    double bleach_b0, bleach_b1, bleach_a1, bleach_zi; /* the one section butter(1, f, output='sos') returns:
+                                     [b0, b1, 0, 1, a1, 0], and sosfilt_zi(sos)[0, 0] (host: scipy, core.py:495-497) */
+    double bleach_clip_min, bleach_clip_med, bleach_clip_max; /* bounds as numpy.clip compares them (a weak Python
+                                     float is rounded to float32 by the caller; log1p(1) stays float64, core.py:529-531) */
+    double pad_constant;          /* padding_mode='constant': log1p(bleach_correction_clip_min) when that is given
+                                     (core.py:1101-1105), else 0                                                  */
     /* --- execution ------------------------------------------------------------------------------------ */
     int32_t max_batch;            /* planes processed per launch group (workspace is sized for this)         */
     int32_t debug_stop_after;     /* b2s_stage; 0 in production                                             */

@@ -128,14 +128,65 @@ def padded_geometry(shape, sigma, padding_mode):
     return base_pad, pad_y, pad_x
 
 
+def butter_lowpass_filter(img, cutoff_frequency, order=1):
+    """core.py:493-499 (scipy.signal is the real library here, as in the reference)."""
+    from scipy.signal import butter, sosfiltfilt
+    d_type = img.dtype
+    sos = butter(order, cutoff_frequency, output='sos')
+    return sosfiltfilt(sos, img).astype(d_type)
+
+
+def correct_bleaching(img, frequency, clip_min, clip_med, clip_max):
+    """core.py:501-559, non-max method, numpy branch (float32 throughout; the numexpr expression has the same order)."""
+    clip_min_lb = np.log1p(1)
+    if clip_min < clip_min_lb:
+        clip_min = clip_min_lb
+    img_filter = img.copy()
+    img_filter[img_filter == 0] = clip_med
+    np.clip(img_filter, clip_min, clip_max, out=img_filter)
+    img_filter = butter_lowpass_filter(img_filter, frequency)
+    img_filter_max = np.max(img_filter)
+    img = img / img_filter
+    img *= img_filter_max
+    return img
+
+
+def sosfiltfilt_order1_restated(x, sos, zi0):
+    """scipy.signal.sosfiltfilt for ONE first-order section [b0, b1, 0, 1, a1, 0] along the last axis of a float32 array,
+    restated operation for operation — the sequence csrc/bleach.cu executes (odd extension by 6 samples in float32,
+    direct form II transposed in float64 with separate multiplies and adds, start value zi * first sample, the reversed
+    second pass, edges dropped).  tests/test_oracle.py pins it bit-for-bit against scipy."""
+    b0, b1, a1 = float(sos[0, 0]), float(sos[0, 1]), float(sos[0, 4])
+    edge = 6
+    x = np.asarray(x, dtype=np.float32)
+    left = (np.float32(2) * x[..., :1] - x[..., edge:0:-1]).astype(np.float32)
+    right = (np.float32(2) * x[..., -1:] - x[..., -2:-(edge + 2):-1]).astype(np.float32)
+    ext = np.concatenate([left, x, right], axis=-1).astype(np.float64)
+
+    def one_pass(sig, start):
+        y = np.empty_like(sig)
+        z = zi0 * start
+        for n in range(sig.shape[-1]):              # vectorised over rows, sequential along the axis
+            xn = sig[..., n]
+            yn = b0 * xn + z
+            z = b1 * xn - a1 * yn
+            y[..., n] = yn
+        return y
+    y = one_pass(ext, ext[..., 0])
+    y = one_pass(y[..., ::-1], y[..., -1])[..., ::-1]
+    return y[..., edge:-edge]
+
+
 def filter_streaks(img, sigma=(250, 250), level=0, wavelet='db9', crossover=10, threshold=None,
                    padding_mode="wrap", bidirectional=False, log1p_normalization_needed=True,
-                   return_log_domain=False):
-    """core.py:982-1159 without the bleach-correction / masking options (never enabled by a caller)."""
+                   return_log_domain=False, bleach_correction_frequency=None, bleach_correction_clip_min=None,
+                   bleach_correction_clip_med=None, bleach_correction_clip_max=None):
+    """core.py:982-1159 without masking, multi-Otsu clip levels and the max-method of the bleach correction."""
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
     s1, s2 = sigma
     if s1 == s2 == 0:
+        assert bleach_correction_frequency is None
         return img
     d_type = img.dtype
     if log1p_normalization_needed:
@@ -144,11 +195,18 @@ def filter_streaks(img, sigma=(250, 250), level=0, wavelet='db9', crossover=10, 
     base_pad, pad_y, pad_x = padded_geometry(shape, sigma, padding_mode)
     if pad_y > 0 or pad_x > 0 or base_pad > 0:
         mode = padding_mode.lower() if padding_mode else 'reflect'
-        img = np.pad(img, ((base_pad, base_pad + pad_y), (base_pad, base_pad + pad_x)), mode=mode)
+        if mode == 'constant' and bleach_correction_clip_min is not None:          # core.py:1101-1105
+            img = np.pad(img, ((base_pad, base_pad + pad_y), (base_pad, base_pad + pad_x)), mode='constant',
+                         constant_values=np.log1p(bleach_correction_clip_min))
+        else:
+            img = np.pad(img, ((base_pad, base_pad + pad_y), (base_pad, base_pad + pad_x)), mode=mode)
     img = filter_streak_dual_band(img, s1, s2, level, wavelet, threshold, axes=(-1, -2) if bidirectional else -1)
     if pad_y > 0 or pad_x > 0 or base_pad > 0:
         img = img[base_pad: img.shape[0] - (base_pad + pad_y), base_pad: img.shape[1] - (base_pad + pad_x)]
         assert img.shape == shape
+    if bleach_correction_frequency is not None:                                    # core.py:1131-1139
+        img = correct_bleaching(np.ascontiguousarray(img), bleach_correction_frequency, bleach_correction_clip_min,
+                                bleach_correction_clip_med, bleach_correction_clip_max)
     if return_log_domain:
         return np.ascontiguousarray(img)
     if log1p_normalization_needed:
@@ -324,7 +382,9 @@ def process_img(img, flat=None, gaussian_filter_2d=False, down_sample=None, down
                 padding_mode="wrap", bidirectional=False, log1p_normalization_needed=True, dark=0,
                 lightsheet=False, artifact_length=150, background_window_size=200, percentile=0.25,
                 lightsheet_vs_background=2.0, rotate=0, flip_upside_down=False, convert_to_16bit=False,
-                convert_to_8bit=False, bit_shift_to_right=8, d_type=None, quirks=False):
+                convert_to_8bit=False, bit_shift_to_right=8, d_type=None, quirks=False,
+                bleach_correction_frequency=None, bleach_correction_clip_min=None, bleach_correction_clip_med=None,
+                bleach_correction_clip_max=None):
     """core.py:1190-1381 (order of operations preserved; bleach / dark-edge options not restated)."""
     if tile_size is None:
         tile_size = img.shape
@@ -361,7 +421,11 @@ def process_img(img, flat=None, gaussian_filter_2d=False, down_sample=None, down
     if tuple(sigma) > (0, 0):                                          # :1302-1320
         img = filter_streaks(img, sigma=sigma, level=level, wavelet=wavelet, threshold=threshold,
                              padding_mode=padding_mode, bidirectional=bidirectional,
-                             log1p_normalization_needed=log1p_normalization_needed)
+                             log1p_normalization_needed=log1p_normalization_needed,
+                             bleach_correction_frequency=bleach_correction_frequency,
+                             bleach_correction_clip_min=bleach_correction_clip_min,
+                             bleach_correction_clip_med=bleach_correction_clip_med,
+                             bleach_correction_clip_max=bleach_correction_clip_max)
     if dark is not None and dark > 0:                                  # :1324-1330 (numpy branch)
         img = np.where(img > dark, img - dark, 0)
     if lightsheet:                                                     # :1333-1348

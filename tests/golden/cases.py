@@ -33,8 +33,24 @@ def all_cases():
     yield "fs_f32", fs, a.astype(np.float32), dict(sigma=(24, 24), wavelet="db8", padding_mode="reflect")
     yield "fs_db10_big", fs, d, dict(sigma=(32, 32), wavelet="db10", padding_mode="reflect")
     yield "fs_u8", fs, (a >> 4).astype(np.uint8), dict(sigma=(16, 16), wavelet="db4")
+    # bleach correction (core.py:501-559): explicit clip levels (log domain), non-max method; real scipy.signal in the reference
+    bl = dict(bleach_correction_frequency=1 / 64.0, bleach_correction_clip_min=4.8, bleach_correction_clip_med=5.6,
+              bleach_correction_clip_max=7.4)
+    yield "fs_bleach_db9_reflect", fs, d, dict(sigma=(32, 32), wavelet="db9", padding_mode="reflect", **bl)
+    yield "fs_bleach_bidir_wrap_lowclip", fs, a, dict(sigma=(16, 16), wavelet="db6", bidirectional=True,
+                                                     bleach_correction_frequency=0.01, bleach_correction_clip_min=0.5,
+                                                     bleach_correction_clip_med=5.0, bleach_correction_clip_max=6.5)
+    yield "fs_bleach_constant_pad_f32", fs, a.astype(np.float32), dict(sigma=(24, 24), wavelet="db4", padding_mode="constant", **bl)
+    yield "fs_clipmin_constant_pad_nofreq", fs, a, dict(sigma=(24, 24), wavelet="db4", padding_mode="constant",
+                                                       bleach_correction_clip_min=4.9, bleach_correction_clip_med=6.0,
+                                                       bleach_correction_clip_max=8.0)
+    zeros_in = a.copy()
+    zeros_in[20:40, 30:90] = 0
+    yield "fs_bleach_zero_patch_odd", fs, zeros_in[:95, :127], dict(sigma=(8, 8), wavelet="db2", padding_mode="symmetric", **bl)
     pi = "process_img"
     img = synth.plane(3, (96, 128))
+    yield "pi_bleach_dark_8bit", pi, img, dict(sigma=(16, 16), wavelet="db6", dark=100, convert_to_8bit=True,
+                                              bit_shift_to_right=3, padding_mode="reflect", **bl)
     yield "pi_dark_8bit", pi, img, dict(sigma=(16, 16), wavelet="db6", dark=100, convert_to_8bit=True, bit_shift_to_right=3)
     yield "pi_ds_max", pi, img, dict(sigma=(16, 16), wavelet="db6", down_sample=(2, 2), dark=90, padding_mode="reflect")
     yield "pi_ds_min_rot", pi, img, dict(sigma=(0, 0), down_sample=(3, 2), down_sample_method="min", rotate=90,

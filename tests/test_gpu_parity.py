@@ -459,3 +459,47 @@ def test_process_img_new_size_after_flat_is_float32_zoom():
     got = core.process_img(img, flat=flat, **kw)
     ref = orc.process_img(img.copy(), flat=orc.normalize_flat(synth.flat_field((160, 200))), **kw)
     _cmp_int("new_size/flat", got, ref)
+
+
+def test_bleach_correction_goldens_bit_exact():
+    """correct_bleaching (core.py:501-559: clip, scipy.signal.sosfiltfilt of a first-order Butterworth section in float64,
+    img / filter * max) inside filter_streaks: every bleach golden written by the reference run verbatim, bit for bit —
+    float32 outputs included."""
+    gold = np.load(ROOT / "tests" / "golden" / "pystripe_golden.npz")
+    n = 0
+    for name, kind, img, kw in cases.all_cases():
+        if "bleach" not in name and "clipmin" not in name:
+            continue
+        got = np.asarray(_gpu_case(kind, img, kw))
+        ref = gold[name]
+        assert got.dtype == ref.dtype and got.shape == ref.shape, name
+        same = got.view(np.uint32) == ref.view(np.uint32) if ref.dtype == np.float32 else got == ref
+        REPORT["bleach/" + name] = {"exact_fraction": float(same.mean())}
+        assert same.all(), (name, float(same.mean()), float(np.abs(got.astype(np.float64) - ref).max()))
+        n += 1
+    assert n == 6
+
+
+@pytest.mark.parametrize("shape,freq", [((700, 900), 1 / 700.0), ((257, 2051), 1 / 2048.0)])
+def test_bleach_correction_against_oracle(shape, freq):
+    from pystripe import core
+    img = synth.plane(11, shape)
+    kw = dict(sigma=(64, 64), wavelet="db9", padding_mode="reflect", bleach_correction_frequency=freq,
+              bleach_correction_clip_min=4.7, bleach_correction_clip_med=5.5, bleach_correction_clip_max=7.9)
+    got = core.filter_streaks(np.stack([img, img[::-1].copy()]), **kw)          # batch of two through one plan
+    for z, src in enumerate((img, img[::-1].copy())):
+        ref = orc.filter_streaks(src, **kw)
+        _cmp_int(f"bleach/{shape}/{z}", got[z], ref, min_exact=1.0)
+
+
+def test_bleach_argument_errors():
+    from pystripe import core
+    img = synth.plane(0, (64, 64))
+    with pytest.raises(NotImplementedError):          # clip levels left to multi-Otsu
+        core.filter_streaks(img, sigma=(8, 8), bleach_correction_frequency=0.01)
+    with pytest.raises(AssertionError):               # core.py:524-527
+        core.filter_streaks(img, sigma=(8, 8), bleach_correction_frequency=0.01, bleach_correction_clip_min=5.0,
+                            bleach_correction_clip_med=4.0, bleach_correction_clip_max=6.0)
+    with pytest.raises(NotImplementedError):
+        core.filter_streaks(img, sigma=(0, 0), bleach_correction_frequency=0.01, bleach_correction_clip_min=1.0,
+                            bleach_correction_clip_med=4.0, bleach_correction_clip_max=6.0)

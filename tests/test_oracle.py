@@ -233,3 +233,18 @@ def test_fft_restatement_even_lengths_above_1000():
             y = x.copy()
             L.orc_fftpack_r2r_f32(ctypes.c_void_p(y.ctypes.data), ctypes.c_size_t(rows), ctypes.c_size_t(n), ctypes.c_int(1))
             assert np.array_equal(rfft(x, axis=-1).view(np.uint32), y.view(np.uint32)), (n, rows)
+
+
+@pytest.mark.parametrize("n,freq", [(7, 0.25), (64, 1 / 64.0), (301, 0.01), (2048, 1 / 2048.0)])
+def test_sosfiltfilt_restatement(n, freq):
+    """the operation sequence csrc/bleach.cu executes for butter_lowpass_filter (core.py:493-499) against the real
+    scipy.signal.sosfiltfilt: every bit of the float64 result."""
+    from scipy.signal import butter, sosfilt_zi, sosfiltfilt
+    rng = np.random.default_rng(n)
+    x = rng.uniform(0.7, 9.0, (5, n)).astype(np.float32)
+    sos = butter(1, freq, output='sos')
+    zi = sosfilt_zi(sos)
+    assert sos.shape == (1, 6) and sos[0, 2] == 0 and sos[0, 5] == 0 and sos[0, 3] == 1 and zi[0, 1] == 0
+    got = orc.sosfiltfilt_order1_restated(x, sos, float(zi[0, 0]))
+    ref = sosfiltfilt(sos, x)
+    assert ref.dtype == np.float64 and np.array_equal(got.view(np.uint64), ref.view(np.uint64))
