@@ -79,6 +79,7 @@ struct Geometry {
     int dsy, dsx;
     int base_pad, pad_y, pad_x, PH, PW;
     int n_passes;
+    bool log_image;       // a log-domain working image exists: destripe passes and / or bleach correction
     double pass_sigma[2];
     int levels;
     int my[B2S_MAX_LEVELS + 1], mx[B2S_MAX_LEVELS + 1];  // index 0 = padded image, l = level l sub-bands
@@ -127,14 +128,13 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
     for (int i = 0; i < g.n_passes; ++i)
         if (g.pass_sigma[i] <= 0) return fail(ctx, B2S_ERR_INVALID, "np_notch: sigma must be positive");
     if (p.bleach) {   // correct_bleaching, core.py:501-559 (non-max method) — runs on the cropped reconstruction
-        if (g.n_passes == 0)
-            return fail(ctx, B2S_ERR_UNSUPPORTED, "bleach correction without a destripe pass (sigma = (0, 0)) is not implemented");
         if (!p.log1p)
             return fail(ctx, B2S_ERR_UNSUPPORTED, "bleach correction needs log1p_normalization_needed=True (the reference's clip levels are log-domain)");
         if (g.work_cols <= 6)
             return fail(ctx, B2S_ERR_INVALID, "The length of the input vector x must be greater than padlen, which is 6.");
     }
-    g.fuse_flat = flat && !gauss && !ds && g.n_passes > 0;   // the prologue divides by flat; without a destripe it is a pre-op
+    g.log_image = g.n_passes > 0 || p.bleach;   // sigma = (0, 0) with a bleach frequency: log1p -> bleach -> expm1, no padding (core.py:1081, 1131)
+    g.fuse_flat = flat && !gauss && !ds && g.log_image;   // the prologue divides by flat; without a destripe it is a pre-op
 
     g.base_pad = g.pad_y = g.pad_x = 0;
     g.PH = g.work_rows;
@@ -190,7 +190,7 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
         g.new_cols = p.new_width;
         if (p.lightsheet) g.mid_dtype = p.out_dtype;   // correct_lightsheet returns d_type
     }
-    g.int_path = g.n_passes > 0 && g.work_dtype != B2S_F32;
+    g.int_path = g.log_image && g.work_dtype != B2S_F32;
     if (g.int_path && !p.log1p)
         return fail(ctx, B2S_ERR_UNSUPPORTED,
                     "log1p_normalization_needed=False on an integer image runs in float64 in the reference; not implemented");
@@ -396,7 +396,8 @@ int build_tables(b2s_plan *pl)
     B2sTaps &t = pl->taps;
     memset(&t, 0, sizeof t);
     t.F = F;
-    std::vector<double> dec_lo(p.dec_lo, p.dec_lo + F), rec_lo(F), rec_hi(F), dec_hi(F);
+    std::vector<double> dec_lo(F), rec_lo(F), rec_hi(F), dec_hi(F);
+    for (int k = 0; k < F; ++k) dec_lo[k] = p.dec_lo[k];
     for (int k = 0; k < F; ++k) rec_lo[k] = dec_lo[F - 1 - k];
     for (int k = 0; k < F; ++k) rec_hi[k] = ((k & 1) ? -1.0 : 1.0) * rec_lo[F - 1 - k];
     for (int k = 0; k < F; ++k) dec_hi[k] = rec_hi[F - 1 - k];
@@ -509,12 +510,12 @@ int alloc_slot(b2s_plan *pl, int si)
     b2s_plan::Slot &s = pl->slot[si];
     const size_t B = pl->B;
     int rc;
-    if (g.n_passes > 0) {
+    if (g.log_image) {
         if ((rc = dev_alloc(pl, (void **)&s.padded, sizeof(float) * pl->plane_stride[0] * B))) return rc;
         for (int l = 1; l <= g.levels; ++l)
             for (int k = 0; k < 4; ++k)
                 if ((rc = dev_alloc(pl, (void **)&s.sub[l][k], sizeof(float) * pl->plane_stride[l] * B))) return rc;
-        pl->dwt_scratch_stride = b2s_dwt_scratch_floats(pl->taps.F, g.PH, g.PW);
+        pl->dwt_scratch_stride = g.n_passes > 0 ? b2s_dwt_scratch_floats(pl->taps.F, g.PH, g.PW) : 0;
         if (pl->dwt_scratch_stride &&
             (rc = dev_alloc(pl, (void **)&s.dwt_scratch, sizeof(float) * pl->dwt_scratch_stride * B))) return rc;
     }
@@ -596,7 +597,7 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
     int cur_dt = p.in_dtype;
     // uniform-plane check (core.py:1232): min / max keys of the raw input.  When the prologue reads the raw input itself
     // (no pre-op in between) it accumulates them on the way; otherwise one vectorised pass does.
-    const bool fuse_minmax = p.process_img && g.n_passes > 0 && !(p.gaussian && !p.reference_quirks) &&
+    const bool fuse_minmax = p.process_img && g.log_image && !(p.gaussian && !p.reference_quirks) &&
                              g.work_rows == g.in_rows && g.work_cols == g.in_cols && (!(p.process_img && p.has_flat) || g.fuse_flat);
     if (p.process_img) {
         CU(ctx, cudaMemsetAsync(s.mm, 0xff, sizeof(unsigned) * 2 * nb, st));
@@ -629,7 +630,7 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
     }
 
     B2sImg padded = img_of(pl, s.padded, 0);
-    if (g.n_passes > 0) {
+    if (g.log_image) {
         {
             ClassTimer t(ctx, st, B2S_K_PROLOGUE, 1);
             B2sPrologueArgs a;
@@ -711,7 +712,7 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
         e.in = padded;
         e.raw = cur;
         e.raw_dtype = cur_dt;
-        e.destripe = g.n_passes > 0;
+        e.destripe = g.log_image;
         e.base_pad = g.base_pad;
         e.rows = g.work_rows;
         e.cols = g.work_cols;
@@ -923,9 +924,10 @@ int b2s_plan_create(b2s_context *ctx, const b2s_params *params, b2s_plan **out)
         pl->plane_stride[l] = (size_t)pl->pitch[l] * g.my[l];
     }
     if (g.n_passes == 0) { pl->pitch[0] = round4(g.PW); pl->plane_stride[0] = (size_t)pl->pitch[0] * g.PH; }
-    if (g.n_passes > 0) {
-        const int need = b2s_dwt_max_smem(params->n_taps);
+    if (g.log_image) {
+        const int need = g.n_passes > 0 ? b2s_dwt_max_smem(params->n_taps) : 0;
         if (need > 227 * 1024) { delete pl; return fail(ctx, B2S_ERR_UNSUPPORTED, "filter too long for the shared-memory tiles"); }
+        if (g.n_passes == 0) pl->p.n_taps = 0;     // no filter bank: build_tables only lays out the prologue maps
         rc = build_tables(pl);
     }
     if (rc == B2S_OK) rc = build_resize_tables(pl);

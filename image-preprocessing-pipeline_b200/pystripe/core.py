@@ -583,8 +583,6 @@ def process_img(
                             "(reference core.py:1250 as written)")
     if not tuple(sigma) > (0, 0):                                       # core.py:1302
         sigma = (0, 0)
-        if bleach is not None:
-            raise NotImplementedError("bleach correction without a destripe pass (sigma = (0, 0)) is not implemented")
     plan = _get_plan(_device_of(arr), shape, _code_of(arr), process=1, sigma=sigma, level=level, wavelet=wavelet,
                      threshold=threshold, padding_mode=padding_mode, bidirectional=bidirectional,
                      log1p=log1p_normalization_needed, flat=flat, gaussian=gaussian_filter_2d, down_sample=down_sample,

@@ -185,25 +185,25 @@ def filter_streaks(img, sigma=(250, 250), level=0, wavelet='db9', crossover=10, 
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
     s1, s2 = sigma
-    if s1 == s2 == 0:
-        assert bleach_correction_frequency is None
+    if s1 == s2 == 0 and bleach_correction_frequency is None:
         return img
     d_type = img.dtype
     if log1p_normalization_needed:
         img = log1p_f32(img.astype(np.float32))
-    shape = img.shape
-    base_pad, pad_y, pad_x = padded_geometry(shape, sigma, padding_mode)
-    if pad_y > 0 or pad_x > 0 or base_pad > 0:
-        mode = padding_mode.lower() if padding_mode else 'reflect'
-        if mode == 'constant' and bleach_correction_clip_min is not None:          # core.py:1101-1105
-            img = np.pad(img, ((base_pad, base_pad + pad_y), (base_pad, base_pad + pad_x)), mode='constant',
-                         constant_values=np.log1p(bleach_correction_clip_min))
-        else:
-            img = np.pad(img, ((base_pad, base_pad + pad_y), (base_pad, base_pad + pad_x)), mode=mode)
-    img = filter_streak_dual_band(img, s1, s2, level, wavelet, threshold, axes=(-1, -2) if bidirectional else -1)
-    if pad_y > 0 or pad_x > 0 or base_pad > 0:
-        img = img[base_pad: img.shape[0] - (base_pad + pad_y), base_pad: img.shape[1] - (base_pad + pad_x)]
-        assert img.shape == shape
+    if not s1 == s2 == 0:                                                          # core.py:1081 (no padding otherwise)
+        shape = img.shape
+        base_pad, pad_y, pad_x = padded_geometry(shape, sigma, padding_mode)
+        if pad_y > 0 or pad_x > 0 or base_pad > 0:
+            mode = padding_mode.lower() if padding_mode else 'reflect'
+            if mode == 'constant' and bleach_correction_clip_min is not None:      # core.py:1101-1105
+                img = np.pad(img, ((base_pad, base_pad + pad_y), (base_pad, base_pad + pad_x)), mode='constant',
+                             constant_values=np.log1p(bleach_correction_clip_min))
+            else:
+                img = np.pad(img, ((base_pad, base_pad + pad_y), (base_pad, base_pad + pad_x)), mode=mode)
+        img = filter_streak_dual_band(img, s1, s2, level, wavelet, threshold, axes=(-1, -2) if bidirectional else -1)
+        if pad_y > 0 or pad_x > 0 or base_pad > 0:
+            img = img[base_pad: img.shape[0] - (base_pad + pad_y), base_pad: img.shape[1] - (base_pad + pad_x)]
+            assert img.shape == shape
     if bleach_correction_frequency is not None:                                    # core.py:1131-1139
         img = correct_bleaching(np.ascontiguousarray(img), bleach_correction_frequency, bleach_correction_clip_min,
                                 bleach_correction_clip_med, bleach_correction_clip_max)
@@ -418,7 +418,7 @@ def process_img(img, flat=None, gaussian_filter_2d=False, down_sample=None, down
             raise RuntimeError(f"unsupported down-sampling method: {down_sample_method}")
         img = block_reduce(img, down_sample, method)
         tile_size = tuple(calculate_down_sampled_size(tile_size, down_sample))
-    if tuple(sigma) > (0, 0):                                          # :1302-1320
+    if bleach_correction_frequency is not None or tuple(sigma) > (0, 0):   # :1302-1320
         img = filter_streaks(img, sigma=sigma, level=level, wavelet=wavelet, threshold=threshold,
                              padding_mode=padding_mode, bidirectional=bidirectional,
                              log1p_normalization_needed=log1p_normalization_needed,

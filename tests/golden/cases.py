@@ -47,8 +47,11 @@ def all_cases():
     zeros_in = a.copy()
     zeros_in[20:40, 30:90] = 0
     yield "fs_bleach_zero_patch_odd", fs, zeros_in[:95, :127], dict(sigma=(8, 8), wavelet="db2", padding_mode="symmetric", **bl)
+    yield "fs_bleach_only_sigma0_odd", fs, zeros_in[:95, :127], dict(sigma=(0, 0), **bl)
     pi = "process_img"
     img = synth.plane(3, (96, 128))
+    yield "pi_bleach_only_flat_16bit", pi, img, dict(sigma=(0, 0), dark=100, convert_to_16bit=True,
+                                                    _flat=normalize_flat(synth.flat_field((96, 128))), **bl)
     yield "pi_bleach_dark_8bit", pi, img, dict(sigma=(16, 16), wavelet="db6", dark=100, convert_to_8bit=True,
                                               bit_shift_to_right=3, padding_mode="reflect", **bl)
     yield "pi_dark_8bit", pi, img, dict(sigma=(16, 16), wavelet="db6", dark=100, convert_to_8bit=True, bit_shift_to_right=3)
