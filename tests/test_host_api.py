@@ -220,3 +220,30 @@ def test_new_size_geometry_and_rejections():
     assert core._resize_target((96, 128), (96, 128), None, (96, 128)) is None
     assert core._resize_target((96, 128), (96, 128), (2, 2), (48, 64)) is None
     assert core._resize_target((96, 128), (96, 128), (2, 2), (40, 50)) == (40, 50)
+
+
+def test_bleach_plan_args_host_logic():
+    """host side of correct_bleaching (core.py:521-531): argument checks, the clip levels in the precision numpy.clip
+    compares them in, the Butterworth section from scipy.signal, the constant padding value (core.py:1101-1105)."""
+    from scipy.signal import butter, sosfilt_zi
+    from pystripe import core
+    assert core._bleach_plan_args(None, None, None, None, False, False) == (None, 0.0)
+    none, pad = core._bleach_plan_args(None, 4.9, 6.0, 8.0, False, False)       # the production call: frequency None
+    assert none is None and pad == float(np.float32(np.log1p(4.9)))
+    b, pad = core._bleach_plan_args(1 / 64.0, 0.5, 5.0, np.float64(6.5), False, False)
+    sos = butter(1, 1 / 64.0, output='sos')
+    assert b[:4] == (sos[0, 0], sos[0, 1], sos[0, 4], sosfilt_zi(sos)[0, 0])
+    assert b[4] == float(np.log1p(1))                    # raised to log1p(1), a numpy float64: compared in float64
+    assert b[5] == float(np.float32(5.0)) and b[6] == 6.5
+    b2, _ = core._bleach_plan_args(0.01, 4.8, 5.6, 7.4, False, False)           # weak Python floats: float32 bounds
+    assert b2[4] == float(np.float32(4.8)) and b2[6] == float(np.float32(7.4))
+    with pytest.raises(NotImplementedError):
+        core._bleach_plan_args(0.01, None, 5.0, 6.0, False, False)
+    with pytest.raises(NotImplementedError):
+        core._bleach_plan_args(0.01, 4.0, 5.0, 6.0, True, False)
+    with pytest.raises(NotImplementedError):
+        core._bleach_plan_args(None, None, None, None, False, True)
+    with pytest.raises(AssertionError):
+        core._bleach_plan_args(0.01, 5.0, 4.0, 6.0, False, False)
+    with pytest.raises(AssertionError):
+        core._bleach_plan_args(1, 4.0, 5.0, 6.0, False, False)                   # int frequency, as the reference asserts
