@@ -88,6 +88,7 @@ struct Geometry {
     int final_mode, out_dtype;
     int out_rows, out_cols;
     bool fuse_flat;
+    bool aa;                      // anti-aliasing Gaussian ahead of the zoom (aa_radius_y / aa_radius_x)
     bool resize;                  // new_size differs from the work image: order-1 zoom before the final conversion
     int new_rows, new_cols;
     int mid_dtype;                // dtype of the image the resize reads (after dark / lightsheet)
@@ -174,18 +175,23 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
     }
     // new_size, core.py:1356-1359: `tile_size < new_size` / `>` compare (rows, cols) tuples lexicographically
     g.resize = false;
+    g.aa = false;
     g.new_rows = g.work_rows;
     g.new_cols = g.work_cols;
     g.mid_dtype = g.work_dtype;
     if (p.process_img && p.new_height > 0 && p.new_width > 0 && (p.new_height != g.work_rows || p.new_width != g.work_cols)) {
         const bool up = g.work_rows < p.new_height || (g.work_rows == p.new_height && g.work_cols < p.new_width);
-        // anti_aliasing=True filters with sigma = max(0, (in/out - 1) / 2) per axis: only the sigma == 0 case is built
-        if (up && (g.work_rows > p.new_height || g.work_cols > p.new_width))
+        // anti_aliasing=True (`tile_size < new_size`) filters with sigma = max(0, (in/out - 1) / 2) per axis: a new_size
+        // larger along one axis and smaller along the other needs the caller's Gaussian (aa_radius_*, b2s_plan_set_aa_weights)
+        if (up && ((g.work_rows > p.new_height && p.aa_radius_y <= 0) || (g.work_cols > p.new_width && p.aa_radius_x <= 0)))
             return fail(ctx, B2S_ERR_UNSUPPORTED,
-                        "new_size larger along one axis and smaller along the other (anti-aliasing Gaussian of skimage.transform.resize) is not implemented");
+                        "new_size larger along one axis and smaller along the other needs the anti-aliasing Gaussian of skimage.transform.resize (aa_radius_y / aa_radius_x)");
+        if (p.aa_radius_y < 0 || p.aa_radius_x < 0 || p.aa_radius_y > 4096 || p.aa_radius_x > 4096)
+            return fail(ctx, B2S_ERR_INVALID, "anti-aliasing radius out of range");
         if (g.work_dtype != B2S_F32 && p.dark > 0 && p.dark != std::floor(p.dark))
             return fail(ctx, B2S_ERR_UNSUPPORTED, "new_size after a fractional dark on an integer image (float64 in the reference) is not implemented");
         g.resize = true;
+        g.aa = p.aa_radius_y > 0 || p.aa_radius_x > 0;
         g.new_rows = p.new_height;
         g.new_cols = p.new_width;
         if (p.lightsheet) g.mid_dtype = p.out_dtype;   // correct_lightsheet returns d_type
@@ -287,6 +293,7 @@ struct b2s_plan {
         void *mid = nullptr;                       // lightsheet / resize: post-dark image
         void *mid2 = nullptr;                      // lightsheet followed by resize: the cleaned image
         unsigned *mm2 = nullptr;                   // resize: per-plane min / max keys of the image it reads
+        void *aa_a = nullptr, *aa_b = nullptr;     // resize with anti-aliasing: the filtered image after each axis (f64 / f32)
         unsigned short *ls_grid = nullptr, *bg_grid = nullptr, *ls_cells = nullptr;
         unsigned *mm = nullptr;
         double *bleach_scratch = nullptr;          // bleach correction: forward low-pass output, rows x (cols + 12) per plane
@@ -310,6 +317,7 @@ struct b2s_plan {
     float *d_lut = nullptr;
     int *d_rz_idx = nullptr;                        // new_size: [iy0 | iy1 | ix0 | ix1]
     double *d_rz_w = nullptr;                       //           [wy0 | wy1 | wx0 | wx1]
+    double *d_aa_w[2] = {nullptr, nullptr};         // anti-aliasing Gaussian weights per axis (2 r + 1), caller-supplied
     std::map<int, B2sFftPlan> fft;                  // by length
     B2sLightsheet *ls = nullptr;
     std::map<int, B2sXfftPlan *> xfft;              // by length: rounding-exact transform (exact mode, covered lengths)
@@ -536,6 +544,11 @@ int alloc_slot(b2s_plan *pl, int si)
         if (!pl->ls && (rc = dev_alloc(pl, &s.mid, work_elems * 4 * B))) return rc;
         if (pl->ls && (rc = dev_alloc(pl, &s.mid2, work_elems * 4 * B))) return rc;
         if ((rc = dev_alloc(pl, (void **)&s.mm2, sizeof(unsigned) * 2 * B))) return rc;
+        if (g.aa) {   // skimage filters a float64 copy of an integer image, a float32 image stays float32
+            const size_t esz = g.mid_dtype == B2S_F32 ? 4 : 8;
+            if ((rc = dev_alloc(pl, &s.aa_a, work_elems * esz * B))) return rc;
+            if (p.aa_radius_y > 0 && p.aa_radius_x > 0 && (rc = dev_alloc(pl, &s.aa_b, work_elems * esz * B))) return rc;
+        }
     }
     if (pl->ls) {
         if ((rc = dev_alloc(pl, &s.mid, work_elems * 4 * B))) return rc;
@@ -756,8 +769,23 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             ClassTimer t3(ctx, st, B2S_K_EPILOGUE, 2);
             CU(ctx, cudaMemsetAsync(s.mm2, 0xff, sizeof(unsigned) * 2 * nb, st));
             b2s_launch_minmax(src, g.mid_dtype, (size_t)g.work_rows * g.work_cols, nb, s.mm2, st);
+            int rdt = g.mid_dtype;
+            if (g.aa) {   // scipy.ndimage.gaussian_filter: axis 0, then axis 1, each pass stored in the output dtype
+                const int f64 = g.mid_dtype != B2S_F32;
+                void *bufs[2] = {s.aa_a, s.aa_b};
+                const int radius[2] = {p.aa_radius_y, p.aa_radius_x};
+                int k = 0;
+                for (int axis = 0; axis < 2; ++axis) {
+                    if (radius[axis] <= 0) continue;
+                    if (!pl->d_aa_w[axis]) return fail(ctx, B2S_ERR_INVALID, "aa_radius is set but b2s_plan_set_aa_weights was not called for axis %d", axis);
+                    ctx->launches += 1;
+                    b2s_launch_gauss_aa(src, rdt, bufs[k], f64, g.work_rows, g.work_cols, axis, pl->d_aa_w[axis], radius[axis], nb, st);
+                    src = bufs[k++];
+                    rdt = f64 ? B2S_F64_INTERNAL : B2S_F32;
+                }
+            }
             B2sResizeArgs r;
-            r.src = src; r.dtype = g.mid_dtype; r.rows = g.work_rows; r.cols = g.work_cols;
+            r.src = src; r.dtype = rdt; r.mm_dtype = g.mid_dtype; r.rows = g.work_rows; r.cols = g.work_cols;
             r.new_rows = g.new_rows; r.new_cols = g.new_cols;
             r.iy0 = pl->d_rz_idx; r.iy1 = r.iy0 + g.new_rows; r.ix0 = r.iy1 + g.new_rows; r.ix1 = r.ix0 + g.new_cols;
             r.wy0 = pl->d_rz_w; r.wy1 = r.wy0 + g.new_rows; r.wx0 = r.wy1 + g.new_rows; r.wx1 = r.wx0 + g.new_cols;
@@ -984,6 +1012,24 @@ int b2s_plan_set_flat(b2s_plan *pl, const float *flat, int is_device)
         if (rc) return rc;
     }
     CU(ctx, cudaMemcpy(pl->d_flat, flat, bytes, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return B2S_OK;
+}
+
+int b2s_plan_set_aa_weights(b2s_plan *pl, int axis, const double *w, int n)
+{
+    if (!pl || !w) return B2S_ERR_INVALID;
+    b2s_context *ctx = pl->ctx;
+    if (axis < 0 || axis > 1) return fail(ctx, B2S_ERR_INVALID, "b2s_plan_set_aa_weights: axis must be 0 (rows) or 1 (columns)");
+    const int r = axis == 0 ? pl->p.aa_radius_y : pl->p.aa_radius_x;
+    if (!pl->g.aa || r <= 0 || n != 2 * r + 1)
+        return fail(ctx, B2S_ERR_INVALID, "b2s_plan_set_aa_weights: the plan expects %d weights along axis %d, got %d", r > 0 ? 2 * r + 1 : 0, axis, n);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    if (!pl->d_aa_w[axis]) {
+        int rc = dev_alloc(pl, (void **)&pl->d_aa_w[axis], sizeof(double) * n);
+        if (rc) return rc;
+    }
+    CU(ctx, cudaMemcpy(pl->d_aa_w[axis], w, sizeof(double) * n, cudaMemcpyHostToDevice));
     return B2S_OK;
 }
 

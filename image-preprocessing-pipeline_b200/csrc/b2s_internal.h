@@ -73,8 +73,14 @@ struct B2sResizeArgs {
     int new_rows, new_cols;
     const int *iy0, *iy1, *ix0, *ix1;            // per output row / column: the two source indices
     const double *wy0, *wy1, *wx0, *wx1;         // and their float64 weights
-    const unsigned *mm;    // per-plane {min key, ~max key} of src (the clip range)
+    const unsigned *mm;    // per-plane {min key, ~max key} of the unfiltered image (the clip range)
+    int mm_dtype;          // dtype the keys were taken in (src may be the anti-aliased float64 / float32 copy)
 };
+#define B2S_F64_INTERNAL 100   // resize source after the anti-aliasing Gaussian on an integer image (float64 in skimage)
+// scipy.ndimage.gaussian_filter1d along one axis (mode='mirror', float64 accumulation in correlate1d's symmetric
+// order): in (u8/u16/f32/f64) -> out (f64 when out_f64, else f32); w: 2r+1 weights on the device
+void b2s_launch_gauss_aa(const void *in, int in_dtype, void *out, int out_f64, int rows, int cols, int axis,
+                         const double *w, int radius, int n_planes, cudaStream_t s);
 void b2s_resize_axis_table(int n_in, int n_out, int *idx0, int *idx1, double *w0, double *w1);   // host
 void b2s_launch_resize_final(const B2sResizeArgs &r, const B2sEpilogueArgs &a, int n_planes, cudaStream_t s);
 

@@ -12,14 +12,14 @@
 //       y = b0*x + z;  z = (b1*x - a1*y) [+ 0]        (separate multiplies and adds: file compiled with -fmad=false)
 //     started at z = zi * x_ext[0]; the output is reversed and filtered again from z = zi * y[last]; the edges are
 //     dropped and the result is cast to float32.
-// The recurrence is sequential along a row, rows are independent: one thread per row, 64 rows per CTA, the row segments
+// The recurrence is sequential along a row, rows are independent: one thread per row, 32 rows (one warp) per CTA, the row segments
 // pass through shared-memory tiles so that global loads/stores stay coalesced (a warp moves 128 / 256 contiguous bytes
 // of one row).  The forward output (float64) goes through a per-slot scratch buffer that the same CTA reads back.
 #include "b2s_internal.h"
 
 namespace {
 
-constexpr int kRows = 64;      // rows (= threads) per CTA
+constexpr int kRows = 32;      // rows (= threads) per CTA: one warp, so that 2048 rows x 8 planes already give 512 CTAs
 constexpr int kChunk = 32;     // samples per tile
 constexpr int kEdge = 6;       // sosfiltfilt: ntaps = 2*1 + 1 - min(#(b2 == 0), #(a2 == 0)) = 2; edge = 3 * ntaps
 
@@ -70,9 +70,19 @@ __global__ void __launch_bounds__(kRows) k_bleach_lowpass(B2sBleachArgs a)
 
     // forward over the extended row
     for (int j0 = 0; j0 < N; j0 += kChunk) {
-        for (int e = tid; e < kRows * kChunk; e += kRows) {
-            const int rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = j0 + jj;
-            if (r < a.rows && j < N) s_in[rr][jj] = ext_sample(img + (size_t)r * a.img.pitch, j, n, a);
+        // loads first, stores after: 8 independent global loads in flight per thread instead of one
+        for (int e0 = tid; e0 < kRows * kChunk; e0 += 8 * kRows) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * kRows, rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = j0 + jj;
+                v[u] = (r < a.rows && j < N) ? ext_sample(img + (size_t)r * a.img.pitch, j, n, a) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * kRows;
+                s_in[e / kChunk][e % kChunk] = v[u];
+            }
         }
         __syncthreads();
         if (live) {
@@ -98,9 +108,18 @@ __global__ void __launch_bounds__(kRows) k_bleach_lowpass(B2sBleachArgs a)
     z = a.zi * last;
     float mx = -INFINITY;
     for (int j0 = ((N - 1) / kChunk) * kChunk; j0 >= 0; j0 -= kChunk) {
-        for (int e = tid; e < kRows * kChunk; e += kRows) {
-            const int rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = j0 + jj;
-            if (r < a.rows && j < N) s_y[rr][jj] = scr[(size_t)r * N + j];
+        for (int e0 = tid; e0 < kRows * kChunk; e0 += 8 * kRows) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * kRows, rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = j0 + jj;
+                v[u] = (r < a.rows && j < N) ? scr[(size_t)r * N + j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * kRows;
+                s_y[e / kChunk][e % kChunk] = v[u];
+            }
         }
         __syncthreads();
         if (live) {

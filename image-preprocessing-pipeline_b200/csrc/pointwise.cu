@@ -551,7 +551,11 @@ __global__ void __launch_bounds__(256) k_resize_final(B2sResizeArgs r, B2sEpilog
         const double wy0 = __ldg(r.wy0 + y), wy1 = __ldg(r.wy1 + y), wx0 = __ldg(r.wx0 + x), wx1 = __ldg(r.wx1 + x);
         const size_t base = plane * (size_t)r.rows * r.cols;
         double v00, v01, v10, v11;
-        if (r.dtype == B2S_F32) {
+        if (r.dtype == B2S_F64_INTERNAL) {
+            const double *s = reinterpret_cast<const double *>(r.src) + base;
+            v00 = s[(size_t)y0 * r.cols + x0]; v01 = s[(size_t)y0 * r.cols + x1];
+            v10 = s[(size_t)y1 * r.cols + x0]; v11 = s[(size_t)y1 * r.cols + x1];
+        } else if (r.dtype == B2S_F32) {
             const float *s = reinterpret_cast<const float *>(r.src) + base;
             v00 = s[(size_t)y0 * r.cols + x0]; v01 = s[(size_t)y0 * r.cols + x1];
             v10 = s[(size_t)y1 * r.cols + x0]; v11 = s[(size_t)y1 * r.cols + x1];
@@ -570,7 +574,7 @@ __global__ void __launch_bounds__(256) k_resize_final(B2sResizeArgs r, B2sEpilog
         t = __dadd_rn(t, __dmul_rn(__dmul_rn(v10, wy1), wx0));
         t = __dadd_rn(t, __dmul_rn(__dmul_rn(v11, wy1), wx1));
         const unsigned klo = r.mm[2 * plane], khi = ~r.mm[2 * plane + 1];
-        if (r.dtype == B2S_F32) {
+        if (r.mm_dtype == B2S_F32) {
             float tf = (float)t;
             const float lo = key2f(klo), hi = key2f(khi);
             tf = fminf(fmaxf(tf, lo), hi);
@@ -595,6 +599,45 @@ __global__ void __launch_bounds__(256) k_resize_final(B2sResizeArgs r, B2sEpilog
     }
     if (a.out_dtype == B2S_U8) reinterpret_cast<unsigned char *>(a.out)[oidx] = (unsigned char)u;
     else reinterpret_cast<unsigned short *>(a.out)[oidx] = (unsigned short)u;
+}
+
+// one output sample of scipy.ndimage.correlate1d with a symmetric kernel (ni_filters.c): the centre product first, then
+// the pairs from the outermost inwards, (in[c-k] + in[c+k]) * w, each added in float64; boundary mode 'mirror'
+__global__ void __launch_bounds__(256) k_gauss_aa(const void *in, int in_dtype, void *out, int out_f64, int rows, int cols,
+                                                   int axis, const double *w, int radius)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= cols) return;
+    const size_t base = (size_t)blockIdx.z * rows * cols;
+    const int n = axis == 0 ? rows : cols;
+    const int c = axis == 0 ? y : x;
+    auto at = [&](int i) -> double {
+        if (n == 1) i = 0;
+        else {
+            const int p2 = 2 * (n - 1);
+            i %= p2;
+            if (i < 0) i += p2;
+            if (i >= n) i = p2 - i;
+        }
+        const size_t idx = base + (axis == 0 ? (size_t)i * cols + x : (size_t)y * cols + i);
+        if (in_dtype == B2S_F64_INTERNAL) return reinterpret_cast<const double *>(in)[idx];
+        if (in_dtype == B2S_F32) return (double)reinterpret_cast<const float *>(in)[idx];
+        if (in_dtype == B2S_U16) return (double)reinterpret_cast<const unsigned short *>(in)[idx];
+        return (double)reinterpret_cast<const unsigned char *>(in)[idx];
+    };
+    double tmp = __dmul_rn(at(c), __ldg(w + radius));
+    for (int jj = -radius; jj < 0; ++jj)
+        tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(at(c + jj), at(c - jj)), __ldg(w + jj + radius)));
+    const size_t o = base + (size_t)y * cols + x;
+    if (out_f64) reinterpret_cast<double *>(out)[o] = tmp;
+    else reinterpret_cast<float *>(out)[o] = (float)tmp;
+}
+
+void b2s_launch_gauss_aa(const void *in, int in_dtype, void *out, int out_f64, int rows, int cols, int axis,
+                         const double *w, int radius, int n_planes, cudaStream_t s)
+{
+    k_gauss_aa<<<dim3((cols + 255) / 256, rows, n_planes), 256, 0, s>>>(in, in_dtype, out, out_f64, rows, cols, axis, w, radius);
 }
 
 void b2s_launch_resize_final(const B2sResizeArgs &r, const B2sEpilogueArgs &a, int n_planes, cudaStream_t s)

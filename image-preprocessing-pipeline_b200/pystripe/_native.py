@@ -41,6 +41,7 @@ class Params(C.Structure):
         ("bleach_b0", C.c_double), ("bleach_b1", C.c_double), ("bleach_a1", C.c_double), ("bleach_zi", C.c_double),
         ("bleach_clip_min", C.c_double), ("bleach_clip_med", C.c_double), ("bleach_clip_max", C.c_double),
         ("pad_constant", C.c_double),
+        ("aa_radius_y", C.c_int32), ("aa_radius_x", C.c_int32),
         ("max_batch", C.c_int32), ("debug_stop_after", C.c_int32), ("exact", C.c_int32),
     ]
 
@@ -58,7 +59,7 @@ class PlanInfo(C.Structure):
 
 EXPORTS = (
     "b2s_version", "b2s_params_default", "b2s_create", "b2s_destroy", "b2s_last_error", "b2s_device_sm_count",
-    "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_run",
+    "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_plan_set_aa_weights", "b2s_run",
     "b2s_host_alloc", "b2s_host_free", "b2s_launch_count", "b2s_timing_enable", "b2s_timing_read",
     "b2s_debug_read", "b2s_debug_math",
 )
@@ -98,6 +99,7 @@ def lib():
             L.b2s_plan_geometry.argtypes = [C.POINTER(Params), C.POINTER(PlanInfo), C.c_char_p, C.c_size_t]
             L.b2s_plan_set_flat.argtypes = [vp, vp, i32]
             L.b2s_plan_set_notch.argtypes = [vp, i32, i32, i32, vp, i32]
+            L.b2s_plan_set_aa_weights.argtypes = [vp, i32, vp, i32]
             L.b2s_run.argtypes = [vp, vp, vp, i64, i32, i32, vp]
             L.b2s_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
             L.b2s_host_free.argtypes = [vp, vp]
@@ -292,6 +294,11 @@ class Plan:
         """upload a host-evaluated np_notch table (float32) for (pass, 1-based level, axis 0 = cH / 1 = cV)."""
         g = np.ascontiguousarray(g, dtype=np.float32)
         self.ctx.check(lib().b2s_plan_set_notch(self._h, pass_idx, level, axis, C.c_void_p(g.ctypes.data), int(g.size)))
+
+    def set_aa_weights(self, axis: int, w: np.ndarray):
+        """upload the anti-aliasing Gaussian of skimage.transform.resize along one axis (2 * radius + 1 float64 weights)."""
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        self.ctx.check(lib().b2s_plan_set_aa_weights(self._h, axis, C.c_void_p(w.ctypes.data), int(w.size)))
 
     def run_host(self, src: np.ndarray, dst: np.ndarray = None) -> np.ndarray:
         """src: (n, H, W) or (H, W) numpy array in host memory (pinned or pageable)."""

@@ -260,7 +260,7 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
               log1p, flat=None, gaussian=False, down_sample=None, down_sample_method='max', dark=0, lightsheet=False,
               artifact_length=150, background_window_size=200, percentile=0.25, lightsheet_vs_background=2.0,
               convert_to_16bit=False, convert_to_8bit=False, bit_shift_to_right=8, rotate=0, flip=False,
-              out_code=None, max_batch=None, stop_after=0, exact=None, new_size=None, bleach=None, pad_constant=0.0):
+              out_code=None, max_batch=None, stop_after=0, exact=None, new_size=None, bleach=None, pad_constant=0.0, aa=(None, None)):
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
     s1, s2 = float(sigma[0]), float(sigma[1])
@@ -292,7 +292,7 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
            bool(bidirectional), bool(log1p), threshold is not None and threshold <= 0, flat_key, bool(gaussian), ds,
            method, float(dark or 0), bool(lightsheet), artifact_length, background_window_size, percentile,
            lightsheet_vs_background, bool(convert_to_16bit), bool(convert_to_8bit), bit_shift_to_right, rotate,
-           bool(flip), out_code, max_batch, stop_after, exact, REFERENCE_QUIRKS, new_size, bleach,
+           bool(flip), out_code, max_batch, stop_after, exact, REFERENCE_QUIRKS, new_size, bleach, tuple(None if a is None else a[0] for a in aa),
            float(pad_constant) if (destripe and mode == 'constant') else 0.0)
     with _plans_lock:
         plan = _plans.get(key)
@@ -333,12 +333,17 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
              p.bleach_clip_min, p.bleach_clip_med, p.bleach_clip_max) = bleach
             p.bleach = 1
         p.pad_constant = float(pad_constant)
+        p.aa_radius_y = 0 if aa[0] is None else int(aa[0][0])
+        p.aa_radius_x = 0 if aa[1] is None else int(aa[1][0])
         p.max_batch = int(max_batch or MAX_BATCH)
         p.debug_stop_after = int(stop_after)
         p.exact = int(EXACT if exact is None else exact)
         plan = _native.Plan(_native.context(device), p, dec_lo=taps, flat=flat)
         plan._flat_ref = flat  # keep id(flat) stable while the plan is cached
         _upload_numpy_notch_tables(plan, s1, s2)
+        for ax in range(2):
+            if aa[ax] is not None:
+                plan.set_aa_weights(ax, aa[ax][1])
         if len(_plans) > 16:   # plans own GPU workspace: keep the cache small
             _, old = _plans.popitem()
             old.close()
@@ -493,22 +498,37 @@ def filter_streaks(
 # --------------------------------------------------------------------------------------------------------------
 def _resize_target(shape, tile_size, down_sample, new_size):
     """core.py:1356-1359: `resize(img, new_size, preserve_range=True, anti_aliasing=tile_size < new_size)` unless the
-    (down-sampled) tile_size equals new_size.  Returns the (rows, cols) the GPU plan resizes to, or None."""
+    (down-sampled) tile_size equals new_size.  Returns (the (rows, cols) the GPU plan resizes to or None, the
+    anti-aliasing Gaussian per axis as [(radius, weights) | None, ...])."""
     if new_size is None:
-        return None
+        return None, (None, None)
     new_size = tuple(int(v) for v in new_size)
     ts, work = tuple(int(v) for v in tile_size), tuple(shape)
     if down_sample is not None:
         ts = tuple(calculate_down_sampled_size(ts, down_sample))        # core.py:1300
         work = tuple(calculate_down_sampled_size(work, down_sample))
     if ts == new_size:
-        return None
+        return None, (None, None)
     if work == new_size or (ts < new_size) != (work < new_size):
         raise NotImplementedError("new_size with a tile_size that differs from the image shape is not implemented")
     for n_in, n_out in zip(work, new_size):                             # the shape scipy.ndimage.zoom derives from the factors
         if int(round(n_in * (1 / np.divide(n_in, n_out)))) != n_out:
             raise NotImplementedError(f"new_size {new_size}: skimage's zoom factor rounds to another output shape")
-    return new_size
+    aa = [None, None]
+    if ts < new_size:                                                   # anti_aliasing=True (tuple comparison, core.py:1357)
+        # skimage.transform.resize: sigma = max(0, (in / out - 1) / 2); scipy.ndimage.gaussian_filter skips an axis
+        # with sigma <= 1e-15 and builds _gaussian_kernel1d(sigma, 0, int(4 sigma + 0.5)) — numpy arithmetic, done here
+        factors = np.divide(work, new_size)
+        sigmas = np.maximum(0, (factors - 1) / 2)
+        for ax in range(2):
+            sd = float(sigmas[ax])
+            if sd > 1e-15:
+                radius = int(4.0 * sd + 0.5)
+                if radius > 0:                                          # radius 0: the kernel is [1.0], x * 1.0 == x
+                    x = np.arange(-radius, radius + 1)
+                    phi = np.exp(-0.5 / (sd * sd) * x ** 2)
+                    aa[ax] = (radius, (phi / phi.sum())[::-1].copy())
+    return new_size, tuple(aa)
 
 
 def process_img(
@@ -563,7 +583,7 @@ def process_img(
     shape = tuple(arr.shape[-2:])
     if tile_size is None:
         tile_size = shape
-    resize_to = _resize_target(shape, tile_size, down_sample, new_size)
+    resize_to, aa = _resize_target(shape, tile_size, down_sample, new_size)
     if d_type is None:
         d_type = np.float64 if restore is not None else (
             _native.CODE_TO_NP[_code_of(arr)])
@@ -591,7 +611,7 @@ def process_img(
                      percentile=percentile, lightsheet_vs_background=lightsheet_vs_background,
                      convert_to_16bit=convert_to_16bit, convert_to_8bit=convert_to_8bit,
                      bit_shift_to_right=bit_shift_to_right, rotate=rotate, flip=flip_upside_down, out_code=out_code,
-                     max_batch=_max_batch, new_size=resize_to, bleach=bleach, pad_constant=pad_constant)
+                     max_batch=_max_batch, new_size=resize_to, bleach=bleach, pad_constant=pad_constant, aa=aa)
     out = _run(plan, arr)
     if out_code == _native.F32 and plan.info.out_dtype == _native.F32 and d_type != np.float32:
         out = out.astype(d_type) if not _native._is_torch(out) else out.double()

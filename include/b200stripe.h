@@ -92,6 +92,10 @@ typedef struct b2s_params {
                                      float is rounded to float32 by the caller; log1p(1) stays float64, core.py:529-531) */
     double pad_constant;          /* padding_mode='constant': log1p(bleach_correction_clip_min) when that is given
                                      (core.py:1101-1105), else 0                                                  */
+    int32_t aa_radius_y, aa_radius_x; /* new_size with anti_aliasing (skimage.transform.resize -> scipy.ndimage.
+                                     gaussian_filter(sigma = (in/out - 1) / 2, mode='mirror', truncate 4) ahead of the zoom):
+                                     kernel radius int(4 sigma + 0.5) per axis, 0 = no filter along that axis; the 2r+1
+                                     weights are uploaded with b2s_plan_set_aa_weights                              */
     /* --- execution ------------------------------------------------------------------------------------ */
     int32_t max_batch;            /* planes processed per launch group (workspace is sized for this)         */
     int32_t debug_stop_after;     /* b2s_stage; 0 in production                                             */
@@ -143,6 +147,10 @@ int b2s_plan_set_flat(b2s_plan *plan, const float *flat, int is_device);
  * libm expf; numpy's float32 exp is a SIMD routine whose last bit differs from libm on ~40 % of arguments, so a host
  * that wants the reference's numpy values bit for bit uploads them here.  pass: 0 or 1 (sigma1 / sigma2 pass),
  * level: 1-based, axis: 0 = cH filtered along axis -1, 1 = cV along axis -2 (bidirectional); g: n host floats. */
+/* replaces: scipy.ndimage._filters._gaussian_kernel1d as gaussian_filter calls it under skimage.transform.resize
+ * (core.py:1356-1359).  axis 0 = rows (y), 1 = columns (x); n = 2 * aa_radius + 1 float64 weights, evaluated by the caller
+ * with numpy exactly as scipy does (numpy's exp is not libm's). */
+int b2s_plan_set_aa_weights(b2s_plan *plan, int axis, const double *weights, int n);
 int b2s_plan_set_notch(b2s_plan *plan, int pass, int level, int axis, const float *g, int n);
 
 /*

@@ -76,5 +76,14 @@ def all_cases():
                                                background_window_size=40, dark=100, new_size=(120, 160))
     yield "pi_resize_flat", pi, img, dict(sigma=(16, 16), wavelet="db6", dark=100, padding_mode="reflect", new_size=(77, 99),
                                          _flat=normalize_flat(synth.flat_field((96, 128))))
+    # new_size larger along one axis, smaller along the other: anti_aliasing=True with a Gaussian along the shrinking axis
+    # (float64 for an integer image, float32 after a flat-field)
+    yield "pi_resize_mixed_aa_x", pi, img, dict(sigma=(16, 16), wavelet="db6", dark=100, new_size=(120, 50))
+    yield "pi_resize_mixed_aa_x_8bit_rot", pi, img, dict(sigma=(0, 0), new_size=(97, 31), convert_to_8bit=True,
+                                                        bit_shift_to_right=3, rotate=270)
+    yield "pi_resize_mixed_aa_flat", pi, img, dict(sigma=(16, 16), wavelet="db6", dark=100, padding_mode="reflect",
+                                                  new_size=(150, 77), _flat=normalize_flat(synth.flat_field((96, 128))))
+    yield "pi_resize_mixed_lightsheet", pi, img, dict(sigma=(0, 0), lightsheet=True, artifact_length=30,
+                                                     background_window_size=40, dark=100, new_size=(100, 90))
     yield "pi_uniform", pi, np.full((64, 80), 7, np.uint16), dict(sigma=(8, 8), wavelet="db2", down_sample=(2, 2),
                                                                   rotate=90, convert_to_8bit=True)

@@ -215,11 +215,21 @@ def test_new_size_geometry_and_rejections():
     info = _native.plan_geometry(p)
     assert (info.out_height, info.out_width) == (108, 81)
     p.new_height, p.new_width = 120, 100          # up along y, down along x: skimage's anti-aliasing Gaussian
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):      # ... which the caller has to supply
         _native.plan_geometry(p)
-    assert core._resize_target((96, 128), (96, 128), None, (96, 128)) is None
-    assert core._resize_target((96, 128), (96, 128), (2, 2), (48, 64)) is None
-    assert core._resize_target((96, 128), (96, 128), (2, 2), (40, 50)) == (40, 50)
+    p.aa_radius_x = 1
+    assert (_native.plan_geometry(p).out_height, _native.plan_geometry(p).out_width) == (100, 120)
+    assert core._resize_target((96, 128), (96, 128), None, (96, 128)) == (None, (None, None))
+    assert core._resize_target((96, 128), (96, 128), (2, 2), (48, 64)) == (None, (None, None))
+    assert core._resize_target((96, 128), (96, 128), (2, 2), (40, 50)) == ((40, 50), (None, None))   # down: anti_aliasing=False
+    assert core._resize_target((96, 128), (96, 128), None, (130, 171)) == ((130, 171), (None, None))  # up: sigma 0
+    # mixed: the weights scipy.ndimage.gaussian_filter would use along the shrinking axis, bit for bit
+    from scipy.ndimage import _filters
+    size, aa = core._resize_target((96, 128), (96, 128), None, (120, 50))
+    assert size == (120, 50) and aa[0] is None
+    sd = (128 / 50 - 1) / 2
+    radius = int(4.0 * sd + 0.5)
+    assert aa[1][0] == radius and np.array_equal(aa[1][1], _filters._gaussian_kernel1d(sd, 0, radius)[::-1])
 
 
 def test_bleach_plan_args_host_logic():
