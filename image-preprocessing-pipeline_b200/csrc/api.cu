@@ -1224,6 +1224,134 @@ int b2s_debug_read(b2s_plan *pl, int what, int level, int plane, float *out, int
     return B2S_OK;
 }
 
+int b2s_isotropic_xy(b2s_context *ctx, const void *d_in, int in_dtype, int rows, int cols, int n_steps, const int32_t *steps,
+                     int target_rows, int target_cols, int pre_rows, int pre_cols, const double *wy, int ry,
+                     const double *wx, int rx, float *d_out, int n_planes, void *stream)
+{
+    if (!ctx || !d_in || !d_out || rows <= 0 || cols <= 0 || target_rows <= 0 || target_cols <= 0 || n_planes <= 0 ||
+        n_steps < 0 || (n_steps && !steps) || in_dtype < B2S_U8 || in_dtype > B2S_F32 || ry < 0 || rx < 0 ||
+        (ry && !wy) || (rx && !wx))
+        return B2S_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t full = (size_t)rows * cols * n_planes;
+    std::vector<void *> tmp;
+    auto dalloc = [&](size_t bytes) -> void * {
+        void *p = nullptr;
+        if (cudaMallocAsync(&p, bytes ? bytes : 16, st) != cudaSuccess) return nullptr;
+        tmp.push_back(p);
+        return p;
+    };
+    auto release = [&]() { for (void *p : tmp) cudaFreeAsync(p, st); };
+    unsigned *mm0 = (unsigned *)dalloc(sizeof(unsigned) * 2 * n_planes);      // uniform check on the source plane
+    unsigned *mm1 = (unsigned *)dalloc(sizeof(unsigned) * 2 * n_planes);      // clip range of the image resize() sees
+    float *buf[2] = {(float *)dalloc(sizeof(float) * full), (float *)dalloc(sizeof(float) * full)};
+    if (!mm0 || !mm1 || !buf[0] || !buf[1]) { release(); return fail(ctx, B2S_ERR_NOMEM, "cudaMallocAsync failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    CU(ctx, cudaMemsetAsync(mm0, 0xff, sizeof(unsigned) * 2 * n_planes, st));
+    CU(ctx, cudaMemsetAsync(mm1, 0xff, sizeof(unsigned) * 2 * n_planes, st));
+    b2s_launch_minmax(d_in, in_dtype, (size_t)rows * cols, n_planes, mm0, st);
+    // img.astype(float32) (an identity block reduce), then the alternating 2 x 1 / 1 x 2 reductions
+    const void *cur = d_in;
+    int cur_dt = in_dtype, r = rows, c = cols, k = 0, launches = 1;
+    auto reduce = [&](int by, int bx, int method) {
+        const int nr = (r + by - 1) / by, nc = (c + bx - 1) / bx;
+        b2s_launch_block_reduce(cur, cur_dt, r, c, by, bx, method, buf[k], B2S_F32, nr, nc, n_planes, st);
+        cur = buf[k]; cur_dt = B2S_F32; r = nr; c = nc; k ^= 1; ++launches;
+    };
+    reduce(1, 1, B2S_DS_MAX);
+    for (int i = 0; i < n_steps; ++i) {
+        const int ym = steps[2 * i], xm = steps[2 * i + 1];
+        if (ym >= 0 && (r + 1) / 2 >= target_rows) reduce(2, 1, ym);
+        if (xm >= 0 && (c + 1) / 2 >= target_cols) reduce(1, 2, xm);
+    }
+    if (r != pre_rows || c != pre_cols) {
+        release();
+        return fail(ctx, B2S_ERR_INVALID, "isotropic down-sampling: the reductions end at %d x %d, the caller expected %d x %d", r, c, pre_rows, pre_cols);
+    }
+    b2s_launch_minmax(cur, B2S_F32, (size_t)r * c, n_planes, mm1, st);
+    ++launches;
+    // resize(anti_aliasing=True): Gaussian per axis (float32 image: each pass stored as float32), order-1 zoom, clip
+    const int radius[2] = {ry, rx};
+    const double *w[2] = {wy, wx};
+    for (int axis = 0; axis < 2; ++axis) {
+        if (radius[axis] <= 0) continue;
+        const int n = 2 * radius[axis] + 1;
+        double *dw = (double *)dalloc(sizeof(double) * n);
+        if (!dw) { release(); return fail(ctx, B2S_ERR_NOMEM, "cudaMallocAsync failed"); }
+        CU(ctx, cudaMemcpyAsync(dw, w[axis], sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        b2s_launch_gauss_aa(cur, B2S_F32, buf[k], 0, r, c, axis, dw, radius[axis], n_planes, st);
+        cur = buf[k]; k ^= 1; ++launches;
+    }
+    std::vector<int> idx(2 * (size_t)(target_rows + target_cols));
+    std::vector<double> wt(2 * (size_t)(target_rows + target_cols));
+    b2s_resize_axis_table(r, target_rows, idx.data(), idx.data() + target_rows, wt.data(), wt.data() + target_rows);
+    b2s_resize_axis_table(c, target_cols, idx.data() + 2 * target_rows, idx.data() + 2 * target_rows + target_cols,
+                          wt.data() + 2 * target_rows, wt.data() + 2 * target_rows + target_cols);
+    int *d_idx = (int *)dalloc(sizeof(int) * idx.size());
+    double *d_w = (double *)dalloc(sizeof(double) * wt.size());
+    if (!d_idx || !d_w) { release(); return fail(ctx, B2S_ERR_NOMEM, "cudaMallocAsync failed"); }
+    CU(ctx, cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(d_w, wt.data(), sizeof(double) * wt.size(), cudaMemcpyHostToDevice, st));
+    B2sResizeArgs ra;
+    ra.src = cur; ra.dtype = B2S_F32; ra.mm_dtype = B2S_F32; ra.rows = r; ra.cols = c;
+    ra.new_rows = target_rows; ra.new_cols = target_cols;
+    ra.iy0 = d_idx; ra.iy1 = ra.iy0 + target_rows; ra.ix0 = ra.iy1 + target_rows; ra.ix1 = ra.ix0 + target_cols;
+    ra.wy0 = d_w; ra.wy1 = ra.wy0 + target_rows; ra.wx0 = ra.wy1 + target_rows; ra.wx1 = ra.wx0 + target_cols;
+    ra.mm = mm1;
+    B2sEpilogueArgs e;
+    memset(&e, 0, sizeof e);
+    e.final_mode = 3; e.out_dtype = B2S_F32; e.out = d_out; e.out_rows = target_rows; e.out_cols = target_cols;
+    e.uniform_mm = mm0;                       // is_uniform_2d(img): zeros (parallel_image_processor.py:373-374)
+    b2s_launch_resize_final(ra, e, n_planes, st);
+    ctx->launches += launches + 1;
+    CU(ctx, cudaStreamSynchronize(st));       // the host tables above are read by the asynchronous copies
+    release();
+    CU(ctx, cudaGetLastError());
+    return B2S_OK;
+}
+
+int b2s_isotropic_z(b2s_context *ctx, const float *d_in, int n_in, int64_t plane_elems, int method, float *d_out, void *stream)
+{
+    if (!ctx || !d_in || !d_out || n_in <= 0 || plane_elems <= 0 || method < B2S_DS_MAX || method > B2S_DS_MEAN) return B2S_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    for (int k = 0; 2 * k < n_in; ++k) {
+        const float *a = d_in + (size_t)(2 * k) * plane_elems;
+        const float *b = 2 * k + 1 < n_in ? a + plane_elems : nullptr;
+        b2s_launch_z_pair(a, b, method, d_out + (size_t)k * plane_elems, plane_elems, (cudaStream_t)stream);
+        ctx->launches += 1;
+    }
+    CU(ctx, cudaGetLastError());
+    return B2S_OK;
+}
+
+int b2s_isotropic_convert(b2s_context *ctx, const float *d_in, int64_t n, int mode, int shift, void *d_out, void *stream)
+{
+    if (!ctx || !d_in || !d_out || n <= 0 || (mode != 1 && mode != 2 && mode != 4)) return B2S_ERR_INVALID;
+    if (mode == 2 && (shift < 0 || shift > 8)) return fail(ctx, B2S_ERR_INVALID, "right shift should be between 0 and 8");
+    CU(ctx, cudaSetDevice(ctx->device));
+    b2s_launch_convert_f32(d_in, n, mode, shift, d_out, (cudaStream_t)stream);
+    ctx->launches += 1;
+    CU(ctx, cudaGetLastError());
+    return B2S_OK;
+}
+
+int b2s_is_uniform(b2s_context *ctx, const void *d_in, int dtype, int64_t n, int32_t *uniform, void *stream)
+{
+    if (!ctx || !d_in || !uniform || n <= 0 || dtype < B2S_U8 || dtype > B2S_F32) return B2S_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned *mm = nullptr, h[2];
+    CU(ctx, cudaMallocAsync((void **)&mm, sizeof(unsigned) * 2, st));
+    cudaMemsetAsync(mm, 0xff, sizeof(unsigned) * 2, st);
+    b2s_launch_minmax(d_in, dtype, (size_t)n, 1, mm, st);
+    ctx->launches += 1;
+    cudaMemcpyAsync(h, mm, sizeof h, cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(mm, st);
+    CU(ctx, cudaStreamSynchronize(st));
+    *uniform = h[0] == ~h[1];
+    return B2S_OK;
+}
+
 int b2s_debug_math(b2s_context *ctx, int which, const float *in, float *out, int64_t n)
 {
     if (!ctx || !in || !out || n < 0) return B2S_ERR_INVALID;

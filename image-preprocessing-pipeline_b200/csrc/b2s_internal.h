@@ -95,6 +95,9 @@ void b2s_launch_gauss5_u16(const uint16_t *in, uint16_t *out, int rows, int cols
 void b2s_launch_gauss5_f32(const float *in, float *out, int rows, int cols, int n_planes, cudaStream_t s);
 void b2s_launch_block_reduce(const void *in, int dtype, int rows, int cols, int by, int bx, int method, void *out,
                              int out_dtype, int out_rows, int out_cols, int n_planes, cudaStream_t s);
+// isotropic down-sampling helpers (parallel_image_processor.py:417-433)
+void b2s_launch_z_pair(const float *a, const float *b, int method, float *out, int64_t n, cudaStream_t s);
+void b2s_launch_convert_f32(const float *in, int64_t n, int mode, int shift, void *out, cudaStream_t s);
 void b2s_launch_math(int which, const float *in, float *out, int64_t n, cudaStream_t s);
 void b2s_launch_log1p_lut(float *lut, int n, cudaStream_t s);
 

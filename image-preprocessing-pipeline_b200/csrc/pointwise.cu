@@ -652,6 +652,38 @@ __global__ void k_log1p_lut(float *lut, int n)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) lut[i] = b2s_log1pf_dev((float)i);
 }
+// block_reduce(z_stack, (2, 1, 1), func) for one pair of planes: numpy max, or the float32 mean (a + b) / 2
+__global__ void k_z_pair(const float *a, const float *b, int method, float *out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = a[i], y = b ? b[i] : 0.f;
+    out[i] = method == B2S_DS_MAX ? fmaxf(x, y) : (method == B2S_DS_MIN ? fminf(x, y) : __fdiv_rn(__fadd_rn(x, y), 2.0f));
+}
+void b2s_launch_z_pair(const float *a, const float *b, int method, float *out, int64_t n, cudaStream_t s)
+{
+    k_z_pair<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, b, method, out, n);
+}
+
+// convert_to_16bit_fun / convert_to_8bit_fun / astype(uint8) of a float32 plane (core.py:397-423)
+__global__ void k_convert_f32(const float *in, int64_t n, int mode, int shift, void *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = in[i];
+    if (mode == 4) { reinterpret_cast<unsigned char *>(out)[i] = (unsigned char)(int)v; return; }
+    const float c = v < 0.f ? 0.f : (v > 65535.f ? 65535.f : v);     // clip(0, 65535).astype(uint16): truncation
+    unsigned u = (unsigned)c;
+    if (mode == 1) { reinterpret_cast<unsigned short *>(out)[i] = (unsigned short)u; return; }
+    const unsigned lower = 1u << shift;
+    u = (u > 0 && u < lower) ? 1u : (u >> shift);
+    reinterpret_cast<unsigned char *>(out)[i] = (unsigned char)(u > 255u ? 255u : u);
+}
+void b2s_launch_convert_f32(const float *in, int64_t n, int mode, int shift, void *out, cudaStream_t s)
+{
+    k_convert_f32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, n, mode, shift, out);
+}
+
 void b2s_launch_log1p_lut(float *lut, int n, cudaStream_t s) { k_log1p_lut<<<(n + 255) / 256, 256, 0, s>>>(lut, n); }
 
 void b2s_launch_minmax(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned *mm, cudaStream_t s)

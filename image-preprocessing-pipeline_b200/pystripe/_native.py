@@ -62,6 +62,7 @@ EXPORTS = (
     "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_plan_set_aa_weights", "b2s_run",
     "b2s_host_alloc", "b2s_host_free", "b2s_launch_count", "b2s_timing_enable", "b2s_timing_read",
     "b2s_debug_read", "b2s_debug_math",
+    "b2s_isotropic_xy", "b2s_isotropic_z", "b2s_isotropic_convert", "b2s_is_uniform",
 )
 
 _lib = None
@@ -100,6 +101,10 @@ def lib():
             L.b2s_plan_set_flat.argtypes = [vp, vp, i32]
             L.b2s_plan_set_notch.argtypes = [vp, i32, i32, i32, vp, i32]
             L.b2s_plan_set_aa_weights.argtypes = [vp, i32, vp, i32]
+            L.b2s_isotropic_xy.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
+            L.b2s_isotropic_z.argtypes = [vp, vp, i32, i64, i32, vp, vp]
+            L.b2s_isotropic_convert.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+            L.b2s_is_uniform.argtypes = [vp, vp, i32, i64, vp, vp]
             L.b2s_run.argtypes = [vp, vp, vp, i64, i32, i32, vp]
             L.b2s_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
             L.b2s_host_free.argtypes = [vp, vp]

@@ -191,6 +191,30 @@ int b2s_timing_read(b2s_context *ctx, double *ms_per_class, int64_t *launches_pe
 int b2s_debug_read(b2s_plan *plan, int what, int level, int plane, float *out, int32_t *rows, int32_t *cols);
 
 /* device-side math used by the kernels, exposed so tests can compare them with the host libm bit for bit */
+/* --- isotropic down-sampling of the post-stitch path (parallel_image_processor.py:371-435) -------------------------
+ * b2s_isotropic_xy replaces, per plane: `img.astype(float32)`; for every (y_method, x_method) pair of
+ * down_sampling_methods: block_reduce(img, (2, 1), y_method) while ceil(rows / 2) >= target_rows, block_reduce(img, (1, 2),
+ * x_method) while ceil(cols / 2) >= target_cols (parallel_image_processor.py:376-381); then skimage.transform.resize(img,
+ * target, preserve_range=True, anti_aliasing=True) (:383); uniform planes give zeros (:373-374).
+ * steps: n_steps pairs (y_method, x_method), b2s_ds_method or -1 for None.  pre_rows / pre_cols: the shape the caller
+ * expects ahead of the resize (checked).  wy / wx: the anti-aliasing Gaussian along each axis as numpy evaluates it
+ * (2 * radius + 1 float64 weights, NULL / radius 0 = none).  d_in: n_planes planes of in_dtype, d_out: n_planes float32
+ * planes of target_rows x target_cols, both DEVICE pointers; work is enqueued on `stream`. */
+int b2s_isotropic_xy(b2s_context *ctx, const void *d_in, int in_dtype, int rows, int cols, int n_steps, const int32_t *steps,
+                     int target_rows, int target_cols, int pre_rows, int pre_cols, const double *wy, int ry,
+                     const double *wx, int rx, float *d_out, int n_planes, void *stream);
+/* replaces: the z loop `block_reduce(z_stack, (2, 1, 1), z_method)` (parallel_image_processor.py:417-419) one level at
+ * a time: d_out[k] = method(d_in[2k], d_in[2k+1]) over float32 planes of plane_elems elements; an odd last plane is paired
+ * with zeros (cval = 0).  n_out = ceil(n_in / 2) planes are written. */
+int b2s_isotropic_z(b2s_context *ctx, const float *d_in, int n_in, int64_t plane_elems, int method, float *d_out, void *stream);
+/* replaces: the final conversion of the down-sampled plane (parallel_image_processor.py:422-433): mode 1 =
+ * convert_to_16bit_fun (core.py:397-399), 2 = convert_to_8bit_fun with `shift` (core.py:402-423), 4 = astype(uint8).
+ * d_out: uint16 (mode 1) or uint8. */
+int b2s_isotropic_convert(b2s_context *ctx, const float *d_in, int64_t n, int mode, int shift, void *d_out, void *stream);
+
+/* replaces: is_uniform_2d / is_uniform_3d (core.py:106-121) on a device array of n elements: *uniform = 1 when all equal */
+int b2s_is_uniform(b2s_context *ctx, const void *d_in, int dtype, int64_t n, int32_t *uniform, void *stream);
+
 int b2s_debug_math(b2s_context *ctx, int which /*0 log1pf, 1 expm1f*/, const float *in, float *out, int64_t n);
 
 #ifdef __cplusplus

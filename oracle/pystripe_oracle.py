@@ -376,6 +376,47 @@ def skimage_resize(image, output_shape, preserve_range=True, anti_aliasing=True,
     return out
 
 
+# ---- isotropic down-sampling of the post-stitch path (parallel_image_processor.py:371-433) -------
+def down_sample_xy(img, target_shape, down_sampling_methods):
+    """parallel_image_processor.py:371-385 (methods as 'max' / 'mean' / None)"""
+    if is_uniform_2d(img):
+        return np.zeros(target_shape, dtype=np.float32)
+    img = img.astype(np.float32)
+    for y_method, x_method in down_sampling_methods:
+        if y_method is not None and ceil(img.shape[0] / 2) >= target_shape[0]:
+            img = block_reduce(img, (2, 1), y_method)
+        if x_method is not None and ceil(img.shape[1] / 2) >= target_shape[1]:
+            img = block_reduce(img, (1, 2), x_method)
+    img = skimage_resize(img, target_shape, preserve_range=True, anti_aliasing=True)
+    return img.astype(np.float32)
+
+
+def down_sample_z(z_stack, down_sampling_method_z, down_sampled_dtype="float32", post_processed_dtype=None):
+    """parallel_image_processor.py:412-433"""
+    if (z_stack == z_stack.flat[0]).all():
+        return np.zeros(z_stack.shape[1:], dtype=np.float32)
+    for z_method in down_sampling_method_z:
+        if z_method is not None and z_stack.shape[0] > 1:
+            func = {'max': np.max, 'mean': np.mean}[z_method]
+            if z_stack.shape[0] % 2:
+                z_stack = np.concatenate([z_stack, np.zeros((1,) + z_stack.shape[1:], z_stack.dtype)])
+            z_stack = func(z_stack.reshape(z_stack.shape[0] // 2, 2, *z_stack.shape[1:]), axis=1)
+    assert z_stack.shape[0] == 1
+    img = z_stack[0]
+    dt = np.dtype(down_sampled_dtype)
+    if dt != np.float32:
+        if dt == np.uint16:
+            img = convert_to_16bit_fun(img)
+        elif dt == np.uint8:
+            if post_processed_dtype is not None and np.dtype(post_processed_dtype) == np.uint8:
+                img = img.astype(np.uint8)
+            else:
+                img = convert_to_8bit_fun(img)
+        else:
+            raise RuntimeError
+    return img
+
+
 # ---- process_img -------------------------------------------------------------------------------
 def process_img(img, flat=None, gaussian_filter_2d=False, down_sample=None, down_sample_method='max',
                 tile_size=None, new_size=None, sigma=(0, 0), level=0, wavelet='coif15', threshold=None,
