@@ -54,9 +54,9 @@ __device__ __forceinline__ float ext_sample(const float *row, int j, int n, cons
 
 __global__ void __launch_bounds__(kRows) k_bleach_lowpass(B2sBleachArgs a)
 {
+    static_assert(kRows == 32 && kChunk == 32, "one warp per CTA: lane = tile column on the global side, tile row in the recurrence");
     __shared__ float s_in[kRows][kChunk + 1];
     __shared__ double s_y[kRows][kChunk + 1];
-    __shared__ float s_red[kRows / 32];
     const int tid = threadIdx.x;
     const size_t plane = blockIdx.y;
     const int r0 = blockIdx.x * kRows;
@@ -68,26 +68,27 @@ __global__ void __launch_bounds__(kRows) k_bleach_lowpass(B2sBleachArgs a)
     const double b0 = a.b0, b1 = a.b1, a1 = a.a1;
     double z = 0.0, last = 0.0;
 
-    // forward over the extended row
-    for (int j0 = 0; j0 < N; j0 += kChunk) {
-        // loads first, stores after: 8 independent global loads in flight per thread instead of one
-        for (int e0 = tid; e0 < kRows * kChunk; e0 += 8 * kRows) {
-            float v[8];
+    // Global side: lane `tid` moves column j0 + tid of the 32 rows (a warp access = 128 / 256 contiguous bytes of one
+    // row).  The next tile is fetched into registers BEFORE the recurrence of the current one runs, so the global-load
+    // latency hides behind the dependent FP64 chain.
+    float pre[kRows];
+    auto fetch_ext = [&](int j0) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * kRows, rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = j0 + jj;
-                v[u] = (r < a.rows && j < N) ? ext_sample(img + (size_t)r * a.img.pitch, j, n, a) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * kRows;
-                s_in[e / kChunk][e % kChunk] = v[u];
-            }
+        for (int u = 0; u < kRows; ++u) {
+            const int r = r0 + u, j = j0 + tid;
+            pre[u] = (r < a.rows && j < N) ? ext_sample(img + (size_t)r * a.img.pitch, j, n, a) : 0.f;
         }
+    };
+    fetch_ext(0);
+    for (int j0 = 0; j0 < N; j0 += kChunk) {
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) s_in[u][tid] = pre[u];
         __syncthreads();
+        if (j0 + kChunk < N) fetch_ext(j0 + kChunk);
         if (live) {
             if (j0 == 0) z = a.zi * (double)s_in[tid][0];
             const int m = min(kChunk, N - j0);
+#pragma unroll 8
             for (int jj = 0; jj < m; ++jj) {
                 const double x = (double)s_in[tid][jj];
                 const double y = __dadd_rn(__dmul_rn(b0, x), z);
@@ -97,33 +98,36 @@ __global__ void __launch_bounds__(kRows) k_bleach_lowpass(B2sBleachArgs a)
             }
         }
         __syncthreads();
-        for (int e = tid; e < kRows * kChunk; e += kRows) {
-            const int rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = j0 + jj;
-            if (r < a.rows && j < N) scr[(size_t)r * N + j] = s_y[rr][jj];
-        }
-        __syncthreads();     // also orders this CTA's scratch writes before its own reads below
-    }
-
-    // backward: the reversed forward output through the same section, started from zi * y[last]
-    z = a.zi * last;
-    float mx = -INFINITY;
-    for (int j0 = ((N - 1) / kChunk) * kChunk; j0 >= 0; j0 -= kChunk) {
-        for (int e0 = tid; e0 < kRows * kChunk; e0 += 8 * kRows) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * kRows, rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = j0 + jj;
-                v[u] = (r < a.rows && j < N) ? scr[(size_t)r * N + j] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int e = e0 + u * kRows;
-                s_y[e / kChunk][e % kChunk] = v[u];
-            }
+#pragma unroll 8
+        for (int u = 0; u < kRows; ++u) {
+            const int r = r0 + u, j = j0 + tid;
+            if (r < a.rows && j < N) scr[(size_t)r * N + j] = s_y[u][tid];
         }
         __syncthreads();
+    }
+
+    // backward: the reversed forward output through the same section, started from zi * y[last].  Every lane reads
+    // back exactly the scratch addresses it wrote (same tile mapping), so program order makes the data visible.
+    z = a.zi * last;
+    float mx = -INFINITY;
+    double prd[kRows];
+    auto fetch_scr = [&](int j0) {
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+            const int r = r0 + u, j = j0 + tid;
+            prd[u] = (r < a.rows && j < N) ? scr[(size_t)r * N + j] : 0.0;
+        }
+    };
+    const int jlast = ((N - 1) / kChunk) * kChunk;
+    fetch_scr(jlast);
+    for (int j0 = jlast; j0 >= 0; j0 -= kChunk) {
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) s_y[u][tid] = prd[u];
+        __syncthreads();
+        if (j0 >= kChunk) fetch_scr(j0 - kChunk);
         if (live) {
             const int m = min(kChunk, N - j0);
+#pragma unroll 8
             for (int jj = m - 1; jj >= 0; --jj) {
                 const double x = s_y[tid][jj];
                 const double y = __dadd_rn(__dmul_rn(b0, x), z);
@@ -135,9 +139,10 @@ __global__ void __launch_bounds__(kRows) k_bleach_lowpass(B2sBleachArgs a)
             }
         }
         __syncthreads();
-        for (int e = tid; e < kRows * kChunk; e += kRows) {
-            const int rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = j0 + jj;
-            if (r < a.rows && j >= kEdge && j < kEdge + n) filt[(size_t)r * n + (j - kEdge)] = s_in[rr][jj];
+#pragma unroll 8
+        for (int u = 0; u < kRows; ++u) {
+            const int r = r0 + u, j = j0 + tid;
+            if (r < a.rows && j >= kEdge && j < kEdge + n) filt[(size_t)r * n + (j - kEdge)] = s_in[u][tid];
         }
         __syncthreads();
     }
@@ -146,12 +151,7 @@ __global__ void __launch_bounds__(kRows) k_bleach_lowpass(B2sBleachArgs a)
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < kRows / 32; ++w) mx = fmaxf(mx, s_red[w]);
-        atomicMax(a.maxkey + plane, f2key(mx));
-    }
+    if (tid == 0) atomicMax(a.maxkey + plane, f2key(mx));
 }
 
 // img = img / img_filter * max(img_filter), float32, in place on the cropped window of the padded image

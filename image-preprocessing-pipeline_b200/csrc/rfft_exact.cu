@@ -16,6 +16,7 @@
 // (k_notch_cplx below: complex radices 2,3,4,5,7,8,11, generic, Bluestein).  k_notch (fft.cu) remains for exact=0.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "b2s_internal.h"
@@ -1692,7 +1693,10 @@ void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B
     a.groups_per_plane = (a.nseq + a.G - 1) / a.G;
     cudaFuncSetAttribute(k_notch_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
     int bx = a.groups_per_plane;
-    const int cap = (sm_count * 8 + n_planes - 1) / n_planes;
+    // CTAs per SM the grid is capped at.  Measured on the bench workload (32 planes, 167 groups of 8 rows per plane):
+    // 8 -> 31.7 us/plane at level 1 (CTAs loop over 4 or 5 groups: a 10 % tail), 40 (one group per CTA) -> 29.5
+    static const int cap_mult = getenv("B2S_XFFT_CAP") ? atoi(getenv("B2S_XFFT_CAP")) : 40;
+    const int cap = (sm_count * cap_mult + n_planes - 1) / n_planes;
     if (bx > cap) bx = cap > 0 ? cap : 1;
     k_notch_exact<<<dim3(bx, n_planes), kXT, pl->smem, s>>>(a);
 }
