@@ -131,7 +131,7 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
     if (p.bleach) {   // correct_bleaching, core.py:501-559 (non-max method) — runs on the cropped reconstruction
         if (!p.log1p)
             return fail(ctx, B2S_ERR_UNSUPPORTED, "bleach correction needs log1p_normalization_needed=True (the reference's clip levels are log-domain)");
-        if (g.work_cols <= 6)
+        if (g.work_cols <= 6 || (p.bleach == 2 && g.work_rows <= 6))
             return fail(ctx, B2S_ERR_INVALID, "The length of the input vector x must be greater than padlen, which is 6.");
     }
     g.log_image = g.n_passes > 0 || p.bleach;   // sigma = (0, 0) with a bleach frequency: log1p -> bleach -> expm1, no padding (core.py:1081, 1131)
@@ -716,7 +716,8 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             b.scratch_plane_stride = (size_t)g.work_rows * (g.work_cols + 12);
             b.filt = s.bleach_filt;
             b.maxkey = s.bleach_max;
-            b2s_launch_bleach(b, nb, st);
+            if (p.bleach == 2) b2s_launch_bleach_max_method(b, nb, st);
+            else b2s_launch_bleach(b, nb, st);
         }
     }
     {

@@ -160,6 +160,8 @@ struct B2sBleachArgs {
 };
 // correct_bleaching (core.py:501-559, non-max method) in place on the cropped window
 void b2s_launch_bleach(const B2sBleachArgs &a, int n_planes, cudaStream_t s);
+// max method (core.py:533-545); a.filt: 2 * (rows + cols) floats per plane, a.scratch: max(rows, cols) + 12 doubles per plane
+void b2s_launch_bleach_max_method(const B2sBleachArgs &a, int n_planes, cudaStream_t s);
 
 // lightsheet.cu -------------------------------------------------------------------------------------------------
 struct B2sLightsheet;

@@ -167,7 +167,93 @@ __global__ void __launch_bounds__(256) k_bleach_apply(B2sBleachArgs a)
     *p = __fmul_rn(__fdiv_rn(*p, f), mx);
 }
 
+// ---- max method (core.py:533-545): the filter is the outer product of the low-passed row maxima and column maxima
+__global__ void __launch_bounds__(256) k_bleach_row_max(B2sBleachArgs a, float *vy)
+{
+    __shared__ float s_red[8];
+    const size_t plane = blockIdx.y;
+    const int r = blockIdx.x;
+    const float *row = a.img.ptr + plane * a.img.plane_stride + (size_t)(a.base_pad + r) * a.img.pitch + a.base_pad;
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < a.cols; c += 256) m = fmaxf(m, row[c]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w]);
+        vy[plane * a.rows + r] = m;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bleach_col_max(B2sBleachArgs a, float *vx)
+{
+    const size_t plane = blockIdx.y;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= a.cols) return;
+    const float *p = a.img.ptr + plane * a.img.plane_stride + (size_t)a.base_pad * a.img.pitch + a.base_pad + c;
+    float m = -INFINITY;
+    for (int r = 0; r < a.rows; ++r) m = fmaxf(m, p[(size_t)r * a.img.pitch]);
+    vx[plane * a.cols + c] = m;
+}
+
+// max over the outer product (float32 products, as numpy.dot of an (H, 1) by a (1, W) matrix forms them)
+__global__ void __launch_bounds__(256) k_bleach_outer_max(B2sBleachArgs a, const float *fy, const float *fx)
+{
+    __shared__ float s_red[8];
+    const size_t plane = blockIdx.y;
+    const float y = fy[plane * a.rows + blockIdx.x];
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < a.cols; c += 256) m = fmaxf(m, __fmul_rn(y, fx[plane * a.cols + c]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w]);
+        atomicMax(a.maxkey + plane, f2key(m));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bleach_apply_outer(B2sBleachArgs a, const float *fy, const float *fx)
+{
+    const size_t plane = blockIdx.z;
+    const int r = blockIdx.y;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= a.cols) return;
+    float *p = a.img.ptr + plane * a.img.plane_stride + (size_t)(a.base_pad + r) * a.img.pitch + a.base_pad + c;
+    const float f = __fmul_rn(fy[plane * a.rows + r], fx[plane * a.cols + c]);
+    *p = __fmul_rn(__fdiv_rn(*p, f), key2f(a.maxkey[plane]));
+}
+
 }  // namespace
+
+// max method: a.filt holds, per plane, [row maxima (rows) | column maxima (cols) | filtered rows | filtered cols];
+// a.scratch needs (max(rows, cols) + 12) doubles per plane
+void b2s_launch_bleach_max_method(const B2sBleachArgs &a, int n_planes, cudaStream_t s)
+{
+    const size_t per = 2 * ((size_t)a.rows + a.cols);
+    float *vy = a.filt, *vx = vy + (size_t)n_planes * a.rows;
+    float *fy = vx + (size_t)n_planes * a.cols, *fx = fy + (size_t)n_planes * a.rows;
+    (void)per;
+    k_bleach_row_max<<<dim3(a.rows, n_planes), 256, 0, s>>>(a, vy);
+    k_bleach_col_max<<<dim3((a.cols + 255) / 256, n_planes), 256, 0, s>>>(a, vx);
+    // the 1-D low-pass of each vector = the 2-D kernel on a one-row image per plane
+    for (int which = 0; which < 2; ++which) {
+        B2sBleachArgs v = a;
+        const int len = which == 0 ? a.rows : a.cols;
+        v.img.ptr = which == 0 ? vy : vx;
+        v.img.plane_stride = len; v.img.pitch = len; v.img.rows = 1; v.img.cols = len;
+        v.base_pad = 0; v.rows = 1; v.cols = len;
+        v.scratch_plane_stride = (size_t)len + 12;
+        v.filt = which == 0 ? fy : fx;
+        cudaMemsetAsync(a.maxkey, 0, sizeof(unsigned) * n_planes, s);
+        k_bleach_lowpass<<<dim3(1, n_planes), kRows, 0, s>>>(v);
+    }
+    cudaMemsetAsync(a.maxkey, 0, sizeof(unsigned) * n_planes, s);
+    k_bleach_outer_max<<<dim3(a.rows, n_planes), 256, 0, s>>>(a, fy, fx);
+    k_bleach_apply_outer<<<dim3((a.cols + 255) / 256, a.rows, n_planes), 256, 0, s>>>(a, fy, fx);
+}
 
 void b2s_launch_bleach(const B2sBleachArgs &a, int n_planes, cudaStream_t s)
 {

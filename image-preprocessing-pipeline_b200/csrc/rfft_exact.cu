@@ -1668,6 +1668,14 @@ void b2s_xfft_destroy(B2sXfftPlan *pl)
     delete pl;
 }
 
+// CTAs per SM the grid is capped at.  Measured on the bench workload (32 planes, 167 groups of 8 rows per plane):
+// 8 -> 31.7 us/plane at level 1 (CTAs loop over 4 or 5 groups: a 10 % tail), 40 (one group per CTA) -> 29.5
+static int xfft_cap_mult()
+{
+    static const int m = getenv("B2S_XFFT_CAP") ? atoi(getenv("B2S_XFFT_CAP")) : 40;
+    return m > 0 ? m : 1;
+}
+
 void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B2sImg &img, int along_cols, int n_planes,
                             int sm_count, cudaStream_t s)
 {
@@ -1680,7 +1688,7 @@ void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B
         a.groups_per_plane = (a.nseq + a.G - 1) / a.G;
         cudaFuncSetAttribute(k_notch_cplx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
         int bx = a.groups_per_plane;
-        const int cap = (sm_count * 8 + n_planes - 1) / n_planes;
+        const int cap = (sm_count * xfft_cap_mult() + n_planes - 1) / n_planes;
         if (bx > cap) bx = cap > 0 ? cap : 1;
         k_notch_cplx<<<dim3(bx, n_planes), kXT, pl->smem, s>>>(a);
         return;
@@ -1693,10 +1701,7 @@ void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B
     a.groups_per_plane = (a.nseq + a.G - 1) / a.G;
     cudaFuncSetAttribute(k_notch_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
     int bx = a.groups_per_plane;
-    // CTAs per SM the grid is capped at.  Measured on the bench workload (32 planes, 167 groups of 8 rows per plane):
-    // 8 -> 31.7 us/plane at level 1 (CTAs loop over 4 or 5 groups: a 10 % tail), 40 (one group per CTA) -> 29.5
-    static const int cap_mult = getenv("B2S_XFFT_CAP") ? atoi(getenv("B2S_XFFT_CAP")) : 40;
-    const int cap = (sm_count * cap_mult + n_planes - 1) / n_planes;
+    const int cap = (sm_count * xfft_cap_mult() + n_planes - 1) / n_planes;
     if (bx > cap) bx = cap > 0 ? cap : 1;
     k_notch_exact<<<dim3(bx, n_planes), kXT, pl->smem, s>>>(a);
 }

@@ -330,8 +330,7 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
             p.new_height, p.new_width = int(new_size[0]), int(new_size[1])
         if bleach is not None:
             (p.bleach_b0, p.bleach_b1, p.bleach_a1, p.bleach_zi,
-             p.bleach_clip_min, p.bleach_clip_med, p.bleach_clip_max) = bleach
-            p.bleach = 1
+             p.bleach_clip_min, p.bleach_clip_med, p.bleach_clip_max, p.bleach) = bleach
         p.pad_constant = float(pad_constant)
         p.aa_radius_y = 0 if aa[0] is None else int(aa[0][0])
         p.aa_radius_x = 0 if aa[1] is None else int(aa[1][0])
@@ -423,8 +422,6 @@ def _bleach_plan_args(frequency, clip_min, clip_med, clip_max, max_method, enabl
     if clip_min is None or clip_med is None or clip_max is None:
         raise NotImplementedError("bleach correction with clip levels left to threshold_multiotsu (core.py:1066-1077) is "
                                   "not implemented: pass bleach_correction_clip_min / _med / _max")
-    if max_method:
-        raise NotImplementedError("bleach_correction_max_method=True is not implemented on the GPU path")
     ok = (float, float32, np.float64)
     assert isinstance(frequency, ok) and frequency > 0                   # core.py:521-527
     assert isinstance(clip_min, ok) and clip_min >= 0
@@ -442,7 +439,8 @@ def _bleach_plan_args(frequency, clip_min, clip_med, clip_max, max_method, enabl
     zi = sosfilt_zi(sos)
     assert sos.shape == (1, 6) and sos[0, 2] == 0 and sos[0, 5] == 0 and sos[0, 3] == 1 and zi[0, 1] == 0
     return (float(sos[0, 0]), float(sos[0, 1]), float(sos[0, 4]), float(zi[0, 0]),
-            as_clip_sees(clip_min), float(np.float32(clip_med)), as_clip_sees(clip_max)), pad_constant
+            as_clip_sees(clip_min), float(np.float32(clip_med)), as_clip_sees(clip_max),
+            2 if max_method else 1), pad_constant
 
 
 def filter_streaks(

@@ -81,7 +81,8 @@ typedef struct b2s_params {
                                      lightsheet stage, before the 8/16-bit conversion; 0 = none.  Pure up-sizing
                                      (anti_aliasing with sigma 0) and down-sizing (anti_aliasing=False) only     */
     /* --- bleach correction inside filter_streaks (core.py:501-559, 1131-1148) -------------------------- */
-    int32_t bleach;               /* 1: correct_bleaching (non-max method) on the cropped log image, before expm1:
+    int32_t bleach;               /* 1: correct_bleaching (non-max method) on the cropped log image, before expm1;
+                                     2: max method (core.py:533-545): outer product of the low-passed row / column maxima:
                                      filter = sosfiltfilt(butter(1, frequency), clip(img with 0 -> clip_med)) along each
                                      row in float64 (scipy.signal, odd extension of 6 samples, sosfilt_zi start), cast to
                                      float32; img = img / filter * max(filter)                                    */

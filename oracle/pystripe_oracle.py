@@ -136,15 +136,23 @@ def butter_lowpass_filter(img, cutoff_frequency, order=1):
     return sosfiltfilt(sos, img).astype(d_type)
 
 
-def correct_bleaching(img, frequency, clip_min, clip_med, clip_max):
-    """core.py:501-559, non-max method, numpy branch (float32 throughout; the numexpr expression has the same order)."""
+def correct_bleaching(img, frequency, clip_min, clip_med, clip_max, max_method=False):
+    """core.py:501-559, numpy branch (float32 throughout; the numexpr expression has the same order)."""
     clip_min_lb = np.log1p(1)
     if clip_min < clip_min_lb:
         clip_min = clip_min_lb
-    img_filter = img.copy()
-    img_filter[img_filter == 0] = clip_med
-    np.clip(img_filter, clip_min, clip_max, out=img_filter)
-    img_filter = butter_lowpass_filter(img_filter, frequency)
+    if max_method:                                                                 # core.py:533-545
+        fy, fx = np.max(img, axis=1), np.max(img, axis=0)
+        fy[fy == 0] = clip_med
+        fx[fx == 0] = clip_med
+        fy, fx = np.clip(fy, clip_min, clip_max), np.clip(fx, clip_min, clip_max)
+        fy, fx = butter_lowpass_filter(fy, frequency), butter_lowpass_filter(fx, frequency)
+        img_filter = np.dot(fy.reshape(len(fy), 1), fx.reshape(1, len(fx)))
+    else:
+        img_filter = img.copy()
+        img_filter[img_filter == 0] = clip_med
+        np.clip(img_filter, clip_min, clip_max, out=img_filter)
+        img_filter = butter_lowpass_filter(img_filter, frequency)
     img_filter_max = np.max(img_filter)
     img = img / img_filter
     img *= img_filter_max
@@ -180,8 +188,8 @@ def sosfiltfilt_order1_restated(x, sos, zi0):
 def filter_streaks(img, sigma=(250, 250), level=0, wavelet='db9', crossover=10, threshold=None,
                    padding_mode="wrap", bidirectional=False, log1p_normalization_needed=True,
                    return_log_domain=False, bleach_correction_frequency=None, bleach_correction_clip_min=None,
-                   bleach_correction_clip_med=None, bleach_correction_clip_max=None):
-    """core.py:982-1159 without masking, multi-Otsu clip levels and the max-method of the bleach correction."""
+                   bleach_correction_clip_med=None, bleach_correction_clip_max=None, bleach_correction_max_method=False):
+    """core.py:982-1159 without masking and multi-Otsu clip levels."""
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
     s1, s2 = sigma
@@ -206,7 +214,7 @@ def filter_streaks(img, sigma=(250, 250), level=0, wavelet='db9', crossover=10, 
             assert img.shape == shape
     if bleach_correction_frequency is not None:                                    # core.py:1131-1139
         img = correct_bleaching(np.ascontiguousarray(img), bleach_correction_frequency, bleach_correction_clip_min,
-                                bleach_correction_clip_med, bleach_correction_clip_max)
+                                bleach_correction_clip_med, bleach_correction_clip_max, bleach_correction_max_method)
     if return_log_domain:
         return np.ascontiguousarray(img)
     if log1p_normalization_needed:
@@ -425,7 +433,7 @@ def process_img(img, flat=None, gaussian_filter_2d=False, down_sample=None, down
                 lightsheet_vs_background=2.0, rotate=0, flip_upside_down=False, convert_to_16bit=False,
                 convert_to_8bit=False, bit_shift_to_right=8, d_type=None, quirks=False,
                 bleach_correction_frequency=None, bleach_correction_clip_min=None, bleach_correction_clip_med=None,
-                bleach_correction_clip_max=None):
+                bleach_correction_clip_max=None, bleach_correction_max_method=False):
     """core.py:1190-1381 (order of operations preserved; bleach / dark-edge options not restated)."""
     if tile_size is None:
         tile_size = img.shape
@@ -466,7 +474,8 @@ def process_img(img, flat=None, gaussian_filter_2d=False, down_sample=None, down
                              bleach_correction_frequency=bleach_correction_frequency,
                              bleach_correction_clip_min=bleach_correction_clip_min,
                              bleach_correction_clip_med=bleach_correction_clip_med,
-                             bleach_correction_clip_max=bleach_correction_clip_max)
+                             bleach_correction_clip_max=bleach_correction_clip_max,
+                             bleach_correction_max_method=bleach_correction_max_method)
     if dark is not None and dark > 0:                                  # :1324-1330 (numpy branch)
         img = np.where(img > dark, img - dark, 0)
     if lightsheet:                                                     # :1333-1348

@@ -47,6 +47,9 @@ def all_cases():
     zeros_in = a.copy()
     zeros_in[20:40, 30:90] = 0
     yield "fs_bleach_zero_patch_odd", fs, zeros_in[:95, :127], dict(sigma=(8, 8), wavelet="db2", padding_mode="symmetric", **bl)
+    yield "fs_bleach_max_method", fs, d, dict(sigma=(32, 32), wavelet="db9", padding_mode="reflect",
+                                             bleach_correction_max_method=True, **bl)
+    yield "fs_bleach_max_method_zero_rows_odd", fs, zeros_in[:95, :127], dict(sigma=(0, 0), bleach_correction_max_method=True, **bl)
     yield "fs_bleach_only_sigma0_odd", fs, zeros_in[:95, :127], dict(sigma=(0, 0), **bl)
     pi = "process_img"
     img = synth.plane(3, (96, 128))

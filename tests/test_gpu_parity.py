@@ -477,7 +477,7 @@ def test_bleach_correction_goldens_bit_exact():
         REPORT["bleach/" + name] = {"exact_fraction": float(same.mean())}
         assert same.all(), (name, float(same.mean()), float(np.abs(got.astype(np.float64) - ref).max()))
         n += 1
-    assert n == 8
+    assert n == 10
 
 
 @pytest.mark.parametrize("shape,freq", [((700, 900), 1 / 700.0), ((257, 2051), 1 / 2048.0)])
@@ -501,5 +501,4 @@ def test_bleach_argument_errors():
         core.filter_streaks(img, sigma=(8, 8), bleach_correction_frequency=0.01, bleach_correction_clip_min=5.0,
                             bleach_correction_clip_med=4.0, bleach_correction_clip_max=6.0)
     with pytest.raises(NotImplementedError):
-        core.filter_streaks(img, sigma=(8, 8), bleach_correction_frequency=0.01, bleach_correction_clip_min=1.0,
-                            bleach_correction_clip_med=4.0, bleach_correction_clip_max=6.0, bleach_correction_max_method=True)
+        core.filter_streaks(img, sigma=(8, 8), enable_masking=True)

@@ -249,8 +249,8 @@ def test_bleach_plan_args_host_logic():
     assert b2[4] == float(np.float32(4.8)) and b2[6] == float(np.float32(7.4))
     with pytest.raises(NotImplementedError):
         core._bleach_plan_args(0.01, None, 5.0, 6.0, False, False)
-    with pytest.raises(NotImplementedError):
-        core._bleach_plan_args(0.01, 4.0, 5.0, 6.0, True, False)
+    assert core._bleach_plan_args(0.01, 4.0, 5.0, 6.0, True, False)[0][7] == 2    # max method (batch_filter's default)
+    assert b[7] == 1
     with pytest.raises(NotImplementedError):
         core._bleach_plan_args(None, None, None, None, False, True)
     with pytest.raises(AssertionError):
