@@ -337,7 +337,14 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
         p.max_batch = int(max_batch or MAX_BATCH)
         p.debug_stop_after = int(stop_after)
         p.exact = int(EXACT if exact is None else exact)
-        plan = _native.Plan(_native.context(device), p, dec_lo=taps, flat=flat)
+        try:
+            plan = _native.Plan(_native.context(device), p, dec_lo=taps, flat=flat)
+        except MemoryError:
+            # cached plans own workspace (gigabytes each for whole stitched slices): give it back and try once more
+            for old in _plans.values():
+                old.close()
+            _plans.clear()
+            plan = _native.Plan(_native.context(device), p, dec_lo=taps, flat=flat)
         plan._flat_ref = flat  # keep id(flat) stable while the plan is cached
         _upload_numpy_notch_tables(plan, s1, s2)
         for ax in range(2):

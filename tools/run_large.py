@@ -44,3 +44,23 @@ for name, (img, kw) in cases.items():
     torch.cuda.empty_cache()
 (ROOT / "gpurun_out").mkdir(exist_ok=True)
 (ROOT / "gpurun_out" / "large_report.json").write_text(json.dumps(out, indent=1))
+
+# isotropic down-sampling of the same slices (parallel_image_processor.py:371-385), device-resident uint8 planes
+from pystripe import isotropic as iso
+iso_out = {}
+for shape in ((4096, 6144), (10000, 14000), (15000, 20000)):
+    t, m = iso.calculate_down_sampling_target(shape, shape, (1.0, 0.8, 0.8), 10.0)
+    d_in = (torch.arange(shape[0] * shape[1], device="cuda", dtype=torch.int32) % 251).to(torch.uint8).reshape(1, *shape)
+    iso.down_sample_xy(d_in, t, m)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        iso.down_sample_xy(d_in, t, m)
+    e1.record()
+    torch.cuda.synchronize()
+    iso_out[f"{shape[0]}x{shape[1]}"] = {"target": list(t), "steps": len(m), "ms_per_plane": round(e0.elapsed_time(e1) / 3, 3)}
+    print("isotropic", shape, iso_out[f"{shape[0]}x{shape[1]}"], flush=True)
+    del d_in
+out["isotropic_down_sample_xy"] = iso_out
+(ROOT / "gpurun_out" / "large_report.json").write_text(json.dumps(out, indent=1))
