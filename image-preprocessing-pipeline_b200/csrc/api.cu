@@ -1259,12 +1259,14 @@ int b2s_isotropic_xy(b2s_context *ctx, const void *d_in, int in_dtype, int rows,
         b2s_launch_block_reduce(cur, cur_dt, r, c, by, bx, method, buf[k], B2S_F32, nr, nc, n_planes, st);
         cur = buf[k]; cur_dt = B2S_F32; r = nr; c = nc; k ^= 1; ++launches;
     };
-    reduce(1, 1, B2S_DS_MAX);
+    // (the first reduction reads the integer plane itself: max / mean of two integers in float32 equals the same
+    // operation on their float32 copies; only a plane that is not reduced at all needs the explicit conversion)
     for (int i = 0; i < n_steps; ++i) {
         const int ym = steps[2 * i], xm = steps[2 * i + 1];
         if (ym >= 0 && (r + 1) / 2 >= target_rows) reduce(2, 1, ym);
         if (xm >= 0 && (c + 1) / 2 >= target_cols) reduce(1, 2, xm);
     }
+    if (cur_dt != B2S_F32) reduce(1, 1, B2S_DS_MAX);
     if (r != pre_rows || c != pre_cols) {
         release();
         return fail(ctx, B2S_ERR_INVALID, "isotropic down-sampling: the reductions end at %d x %d, the caller expected %d x %d", r, c, pre_rows, pre_cols);

@@ -12,9 +12,10 @@
 //       y = b0*x + z;  z = (b1*x - a1*y) [+ 0]        (separate multiplies and adds: file compiled with -fmad=false)
 //     started at z = zi * x_ext[0]; the output is reversed and filtered again from z = zi * y[last]; the edges are
 //     dropped and the result is cast to float32.
-// The recurrence is sequential along a row, rows are independent: one thread per row, 32 rows (one warp) per CTA, the row segments
-// pass through shared-memory tiles so that global loads/stores stay coalesced (a warp moves 128 / 256 contiguous bytes
-// of one row).  The forward output (float64) goes through a per-slot scratch buffer that the same CTA reads back.
+// The recurrence is sequential along a row, rows are independent: one thread per row, 32 rows per CTA run by one consumer
+// warp; three producer warps move the row segments through double-buffered shared-memory tiles so that global
+// loads/stores stay coalesced and overlap the recurrence.  The forward output (float64) goes through a per-slot scratch
+// buffer that the same CTA reads back.
 #include "b2s_internal.h"
 
 namespace {
@@ -52,106 +53,134 @@ __device__ __forceinline__ float ext_sample(const float *row, int j, int n, cons
     return __fsub_rn(2.0f * filt_input(row, n - 1, a), filt_input(row, n - 2 - (j - kEdge - n), a));
 }
 
-__global__ void __launch_bounds__(kRows) k_bleach_lowpass(B2sBleachArgs a)
+// One CTA = 32 rows: warp 0 runs the recurrences (lane = row), warps 1-3 move the tiles.  Tiles are double-buffered in
+// shared memory, one barrier per tile: while the consumer warp works through tile k, the producer warps fetch tile k+1
+// from global memory (clip / odd extension applied on the way) and write the consumer's tile k-1 back, so the time per
+// tile is max(recurrence, memory) instead of their sum.
+constexpr int kProducers = 96;
+constexpr int kTileElems = kRows * kChunk;
+constexpr int kPerProducer = (kTileElems + kProducers - 1) / kProducers;   // 11
+
+__global__ void __launch_bounds__(kRows + kProducers) k_bleach_lowpass(B2sBleachArgs a)
 {
-    static_assert(kRows == 32 && kChunk == 32, "one warp per CTA: lane = tile column on the global side, tile row in the recurrence");
-    __shared__ float s_in[kRows][kChunk + 1];
-    __shared__ double s_y[kRows][kChunk + 1];
+    static_assert(kRows == 32 && kChunk == 32, "warp 0: lane = row of the tile");
+    __shared__ float s_f[2][kRows][kChunk + 1];
+    __shared__ double s_d[2][kRows][kChunk + 1];
     const int tid = threadIdx.x;
+    const bool consumer = tid < kRows;
+    const int ptid = tid - kRows;
     const size_t plane = blockIdx.y;
     const int r0 = blockIdx.x * kRows;
     const int n = a.cols, N = n + 2 * kEdge;
+    const int nch = (N + kChunk - 1) / kChunk;
     const float *img = a.img.ptr + plane * a.img.plane_stride + (size_t)a.base_pad * a.img.pitch + a.base_pad;
     double *scr = a.scratch + plane * a.scratch_plane_stride;
     float *filt = a.filt + plane * (size_t)a.rows * n;
-    const bool live = r0 + tid < a.rows;
+    const bool live = consumer && r0 + tid < a.rows;
     const double b0 = a.b0, b1 = a.b1, a1 = a.a1;
     double z = 0.0, last = 0.0;
 
-    // Global side: lane `tid` moves column j0 + tid of the 32 rows (a warp access = 128 / 256 contiguous bytes of one
-    // row).  The next tile is fetched into registers BEFORE the recurrence of the current one runs, so the global-load
-    // latency hides behind the dependent FP64 chain.
-    float pre[kRows];
-    auto fetch_ext = [&](int j0) {
+    auto load_ext = [&](int t, int buf) {            // producers: tile t of the extended rows -> s_f[buf]
+        float v[kPerProducer];
 #pragma unroll
-        for (int u = 0; u < kRows; ++u) {
-            const int r = r0 + u, j = j0 + tid;
-            pre[u] = (r < a.rows && j < N) ? ext_sample(img + (size_t)r * a.img.pitch, j, n, a) : 0.f;
+        for (int i = 0; i < kPerProducer; ++i) {
+            const int e = ptid + kProducers * i, rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = t * kChunk + jj;
+            v[i] = (e < kTileElems && r < a.rows && j < N) ? ext_sample(img + (size_t)r * a.img.pitch, j, n, a) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < kPerProducer; ++i) {
+            const int e = ptid + kProducers * i;
+            if (e < kTileElems) s_f[buf][e / kChunk][e % kChunk] = v[i];
         }
     };
-    fetch_ext(0);
-    for (int j0 = 0; j0 < N; j0 += kChunk) {
+    auto store_scr = [&](int t, int buf) {           // producers: s_d[buf] -> scratch tile t
 #pragma unroll
-        for (int u = 0; u < kRows; ++u) s_in[u][tid] = pre[u];
-        __syncthreads();
-        if (j0 + kChunk < N) fetch_ext(j0 + kChunk);
-        if (live) {
-            if (j0 == 0) z = a.zi * (double)s_in[tid][0];
-            const int m = min(kChunk, N - j0);
+        for (int i = 0; i < kPerProducer; ++i) {
+            const int e = ptid + kProducers * i, rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = t * kChunk + jj;
+            if (e < kTileElems && r < a.rows && j < N) scr[(size_t)r * N + j] = s_d[buf][rr][jj];
+        }
+    };
+    auto load_scr = [&](int t, int buf) {            // producers: scratch tile t -> s_d[buf]
+        double v[kPerProducer];
+#pragma unroll
+        for (int i = 0; i < kPerProducer; ++i) {
+            const int e = ptid + kProducers * i, rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = t * kChunk + jj;
+            v[i] = (e < kTileElems && r < a.rows && j < N) ? scr[(size_t)r * N + j] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < kPerProducer; ++i) {
+            const int e = ptid + kProducers * i;
+            if (e < kTileElems) s_d[buf][e / kChunk][e % kChunk] = v[i];
+        }
+    };
+    auto store_filt = [&](int t, int buf) {          // producers: s_f[buf] -> img_filter tile t (edges dropped)
+#pragma unroll
+        for (int i = 0; i < kPerProducer; ++i) {
+            const int e = ptid + kProducers * i, rr = e / kChunk, jj = e % kChunk, r = r0 + rr, j = t * kChunk + jj;
+            if (e < kTileElems && r < a.rows && j >= kEdge && j < kEdge + n) filt[(size_t)r * n + (j - kEdge)] = s_f[buf][rr][jj];
+        }
+    };
+
+    // forward over the extended row
+    if (!consumer) load_ext(0, 0);
+    __syncthreads();
+    for (int k = 0; k < nch; ++k) {
+        if (!consumer) {
+            if (k + 1 < nch) load_ext(k + 1, (k + 1) & 1);
+            if (k >= 1) store_scr(k - 1, (k - 1) & 1);
+        } else if (live) {
+            const int b = k & 1;
+            if (k == 0) z = a.zi * (double)s_f[0][tid][0];
+            const int m = min(kChunk, N - k * kChunk);
 #pragma unroll 8
             for (int jj = 0; jj < m; ++jj) {
-                const double x = (double)s_in[tid][jj];
+                const double x = (double)s_f[b][tid][jj];
                 const double y = __dadd_rn(__dmul_rn(b0, x), z);
                 z = __dsub_rn(__dmul_rn(b1, x), __dmul_rn(a1, y));
-                s_y[tid][jj] = y;
+                s_d[b][tid][jj] = y;
                 last = y;
             }
         }
         __syncthreads();
-#pragma unroll 8
-        for (int u = 0; u < kRows; ++u) {
-            const int r = r0 + u, j = j0 + tid;
-            if (r < a.rows && j < N) scr[(size_t)r * N + j] = s_y[u][tid];
-        }
-        __syncthreads();
     }
+    if (!consumer) store_scr(nch - 1, (nch - 1) & 1);
+    __syncthreads();     // block-wide: the scratch writes above are visible to this CTA's reads below
 
-    // backward: the reversed forward output through the same section, started from zi * y[last].  Every lane reads
-    // back exactly the scratch addresses it wrote (same tile mapping), so program order makes the data visible.
+    // backward: the reversed forward output through the same section, started from zi * y[last]
     z = a.zi * last;
     float mx = -INFINITY;
-    double prd[kRows];
-    auto fetch_scr = [&](int j0) {
-#pragma unroll
-        for (int u = 0; u < kRows; ++u) {
-            const int r = r0 + u, j = j0 + tid;
-            prd[u] = (r < a.rows && j < N) ? scr[(size_t)r * N + j] : 0.0;
-        }
-    };
-    const int jlast = ((N - 1) / kChunk) * kChunk;
-    fetch_scr(jlast);
-    for (int j0 = jlast; j0 >= 0; j0 -= kChunk) {
-#pragma unroll
-        for (int u = 0; u < kRows; ++u) s_y[u][tid] = prd[u];
-        __syncthreads();
-        if (j0 >= kChunk) fetch_scr(j0 - kChunk);
-        if (live) {
-            const int m = min(kChunk, N - j0);
+    if (!consumer) load_scr(nch - 1, 0);
+    __syncthreads();
+    for (int q = 0; q < nch; ++q) {
+        const int t = nch - 1 - q;
+        if (!consumer) {
+            if (q + 1 < nch) load_scr(t - 1, (q + 1) & 1);
+            if (q >= 1) store_filt(t + 1, (q - 1) & 1);
+        } else if (live) {
+            const int b = q & 1;
+            const int m = min(kChunk, N - t * kChunk);
 #pragma unroll 8
             for (int jj = m - 1; jj >= 0; --jj) {
-                const double x = s_y[tid][jj];
+                const double x = s_d[b][tid][jj];
                 const double y = __dadd_rn(__dmul_rn(b0, x), z);
                 z = __dsub_rn(__dmul_rn(b1, x), __dmul_rn(a1, y));
                 const float f = (float)y;
-                s_in[tid][jj] = f;
-                const int j = j0 + jj;
+                s_f[b][tid][jj] = f;
+                const int j = t * kChunk + jj;
                 if (j >= kEdge && j < kEdge + n) mx = fmaxf(mx, f);
             }
         }
         __syncthreads();
-#pragma unroll 8
-        for (int u = 0; u < kRows; ++u) {
-            const int r = r0 + u, j = j0 + tid;
-            if (r < a.rows && j >= kEdge && j < kEdge + n) filt[(size_t)r * n + (j - kEdge)] = s_in[u][tid];
-        }
-        __syncthreads();
     }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    if (tid == 0) atomicMax(a.maxkey + plane, f2key(mx));
+    if (!consumer) store_filt(0, (nch - 1) & 1);
+    if (consumer) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        if (tid == 0) atomicMax(a.maxkey + plane, f2key(mx));
+    }
 }
 
 // img = img / img_filter * max(img_filter), float32, in place on the cropped window of the padded image
@@ -248,7 +277,7 @@ void b2s_launch_bleach_max_method(const B2sBleachArgs &a, int n_planes, cudaStre
         v.scratch_plane_stride = (size_t)len + 12;
         v.filt = which == 0 ? fy : fx;
         cudaMemsetAsync(a.maxkey, 0, sizeof(unsigned) * n_planes, s);
-        k_bleach_lowpass<<<dim3(1, n_planes), kRows, 0, s>>>(v);
+        k_bleach_lowpass<<<dim3(1, n_planes), kRows + kProducers, 0, s>>>(v);
     }
     cudaMemsetAsync(a.maxkey, 0, sizeof(unsigned) * n_planes, s);
     k_bleach_outer_max<<<dim3(a.rows, n_planes), 256, 0, s>>>(a, fy, fx);
@@ -258,6 +287,6 @@ void b2s_launch_bleach_max_method(const B2sBleachArgs &a, int n_planes, cudaStre
 void b2s_launch_bleach(const B2sBleachArgs &a, int n_planes, cudaStream_t s)
 {
     cudaMemsetAsync(a.maxkey, 0, sizeof(unsigned) * n_planes, s);
-    k_bleach_lowpass<<<dim3((a.rows + kRows - 1) / kRows, n_planes), kRows, 0, s>>>(a);
+    k_bleach_lowpass<<<dim3((a.rows + kRows - 1) / kRows, n_planes), kRows + kProducers, 0, s>>>(a);
     k_bleach_apply<<<dim3((a.cols + 255) / 256, a.rows, n_planes), 256, 0, s>>>(a);
 }

@@ -18,6 +18,13 @@ CONFIGS = {
                                                 down_sample=(2, 2), convert_to_8bit=True, bit_shift_to_right=8), flat=True),
     "config4_lightsheet_destripe": dict(kw=dict(sigma=(256, 256), wavelet="db10", padding_mode="wrap", lightsheet=True), flat=False),
     "config5_coif15_dual_sigma": dict(kw=dict(sigma=(128, 512), wavelet="coif15", padding_mode="reflect"), flat=False),
+    "bleach_db9_sigma250_bidirectional": dict(kw=dict(sigma=(250, 250), wavelet="db9", padding_mode="reflect", bidirectional=True,
+                                                      bleach_correction_frequency=1 / 2048.0, bleach_correction_clip_min=4.7,
+                                                      bleach_correction_clip_med=5.5, bleach_correction_clip_max=8.0), flat=False),
+    "bleach_max_method_db9": dict(kw=dict(sigma=(250, 250), wavelet="db9", padding_mode="reflect",
+                                          bleach_correction_frequency=1 / 2048.0, bleach_correction_clip_min=4.7,
+                                          bleach_correction_clip_med=5.5, bleach_correction_clip_max=8.0,
+                                          bleach_correction_max_method=True), flat=False),
     "step3_db9_sigma250_bidirectional": dict(kw=dict(sigma=(250, 250), wavelet="db9", padding_mode="reflect", bidirectional=True), flat=False),
 }
 if __name__ != "__main__":
