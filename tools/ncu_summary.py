@@ -32,7 +32,10 @@ COLS = [
 
 def main():
     rep = sys.argv[1]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):      # already exported on the GPU box (`ncu -i rep --page raw --csv`): reports can exceed gpurun's 64 MiB
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, body = rows[0], rows[1], rows[2:]
     idx = [(hdr.index(c), name) for c, name, _ in COLS if c in hdr]
