@@ -343,6 +343,7 @@ def run_b200(a):
                     "d2h_bytes_per_step": int(P * plan.out_shape[0] * plan.out_shape[1] * np.dtype(plan.out_dtype).itemsize),
                     "timer": "host wall clock around the synchronous C-ABI call (internal streams), max over ranks",
                     "copy_only_ceiling": copy_only,
+                    "frac_of_copy_only_ceiling": (e2e_v / copy_only) if copy_only else None,
                     "copy_only_note": "same bytes per step moved H2D + D2H with no kernels, all ranks at once (PCIe / host "
                                       "memory ceiling of this box, in the metric's unit); e2e / ceiling is the overlap achieved"},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
