@@ -1116,11 +1116,12 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
     const int nsh = std::max(1, std::min(pl->n_slots, host_slots_env));
     int si = 0;
     int64_t z = 0;
-    int nb_next = Bh < 4 ? Bh : 4;
+    static const int ramp = std::max(1, getenv("B2S_HOST_RAMP") ? atoi(getenv("B2S_HOST_RAMP")) : 4);   // first / last batch size
+    int nb_next = Bh < ramp ? Bh : ramp;
     while (z < n_planes) {
         const int64_t left = n_planes - z;
         int nb = (int)std::min<int64_t>(nb_next, left);
-        if (left > 4 && nb > left / 2) nb = (int)std::max<int64_t>(4, left / 2);   // ramp down: halve what is left
+        if (left > ramp && nb > left / 2) nb = (int)std::max<int64_t>(ramp, left / 2);   // ramp down: halve what is left
         nb_next = std::min(Bh, nb_next * 2);
         b2s_plan::Slot &s = pl->slot[si];
         int rc = drain(si);
