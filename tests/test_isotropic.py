@@ -113,3 +113,22 @@ def test_gpu_down_sample_z_bit_exact(nz, dtype, post):
     ref = orc.down_sample_z(z, methods, dtype, post)
     assert got.dtype == ref.dtype and np.array_equal(got, ref)
     assert not iso.down_sample_z(np.full((4, 8, 8), 3.0, np.float32), methods).any()
+
+
+@pytest.mark.gpu
+def test_gpu_isotropic_accepts_cuda_tensors_zero_copy():
+    import torch
+    from pystripe import isotropic as iso
+    shape = (301, 407)
+    t, m = iso.calculate_down_sampling_target(shape, shape, (1.0, 0.8, 0.8), 10.0)
+    img = synth.plane(9, shape)
+    d = torch.from_numpy(img).cuda()
+    got = iso.down_sample_xy(d, t, m)
+    assert got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == t
+    ref = orc.down_sample_xy(img, t, m)
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    stack = torch.stack([got, got * 2, got * 0.5])
+    z = iso.down_sample_z(stack, ["max", "mean"], "uint16")
+    assert z.is_cuda and z.dtype == torch.uint16
+    assert np.array_equal(z.cpu().numpy(), orc.down_sample_z(stack.cpu().numpy(), ["max", "mean"], "uint16"))
+    assert iso.is_uniform(torch.full((64, 64), 5, dtype=torch.uint16, device="cuda")) and not iso.is_uniform(d)
