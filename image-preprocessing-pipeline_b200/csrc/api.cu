@@ -1,8 +1,14 @@
 // C ABI (include/b200stripe.h): contexts, plans (geometry, tables, workspace) and the batched run loop.
 #include <sched.h>
 
+#include <atomic>
 #include <cctype>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -14,7 +20,55 @@
 #include "../../include/b200stripe.h"
 #include "b2s_internal.h"
 
+// Host staging pool: pageable caller buffers are copied to / from the slots' pinned staging buffers by a few worker
+// threads (one memcpy thread moves ~10 GB/s, a PCIe 5 x16 link wants 2 x 46 GB/s), asynchronously to the run loop.
+struct HostPool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    bool stop = false;
+    explicit HostPool(int n)
+    {
+        for (int i = 0; i < n; ++i)
+            th.emplace_back([this] {
+                for (;;) {
+                    std::function<void()> f;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv.wait(lk, [this] { return stop || !q.empty(); });
+                        if (q.empty()) return;
+                        f = std::move(q.front());
+                        q.pop_front();
+                    }
+                    f();
+                }
+            });
+    }
+    ~HostPool()
+    {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv.notify_all();
+        for (auto &t : th) t.join();
+    }
+    void submit(std::function<void()> f)
+    {
+        { std::lock_guard<std::mutex> lk(m); q.push_back(std::move(f)); }
+        cv.notify_one();
+    }
+    int size() const { return (int)th.size(); }
+};
+struct TaskGroup {
+    std::mutex m;
+    std::condition_variable cv;
+    int pending = 0;
+    void add(int n) { std::lock_guard<std::mutex> lk(m); pending += n; }
+    void done() { std::lock_guard<std::mutex> lk(m); if (--pending == 0) cv.notify_all(); }
+    void wait() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [this] { return pending == 0; }); }
+};
+
 struct b2s_context {
+    HostPool *pool = nullptr;
     int device = 0;
     int sm_count = 0;
     std::string err;
@@ -830,7 +884,8 @@ cudaError_t numa_local_malloc_host(b2s_context *ctx, void **ptr, size_t bytes)
                 if (fgets(line, sizeof line, f)) {
                     CPU_ZERO(&local);
                     int n_local = 0;
-                    for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+                    char *save = nullptr;   // strtok_r: feeder threads of several GPUs allocate concurrently
+                    for (char *tok = strtok_r(line, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {
                         int a = 0, b = 0;
                         const int k = sscanf(tok, "%d-%d", &a, &b);
                         if (k == 1) b = a;
@@ -856,6 +911,36 @@ bool is_pinned_host(const void *p)
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeHost;
+}
+
+// worker threads for pageable staging: B2S_HOST_THREADS, else min(8, cores / (2 x processes on this box))
+HostPool *host_pool(b2s_context *ctx)
+{
+    if (!ctx->pool) {
+        int n = getenv("B2S_HOST_THREADS") ? atoi(getenv("B2S_HOST_THREADS")) : 0;
+        if (n <= 0) {
+            const char *w = getenv("LOCAL_WORLD_SIZE") ? getenv("LOCAL_WORLD_SIZE") : getenv("WORLD_SIZE");
+            const int world = std::max(1, w ? atoi(w) : 1);
+            const int hw = (int)std::thread::hardware_concurrency();
+            n = std::max(1, std::min(8, hw / (2 * world)));
+        }
+        ctx->pool = new HostPool(n);
+    }
+    return ctx->pool;
+}
+
+// memcpy split over the pool; `grp` counts the chunks still running
+void copy_async(HostPool *pool, TaskGroup *grp, void *dst, const void *src, size_t bytes)
+{
+    const size_t min_chunk = 1 << 20;
+    int parts = (int)std::min<size_t>((size_t)pool->size(), (bytes + min_chunk - 1) / min_chunk);
+    if (parts < 1) parts = 1;
+    const size_t per = ((bytes + parts - 1) / parts + 63) & ~(size_t)63;
+    grp->add(parts);
+    for (int i = 0; i < parts; ++i) {
+        const size_t o = std::min(bytes, per * i), e = std::min(bytes, per * (i + 1));
+        pool->submit([=] { if (e > o) memcpy((char *)dst + o, (const char *)src + o, e - o); grp->done(); });
+    }
 }
 
 }  // namespace
@@ -907,6 +992,7 @@ void b2s_destroy(b2s_context *ctx)
 {
     if (!ctx) return;
     for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    delete ctx->pool;
     delete ctx;
 }
 
@@ -1097,12 +1183,20 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
         if (!out_pinned && !s.h_out) CU(ctx, numa_local_malloc_host(ctx, &s.h_out, out_plane * B));
     }
     struct Pending { int64_t z; int nb; bool active; } pend[b2s_plan::kSlots] = {};
+    // pageable buffers: the staging copies run on the context's worker threads.  Per slot, `in_grp` counts the chunks of
+    // the running copy caller -> h_in, `out_grp` those of h_out -> caller; both directions proceed at the same time.
+    HostPool *pool = (!in_pinned || !out_pinned) ? host_pool(ctx) : nullptr;
+    TaskGroup in_grp[b2s_plan::kSlots], out_grp[b2s_plan::kSlots];
+    struct WaitAll {   // no early return may leave worker threads writing into the caller's buffers
+        TaskGroup *a, *b; int n;
+        ~WaitAll() { for (int i = 0; i < n; ++i) { a[i].wait(); b[i].wait(); } }
+    } wait_all{in_grp, out_grp, b2s_plan::kSlots};
     auto drain = [&](int si) -> int {
         if (!pend[si].active) return B2S_OK;
         b2s_plan::Slot &s = pl->slot[si];
         CU(ctx, cudaEventSynchronize(s.done));
         if (!out_is_device && !out_pinned)
-            memcpy((char *)out + pend[si].z * out_plane, s.h_out, out_plane * pend[si].nb);
+            copy_async(pool, &out_grp[si], (char *)out + pend[si].z * out_plane, s.h_out, out_plane * pend[si].nb);
         pend[si].active = false;
         return B2S_OK;
     };
@@ -1116,22 +1210,28 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
     const int nsh = std::max(1, std::min(pl->n_slots, host_slots_env));
     int si = 0;
     int64_t z = 0;
-    static const int ramp = std::max(1, getenv("B2S_HOST_RAMP") ? atoi(getenv("B2S_HOST_RAMP")) : 4);   // first / last batch size
-    int nb_next = Bh < ramp ? Bh : ramp;
+    static const int ramp_env = std::max(1, getenv("B2S_HOST_RAMP") ? atoi(getenv("B2S_HOST_RAMP")) : 4);   // first / last batch size
+    const int ramp = std::min(ramp_env, Bh);   // never above the batch the slot buffers were sized for
+    int nb_next = ramp;
     while (z < n_planes) {
         const int64_t left = n_planes - z;
         int nb = (int)std::min<int64_t>(nb_next, left);
         if (left > ramp && nb > left / 2) nb = (int)std::max<int64_t>(ramp, left / 2);   // ramp down: halve what is left
+        nb = std::max(1, std::min(nb, Bh));   // every slot buffer holds exactly B planes (B = 3 with 5, 8, 11 ... planes left)
         nb_next = std::min(Bh, nb_next * 2);
         b2s_plan::Slot &s = pl->slot[si];
-        int rc = drain(si);
+        int rc = drain(si);   // the slot's previous batch has left the device; its copy-out (if any) is now running
         if (rc) return rc;
         const void *d_in;
         if (in_is_device) {
             d_in = (const char *)in + z * in_plane;
         } else {
             const void *src = (const char *)in + z * in_plane;
-            if (!in_pinned) { memcpy(s.h_in, src, in_plane * nb); src = s.h_in; }
+            if (!in_pinned) {
+                copy_async(pool, &in_grp[si], s.h_in, src, in_plane * nb);
+                in_grp[si].wait();
+                src = s.h_in;
+            }
             CU(ctx, cudaMemcpyAsync(s.d_in, src, in_plane * nb, cudaMemcpyHostToDevice, s.stream));
             d_in = s.d_in;
         }
@@ -1140,6 +1240,7 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
         if (rc) return rc;
         if (!out_is_device) {
             void *dst = out_pinned ? (void *)((char *)out + z * out_plane) : s.h_out;
+            if (!out_pinned) out_grp[si].wait();   // h_out is free once the previous batch has been copied out of it
             CU(ctx, cudaMemcpyAsync(dst, s.d_out, out_plane * nb, cudaMemcpyDeviceToHost, s.stream));
         }
         CU(ctx, cudaEventRecord(s.done, s.stream));
@@ -1151,7 +1252,7 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
         int rc = drain(k);
         if (rc) return rc;
     }
-    return B2S_OK;
+    return B2S_OK;   // ~WaitAll: the last copy-outs have landed in `out`
 }
 
 int b2s_host_alloc(b2s_context *ctx, size_t bytes, void **ptr)
@@ -1244,7 +1345,8 @@ int b2s_isotropic_xy(b2s_context *ctx, const void *d_in, int in_dtype, int rows,
         tmp.push_back(p);
         return p;
     };
-    auto release = [&]() { for (void *p : tmp) cudaFreeAsync(p, st); };
+    auto release = [&]() { for (void *p : tmp) cudaFreeAsync(p, st); tmp.clear(); };
+    struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};   // early CU(...) returns free the temporaries too
     unsigned *mm0 = (unsigned *)dalloc(sizeof(unsigned) * 2 * n_planes);      // uniform check on the source plane
     unsigned *mm1 = (unsigned *)dalloc(sizeof(unsigned) * 2 * n_planes);      // clip range of the image resize() sees
     float *buf[2] = {(float *)dalloc(sizeof(float) * full), (float *)dalloc(sizeof(float) * full)};
@@ -1310,6 +1412,73 @@ int b2s_isotropic_xy(b2s_context *ctx, const void *d_in, int in_dtype, int rows,
     ctx->launches += launches + 1;
     CU(ctx, cudaStreamSynchronize(st));       // the host tables above are read by the asynchronous copies
     release();
+    CU(ctx, cudaGetLastError());
+    return B2S_OK;
+}
+
+int b2s_resize_aa(b2s_context *ctx, const void *d_in, int in_dtype, int rows, int cols, int new_rows, int new_cols,
+                  const double *wy, int ry, const double *wx, int rx, float *d_out, int n_planes, void *stream)
+{
+    if (!ctx || !d_in || !d_out || rows <= 0 || cols <= 0 || new_rows <= 0 || new_cols <= 0 || n_planes <= 0 ||
+        in_dtype < B2S_U8 || in_dtype > B2S_F32 || ry < 0 || rx < 0 || (ry && !wy) || (rx && !wx))
+        return B2S_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<void *> tmp;
+    auto dalloc = [&](size_t bytes) -> void * {
+        void *p = nullptr;
+        if (cudaMallocAsync(&p, bytes ? bytes : 16, st) != cudaSuccess) return nullptr;
+        tmp.push_back(p);
+        return p;
+    };
+    auto release = [&]() { for (void *p : tmp) cudaFreeAsync(p, st); tmp.clear(); };
+    struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
+    const size_t elems = (size_t)rows * cols * n_planes;
+    const int f64 = in_dtype != B2S_F32;          // skimage filters a float64 copy of an integer image
+    const size_t esz = f64 ? 8 : 4;
+    unsigned *mm = (unsigned *)dalloc(sizeof(unsigned) * 2 * n_planes);
+    if (!mm) return fail(ctx, B2S_ERR_NOMEM, "cudaMallocAsync failed");
+    CU(ctx, cudaMemsetAsync(mm, 0xff, sizeof(unsigned) * 2 * n_planes, st));
+    b2s_launch_minmax(d_in, in_dtype, (size_t)rows * cols, n_planes, mm, st);
+    int launches = 1;
+    const void *cur = d_in;
+    int cur_dt = in_dtype;
+    const int radius[2] = {ry, rx};
+    const double *w[2] = {wy, wx};
+    for (int axis = 0; axis < 2; ++axis) {
+        if (radius[axis] <= 0) continue;
+        const int n = 2 * radius[axis] + 1;
+        double *dw = (double *)dalloc(sizeof(double) * n);
+        void *buf = dalloc(elems * esz);
+        if (!dw || !buf) return fail(ctx, B2S_ERR_NOMEM, "cudaMallocAsync failed");
+        CU(ctx, cudaMemcpyAsync(dw, w[axis], sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        b2s_launch_gauss_aa(cur, cur_dt, buf, f64, rows, cols, axis, dw, radius[axis], n_planes, st);
+        cur = buf;
+        cur_dt = f64 ? B2S_F64_INTERNAL : B2S_F32;
+        ++launches;
+    }
+    std::vector<int> idx(2 * (size_t)(new_rows + new_cols));
+    std::vector<double> wt(2 * (size_t)(new_rows + new_cols));
+    b2s_resize_axis_table(rows, new_rows, idx.data(), idx.data() + new_rows, wt.data(), wt.data() + new_rows);
+    b2s_resize_axis_table(cols, new_cols, idx.data() + 2 * new_rows, idx.data() + 2 * new_rows + new_cols,
+                          wt.data() + 2 * new_rows, wt.data() + 2 * new_rows + new_cols);
+    int *d_idx = (int *)dalloc(sizeof(int) * idx.size());
+    double *d_w = (double *)dalloc(sizeof(double) * wt.size());
+    if (!d_idx || !d_w) return fail(ctx, B2S_ERR_NOMEM, "cudaMallocAsync failed");
+    CU(ctx, cudaMemcpyAsync(d_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(d_w, wt.data(), sizeof(double) * wt.size(), cudaMemcpyHostToDevice, st));
+    B2sResizeArgs ra;
+    ra.src = cur; ra.dtype = cur_dt; ra.mm_dtype = in_dtype; ra.rows = rows; ra.cols = cols;
+    ra.new_rows = new_rows; ra.new_cols = new_cols;
+    ra.iy0 = d_idx; ra.iy1 = ra.iy0 + new_rows; ra.ix0 = ra.iy1 + new_rows; ra.ix1 = ra.ix0 + new_cols;
+    ra.wy0 = d_w; ra.wy1 = ra.wy0 + new_rows; ra.wx0 = ra.wy1 + new_rows; ra.wx1 = ra.wx0 + new_cols;
+    ra.mm = mm;
+    B2sEpilogueArgs e;
+    memset(&e, 0, sizeof e);
+    e.final_mode = 3; e.out_dtype = B2S_F32; e.out = d_out; e.out_rows = new_rows; e.out_cols = new_cols;
+    b2s_launch_resize_final(ra, e, n_planes, st);
+    ctx->launches += launches + 1;
+    CU(ctx, cudaStreamSynchronize(st));       // the host tables above are read by the asynchronous copies
     CU(ctx, cudaGetLastError());
     return B2S_OK;
 }

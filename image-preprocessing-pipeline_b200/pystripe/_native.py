@@ -4,6 +4,7 @@ B200 is visible, every entry point raises.
 import ctypes as C
 import os
 import threading
+import weakref
 from pathlib import Path
 
 import numpy as np
@@ -62,7 +63,7 @@ EXPORTS = (
     "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_plan_set_aa_weights", "b2s_run",
     "b2s_host_alloc", "b2s_host_free", "b2s_launch_count", "b2s_timing_enable", "b2s_timing_read",
     "b2s_debug_read", "b2s_debug_math",
-    "b2s_isotropic_xy", "b2s_isotropic_z", "b2s_isotropic_convert", "b2s_is_uniform",
+    "b2s_resize_aa", "b2s_isotropic_xy", "b2s_isotropic_z", "b2s_isotropic_convert", "b2s_is_uniform",
 )
 
 _lib = None
@@ -102,6 +103,7 @@ def lib():
             L.b2s_plan_set_notch.argtypes = [vp, i32, i32, i32, vp, i32]
             L.b2s_plan_set_aa_weights.argtypes = [vp, i32, vp, i32]
             L.b2s_isotropic_xy.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
+            L.b2s_resize_aa.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
             L.b2s_isotropic_z.argtypes = [vp, vp, i32, i64, i32, vp, vp]
             L.b2s_isotropic_convert.argtypes = [vp, vp, i64, i32, i32, vp, vp]
             L.b2s_is_uniform.argtypes = [vp, vp, i32, i64, vp, vp]
@@ -169,6 +171,9 @@ class Context:
         self.device = int(device)
         self._h = C.c_void_p()
         self._pinned = {}
+        self._pool_lock = threading.Lock()
+        self._pool_free = {}
+        self._pool_bytes = 0
         rc = lib().b2s_create(self.device, C.byref(self._h))
         if rc:
             msg = lib().b2s_last_error(self._h) if self._h else b"b2s_create failed"
@@ -221,6 +226,46 @@ class Context:
         if ptr is not None and self._h:
             lib().b2s_host_free(self._h, ptr)
 
+    # -- recycled page-locked result buffers: run_host() writes results straight into them (the device-to-host copy lands
+    #    in the array the caller receives: no staging copy, no first-touch page faults on a fresh pageable array).  A block
+    #    returns to the free list when the last view of the array is garbage-collected.
+    POOL_LIMIT = int(float(os.environ.get("B200STRIPE_PINNED_POOL_GB", "16")) * 2 ** 30)
+    POOL_MIN = 1 << 20
+
+    def pooled_empty(self, shape, dtype):
+        """array for a result: pinned and recycled when large enough and the pool has room, else plain numpy.empty."""
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        nbytes = count * dtype.itemsize
+        if nbytes < self.POOL_MIN or not self._h:
+            return np.empty(shape, dtype)
+        size = -(-nbytes // (1 << 21)) << 21                      # 2 MiB classes
+        with self._pool_lock:
+            free = self._pool_free.setdefault(size, [])
+            addr = free.pop() if free else None
+            if addr is None:
+                if self._pool_bytes + size > self.POOL_LIMIT:
+                    # give idle blocks of other sizes back before giving up on pinned results
+                    for sz, lst in list(self._pool_free.items()):
+                        while lst and self._pool_bytes + size > self.POOL_LIMIT:
+                            lib().b2s_host_free(self._h, C.c_void_p(lst.pop()))
+                            self._pool_bytes -= sz
+                if self._pool_bytes + size > self.POOL_LIMIT:
+                    return np.empty(shape, dtype)
+                ptr = C.c_void_p()
+                if lib().b2s_host_alloc(self._h, size, C.byref(ptr)):
+                    return np.empty(shape, dtype)
+                addr = ptr.value
+                self._pool_bytes += size
+        buf = (C.c_char * size).from_address(addr)
+        base = np.frombuffer(buf, dtype=np.uint8, count=size)
+        weakref.finalize(base, self._pool_release, size, addr)
+        return base[:nbytes].view(dtype).reshape(shape)
+
+    def _pool_release(self, size, addr):
+        with self._pool_lock:
+            self._pool_free.setdefault(size, []).append(addr)
+
     def debug_math(self, which: int, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float32)
         out = np.empty_like(x)
@@ -232,6 +277,11 @@ class Context:
             for ptr in list(self._pinned.values()):
                 lib().b2s_host_free(self._h, ptr)
             self._pinned.clear()
+            with self._pool_lock:                       # blocks still held by live result arrays are left alone
+                for lst in self._pool_free.values():
+                    for addr in lst:
+                        lib().b2s_host_free(self._h, C.c_void_p(addr))
+                self._pool_free.clear()
             lib().b2s_destroy(self._h)
             self._h = None
 
@@ -243,12 +293,14 @@ class Context:
 
 
 _contexts = {}
+_contexts_lock = threading.Lock()
 
 
 def context(device: int = 0) -> Context:
-    if device not in _contexts:
-        _contexts[device] = Context(device)
-    return _contexts[device]
+    with _contexts_lock:
+        if device not in _contexts:
+            _contexts[device] = Context(device)
+        return _contexts[device]
 
 
 class Plan:
@@ -257,6 +309,9 @@ class Plan:
     def __init__(self, ctx: Context, params: Params, dec_lo=None, flat=None):
         self.ctx = ctx
         self._keep = None
+        self.lock = threading.RLock()      # one b2s_run per plan at a time (its workspace is the plan's)
+        self._users = 0
+        self._last_stream = None
         if dec_lo is not None:
             arr = (C.c_double * len(dec_lo))(*[float(v) for v in dec_lo])
             params.n_taps = len(dec_lo)
@@ -314,17 +369,28 @@ class Plan:
         s = np.ascontiguousarray(s)
         n = s.shape[0]
         if dst is None:
-            dst = np.empty((n,) + self.out_shape, dtype=self.out_dtype)
+            dst = self.ctx.pooled_empty((n,) + self.out_shape, self.out_dtype)
         d = dst[None] if dst.ndim == 2 else dst
         if not d.flags.c_contiguous or d.shape != (n,) + self.out_shape or d.dtype != self.out_dtype:
             raise ValueError("dst must be a C-contiguous array of the plan's output shape and dtype")
-        self.ctx.check(lib().b2s_run(self._h, s.ctypes.data, d.ctypes.data, n, 0, 0, None))
+        with self.lock:
+            if not self._h:
+                raise B200StripeError("plan was closed")
+            self.ctx.check(lib().b2s_run(self._h, s.ctypes.data, d.ctypes.data, n, 0, 0, None))
         return d[0] if single else d
 
     def run_device(self, src_ptr: int, dst_ptr: int, n: int, stream: int = 0):
         """raw device pointers (zero-copy torch tensors); asynchronous on `stream`."""
-        self.ctx.check(lib().b2s_run(self._h, C.c_void_p(src_ptr), C.c_void_p(dst_ptr), n, 1, 1,
-                                     C.c_void_p(stream) if stream else None))
+        with self.lock:
+            if not self._h:
+                raise B200StripeError("plan was closed")
+            if self._last_stream is not None and self._last_stream != stream:
+                # the workspace is still in flight on another stream: order the two users
+                import torch
+                torch.cuda.synchronize(self.ctx.device)
+            self._last_stream = stream
+            self.ctx.check(lib().b2s_run(self._h, C.c_void_p(src_ptr), C.c_void_p(dst_ptr), n, 1, 1,
+                                         C.c_void_p(stream) if stream else None))
 
     def run_torch(self, src, dst=None):
         """src: CUDA torch tensor (n, H, W) / (H, W); runs on torch's current stream, no copies."""
@@ -351,9 +417,10 @@ class Plan:
         return out
 
     def close(self):
-        if self._h:
-            lib().b2s_plan_destroy(self._h)
-            self._h = None
+        with self.lock:
+            if self._h:
+                lib().b2s_plan_destroy(self._h)
+                self._h = None
 
     def __del__(self):
         try:

@@ -13,6 +13,7 @@ import os
 import re
 import sys
 import threading
+from collections import OrderedDict
 from concurrent.futures import ThreadPoolExecutor
 from math import ceil, exp, log, sqrt
 from multiprocessing import Process, Queue
@@ -25,7 +26,7 @@ import numpy as np
 from numpy import max as np_max, mean as np_mean, median as np_median, min as np_min
 from numpy import ndarray, float32, uint8, uint16, zeros
 
-from . import _native
+from . import _io, _native
 from ._util import PrintColors, date_time_now
 from ._wavelet_tables import DEC_LO
 from .lightsheet_correct import correct_lightsheet, prctl  # noqa: F401  (re-exported, process_images.py:39)
@@ -223,8 +224,9 @@ def wavelist():
 
 _PAD_ALL = ('constant', 'edge', 'linear_ramp', 'maximum', 'mean', 'median', 'minimum', 'reflect', 'symmetric',
             'wrap', 'empty')
-_plans = {}
+_plans = OrderedDict()            # LRU: most recently used last
 _plans_lock = threading.Lock()
+_MAX_CACHED_PLANS = 16
 
 
 _tls = threading.local()
@@ -260,7 +262,11 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
               log1p, flat=None, gaussian=False, down_sample=None, down_sample_method='max', dark=0, lightsheet=False,
               artifact_length=150, background_window_size=200, percentile=0.25, lightsheet_vs_background=2.0,
               convert_to_16bit=False, convert_to_8bit=False, bit_shift_to_right=8, rotate=0, flip=False,
-              out_code=None, max_batch=None, stop_after=0, exact=None, new_size=None, bleach=None, pad_constant=0.0, aa=(None, None)):
+              out_code=None, max_batch=None, stop_after=0, exact=None, new_size=None, bleach=None, pad_constant=0.0, aa=(None, None),
+              _acquire=False):
+    """Cached plan for one (device, shape, dtype, parameter set).  `_acquire=True` marks the plan in use until
+    `_release_plan` (eviction and the out-of-memory retry only close idle plans); a plan serialises its own runs
+    with `plan.lock`, so two threads that ask for the same parameters share tables and workspace safely."""
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
     s1, s2 = float(sigma[0]), float(sigma[1])
@@ -297,6 +303,9 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
     with _plans_lock:
         plan = _plans.get(key)
         if plan is not None:
+            _plans.move_to_end(key)
+            if _acquire:
+                plan._users += 1
             return plan
         p = _native.default_params()
         p.height, p.width = int(shape[0]), int(shape[1])
@@ -340,21 +349,38 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
         try:
             plan = _native.Plan(_native.context(device), p, dec_lo=taps, flat=flat)
         except MemoryError:
-            # cached plans own workspace (gigabytes each for whole stitched slices): give it back and try once more
-            for old in _plans.values():
-                old.close()
-            _plans.clear()
+            # cached plans own workspace (gigabytes each for whole stitched slices): give back what is idle, try once more
+            _evict_idle(keep=0)
             plan = _native.Plan(_native.context(device), p, dec_lo=taps, flat=flat)
         plan._flat_ref = flat  # keep id(flat) stable while the plan is cached
+        plan._users = 1 if _acquire else 0
         _upload_numpy_notch_tables(plan, s1, s2)
         for ax in range(2):
             if aa[ax] is not None:
                 plan.set_aa_weights(ax, aa[ax][1])
-        if len(_plans) > 16:   # plans own GPU workspace: keep the cache small
-            _, old = _plans.popitem()
-            old.close()
         _plans[key] = plan
+        _evict_idle(keep=_MAX_CACHED_PLANS, protect=plan)   # plans own GPU workspace: keep the cache small
         return plan
+
+
+def _evict_idle(keep, protect=None):
+    """close least-recently-used plans nobody is running until at most `keep` remain (caller holds _plans_lock)."""
+    for k in list(_plans.keys()):
+        if len(_plans) <= keep:
+            break
+        old = _plans[k]
+        if old is protect or getattr(old, "_users", 0) > 0 or not old.lock.acquire(blocking=False):
+            continue                                  # another thread is inside b2s_run with it
+        try:
+            del _plans[k]
+            old.close()
+        finally:
+            old.lock.release()
+
+
+def _release_plan(plan):
+    with _plans_lock:
+        plan._users = max(0, getattr(plan, "_users", 0) - 1)
 
 
 def _upload_numpy_notch_tables(plan, s1, s2):
@@ -374,10 +400,9 @@ def _upload_numpy_notch_tables(plan, s1, s2):
 
 
 def clear_plan_cache():
+    """close every idle cached plan (plans another thread is running stay until it is done)."""
     with _plans_lock:
-        for pl in _plans.values():
-            pl.close()
-        _plans.clear()
+        _evict_idle(keep=0)
 
 
 def _run(plan, img):
@@ -396,6 +421,8 @@ def _as_supported(img):
             return img.float(), torch.float64
         raise TypeError(f"unsupported tensor dtype {img.dtype}")
     img = np.asarray(img)
+    if not img.dtype.isnative:                     # big-endian .raw tiles (raw.py:33-38): same values, native order
+        img = img.astype(img.dtype.newbyteorder('='))
     if img.dtype in (np.uint8, np.uint16, np.float32):
         return img, None
     if img.dtype == np.float64:
@@ -488,8 +515,11 @@ def filter_streaks(
     arr, restore = _as_supported(img)
     plan = _get_plan(_device_of(arr), arr.shape[-2:], _code_of(arr), process=0, sigma=sigma, level=level,
                      wavelet=wavelet, threshold=threshold, padding_mode=padding_mode, bidirectional=bidirectional,
-                     log1p=log1p_normalization_needed, bleach=bleach, pad_constant=pad_constant)
-    out = _run(plan, arr)
+                     log1p=log1p_normalization_needed, bleach=bleach, pad_constant=pad_constant, _acquire=True)
+    try:
+        out = _run(plan, arr)
+    finally:
+        _release_plan(plan)
     if verbose:
         print(f"de-striping applied: sigma={sigma}, level={level}, wavelet={wavelet}, crossover={crossover}, "
               f"threshold={threshold}, bidirectional={bidirectional}.")
@@ -616,8 +646,12 @@ def process_img(
                      percentile=percentile, lightsheet_vs_background=lightsheet_vs_background,
                      convert_to_16bit=convert_to_16bit, convert_to_8bit=convert_to_8bit,
                      bit_shift_to_right=bit_shift_to_right, rotate=rotate, flip=flip_upside_down, out_code=out_code,
-                     max_batch=_max_batch, new_size=resize_to, bleach=bleach, pad_constant=pad_constant, aa=aa)
-    out = _run(plan, arr)
+                     max_batch=_max_batch, new_size=resize_to, bleach=bleach, pad_constant=pad_constant, aa=aa,
+                     _acquire=True)
+    try:
+        out = _run(plan, arr)
+    finally:
+        _release_plan(plan)
     if out_code == _native.F32 and plan.info.out_dtype == _native.F32 and d_type != np.float32:
         out = out.astype(d_type) if not _native._is_torch(out) else out.double()
     return out
@@ -657,12 +691,19 @@ def imread_tif_raw_png(path: Path, dtype: str = None, shape: Tuple[int, int] = N
 
 
 def _decode_image(path: Path):
-    try:
-        import tifffile
-        if path.suffix.lower() in ('.tif', '.tiff'):
+    if path.suffix.lower() in ('.tif', '.tiff'):
+        try:                                        # native codec (libb2sio): strips / tiles decoded on several threads
+            return _io.read(path)
+        except _io.CodecError as e:
+            if e.code == _io.ERR_IO:
+                raise OSError(str(e))
+        except OSError:
+            pass                                    # library not built: fall through to the Python decoders
+        try:
+            import tifffile
             return tifffile.imread(path)
-    except ImportError:
-        pass
+        except ImportError:
+            pass
     from PIL import Image
     Image.MAX_IMAGE_PIXELS = None
     with Image.open(path) as im:
@@ -698,6 +739,13 @@ _PIL_COMPRESSION = {'ADOBE_DEFLATE': 'tiff_adobe_deflate', 'DEFLATE': 'tiff_defl
 
 
 def _encode_tif(path: Path, img: ndarray, compression):
+    if _io.can_write(img, compression):
+        try:
+            _io.write_tiff(path, img, compression)
+            return
+        except _io.CodecError as e:
+            if e.code == _io.ERR_IO:
+                raise OSError(str(e))
     try:
         import tifffile
         tifffile.imwrite(path, data=img, compression=compression)
@@ -741,6 +789,34 @@ def glob_re(pattern: str, path: Path) -> Iterator[Path]:
             yield Path(p.path)
         elif p.is_dir(follow_symlinks=False):
             yield from glob_re(pattern, Path(p.path))
+
+
+def resize_to_tile(img: ndarray, tile_size: Tuple[int, int]) -> ndarray:
+    """`resize(img, tile_size, preserve_range=True, anti_aliasing=True)` of read_filter_save (core.py:1540-1549) on the GPU
+    (b2s_resize_aa): Gaussian per shrinking axis, order-1 zoom, clip to the image's own range.  Returns float32 — the
+    reference holds float64 here and filter_streaks casts it to float32 on entry."""
+    import ctypes as C
+    import torch
+    from .isotropic import anti_aliasing_kernels
+    arr, _ = _as_supported(img)
+    tile_size = (int(tile_size[0]), int(tile_size[1]))
+    for n_in, n_out in zip(arr.shape, tile_size):   # the shape scipy.ndimage.zoom derives from skimage's factors
+        if int(round(n_in * (1 / np.divide(n_in, n_out)))) != n_out:
+            raise NotImplementedError(f"tile_size {tile_size}: skimage's zoom factor rounds to another output shape")
+    aa = anti_aliasing_kernels(arr.shape, tile_size)
+    dev = _device_of(arr)
+    with torch.cuda.device(dev):
+        t = torch.from_numpy(np.ascontiguousarray(arr)).cuda(dev)
+        out = torch.empty(tile_size, dtype=torch.float32, device=t.device)
+        ctx = _native.context(dev)
+        wy = aa[0][1] if aa[0] else None
+        wx = aa[1][1] if aa[1] else None
+        ctx.check(_native.lib().b2s_resize_aa(
+            ctx._h, C.c_void_p(t.data_ptr()), _code_of(arr), arr.shape[0], arr.shape[1], tile_size[0], tile_size[1],
+            C.c_void_p(wy.ctypes.data if wy is not None else None), aa[0][0] if aa[0] else 0,
+            C.c_void_p(wx.ctypes.data if wx is not None else None), aa[1][0] if aa[1] else 0,
+            C.c_void_p(out.data_ptr()), 1, C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
+        return out.cpu().numpy()
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -804,10 +880,13 @@ def read_filter_save(
         img = _read_one(input_file, z_idx, d_type, tile_size, output_file)
         if img is None:
             return
-        if tile_size is not None and img.shape != tuple(tile_size):
-            raise NotImplementedError("resizing an input tile to tile_size needs skimage.transform.resize (next row N3)")
         if d_type is None:
             d_type = img.dtype
+        if tile_size is not None and img.shape != tuple(tile_size):              # core.py:1540-1549
+            print(f"{PrintColors.WARNING}\nwarning: input tile had a different shape. resizing:\n"
+                  f"\tinput_file: {input_file} -> \n\t\tinput shape = {img.shape}\n\t\tnew shape   = {tile_size}\n"
+                  f"{PrintColors.ENDC}")
+            img = resize_to_tile(img, tile_size)
         output_file.parent.mkdir(parents=True, exist_ok=True)
         kw = {k: v for k, v in locals().items() if k in _PROCESS_KEYS}
         img = process_img(np.ascontiguousarray(img), tile_size=img.shape, d_type=d_type, **kw)
@@ -856,23 +935,63 @@ class MultiProcessQueueRunner(Process):
         self.replace_timeout_with_dummy = replace_timeout_with_dummy
 
     def run(self):
+        """core.py:1704-1771: per-item timeout that adapts upwards (max(t, 0.9 t + 0.3 elapsed)); an item that times out
+        gets a zeros tile of `new_size or tile_size` as its output unless one exists already."""
+        from concurrent.futures import ProcessPoolExecutor, ThreadPoolExecutor as _TPE, TimeoutError as _Timeout
+        from concurrent.futures.process import BrokenProcessPool
         if self.gpu is not None:
             os.environ["B200STRIPE_DEVICE"] = str(self.gpu)
         running_next = True
+        timeout = self.timeout
+        pool = ProcessPoolExecutor(max_workers=1) if timeout else _TPE(max_workers=1)
         while not self.die:
             try:
                 args: dict = self.args_queue.get(block=True, timeout=0.5)
             except Empty:
                 break
+            if self.gpu_semaphore is not None:
+                args.update({"gpu_semaphore": self.gpu_semaphore})
             try:
-                self.function(**args)
+                start_time = time()
+                pool.submit(self.function, **args).result(timeout=timeout)
+                if timeout is not None:
+                    timeout = max(timeout, 0.9 * timeout + 0.3 * (time() - start_time))
+            except (BrokenProcessPool, _Timeout, ValueError) as inst:
+                if self.replace_timeout_with_dummy and "output_file" in args:
+                    if _save_dummy_tile(args["output_file"], args.get("new_size"), args.get("tile_size"),
+                                        args.get("convert_to_8bit"), args.get("input_file"), inst):
+                        self.die = True
+                else:
+                    print(f"{PrintColors.WARNING}\nwarning: timeout reached for processing input file:\n\t"
+                          f"{args.get('input_file')}\n\t\nexception instance: {type(inst)}{PrintColors.ENDC}")
+                if isinstance(pool, ProcessPoolExecutor):
+                    pool.shutdown(wait=False, cancel_futures=True)
+                    pool = ProcessPoolExecutor(max_workers=1)
             except KeyboardInterrupt:
                 self.die = True
             except Exception as inst:
                 print(f"{PrintColors.WARNING}\nwarning: process unexpectedly failed for {args}."
                       f"\nexception instance: {type(inst)}\nexception: {inst}{PrintColors.ENDC}")
             self.progress_queue.put(running_next)
+        pool.shutdown(wait=False)
         self.progress_queue.put(not running_next)
+
+
+def _save_dummy_tile(output_file, new_size, tile_size, convert_to_8bit, input_file, reason) -> bool:
+    """core.py:1736-1750: zeros of `new_size or tile_size`, uint8 when convert_to_8bit else uint16, unless the output
+    exists.  Returns imsave_tif's "user interrupted" flag."""
+    output_file = Path(output_file)
+    shape = new_size if new_size else tile_size
+    print(f"{PrintColors.WARNING}\nwarning: timeout reached for processing input file:\n\t{input_file}\n\t"
+          f"a dummy (zeros) image is saved as output instead:\n\t{output_file}\nexception instance: {type(reason)}"
+          f"{PrintColors.ENDC}")
+    if shape is None:
+        print(f"{PrintColors.WARNING}\tno tile_size / new_size given: the dummy tile cannot be written{PrintColors.ENDC}")
+        return False
+    if output_file.exists():
+        return False
+    output_file.parent.mkdir(parents=True, exist_ok=True)
+    return imsave_tif(output_file, zeros(shape=tuple(int(v) for v in shape), dtype=uint8 if convert_to_8bit else uint16))
 
 
 def progress_manager(progress_queue: Queue, workers: int, total: int, desc="PyStripe", unit=" images"):
@@ -987,7 +1106,10 @@ def batch_filter(
 
     Scheduling is re-designed for one box of B200s: `workers` host threads decode files into batches, one feeder
     thread per visible GPU runs a batched plan (Z planes are independent: no collective), encoder threads write the
-    results.  `threads_per_gpu` is the number of planes per GPU batch; `timeout` is accepted and ignored.
+    results.  `threads_per_gpu` is the number of planes per GPU batch.  `timeout` bounds the decode of one file (it
+    adapts upwards like the reference's, core.py:1722-1724); a file that times out gets a zeros tile of `new_size or
+    tile_size` as its output (core.py:1736-1750).  Return code: 0 = done, 1 = interrupted, 2 = done but some images
+    could not be processed (they are listed).
     """
     from tqdm import tqdm
     input_path = Path(input_path)
@@ -1055,85 +1177,284 @@ def batch_filter(
         return 0
 
     gpus = [local_rank] if world > 1 and not os.environ.get("B200STRIPE_DEVICES") else _visible_gpus()
+    gpus = gpus[:max(1, num_images)]
     batch = max(1, int(threads_per_gpu))
+    io_threads = max(1, workers // (2 * len(gpus)))      # decode and encode threads of one GPU's pipeline
     print(f"{PrintColors.GREEN}{date_time_now()}: {PrintColors.ENDC}"
           f"using {workers} decode/encode threads and {len(gpus)} GPU(s). {num_images} images need to be processed.",
           flush=True)
     progress = tqdm(total=num_images, ascii=True, smoothing=0.01, mininterval=1.0, unit=" images", desc="PyStripe")
-    stop = threading.Event()
-    lock = threading.Lock()
-    cursor = [0]
-
-    def decode(job):
-        f, out, z = job
-        try:
-            if print_input_file_names:
-                print(f"\n{f}")
-            img = _read_one(f, z, d_type, tile_size, out)
-            if img is not None and tile_size is not None and img.shape != tuple(tile_size):
-                raise NotImplementedError("resizing an input tile to tile_size is a next-row feature (N3)")
-            return img
-        except (OSError, IndexError, TypeError, RuntimeError, ValueError) as inst:
-            print(f"{PrintColors.WARNING}warning: read failed for {f}: {type(inst)} {inst}{PrintColors.ENDC}")
-            return None
-
-    def encode(out, img):
-        try:
-            out.parent.mkdir(parents=True, exist_ok=True)
-            if imsave_tif(out, img, compression=compression):
-                stop.set()
-        except Exception as inst:  # never propagate per-file failures (core.py:1594-1600)
-            print(f"{PrintColors.WARNING}warning: write failed for {out}: {type(inst)} {inst}{PrintColors.ENDC}")
-
-    def feeder(device, pool):
-        pending = []
-        while not stop.is_set():
-            with lock:                                   # shared plane counter: dynamic Z partition across GPUs
-                lo = cursor[0]
-                hi = min(lo + batch, num_images)
-                cursor[0] = hi
-            if lo >= hi:
-                break
-            group = jobs[lo:hi]
-            imgs = list(pool.map(decode, group))
-            buckets = {}
-            for job, img in zip(group, imgs):
-                if img is None:
-                    progress.update(1)
-                    continue
-                buckets.setdefault((img.shape, img.dtype.str), []).append((job, img))
-            for (shape, _), items in buckets.items():
-                stack = np.stack([np.ascontiguousarray(i) for _, i in items])
-                try:
-                    with use_device(device):
-                        res = process_img(stack, tile_size=shape, d_type=d_type if d_type is not None else stack.dtype,
-                                          _max_batch=batch, **kw)
-                except (TypeError, RuntimeError, ValueError, NotImplementedError) as inst:
-                    print(f"{PrintColors.WARNING}warning: processing failed for {items[0][0][0]} (+{len(items) - 1}): "
-                          f"{type(inst)} {inst}{PrintColors.ENDC}")
-                    progress.update(len(items))
-                    continue
-                for (job, _), plane in zip(items, res):
-                    pending.append(pool.submit(encode, job[1], plane))
-                    progress.update(1)
-            pending = [p for p in pending if not p.done()]
-        for p in pending:
-            p.result()
-
+    # argument errors the reference raises per file are the same for every file: find them before any thread starts
+    _bleach_plan_args(bleach_correction_frequency, bleach_correction_clip_min, bleach_correction_clip_med,
+                      bleach_correction_clip_max, bleach_correction_max_method, False)
+    shared = _BatchShared(jobs=jobs, batch=batch, progress=progress, kw=kw, d_type=d_type, tile_size=tile_size,
+                          compression=compression, timeout=timeout, io_threads=io_threads,
+                          print_input_file_names=print_input_file_names)
     return_code = 0
+    pipelines = [_BatchPipeline(g, shared) for g in gpus]
     try:
-        with ThreadPoolExecutor(max_workers=max(2, workers)) as pool:
-            threads = [threading.Thread(target=feeder, args=(g, pool), daemon=True) for g in gpus[:max(1, num_images)]]
-            for t in threads:
-                t.start()
-            for t in threads:
-                while t.is_alive():
-                    t.join(timeout=0.5)
+        for pl in pipelines:
+            pl.start()
+        for pl in pipelines:
+            pl.join()
     except KeyboardInterrupt:
         print(f"\n{PrintColors.WARNING}Terminating processes with dignity!{PrintColors.ENDC}")
-        stop.set()
+        shared.stop.set()
+        for pl in pipelines:
+            pl.join(timeout=5.0)
         return_code = 1
     progress.close()
-    if stop.is_set():
+    if shared.stop.is_set():
         return_code = 1
+    if shared.failed:
+        print(f"{PrintColors.FAIL}batch_filter: {len(shared.failed)} of {num_images} images were NOT processed:{PrintColors.ENDC}")
+        for f, why in shared.failed[:20]:
+            print(f"\t{f}: {why}")
+        return_code = return_code or 2
     return return_code
+
+
+def _batch_buffer(device, shape, dtype):
+    """page-locked, recycled buffer a batch of tiles is decoded into (the plan reads it over PCIe without staging)."""
+    return _native.context(device).pooled_empty(shape, dtype)
+
+
+class _BatchShared:
+    """state shared by the per-GPU pipelines of one batch_filter call: the job cursor (dynamic Z partition), the progress
+    bar, the failure list and the adaptive per-file timeout (core.py:1722-1724)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+        self.stop = threading.Event()
+        self.lock = threading.Lock()
+        self.cursor = 0
+        self.failed = []
+
+    def claim(self):
+        with self.lock:
+            lo = self.cursor
+            hi = min(lo + self.batch, len(self.jobs))
+            self.cursor = hi
+        return self.jobs[lo:hi]
+
+    def fail(self, job, why):
+        with self.lock:
+            self.failed.append((job[0], why))
+        print(f"{PrintColors.WARNING}warning: processing failed for {job[0]}: {why}{PrintColors.ENDC}")
+
+    def done(self, n=1):
+        with self.lock:
+            self.progress.update(n)
+
+    def timed(self, elapsed):
+        if self.timeout is not None:
+            with self.lock:
+                self.timeout = max(self.timeout, 0.9 * self.timeout + 0.3 * elapsed)
+
+
+class _BatchPipeline:
+    """One GPU's share of batch_filter: reader -> GPU -> writer, three threads joined by bounded queues, so the decode of
+    batch k+1 and the encode of batch k-1 overlap the GPU work of batch k.  A batch is decoded by the native codec
+    (pystripe/_io.py, `io_threads` workers) straight into ONE page-locked buffer, which the plan reads over PCIe without a
+    staging copy; the result comes back in a page-locked buffer the encoder reads.  Both buffers are recycled through the
+    context's pinned pool.  Files the batch path cannot take (another shape or dtype, a format the codec does not cover,
+    DCIMG) go one by one through read_filter_save's logic on the same device."""
+
+    def __init__(self, device, shared):
+        from queue import Queue as _Q
+        self.device, self.sh = device, shared
+        self.q_ready, self.q_write = _Q(maxsize=2), _Q(maxsize=2)
+        self.threads = [threading.Thread(target=self._guard, args=(f,), daemon=True)
+                        for f in (self._reader, self._compute, self._writer)]
+        self.pool = ThreadPoolExecutor(max_workers=max(2, shared.io_threads))
+
+    def start(self):
+        for t in self.threads:
+            t.start()
+
+    def join(self, timeout=None):
+        for t in self.threads:
+            while t.is_alive():
+                t.join(timeout=0.5 if timeout is None else timeout)
+                if timeout is not None:
+                    break
+        self.pool.shutdown(wait=False)
+
+    def _guard(self, stage):
+        try:
+            stage()
+        except BaseException as inst:       # a dying stage must not leave the others blocked on a queue
+            self.sh.stop.set()
+            print(f"{PrintColors.FAIL}batch_filter: {stage.__name__} on GPU {self.device} died: {type(inst)} {inst}{PrintColors.ENDC}")
+            with self.sh.lock:
+                self.sh.failed.append((f"<{stage.__name__} of GPU {self.device}>", repr(inst)))
+            for q in (self.q_ready, self.q_write):
+                try:
+                    q.put_nowait(None)
+                except Exception:
+                    pass
+
+    # ---- stage 1: decode
+    def _expected(self, group):
+        """(shape, dtype) the batch buffer of this group has: the caller's tile_size / d_type, else the first file's."""
+        sh = self.sh
+        if sh.tile_size is not None and sh.d_type is not None and np.dtype(sh.d_type).kind in "uf":
+            return tuple(int(v) for v in sh.tile_size), np.dtype(sh.d_type)
+        for f, _, z in group:
+            if z is None and f.suffix.lower() in ('.tif', '.tiff', '.raw'):
+                try:
+                    shape, dtype, _ = _io.probe(f)
+                    return shape, dtype
+                except OSError:
+                    continue
+        return None, None
+
+    def _reader(self):
+        sh = self.sh
+        while not sh.stop.is_set():
+            group = sh.claim()
+            if not group:
+                break
+            shape, dtype = self._expected(group)
+            fast, slow = [], []
+            for job in group:
+                f, _, z = job
+                ok = shape is not None and z is None and f.suffix.lower() in ('.tif', '.tiff', '.raw') and \
+                    np.dtype(dtype) in (np.uint8, np.uint16, np.float32)
+                (fast if ok else slow).append(job)
+            if fast:
+                buf = _batch_buffer(self.device, (len(fast),) + tuple(shape), dtype)
+                if sh.print_input_file_names:
+                    for f, _, _ in fast:
+                        print(f"\n{f}")
+                valid = self._decode_fast(fast, buf, slow)
+                if any(valid):
+                    self.q_ready.put((fast, buf, valid))
+                else:
+                    del buf
+            for job in slow:                                            # odd files: the reference's per-file logic
+                self.q_ready.put((job,))
+        self.q_ready.put(None)
+
+    def _decode_fast(self, jobs, buf, slow):
+        """decode jobs[i] into buf[i]; returns the per-plane valid flags.  Files of another shape move to `slow`."""
+        sh = self.sh
+        n = len(jobs)
+        valid = [False] * n
+        if sh.timeout is None:
+            status = _io.read_batch([j[0] for j in jobs], buf, threads=sh.io_threads)
+        else:                                                            # per-file timeout (core.py:1719-1724)
+            from concurrent.futures import TimeoutError as _Timeout
+
+            def one(i):
+                try:
+                    _io.read(jobs[i][0], out=buf[i], threads=1)
+                    return _io.OK
+                except _io.CodecError as e:
+                    return e.code
+            t0 = time()
+            futs = [self.pool.submit(one, i) for i in range(n)]
+            status = []
+            for i, fu in enumerate(futs):
+                try:
+                    status.append(fu.result(timeout=max(0.0, sh.timeout - (time() - t0)) if i else sh.timeout))
+                except _Timeout as inst:
+                    status.append(None)
+                    if _save_dummy_tile(jobs[i][1], sh.kw.get("new_size"), sh.tile_size, sh.kw.get("convert_to_8bit"),
+                                        jobs[i][0], inst):
+                        sh.stop.set()
+                    sh.done()
+            sh.timed((time() - t0) / max(1, n))
+        for i, st in enumerate(status):
+            if st == _io.OK:
+                valid[i] = True
+            elif st is None:
+                pass                                                     # timed out: dummy tile written
+            elif st == _io.ERR_SHAPE:
+                slow.append(jobs[i])                                     # another shape / dtype: per-file path
+            else:                                                        # codec does not cover it: Python decoders + retries
+                img = _read_one(jobs[i][0], None, sh.d_type, sh.tile_size, jobs[i][1])
+                if img is None:
+                    sh.done()
+                elif img.shape == buf.shape[1:] and img.dtype == buf.dtype:
+                    buf[i] = img
+                    valid[i] = True
+                else:
+                    slow.append(jobs[i])
+        return valid
+
+    # ---- stage 2: the GPU
+    def _compute(self):
+        sh = self.sh
+        while True:
+            item = self.q_ready.get()
+            if item is None or sh.stop.is_set():
+                break
+            if len(item) == 1:
+                self._slow_file(item[0])
+                continue
+            jobs, buf, valid = item
+            try:
+                with use_device(self.device):
+                    res = process_img(buf, tile_size=buf.shape[1:], d_type=sh.d_type if sh.d_type is not None else buf.dtype,
+                                      _max_batch=sh.batch, **sh.kw)
+            except Exception as inst:                                    # every per-batch failure is reported, none is fatal
+                for job, ok in zip(jobs, valid):
+                    if ok:
+                        sh.fail(job, f"{type(inst).__name__}: {inst}")
+                        sh.done()
+                continue
+            del buf
+            self.q_write.put((jobs, res, valid))
+        self.q_write.put(None)
+
+    def _slow_file(self, job):
+        sh = self.sh
+        f, out, z = job
+        try:
+            with use_device(self.device):
+                kw = dict(sh.kw)
+                read_filter_save(input_file=f, output_file=out, z_idx=z, d_type=sh.d_type, tile_size=sh.tile_size,
+                                 print_input_file_names=sh.print_input_file_names, compression=sh.compression, **kw)
+            if not out.exists():
+                sh.fail(job, "no output was written (see the warning above)")
+        except Exception as inst:
+            sh.fail(job, f"{type(inst).__name__}: {inst}")
+        sh.done()
+
+    # ---- stage 3: encode
+    def _writer(self):
+        sh = self.sh
+        while True:
+            item = self.q_write.get()
+            if item is None:
+                break
+            jobs, res, valid = item
+            res = np.asarray(res)
+            try:
+                for d in {j[1].parent for j in jobs}:
+                    d.mkdir(parents=True, exist_ok=True)
+                todo = [i for i, ok in enumerate(valid) if ok]
+                if todo and res.ndim == 3 and _io.can_write(res[0], sh.compression) and res.flags.c_contiguous:
+                    if len(todo) == len(jobs):
+                        status = _io.write_tiff_batch([j[1] for j in jobs], res, sh.compression, threads=sh.io_threads)
+                    else:
+                        futs = [self.pool.submit(_io.write_tiff_batch, [jobs[i][1]], res[i:i + 1], sh.compression, 1) for i in todo]
+                        status = [fu.result()[0] for fu in futs]
+                    for i, st in zip(todo, status):
+                        if st:                                           # retries etc.: the reference's own writer
+                            if imsave_tif(jobs[i][1], res[i], compression=sh.compression):
+                                sh.stop.set()
+                else:
+                    futs = [self.pool.submit(imsave_tif, jobs[i][1], res[i], sh.compression) for i in todo]
+                    if any(fu.result() for fu in futs):
+                        sh.stop.set()
+                for i in todo:
+                    if not jobs[i][1].exists():
+                        sh.fail(jobs[i], "the output file could not be written")
+            except Exception as inst:
+                for job, ok in zip(jobs, valid):
+                    if ok:
+                        sh.fail(job, f"write failed: {type(inst).__name__}: {inst}")
+            sh.done(sum(1 for ok in valid if ok))
+            del res

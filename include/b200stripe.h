@@ -204,6 +204,14 @@ int b2s_debug_read(b2s_plan *plan, int what, int level, int plane, float *out, i
 int b2s_isotropic_xy(b2s_context *ctx, const void *d_in, int in_dtype, int rows, int cols, int n_steps, const int32_t *steps,
                      int target_rows, int target_cols, int pre_rows, int pre_cols, const double *wy, int ry,
                      const double *wx, int rx, float *d_out, int n_planes, void *stream);
+/* replaces: `resize(img, tile_size, preserve_range=True, anti_aliasing=True)` that read_filter_save applies to an input tile
+ * whose shape differs from tile_size (pystripe/core.py:1540-1549): skimage.transform.resize = scipy.ndimage.gaussian_filter
+ * (sigma = max(0, (in / out - 1) / 2) per axis, mode 'mirror', float64 for an integer image, float32 for a float32 one)
+ * followed by the order-1 zoom and a clip to the image's own range.  wy / wx as for b2s_isotropic_xy.  d_in: n_planes device
+ * planes of in_dtype; d_out: n_planes float32 device planes (the reference's float64 result, which filter_streaks casts to
+ * float32 on entry). */
+int b2s_resize_aa(b2s_context *ctx, const void *d_in, int in_dtype, int rows, int cols, int new_rows, int new_cols,
+                  const double *wy, int ry, const double *wx, int rx, float *d_out, int n_planes, void *stream);
 /* replaces: the z loop `block_reduce(z_stack, (2, 1, 1), z_method)` (parallel_image_processor.py:417-419) one level at
  * a time: d_out[k] = method(d_in[2k], d_in[2k+1]) over float32 planes of plane_elems elements; an odd last plane is paired
  * with zeros (cval = 0).  n_out = ceil(n_in / 2) planes are written. */
