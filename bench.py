@@ -1,25 +1,36 @@
 #!/usr/bin/env python3
 """bench.py — destripe throughput (Mpixel/s at 2048^2 uint16) on N B200s of one node, plus roofline and CPU baseline.
 
-    python bench.py --gpus 1 --steps 8 --warmup 3
+    python bench.py --gpus 1 --steps 8 --warmup 3                      # BASELINE.json configs[1] (the headline)
+    python bench.py --config 3                                         # configs[2]: + Gaussian, 2x2 max, 8-bit output
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
-    python bench.py --impl reference --steps 2 --warmup 1        # the reference's CPU path (oracle port) on the host cores
+    python bench.py --impl reference --steps 2 --warmup 1              # the reference's CPU path (oracle port) on the host cores
 
-Workload (BASELINE.json configs[1]): process_img / batch_filter semantics over a synthetic 2048x2048 uint16 tile stack,
-sigma=(256,256), wavelet db10, level auto, padding 'reflect', dark=100, flat-field; one "step" = one pass over
-`--planes` planes (default 250, so the default 8 steps cover the 2000-plane stack).  Z planes are independent: with
-N GPUs every rank runs its own `--planes` planes per step (weak scaling, no collective on the data path).
+`--config K` selects BASELINE.json configs[K-1] (default 2 = the configuration the metric is quoted on):
+    1  filter_streaks, sigma=(256,256), db10, level auto, wrap padding
+    2  process_img / batch_filter: reflect padding, dark=100, flat-field
+    3  config 2 + 5x5 Gaussian + 2x2 max down-sample + 16->8-bit right shift (uint8 output, 1/8 of the D2H bytes)
+    4  lightsheet_correct background clean + destripe
+    5  coif15, sigma=(128,512) (two passes, 90-tap filters)
+One "step" = one pass over `--planes` planes per GPU.  Z planes are independent: with N GPUs every rank runs its own
+planes (weak scaling, no collective on the data path).
 
-One JSON line on stdout (rank 0).  `value`: device-resident throughput (CUDA events, max over ranks).  `e2e`: the same
-call with pinned HOST buffers through the C ABI (H2D + kernels + D2H inside the timed region).  `roofline`: the dominant
-kernel (largest share of the step), algorithmic bytes / CUDA-event duration measured live, against MEASURED_PEAKS.json.
-`cpu_baseline`: the oracle port on the host cores (bounded sample).
+One JSON line on stdout (rank 0).  Every GPU leg goes through the PUBLIC pystripe API (`core.process_img` /
+`core.filter_streaks` / `core.batch_filter`):
+  value             CUDA torch tensors in, CUDA tensors out (device-resident; CUDA events, max over ranks)
+  e2e               numpy arrays over page-locked host memory (`core.pinned_empty`) in, host arrays out: H2D + kernels + D2H
+  e2e_public_api    ordinary (pageable) numpy stack in, host arrays out
+  e2e_batch_filter  `batch_filter` over uncompressed TIFF files on tmpfs -> TIFF files on tmpfs (decode, H2D, kernels, D2H, encode)
+`roofline`: the dominant kernel (largest share of the step), algorithmic bytes / CUDA-event duration measured live,
+against MEASURED_PEAKS.json.  `cpu_baseline`: the oracle port on the host cores (bounded sample, inputs pre-generated).
 """
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 from pathlib import Path
@@ -30,10 +41,24 @@ sys.path[:0] = [str(ROOT), str(ROOT / "image-preprocessing-pipeline_b200")]
 import numpy as np  # noqa: E402
 
 H = W = 2048
-WORK = dict(sigma=(256, 256), wavelet="db10", level=0, padding_mode="reflect", dark=100)
-WORKLOAD = "configs[1]: batch_filter/process_img, 2048x2048 uint16 stack, sigma=(256,256), db10, level auto, reflect pad, dark=100, flat-field"
 METRIC = "destripe_mpixel_per_s_2048x2048_uint16"
 UNIT = "Mpixel/s"
+_BASE = dict(sigma=(256, 256), wavelet="db10", level=0)
+CONFIGS = {
+    1: dict(fn="filter_streaks", flat=False, kw=dict(_BASE, padding_mode="wrap"),
+            workload="configs[0]: filter_streaks, 2048x2048 uint16 planes, sigma=(256,256), db10, level auto, wrap pad"),
+    2: dict(fn="process_img", flat=True, kw=dict(_BASE, padding_mode="reflect", dark=100),
+            workload="configs[1]: batch_filter/process_img, 2048x2048 uint16 stack, sigma=(256,256), db10, level auto, reflect pad, dark=100, flat-field"),
+    3: dict(fn="process_img", flat=True,
+            kw=dict(_BASE, padding_mode="reflect", dark=100, gaussian_filter_2d=True, down_sample=(2, 2),
+                    convert_to_8bit=True, bit_shift_to_right=8),
+            workload="configs[2]: configs[1] + 5x5 Gaussian + 2x2 max down-sample + 16->8-bit right shift (uint8 out)"),
+    4: dict(fn="process_img", flat=False, kw=dict(_BASE, padding_mode="wrap", lightsheet=True),
+            workload="configs[3]: lightsheet_correct background clean + destripe (sigma=(256,256), db10, wrap pad), 2048x2048 uint16"),
+    5: dict(fn="process_img", flat=False, kw=dict(sigma=(128, 512), wavelet="coif15", level=0, padding_mode="reflect"),
+            workload="configs[4]: coif15, sigma=(128,512) (two passes), reflect pad, 2048x2048 uint16"),
+}
+N_DISTINCT = 8
 
 
 def parse():
@@ -41,69 +66,89 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--planes", type=int, default=250, help="planes per step per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[K-1]")
+    ap.add_argument("--planes", type=int, default=0, help="planes per step per GPU (default 250; 64 for configs 4, 5)")
     ap.add_argument("--batch", type=int, default=int(os.environ.get("B200STRIPE_MAX_BATCH", "32")))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic planes (tiled to --planes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-planes", type=int, default=0, help="planes in the CPU sample (default: 2 per core)")
+    ap.add_argument("--no-batch-filter", action="store_true", help="skip the file-based e2e leg")
+    ap.add_argument("--cpu-planes", type=int, default=0, help="planes in the CPU sample (default: 2 per core; 1 per core for configs 4, 5)")
+    ap.add_argument("--files", type=int, default=0, help="files in the batch_filter leg (default 96)")
     ap.add_argument("--fast", action="store_true", help="allow FMA contraction (exact=0); not the parity configuration")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.planes <= 0:
+        a.planes = 250 if a.config <= 3 else 64
+    return a
+
+
+def config_dict(a):
+    """identical for both arms: the driver compares it"""
+    return {"workload": CONFIGS[a.config]["workload"], "config_id": a.config, "plane": f"{H}x{W} uint16"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle)
-def _cpu_worker(args):
-    z, = args
+def _cpu_init(config_id):
+    """per worker process, untimed: the oracle, the flat-field and the N_DISTINCT synthetic input planes"""
     from oracle import pystripe_oracle as orc
     from tools import synth
-    img = synth.plane(z % 8, (H, W))
-    flat = _cpu_worker.flat
+    c = CONFIGS[config_id]
+    _cpu_worker.orc = orc
+    _cpu_worker.cfg = c
+    _cpu_worker.flat = orc.normalize_flat(synth.flat_field((H, W))) if c["flat"] else None
+    _cpu_worker.planes = [synth.plane(z, (H, W)) for z in range(N_DISTINCT)]
+
+
+def _cpu_worker(z):
+    orc, c = _cpu_worker.orc, _cpu_worker.cfg
+    img = _cpu_worker.planes[z % N_DISTINCT].copy()
     t = time.perf_counter()
-    out = orc.process_img(img, flat=flat, **WORK)
-    return time.perf_counter() - t, int(out[::64, ::64].sum())
+    if c["fn"] == "filter_streaks":
+        out = orc.filter_streaks(img, **c["kw"])
+    else:
+        out = orc.process_img(img, flat=_cpu_worker.flat, **c["kw"])
+    return time.perf_counter() - t, int(out[::64, ::64].astype(np.int64).sum())
 
 
-def _cpu_init():
-    from oracle import pystripe_oracle as orc
-    from tools import synth
-    _cpu_worker.flat = orc.normalize_flat(synth.flat_field((H, W)))
-
-
-def cpu_throughput(n_planes, cores):
-    """oracle port (reference algorithm on restated pywt) on `cores` processes; returns (Mpx/s, seconds)."""
+def cpu_pool(config_id, cores):
     import multiprocessing as mp
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init) as pool:
-        pool.map(_cpu_worker, [(z,) for z in range(cores)])          # warm-up (numba / page-in), untimed
+    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(config_id,))
+    pool.map(_cpu_worker, range(cores))          # untimed: every worker has generated its inputs and compiled numba
+    return pool
+
+
+def cpu_throughput(config_id, n_planes, cores):
+    """oracle port (reference algorithm on restated pywt) on `cores` processes, inputs pre-generated in every worker;
+    returns (Mpx/s, seconds)."""
+    with cpu_pool(config_id, cores) as pool:
         t = time.perf_counter()
-        pool.map(_cpu_worker, [(z,) for z in range(n_planes)])
+        pool.map(_cpu_worker, range(n_planes), chunksize=1)
         dt = time.perf_counter() - t
     return n_planes * H * W / dt / 1e6, dt
 
 
 def run_reference(a):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
     per_step = a.cpu_planes or cores
-    import multiprocessing as mp
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init) as pool:
-        for _ in range(max(a.warmup, 1)):
-            pool.map(_cpu_worker, [(z,) for z in range(cores)])
+    with cpu_pool(a.config, cores) as pool:
+        for _ in range(max(a.warmup - 1, 0)):
+            pool.map(_cpu_worker, range(cores), chunksize=1)
         t = time.perf_counter()
         for _ in range(a.steps):
-            pool.map(_cpu_worker, [(z,) for z in range(per_step)])
+            pool.map(_cpu_worker, range(per_step), chunksize=1)
         dt = time.perf_counter() - t
     v = a.steps * per_step * H * W / dt / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "planes_per_step": per_step, "note": "CPU: reference algorithm (oracle port; PyWavelets restated in C, scipy.fftpack, glibc libm), one process per host core"},
+        "config": config_dict(a),
+        "run": {"planes_per_step": per_step,
+                "note": "CPU: reference algorithm (oracle port: PyWavelets restated in C, scipy.fftpack, glibc libm), one process "
+                        "per host core like the reference's batch_filter farm; inputs pre-generated outside the timed region"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{per_step} planes of 2048x2048 per step, {a.steps} steps"},
+                         "sample": f"{per_step} planes of 2048x2048 per step, {a.steps} steps, inputs pre-generated"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -160,7 +205,7 @@ class ClockSampler:
 def run_b200(a):
     import torch
     import torch.distributed as dist
-    from pystripe import core, _native
+    from pystripe import core, _io
     from tools import synth
 
     rank = int(os.environ.get("RANK", "0"))
@@ -176,62 +221,88 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cfg = CONFIGS[a.config]
+    core.MAX_BATCH = a.batch
+    core.EXACT = not a.fast
     P = a.planes
-    base = synth.stack(min(a.distinct, P), (H, W), seed=1234 + 100 * rank)
-    flat = core.normalize_flat(synth.flat_field((H, W)))
-    plan = core._get_plan(local, (H, W), _native.U16, process=1, threshold=None, bidirectional=False, log1p=True,
-                          flat=flat, out_code=_native.U16, max_batch=a.batch, exact=0 if a.fast else 1, **WORK)
-    ctx = plan.ctx
-    info = plan.info
-    # pinned host buffers for the end-to-end leg, device-resident copies for the kernel leg
-    h_in = ctx.pinned_empty((P, H, W), np.uint16)
-    h_out = ctx.pinned_empty((P,) + plan.out_shape, plan.out_dtype)
-    reps = -(-P // base.shape[0])
-    h_in[:] = np.concatenate([base] * reps)[:P]
+    flat = core.normalize_flat(synth.flat_field((H, W))) if cfg["flat"] else None
+
+    def run(x):                                          # the public call, whatever x is (CUDA tensor / numpy)
+        if cfg["fn"] == "filter_streaks":
+            return core.filter_streaks(x, **cfg["kw"])
+        return core.process_img(x, flat=flat, _max_batch=a.batch, **cfg["kw"])
+
+    base = synth.stack(min(N_DISTINCT, P), (H, W), seed=1234 + 100 * rank)
+    h_in = core.pinned_empty((P, H, W), np.uint16, device=local)     # page-locked host input of the e2e leg
+    h_in[:] = np.concatenate([base] * (-(-P // base.shape[0])))[:P]
     d_in = torch.from_numpy(h_in).to(dev)
-    d_out = torch.empty((P,) + plan.out_shape, dtype=torch.uint16, device=dev)
 
     # ---- device-resident: W warm-up, K timed steps, CUDA events on the launching (current) stream
     for _ in range(a.warmup):
-        plan.run_torch(d_in, d_out)
+        d_out = run(d_in)
+    plan = next(reversed(core._plans.values()))          # the plan the public call built (geometry for the roofline model)
+    ctx, info = plan.ctx, plan.info
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        plan.run_torch(d_in, d_out)
+        d_out = run(d_in)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
     clk = clocks.stop() if clocks else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = max_over_ranks(ms)
     value = world * a.steps * P * H * W / (ms_max * 1e-3) / 1e6
+    out_plane_bytes = int(np.prod(d_out.shape[1:])) * d_out.element_size()
 
-    # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H inside the timed region)
-    for _ in range(max(1, min(a.warmup, 2))):
-        plan.run_host(h_in, h_out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        plan.run_host(h_in, h_out)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_v = world * a.steps * P * H * W / float(t.item()) / 1e6
-    checksum = int(h_out[:: max(1, P // 4), ::128, ::128].astype(np.int64).sum())
+    def timed_host(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = fn()
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0), r
 
-    # ---- the platform's ceiling for e2e: one step's host<->device bytes with NO kernels, both directions at once, all
-    # ranks at the same time (pinned buffers of the e2e leg, one stream per direction).  Not a bench value.
-    copy_only = None
+    # ---- end to end, public API, page-locked host input (H2D + kernels + D2H inside the timed region)
+    dt, h_out = timed_host(lambda: run(h_in), a.steps, max(1, min(a.warmup, 2)))
+    e2e_v = world * a.steps * P * H * W / dt / 1e6
+    checksum = int(np.asarray(h_out)[:: max(1, P // 4), ::128, ::128].astype(np.int64).sum())
+    assert np.array_equal(np.asarray(h_out)[:2], d_out[:2].cpu().numpy()), "host and device legs disagree"
+    del h_out
+
+    # ---- end to end, public API, ordinary pageable numpy stack
+    pageable = np.array(h_in, copy=True)
+    e2e_steps = max(2, a.steps // 2)
+    dt, _ = timed_host(lambda: run(pageable), e2e_steps, 1)
+    e2e_pageable = world * e2e_steps * P * H * W / dt / 1e6
+    del pageable
+
+    # ---- end to end through batch_filter over files on tmpfs (uncompressed TIFF in, TIFF out)
+    bf = None
+    if not a.no_batch_filter and cfg["fn"] == "process_img":
+        try:
+            bf = batch_filter_leg(a, cfg, core, _io, base, flat, local, world, barrier, max_over_ranks)
+        except Exception as e:                                   # the file leg must never cost the bench line
+            bf = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- host<->device copy probe: the step's bytes with NO kernels, both directions at once, all ranks at the same time.
+    # A probe of the box's PCIe / host-memory rate, NOT a ceiling (fewer, larger copies than the pipeline issues).
+    copy_probe = None
     try:
-        th_in, th_out = torch.from_numpy(h_in), torch.from_numpy(h_out)
+        th_in = torch.from_numpy(h_in)
+        h_o = core.pinned_empty((P,) + tuple(d_out.shape[1:]), core._native.CODE_TO_NP[info.out_dtype], device=local)
+        th_out = torch.from_numpy(h_o)
         s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
 
         def copies():
@@ -242,116 +313,182 @@ def run_b200(a):
         copies()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(3):
+        for _ in range(10):
             copies()
         torch.cuda.synchronize()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        copy_only = world * 3 * P * H * W / float(t.item()) / 1e6
-    except Exception as e:                                      # the probe must never cost the bench line
-        print(f"copy-only probe failed: {type(e).__name__}: {e}", file=sys.stderr)
+        dtc = max_over_ranks(time.perf_counter() - t0)
+        copy_probe = {"value": world * 10 * P * H * W / dtc / 1e6, "unit": UNIT, "repetitions": 10,
+                      "h2d_GBps_per_gpu": 10 * P * H * W * 2 / dtc / 1e9, "d2h_GBps_per_gpu": 10 * P * out_plane_bytes / dtc / 1e9,
+                      "note": "same bytes per step moved H2D + D2H with no kernels, two large copies, all ranks at once; a probe, not a bound"}
+    except Exception as e:
+        print(f"copy probe failed: {type(e).__name__}: {e}", file=sys.stderr)
 
     # ---- roofline: per-launch CUDA events around every kernel (separate pass so `value` is not perturbed)
-    roof = None
-    shares = {}
+    roof, shares = None, {}
     if rank == 0:
-        ctx.timing_enable(True)
-        ctx.timing_read(reset=True)
-        for _ in range(2):
-            plan.run_torch(d_in, d_out)
-        tm = ctx.timing_read(reset=True, per_level=True)
-        ctx.timing_enable(False)
-        total = sum(v[0] for v in tm.values())
-        shares = {f"{k}@L{l}" if l else k: round(v[0] / total, 4) for (k, l), v in sorted(tm.items(), key=lambda kv: -kv[1][0])}
-        (kname, lvl), (kms, kn) = max(tm.items(), key=lambda kv: kv[1][0])
-        peaks = {}
-        pf = ROOT / "MEASURED_PEAKS.json"
-        if pf.exists():
-            peaks = json.loads(pf.read_text())
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        nb_per_launch = min(a.batch, P)
-        rows = [info.padded_height] + [info.level_rows[i] for i in range(info.levels)]
-        cols = [info.padded_width] + [info.level_cols[i] for i in range(info.levels)]
-        if kname in ("dwt_fwd", "dwt_inv") and lvl >= 1:
-            per_plane = 4 * rows[lvl - 1] * cols[lvl - 1] + 16 * rows[lvl] * cols[lvl]
-        elif kname == "notch" and lvl >= 1:
-            per_plane = 8 * rows[lvl] * cols[lvl]
-        elif kname == "prologue":
-            per_plane = 2 * H * W + 4 * H * W + 4 * rows[0] * cols[0]
-        elif kname == "epilogue":
-            per_plane = 4 * H * W + 2 * H * W
-        else:
-            per_plane = info.algorithmic_bytes_per_plane
-        planes_timed = 2 * P
-        avg_launch_ms = kms / kn
-        launches_per_plane = kn / planes_timed
-        alg_bytes_per_launch = per_plane / launches_per_plane
-        achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
-        # DRAM traffic of that kernel from the committed `ncu --set full` capture (dram__bytes_read+write per launch)
-        traffic, traffic_src = None, None
-        tf = ROOT / "profiles" / "r01_traffic.json"
-        if tf.exists():
-            tj = json.loads(tf.read_text())
-            ent = tj["kernels"].get(f"{kname}@L{lvl}" if lvl else kname)
-            if ent:
-                traffic = ent["dram_bytes_per_plane"] / launches_per_plane
-                traffic_src = tj["source"]
-        # the competing ceiling: FP32 lane-ops (exact mode issues a separate multiply and add per tap)
-        fp32_peak = 148 * 128 * 1.965e9
-        fp32 = {"flops_per_plane_model": int(info.flops_per_plane), "peak_lane_ops_per_s": fp32_peak,
-                "whole_pipeline_frac": info.flops_per_plane * a.steps * P / (ms_max * 1e-3) / fp32_peak,
-                "note": "DWT multiply-adds only (2 lane-ops per MAC in exact mode); FFT, log1p/expm1 and index work come on top"}
-        roof = {"bound": "hbm", "kernel": f"{kname}@level{lvl}" if lvl else kname, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "fp32": fp32,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
-                "planes_per_launch": nb_per_launch, "share_of_step": round(kms / total, 4),
-                "largest_mover": None,
-                "whole_pipeline": {"algorithmic_bytes_per_plane": int(info.algorithmic_bytes_per_plane),
-                                   "achieved_GBps": info.algorithmic_bytes_per_plane * a.steps * P / (ms_max * 1e-3) / 1e9,
-                                   "frac": info.algorithmic_bytes_per_plane * a.steps * P / (ms_max * 1e-3) / 1e9 / peak}}
-
-    # the kernel that moves the most bytes (forward DWT level 1), for the HBM view of the same run
-    if roof is not None and ("dwt_fwd", 1) in tm:
-        kms1, kn1 = tm[("dwt_fwd", 1)]
-        per_plane1 = 4 * rows[0] * cols[0] + 16 * rows[1] * cols[1]
-        ach1 = per_plane1 * (2 * P) / (kms1 * 1e-3) / 1e9
-        roof["largest_mover"] = {"kernel": "dwt_fwd@level1", "achieved": ach1, "frac": ach1 / peak,
-                                 "algorithmic_bytes_per_plane": per_plane1, "share_of_step": round(kms1 / total, 4)}
+        roof, shares = roofline(a, ctx, info, run, d_in, P, ms_max)
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n = a.cpu_planes or 2 * cores
-        v, dt_cpu = cpu_throughput(n, cores)
+        n = a.cpu_planes or (2 * cores if a.config <= 3 else cores)
+        v, dt_cpu = cpu_throughput(a.config, n, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} planes of 2048x2048 (same workload), {dt_cpu:.1f} s wall, one process per core"}
+               "sample": f"{n} planes of 2048x2048 (same workload, inputs pre-generated), {dt_cpu:.1f} s wall, one process per core"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "planes_per_step_per_gpu": P, "planes_per_launch": min(a.batch, P),
-                       "exact_summation_order": not a.fast,
-                       "l2": "inputs larger than L2 (each step streams %d MB of uint16 input per GPU)" % (P * H * W * 2 // 2 ** 20),
-                       "device_resident_streams": int(os.environ.get("B2S_DEV_SLOTS", "3")),
-                       "parallelism": f"z-shard x{world}, no collective"},
+            "config": config_dict(a),
+            "run": {"planes_per_step_per_gpu": P, "planes_per_launch": min(a.batch, P), "exact_summation_order": not a.fast,
+                    "l2": "inputs larger than L2 (each step streams %d MB of uint16 input per GPU)" % (P * H * W * 2 // 2 ** 20),
+                    "device_resident_streams": int(os.environ.get("B2S_DEV_SLOTS", "3")),
+                    "parallelism": f"z-shard x{world}, no collective",
+                    "api": "every GPU leg calls pystripe.core." + cfg["fn"] + " (value: CUDA tensors; e2e: pinned numpy; "
+                           "e2e_public_api: pageable numpy; e2e_batch_filter: files)"},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(P * H * W * 2),
-                    "d2h_bytes_per_step": int(P * plan.out_shape[0] * plan.out_shape[1] * np.dtype(plan.out_dtype).itemsize),
-                    "timer": "host wall clock around the synchronous C-ABI call (internal streams), max over ranks",
-                    "copy_only_ceiling": copy_only,
-                    "frac_of_copy_only_ceiling": (e2e_v / copy_only) if copy_only else None,
-                    "copy_only_note": "same bytes per step moved H2D + D2H with no kernels, all ranks at once (PCIe / host "
-                                      "memory ceiling of this box, in the metric's unit); e2e / ceiling is the overlap achieved"},
+                    "d2h_bytes_per_step": int(P * out_plane_bytes),
+                    "timer": "host wall clock around the synchronous public call, max over ranks",
+                    "input": "numpy array over page-locked memory (core.pinned_empty); output: page-locked array from the result pool"},
+            "e2e_public_api": {"value": e2e_pageable, "unit": UNIT, "steps": e2e_steps,
+                               "input": "pageable numpy stack (staged by the library's copy threads)"},
+            "e2e_batch_filter": bf, "copy_only_probe": copy_probe,
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
             "kernel_time_shares": shares, "checksum": checksum,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def batch_filter_leg(a, cfg, core, _io, base, flat, local, world, barrier, max_over_ranks):
+    """core.batch_filter over `n` uncompressed TIFF tiles on tmpfs -> TIFF tiles on tmpfs.  Every rank owns its own
+    folder and GPU (B200STRIPE_DEVICES), so N ranks run N independent batch_filter calls at once."""
+    n = a.files or 96
+    tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    work = Path(tempfile.mkdtemp(prefix=f"b2s_bench_r{local}_", dir=tmp_root))
+    saved = {k: os.environ.pop(k, None) for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK")}   # one process = one independent farm
+    os.environ["B200STRIPE_DEVICES"] = str(local)
+    try:
+        src, dst = work / "in", work / "out"
+        src.mkdir()
+        stack = np.concatenate([base] * (-(-n // base.shape[0])))[:n]
+        _io.write_tiff_batch([src / f"img_{z:05d}.tif" for z in range(n)], np.ascontiguousarray(stack), None)
+        cores = os.cpu_count() or 1
+        kw = dict(cfg["kw"])
+        if flat is not None:
+            kw["flat"] = flat * 1.0            # batch_filter normalises: a normalised flat stays what it is
+        res = {}
+        for name, compression in (("uncompressed", None), ("adobe_deflate_1", ("ADOBE_DEFLATE", 1))):
+            files = n if compression is None else max(8, n // 4)
+            flist = [src / f"img_{z:05d}.tif" for z in range(files)]
+
+            def once():
+                shutil.rmtree(dst, ignore_errors=True)
+                with open(os.devnull, "w") as null:
+                    old = sys.stdout
+                    sys.stdout = null
+                    try:
+                        rc = core.batch_filter(src, dst, files_list=flist, workers=max(2, cores // world), threads_per_gpu=8,
+                                               compression=compression, **kw)
+                    finally:
+                        sys.stdout = old
+                assert rc == 0, f"batch_filter returned {rc}"
+            if compression is None:
+                once()                                           # warm-up: plan, pinned pools
+            barrier()
+            t0 = time.perf_counter()
+            once()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            res[name] = {"value": world * files * H * W / dt / 1e6, "unit": UNIT, "files": files, "seconds": dt}
+        one = core.imread_tif_raw_png(dst / "img_00000.tif")
+        res["output"] = f"{one.shape[0]}x{one.shape[1]} {one.dtype}"
+        res["note"] = ("tmpfs -> native codec (libb2sio) -> pinned batch -> GPU -> pinned batch -> native codec -> tmpfs, "
+                       f"{max(2, cores // world)} host threads; adobe_deflate_1 is the reference's default output compression")
+        return res
+    finally:
+        os.environ.pop("B200STRIPE_DEVICES", None)
+        for k, v in saved.items():
+            if v is not None:
+                os.environ[k] = v
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def roofline(a, ctx, info, run, d_in, P, ms_max):
+    ctx.timing_enable(True)
+    ctx.timing_read(reset=True)
+    for _ in range(2):
+        run(d_in)
+    tm = ctx.timing_read(reset=True, per_level=True)
+    ctx.timing_enable(False)
+    total = sum(v[0] for v in tm.values())
+    shares = {f"{k}@L{l}" if l else k: round(v[0] / total, 4) for (k, l), v in sorted(tm.items(), key=lambda kv: -kv[1][0])}
+    (kname, lvl), (kms, kn) = max(tm.items(), key=lambda kv: kv[1][0])
+    peaks = {}
+    pf = ROOT / "MEASURED_PEAKS.json"
+    if pf.exists():
+        peaks = json.loads(pf.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    rows = [info.padded_height] + [info.level_rows[i] for i in range(info.levels)]
+    cols = [info.padded_width] + [info.level_cols[i] for i in range(info.levels)]
+    F = 90 if a.config == 5 else 20
+    wh, ww = info.work_height, info.work_width
+
+    def model(kname, lvl):
+        """(algorithmic bytes, FP32 lane-ops in exact mode) per plane of one launch of this class at this level"""
+        if kname in ("dwt_fwd", "dwt_inv") and lvl >= 1:
+            b = 4 * rows[lvl - 1] * cols[lvl - 1] + 16 * rows[lvl] * cols[lvl]
+            macs = 2 * F * rows[lvl] * cols[lvl - 1] + 4 * F * rows[lvl] * cols[lvl]
+            return b, 2 * macs
+        if kname == "notch" and lvl >= 1:
+            return 8 * rows[lvl] * cols[lvl], None
+        if kname == "prologue":
+            return 2 * wh * ww + (4 * wh * ww if CONFIGS[a.config]["flat"] and a.config == 2 else 0) + 4 * rows[0] * cols[0], None
+        if kname == "epilogue":
+            return 4 * wh * ww + int(info.out_height * info.out_width * (1 if info.out_dtype == 0 else 2)), None
+        return int(info.algorithmic_bytes_per_plane), None
+
+    per_plane, lane_ops = model(kname, lvl)
+    planes_timed = 2 * P
+    n_pass = max(1, info.n_passes)
+    avg_launch_ms = kms / kn
+    launches_per_plane = kn / planes_timed
+    alg_bytes_per_launch = per_plane * n_pass / launches_per_plane if kname in ("dwt_fwd", "dwt_inv", "notch") else per_plane / launches_per_plane
+    achieved = alg_bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    for tf in (ROOT / "profiles" / "r02_traffic.json", ROOT / "profiles" / "r01_traffic.json"):
+        if tf.exists() and a.config == 2:
+            tj = json.loads(tf.read_text())
+            ent = tj["kernels"].get(f"{kname}@L{lvl}" if lvl else kname)
+            if ent:
+                traffic = ent["dram_bytes_per_plane"] * n_pass / launches_per_plane
+                traffic_src = tj["source"]
+                break
+    fp32_peak = 148 * 128 * 1.965e9
+    fp32 = {"flops_per_plane_model": int(info.flops_per_plane), "peak_lane_ops_per_s": fp32_peak,
+            "whole_pipeline_frac": info.flops_per_plane * a.steps * P / (ms_max * 1e-3) / fp32_peak,
+            "kernel_frac": (lane_ops * n_pass * planes_timed / (kms * 1e-3) / fp32_peak) if lane_ops else None,
+            "note": "exact mode issues a separate multiply and add per tap (2 lane-ops per MAC): the FP32 pipe, not HBM, is "
+                    "the ceiling of the DWT kernels; kernel_frac = the dominant kernel's lane-ops / its time / peak"}
+    roof = {"bound": "hbm", "kernel": f"{kname}@level{lvl}" if lvl else kname, "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "fp32": fp32,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+            "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
+            "planes_per_launch": min(a.batch, P), "share_of_step": round(kms / total, 4), "largest_mover": None,
+            "whole_pipeline": {"algorithmic_bytes_per_plane": int(info.algorithmic_bytes_per_plane),
+                               "achieved_GBps": info.algorithmic_bytes_per_plane * a.steps * P / (ms_max * 1e-3) / 1e9,
+                               "frac": info.algorithmic_bytes_per_plane * a.steps * P / (ms_max * 1e-3) / 1e9 / peak}}
+    if ("dwt_fwd", 1) in tm:   # the kernel that moves the most bytes, for the HBM view of the same run
+        kms1, kn1 = tm[("dwt_fwd", 1)]
+        b1, ops1 = model("dwt_fwd", 1)
+        ach1 = b1 * n_pass * planes_timed / (kms1 * 1e-3) / 1e9
+        roof["largest_mover"] = {"kernel": "dwt_fwd@level1", "achieved": ach1, "frac": ach1 / peak,
+                                 "fp32_frac": ops1 * n_pass * planes_timed / (kms1 * 1e-3) / fp32_peak,
+                                 "algorithmic_bytes_per_plane": b1, "share_of_step": round(kms1 / total, 4)}
+    return roof, shares
 
 
 def _claim_stdout():

@@ -405,6 +405,14 @@ def clear_plan_cache():
         _evict_idle(keep=0)
 
 
+def pinned_empty(shape, dtype, device: int = None) -> ndarray:
+    """numpy array over page-locked host memory on the GPU's NUMA node (b2s_host_alloc).  Stacks built in such an array
+    travel to the GPU without the staging copy ordinary (pageable) arrays need; results of host calls are returned in
+    arrays of the same kind.  The memory goes back to a recycling pool when the last view of the array is dropped."""
+    dev = device if device is not None else _device_of(None)
+    return _native.context(dev).pooled_empty(tuple(shape), dtype)
+
+
 def _run(plan, img):
     if _native._is_torch(img):
         return plan.run_torch(img)

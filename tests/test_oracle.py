@@ -248,3 +248,18 @@ def test_sosfiltfilt_restatement(n, freq):
     got = orc.sosfiltfilt_order1_restated(x, sos, float(zi[0, 0]))
     ref = sosfiltfilt(sos, x)
     assert ref.dtype == np.float64 and np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+
+
+def test_oracle_reproduces_the_reference_on_its_real_tile():
+    """tests/golden/real_tile_golden.*: the reference source run verbatim on LsDeconvolveMultiGPU/supplements/test.png
+    (Step-3 call, process_images.py:420-447); the restated oracle must give the same array (CRC32 of the whole output)."""
+    import json
+    import zlib
+    from tests.golden import make_golden_real_tile as rt
+    meta = json.loads((ROOT / "tests" / "golden" / "real_tile_golden.json").read_text())
+    img = rt.load_input()
+    assert zlib.crc32(img.tobytes()) == meta["input_crc32"]
+    name = "real_tile_step3_db9_bidir_u16"
+    res = orc.process_img(img.copy(), tile_size=img.shape, **rt.CASES[name])
+    assert str(res.dtype) == meta[name]["dtype"]
+    assert zlib.crc32(np.ascontiguousarray(res).tobytes()) == meta[name]["crc32"]
