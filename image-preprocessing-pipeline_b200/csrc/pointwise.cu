@@ -54,12 +54,21 @@ __device__ __forceinline__ float load_as_float(const void *p, int dtype, size_t 
 }
 
 // One CTA per group of padded rows that share a source row (numpy.pad replicates rows): the source row is converted
-// once ([/ flat], log1p) into shared memory, then every target row is assembled through the column map with 128-bit
-// stores.  Groups without a source row (constant padding) are zero rows.
+// once ([/ flat], log1p) into shared memory, the padded row is assembled once through the column map (scalar, bank-conflict
+// free: the map is runs of consecutive ascending or descending indices), then every target row is a 128-bit copy of it.
+// Groups without a source row (constant padding) are rows of the fill value.
+__device__ __forceinline__ float prologue_value(const B2sPrologueArgs &a, float r, const float *flat, int x)
+{
+    if (flat) { const float fl = __ldg(flat + x); r = (fl > 1.0e-18f && fl < 1.0e18f) ? b2s_div_hot(r, fl) : __fdiv_rn(r, fl); }
+    if (a.use_log1p) r = b2s_log1pf_dev(r);
+    return r;
+}
+
 __global__ void __launch_bounds__(256) k_prologue(B2sPrologueArgs a)
 {
     extern __shared__ __align__(16) float s_row[];
     __shared__ unsigned s_mm[16];
+    float *s_out = s_row + ((a.src_cols + 3) & ~3);     // the padded row (out.pitch floats)
     const int grp = blockIdx.x;
     const size_t plane = blockIdx.y;
     const int sy = a.row_src[grp];
@@ -67,21 +76,37 @@ __global__ void __launch_bounds__(256) k_prologue(B2sPrologueArgs a)
     if (sy >= 0) {
         const size_t base = plane * (size_t)a.src_rows * a.src_cols + (size_t)sy * a.src_cols;
         const float *flat = a.flat ? a.flat + (size_t)sy * a.src_cols : nullptr;
-#pragma unroll 8
-        for (int x = threadIdx.x; x < a.src_cols; x += 256) {
-            float r;
-            if (a.lut) {   // integer pixels, no flat: log1p through the 64 K-entry table (built with b2s_log1pf)
-                const unsigned v = a.in_dtype == B2S_U16 ? __ldg(reinterpret_cast<const unsigned short *>(a.in) + base + x)
-                                                         : __ldg(reinterpret_cast<const unsigned char *>(a.in) + base + x);
-                r = __ldg(a.lut + v);
-                klo = min(klo, v); khi = max(khi, v);
-            } else {
-                r = load_as_float(a.in, a.in_dtype, base + x);
-                if (a.minmax) { const unsigned key = a.in_dtype == B2S_F32 ? f2key(r) : (unsigned)r; klo = min(klo, key); khi = max(khi, key); }
-                if (flat) { const float fl = __ldg(flat + x); r = (fl > 1.0e-18f && fl < 1.0e18f) ? b2s_div_hot(r, fl) : __fdiv_rn(r, fl); }
-                if (a.use_log1p) r = b2s_log1pf_dev(r);
+        if (a.in_dtype == B2S_U16 && (a.src_cols & 3) == 0 && (reinterpret_cast<uintptr_t>(a.in) & 7) == 0) {
+            // 4 pixels per thread and trip: one 64-bit load of the samples (rows start 8-byte aligned: cols % 4 == 0)
+            const uint2 *in4 = reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned short *>(a.in) + base);
+            for (int x4 = threadIdx.x; x4 < (a.src_cols >> 2); x4 += 256) {
+                const uint2 p = __ldg(in4 + x4);
+                const unsigned v[4] = {p.x & 0xffffu, p.x >> 16, p.y & 0xffffu, p.y >> 16};
+                float4 o;
+                float *po = &o.x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    klo = min(klo, v[k]); khi = max(khi, v[k]);
+                    po[k] = a.lut ? __ldg(a.lut + v[k]) : prologue_value(a, (float)v[k], flat, 4 * x4 + k);
+                }
+                *reinterpret_cast<float4 *>(s_row + 4 * x4) = o;
             }
-            s_row[x] = r;
+        } else {
+#pragma unroll 4
+            for (int x = threadIdx.x; x < a.src_cols; x += 256) {
+                float r;
+                if (a.lut) {   // integer pixels, no flat: log1p through the 64 K-entry table (built with b2s_log1pf)
+                    const unsigned v = a.in_dtype == B2S_U16 ? __ldg(reinterpret_cast<const unsigned short *>(a.in) + base + x)
+                                                             : __ldg(reinterpret_cast<const unsigned char *>(a.in) + base + x);
+                    r = __ldg(a.lut + v);
+                    klo = min(klo, v); khi = max(khi, v);
+                } else {
+                    r = load_as_float(a.in, a.in_dtype, base + x);
+                    if (a.minmax) { const unsigned key = a.in_dtype == B2S_F32 ? f2key(r) : (unsigned)r; klo = min(klo, key); khi = max(khi, key); }
+                    r = prologue_value(a, r, flat, x);
+                }
+                s_row[x] = r;
+            }
         }
         if (a.minmax) {   // every source row is read by exactly one CTA: the uniform check costs no extra pass
             klo = __reduce_min_sync(0xffffffffu, klo);
@@ -97,22 +122,17 @@ __global__ void __launch_bounds__(256) k_prologue(B2sPrologueArgs a)
         atomicMin(a.minmax + 2 * plane, lo);
         atomicMin(a.minmax + 2 * plane + 1, ~hi);
     }
+    for (int c = threadIdx.x; c < a.out.pitch; c += 256) {
+        const int m = sy >= 0 ? __ldg(a.colmap + c) : -1;
+        s_out[c] = m >= 0 ? s_row[m] : a.pad_value;
+    }
+    __syncthreads();
     const int q4 = a.out.pitch >> 2;
-    const int4 *cm = reinterpret_cast<const int4 *>(a.colmap);
+    const float4 *so4 = reinterpret_cast<const float4 *>(s_out);
     for (int t = a.row_start[grp]; t < a.row_start[grp + 1]; ++t) {
-        float *drow = a.out.ptr + plane * a.out.plane_stride + (size_t)a.row_targets[t] * a.out.pitch;
+        float4 *drow = reinterpret_cast<float4 *>(a.out.ptr + plane * a.out.plane_stride + (size_t)a.row_targets[t] * a.out.pitch);
 #pragma unroll 4
-        for (int c4 = threadIdx.x; c4 < q4; c4 += 256) {
-            float4 o = make_float4(a.pad_value, a.pad_value, a.pad_value, a.pad_value);
-            if (sy >= 0) {
-                const int4 m = __ldg(cm + c4);
-                if (m.x >= 0) o.x = s_row[m.x];
-                if (m.y >= 0) o.y = s_row[m.y];
-                if (m.z >= 0) o.z = s_row[m.z];
-                if (m.w >= 0) o.w = s_row[m.w];
-            }
-            *reinterpret_cast<float4 *>(drow + 4 * c4) = o;
-        }
+        for (int c4 = threadIdx.x; c4 < q4; c4 += 256) drow[c4] = so4[c4];
     }
 }
 
@@ -453,7 +473,7 @@ __global__ void k_math(int which, const float *in, float *out, int64_t n)
 
 void b2s_launch_prologue(const B2sPrologueArgs &a, int n_planes, cudaStream_t s)
 {
-    const size_t bytes = sizeof(float) * (size_t)a.src_cols;
+    const size_t bytes = sizeof(float) * ((((size_t)a.src_cols + 3) & ~(size_t)3) + (size_t)a.out.pitch);
     if (bytes > 48 * 1024) cudaFuncSetAttribute(k_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     k_prologue<<<dim3(a.n_groups, n_planes), 256, bytes, s>>>(a);
 }

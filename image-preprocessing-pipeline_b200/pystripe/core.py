@@ -258,6 +258,28 @@ def _device_of(x) -> int:
     return int(os.environ.get("B200STRIPE_DEVICE", os.environ.get("LOCAL_RANK", "0")))
 
 
+_flat_ids = {}
+
+
+def _flat_fingerprint(flat):
+    """(shape, CRC32 of the values): two flat-field arrays with the same content share a plan (batch_filter normalises its
+    flat argument into a new array on every call).  The checksum is computed once per array object."""
+    import weakref
+    import zlib
+    ent = _flat_ids.get(id(flat))
+    if ent is not None and ent[0]() is flat:
+        return ent[1]
+    a = flat.detach().cpu().numpy() if _native._is_torch(flat) else np.asarray(flat)
+    fp = (tuple(a.shape), str(a.dtype), zlib.crc32(np.ascontiguousarray(a).view(np.uint8)))
+    try:
+        if len(_flat_ids) > 64:
+            _flat_ids.clear()
+        _flat_ids[id(flat)] = (weakref.ref(flat), fp)
+    except TypeError:
+        pass
+    return fp
+
+
 def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, threshold, padding_mode, bidirectional,
               log1p, flat=None, gaussian=False, down_sample=None, down_sample_method='max', dark=0, lightsheet=False,
               artifact_length=150, background_window_size=200, percentile=0.25, lightsheet_vs_background=2.0,
@@ -293,7 +315,7 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
     taps = _dec_lo(wavelet) if destripe else None
     flat_key = None
     if flat is not None:
-        flat_key = (id(flat), tuple(flat.shape))
+        flat_key = _flat_fingerprint(flat)
     key = (device, tuple(shape), in_code, process, s1, s2, int(level), taps, mode if destripe else None,
            bool(bidirectional), bool(log1p), threshold is not None and threshold <= 0, flat_key, bool(gaussian), ds,
            method, float(dark or 0), bool(lightsheet), artifact_length, background_window_size, percentile,
@@ -1187,7 +1209,14 @@ def batch_filter(
     gpus = [local_rank] if world > 1 and not os.environ.get("B200STRIPE_DEVICES") else _visible_gpus()
     gpus = gpus[:max(1, num_images)]
     batch = max(1, int(threads_per_gpu))
-    io_threads = max(1, workers // (2 * len(gpus)))      # decode and encode threads of one GPU's pipeline
+    # one pipeline item = `group` files: several plan batches per process_img call, so that the call's own slots overlap
+    # H2D / kernels / D2H (a single 8-plane call runs them back to back: 10 vs 19 Gpx/s measured at 2048^2)
+    per_gpu = -(-num_images // len(gpus))
+    group = int(os.environ.get("B200STRIPE_FILE_GROUP", "0")) or max(batch, min(8 * batch, 64, -(-per_gpu // 6)))
+    # writing costs about twice what reading does per thread (new pages of the output files): 1/3 decode, 2/3 encode
+    per_pipe = max(2, workers // len(gpus))
+    read_threads = max(1, per_pipe // 3)
+    write_threads = max(1, per_pipe - read_threads)
     print(f"{PrintColors.GREEN}{date_time_now()}: {PrintColors.ENDC}"
           f"using {workers} decode/encode threads and {len(gpus)} GPU(s). {num_images} images need to be processed.",
           flush=True)
@@ -1195,8 +1224,8 @@ def batch_filter(
     # argument errors the reference raises per file are the same for every file: find them before any thread starts
     _bleach_plan_args(bleach_correction_frequency, bleach_correction_clip_min, bleach_correction_clip_med,
                       bleach_correction_clip_max, bleach_correction_max_method, False)
-    shared = _BatchShared(jobs=jobs, batch=batch, progress=progress, kw=kw, d_type=d_type, tile_size=tile_size,
-                          compression=compression, timeout=timeout, io_threads=io_threads,
+    shared = _BatchShared(jobs=jobs, batch=batch, group=group, progress=progress, kw=kw, d_type=d_type, tile_size=tile_size,
+                          compression=compression, timeout=timeout, io_threads=read_threads, write_threads=write_threads,
                           print_input_file_names=print_input_file_names)
     return_code = 0
     pipelines = [_BatchPipeline(g, shared) for g in gpus]
@@ -1241,7 +1270,7 @@ class _BatchShared:
     def claim(self):
         with self.lock:
             lo = self.cursor
-            hi = min(lo + self.batch, len(self.jobs))
+            hi = min(lo + self.group, len(self.jobs))
             self.cursor = hi
         return self.jobs[lo:hi]
 
@@ -1274,7 +1303,7 @@ class _BatchPipeline:
         self.q_ready, self.q_write = _Q(maxsize=2), _Q(maxsize=2)
         self.threads = [threading.Thread(target=self._guard, args=(f,), daemon=True)
                         for f in (self._reader, self._compute, self._writer)]
-        self.pool = ThreadPoolExecutor(max_workers=max(2, shared.io_threads))
+        self.pool = ThreadPoolExecutor(max_workers=max(2, shared.write_threads))
 
     def start(self):
         for t in self.threads:
@@ -1445,7 +1474,7 @@ class _BatchPipeline:
                 todo = [i for i, ok in enumerate(valid) if ok]
                 if todo and res.ndim == 3 and _io.can_write(res[0], sh.compression) and res.flags.c_contiguous:
                     if len(todo) == len(jobs):
-                        status = _io.write_tiff_batch([j[1] for j in jobs], res, sh.compression, threads=sh.io_threads)
+                        status = _io.write_tiff_batch([j[1] for j in jobs], res, sh.compression, threads=sh.write_threads)
                     else:
                         futs = [self.pool.submit(_io.write_tiff_batch, [jobs[i][1]], res[i:i + 1], sh.compression, 1) for i in todo]
                         status = [fu.result()[0] for fu in futs]
