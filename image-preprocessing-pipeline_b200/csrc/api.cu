@@ -198,8 +198,10 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
     g.my[0] = g.PH;
     g.mx[0] = g.PW;
     if (g.n_passes > 0) {
-        if (p.pad_mode < B2S_PAD_REFLECT || p.pad_mode > B2S_PAD_CONSTANT)
-            return fail(ctx, B2S_ERR_UNSUPPORTED, "padding mode not implemented on the GPU path");
+        if (p.pad_mode < B2S_PAD_REFLECT || p.pad_mode > B2S_PAD_EMPTY)
+            return fail(ctx, B2S_ERR_INVALID, "Unsupported padding mode");
+        if (!b2s_pad_fill_supported(p.pad_mode, g.work_rows, g.work_cols))
+            return fail(ctx, B2S_ERR_UNSUPPORTED, "padding_mode='median' is limited to image sides of 32768 pixels");
         if (p.n_taps < 2 || p.n_taps > B2S_MAX_TAPS || (p.n_taps & 1) || !p.dec_lo)
             return fail(ctx, B2S_ERR_INVALID, "wavelet filter must have an even length in [2, %d]", B2S_MAX_TAPS);
         // core.py:1084-1096
@@ -350,6 +352,7 @@ struct b2s_plan {
         void *aa_a = nullptr, *aa_b = nullptr;     // resize with anti-aliasing: the filtered image after each axis (f64 / f32)
         unsigned short *ls_grid = nullptr, *bg_grid = nullptr, *ls_cells = nullptr;
         unsigned *mm = nullptr;
+        unsigned *pad_flags = nullptr;             // computed padding modes: 4 flags per plane
         double *bleach_scratch = nullptr;          // bleach correction: forward low-pass output, rows x (cols + 12) per plane
         float *bleach_filt = nullptr;              //                    img_filter, rows x cols per plane
         unsigned *bleach_max = nullptr;            //                    per-plane key of max(img_filter)
@@ -577,6 +580,8 @@ int alloc_slot(b2s_plan *pl, int si)
         for (int l = 1; l <= g.levels; ++l)
             for (int k = 0; k < 4; ++k)
                 if ((rc = dev_alloc(pl, (void **)&s.sub[l][k], sizeof(float) * pl->plane_stride[l] * B))) return rc;
+        if (g.n_passes > 0 && p.pad_mode >= B2S_PAD_LINEAR_RAMP &&
+            (rc = dev_alloc(pl, (void **)&s.pad_flags, sizeof(unsigned) * 4 * B))) return rc;
         pl->dwt_scratch_stride = g.n_passes > 0 ? b2s_dwt_scratch_floats(pl->taps.F, g.PH, g.PW) : 0;
         if (pl->dwt_scratch_stride &&
             (rc = dev_alloc(pl, (void **)&s.dwt_scratch, sizeof(float) * pl->dwt_scratch_stride * B))) return rc;
@@ -719,6 +724,10 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             a.lut = (cur_dt != B2S_F32 && !a.flat && p.log1p) ? pl->d_lut : nullptr;
             a.minmax = fuse_minmax ? s.mm : nullptr;
             b2s_launch_prologue(a, nb, st);
+            if (g.n_passes > 0 && p.pad_mode >= B2S_PAD_LINEAR_RAMP) {   // pad areas computed from the image (numpy.pad stat modes)
+                ctx->launches += p.pad_mode == B2S_PAD_EMPTY ? 0 : (p.pad_mode == B2S_PAD_LINEAR_RAMP ? 4 : 2);
+                b2s_launch_pad_fill(p.pad_mode, padded, g.base_pad, g.work_rows, g.work_cols, s.pad_flags, nb, st);
+            }
         }
         if (p.debug_stop_after == B2S_STAGE_PROLOGUE) return B2S_OK;
         for (int pass = 0; pass < g.n_passes; ++pass) {
@@ -1504,6 +1513,55 @@ int b2s_isotropic_convert(b2s_context *ctx, const float *d_in, int64_t n, int mo
     CU(ctx, cudaSetDevice(ctx->device));
     b2s_launch_convert_f32(d_in, n, mode, shift, d_out, (cudaStream_t)stream);
     ctx->launches += 1;
+    CU(ctx, cudaGetLastError());
+    return B2S_OK;
+}
+
+int b2s_histogram(b2s_context *ctx, const void *in, int in_is_device, int dtype, int64_t plane_elems, int n_planes,
+                  uint64_t *hist, int hist_is_device, int per_plane, void *stream)
+{
+    if (!ctx || !in || !hist || plane_elems <= 0 || n_planes <= 0) return B2S_ERR_INVALID;
+    if (dtype != B2S_U8 && dtype != B2S_U16) return fail(ctx, B2S_ERR_INVALID, "b2s_histogram takes uint8 or uint16 planes");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t esz = dtype == B2S_U8 ? 1 : 2;
+    const size_t n_hist = (size_t)65536 * (per_plane ? n_planes : 1);
+    void *d_in = nullptr;
+    unsigned long long *d_hist = reinterpret_cast<unsigned long long *>(hist);
+    std::vector<void *> tmp;
+    auto release = [&]() { for (void *p : tmp) cudaFreeAsync(p, st); tmp.clear(); };
+    struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
+    if (!in_is_device) {
+        // planes go through in slices so that a whole stack never needs a device copy of itself
+        if (cudaMallocAsync(&d_in, esz * (size_t)plane_elems * std::min(n_planes, 16), st) != cudaSuccess)
+            return fail(ctx, B2S_ERR_NOMEM, "cudaMallocAsync failed");
+        tmp.push_back(d_in);
+    }
+    if (!hist_is_device) {
+        void *p = nullptr;
+        if (cudaMallocAsync(&p, sizeof(uint64_t) * n_hist, st) != cudaSuccess) return fail(ctx, B2S_ERR_NOMEM, "cudaMallocAsync failed");
+        tmp.push_back(p);
+        d_hist = reinterpret_cast<unsigned long long *>(p);
+        CU(ctx, cudaMemcpyAsync(d_hist, hist, sizeof(uint64_t) * n_hist, cudaMemcpyHostToDevice, st));   // counts are ADDED
+    }
+    if (in_is_device) {
+        b2s_launch_histogram(in, dtype, (size_t)plane_elems, n_planes, d_hist, per_plane, st);
+        ctx->launches += 1;
+    } else {
+        for (int z = 0; z < n_planes; z += 16) {
+            const int nb = std::min(16, n_planes - z);
+            CU(ctx, cudaMemcpyAsync(d_in, (const char *)in + (size_t)z * plane_elems * esz, esz * (size_t)plane_elems * nb,
+                                    cudaMemcpyHostToDevice, st));
+            b2s_launch_histogram(d_in, dtype, (size_t)plane_elems, nb, d_hist + (per_plane ? (size_t)z * 65536 : 0), per_plane, st);
+            ctx->launches += 1;
+        }
+    }
+    if (!hist_is_device) {
+        CU(ctx, cudaMemcpyAsync(hist, d_hist, sizeof(uint64_t) * n_hist, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+    } else if (!in_is_device) {
+        CU(ctx, cudaStreamSynchronize(st));   // the caller's host planes may be reused on return
+    }
     CU(ctx, cudaGetLastError());
     return B2S_OK;
 }

@@ -101,6 +101,18 @@ void b2s_launch_convert_f32(const float *in, int64_t n, int mode, int shift, voi
 void b2s_launch_math(int which, const float *in, float *out, int64_t n, cudaStream_t s);
 void b2s_launch_log1p_lut(float *lut, int n, cudaStream_t s);
 
+// padfill.cu -----------------------------------------------------------------------------------------------------
+// numpy.pad modes that compute their pad area (linear_ramp, maximum, mean, median, minimum; empty = zeros): run on the
+// padded image after the prologue wrote the interior and zeros around it.  flags: 4 unsigned per plane (scratch).
+int b2s_pad_fill_supported(int mode, int rows, int cols);
+void b2s_launch_pad_fill(int mode, const B2sImg &padded, int base_pad, int rows, int cols, unsigned *flags, int n_planes,
+                         cudaStream_t s);
+
+// stats.cu ---------------------------------------------------------------------------------------------------------
+// exact intensity histogram of uint8 / uint16 planes, ADDED into `hist` (65 536 uint64 counters, per plane or one for all)
+void b2s_launch_histogram(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned long long *hist, int per_plane,
+                          cudaStream_t s);
+
 // dwt.cu --------------------------------------------------------------------------------------------------------
 // forward level: in (ny x nx) -> cA,cH,cV,cD ((ny+F-1)/2 x (nx+F-1)/2); exact!=0 => reference summation order, no FMA
 void b2s_launch_dwt_fwd(const B2sTaps &t, const B2sImg &in, const B2sImg &cA, const B2sImg &cH, const B2sImg &cV,

@@ -24,11 +24,73 @@
 //     round(t*v - 0) == round(t*v) for every input, signed zeros included.
 //   * filters longer than 20 taps (coif15 has 90) run the same code in chunks of J taps (taps are zero-padded to a
 //     multiple of J; adding an exact zero product never changes a float32 sum), so registers stay bounded.
+#include <cuda.h>
+
 #include <cstdlib>
+#include <cstring>
 
 #include "b2s_internal.h"
 
 namespace {
+
+// ---- TMA (cp.async.bulk.tensor) tile loads ------------------------------------------------------------------------
+// One elected thread fetches the whole input window of a tile with a single instruction: the copy engine walks the rows,
+// fills everything outside the image with zeros and signals an mbarrier, so the other 255 threads spend no issue slots on
+// address arithmetic (the LDGSTS loop was 13 % of the forward kernel's instructions, profiles/r02_*).  The inverse transform
+// wants exactly those zeros; the forward transform's half-sample symmetric extension is patched in shared memory for the
+// tiles that touch the border.  B2S_DWT_TMA=0 selects the LDGSTS loaders (kept for windows wider than a TMA box, 256).
+typedef CUresult (*TmaEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmaEncodeFn tma_encode_fn()
+{
+    static TmaEncodeFn fn = [] {
+        const char *e = getenv("B2S_DWT_TMA");
+        if (e && atoi(e) == 0) return (TmaEncodeFn) nullptr;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return (TmaEncodeFn) nullptr; }
+        return (TmaEncodeFn)p;
+    }();
+    return fn;
+}
+// 3-D map (column, row, plane) over the logical image: reads beyond rows / cols (also into the row padding) give zeros
+bool make_tmap(CUtensorMap *m, const B2sImg &im, int n_planes, int box_w, int box_h)
+{
+    memset(m, 0, sizeof *m);
+    TmaEncodeFn fn = tma_encode_fn();
+    if (!fn || box_w > 256 || box_h > 256 || (reinterpret_cast<uintptr_t>(im.ptr) & 15) || (im.pitch & 3) || (im.plane_stride & 3))
+        return false;
+    cuuint64_t dims[3] = {(cuuint64_t)im.cols, (cuuint64_t)im.rows, (cuuint64_t)(n_planes > 0 ? n_planes : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)im.pitch * 4, (cuuint64_t)im.plane_stride * 4};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, im.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(float *dst, const CUtensorMap *map, unsigned long long *bar, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 constexpr int kMaxFp = 160;           // padded analysis filter length bound (B2S_MAX_TAPS rounded up to a chunk)
 constexpr int kSmemPerSm = 227 * 1024;
@@ -84,7 +146,7 @@ struct InvGeom {
         // a quarter warp of the axis -1 pass reads 4 column groups (R floats apart) x 2 rows with 128-bit loads
         ps = R == 4 ? pitch_quads_4mod8(rp) : pitch_quads_odd(rp);
         pm = pitch_quads_odd(2 * TP);
-        sub_floats = rq * ps;
+        sub_floats = (rq * ps + 31) & ~31;   // every window starts on a 128-byte boundary (TMA destination)
         stage_floats = 4 * sub_floats;
         mid_floats = (2 * rq + 8) * pm;   // + slack rows: the last row group may look past TQ when TQ % R != 0
     }
@@ -275,6 +337,7 @@ struct FwdArgs {
     int F, Fp, nch;
     int tiles_x, tiles_y, n_tiles;
     int grid3d;      // launched as (tiles_x, tiles_y, planes): one tile per CTA
+    int use_tma;     // the input window arrives through the tensor map (grid3d launches only)
     float negzero;   // -0.0f, deliberately a run-time value (see mul2_exact)
 };
 
@@ -292,9 +355,13 @@ __device__ __forceinline__ TileCoord tile_of(int t, int tiles_x, int tiles_xy)
 // Persistent CTAs: each walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The input window of the next tile is
 // copied (cp.async) into the input stage while the axis -1 pass of the current tile runs out of the intermediate buffer.
 template <class T, int J, bool MULTI, int MODE>
-__global__ void __launch_bounds__(T::NT) k_dwt_fwd(const __grid_constant__ FwdTaps taps, const FwdArgs a)
+__global__ void __launch_bounds__(T::NT) k_dwt_fwd(const __grid_constant__ FwdTaps taps, const FwdArgs a,
+                                                   const __grid_constant__ CUtensorMap tmap)
 {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    // TMA destinations must sit on a 128-byte boundary of the shared window: align explicitly (the launch adds 128 bytes)
+    float *smem = reinterpret_cast<float *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     constexpr int TY = T::TY, TX = T::TX, NT = T::NT, NW = T::NW, RY = T::R1, RX = T::R2;
     constexpr bool EXACT = MODE == kExact;
     const int Fp = MULTI ? a.Fp : J;
@@ -360,7 +427,43 @@ __global__ void __launch_bounds__(T::NT) k_dwt_fwd(const __grid_constant__ FwdTa
 
     int t = grid3d ? 0 : blockIdx.x;
     const int t_end = grid3d ? 1 : a.n_tiles, t_step = grid3d ? 1 : gridDim.x;
-    if (t < t_end) issue_load(t);
+    const bool tma = grid3d && a.use_tma;
+    if (tma) {
+        // one thread: arm the barrier with the byte count of the box and start the copy; everybody waits on the barrier
+        if (tid == 0) mbar_init(&s_bar);
+        __syncthreads();
+        const int gy0 = 2 * blockIdx.y * TY + 2 - Fp, gx0a = (2 * blockIdx.x * TX + 2 - Fp) & ~3;
+        if (tid == 0) {
+            mbar_expect(&s_bar, (unsigned)(g.rin_y * PIN * sizeof(float)));
+            tma_load_3d(s_in, &tmap, &s_bar, gx0a, gy0, blockIdx.z);
+        }
+        mbar_wait(&s_bar, 0);
+        if (gy0 < 0 || gy0 + g.rin_y > ny || gx0a < 0 || gx0a + 4 * c4n > nx) {
+            // border tile: the copy engine wrote zeros outside the image; replace those within reach of a stored output
+            // by the half-sample symmetric extension (read from global memory: any image size, any number of reflections)
+            const float *src = a.in.ptr + (size_t)blockIdx.z * a.in.plane_stride;
+            const int wq = 4 * c4n;
+            for (int r = warp; r < g.rin_y; r += NW) {
+                const int gy = gy0 + r;
+                if (gy < -Fp || gy >= ny + Fp) continue;
+                const bool row_in = gy >= 0 && gy < ny;
+                const float *srow = src + (size_t)sym_ext(gy, ny) * a.in.pitch;
+                float *drow = s_in + r * PIN;
+                if (row_in) {   // only the columns left / right of the image
+                    for (int cc = lane; cc < 2 * Fp + 8; cc += 32) {
+                        const int gx = cc < Fp + 4 ? -1 - cc : nx + (cc - Fp - 4);
+                        const int sc = gx - gx0a;
+                        if (sc >= 0 && sc < wq && gx >= -Fp && gx < nx + Fp) drow[sc] = srow[sym_ext(gx, nx)];
+                    }
+                } else {
+                    for (int sc = lane; sc < wq; sc += 32) {
+                        const int gx = gx0a + sc;
+                        if (gx >= -Fp && gx < nx + Fp) drow[sc] = srow[sym_ext(gx, nx)];
+                    }
+                }
+            }
+        }
+    } else if (t < t_end) issue_load(t);
     while (t < t_end) {
         cp_async_wait_all();
         __syncthreads();   // tile t has landed; every warp is done with s_mid of the previous tile
@@ -460,13 +563,18 @@ struct InvArgs {
     int H, Hp, nch;
     int tiles_x, tiles_y, n_tiles;
     int grid3d;
+    int use_tma;
     float negzero;
 };
+struct InvMaps { CUtensorMap m[4]; };   // cA, cV, cH, cD (the order of the shared-memory windows)
 
 template <class T, int JH, bool MULTI, int MODE>
-__global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTaps taps, const InvArgs a)
+__global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTaps taps, const InvArgs a,
+                                                   const __grid_constant__ InvMaps maps)
 {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    float *smem = reinterpret_cast<float *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     constexpr int TQ = T::TY, TP = T::TX, NT = T::NT, NW = T::NW, RX = T::R1, RY = T::R2;
     const int Hp = MULTI ? a.Hp : JH;
     const InvGeom g(Hp, TQ, TP, RX);
@@ -536,7 +644,18 @@ __global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTa
 
     int t = grid3d ? 0 : blockIdx.x;
     const int t_end = grid3d ? 1 : a.n_tiles, t_step = grid3d ? 1 : gridDim.x;
-    if (t < t_end) issue_load(t);
+    if (grid3d && a.use_tma) {
+        // four boxes (cA, cV, cH, cD), one barrier; coefficients outside the sub-band arrive as the zeros the synthesis wants
+        if (tid == 0) mbar_init(&s_bar);
+        __syncthreads();
+        if (tid == 0) {
+            const int cy0 = blockIdx.y * TQ + a.H - Hp, cx0 = blockIdx.x * TP + a.H - Hp;
+            mbar_expect(&s_bar, (unsigned)(4 * RQ * PS * sizeof(float)));
+#pragma unroll
+            for (int sb = 0; sb < 4; ++sb) tma_load_3d(s_sub + sb * sub_floats, &maps.m[sb], &s_bar, cx0, cy0, blockIdx.z);
+        }
+        mbar_wait(&s_bar, 0);
+    } else if (t < t_end) issue_load(t);
     while (t < t_end) {
         cp_async_wait_all();
         __syncthreads();   // tile t has landed; every warp is done with s_mid of the previous tile
@@ -923,7 +1042,7 @@ template <class T, int J, bool MULTI, int MODE>
 void launch_fwd_t(const FwdTaps &ft, FwdArgs a, int n_planes, int sm_count, cudaStream_t s)
 {
     const FwdGeom g(a.Fp, T::TY, T::TX);
-    const size_t bytes = g.smem_bytes();
+    const size_t bytes = g.smem_bytes() + 128;   // + alignment slack of the TMA destination
     a.tiles_x = (a.cA.cols + T::TX - 1) / T::TX;
     a.tiles_y = (a.cA.rows + T::TY - 1) / T::TY;
     a.n_tiles = a.tiles_x * a.tiles_y * n_planes;
@@ -934,8 +1053,10 @@ void launch_fwd_t(const FwdTaps &ft, FwdArgs a, int n_planes, int sm_count, cuda
     const bool one_per_cta = !persist || a.n_tiles < sm_count * per_sm;
     a.grid3d = one_per_cta && n_planes <= 65535 && a.tiles_y <= 65535;
     const dim3 grid = a.grid3d ? dim3(a.tiles_x, a.tiles_y, n_planes) : dim3(one_per_cta ? a.n_tiles : sm_count * per_sm);
+    CUtensorMap tmap;
+    a.use_tma = a.grid3d && make_tmap(&tmap, a.in, n_planes, g.pin, g.rin_y);
     cudaFuncSetAttribute(k_dwt_fwd<T, J, MULTI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    k_dwt_fwd<T, J, MULTI, MODE><<<grid, T::NT, bytes, s>>>(ft, a);
+    k_dwt_fwd<T, J, MULTI, MODE><<<grid, T::NT, bytes, s>>>(ft, a, tmap);
 }
 template <int J, bool MULTI>
 void launch_fwd_j(const FwdTaps &ft, const FwdArgs &a, int n_planes, int exact, int sm_count, cudaStream_t s)
@@ -968,7 +1089,7 @@ template <class T, int JH, bool MULTI, int MODE>
 void launch_inv_t(const InvTaps &it, InvArgs a, int n_planes, int sm_count, cudaStream_t s)
 {
     const InvGeom g(a.Hp, T::TY, T::TX, T::R1);
-    const size_t bytes = g.smem_bytes();
+    const size_t bytes = g.smem_bytes() + 128;
     a.tiles_x = (a.out.cols + 2 * T::TX - 1) / (2 * T::TX);
     a.tiles_y = (a.out.rows + 2 * T::TY - 1) / (2 * T::TY);
     a.n_tiles = a.tiles_x * a.tiles_y * n_planes;
@@ -979,8 +1100,14 @@ void launch_inv_t(const InvTaps &it, InvArgs a, int n_planes, int sm_count, cuda
     const bool one_per_cta = !persist || a.n_tiles < sm_count * per_sm;
     a.grid3d = one_per_cta && n_planes <= 65535 && a.tiles_y <= 65535;
     const dim3 grid = a.grid3d ? dim3(a.tiles_x, a.tiles_y, n_planes) : dim3(one_per_cta ? a.n_tiles : sm_count * per_sm);
+    InvMaps maps;
+    // cA is read with the detail bands' logical size (the caller's buffer may be the larger reconstruction target)
+    B2sImg ca = a.cA;
+    ca.rows = a.cH.rows; ca.cols = a.cH.cols;
+    a.use_tma = a.grid3d && make_tmap(&maps.m[0], ca, n_planes, g.ps, g.rq) && make_tmap(&maps.m[1], a.cV, n_planes, g.ps, g.rq) &&
+                make_tmap(&maps.m[2], a.cH, n_planes, g.ps, g.rq) && make_tmap(&maps.m[3], a.cD, n_planes, g.ps, g.rq);
     cudaFuncSetAttribute(k_dwt_inv<T, JH, MULTI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    k_dwt_inv<T, JH, MULTI, MODE><<<grid, T::NT, bytes, s>>>(it, a);
+    k_dwt_inv<T, JH, MULTI, MODE><<<grid, T::NT, bytes, s>>>(it, a, maps);
 }
 template <int JH, bool MULTI>
 void launch_inv_j(const InvTaps &it, const InvArgs &a, int n_planes, int exact, int sm_count, cudaStream_t s)
@@ -1093,7 +1220,7 @@ int b2s_dwt_max_smem(int F)
     pick_inv_chunk(F / 2, &JH, &nchi);
     const size_t a = FwdGeom(J * nch, FwdTile0::TY, FwdTile0::TX).smem_bytes();
     const size_t b = InvGeom(JH * nchi, InvTile0::TY, InvTile0::TX, InvTile0::R1).smem_bytes();
-    return (int)((a > b ? a : b) + 1024);
+    return (int)((a > b ? a : b) + 128 + 1024);
 }
 
 size_t b2s_dwt_scratch_floats(int F, int ny, int nx)

@@ -13,7 +13,8 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("B200STRIPE_LIB", _PKG.parent / "lib" / "libb200stripe.so"))
 
 U8, U16, F32 = 0, 1, 2
-PAD_MODES = {"reflect": 0, "wrap": 1, "symmetric": 2, "edge": 3, "constant": 4}
+PAD_MODES = {"reflect": 0, "wrap": 1, "symmetric": 2, "edge": 3, "constant": 4, "linear_ramp": 5, "maximum": 6, "mean": 7,
+             "median": 8, "minimum": 9, "empty": 10}
 DS_METHODS = {"max": 0, "min": 1, "mean": 2, "median": 3}
 STAGE = {"all": 0, "prologue": 1, "forward": 2, "notch": 3, "inverse": 4}
 N_KERNEL_CLASSES = 8
@@ -63,7 +64,7 @@ EXPORTS = (
     "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_plan_set_aa_weights", "b2s_run",
     "b2s_host_alloc", "b2s_host_free", "b2s_launch_count", "b2s_timing_enable", "b2s_timing_read",
     "b2s_debug_read", "b2s_debug_math",
-    "b2s_resize_aa", "b2s_isotropic_xy", "b2s_isotropic_z", "b2s_isotropic_convert", "b2s_is_uniform",
+    "b2s_resize_aa", "b2s_isotropic_xy", "b2s_isotropic_z", "b2s_isotropic_convert", "b2s_is_uniform", "b2s_histogram",
 )
 
 _lib = None
@@ -106,6 +107,7 @@ def lib():
             L.b2s_resize_aa.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
             L.b2s_isotropic_z.argtypes = [vp, vp, i32, i64, i32, vp, vp]
             L.b2s_isotropic_convert.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+            L.b2s_histogram.argtypes = [vp, vp, i32, i32, i64, i32, vp, i32, i32, vp]
             L.b2s_is_uniform.argtypes = [vp, vp, i32, i64, vp, vp]
             L.b2s_run.argtypes = [vp, vp, vp, i64, i32, i32, vp]
             L.b2s_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]

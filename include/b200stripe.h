@@ -35,7 +35,10 @@ typedef enum b2s_dtype { B2S_U8 = 0, B2S_U16 = 1, B2S_F32 = 2 } b2s_dtype;
 
 /* numpy.pad modes accepted by filter_streaks (pystripe/core.py:1088-1089). */
 typedef enum b2s_pad_mode {
-    B2S_PAD_REFLECT = 0, B2S_PAD_WRAP = 1, B2S_PAD_SYMMETRIC = 2, B2S_PAD_EDGE = 3, B2S_PAD_CONSTANT = 4
+    B2S_PAD_REFLECT = 0, B2S_PAD_WRAP = 1, B2S_PAD_SYMMETRIC = 2, B2S_PAD_EDGE = 3, B2S_PAD_CONSTANT = 4,
+    /* modes whose pad area is computed from the image (numpy defaults: stat_length=None, end_values=0) */
+    B2S_PAD_LINEAR_RAMP = 5, B2S_PAD_MAXIMUM = 6, B2S_PAD_MEAN = 7, B2S_PAD_MEDIAN = 8, B2S_PAD_MINIMUM = 9,
+    B2S_PAD_EMPTY = 10 /* numpy leaves the pad area uninitialised; zeros here */
 } b2s_pad_mode;
 
 typedef enum b2s_ds_method { B2S_DS_MAX = 0, B2S_DS_MIN = 1, B2S_DS_MEAN = 2, B2S_DS_MEDIAN = 3 } b2s_ds_method;
@@ -220,6 +223,15 @@ int b2s_isotropic_z(b2s_context *ctx, const float *d_in, int n_in, int64_t plane
  * convert_to_16bit_fun (core.py:397-399), 2 = convert_to_8bit_fun with `shift` (core.py:402-423), 4 = astype(uint8).
  * d_out: uint16 (mode 1) or uint8. */
 int b2s_isotropic_convert(b2s_context *ctx, const float *d_in, int64_t n, int mode, int shift, void *d_out, void *stream);
+
+/* replaces: the pixel pass of `estimate_img_related_params` (process_images.py:594-659), which feeds log1p of a plane to
+ * skimage.filters.threshold_multiotsu and to a masked percentile (:320-331).  Both are functions of the intensity
+ * histogram: this entry ADDS the exact histogram of n_planes planes of uint8 / uint16 pixels (plane_elems each) into
+ * `hist`: 65 536 uint64 counters when per_plane == 0, n_planes x 65 536 when per_plane != 0.  in / hist may be host or
+ * device pointers.  Histograms are additive, so a whole stack sharded over GPUs needs one all-reduce of 65 536 counters
+ * (the host side, pystripe/stack_stats.py, does it with torch.distributed). */
+int b2s_histogram(b2s_context *ctx, const void *in, int in_is_device, int dtype, int64_t plane_elems, int n_planes,
+                  uint64_t *hist, int hist_is_device, int per_plane, void *stream);
 
 /* replaces: is_uniform_2d / is_uniform_3d (core.py:106-121) on a device array of n elements: *uniform = 1 when all equal */
 int b2s_is_uniform(b2s_context *ctx, const void *d_in, int dtype, int64_t n, int32_t *uniform, void *stream);

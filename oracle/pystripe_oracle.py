@@ -498,3 +498,76 @@ def process_img(img, flat=None, gaussian_filter_2d=False, down_sample=None, down
     if rotate in (90, 180, 270):
         img = np.rot90(img, rotate // 90)
     return np.ascontiguousarray(img)
+
+
+# ---- stack statistics (process_images.py:320-331, 594-659) ---------------------------------------
+def threshold_multiotsu(image, classes=4, nbins=256):
+    """skimage.filters.threshold_multiotsu (skimage is absent: PARITY UNPINNED against skimage itself).  Restated from the
+    published algorithm — skimage/filters/thresholding.py + _multiotsu.pyx: 256-bin np.histogram of the image, float32
+    probabilities, cumulative zeroth / first moments, between-class-variance look-up table, exhaustive recursive search
+    (first maximum wins).  Deliberately written as the plain scalar loops of the Cython source; the product's vectorised
+    search (pystripe/stack_stats.py) and a float64 brute force are checked against it in tests/test_stack_stats.py."""
+    image = np.asarray(image)
+    hist, bin_edges = np.histogram(image.reshape(-1), bins=nbins, range=None)
+    bin_centers = (bin_edges[:-1] + bin_edges[1:]) / 2.0
+    prob = (hist / np.sum(hist)).astype(np.float32)
+    if np.count_nonzero(prob) < classes:
+        raise ValueError("cannot be thresholded in %d classes" % classes)
+    f32 = np.float32
+    n = nbins
+    thresh_count = classes - 1
+    var = np.zeros(n * (n + 1) // 2, np.float32)
+    m0 = np.empty(n, np.float32)
+    m1 = np.empty(n, np.float32)
+    m0[0] = prob[0]
+    m1[0] = prob[0]
+    for i in range(1, n):
+        m0[i] = m0[i - 1] + prob[i]
+        m1[i] = m1[i - 1] + f32(i) * prob[i]
+        if m0[i] > 0:
+            var[i] = (m1[i] * m1[i]) / m0[i]
+    idx = n
+    for i in range(1, n):
+        zi = m0[i:] - m0[i - 1]
+        fi = m1[i:] - m1[i - 1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            row = np.where(zi > 0, (fi * fi) / np.where(zi > 0, zi, f32(1)), f32(0)).astype(np.float32)
+        var[idx:idx + n - i] = row
+        idx += n - i
+
+    def lut(i, j):
+        return var[(i * (2 * n - i + 1)) // 2 + j - i]
+
+    # the recursion of _set_thresh_indices_lut for three thresholds; the innermost loop (c2) is evaluated as one float32
+    # vector expression with the same association order: (var(0, c0) + var(c2 + 1, n - 1)) + var(c0 + 1, c1) + var(c1 + 1, c2)
+    assert thresh_count == 3
+    best = [f32(0), None]
+    tail = np.array([lut(c2 + 1, n - 1) for c2 in range(n - 1)], dtype=np.float32)
+    for c0 in range(0, n - 3):
+        head = lut(0, c0)
+        for c1 in range(c0 + 1, n - 2):
+            c2 = np.arange(c1 + 1, n - 1)
+            base = (c1 + 1) * (2 * n - (c1 + 1) + 1) // 2 - (c1 + 1)
+            sigma = ((head + tail[c2]).astype(np.float32) + lut(c0 + 1, c1)).astype(np.float32)
+            sigma = (sigma + var[base + c2]).astype(np.float32)
+            k = int(np.argmax(sigma))                      # first maximum, as the strict `>` of the scalar loop keeps
+            if sigma[k] > best[0]:
+                best[0] = sigma[k]
+                best[1] = [c0, c1, int(c2[k])]
+    return tuple(np.float32(bin_centers[i]) for i in best[1])
+
+
+def estimate_bit_shift(img, threshold, percentile=99.9):
+    """process_images.py:320-331 on the float32 log image."""
+    try:
+        sel = img[img > threshold]
+        if sel.size == 0:
+            raise ValueError
+        upper_bound = _percentile_numba(sel, percentile)
+    except (ValueError, AssertionError):
+        upper_bound = np.max(img)
+    upper_bound = int(np.round(np.expm1(upper_bound)))
+    for b in range(0, 9):
+        if 256 * 2 ** b >= upper_bound:
+            return b
+    return 8

@@ -61,6 +61,40 @@ def test_prologue_log1p_and_padding_bit_exact(mode):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("mode", ["linear_ramp", "maximum", "mean", "median", "minimum"])
+@pytest.mark.parametrize("shape", [(70, 91), (131, 300)])
+def test_computed_padding_modes_bit_exact(mode, shape):
+    """numpy.pad modes that compute their pad area (core.py:1088-1110 accepts all eleven): column statistics over the
+    original rows first, then row statistics over every row of the padded array; float32 rounding as numpy's reductions
+    (sequential down a column, pairwise along a row), linear ramps in float64 with numpy's zero-step switch."""
+    for variant in range(2):
+        img = synth.plane(5 + variant, shape)
+        if variant:
+            img[0, 3] = 0          # a zero edge value: numpy.linspace switches the whole side to (i / n) * edge
+            img[-1, -1] = 0
+            img[7, 0] = 0
+        plan = _plan(img.shape, 1, sigma=(40, 40), padding_mode=mode, stop_after=1)
+        plan.run_host(np.stack([img, img[::-1].copy()]))
+        base, py, px = orc.padded_geometry(img.shape, (40, 40), mode)
+        for z, src in enumerate((img, img[::-1])):
+            got = plan.debug_read(0, plane=z)
+            ref = np.pad(orc.log1p_f32(src.astype(np.float32)), ((base, base + py), (base, base + px)), mode=mode)
+            assert np.array_equal(got, ref), (mode, shape, variant, z, float(np.abs(got - ref).max()))
+
+
+def test_filter_streaks_with_computed_padding_modes():
+    from pystripe import core
+    img = synth.plane(9, (150, 180))
+    for mode in ("mean", "maximum", "linear_ramp", "median", "minimum"):
+        got = core.filter_streaks(img, sigma=(20, 20), wavelet="db5", padding_mode=mode)
+        ref = orc.filter_streaks(img, sigma=(20, 20), wavelet="db5", padding_mode=mode)
+        _cmp_int(f"pad_mode/{mode}", got, ref)
+    out = core.filter_streaks(img, sigma=(20, 20), wavelet="db5", padding_mode="empty")     # numpy: uninitialised pad area
+    assert out.shape == img.shape and out.dtype == img.dtype
+    with pytest.raises(RuntimeError):
+        core.filter_streaks(img, sigma=(20, 20), padding_mode="no_such_mode")
+
+
 @pytest.mark.parametrize("shape,wavelet,sigma", [((96, 128), "db10", (24, 24)), ((70, 91), "db5", (10, 10)),
                                                   ((160, 200), "db2", (64, 64)), ((128, 96), "db9", (16, 16)),
                                                   ((200, 300), "db16", (30, 30)),
