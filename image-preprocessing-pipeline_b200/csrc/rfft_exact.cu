@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr int kXT = 512;   // threads per CTA
+constexpr int kXT = 512;   // largest CTA (launch bound); the launch picks 256 .. 512 threads per length (xfft_threads)
 
 struct Ctx { int r, item0, istride, GP; };
 // one pass of the real transform.  kind: 2,3,4,5 = radix, 6 = generic, 7 = Bluestein; m_*: fdiv magics for l1, ni = (ido-1)/2,
@@ -261,7 +261,7 @@ __device__ void radfg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
     const int ido = P.ido, ip = P.ip, l1 = P.l1;
     const int cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
     const int nlb = (ipph - 1 + LB - 1) / LB;
-    for (int i = threadIdx.x; i < nlb * LB * (kRow / 2); i += kXT)   // visible after the next barrier
+    for (int i = threadIdx.x; i < nlb * LB * (kRow / 2); i += blockDim.x)   // visible after the next barrier
         reinterpret_cast<float4 *>(sgt)[i] = __ldg(reinterpret_cast<const float4 *>(gt) + i);
 #define CC(a, b, k_) cc[IDX((a) + ido * ((b) + cdim * (k_)))]
 #define CH(a, b, k_) ch[IDX((a) + ido * ((b) + l1 * (k_)))]
@@ -475,7 +475,7 @@ __device__ void radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
     const int ido = P.ido, ip = P.ip, l1 = P.l1;
     const int cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
     const int nlb = (ipph - 1 + LB - 1) / LB;
-    for (int i = threadIdx.x; i < nlb * LB * (kRow / 2); i += kXT)   // visible after the next barrier
+    for (int i = threadIdx.x; i < nlb * LB * (kRow / 2); i += blockDim.x)   // visible after the next barrier
         reinterpret_cast<float4 *>(sgt)[i] = __ldg(reinterpret_cast<const float4 *>(gt) + i);
 #define CC(a, b, k_) cc[IDX((a) + ido * ((b) + cdim * (k_)))]
 #define CH(a, b, k_) ch[IDX((a) + ido * ((b) + l1 * (k_)))]
@@ -544,13 +544,23 @@ __device__ void radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
 #undef WA
 
 // ================================================================ complex passes (mirror of cfftp pass*)
-__device__ __forceinline__ float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex arithmetic on packed f32x2 registers.  Every component sees the same IEEE operations in the same order as the
+// scalar expressions of pocketfft's cmplx<float> (one rounding per product, one per sum; a - b is a + (-b) and (-a) * b is
+// -(a * b) exactly), at half the instruction count.  Products are formed as fma(a, b, -0.0) with the -0.0 read from
+// constant memory, which ptxas cannot fold: a plain packed multiply followed by a packed add would be re-contracted into
+// FFMA2 even under -fmad=false (see mul2x above).
+__constant__ float2 c_nz2 = {-0.0f, -0.0f};
+__device__ __forceinline__ float2 p_mul(float2 a, float2 b) { return __ffma2_rn(a, b, c_nz2); }
+__device__ __forceinline__ float2 p_muls(float s_, float2 a) { return __ffma2_rn(make_float2(s_, s_), a, c_nz2); }
+__device__ __forceinline__ float2 c_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 c_sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 template <bool FWD>
 __device__ __forceinline__ float2 smul(float2 v1, float2 v2)   // FWD ? v1 * conj(v2) : v1 * v2
 {
-    return FWD ? make_float2(v1.x * v2.x + v1.y * v2.y, v1.y * v2.x - v1.x * v2.y)
-               : make_float2(v1.x * v2.x - v1.y * v2.y, v1.x * v2.y + v1.y * v2.x);
+    // FWD: (v1.x v2.x + v1.y v2.y, v1.y v2.x - v1.x v2.y);  !FWD: (v1.x v2.x - v1.y v2.y, v1.x v2.y + v1.y v2.x)
+    const float2 p = p_mul(v1, make_float2(v2.x, v2.x));
+    const float2 q = p_mul(FWD ? make_float2(v1.y, -v1.x) : make_float2(-v1.y, v1.x), make_float2(v2.y, v2.y));
+    return __fadd2_rn(p, q);
 }
 template <bool FWD>
 __device__ __forceinline__ float2 rotx90(float2 a) { return FWD ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x); }
@@ -558,25 +568,30 @@ template <bool FWD>
 __device__ __forceinline__ float2 rotx45(float2 a)
 {
     const float hsqt2 = 0.707106781186547524400844362104849f;
-    return FWD ? make_float2(hsqt2 * (a.x + a.y), hsqt2 * (a.y - a.x)) : make_float2(hsqt2 * (a.x - a.y), hsqt2 * (a.y + a.x));
+    // FWD: h (a.x + a.y, a.y - a.x);  !FWD: h (a.x - a.y, a.y + a.x)
+    return p_muls(hsqt2, __fadd2_rn(a, FWD ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x)));
 }
 template <bool FWD>
 __device__ __forceinline__ float2 rotx135(float2 a)
 {
     const float hsqt2 = 0.707106781186547524400844362104849f;
-    return FWD ? make_float2(hsqt2 * (a.y - a.x), hsqt2 * (-a.x - a.y)) : make_float2(hsqt2 * (-a.x - a.y), hsqt2 * (a.x - a.y));
+    // FWD: h (a.y - a.x, -a.x - a.y);  !FWD: h (-a.x - a.y, a.x - a.y)
+    return p_muls(hsqt2, FWD ? __fadd2_rn(make_float2(a.y, -a.x), make_float2(-a.x, -a.y))
+                             : __fadd2_rn(make_float2(-a.x, a.x), make_float2(-a.y, -a.y)));
 }
 #define CPM(a, b, cc_, d) { a = c_add(cc_, d); b = c_sub(cc_, d); }
 #define CWA(x, i) __ldg(wa + (i) - 1 + (x) * (ido - 1))
 
 // one complex pass of radix IP over `ninst` transforms of length n2 per row; element e of instance q at (q*n2 + e)
 template <int IP, bool FWD>
-__device__ void cpass(const Ctx &c, int ido, int l1, const float2 *cc0, float2 *ch0, const float2 *wa, int ninst, int n2)
+__device__ void cpass(const Ctx &c, int ido, int l1, const float2 *cc0, float2 *ch0, const float2 *wa, int ninst, int n2,
+                      unsigned m_ido, unsigned m_per)
 {
     const int per = l1 * ido;
     FOR_ITEMS(it, ninst * per) {
-        const int q = it / per, rem = it - q * per;
-        const int k = rem / ido, i = rem - k * ido;
+        // (instance, k, i) of the butterfly: divisions by the pass constants through their magic multipliers
+        const int q = ninst == 1 ? 0 : fdiv(it, m_per), rem = it - q * per;
+        const int k = fdiv(rem, m_ido), i = rem - k * ido;
         const float2 *cc = cc0 + (size_t)q * n2 * c.GP;
         float2 *ch = ch0 + (size_t)q * n2 * c.GP;
 #define CCC(a, b, k_) cc[IDX((a) + ido * ((b) + IP * (k_)))]
@@ -591,8 +606,8 @@ __device__ void cpass(const Ctx &c, int ido, int l1, const float2 *cc0, float2 *
             float2 t1, t2;
             CPM(t1, t2, CCC(i, 1, k), CCC(i, 2, k))
             CCH(i, k, 0) = c_add(t0, t1);
-            const float2 ca = make_float2(t0.x + t1.x * tw1r, t0.y + t1.y * tw1r);
-            const float2 cb = make_float2(-t2.y * tw1i, t2.x * tw1i);
+            const float2 ca = c_add(t0, p_muls(tw1r, t1));
+            const float2 cb = p_muls(tw1i, make_float2(-t2.y, t2.x));
             if (i == 0) { CPM(CCH(0, k, 1), CCH(0, k, 2), ca, cb) }
             else {
                 CCH(i, k, 1) = smul<FWD>(c_add(ca, cb), CWA(0, i));
@@ -621,14 +636,12 @@ __device__ void cpass(const Ctx &c, int ido, int l1, const float2 *cc0, float2 *
             float2 t1, t2, t3, t4;
             CPM(t1, t4, CCC(i, 1, k), CCC(i, 4, k))
             CPM(t2, t3, CCC(i, 2, k), CCC(i, 3, k))
-            CCH(i, k, 0) = make_float2(t0.x + t1.x + t2.x, t0.y + t1.y + t2.y);
+            CCH(i, k, 0) = c_add(c_add(t0, t1), t2);
 #define STEP5(u1, u2, twar, twbr, twai, twbi)                                           \
             {                                                                           \
-                float2 ca, cb;                                                          \
-                ca.x = t0.x + twar * t1.x + twbr * t2.x;                                \
-                ca.y = t0.y + twar * t1.y + twbr * t2.y;                                \
-                cb.y = twai * t4.x twbi * t3.x;                                         \
-                cb.x = -(twai * t4.y twbi * t3.y);                                      \
+                const float2 ca = c_add(c_add(t0, p_muls(twar, t1)), p_muls(twbr, t2)); \
+                const float2 u_ = c_add(p_muls((twai), t4), p_muls((twbi), t3));        \
+                const float2 cb = make_float2(-u_.y, u_.x);                             \
                 if (i == 0) { CPM(CCH(0, k, u1), CCH(0, k, u2), ca, cb) }               \
                 else {                                                                  \
                     CCH(i, k, u1) = smul<FWD>(c_add(ca, cb), CWA(u1 - 1, i));           \
@@ -650,14 +663,12 @@ __device__ void cpass(const Ctx &c, int ido, int l1, const float2 *cc0, float2 *
             CPM(t2, t7, CCC(i, 1, k), CCC(i, 6, k))
             CPM(t3, t6, CCC(i, 2, k), CCC(i, 5, k))
             CPM(t4, t5, CCC(i, 3, k), CCC(i, 4, k))
-            CCH(i, k, 0) = make_float2(t1.x + t2.x + t3.x + t4.x, t1.y + t2.y + t3.y + t4.y);
+            CCH(i, k, 0) = c_add(c_add(c_add(t1, t2), t3), t4);
 #define STEP7(u1, u2, x1, x2, x3, y1, y2, y3)                                           \
             {                                                                           \
-                float2 ca, cb;                                                          \
-                ca.x = t1.x + x1 * t2.x + x2 * t3.x + x3 * t4.x;                        \
-                ca.y = t1.y + x1 * t2.y + x2 * t3.y + x3 * t4.y;                        \
-                cb.y = y1 * t7.x y2 * t6.x y3 * t5.x;                                   \
-                cb.x = -(y1 * t7.y y2 * t6.y y3 * t5.y);                                \
+                const float2 ca = c_add(c_add(c_add(t1, p_muls(x1, t2)), p_muls(x2, t3)), p_muls(x3, t4)); \
+                const float2 u_ = c_add(c_add(p_muls((y1), t7), p_muls((y2), t6)), p_muls((y3), t5));     \
+                const float2 cb = make_float2(-u_.y, u_.x);                             \
                 if (i == 0) { CPM(CCH(0, k, u1), CCH(0, k, u2), ca, cb) }               \
                 else {                                                                  \
                     CCH(i, k, u1) = smul<FWD>(c_add(ca, cb), CWA(u1 - 1, i));           \
@@ -717,14 +728,14 @@ __device__ void cpass(const Ctx &c, int ido, int l1, const float2 *cc0, float2 *
             CPM(t4, t9, CCC(i, 3, k), CCC(i, 8, k))
             CPM(t5, t8, CCC(i, 4, k), CCC(i, 7, k))
             CPM(t6, t7, CCC(i, 5, k), CCC(i, 6, k))
-            CCH(i, k, 0) = make_float2(t1.x + t2.x + t3.x + t4.x + t5.x + t6.x, t1.y + t2.y + t3.y + t4.y + t5.y + t6.y);
+            CCH(i, k, 0) = c_add(c_add(c_add(c_add(c_add(t1, t2), t3), t4), t5), t6);
 #define STEP11(u1, u2, x1, x2, x3, x4, x5, y1, y2, y3, y4, y5)                                      \
             {                                                                                       \
-                float2 ca, cb;                                                                      \
-                ca.x = t1.x + x1 * t2.x + x2 * t3.x + x3 * t4.x + x4 * t5.x + x5 * t6.x;            \
-                ca.y = t1.y + x1 * t2.y + x2 * t3.y + x3 * t4.y + x4 * t5.y + x5 * t6.y;            \
-                cb.y = y1 * t11.x y2 * t10.x y3 * t9.x y4 * t8.x y5 * t7.x;                         \
-                cb.x = -(y1 * t11.y y2 * t10.y y3 * t9.y y4 * t8.y y5 * t7.y);                      \
+                const float2 ca = c_add(c_add(c_add(c_add(c_add(t1, p_muls(x1, t2)), p_muls(x2, t3)), p_muls(x3, t4)), \
+                                              p_muls(x4, t5)), p_muls(x5, t6));                     \
+                const float2 u_ = c_add(c_add(c_add(c_add(p_muls((y1), t11), p_muls((y2), t10)), p_muls((y3), t9)), \
+                                              p_muls((y4), t8)), p_muls((y5), t7));                 \
+                const float2 cb = make_float2(-u_.y, u_.x);                                         \
                 if (i == 0) { CPM(CCH(0, k, u1), CCH(0, k, u2), ca, cb) }                           \
                 else {                                                                              \
                     CCH(i, k, u1) = smul<FWD>(c_add(ca, cb), CWA(u1 - 1, i));                       \
@@ -746,6 +757,7 @@ __device__ void cpass(const Ctx &c, int ido, int l1, const float2 *cc0, float2 *
 struct XBlue {
     int ip, n2, nf;
     int fct[12], tw[12];   // complex sub-plan: factors in pass order, twiddle offsets (floats) into the table
+    unsigned m_ido[12], m_per[12], m_n2;   // fdiv magics of ido, l1 * ido per pass and of n2
     int bk, bkf;           // offsets (floats) of bk[ip] and bkf[n2/2+1] (complex)
     int inst;              // Bluestein transforms evaluated concurrently per row
 };
@@ -776,7 +788,7 @@ __device__ void cpassg(const Ctx &c, int ido, int ip, int l1, float2 *cc, float2
 #define GCX(a, b, k_) cc[IDX((a) + ido * ((b) + l1 * (k_)))]
 #define GCX2(a, b) cc[IDX((a) + idl1 * (b))]
 #define GCH2(a, b) ch[IDX((a) + idl1 * (b))]
-    for (int i = threadIdx.x; i < ip; i += kXT) {
+    for (int i = threadIdx.x; i < ip; i += blockDim.x) {
         const float2 w = __ldg(csarr + i);
         wal[i] = i == 0 ? make_float2(1.f, 0.f) : make_float2(w.x, FWD ? -w.y : w.y);
     }
@@ -869,13 +881,13 @@ __device__ __forceinline__ void cfft_all(const Ctx &c, const XBlue &b, const flo
         const float2 *wa = reinterpret_cast<const float2 *>(tab + b.tw[f]);
         bool swap = true;
         switch (ip) {
-        case 2: cpass<2, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
-        case 3: cpass<3, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
-        case 4: cpass<4, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
-        case 5: cpass<5, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
-        case 7: cpass<7, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
-        case 8: cpass<8, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
-        case 11: cpass<11, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2); break;
+        case 2: cpass<2, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2, b.m_ido[f], b.m_per[f]); break;
+        case 3: cpass<3, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2, b.m_ido[f], b.m_per[f]); break;
+        case 4: cpass<4, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2, b.m_ido[f], b.m_per[f]); break;
+        case 5: cpass<5, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2, b.m_ido[f], b.m_per[f]); break;
+        case 7: cpass<7, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2, b.m_ido[f], b.m_per[f]); break;
+        case 8: cpass<8, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2, b.m_ido[f], b.m_per[f]); break;
+        case 11: cpass<11, FWD>(c, ido, l1, cur, nxt, wa, ninst, b.n2, b.m_ido[f], b.m_per[f]); break;
         default:
             if (OUTER) {
                 if (ip >= 110) { cblue<FWD>(c, *blue, tab, ido, l1, cur, nxt, wa, BX0, BX1); swap = l1 > 1; }
@@ -905,7 +917,7 @@ __device__ void cblue(const Ctx &c, const XBlue &b, const float *tab, int ido, i
     for (int base = 0; base < total; base += b.inst) {
         const int ninst = min(b.inst, total - base);
         FOR_ITEMS(it, ninst * n2) {
-            const int q = it / n2, m = it - q * n2;
+            const int q = ninst == 1 ? 0 : fdiv(it, b.m_n2), m = it - q * n2;
             const int inst = base + q, k = inst / ido, i = inst - k * ido;
             const float2 a0 = smul<FWD>(BCC(i, 0, k), __ldg(bk));
             X0[IDX(q * n2 + m)] = m < ip ? smul<FWD>(BCC(i, m, k), __ldg(bk + m)) : make_float2(a0.x * 0.f, a0.y * 0.f);
@@ -914,14 +926,14 @@ __device__ void cblue(const Ctx &c, const XBlue &b, const float *tab, int ido, i
         float2 *cur = X0, *nxt = X1;
         cfft_all<true>(c, b, tab, cur, nxt, ninst);
         FOR_ITEMS(it, ninst * n2) {
-            const int q = it / n2, m = it - q * n2;
+            const int q = ninst == 1 ? 0 : fdiv(it, b.m_n2), m = it - q * n2;
             const int mb = 2 * m <= n2 ? m : n2 - m;
             cur[IDX(q * n2 + m)] = smul<!FWD>(cur[IDX(q * n2 + m)], __ldg(bkf + mb));
         }
         __syncthreads();
         cfft_all<false>(c, b, tab, cur, nxt, ninst);
         FOR_ITEMS(it, ninst * ip) {
-            const int q = it / ip, m = it - q * ip;
+            const int q = ninst == 1 ? 0 : it / ip, m = it - q * ip;
             const int inst = base + q, k = inst / ido, i = inst - k * ido;
             float2 w = __ldg(bk + m);
             if (i != 0 && m != 0) {
@@ -954,8 +966,8 @@ __device__ void rblue(const Ctx &c, const XBlue &b, const float *tab, int ido, i
         const int ninst = min(b.inst, total - base);
         // ---- a_m = x_m * conj/plain(b_m), zero padded
         FOR_ITEMS(it, ninst * n2) {
-            const int q = it / n2, m = it - q * n2;
-            const int inst = base + q, k = inst / per_k, ii = inst - k * per_k, i = 2 * ii, ic = ido - i;
+            const int q = ninst == 1 ? 0 : fdiv(it, b.m_n2), m = it - q * n2;
+            const int inst = base + q, k = per_k == 1 ? inst : inst / per_k, ii = inst - k * per_k, i = 2 * ii, ic = ido - i;
             float2 x0;   // element 0 of the transform's input
             if (FWD) {
 #define CC(a, k_, m_) cc[IDX((a) + ido * ((k_) + l1 * (m_)))]
@@ -990,7 +1002,7 @@ __device__ void rblue(const Ctx &c, const XBlue &b, const float *tab, int ido, i
         cfft_all<true>(c, b, tab, cur, nxt, ninst);
         // ---- convolution: multiply by the (half-stored, symmetric) transform of b
         FOR_ITEMS(it, ninst * n2) {
-            const int q = it / n2, m = it - q * n2;
+            const int q = ninst == 1 ? 0 : fdiv(it, b.m_n2), m = it - q * n2;
             const int mb = 2 * m <= n2 ? m : n2 - m;
             cur[IDX(q * n2 + m)] = smul<!FWD>(cur[IDX(q * n2 + m)], __ldg(bkf + mb));
         }
@@ -998,8 +1010,8 @@ __device__ void rblue(const Ctx &c, const XBlue &b, const float *tab, int ido, i
         cfft_all<false>(c, b, tab, cur, nxt, ninst);
         // ---- multiply by b_k and scatter into the pass output
         FOR_ITEMS(it, ninst * ip) {
-            const int q = it / ip, m = it - q * ip;
-            const int inst = base + q, k = inst / per_k, ii = inst - k * per_k, i = 2 * ii, ic = ido - i;
+            const int q = ninst == 1 ? 0 : it / ip, m = it - q * ip;
+            const int inst = base + q, k = per_k == 1 ? inst : inst / per_k, ii = inst - k * per_k, i = 2 * ii, ic = ido - i;
             const float2 res = smul<FWD>(cur[IDX(q * n2 + m)], __ldg(bk + m));
             if (FWD) {
 #define CH(a, m_, k_) ch[IDX((a) + ido * ((m_) + ip * (k_)))]
@@ -1038,7 +1050,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
     Ctx c;
     c.r = threadIdx.x & (G - 1);
     c.item0 = threadIdx.x >> a.lgG;
-    c.istride = kXT >> a.lgG;
+    c.istride = blockDim.x >> a.lgG;
     c.GP = GP;
 
     float *plane = a.img.ptr + (size_t)blockIdx.y * a.img.plane_stride;
@@ -1049,12 +1061,12 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
         // ---- gather (rows beyond the sub-band are zero sequences)
         // a warp covers 32/G consecutive elements of G rows: each row contributes one 16..128-byte run
         if (!a.along_cols) {
-            for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
+            for (int idx = threadIdx.x; idx < G * n; idx += blockDim.x) {
                 const int e = idx >> a.lgG, rr = idx & (G - 1);
                 A[idx] = rr < ns ? plane[(size_t)(s0 + rr) * a.img.pitch + e] : 0.f;
             }
         } else {
-            for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
+            for (int idx = threadIdx.x; idx < G * n; idx += blockDim.x) {
                 const int e = idx >> a.lgG, rr = idx & (G - 1);
                 A[idx] = rr < ns ? plane[(size_t)e * a.img.pitch + s0 + rr] : 0.f;
             }
@@ -1078,7 +1090,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
             if (swap) { float *t = p1; p1 = p2; p2 = t; }
         }
         // ---- notch on packed positions (core.py:752: spec *= g)
-        for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
+        for (int idx = threadIdx.x; idx < G * n; idx += blockDim.x) {
             const int e = idx >> a.lgG, rr = idx & (G - 1);
             p1[idx] = p1[idx] * __ldg(a.g + e);
         }
@@ -1100,12 +1112,12 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
         }
         // ---- scale by 1/n (copy_and_norm) and scatter
         if (!a.along_cols) {
-            for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
+            for (int idx = threadIdx.x; idx < G * n; idx += blockDim.x) {
                 const int e = idx >> a.lgG, rr = idx & (G - 1);
                 if (rr < ns) plane[(size_t)(s0 + rr) * a.img.pitch + e] = a.fct * p1[idx];
             }
         } else {
-            for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
+            for (int idx = threadIdx.x; idx < G * n; idx += blockDim.x) {
                 const int e = idx >> a.lgG, rr = idx & (G - 1);
                 if (rr < ns) plane[(size_t)e * a.img.pitch + s0 + rr] = a.fct * p1[idx];
             }
@@ -1143,7 +1155,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_cplx(const __grid_constant__ X
     Ctx c;
     c.r = threadIdx.x & (G - 1);
     c.item0 = threadIdx.x >> a.lgG;
-    c.istride = kXT >> a.lgG;
+    c.istride = blockDim.x >> a.lgG;
     c.GP = G;
     const float2 *roots = reinterpret_cast<const float2 *>(a.tab + a.roots);
     float *plane = a.img.ptr + (size_t)blockIdx.y * a.img.plane_stride;
@@ -1151,7 +1163,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_cplx(const __grid_constant__ X
         const int s0 = grp * G;
         const int ns = min(G, a.nseq - s0);
         __syncthreads();
-        for (int idx = threadIdx.x; idx < G * h; idx += kXT) {
+        for (int idx = threadIdx.x; idx < G * h; idx += blockDim.x) {
             const int m = idx >> a.lgG, rr = idx & (G - 1);
             float2 v = make_float2(0.f, 0.f);
             if (rr < ns) {
@@ -1191,7 +1203,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_cplx(const __grid_constant__ X
         }
         __syncthreads();
         cfft_all<false, true>(c, a.cp, a.tab, cur, nxt, 1, a.cs, wal, &a.blue, BX0, BX1);
-        for (int idx = threadIdx.x; idx < G * h; idx += kXT) {
+        for (int idx = threadIdx.x; idx < G * h; idx += blockDim.x) {
             const int m = idx >> a.lgG, rr = idx & (G - 1);
             if (rr >= ns) continue;
             const float2 v = cur[idx];
@@ -1208,12 +1220,12 @@ __global__ void __launch_bounds__(kXT) k_blue_setup(XBlue b, const float *tab, c
     extern __shared__ __align__(16) float xs[];
     float2 *X0 = reinterpret_cast<float2 *>(xs), *X1 = X0 + b.n2;
     Ctx c;
-    c.r = 0; c.item0 = threadIdx.x; c.istride = kXT; c.GP = 1;
-    for (int m = threadIdx.x; m < b.n2; m += kXT) X0[m] = tbkf[m];
+    c.r = 0; c.item0 = threadIdx.x; c.istride = blockDim.x; c.GP = 1;
+    for (int m = threadIdx.x; m < b.n2; m += blockDim.x) X0[m] = tbkf[m];
     __syncthreads();
     float2 *cur = X0, *nxt = X1;
     cfft_all<true>(c, b, tab, cur, nxt, 1);
-    for (int m = threadIdx.x; m < b.n2 / 2 + 1; m += kXT) out[m] = cur[m];
+    for (int m = threadIdx.x; m < b.n2 / 2 + 1; m += blockDim.x) out[m] = cur[m];
 }
 
 // ================================================================ host: plan + tables
@@ -1269,6 +1281,20 @@ struct SinCos {
         *im = low ? float(ir + ii) : -float(ir + ii);
     }
 };
+
+// fdiv magics of a complex sub-plan (see fdiv): valid while item * divisor < 2^32, true for every n2 a CTA can hold
+void fill_magics(XBlue &b)
+{
+    auto magic = [](int d) -> unsigned { return d <= 1 ? 0u : (unsigned)((1ULL << 32) / (unsigned)d) + 1u; };
+    int l1 = 1;
+    for (int f = 0; f < b.nf; ++f) {
+        const int ip = b.fct[f], ido = b.n2 / (l1 * ip);
+        b.m_ido[f] = magic(ido);
+        b.m_per[f] = magic(l1 * ido);
+        l1 *= ip;
+    }
+    b.m_n2 = magic(b.n2);
+}
 
 size_t good_size_cmplx(size_t n)
 {
@@ -1383,6 +1409,7 @@ static B2sXfftPlan *xfft_create_cplx(int n)
         }
         l1 *= ip;
     }
+    fill_magics(b);
     std::vector<float2> tbkf;
     XBlue &bl = a.blue;
     if (blue_ip) {   // Bluestein sub-plan: same construction as for the real passes (b2s_xfft_create)
@@ -1412,6 +1439,7 @@ static B2sXfftPlan *xfft_create_cplx(int n)
                            &tab[bl.tw[k] + 2 * ((j - 1) * (ido - 1) + i - 1) + 1]);
             m1 *= ip;
         }
+        fill_magics(bl);
         while (tab.size() & 1) tab.push_back(0.f);
         bl.bk = (int)tab.size();
         tab.resize(tab.size() + 2 * (size_t)blue_ip, 0.f);
@@ -1599,6 +1627,7 @@ B2sXfftPlan *b2s_xfft_create(int n)
                              &tab[b.tw[k] + 2 * ((j - 1) * (ido - 1) + i - 1) + 1]);
             l1 *= ip;
         }
+        fill_magics(b);
         // bk
         while (tab.size() & 1) tab.push_back(0.f);
         b.bk = (int)tab.size();
@@ -1676,6 +1705,16 @@ static int xfft_cap_mult()
     return m > 0 ? m : 1;
 }
 
+// Threads per CTA: kXT unless B2S_XFFT_THREADS says otherwise (a multiple of 32 and of the rows per CTA; tuning knob: a
+// CTA works on threads / G butterfly items at a time, which decides how full the last round of a pass is).
+static int xfft_threads(const B2sXfftPlan *pl)
+{
+    static const int forced = getenv("B2S_XFFT_THREADS") ? atoi(getenv("B2S_XFFT_THREADS")) : 0;
+    const int G = pl->cplx ? pl->ca.G : pl->a.G;
+    if (forced >= 32 && forced <= kXT && forced % 32 == 0 && forced % G == 0) return forced;
+    return kXT;
+}
+
 void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B2sImg &img, int along_cols, int n_planes,
                             int sm_count, cudaStream_t s)
 {
@@ -1690,7 +1729,7 @@ void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B
         int bx = a.groups_per_plane;
         const int cap = (sm_count * xfft_cap_mult() + n_planes - 1) / n_planes;
         if (bx > cap) bx = cap > 0 ? cap : 1;
-        k_notch_cplx<<<dim3(bx, n_planes), kXT, pl->smem, s>>>(a);
+        k_notch_cplx<<<dim3(bx, n_planes), xfft_threads(pl), pl->smem, s>>>(a);
         return;
     }
     XArgs a = pl->a;
@@ -1703,5 +1742,5 @@ void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B
     int bx = a.groups_per_plane;
     const int cap = (sm_count * xfft_cap_mult() + n_planes - 1) / n_planes;
     if (bx > cap) bx = cap > 0 ? cap : 1;
-    k_notch_exact<<<dim3(bx, n_planes), kXT, pl->smem, s>>>(a);
+    k_notch_exact<<<dim3(bx, n_planes), xfft_threads(pl), pl->smem, s>>>(a);
 }
