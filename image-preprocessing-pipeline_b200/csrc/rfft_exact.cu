@@ -23,12 +23,12 @@
 
 namespace {
 
-constexpr int kXT = 512;   // largest CTA (launch bound); the launch picks 256 .. 512 threads per length (xfft_threads)
+constexpr int kXT = 512;   // threads per CTA (compile-time: 448 / 384 / 320 / 256 measured 1 - 10 % slower, profiles/r02_notch_experiments.md)
 
 struct Ctx { int r, item0, istride, GP; };
 // one pass of the real transform.  kind: 2,3,4,5 = radix, 6 = generic, 7 = Bluestein; m_*: fdiv magics for l1, ni = (ido-1)/2,
 // l1*ni, ido, ido*l1
-struct XPass { int kind, ip, l1, ido, tw, cs; unsigned m_l1, m_ni, m_l1ni, m_ido, m_idl1; };
+struct XPass { int kind, ip, l1, ido, tw, cs; unsigned m_l1, m_ni, m_l1ni, m_ido, m_idl1; int lb; };
 #define IDX(e) ((e) * c.GP + c.r)
 #define FOR_ITEMS(it, count) for (int it = c.item0, cnt__ = (count); it < cnt__; it += c.istride)
 #define PM(a, b, cc_, d) { a = (cc_) + (d); b = (cc_) - (d); }
@@ -183,10 +183,12 @@ __device__ void radf5(const Ctx &c, int ido, int l1, const float *cc, float *ch,
 // advance in lock step, so they share packed f32x2 instructions: products as fma(t, v, -0.0) (an exactly rounded
 // product that ptxas cannot re-contract with the following add; -0.0 arrives as a kernel argument), sums as FADD2 in
 // the reference's association order.
-constexpr int LB = 8;
+constexpr int kLBMax = 8;   // outputs (l values) per thread in the O(radix^2) phase: 4 .. 8, chosen per pass (XPass::lb) so that the
+                           // equally heavy items fill whole rounds of the CTA's item slots
 constexpr int kRow = 68;   // float2 entries per table row (radix < 135 => at most 66 columns); compile-time so that the LB rows
                           // a thread reads sit at immediate offsets from one running pointer
 __device__ __forceinline__ float2 mul2x(float2 t, float2 v, float2 nz) { return __ffma2_rn(t, v, nz); }
+template <int LB>
 __device__ __forceinline__ void generic_block(const Ctx &c, const float *src, float *dst, const float2 *sgt, int ip,
                                               int ipph, int idl1, int lb, int ik, float2 nz)
 {
@@ -251,6 +253,18 @@ __device__ __forceinline__ void generic_block(const Ctx &c, const float *src, fl
         if (q < nl) { pd[(l0 + q) * st] = A[q].x; pd[(ip - l0 - q) * st] = A[q].y; }
 }
 
+__device__ __forceinline__ void generic_block_lb(int LBsel, const Ctx &c, const float *src, float *dst, const float2 *sgt, int ip,
+                                                 int ipph, int idl1, int lb, int ik, float2 nz)
+{
+    switch (LBsel) {
+    case 4: generic_block<4>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz); break;
+    case 5: generic_block<5>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz); break;
+    case 6: generic_block<6>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz); break;
+    case 7: generic_block<7>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz); break;
+    default: generic_block<8>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz); break;
+    }
+}
+
 // exact integer division by a per-pass constant: q = umulhi(it, magic), magic = floor(2^32 / d) + 1 (0 encodes d == 1);
 // valid while it * d < 2^32, which the plan builder checks
 __device__ __forceinline__ int fdiv(int it, unsigned magic) { return magic ? (int)__umulhi((unsigned)it, magic) : it; }
@@ -260,8 +274,9 @@ __device__ void radfg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
 {
     const int ido = P.ido, ip = P.ip, l1 = P.l1;
     const int cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
+    const int LB = P.lb;
     const int nlb = (ipph - 1 + LB - 1) / LB;
-    for (int i = threadIdx.x; i < nlb * LB * (kRow / 2); i += blockDim.x)   // visible after the next barrier
+    for (int i = threadIdx.x; i < nlb * LB * (kRow / 2); i += kXT)   // visible after the next barrier
         reinterpret_cast<float4 *>(sgt)[i] = __ldg(reinterpret_cast<const float4 *>(gt) + i);
 #define CC(a, b, k_) cc[IDX((a) + ido * ((b) + cdim * (k_)))]
 #define CH(a, b, k_) ch[IDX((a) + ido * ((b) + l1 * (k_)))]
@@ -294,7 +309,7 @@ __device__ void radfg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
             float s = C2(ik, 0);
             for (int j = 1; j < ipph; ++j) s += C2(ik, j);
             CH2(ik, 0) = s;
-        } else generic_block(c, cc, ch, sgt, ip, ipph, idl1, lb, ik, nz);
+        } else generic_block_lb(LB, c, cc, ch, sgt, ip, ipph, idl1, lb, ik, nz);
     }
     __syncthreads();
     FOR_ITEMS(it, l1 * ido) {
@@ -474,8 +489,9 @@ __device__ void radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
 {
     const int ido = P.ido, ip = P.ip, l1 = P.l1;
     const int cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
+    const int LB = P.lb;
     const int nlb = (ipph - 1 + LB - 1) / LB;
-    for (int i = threadIdx.x; i < nlb * LB * (kRow / 2); i += blockDim.x)   // visible after the next barrier
+    for (int i = threadIdx.x; i < nlb * LB * (kRow / 2); i += kXT)   // visible after the next barrier
         reinterpret_cast<float4 *>(sgt)[i] = __ldg(reinterpret_cast<const float4 *>(gt) + i);
 #define CC(a, b, k_) cc[IDX((a) + ido * ((b) + cdim * (k_)))]
 #define CH(a, b, k_) ch[IDX((a) + ido * ((b) + l1 * (k_)))]
@@ -509,7 +525,7 @@ __device__ void radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
             float s = CH2(ik, 0);
             for (int j = 1; j < ipph; ++j) s += CH2(ik, j);
             C2(ik, 0) = s;
-        } else generic_block(c, ch, cc, sgt, ip, ipph, idl1, lb, ik, nz);
+        } else generic_block_lb(LB, c, ch, cc, sgt, ip, ipph, idl1, lb, ik, nz);
     }
     __syncthreads();
     FOR_ITEMS(ik, idl1) CH2(ik, 0) = C2(ik, 0);
@@ -788,7 +804,7 @@ __device__ void cpassg(const Ctx &c, int ido, int ip, int l1, float2 *cc, float2
 #define GCX(a, b, k_) cc[IDX((a) + ido * ((b) + l1 * (k_)))]
 #define GCX2(a, b) cc[IDX((a) + idl1 * (b))]
 #define GCH2(a, b) ch[IDX((a) + idl1 * (b))]
-    for (int i = threadIdx.x; i < ip; i += blockDim.x) {
+    for (int i = threadIdx.x; i < ip; i += kXT) {
         const float2 w = __ldg(csarr + i);
         wal[i] = i == 0 ? make_float2(1.f, 0.f) : make_float2(w.x, FWD ? -w.y : w.y);
     }
@@ -1050,7 +1066,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
     Ctx c;
     c.r = threadIdx.x & (G - 1);
     c.item0 = threadIdx.x >> a.lgG;
-    c.istride = blockDim.x >> a.lgG;
+    c.istride = kXT >> a.lgG;
     c.GP = GP;
 
     float *plane = a.img.ptr + (size_t)blockIdx.y * a.img.plane_stride;
@@ -1061,12 +1077,12 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
         // ---- gather (rows beyond the sub-band are zero sequences)
         // a warp covers 32/G consecutive elements of G rows: each row contributes one 16..128-byte run
         if (!a.along_cols) {
-            for (int idx = threadIdx.x; idx < G * n; idx += blockDim.x) {
+            for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
                 const int e = idx >> a.lgG, rr = idx & (G - 1);
                 A[idx] = rr < ns ? plane[(size_t)(s0 + rr) * a.img.pitch + e] : 0.f;
             }
         } else {
-            for (int idx = threadIdx.x; idx < G * n; idx += blockDim.x) {
+            for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
                 const int e = idx >> a.lgG, rr = idx & (G - 1);
                 A[idx] = rr < ns ? plane[(size_t)e * a.img.pitch + s0 + rr] : 0.f;
             }
@@ -1090,7 +1106,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
             if (swap) { float *t = p1; p1 = p2; p2 = t; }
         }
         // ---- notch on packed positions (core.py:752: spec *= g)
-        for (int idx = threadIdx.x; idx < G * n; idx += blockDim.x) {
+        for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
             const int e = idx >> a.lgG, rr = idx & (G - 1);
             p1[idx] = p1[idx] * __ldg(a.g + e);
         }
@@ -1112,12 +1128,12 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
         }
         // ---- scale by 1/n (copy_and_norm) and scatter
         if (!a.along_cols) {
-            for (int idx = threadIdx.x; idx < G * n; idx += blockDim.x) {
+            for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
                 const int e = idx >> a.lgG, rr = idx & (G - 1);
                 if (rr < ns) plane[(size_t)(s0 + rr) * a.img.pitch + e] = a.fct * p1[idx];
             }
         } else {
-            for (int idx = threadIdx.x; idx < G * n; idx += blockDim.x) {
+            for (int idx = threadIdx.x; idx < G * n; idx += kXT) {
                 const int e = idx >> a.lgG, rr = idx & (G - 1);
                 if (rr < ns) plane[(size_t)e * a.img.pitch + s0 + rr] = a.fct * p1[idx];
             }
@@ -1155,7 +1171,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_cplx(const __grid_constant__ X
     Ctx c;
     c.r = threadIdx.x & (G - 1);
     c.item0 = threadIdx.x >> a.lgG;
-    c.istride = blockDim.x >> a.lgG;
+    c.istride = kXT >> a.lgG;
     c.GP = G;
     const float2 *roots = reinterpret_cast<const float2 *>(a.tab + a.roots);
     float *plane = a.img.ptr + (size_t)blockIdx.y * a.img.plane_stride;
@@ -1163,7 +1179,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_cplx(const __grid_constant__ X
         const int s0 = grp * G;
         const int ns = min(G, a.nseq - s0);
         __syncthreads();
-        for (int idx = threadIdx.x; idx < G * h; idx += blockDim.x) {
+        for (int idx = threadIdx.x; idx < G * h; idx += kXT) {
             const int m = idx >> a.lgG, rr = idx & (G - 1);
             float2 v = make_float2(0.f, 0.f);
             if (rr < ns) {
@@ -1203,7 +1219,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_cplx(const __grid_constant__ X
         }
         __syncthreads();
         cfft_all<false, true>(c, a.cp, a.tab, cur, nxt, 1, a.cs, wal, &a.blue, BX0, BX1);
-        for (int idx = threadIdx.x; idx < G * h; idx += blockDim.x) {
+        for (int idx = threadIdx.x; idx < G * h; idx += kXT) {
             const int m = idx >> a.lgG, rr = idx & (G - 1);
             if (rr >= ns) continue;
             const float2 v = cur[idx];
@@ -1220,12 +1236,12 @@ __global__ void __launch_bounds__(kXT) k_blue_setup(XBlue b, const float *tab, c
     extern __shared__ __align__(16) float xs[];
     float2 *X0 = reinterpret_cast<float2 *>(xs), *X1 = X0 + b.n2;
     Ctx c;
-    c.r = 0; c.item0 = threadIdx.x; c.istride = blockDim.x; c.GP = 1;
-    for (int m = threadIdx.x; m < b.n2; m += blockDim.x) X0[m] = tbkf[m];
+    c.r = 0; c.item0 = threadIdx.x; c.istride = kXT; c.GP = 1;
+    for (int m = threadIdx.x; m < b.n2; m += kXT) X0[m] = tbkf[m];
     __syncthreads();
     float2 *cur = X0, *nxt = X1;
     cfft_all<true>(c, b, tab, cur, nxt, 1);
-    for (int m = threadIdx.x; m < b.n2 / 2 + 1; m += blockDim.x) out[m] = cur[m];
+    for (int m = threadIdx.x; m < b.n2 / 2 + 1; m += kXT) out[m] = cur[m];
 }
 
 // ================================================================ host: plan + tables
@@ -1549,7 +1565,7 @@ B2sXfftPlan *b2s_xfft_create(int n)
                     twid.get((size_t)(i / 2) * (n / ip), &re, &im);
                     tws[i] = re; tws[i + 1] = im; tws[ic] = re; tws[ic + 1] = -im;
                 }
-                const int ipph = (ip + 1) / 2, JP = kRow, rows = (ipph - 1 + LB - 1) / LB * LB;   // zero rows pad the last block
+                const int ipph = (ip + 1) / 2, JP = kRow, rows = ipph - 1 + kLBMax;   // zero rows pad the last block of any block size
                 while (tab.size() & 3) tab.push_back(0.f);
                 cs_off[k] = (int)tab.size();
                 tab.resize(tab.size() + 2 * (size_t)rows * JP, 0.f);
@@ -1578,8 +1594,8 @@ B2sXfftPlan *b2s_xfft_create(int n)
         const int ip = fct[k], ni = (ido - 1) / 2, ipph = (ip + 1) / 2;
         const long long max_it = (long long)n * 2 + 64;     // every item loop of a pass runs over fewer than 2n items
         XPass p{ip <= 5 ? ip : (ip < 135 ? 6 : 7), ip, l1, ido, tw_off[k], cs_off[k],
-                magic(l1, max_it), magic(ni, max_it), magic(l1 * ni, max_it), magic(ido, max_it), magic(ido * l1, max_it)};
-        if (p.kind == 6) a.gt_max = std::max(a.gt_max, (ipph - 1 + LB - 1) / LB * LB * kRow);
+                magic(l1, max_it), magic(ni, max_it), magic(l1 * ni, max_it), magic(ido, max_it), magic(ido * l1, max_it), kLBMax};
+        if (p.kind == 6) a.gt_max = std::max(a.gt_max, (ipph - 1 + kLBMax) * kRow);
         return p;
     };
     {
@@ -1687,6 +1703,15 @@ B2sXfftPlan *b2s_xfft_create(int n)
     a.lgG = 0;
     while ((1 << a.lgG) < G) ++a.lgG;
     pl->smem = xfft_smem(n, G, b, a.gt_max);
+    // block size of the O(radix^2) phase (outputs per thread): 8.  Smaller blocks fill the rounds of the CTA's item slots
+    // better (n = 1333 = 31 * 43, 64 slots: LB = 8 -> 93 and 86 items, 73 % / 67 % of two rounds; LB = 6 / 4 -> 97 % / 90 %) but
+    // measured no faster — the kernel is issue-bound, a warp idling at a barrier costs nothing while others issue
+    // (profiles/r02_notch_experiments.md).  B2S_XFFT_LB = 4 .. 8 forces a size for experiments.
+    {
+        static const int forced = getenv("B2S_XFFT_LB") ? atoi(getenv("B2S_XFFT_LB")) : 0;
+        const int lb = (forced >= 4 && forced <= kLBMax) ? forced : kLBMax;
+        for (int f = 0; f < nf; ++f) { a.fwd[f].lb = lb; a.bwd[f].lb = lb; }
+    }
     return pl;
 }
 
@@ -1705,16 +1730,6 @@ static int xfft_cap_mult()
     return m > 0 ? m : 1;
 }
 
-// Threads per CTA: kXT unless B2S_XFFT_THREADS says otherwise (a multiple of 32 and of the rows per CTA; tuning knob: a
-// CTA works on threads / G butterfly items at a time, which decides how full the last round of a pass is).
-static int xfft_threads(const B2sXfftPlan *pl)
-{
-    static const int forced = getenv("B2S_XFFT_THREADS") ? atoi(getenv("B2S_XFFT_THREADS")) : 0;
-    const int G = pl->cplx ? pl->ca.G : pl->a.G;
-    if (forced >= 32 && forced <= kXT && forced % 32 == 0 && forced % G == 0) return forced;
-    return kXT;
-}
-
 void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B2sImg &img, int along_cols, int n_planes,
                             int sm_count, cudaStream_t s)
 {
@@ -1729,7 +1744,7 @@ void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B
         int bx = a.groups_per_plane;
         const int cap = (sm_count * xfft_cap_mult() + n_planes - 1) / n_planes;
         if (bx > cap) bx = cap > 0 ? cap : 1;
-        k_notch_cplx<<<dim3(bx, n_planes), xfft_threads(pl), pl->smem, s>>>(a);
+        k_notch_cplx<<<dim3(bx, n_planes), kXT, pl->smem, s>>>(a);
         return;
     }
     XArgs a = pl->a;
@@ -1742,5 +1757,5 @@ void b2s_launch_notch_exact(const B2sXfftPlan *pl, const float *d_notch, const B
     int bx = a.groups_per_plane;
     const int cap = (sm_count * xfft_cap_mult() + n_planes - 1) / n_planes;
     if (bx > cap) bx = cap > 0 ? cap : 1;
-    k_notch_exact<<<dim3(bx, n_planes), xfft_threads(pl), pl->smem, s>>>(a);
+    k_notch_exact<<<dim3(bx, n_planes), kXT, pl->smem, s>>>(a);
 }
