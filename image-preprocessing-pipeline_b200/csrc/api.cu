@@ -372,6 +372,9 @@ struct b2s_plan {
     int n_row_groups = 0;
     int *d_row_src = nullptr, *d_row_start = nullptr, *d_row_targets = nullptr, *d_colmap = nullptr;
     float *d_lut = nullptr;
+    double *d_clip_pp = nullptr;                   // bleach_per_plane: (min, med, max) per plane of the coming b2s_run
+    float *d_padv_pp = nullptr;                     //                   constant-padding value per plane (or null)
+    int64_t n_levels = 0, cap_levels = 0;
     int *d_rz_idx = nullptr;                        // new_size: [iy0 | iy1 | ix0 | ix1]
     double *d_rz_w = nullptr;                       //           [wy0 | wy1 | wx0 | wx1]
     double *d_aa_w[2] = {nullptr, nullptr};         // anti-aliasing Gaussian weights per axis (2 r + 1), caller-supplied
@@ -656,7 +659,7 @@ int fit_workspace(b2s_plan *pl)
 }
 
 // enqueue the whole per-batch pipeline on `st` using slot workspace `s`
-int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out, int nb, cudaStream_t st)
+int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out, int nb, cudaStream_t st, int64_t z0 = 0)
 {
     b2s_context *ctx = pl->ctx;
     const Geometry &g = pl->g;
@@ -715,6 +718,7 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             a.base_pad = g.base_pad;
             a.use_log1p = p.log1p;
             a.pad_value = p.pad_mode == B2S_PAD_CONSTANT ? (float)p.pad_constant : 0.f;
+            a.pad_value_pp = (p.bleach_per_plane && p.pad_mode == B2S_PAD_CONSTANT && pl->d_padv_pp) ? pl->d_padv_pp + z0 : nullptr;
             a.out = padded;
             a.n_groups = pl->n_row_groups;
             a.row_src = pl->d_row_src;
@@ -775,6 +779,7 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             b.base_pad = g.base_pad; b.rows = g.work_rows; b.cols = g.work_cols;
             b.b0 = p.bleach_b0; b.b1 = p.bleach_b1; b.a1 = p.bleach_a1; b.zi = p.bleach_zi;
             b.clip_min = p.bleach_clip_min; b.clip_med = p.bleach_clip_med; b.clip_max = p.bleach_clip_max;
+            b.clip_pp = p.bleach_per_plane ? pl->d_clip_pp + 3 * z0 : nullptr;
             b.scratch = s.bleach_scratch;
             b.scratch_plane_stride = (size_t)g.work_rows * (g.work_cols + 12);
             b.filt = s.bleach_filt;
@@ -1129,6 +1134,27 @@ int b2s_plan_set_aa_weights(b2s_plan *pl, int axis, const double *w, int n)
     return B2S_OK;
 }
 
+int b2s_plan_set_bleach_levels(b2s_plan *pl, const double *clip, const float *pad_value, int64_t n_planes)
+{
+    if (!pl || !clip || n_planes <= 0) return B2S_ERR_INVALID;
+    b2s_context *ctx = pl->ctx;
+    if (!pl->p.bleach || !pl->p.bleach_per_plane)
+        return fail(ctx, B2S_ERR_INVALID, "b2s_plan_set_bleach_levels: the plan was not created with bleach_per_plane");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    if (n_planes > pl->cap_levels) {   // grow (the old blocks stay in the plan's allocation list until it is destroyed)
+        int rc = dev_alloc(pl, (void **)&pl->d_clip_pp, sizeof(double) * 3 * (size_t)n_planes);
+        if (rc) return rc;
+        if ((rc = dev_alloc(pl, (void **)&pl->d_padv_pp, sizeof(float) * (size_t)n_planes))) return rc;
+        pl->cap_levels = n_planes;
+    }
+    CU(ctx, cudaMemcpy(pl->d_clip_pp, clip, sizeof(double) * 3 * (size_t)n_planes, cudaMemcpyHostToDevice));
+    if (pad_value) CU(ctx, cudaMemcpy(pl->d_padv_pp, pad_value, sizeof(float) * (size_t)n_planes, cudaMemcpyHostToDevice));
+    else CU(ctx, cudaMemset(pl->d_padv_pp, 0, sizeof(float) * (size_t)n_planes));
+    pl->n_levels = n_planes;
+    return B2S_OK;
+}
+
 int b2s_plan_set_notch(b2s_plan *pl, int pass, int level, int axis, const float *g, int n)
 {
     if (!pl || !g) return B2S_ERR_INVALID;
@@ -1153,6 +1179,9 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
     const size_t in_plane = (size_t)g.in_rows * g.in_cols * dtype_size(pl->p.in_dtype);
     const size_t out_plane = (size_t)g.out_rows * g.out_cols * dtype_size(g.out_dtype);
     const int B = pl->B;
+    if (pl->p.bleach && pl->p.bleach_per_plane && pl->n_levels < n_planes)
+        return fail(ctx, B2S_ERR_INVALID, "bleach_per_plane: b2s_plan_set_bleach_levels supplied %lld planes, the run has %lld",
+                    (long long)pl->n_levels, (long long)n_planes);
 
     if (in_is_device && out_is_device) {
         cudaStream_t st = (cudaStream_t)stream;
@@ -1170,7 +1199,7 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
         for (int64_t z = 0; z < n_planes; z += B) {
             const int nb = (int)std::min<int64_t>(B, n_planes - z);
             b2s_plan::Slot &s = pl->slot[si];
-            int rc = enqueue_batch(pl, s, (const char *)in + z * in_plane, (char *)out + z * out_plane, nb, ns > 1 ? s.stream : st);
+            int rc = enqueue_batch(pl, s, (const char *)in + z * in_plane, (char *)out + z * out_plane, nb, ns > 1 ? s.stream : st, z);
             if (rc) return rc;
             si = (si + 1) % ns;
         }
@@ -1245,7 +1274,7 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
             d_in = s.d_in;
         }
         void *d_out = out_is_device ? (void *)((char *)out + z * out_plane) : s.d_out;
-        rc = enqueue_batch(pl, s, d_in, d_out, nb, s.stream);
+        rc = enqueue_batch(pl, s, d_in, d_out, nb, s.stream, z);
         if (rc) return rc;
         if (!out_is_device) {
             void *dst = out_pinned ? (void *)((char *)out + z * out_plane) : s.h_out;

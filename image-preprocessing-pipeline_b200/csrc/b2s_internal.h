@@ -31,6 +31,7 @@ struct B2sPrologueArgs {
     int pad_mode, base_pad;
     int use_log1p;
     float pad_value;       // constant padding: the fill value (core.py:1101-1105), 0 otherwise
+    const float *pad_value_pp; // optional: one fill value per plane (clip_min from multi-Otsu, core.py:1066-1077, 1101-1105)
     B2sImg out;            // padded image
     // numpy.pad as tables (built once per plan): padded rows grouped by the source row they replicate
     int n_groups;          // source rows + padded rows without a source (constant mode)
@@ -165,6 +166,7 @@ struct B2sBleachArgs {
     int base_pad, rows, cols;
     double b0, b1, a1, zi;         // butter(1, f, output='sos') = [b0, b1, 0, 1, a1, 0]; sosfilt_zi(sos)[0, 0]
     double clip_min, clip_med, clip_max;
+    const double *clip_pp;         // optional: (clip_min, clip_med, clip_max) per plane (multi-Otsu levels, core.py:1066-1077)
     double *scratch;               // forward-pass output, rows x (cols + 12) doubles per plane
     size_t scratch_plane_stride;   // doubles
     float *filt;                   // img_filter, rows x cols per plane

@@ -61,8 +61,13 @@ constexpr int kProducers = 96;
 constexpr int kTileElems = kRows * kChunk;
 constexpr int kPerProducer = (kTileElems + kProducers - 1) / kProducers;   // 11
 
-__global__ void __launch_bounds__(kRows + kProducers) k_bleach_lowpass(B2sBleachArgs a)
+__global__ void __launch_bounds__(kRows + kProducers) k_bleach_lowpass(const B2sBleachArgs a_in)
 {
+    B2sBleachArgs a = a_in;
+    if (a.clip_pp) {   // per-plane clip levels (multi-Otsu)
+        const double *cl = a.clip_pp + 3 * (size_t)blockIdx.y;
+        a.clip_min = cl[0]; a.clip_med = cl[1]; a.clip_max = cl[2];
+    }
     static_assert(kRows == 32 && kChunk == 32, "warp 0: lane = row of the tile");
     __shared__ float s_f[2][kRows][kChunk + 1];
     __shared__ double s_d[2][kRows][kChunk + 1];

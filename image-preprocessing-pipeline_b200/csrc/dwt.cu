@@ -337,7 +337,7 @@ struct FwdArgs {
     int F, Fp, nch;
     int tiles_x, tiles_y, n_tiles;
     int grid3d;      // launched as (tiles_x, tiles_y, planes): one tile per CTA
-    int use_tma;     // the input window arrives through the tensor map (grid3d launches only)
+    int use_tma;     // the input window arrives through the tensor map
     float negzero;   // -0.0f, deliberately a run-time value (see mul2_exact)
 };
 
@@ -427,45 +427,55 @@ __global__ void __launch_bounds__(T::NT) k_dwt_fwd(const __grid_constant__ FwdTa
 
     int t = grid3d ? 0 : blockIdx.x;
     const int t_end = grid3d ? 1 : a.n_tiles, t_step = grid3d ? 1 : gridDim.x;
-    const bool tma = grid3d && a.use_tma;
-    if (tma) {
-        // one thread: arm the barrier with the byte count of the box and start the copy; everybody waits on the barrier
-        if (tid == 0) mbar_init(&s_bar);
-        __syncthreads();
-        const int gy0 = 2 * blockIdx.y * TY + 2 - Fp, gx0a = (2 * blockIdx.x * TX + 2 - Fp) & ~3;
+    const bool tma = a.use_tma != 0;
+    unsigned phase = 0;
+    // TMA: one thread arms the barrier with the byte count of the box and starts the copy; everybody waits on the barrier
+    auto tma_issue = [&](int tt) {
         if (tid == 0) {
+            const TileCoord c = coord_of(tt);
             mbar_expect(&s_bar, (unsigned)(g.rin_y * PIN * sizeof(float)));
-            tma_load_3d(s_in, &tmap, &s_bar, gx0a, gy0, blockIdx.z);
+            tma_load_3d(s_in, &tmap, &s_bar, (2 * c.tx * TX + 2 - Fp) & ~3, 2 * c.ty * TY + 2 - Fp, c.plane);
         }
-        mbar_wait(&s_bar, 0);
-        if (gy0 < 0 || gy0 + g.rin_y > ny || gx0a < 0 || gx0a + 4 * c4n > nx) {
-            // border tile: the copy engine wrote zeros outside the image; replace those within reach of a stored output
-            // by the half-sample symmetric extension (read from global memory: any image size, any number of reflections)
-            const float *src = a.in.ptr + (size_t)blockIdx.z * a.in.plane_stride;
-            const int wq = 4 * c4n;
-            for (int r = warp; r < g.rin_y; r += NW) {
-                const int gy = gy0 + r;
-                if (gy < -Fp || gy >= ny + Fp) continue;
-                const bool row_in = gy >= 0 && gy < ny;
-                const float *srow = src + (size_t)sym_ext(gy, ny) * a.in.pitch;
-                float *drow = s_in + r * PIN;
-                if (row_in) {   // only the columns left / right of the image
-                    for (int cc = lane; cc < 2 * Fp + 8; cc += 32) {
-                        const int gx = cc < Fp + 4 ? -1 - cc : nx + (cc - Fp - 4);
-                        const int sc = gx - gx0a;
-                        if (sc >= 0 && sc < wq && gx >= -Fp && gx < nx + Fp) drow[sc] = srow[sym_ext(gx, nx)];
-                    }
-                } else {
-                    for (int sc = lane; sc < wq; sc += 32) {
-                        const int gx = gx0a + sc;
-                        if (gx >= -Fp && gx < nx + Fp) drow[sc] = srow[sym_ext(gx, nx)];
-                    }
+    };
+    // border tile: the copy engine wrote zeros outside the image; replace those within reach of a stored output by the
+    // half-sample symmetric extension (read from global memory: any image size, any number of reflections)
+    auto tma_fixup = [&](int tt) {
+        const TileCoord c = coord_of(tt);
+        const int gy0 = 2 * c.ty * TY + 2 - Fp, gx0a = (2 * c.tx * TX + 2 - Fp) & ~3;
+        if (!(gy0 < 0 || gy0 + g.rin_y > ny || gx0a < 0 || gx0a + 4 * c4n > nx)) return;
+        const float *src = a.in.ptr + (size_t)c.plane * a.in.plane_stride;
+        const int wq = 4 * c4n;
+        for (int r = warp; r < g.rin_y; r += NW) {
+            const int gy = gy0 + r;
+            if (gy < -Fp || gy >= ny + Fp) continue;
+            const bool row_in = gy >= 0 && gy < ny;
+            const float *srow = src + (size_t)sym_ext(gy, ny) * a.in.pitch;
+            float *drow = s_in + r * PIN;
+            if (row_in) {   // only the columns left / right of the image
+                for (int cc = lane; cc < 2 * Fp + 8; cc += 32) {
+                    const int gx = cc < Fp + 4 ? -1 - cc : nx + (cc - Fp - 4);
+                    const int sc = gx - gx0a;
+                    if (sc >= 0 && sc < wq && gx >= -Fp && gx < nx + Fp) drow[sc] = srow[sym_ext(gx, nx)];
+                }
+            } else {
+                for (int sc = lane; sc < wq; sc += 32) {
+                    const int gx = gx0a + sc;
+                    if (gx >= -Fp && gx < nx + Fp) drow[sc] = srow[sym_ext(gx, nx)];
                 }
             }
         }
+    };
+    if (tma) {
+        if (tid == 0) mbar_init(&s_bar);
+        __syncthreads();
+        if (t < t_end) tma_issue(t);
     } else if (t < t_end) issue_load(t);
     while (t < t_end) {
-        cp_async_wait_all();
+        if (tma) {
+            mbar_wait(&s_bar, phase);
+            phase ^= 1u;
+            tma_fixup(t);
+        } else cp_async_wait_all();
         __syncthreads();   // tile t has landed; every warp is done with s_mid of the previous tile
 
         const TileCoord c = coord_of(t);
@@ -505,7 +515,7 @@ __global__ void __launch_bounds__(T::NT) k_dwt_fwd(const __grid_constant__ FwdTa
         __syncthreads();   // s_mid complete; s_in is free again
 
         const int tn = t + t_step;
-        if (tn < t_end) issue_load(tn);
+        if (tn < t_end) { if (tma) tma_issue(tn); else issue_load(tn); }
 
         // ---- axis -1 pass.  RX = 4: a warp covers 8 rows x 4 column groups; RX = 8: 16 rows x 2 column groups.  Either way
         //      the 128-bit window loads of a quarter warp hit 8 different bank quads (PM/4 odd).
@@ -644,20 +654,28 @@ __global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTa
 
     int t = grid3d ? 0 : blockIdx.x;
     const int t_end = grid3d ? 1 : a.n_tiles, t_step = grid3d ? 1 : gridDim.x;
-    if (grid3d && a.use_tma) {
-        // four boxes (cA, cV, cH, cD), one barrier; coefficients outside the sub-band arrive as the zeros the synthesis wants
-        if (tid == 0) mbar_init(&s_bar);
-        __syncthreads();
+    const bool tma = a.use_tma != 0;
+    unsigned phase = 0;
+    // TMA: four boxes (cA, cV, cH, cD), one barrier; coefficients outside the sub-band arrive as the zeros the synthesis wants
+    auto tma_issue = [&](int tt) {
         if (tid == 0) {
-            const int cy0 = blockIdx.y * TQ + a.H - Hp, cx0 = blockIdx.x * TP + a.H - Hp;
+            const TileCoord c = coord_of(tt);
+            const int cy0 = c.ty * TQ + a.H - Hp, cx0 = c.tx * TP + a.H - Hp;
             mbar_expect(&s_bar, (unsigned)(4 * RQ * PS * sizeof(float)));
 #pragma unroll
-            for (int sb = 0; sb < 4; ++sb) tma_load_3d(s_sub + sb * sub_floats, &maps.m[sb], &s_bar, cx0, cy0, blockIdx.z);
+            for (int sb = 0; sb < 4; ++sb) tma_load_3d(s_sub + sb * sub_floats, &maps.m[sb], &s_bar, cx0, cy0, c.plane);
         }
-        mbar_wait(&s_bar, 0);
+    };
+    if (tma) {
+        if (tid == 0) mbar_init(&s_bar);
+        __syncthreads();
+        if (t < t_end) tma_issue(t);
     } else if (t < t_end) issue_load(t);
     while (t < t_end) {
-        cp_async_wait_all();
+        if (tma) {
+            mbar_wait(&s_bar, phase);
+            phase ^= 1u;
+        } else cp_async_wait_all();
         __syncthreads();   // tile t has landed; every warp is done with s_mid of the previous tile
 
         const TileCoord c = coord_of(t);
@@ -689,7 +707,7 @@ __global__ void __launch_bounds__(T::NT) k_dwt_inv(const __grid_constant__ InvTa
         __syncthreads();   // s_mid complete; s_sub is free again
 
         const int tn = t + t_step;
-        if (tn < t_end) issue_load(tn);
+        if (tn < t_end) { if (tma) tma_issue(tn); else issue_load(tn); }
 
         // ---- axis -2 synthesis: (a, d) -> out rows 2q, 2q+1
         {
@@ -1054,7 +1072,7 @@ void launch_fwd_t(const FwdTaps &ft, FwdArgs a, int n_planes, int sm_count, cuda
     a.grid3d = one_per_cta && n_planes <= 65535 && a.tiles_y <= 65535;
     const dim3 grid = a.grid3d ? dim3(a.tiles_x, a.tiles_y, n_planes) : dim3(one_per_cta ? a.n_tiles : sm_count * per_sm);
     CUtensorMap tmap;
-    a.use_tma = a.grid3d && make_tmap(&tmap, a.in, n_planes, g.pin, g.rin_y);
+    a.use_tma = make_tmap(&tmap, a.in, n_planes, g.pin, g.rin_y);
     cudaFuncSetAttribute(k_dwt_fwd<T, J, MULTI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     k_dwt_fwd<T, J, MULTI, MODE><<<grid, T::NT, bytes, s>>>(ft, a, tmap);
 }
@@ -1104,7 +1122,7 @@ void launch_inv_t(const InvTaps &it, InvArgs a, int n_planes, int sm_count, cuda
     // cA is read with the detail bands' logical size (the caller's buffer may be the larger reconstruction target)
     B2sImg ca = a.cA;
     ca.rows = a.cH.rows; ca.cols = a.cH.cols;
-    a.use_tma = a.grid3d && make_tmap(&maps.m[0], ca, n_planes, g.ps, g.rq) && make_tmap(&maps.m[1], a.cV, n_planes, g.ps, g.rq) &&
+    a.use_tma = make_tmap(&maps.m[0], ca, n_planes, g.ps, g.rq) && make_tmap(&maps.m[1], a.cV, n_planes, g.ps, g.rq) &&
                 make_tmap(&maps.m[2], a.cH, n_planes, g.ps, g.rq) && make_tmap(&maps.m[3], a.cD, n_planes, g.ps, g.rq);
     cudaFuncSetAttribute(k_dwt_inv<T, JH, MULTI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     k_dwt_inv<T, JH, MULTI, MODE><<<grid, T::NT, bytes, s>>>(it, a, maps);

@@ -122,9 +122,10 @@ __global__ void __launch_bounds__(256) k_prologue(B2sPrologueArgs a)
         atomicMin(a.minmax + 2 * plane, lo);
         atomicMin(a.minmax + 2 * plane + 1, ~hi);
     }
+    const float pad_value = a.pad_value_pp ? a.pad_value_pp[plane] : a.pad_value;
     for (int c = threadIdx.x; c < a.out.pitch; c += 256) {
         const int m = sy >= 0 ? __ldg(a.colmap + c) : -1;
-        s_out[c] = m >= 0 ? s_row[m] : a.pad_value;
+        s_out[c] = m >= 0 ? s_row[m] : pad_value;
     }
     __syncthreads();
     const int q4 = a.out.pitch >> 2;

@@ -39,7 +39,7 @@ class Params(C.Structure):
         ("convert_to_16bit", C.c_int32), ("convert_to_8bit", C.c_int32), ("bit_shift_to_right", C.c_int32),
         ("rotate", C.c_int32), ("flip_upside_down", C.c_int32), ("reference_quirks", C.c_int32),
         ("new_height", C.c_int32), ("new_width", C.c_int32),
-        ("bleach", C.c_int32), ("bleach_reserved", C.c_int32),
+        ("bleach", C.c_int32), ("bleach_per_plane", C.c_int32),
         ("bleach_b0", C.c_double), ("bleach_b1", C.c_double), ("bleach_a1", C.c_double), ("bleach_zi", C.c_double),
         ("bleach_clip_min", C.c_double), ("bleach_clip_med", C.c_double), ("bleach_clip_max", C.c_double),
         ("pad_constant", C.c_double),
@@ -61,7 +61,7 @@ class PlanInfo(C.Structure):
 
 EXPORTS = (
     "b2s_version", "b2s_params_default", "b2s_create", "b2s_destroy", "b2s_last_error", "b2s_device_sm_count",
-    "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_plan_set_aa_weights", "b2s_run",
+    "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_plan_set_bleach_levels", "b2s_plan_set_aa_weights", "b2s_run",
     "b2s_host_alloc", "b2s_host_free", "b2s_launch_count", "b2s_timing_enable", "b2s_timing_read",
     "b2s_debug_read", "b2s_debug_math",
     "b2s_resize_aa", "b2s_isotropic_xy", "b2s_isotropic_z", "b2s_isotropic_convert", "b2s_is_uniform", "b2s_histogram",
@@ -103,6 +103,7 @@ def lib():
             L.b2s_plan_set_flat.argtypes = [vp, vp, i32]
             L.b2s_plan_set_notch.argtypes = [vp, i32, i32, i32, vp, i32]
             L.b2s_plan_set_aa_weights.argtypes = [vp, i32, vp, i32]
+            L.b2s_plan_set_bleach_levels.argtypes = [vp, vp, vp, i64]
             L.b2s_isotropic_xy.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
             L.b2s_resize_aa.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
             L.b2s_isotropic_z.argtypes = [vp, vp, i32, i64, i32, vp, vp]
@@ -356,6 +357,14 @@ class Plan:
         """upload a host-evaluated np_notch table (float32) for (pass, 1-based level, axis 0 = cH / 1 = cV)."""
         g = np.ascontiguousarray(g, dtype=np.float32)
         self.ctx.check(lib().b2s_plan_set_notch(self._h, pass_idx, level, axis, C.c_void_p(g.ctypes.data), int(g.size)))
+
+    def set_bleach_levels(self, clip: np.ndarray, pad_value: np.ndarray = None):
+        """per-plane (clip_min, clip_med, clip_max) [n, 3] float64 and optional constant-padding values [n] float32 for the
+        next run of a plan created with bleach_per_plane."""
+        clip = np.ascontiguousarray(clip, dtype=np.float64).reshape(-1, 3)
+        pv = None if pad_value is None else np.ascontiguousarray(pad_value, dtype=np.float32)
+        self.ctx.check(lib().b2s_plan_set_bleach_levels(self._h, C.c_void_p(clip.ctypes.data),
+                                                        C.c_void_p(pv.ctypes.data) if pv is not None else None, clip.shape[0]))
 
     def set_aa_weights(self, axis: int, w: np.ndarray):
         """upload the anti-aliasing Gaussian of skimage.transform.resize along one axis (2 * radius + 1 float64 weights)."""

@@ -361,7 +361,7 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
             p.new_height, p.new_width = int(new_size[0]), int(new_size[1])
         if bleach is not None:
             (p.bleach_b0, p.bleach_b1, p.bleach_a1, p.bleach_zi,
-             p.bleach_clip_min, p.bleach_clip_med, p.bleach_clip_max, p.bleach) = bleach
+             p.bleach_clip_min, p.bleach_clip_med, p.bleach_clip_max, p.bleach, p.bleach_per_plane) = bleach
         p.pad_constant = float(pad_constant)
         p.aa_radius_y = 0 if aa[0] is None else int(aa[0][0])
         p.aa_radius_x = 0 if aa[1] is None else int(aa[1][0])
@@ -435,6 +435,21 @@ def pinned_empty(shape, dtype, device: int = None) -> ndarray:
     return _native.context(dev).pooled_empty(tuple(shape), dtype)
 
 
+def _run_with_levels(plan, arr, bleach, clip_min, clip_med, clip_max, padding_mode, skip_uniform):
+    """run the plan; when bleach clip levels are per plane (multi-Otsu), compute and upload them first, atomically with the
+    run (the plan may be shared with another thread)."""
+    if bleach is None or not bleach[-1]:
+        return _run(plan, arr)
+    if _code_of(arr) == _native.F32:
+        raise NotImplementedError("bleach clip levels left to threshold_multiotsu need integer pixels (uint8 / uint16): the "
+                                  "levels come from the exact intensity histogram")
+    constant = isinstance(padding_mode, str) and padding_mode.lower() == 'constant'
+    levels, pads = _otsu_levels(arr, clip_min, clip_med, clip_max, constant, skip_uniform)
+    with plan.lock:
+        plan.set_bleach_levels(levels, pads)
+        return _run(plan, arr)
+
+
 def _run(plan, img):
     if _native._is_torch(img):
         return plan.run_torch(img)
@@ -483,11 +498,22 @@ def _bleach_plan_args(frequency, clip_min, clip_med, clip_max, max_method, enabl
                                   "of the GPU hot path (SURVEY.md §8f N3)")
     if frequency is None:
         return None, pad_constant
+    assert isinstance(frequency, (float, float32, np.float64)) and frequency > 0     # core.py:521
+    from scipy.signal import butter, sosfilt_zi
+    sos = butter(1, frequency, output='sos')                            # core.py:495: [[b0, b1, 0, 1, a1, 0]]
+    zi = sosfilt_zi(sos)
+    assert sos.shape == (1, 6) and sos[0, 2] == 0 and sos[0, 5] == 0 and sos[0, 3] == 1 and zi[0, 1] == 0
+    section = (float(sos[0, 0]), float(sos[0, 1]), float(sos[0, 4]), float(zi[0, 0]))
+    method = 2 if max_method else 1
     if clip_min is None or clip_med is None or clip_max is None:
-        raise NotImplementedError("bleach correction with clip levels left to threshold_multiotsu (core.py:1066-1077) is "
-                                  "not implemented: pass bleach_correction_clip_min / _med / _max")
+        # core.py:1066-1077: the missing levels come from threshold_multiotsu(log1p(img)), per image -> per-plane device data
+        return section + (0.0, 0.0, 0.0, method, 1), pad_constant
+    return section + _clip_levels(clip_min, clip_med, clip_max) + (method, 0), pad_constant
+
+
+def _clip_levels(clip_min, clip_med, clip_max):
+    """correct_bleaching's argument checks (core.py:522-531) and the three levels in the precision numpy.clip compares them."""
     ok = (float, float32, np.float64)
-    assert isinstance(frequency, ok) and frequency > 0                   # core.py:521-527
     assert isinstance(clip_min, ok) and clip_min >= 0
     assert isinstance(clip_med, ok) and clip_med > clip_min
     assert isinstance(clip_max, ok) and clip_max > clip_min
@@ -498,13 +524,31 @@ def _bleach_plan_args(frequency, clip_min, clip_med, clip_max, max_method, enabl
 
     def as_clip_sees(v):      # numpy.clip(float32 array, bound): a Python float is weak (-> float32), numpy.float64 is not
         return float(v) if isinstance(v, np.float64) else float(np.float32(v))
-    from scipy.signal import butter, sosfilt_zi
-    sos = butter(1, frequency, output='sos')                            # core.py:495: [[b0, b1, 0, 1, a1, 0]]
-    zi = sosfilt_zi(sos)
-    assert sos.shape == (1, 6) and sos[0, 2] == 0 and sos[0, 5] == 0 and sos[0, 3] == 1 and zi[0, 1] == 0
-    return (float(sos[0, 0]), float(sos[0, 1]), float(sos[0, 4]), float(zi[0, 0]),
-            as_clip_sees(clip_min), float(np.float32(clip_med)), as_clip_sees(clip_max),
-            2 if max_method else 1), pad_constant
+    return as_clip_sees(clip_min), float(np.float32(clip_med)), as_clip_sees(clip_max)
+
+
+def _otsu_levels(arr, clip_min, clip_med, clip_max, constant_padding: bool, skip_uniform: bool):
+    """Per-plane clip levels when some are left to multi-Otsu (core.py:1066-1077): exact per-plane histograms on the GPU
+    (b2s_histogram), thresholds on the host from the bins (pystripe/stack_stats.py), then the same checks as explicit levels.
+    Returns ([n, 3] float64 levels, [n] float32 constant-padding values or None)."""
+    from . import stack_stats
+    a3 = arr if arr.ndim == 3 else arr[None]
+    h = stack_stats.histogram(a3, per_plane=True)
+    h = h.cpu().numpy() if _native._is_torch(h) else h
+    levels = np.empty((h.shape[0], 3), np.float64)
+    pads = np.zeros(h.shape[0], np.float32) if constant_padding else None
+    for z in range(h.shape[0]):
+        if skip_uniform and np.count_nonzero(h[z]) <= 1:               # process_img returns zeros for such a plane (core.py:1232)
+            levels[z] = (1.0, 2.0, 3.0)
+            continue
+        lb, mb, ub = stack_stats.threshold_multiotsu_from_histogram(h[z], classes=4)
+        cmin = lb if clip_min is None else clip_min
+        cmed = mb if clip_med is None else clip_med
+        cmax = ub if clip_max is None else clip_max
+        levels[z] = _clip_levels(cmin, cmed, cmax)
+        if constant_padding:
+            pads[z] = np.float32(np.log1p(cmin))                       # core.py:1101-1105
+    return levels, pads
 
 
 def filter_streaks(
@@ -547,7 +591,8 @@ def filter_streaks(
                      wavelet=wavelet, threshold=threshold, padding_mode=padding_mode, bidirectional=bidirectional,
                      log1p=log1p_normalization_needed, bleach=bleach, pad_constant=pad_constant, _acquire=True)
     try:
-        out = _run(plan, arr)
+        out = _run_with_levels(plan, arr, bleach, bleach_correction_clip_min, bleach_correction_clip_med,
+                               bleach_correction_clip_max, padding_mode, skip_uniform=False)
     finally:
         _release_plan(plan)
     if verbose:
@@ -679,7 +724,11 @@ def process_img(
                      max_batch=_max_batch, new_size=resize_to, bleach=bleach, pad_constant=pad_constant, aa=aa,
                      _acquire=True)
     try:
-        out = _run(plan, arr)
+        if bleach is not None and bleach[-1] and (flat is not None or gaussian_filter_2d or down_sample is not None):
+            raise NotImplementedError("bleach clip levels left to threshold_multiotsu (core.py:1066-1077) need the integer image "
+                                      "that enters filter_streaks: not implemented together with flat / Gaussian / down-sampling")
+        out = _run_with_levels(plan, arr, bleach, bleach_correction_clip_min, bleach_correction_clip_med,
+                               bleach_correction_clip_max, padding_mode, skip_uniform=True)
     finally:
         _release_plan(plan)
     if out_code == _native.F32 and plan.info.out_dtype == _native.F32 and d_type != np.float32:

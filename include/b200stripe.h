@@ -89,7 +89,9 @@ typedef struct b2s_params {
                                      filter = sosfiltfilt(butter(1, frequency), clip(img with 0 -> clip_med)) along each
                                      row in float64 (scipy.signal, odd extension of 6 samples, sosfilt_zi start), cast to
                                      float32; img = img / filter * max(filter)                                    */
-    int32_t bleach_reserved;
+    int32_t bleach_per_plane;     /* 1: the three clip levels (and the constant-padding value) differ per plane and arrive through
+                                     b2s_plan_set_bleach_levels before every b2s_run — the reference derives them per image with
+                                     skimage.filters.threshold_multiotsu when they are not given (core.py:1066-1077) */
     double bleach_b0, bleach_b1, bleach_a1, bleach_zi; /* the one section butter(1, f, output='sos') returns:
                                      [b0, b1, 0, 1, a1, 0], and sosfilt_zi(sos)[0, 0] (host: scipy, core.py:495-497) */
     double bleach_clip_min, bleach_clip_med, bleach_clip_max; /* bounds as numpy.clip compares them (a weak Python
@@ -156,6 +158,11 @@ int b2s_plan_set_flat(b2s_plan *plan, const float *flat, int is_device);
  * with numpy exactly as scipy does (numpy's exp is not libm's). */
 int b2s_plan_set_aa_weights(b2s_plan *plan, int axis, const double *weights, int n);
 int b2s_plan_set_notch(b2s_plan *plan, int pass, int level, int axis, const float *g, int n);
+/* replaces: the per-image clip levels of filter_streaks when bleach_correction_clip_min / _med / _max are None
+ * (core.py:1066-1077: lb, mb, ub = threshold_multiotsu(log1p(img), classes=4)).  clip: n_planes x 3 doubles (min, med, max as
+ * numpy.clip compares them, after the clip_min >= log1p(1) rule of core.py:529-531); pad_value: n_planes floats,
+ * log1p(clip_min) for padding_mode='constant' (core.py:1101-1105), or NULL.  Plane z of the next b2s_run uses entry z. */
+int b2s_plan_set_bleach_levels(b2s_plan *plan, const double *clip, const float *pad_value, int64_t n_planes);
 
 /*
  * replaces: process_img(img, ...) / filter_streaks(img, ...) applied to n_planes independent planes

@@ -189,7 +189,7 @@ def filter_streaks(img, sigma=(250, 250), level=0, wavelet='db9', crossover=10, 
                    padding_mode="wrap", bidirectional=False, log1p_normalization_needed=True,
                    return_log_domain=False, bleach_correction_frequency=None, bleach_correction_clip_min=None,
                    bleach_correction_clip_med=None, bleach_correction_clip_max=None, bleach_correction_max_method=False):
-    """core.py:982-1159 without masking and multi-Otsu clip levels."""
+    """core.py:982-1159 without masking (multi-Otsu clip levels through the restated threshold_multiotsu below)."""
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
     s1, s2 = sigma
@@ -198,6 +198,15 @@ def filter_streaks(img, sigma=(250, 250), level=0, wavelet='db9', crossover=10, 
     d_type = img.dtype
     if log1p_normalization_needed:
         img = log1p_f32(img.astype(np.float32))
+    if bleach_correction_frequency is not None and (bleach_correction_clip_min is None or bleach_correction_clip_med is None
+                                                    or bleach_correction_clip_max is None):     # core.py:1066-1077
+        lb, mb, ub = threshold_multiotsu(img, classes=4)
+        if bleach_correction_clip_min is None:
+            bleach_correction_clip_min = lb
+        if bleach_correction_clip_med is None:
+            bleach_correction_clip_med = mb
+        if bleach_correction_clip_max is None:
+            bleach_correction_clip_max = ub
     if not s1 == s2 == 0:                                                          # core.py:1081 (no padding otherwise)
         shape = img.shape
         base_pad, pad_y, pad_x = padded_geometry(shape, sigma, padding_mode)

@@ -526,11 +526,32 @@ def test_bleach_correction_against_oracle(shape, freq):
         _cmp_int(f"bleach/{shape}/{z}", got[z], ref, min_exact=1.0)
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(bleach_correction_clip_min=4.9), dict(padding_mode="constant"),
+                                dict(bleach_correction_max_method=True, bleach_correction_clip_max=7.8)])
+def test_bleach_clip_levels_from_multiotsu_per_plane(kw):
+    """clip levels left to threshold_multiotsu (core.py:1066-1077): per-plane levels from exact GPU histograms, every plane of
+    a batch with its own levels (and its own constant-padding value)."""
+    from pystripe import core
+    stack = np.stack([synth.plane(21, (300, 420)), (synth.plane(22, (300, 420)).astype(np.uint32) * 3).clip(0, 65535).astype(np.uint16),
+                      synth.plane(23, (300, 420))[::-1].copy()])
+    base = dict(sigma=(32, 32), wavelet="db9", padding_mode="reflect", bleach_correction_frequency=1 / 300.0)
+    base.update(kw)
+    got = core.filter_streaks(stack, **base)
+    for z in range(3):
+        ref = orc.filter_streaks(stack[z], **base)
+        _cmp_int(f"bleach_otsu/{kw}/{z}", got[z], ref, min_exact=1.0)
+    # process_img: a uniform plane in the batch is zeros and does not disturb the others
+    stack[1] = 9
+    out = core.process_img(stack, dark=100, **base)
+    assert not out[1].any()
+    assert np.array_equal(out[0], orc.process_img(stack[0].copy(), dark=100, **base))
+
+
 def test_bleach_argument_errors():
     from pystripe import core
     img = synth.plane(0, (64, 64))
-    with pytest.raises(NotImplementedError):          # clip levels left to multi-Otsu
-        core.filter_streaks(img, sigma=(8, 8), bleach_correction_frequency=0.01)
+    with pytest.raises(NotImplementedError):          # multi-Otsu levels need the integer image entering filter_streaks
+        core.process_img(img, sigma=(8, 8), bleach_correction_frequency=0.01, gaussian_filter_2d=True)
     with pytest.raises(AssertionError):               # core.py:524-527
         core.filter_streaks(img, sigma=(8, 8), bleach_correction_frequency=0.01, bleach_correction_clip_min=5.0,
                             bleach_correction_clip_med=4.0, bleach_correction_clip_max=6.0)
