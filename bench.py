@@ -368,7 +368,7 @@ def run_b200(a):
 def batch_filter_leg(a, cfg, core, _io, base, flat, local, world, barrier, max_over_ranks):
     """core.batch_filter over `n` uncompressed TIFF tiles on tmpfs -> TIFF tiles on tmpfs.  Every rank owns its own
     folder and GPU (B200STRIPE_DEVICES), so N ranks run N independent batch_filter calls at once."""
-    n = a.files or 384
+    n = a.files or max(96, 384 // world)       # tmpfs holds the inputs and the outputs of every rank
     tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") else None
     work = Path(tempfile.mkdtemp(prefix=f"b2s_bench_r{local}_", dir=tmp_root))
     saved = {k: os.environ.pop(k, None) for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK")}   # one process = one independent farm

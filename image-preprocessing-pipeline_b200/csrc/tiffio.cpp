@@ -3,6 +3,7 @@
 //
 // Replaces the per-file Python I/O of the reference (pystripe/core.py:200-334, pystripe/raw.py:9-68); see the header for
 // the entry-by-entry mapping.  Host-only code: g++ -O3, zlib for inflate / deflate, no CUDA.
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -38,6 +39,33 @@ int fail(int code, const char *fmt, ...)
 }
 
 int dtype_size(int d) { return d == 0 ? 1 : (d == 1 ? 2 : 4); }
+
+// Zstandard (TIFF compression 50000, the reference's other output option ('ZSTD', level)): libzstd is bound at run time —
+// the image ships the library without its header; absent library => those files report B2SIO_ERR_UNSUPPORTED.
+struct Zstd {
+    size_t (*decompress)(void *, size_t, const void *, size_t) = nullptr;
+    size_t (*compress)(void *, size_t, const void *, size_t, int) = nullptr;
+    size_t (*bound)(size_t) = nullptr;
+    unsigned (*is_error)(size_t) = nullptr;
+    bool ok = false;
+    Zstd()
+    {
+        void *h = nullptr;
+        for (const char *name : {"libzstd.so.1", "libzstd.so"})
+            if ((h = dlopen(name, RTLD_NOW | RTLD_LOCAL))) break;
+        if (!h) return;
+        decompress = (decltype(decompress))dlsym(h, "ZSTD_decompress");
+        compress = (decltype(compress))dlsym(h, "ZSTD_compress");
+        bound = (decltype(bound))dlsym(h, "ZSTD_compressBound");
+        is_error = (decltype(is_error))dlsym(h, "ZSTD_isError");
+        ok = decompress && compress && bound && is_error;
+    }
+};
+const Zstd &zstd()
+{
+    static const Zstd z;
+    return z;
+}
 
 bool host_is_le()
 {
@@ -212,7 +240,8 @@ int parse_tiff(const uint8_t *p, size_t size, const char *path, Tiff &t)
     else if (t.bits == 16 && t.sample_format == 1) t.dtype = 1;
     else if (t.bits == 32 && t.sample_format == 3) t.dtype = 2;
     else return fail(B2SIO_ERR_UNSUPPORTED, "%s: %d-bit samples of format %d", path, t.bits, t.sample_format);
-    if (t.compression != 1 && t.compression != 5 && t.compression != 8 && t.compression != 32946)
+    if (t.compression != 1 && t.compression != 5 && t.compression != 8 && t.compression != 32946 &&
+        !(t.compression == 50000 && zstd().ok))
         return fail(B2SIO_ERR_UNSUPPORTED, "%s: TIFF compression %d", path, t.compression);
     if (t.predictor != 1 && t.predictor != 2) return fail(B2SIO_ERR_UNSUPPORTED, "%s: TIFF predictor %d", path, t.predictor);
     if (t.predictor == 2 && t.dtype == 2) return fail(B2SIO_ERR_UNSUPPORTED, "%s: horizontal predictor on float samples", path);
@@ -300,6 +329,12 @@ int decode_chunk(const Tiff &t, const uint8_t *src, size_t n, uint8_t *dst, size
     }
     if (t.compression == 5) {
         const size_t got = lzw_decode(src, n, dst, want);
+        if (got < want) memset(dst + got, 0, want - got);
+        return 0;
+    }
+    if (t.compression == 50000) {
+        const size_t got = zstd().decompress(dst, want, src, n);
+        if (zstd().is_error(got)) return fail(B2SIO_ERR_FORMAT, "%s: zstd decompression failed", path);
         if (got < want) memset(dst + got, 0, want - got);
         return 0;
     }
@@ -468,8 +503,11 @@ int write_all(int fd, const void *p, size_t n, const char *path)
 
 int write_tiff(const char *path, const void *src, int32_t height, int32_t width, int32_t dtype, int level, int n_threads)
 {
-    if (!path || !src || height <= 0 || width <= 0 || dtype < 0 || dtype > 2 || level < 0 || level > 9)
+    const bool use_zstd = level > 100;
+    const int zlevel = use_zstd ? level - 100 : 0;
+    if (!path || !src || height <= 0 || width <= 0 || dtype < 0 || dtype > 2 || level < 0 || (level > 9 && !(use_zstd && zlevel <= 22)))
         return fail(B2SIO_ERR_INVALID, "bad argument");
+    if (use_zstd && !zstd().ok) return fail(B2SIO_ERR_UNSUPPORTED, "libzstd is not available");
     if (!host_is_le()) return fail(B2SIO_ERR_UNSUPPORTED, "the writer emits little-endian TIFF from a little-endian host only");
     const int es = dtype_size(dtype);
     const size_t row_bytes = (size_t)width * es, total = row_bytes * (size_t)height;
@@ -485,6 +523,13 @@ int write_tiff(const char *path, const void *src, int32_t height, int32_t width,
         parallel_for(n_strips, n_threads, [&](int64_t s) {
             const int64_t y0 = s * rps, rows = std::min(rps, height - y0);
             const uLong n = (uLong)((size_t)rows * row_bytes);
+            if (use_zstd) {
+                comp[s].resize(zstd().bound(n));
+                const size_t got = zstd().compress(comp[s].data(), comp[s].size(), in + (size_t)y0 * row_bytes, n, zlevel);
+                if (zstd().is_error(got)) err.store(1);
+                else comp[s].resize(got);
+                return;
+            }
             uLongf cap = compressBound(n);
             comp[s].resize(cap);
             if (compress2(comp[s].data(), &cap, in + (size_t)y0 * row_bytes, n, level) != Z_OK) err.store(1);
@@ -516,7 +561,7 @@ int write_tiff(const char *path, const void *src, int32_t height, int32_t width,
     struct Ent { uint16_t tag, type; uint32_t count, value; };
     std::vector<Ent> ents = {
         {256, 4, 1, (uint32_t)width}, {257, 4, 1, (uint32_t)height}, {258, 3, 1, (uint32_t)(8 * es)},
-        {259, 3, 1, (uint32_t)(level > 0 ? 8 : 1)}, {262, 3, 1, 1},
+        {259, 3, 1, (uint32_t)(use_zstd ? 50000 : (level > 0 ? 8 : 1))}, {262, 3, 1, 1},
         {273, 4, (uint32_t)n_strips, n_strips > 1 ? offs_at : offs[0]}, {277, 3, 1, 1}, {278, 4, 1, (uint32_t)rps},
         {279, 4, (uint32_t)n_strips, n_strips > 1 ? cnts_at : cnts[0]}, {284, 3, 1, 1}, {339, 3, 1, (uint32_t)(dtype == 2 ? 3 : 1)},
     };

@@ -110,6 +110,9 @@ def _level(compression):
     if name in ("ADOBE_DEFLATE", "DEFLATE", "ZLIB", "8"):
         level = 6 if level is None else int(level)
         return 0 if level <= 0 else min(level, 9)
+    if name in ("ZSTD", "50000"):                      # the reference's other option: compression=('ZSTD', 1)
+        level = 1 if level is None else int(level)
+        return 100 + max(1, min(level, 22))
     return None
 
 

@@ -10,7 +10,7 @@
  *
  * Plain C ABI, no CUDA: this library only touches host memory.  Host binding: pystripe/_io.py (ctypes).
  * Supported TIFF subset (what light-sheet tile stacks are): classic and BigTIFF, II / MM byte order, one sample per
- * pixel, 8 / 16-bit unsigned or 32-bit float, strips or tiles, compression none (1), LZW (5), deflate (8, 32946),
+ * pixel, 8 / 16-bit unsigned or 32-bit float, strips or tiles, compression none (1), LZW (5), deflate (8, 32946), ZSTD (50000),
  * predictor none or horizontal differencing (2); the first IFD is the image.  Anything else returns
  * B2SIO_ERR_UNSUPPORTED and the Python host falls back to Pillow for that file, as the reference does.
  */
@@ -66,8 +66,8 @@ int b2sio_read_batch(const char *const *paths, int n_files, void *dst, size_t pl
                      int32_t width, int32_t dtype, int n_threads, int32_t *status);
 
 /* replaces: imsave_tif (core.py:276-334): one classic little-endian TIFF, strips of whole rows.
- * deflate_level 0 = uncompressed (compression tag 1), 1..9 = ADOBE_DEFLATE (tag 8) at that zlib level, strips compressed
- * in parallel on n_threads.  The file is written under a temporary name and renamed, mode 0777 like the reference. */
+ * deflate_level 0 = uncompressed (compression tag 1), 1..9 = ADOBE_DEFLATE (tag 8) at that zlib level, 100 + L (L = 1..22) =
+ * Zstandard (tag 50000) at level L when libzstd can be loaded; strips compressed in parallel on n_threads.  The file is written under a temporary name and renamed, mode 0777 like the reference. */
 int b2sio_write_tiff(const char *path, const void *src, int32_t height, int32_t width, int32_t dtype, int deflate_level,
                      int n_threads);
 

@@ -188,3 +188,20 @@ def test_batch_reports_per_file_status(tmp_path):
     with pytest.raises(_io.CodecError) as e:
         _io.read(missing)
     assert e.value.code == _io.ERR_IO
+
+
+def test_zstd_tiff_round_trip(tmp_path):
+    """compression=('ZSTD', level) is the reference GUI's other output option (TIFF tag 50000); libzstd is bound at run time."""
+    img = _tile(400, 333, np.uint16, seed=4)
+    p = tmp_path / "z.tif"
+    if not _io.can_write(img, ("ZSTD", 1)):
+        pytest.skip("no libzstd")
+    try:
+        _io.write_tiff(p, img, ("ZSTD", 1))
+    except _io.CodecError as e:
+        if e.code == _io.ERR_UNSUPPORTED:
+            pytest.skip("libzstd could not be loaded")
+        raise
+    assert _io.probe(p)[2].compression == 50000
+    assert np.array_equal(_io.read(p), img) and np.array_equal(_io.read(p, threads=1), img)
+    assert p.stat().st_size < img.nbytes
