@@ -247,10 +247,13 @@ def test_bleach_plan_args_host_logic():
     assert b[5] == float(np.float32(5.0)) and b[6] == 6.5
     b2, _ = core._bleach_plan_args(0.01, 4.8, 5.6, 7.4, False, False)           # weak Python floats: float32 bounds
     assert b2[4] == float(np.float32(4.8)) and b2[6] == float(np.float32(7.4))
-    with pytest.raises(NotImplementedError):
-        core._bleach_plan_args(0.01, None, 5.0, 6.0, False, False)
+    per_plane, _ = core._bleach_plan_args(0.01, None, 5.0, 6.0, False, False)    # a level left to multi-Otsu (core.py:1066-1077):
+    assert per_plane[8] == 1 and per_plane[4:7] == (0.0, 0.0, 0.0)               # per-plane device data, not plan constants
     assert core._bleach_plan_args(0.01, 4.0, 5.0, 6.0, True, False)[0][7] == 2    # max method (batch_filter's default)
-    assert b[7] == 1
+    assert b[7] == 1 and b[8] == 0
+    # per-plane levels: multi-Otsu values for the missing ones, the same checks and float32 / float64 rules as explicit levels
+    lv = core._clip_levels(np.float32(0.5), np.float32(5.0), 6.5)
+    assert lv == (float(np.log1p(1)), 5.0, float(np.float32(6.5)))
     with pytest.raises(NotImplementedError):
         core._bleach_plan_args(None, None, None, None, False, True)
     with pytest.raises(AssertionError):
