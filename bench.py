@@ -418,6 +418,34 @@ def batch_filter_leg(a, cfg, core, _io, base, flat, local, world, barrier, max_o
         shutil.rmtree(work, ignore_errors=True)
 
 
+def notch_lane_ops_per_row(n):
+    """FP32 lane-ops of the O(radix^2) phases of scipy's real transform of length n (rfftp, generic odd radices 7 .. 133),
+    forward + backward, exact mode (separate multiply and add): per generic pass ido * l1 * (ipph - 1)^2 cos/sin pairs.
+    Returns None for lengths that run as another plan class (even > 1000, Bluestein)."""
+    if n < 2 or (n > 1000 and n % 2 == 0):
+        return None
+    f, m = [], n
+    while m % 4 == 0:
+        f.append(4); m //= 4
+    if m % 2 == 0:
+        f.append(2); m //= 2
+    d = 3
+    while d * d <= m:
+        while m % d == 0:
+            f.append(d); m //= d
+        d += 2
+    if m > 1:
+        f.append(m)
+    if any(p >= 135 for p in f):
+        return None
+    ops = 0
+    for p in f:
+        if p > 5:
+            ipph = (p + 1) // 2
+            ops += (n // p) * (ipph - 1) ** 2 * 2 * 2          # idl1 x pairs x (cos, sin) x (mul, add)
+    return 2 * ops if ops else None
+
+
 def roofline(a, ctx, info, run, d_in, P, ms_max):
     ctx.timing_enable(True)
     ctx.timing_read(reset=True)
@@ -445,7 +473,8 @@ def roofline(a, ctx, info, run, d_in, P, ms_max):
             macs = 2 * F * rows[lvl] * cols[lvl - 1] + 4 * F * rows[lvl] * cols[lvl]
             return b, 2 * macs
         if kname == "notch" and lvl >= 1:
-            return 8 * rows[lvl] * cols[lvl], None
+            per_row = notch_lane_ops_per_row(cols[lvl])
+            return 8 * rows[lvl] * cols[lvl], (per_row * rows[lvl] if per_row else None)
         if kname == "prologue":
             return 2 * wh * ww + (4 * wh * ww if CONFIGS[a.config]["flat"] and a.config == 2 else 0) + 4 * rows[0] * cols[0], None
         if kname == "epilogue":
@@ -472,9 +501,11 @@ def roofline(a, ctx, info, run, d_in, P, ms_max):
     fp32 = {"flops_per_plane_model": int(info.flops_per_plane), "peak_lane_ops_per_s": fp32_peak,
             "whole_pipeline_frac": info.flops_per_plane * a.steps * P / (ms_max * 1e-3) / fp32_peak,
             "kernel_frac": (lane_ops * n_pass * planes_timed / (kms * 1e-3) / fp32_peak) if lane_ops else None,
-            "note": "exact mode issues a separate multiply and add per tap (2 lane-ops per MAC): the FP32 pipe, not HBM, is "
-                    "the ceiling of the DWT kernels; kernel_frac = the dominant kernel's lane-ops / its time / peak"}
-    roof = {"bound": "hbm", "kernel": f"{kname}@level{lvl}" if lvl else kname, "achieved": achieved, "peak": peak,
+            "note": "exact mode issues a separate multiply and add per tap / butterfly term (2 lane-ops per MAC): instruction issue "
+                    "and the FP32 pipe, not HBM, bound the DWT and notch kernels; kernel_frac = the dominant kernel's modelled "
+                    "lane-ops (DWT: taps; notch: the O(radix^2) phases of scipy's generic radices only) / its time / peak"}
+    roof = {"bound": "hbm", "binding_in_practice": "instruction issue / FP32 pipe (ncu: profiles/r02_main_kernels.md)",
+            "kernel": f"{kname}@level{lvl}" if lvl else kname, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "fp32": fp32,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
             "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
