@@ -220,6 +220,59 @@ __device__ __forceinline__ float b2s_expm1f_dev(float x)
     return b2s_i2f(b2s_f2i(y) + (k << 23));
 }
 
+// Branch-free variants of the two hot paths for loops that evaluate several pixels per thread: the same operations in
+// the same order, but an argument outside the hot range (or log1p's |f| < 2^-20 case) only raises `bad` — the caller
+// re-evaluates such a group of pixels with b2s_log1pf_dev / b2s_expm1f_dev.  One reconvergence point per group instead of
+// three per pixel (BRA + BSSY + BSYNC were 14 % of k_prologue's instructions, profiles/r02_pre_tma_pro.source.csv.gz).
+__device__ __forceinline__ float b2s_log1pf_hot(float x, bool &bad)
+{
+    const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f;
+    const float Lp1 = 6.6666668653e-01f, Lp2 = 4.0000000596e-01f, Lp3 = 2.8571429849e-01f,
+                Lp4 = 2.2222198546e-01f, Lp5 = 1.8183572590e-01f, Lp6 = 1.5313838422e-01f,
+                Lp7 = 1.4798198640e-01f;
+    bad |= !(x >= 0.5f && x < 1.0e9f);
+    float u = 1.0f + x;
+    int32_t hu = b2s_f2i(u);
+    int32_t k = (hu >> 23) - 127;
+    float c = (k > 0) ? 1.0f - (u - x) : x - (u - 1.0f);
+    c = b2s_div_hot(c, u);
+    hu &= 0x007fffff;
+    const bool low = hu < 0x3504f7;
+    k += low ? 0 : 1;
+    u = b2s_i2f(hu | (low ? 0x3f800000 : 0x3f000000));
+    hu = low ? hu : ((0x00800000 - hu) >> 2);
+    bad |= hu == 0;
+    const float f = u - 1.0f;
+    const float hfsq = 0.5f * f * f;
+    const float s = b2s_div_hot(f, 2.0f + f);
+    const float z = s * s;
+    const float R = z * (Lp1 + z * (Lp2 + z * (Lp3 + z * (Lp4 + z * (Lp5 + z * (Lp6 + z * Lp7))))));
+    const float kf = (float)k;
+    return kf * ln2_hi - ((hfsq - (s * (hfsq + R) + (kf * ln2_lo + c))) - f);
+}
+
+__device__ __forceinline__ float b2s_expm1f_hot(float x, bool &bad)
+{
+    bad |= !(x >= 1.1f && x < 15.5f);                           // here 2 <= k <= 22: one form of the final scaling
+    const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f, invln2 = 1.4426950216e+00f;
+    const float Q1 = -3.3333335072e-02f, Q2 = 1.5873016091e-03f, Q3 = -7.9365076090e-05f,
+                Q4 = 4.0082177293e-06f, Q5 = -2.0109921195e-07f;
+    const int32_t k = (int32_t)(invln2 * x + 0.5f);
+    const float t = (float)k;
+    const float hi = x - t * ln2_hi, lo = t * ln2_lo;
+    const float xr = hi - lo;
+    const float c = (hi - xr) - lo;
+    const float hfx = 0.5f * xr;
+    const float hxs = xr * hfx;
+    const float r1 = 1.0f + hxs * (Q1 + hxs * (Q2 + hxs * (Q3 + hxs * (Q4 + hxs * Q5))));
+    const float tt = 3.0f - r1 * hfx;
+    float e = hxs * b2s_div_hot(r1 - tt, 6.0f - xr * tt);
+    e = (xr * (e - c) - c);
+    e -= hxs;
+    const float y = b2s_i2f(0x3f800000 - (0x1000000 >> (k & 31))) - (e - xr);
+    return b2s_i2f(b2s_f2i(y) + (k << 23));
+}
+
 __device__ __forceinline__ float b2s_log1pf_dev(float x)
 {
     if (!(x >= 0.5f && x < 1.0e9f)) return b2s_log1pf(x);     // here k != 0 and hx < 0x5a000000

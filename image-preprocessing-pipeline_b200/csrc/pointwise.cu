@@ -5,6 +5,8 @@
 //   epilogue : crop -> expm1 -> rint/clip -> dark -> convert -> flip/rot  (core.py:1124-1158, 1324-1330, 1361-1379, 397-423)
 //   uniform  : per-plane "all pixels equal" flag                          (core.py:106-121, 1232-1246)
 //   pre-ops  : flat division, 5x5 Gaussian (cv2 fixed point), block reduce (core.py:1248-1300)
+#include <cstdlib>
+
 #include "b2s_internal.h"
 #include "libm_mirror.h"
 #include "../../include/b200stripe.h"
@@ -79,15 +81,40 @@ __global__ void __launch_bounds__(256) k_prologue(B2sPrologueArgs a)
         if (a.in_dtype == B2S_U16 && (a.src_cols & 3) == 0 && (reinterpret_cast<uintptr_t>(a.in) & 7) == 0) {
             // 4 pixels per thread and trip: one 64-bit load of the samples (rows start 8-byte aligned: cols % 4 == 0)
             const uint2 *in4 = reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned short *>(a.in) + base);
+            const bool flat4 = flat && (reinterpret_cast<uintptr_t>(flat) & 15) == 0;
             for (int x4 = threadIdx.x; x4 < (a.src_cols >> 2); x4 += 256) {
                 const uint2 p = __ldg(in4 + x4);
                 const unsigned v[4] = {p.x & 0xffffu, p.x >> 16, p.y & 0xffffu, p.y >> 16};
                 float4 o;
                 float *po = &o.x;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    klo = min(klo, v[k]); khi = max(khi, v[k]);
-                    po[k] = a.lut ? __ldg(a.lut + v[k]) : prologue_value(a, (float)v[k], flat, 4 * x4 + k);
+                for (int k = 0; k < 4; ++k) { klo = min(klo, v[k]); khi = max(khi, v[k]); }
+                if (a.lut) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) po[k] = __ldg(a.lut + v[k]);
+                } else {
+                    // hot path for the four pixels at once (no per-pixel branches); a group with an argument outside the hot
+                    // ranges is evaluated again by the general routines
+                    float fl[4] = {1.f, 1.f, 1.f, 1.f};
+                    if (flat4) {
+                        const float4 f4 = __ldg(reinterpret_cast<const float4 *>(flat) + x4);
+                        fl[0] = f4.x; fl[1] = f4.y; fl[2] = f4.z; fl[3] = f4.w;
+                    } else if (flat) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) fl[k] = __ldg(flat + 4 * x4 + k);
+                    }
+                    bool bad = false;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float r = (float)v[k];
+                        if (flat) { bad |= !(fl[k] > 1.0e-18f && fl[k] < 1.0e18f); r = b2s_div_hot(r, fl[k]); }
+                        if (a.use_log1p) r = b2s_log1pf_hot(r, bad);
+                        po[k] = r;
+                    }
+                    if (bad) {
+#pragma unroll 1
+                        for (int k = 0; k < 4; ++k) po[k] = prologue_value(a, (float)v[k], flat, 4 * x4 + k);
+                    }
                 }
                 *reinterpret_cast<float4 *>(s_row + 4 * x4) = o;
             }
@@ -221,6 +248,71 @@ __global__ void __launch_bounds__(256) k_epilogue_rows(B2sEpilogueArgs a)
         }
     }
     if (a.out_dtype == B2S_U8) {
+        unsigned char *o = reinterpret_cast<unsigned char *>(a.out) + oidx;
+        if (nvalid == 4 && (oidx & 3) == 0) *reinterpret_cast<uchar4 *>(o) = make_uchar4(u[0], u[1], u[2], u[3]);
+        else for (int k = 0; k < nvalid; ++k) o[k] = (unsigned char)u[k];
+    } else {
+        unsigned short *o = reinterpret_cast<unsigned short *>(a.out) + oidx;
+        if (nvalid == 4 && (oidx & 3) == 0) *reinterpret_cast<ushort4 *>(o) = make_ushort4(u[0], u[1], u[2], u[3]);
+        else for (int k = 0; k < nvalid; ++k) o[k] = (unsigned short)u[k];
+    }
+}
+
+// The common destripe epilogue (log domain, every value exact in float32, no rotation) with its branches resolved at
+// compile time and the branch-free expm1 hot path: crop -> expm1 -> [rint, clip] -> dark -> final conversion, 4 pixels per
+// thread.  Same arithmetic as k_epilogue_rows, which keeps every other combination.
+template <bool INT, bool TO8, bool U8>
+__global__ void __launch_bounds__(256) k_epilogue_fast(const B2sEpilogueArgs a)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int i = blockIdx.y;
+    if (x4 >= a.out_cols) return;
+    const size_t plane = blockIdx.z;
+    const size_t oidx = plane * (size_t)a.out_rows * a.out_cols + (size_t)i * a.out_cols + x4;
+    const int nvalid = min(4, a.out_cols - x4);
+    unsigned u[4] = {0u, 0u, 0u, 0u};
+    const bool zero_plane = a.uniform_mm && a.uniform_mm[2 * plane] == ~a.uniform_mm[2 * plane + 1];
+    if (!zero_plane) {
+        const int y = a.flip ? a.rows - 1 - i : i;
+        const float *src = a.in.ptr + plane * a.in.plane_stride + (size_t)(y + a.base_pad) * a.in.pitch + (x4 + a.base_pad);
+        float v[4];
+        if (nvalid == 4) {
+            const float2 p0 = __ldg(reinterpret_cast<const float2 *>(src)), p1 = __ldg(reinterpret_cast<const float2 *>(src + 2));
+            v[0] = p0.x; v[1] = p0.y; v[2] = p1.x; v[3] = p1.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = k < nvalid ? __ldg(src + k) : 1.5f;
+        }
+        const float hi_w = a.work_dtype == B2S_U8 ? 255.f : 65535.f;
+        const float darkf = (float)a.dark;
+        const int shift = a.shift;
+        float e[4];
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e[k] = b2s_expm1f_hot(v[k], bad);
+        if (bad) {   // (unrolled: dynamic indexing would push e[] / v[] into local memory)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[k] = b2s_expm1f_dev(v[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float vf = e[k];
+            if (INT) vf = fminf(fmaxf(rintf(vf), 0.f), hi_w);   // core.py:1153-1158
+            if (darkf > 0.f) vf = vf > darkf ? __fsub_rn(vf, darkf) : 0.f;
+            if (TO8) {
+                const float c = vf < 0.f ? 0.f : (vf > 65535.f ? 65535.f : vf);
+                unsigned w = (unsigned)c;
+                const unsigned lower = 1u << shift;
+                w = (w > 0 && w < lower) ? 1u : (w >> shift);
+                u[k] = w > 255u ? 255u : w;
+            } else {
+                const float hi = U8 ? 255.f : 65535.f;
+                const float c = vf < 0.f ? 0.f : (vf > hi ? hi : vf);
+                u[k] = (unsigned)c;
+            }
+        }
+    }
+    if (U8) {
         unsigned char *o = reinterpret_cast<unsigned char *>(a.out) + oidx;
         if (nvalid == 4 && (oidx & 3) == 0) *reinterpret_cast<uchar4 *>(o) = make_uchar4(u[0], u[1], u[2], u[3]);
         else for (int k = 0; k < nvalid; ++k) o[k] = (unsigned char)u[k];
@@ -483,6 +575,22 @@ void b2s_launch_epilogue(const B2sEpilogueArgs &a, int n_planes, cudaStream_t s)
 {
     if (a.destripe && a.rot == 0 && a.final_mode != 3) {
         dim3 grid(((a.out_cols + 3) / 4 + 255) / 256, a.out_rows, n_planes);
+        static const bool no_fast = getenv("B2S_EPILOGUE_GENERIC") != nullptr;
+        if (a.use_log1p && a.f32_exact && !a.ls_sub && !no_fast) {
+            const bool to8 = a.final_mode == 2, u8 = a.out_dtype == B2S_U8;
+            if (!(to8 && !u8)) {   // convert_to_8bit always writes uint8
+                const int sel = (a.int_path ? 4 : 0) | (to8 ? 2 : 0) | (u8 ? 1 : 0);
+                switch (sel) {
+                case 0: k_epilogue_fast<false, false, false><<<grid, 256, 0, s>>>(a); return;
+                case 1: k_epilogue_fast<false, false, true><<<grid, 256, 0, s>>>(a); return;
+                case 3: k_epilogue_fast<false, true, true><<<grid, 256, 0, s>>>(a); return;
+                case 4: k_epilogue_fast<true, false, false><<<grid, 256, 0, s>>>(a); return;
+                case 5: k_epilogue_fast<true, false, true><<<grid, 256, 0, s>>>(a); return;
+                case 7: k_epilogue_fast<true, true, true><<<grid, 256, 0, s>>>(a); return;
+                default: break;
+                }
+            }
+        }
         k_epilogue_rows<<<grid, 256, 0, s>>>(a);
         return;
     }

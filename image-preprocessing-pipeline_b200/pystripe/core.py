@@ -1262,10 +1262,10 @@ def batch_filter(
     # H2D / kernels / D2H (a single 8-plane call runs them back to back: 10 vs 19 Gpx/s measured at 2048^2)
     per_gpu = -(-num_images // len(gpus))
     group = int(os.environ.get("B200STRIPE_FILE_GROUP", "0")) or max(batch, min(8 * batch, 64, -(-per_gpu // 6)))
-    # writing costs about twice what reading does per thread (new pages of the output files): 1/3 decode, 2/3 encode
+    # writing costs about twice what reading does per thread (new pages of the output files): the encoder is the bottleneck stage
     per_pipe = max(2, workers // len(gpus))
     read_threads = max(1, per_pipe // 3)
-    write_threads = max(1, per_pipe - read_threads)
+    write_threads = per_pipe          # mild over-subscription: the reader blocks on its bounded queue most of the time
     print(f"{PrintColors.GREEN}{date_time_now()}: {PrintColors.ENDC}"
           f"using {workers} decode/encode threads and {len(gpus)} GPU(s). {num_images} images need to be processed.",
           flush=True)
