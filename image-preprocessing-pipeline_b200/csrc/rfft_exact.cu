@@ -183,14 +183,25 @@ __device__ void radf5(const Ctx &c, int ido, int l1, const float *cc, float *ch,
 // advance in lock step, so they share packed f32x2 instructions: products as fma(t, v, -0.0) (an exactly rounded
 // product that ptxas cannot re-contract with the following add; -0.0 arrives as a kernel argument), sums as FADD2 in
 // the reference's association order.
+// exact integer division by a per-pass constant: q = umulhi(it, magic), magic = floor(2^32 / d) + 1 (0 encodes d == 1);
+// valid while it * d < 2^32, which the plan builder checks
+__device__ __forceinline__ int fdiv(int it, unsigned magic) { return magic ? (int)__umulhi((unsigned)it, magic) : it; }
+
 constexpr int kLBMax = 8;   // outputs (l values) per thread in the O(radix^2) phase: 4 .. 8, chosen per pass (XPass::lb) so that the
                            // equally heavy items fill whole rounds of the CTA's item slots
 constexpr int kRow = 68;   // float2 entries per table row (radix < 135 => at most 66 columns); compile-time so that the LB rows
                           // a thread reads sit at immediate offsets from one running pointer
 __device__ __forceinline__ float2 mul2x(float2 t, float2 v, float2 nz) { return __ffma2_rn(t, v, nz); }
-template <int LB>
+// MODE 0: store the pair (cos sum, sin sum) of output l at (ik, l) and (ik, ip - l) of dst.
+// MODE 1 (radfg): the sums of one item are all that the rest of the forward pass needs — its shuffle into the r2hc layout
+//   and, for i >= 1, the sum / difference of the pair — so they are stored straight at their final positions
+//   OUT(a, b, k) = dst[a + ido * (b + ip * k)]:  i == 0: OUT(ido-1, 2l-1, k) = X, OUT(0, 2l, k) = Y;
+//   i odd: OUT(i, 2l, k) = X + Y, OUT(ido-i-2, 2l-1, k) = X - Y;  i even: OUT(i, 2l, k) = X + Y, OUT(ido-i, 2l-1, k) = Y - X
+//   (the same single add / subtract of the same two floats as pocketfft's last loop of radfg).
+// MODE 2 (radbg with ido == 1): every item is an i == 0 item: dst(ik, l) = X - Y, dst(ik, ip - l) = X + Y (pocketfft's PM).
+template <int LB, int MODE>
 __device__ __forceinline__ void generic_block(const Ctx &c, const float *src, float *dst, const float2 *sgt, int ip,
-                                              int ipph, int idl1, int lb, int ik, float2 nz)
+                                              int ipph, int idl1, int lb, int ik, float2 nz, int ido = 1, unsigned m_ido = 0)
 {
     const int l0 = 1 + LB * lb, nl = min(LB, ipph - l0);
     const int st = idl1 * c.GP;
@@ -247,29 +258,57 @@ __device__ __forceinline__ void generic_block(const Ctx &c, const float *src, fl
             A[q] = __fadd2_rn(A[q], mul2x(t, v0, nz));
         }
     }
-    float *pd = dst + ik * c.GP + c.r;
+    if (MODE == 0) {
+        float *pd = dst + ik * c.GP + c.r;
 #pragma unroll
-    for (int q = 0; q < LB; ++q)
-        if (q < nl) { pd[(l0 + q) * st] = A[q].x; pd[(ip - l0 - q) * st] = A[q].y; }
-}
-
-__device__ __forceinline__ void generic_block_lb(int LBsel, const Ctx &c, const float *src, float *dst, const float2 *sgt, int ip,
-                                                 int ipph, int idl1, int lb, int ik, float2 nz)
-{
-    switch (LBsel) {
-    case 4: generic_block<4>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz); break;
-    case 5: generic_block<5>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz); break;
-    case 6: generic_block<6>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz); break;
-    case 7: generic_block<7>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz); break;
-    default: generic_block<8>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz); break;
+        for (int q = 0; q < LB; ++q)
+            if (q < nl) { pd[(l0 + q) * st] = A[q].x; pd[(ip - l0 - q) * st] = A[q].y; }
+    } else if (MODE == 2) {
+        float *pd = dst + ik * c.GP + c.r;
+#pragma unroll
+        for (int q = 0; q < LB; ++q)
+            if (q < nl) { pd[(l0 + q) * st] = A[q].x - A[q].y; pd[(ip - l0 - q) * st] = A[q].x + A[q].y; }
+    } else {
+        const int k = fdiv(ik, m_ido), i = ik - k * ido;
+        // element (a, b) of block k: dst[(a + ido * (b + ip * k)) * GP + r]
+        float *blk = dst + (ido * ip * k) * c.GP + c.r;
+        const int rs = ido * c.GP;                       // one step of b
+        int a1, a2;                                      // first index of the 2l row and of the 2l-1 row
+        if (i == 0) { a1 = 0; a2 = ido - 1; }
+        else if (i & 1) { a1 = i; a2 = ido - i - 2; }
+        else { a1 = i; a2 = ido - i; }
+        float *p1 = blk + a1 * c.GP, *p2 = blk + a2 * c.GP;
+#pragma unroll
+        for (int q = 0; q < LB; ++q) {
+            if (q < nl) {
+                const int l = l0 + q;
+                const float X = A[q].x, Y = A[q].y;
+                float hi, lo;                            // -> row 2l, row 2l-1
+                if (i == 0) { hi = Y; lo = X; }
+                else if (i & 1) { hi = X + Y; lo = X - Y; }
+                else { hi = X + Y; lo = Y - X; }
+                p1[(2 * l) * rs] = hi;
+                p2[(2 * l - 1) * rs] = lo;
+            }
+        }
     }
 }
 
-// exact integer division by a per-pass constant: q = umulhi(it, magic), magic = floor(2^32 / d) + 1 (0 encodes d == 1);
-// valid while it * d < 2^32, which the plan builder checks
-__device__ __forceinline__ int fdiv(int it, unsigned magic) { return magic ? (int)__umulhi((unsigned)it, magic) : it; }
+template <int MODE>
+__device__ __forceinline__ void generic_block_lb(int LBsel, const Ctx &c, const float *src, float *dst, const float2 *sgt, int ip,
+                                                 int ipph, int idl1, int lb, int ik, float2 nz, int ido = 1, unsigned m_ido = 0)
+{
+    switch (LBsel) {
+    case 4: generic_block<4, MODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
+    case 5: generic_block<5, MODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
+    case 6: generic_block<6, MODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
+    case 7: generic_block<7, MODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
+    default: generic_block<8, MODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
+    }
+}
 
-// generic odd radix, forward; the result ends in cc.  `cs` is a shared-memory copy of csarr (2*ip floats).
+
+// generic odd radix, forward; the result ends in ch.  `cs` is a shared-memory copy of csarr (2*ip floats).
 __device__ void radfg(const Ctx &c, const XPass &P, float *cc, float *ch, const float *wa, const float2 *gt, float2 *sgt, float2 nz)
 {
     const int ido = P.ido, ip = P.ip, l1 = P.l1;
@@ -303,35 +342,16 @@ __device__ void radfg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
         PM(C1(0, k, j), C1(0, k, jc), t2, t1)
     }
     __syncthreads();
+    // O(ip^2) phase; every item stores its results at their final r2hc positions in ch (see generic_block, MODE 1), the
+    // l == 0 item (the plain sum) at OUT(i, 0, k): the result of the pass is in ch
     FOR_ITEMS(it, (nlb + 1) * idl1) {
         const int lb = fdiv(it, P.m_idl1), ik = it - lb * idl1;
         if (lb == nlb) {
             float s = C2(ik, 0);
             for (int j = 1; j < ipph; ++j) s += C2(ik, j);
-            CH2(ik, 0) = s;
-        } else generic_block_lb(LB, c, cc, ch, sgt, ip, ipph, idl1, lb, ik, nz);
-    }
-    __syncthreads();
-    FOR_ITEMS(it, l1 * ido) {
-        const int k = fdiv(it, P.m_ido), i = it - k * ido;
-        CC(i, 0, k) = CH(i, k, 0);
-    }
-    FOR_ITEMS(it, (ipph - 1) * l1) {
-        const int jj = fdiv(it, P.m_l1), k = it - jj * l1, j = jj + 1, jc = ip - j, j2 = 2 * j - 1;
-        CC(ido - 1, j2, k) = CH(0, k, j);
-        CC(0, j2 + 1, k) = CH(0, k, jc);
-    }
-    if (ido > 1) {
-        const int ni = (ido - 1) >> 1;
-        FOR_ITEMS(it, (ipph - 1) * l1 * ni) {
-            const int jj = fdiv(it, P.m_l1ni), rem = it - jj * (l1 * ni);
-            const int k = fdiv(rem, P.m_ni), i = 1 + 2 * (rem - k * ni), ic = ido - i - 2;
-            const int j = jj + 1, jc = ip - j, j2 = 2 * j - 1;
-            CC(i, j2 + 1, k) = CH(i, k, j) + CH(i, k, jc);
-            CC(ic, j2, k) = CH(i, k, j) - CH(i, k, jc);
-            CC(i + 1, j2 + 1, k) = CH(i + 1, k, j) + CH(i + 1, k, jc);
-            CC(ic + 1, j2, k) = CH(i + 1, k, jc) - CH(i + 1, k, j);
-        }
+            const int k = fdiv(ik, P.m_ido), i = ik - k * ido;
+            ch[IDX(i + ido * (cdim * k))] = s;
+        } else generic_block_lb<1>(LB, c, cc, ch, sgt, ip, ipph, idl1, lb, ik, nz, ido, P.m_ido);
     }
 #undef CC
 #undef CH
@@ -484,8 +504,8 @@ __device__ void radb5(const Ctx &c, int ido, int l1, const float *cc, float *ch,
 #undef CH
 }
 
-// generic odd radix, backward; the result ends in ch
-__device__ void radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const float *wa, const float2 *gt, float2 *sgt, float2 nz)
+// generic odd radix, backward; returns true when the result ends in ch (false: in cc, the ido == 1 case)
+__device__ bool radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const float *wa, const float2 *gt, float2 *sgt, float2 nz)
 {
     const int ido = P.ido, ip = P.ip, l1 = P.l1;
     const int cdim = ip, ipph = (ip + 1) / 2, idl1 = ido * l1;
@@ -517,6 +537,19 @@ __device__ void radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
         }
     }
     __syncthreads();
+    if (ido == 1) {
+        // every item is an i == 0 item: the PM that follows the O(ip^2) phase needs only the item's own two sums, so it is
+        // applied on the way out (generic_block MODE 2) and the pass is complete: its result is in cc, not in ch
+        FOR_ITEMS(it, (nlb + 1) * idl1) {
+            const int lb = fdiv(it, P.m_idl1), ik = it - lb * idl1;
+            if (lb == nlb) {
+                float s = CH2(ik, 0);
+                for (int j = 1; j < ipph; ++j) s += CH2(ik, j);
+                C2(ik, 0) = s;
+            } else generic_block_lb<2>(LB, c, ch, cc, sgt, ip, ipph, idl1, lb, ik, nz);
+        }
+        return false;
+    }
     // C2(ik, l >= 1) from CH2; the l == 0 item forms CH2(ik,0) + sum_j CH2(ik,j) and parks it in C2(ik,0) (cc's slot 0
     // is free) because the other items of this phase still read the old CH2(ik,0)
     FOR_ITEMS(it, (nlb + 1) * idl1) {
@@ -525,7 +558,7 @@ __device__ void radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
             float s = CH2(ik, 0);
             for (int j = 1; j < ipph; ++j) s += CH2(ik, j);
             C2(ik, 0) = s;
-        } else generic_block_lb(LB, c, ch, cc, sgt, ip, ipph, idl1, lb, ik, nz);
+        } else generic_block_lb<0>(LB, c, ch, cc, sgt, ip, ipph, idl1, lb, ik, nz);
     }
     __syncthreads();
     FOR_ITEMS(ik, idl1) CH2(ik, 0) = C2(ik, 0);
@@ -551,6 +584,7 @@ __device__ void radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
             CH(i + 1, k, jc) = v0 * b1 + v1 * a1;
         }
     }
+    return true;
 #undef CC
 #undef CH
 #undef C1
@@ -1099,7 +1133,7 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
             case 3: radf3(c, p.ido, p.l1, p1, p2, wa); break;
             case 4: radf4(c, p.ido, p.l1, p1, p2, wa); break;
             case 5: radf5(c, p.ido, p.l1, p1, p2, wa); break;
-            case 6: radfg(c, p, p1, p2, wa, reinterpret_cast<const float2 *>(a.tab + p.cs), sgt, nz); swap = false; break;
+            case 6: radfg(c, p, p1, p2, wa, reinterpret_cast<const float2 *>(a.tab + p.cs), sgt, nz); break;   // result in p2
             default: rblue<true>(c, a.blue, a.tab, p.ido, p.l1, p1, p2, wa, X0, X1); break;
             }
             __syncthreads();
@@ -1115,16 +1149,17 @@ __global__ void __launch_bounds__(kXT, 2) k_notch_exact(const __grid_constant__ 
         for (int f = 0; f < a.nf; ++f) {
             const XPass &p = a.bwd[f];
             const float *wa = a.tab + p.tw;
+            bool swap = true;
             switch (p.kind) {
             case 2: radb2(c, p.ido, p.l1, p1, p2, wa); break;
             case 3: radb3(c, p.ido, p.l1, p1, p2, wa); break;
             case 4: radb4(c, p.ido, p.l1, p1, p2, wa); break;
             case 5: radb5(c, p.ido, p.l1, p1, p2, wa); break;
-            case 6: radbg(c, p, p1, p2, wa, reinterpret_cast<const float2 *>(a.tab + p.cs), sgt, nz); break;
+            case 6: swap = radbg(c, p, p1, p2, wa, reinterpret_cast<const float2 *>(a.tab + p.cs), sgt, nz); break;
             default: rblue<false>(c, a.blue, a.tab, p.ido, p.l1, p1, p2, wa, X0, X1); break;
             }
             __syncthreads();
-            float *t = p1; p1 = p2; p2 = t;
+            if (swap) { float *t = p1; p1 = p2; p2 = t; }
         }
         // ---- scale by 1/n (copy_and_norm) and scatter
         if (!a.along_cols) {
