@@ -199,36 +199,48 @@ __device__ __forceinline__ float2 mul2x(float2 t, float2 v, float2 nz) { return 
 //   i odd: OUT(i, 2l, k) = X + Y, OUT(ido-i-2, 2l-1, k) = X - Y;  i even: OUT(i, 2l, k) = X + Y, OUT(ido-i, 2l-1, k) = Y - X
 //   (the same single add / subtract of the same two floats as pocketfft's last loop of radfg).
 // MODE 2 (radbg with ido == 1): every item is an i == 0 item: dst(ik, l) = X - Y, dst(ik, ip - l) = X + Y (pocketfft's PM).
-template <int LB, int MODE>
+// INMODE 0: the inputs are (src(ik, j), src(ik, ip - j)).
+// INMODE 1 (radfg with ido == 1): the PM that precedes the O(ip^2) phase is applied on the way in: (b + a, b - a) of the
+//   same two elements a = src(ik, j), b = src(ik, ip - j).
+// INMODE 2 (radbg with ido == 1): src is still in the r2hc layout: (2 * src[2j - 1], 2 * src[2j]) of block ik, x0 = src[0].
+template <int INMODE>
+__device__ __forceinline__ float2 gin(float a, float b)
+{
+    return INMODE == 0 ? make_float2(a, b) : (INMODE == 1 ? make_float2(b + a, b - a) : make_float2(2.f * a, 2.f * b));
+}
+template <int LB, int MODE, int INMODE = 0>
 __device__ __forceinline__ void generic_block(const Ctx &c, const float *src, float *dst, const float2 *sgt, int ip,
                                               int ipph, int idl1, int lb, int ik, float2 nz, int ido = 1, unsigned m_ido = 0)
 {
     const int l0 = 1 + LB * lb, nl = min(LB, ipph - l0);
     const int st = idl1 * c.GP;
-    const float *pf = src + ik * c.GP + c.r;
-    const float *pb = pf + (ip - 1) * st;
+    // pf[0] / pb[0]: the two inputs of index j = 1; they advance by sf / sb per j
+    const int sf = INMODE == 2 ? 2 * c.GP : st, sb = INMODE == 2 ? 2 * c.GP : -st;
+    const float *p0 = INMODE == 2 ? src + (ip * ik) * c.GP + c.r : src + ik * c.GP + c.r;
+    const float *pf = INMODE == 2 ? p0 + c.GP : p0 + st;
+    const float *pb = INMODE == 2 ? p0 + 2 * c.GP : p0 + (ip - 1) * st;
     float2 A[LB];
     // rows l0 .. l0+LB-1 of the table (rows past ipph-1 are zero padding: their results are not stored)
     const float4 *tb = reinterpret_cast<const float4 *>(sgt + (l0 - 1) * kRow);
     constexpr int RQ = kRow / 2;   // float4 per row
     {
-        const float2 x0 = make_float2(pf[0], 0.f);
-        const float2 v1 = make_float2(pf[st], pb[0]), v2 = make_float2(pf[2 * st], pb[-st]);
+        const float2 x0 = make_float2(p0[0], 0.f);
+        const float2 v1 = gin<INMODE>(pf[0], pb[0]), v2 = gin<INMODE>(pf[sf], pb[sb]);
 #pragma unroll
         for (int q = 0; q < LB; ++q) {
             const float4 t = tb[q * RQ];
             A[q] = __fadd2_rn(__fadd2_rn(x0, mul2x(make_float2(t.x, t.y), v1, nz)), mul2x(make_float2(t.z, t.w), v2, nz));
         }
     }
-    pf += 3 * st;
-    pb -= 2 * st;
+    pf += 2 * sf;
+    pb += 2 * sb;
     tb += 1;
     int j = 3;
     for (; j + 3 < ipph; j += 4) {
-        const float2 v0 = make_float2(pf[0], pb[0]), v1 = make_float2(pf[st], pb[-st]);
-        const float2 v2 = make_float2(pf[2 * st], pb[-2 * st]), v3 = make_float2(pf[3 * st], pb[-3 * st]);
-        pf += 4 * st;
-        pb -= 4 * st;
+        const float2 v0 = gin<INMODE>(pf[0], pb[0]), v1 = gin<INMODE>(pf[sf], pb[sb]);
+        const float2 v2 = gin<INMODE>(pf[2 * sf], pb[2 * sb]), v3 = gin<INMODE>(pf[3 * sf], pb[3 * sb]);
+        pf += 4 * sf;
+        pb += 4 * sb;
 #pragma unroll
         for (int q = 0; q < LB; ++q) {
             const float4 t = tb[q * RQ], u = tb[q * RQ + 1];
@@ -240,9 +252,9 @@ __device__ __forceinline__ void generic_block(const Ctx &c, const float *src, fl
         tb += 2;
     }
     for (; j + 1 < ipph; j += 2) {
-        const float2 v0 = make_float2(pf[0], pb[0]), v1 = make_float2(pf[st], pb[-st]);
-        pf += 2 * st;
-        pb -= 2 * st;
+        const float2 v0 = gin<INMODE>(pf[0], pb[0]), v1 = gin<INMODE>(pf[sf], pb[sb]);
+        pf += 2 * sf;
+        pb += 2 * sb;
 #pragma unroll
         for (int q = 0; q < LB; ++q) {
             const float4 t = tb[q * RQ];
@@ -251,7 +263,7 @@ __device__ __forceinline__ void generic_block(const Ctx &c, const float *src, fl
         tb += 1;
     }
     if (j < ipph) {
-        const float2 v0 = make_float2(pf[0], pb[0]);
+        const float2 v0 = gin<INMODE>(pf[0], pb[0]);
 #pragma unroll
         for (int q = 0; q < LB; ++q) {
             const float2 t = reinterpret_cast<const float2 *>(tb + q * RQ)[0];
@@ -294,16 +306,16 @@ __device__ __forceinline__ void generic_block(const Ctx &c, const float *src, fl
     }
 }
 
-template <int MODE>
+template <int MODE, int INMODE = 0>
 __device__ __forceinline__ void generic_block_lb(int LBsel, const Ctx &c, const float *src, float *dst, const float2 *sgt, int ip,
                                                  int ipph, int idl1, int lb, int ik, float2 nz, int ido = 1, unsigned m_ido = 0)
 {
     switch (LBsel) {
-    case 4: generic_block<4, MODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
-    case 5: generic_block<5, MODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
-    case 6: generic_block<6, MODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
-    case 7: generic_block<7, MODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
-    default: generic_block<8, MODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
+    case 4: generic_block<4, MODE, INMODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
+    case 5: generic_block<5, MODE, INMODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
+    case 6: generic_block<6, MODE, INMODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
+    case 7: generic_block<7, MODE, INMODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
+    default: generic_block<8, MODE, INMODE>(c, src, dst, sgt, ip, ipph, idl1, lb, ik, nz, ido, m_ido); break;
     }
 }
 
@@ -322,6 +334,19 @@ __device__ void radfg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
 #define C1(a, b, k_) cc[IDX((a) + ido * ((b) + l1 * (k_)))]
 #define C2(a, b) cc[IDX((a) + idl1 * (b))]
 #define CH2(a, b) ch[IDX((a) + idl1 * (b))]
+    if (ido == 1) {
+        // one phase: the PM of the (i == 0) elements rides on the loads (INMODE 1), the r2hc shuffle on the stores (MODE 1)
+        __syncthreads();   // sgt
+        FOR_ITEMS(it, (nlb + 1) * idl1) {
+            const int lb = fdiv(it, P.m_idl1), ik = it - lb * idl1;
+            if (lb == nlb) {
+                float s = C2(ik, 0);
+                for (int j = 1; j < ipph; ++j) s += C2(ik, ip - j) + C2(ik, j);      // C1(0,k,j) after the PM: t2 + t1
+                ch[IDX(cdim * ik)] = s;
+            } else generic_block_lb<1, 1>(LB, c, cc, ch, sgt, ip, ipph, idl1, lb, ik, nz, ido, P.m_ido);
+        }
+        return;
+    }
     if (ido > 1) {
         const int ni = (ido - 1) >> 1;
         FOR_ITEMS(it, (ipph - 1) * l1 * ni) {
@@ -504,7 +529,7 @@ __device__ void radb5(const Ctx &c, int ido, int l1, const float *cc, float *ch,
 #undef CH
 }
 
-// generic odd radix, backward; returns true when the result ends in ch (false: in cc, the ido == 1 case)
+// generic odd radix, backward; returns true when the result ends in ch
 __device__ bool radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const float *wa, const float2 *gt, float2 *sgt, float2 nz)
 {
     const int ido = P.ido, ip = P.ip, l1 = P.l1;
@@ -515,6 +540,20 @@ __device__ bool radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
         reinterpret_cast<float4 *>(sgt)[i] = __ldg(reinterpret_cast<const float4 *>(gt) + i);
 #define CC(a, b, k_) cc[IDX((a) + ido * ((b) + cdim * (k_)))]
 #define CH(a, b, k_) ch[IDX((a) + ido * ((b) + l1 * (k_)))]
+    if (ido == 1) {
+        // one phase: the inputs are read from the r2hc layout with their factor 2 (INMODE 2), the PM that follows the
+        // O(ip^2) phase is applied on the way out (MODE 2); the result is in ch
+        __syncthreads();   // sgt
+        FOR_ITEMS(it, (nlb + 1) * idl1) {
+            const int lb = fdiv(it, P.m_idl1), ik = it - lb * idl1;
+            if (lb == nlb) {
+                float s = CC(0, 0, ik);
+                for (int j = 1; j < ipph; ++j) s += 2 * CC(0, 2 * j - 1, ik);
+                ch[IDX(ik)] = s;
+            } else generic_block_lb<2, 2>(LB, c, cc, ch, sgt, ip, ipph, idl1, lb, ik, nz);
+        }
+        return true;
+    }
     FOR_ITEMS(it, l1 * ido) {
         const int k = fdiv(it, P.m_ido), i = it - k * ido;
         CH(i, k, 0) = CC(i, 0, k);
@@ -537,19 +576,6 @@ __device__ bool radbg(const Ctx &c, const XPass &P, float *cc, float *ch, const 
         }
     }
     __syncthreads();
-    if (ido == 1) {
-        // every item is an i == 0 item: the PM that follows the O(ip^2) phase needs only the item's own two sums, so it is
-        // applied on the way out (generic_block MODE 2) and the pass is complete: its result is in cc, not in ch
-        FOR_ITEMS(it, (nlb + 1) * idl1) {
-            const int lb = fdiv(it, P.m_idl1), ik = it - lb * idl1;
-            if (lb == nlb) {
-                float s = CH2(ik, 0);
-                for (int j = 1; j < ipph; ++j) s += CH2(ik, j);
-                C2(ik, 0) = s;
-            } else generic_block_lb<2>(LB, c, ch, cc, sgt, ip, ipph, idl1, lb, ik, nz);
-        }
-        return false;
-    }
     // C2(ik, l >= 1) from CH2; the l == 0 item forms CH2(ik,0) + sum_j CH2(ik,j) and parks it in C2(ik,0) (cc's slot 0
     // is free) because the other items of this phase still read the old CH2(ik,0)
     FOR_ITEMS(it, (nlb + 1) * idl1) {
