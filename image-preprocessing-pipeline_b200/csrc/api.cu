@@ -930,6 +930,8 @@ bool is_pinned_host(const void *p)
 // worker threads for pageable staging: B2S_HOST_THREADS, else min(8, cores / (2 x processes on this box))
 HostPool *host_pool(b2s_context *ctx)
 {
+    static std::mutex create_mutex;   // plans of one context may run from several host threads (each under its own plan lock)
+    std::lock_guard<std::mutex> lk(create_mutex);
     if (!ctx->pool) {
         int n = getenv("B2S_HOST_THREADS") ? atoi(getenv("B2S_HOST_THREADS")) : 0;
         if (n <= 0) {

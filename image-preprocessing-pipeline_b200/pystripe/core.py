@@ -1366,6 +1366,17 @@ class _BatchPipeline:
                     break
         self.pool.shutdown(wait=False)
 
+    def _put(self, q, item) -> bool:
+        """bounded put that gives up when the pipeline is stopping (a dead consumer must not block its producer for ever)."""
+        from queue import Full
+        while True:
+            try:
+                q.put(item, timeout=0.2)
+                return True
+            except Full:
+                if self.sh.stop.is_set():
+                    return False
+
     def _guard(self, stage):
         try:
             stage()
@@ -1415,12 +1426,14 @@ class _BatchPipeline:
                         print(f"\n{f}")
                 valid = self._decode_fast(fast, buf, slow)
                 if any(valid):
-                    self.q_ready.put((fast, buf, valid))
+                    if not self._put(self.q_ready, (fast, buf, valid)):
+                        return
                 else:
                     del buf
             for job in slow:                                            # odd files: the reference's per-file logic
-                self.q_ready.put((job,))
-        self.q_ready.put(None)
+                if not self._put(self.q_ready, (job,)):
+                    return
+        self._put(self.q_ready, None)
 
     def _decode_fast(self, jobs, buf, slow):
         """decode jobs[i] into buf[i]; returns the per-plane valid flags.  Files of another shape move to `slow`."""
@@ -1491,8 +1504,9 @@ class _BatchPipeline:
                         sh.done()
                 continue
             del buf
-            self.q_write.put((jobs, res, valid))
-        self.q_write.put(None)
+            if not self._put(self.q_write, (jobs, res, valid)):
+                return
+        self._put(self.q_write, None)
 
     def _slow_file(self, job):
         sh = self.sh

@@ -103,6 +103,25 @@ def test_timeout_writes_a_zero_dummy_tile(tmp_path, host_only, monkeypatch):
     assert core.imread_tif_raw_png(tmp_path / "out" / "img_0000.tif").dtype == np.uint8
 
 
+@pytest.mark.timeout(120)
+def test_a_dying_stage_does_not_deadlock_the_pipeline(tmp_path, host_only, monkeypatch):
+    """the encoder dies on its first group while the bounded queues are full: the other stages must unblock and the call
+    must return a non-zero code instead of hanging."""
+    _write_stack(tmp_path / "in", 40)
+
+    class Boom(BaseException):
+        pass
+
+    def die(*a, **k):
+        raise Boom("encoder died")
+    monkeypatch.setattr(core, "process_img", lambda stack, **kw: stack)
+    monkeypatch.setattr(_io, "write_tiff_batch", die)
+    monkeypatch.setenv("B200STRIPE_FILE_GROUP", "2")          # 20 groups through queues of depth 2
+    rc = core.batch_filter(tmp_path / "in", tmp_path / "out", workers=2, threads_per_gpu=2, sigma=(8, 8), wavelet="db2",
+                           compression=None)
+    assert rc != 0
+
+
 def test_queue_runner_replaces_a_timed_out_item_with_a_dummy(tmp_path):
     from multiprocessing import Queue
     args_q, prog_q = Queue(), Queue()
