@@ -146,6 +146,7 @@ struct Geometry {
     bool resize;                  // new_size differs from the work image: order-1 zoom before the final conversion
     int new_rows, new_cols;
     int mid_dtype;                // dtype of the image the resize reads (after dark / lightsheet)
+    bool f64;                     // integer pixels without log1p: the destripe runs in float64 (f64path.cu)
 };
 
 int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
@@ -253,9 +254,10 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
         if (p.lightsheet) g.mid_dtype = p.out_dtype;   // correct_lightsheet returns d_type
     }
     g.int_path = g.log_image && g.work_dtype != B2S_F32;
-    if (g.int_path && !p.log1p)
+    g.f64 = g.int_path && !p.log1p;   // pywt / scipy promote the integer image to float64 (core.py:1063, 1081-1158)
+    if (g.f64 && (p.bleach || g.n_passes == 0 || p.pad_mode > B2S_PAD_CONSTANT))
         return fail(ctx, B2S_ERR_UNSUPPORTED,
-                    "log1p_normalization_needed=False on an integer image runs in float64 in the reference; not implemented");
+                    "log1p_normalization_needed=False on an integer image: only the destripe with a copying padding mode is implemented");
 
     // final conversion, core.py:1361-1369
     if (!p.process_img) {
@@ -353,6 +355,7 @@ struct b2s_plan {
         unsigned short *ls_grid = nullptr, *bg_grid = nullptr, *ls_cells = nullptr;
         unsigned *mm = nullptr;
         unsigned *pad_flags = nullptr;             // computed padding modes: 4 flags per plane
+        double *f64_work = nullptr;                // f64 path: padded image, sub-bands, intermediates (doubles per plane x B)
         double *bleach_scratch = nullptr;          // bleach correction: forward low-pass output, rows x (cols + 12) per plane
         float *bleach_filt = nullptr;              //                    img_filter, rows x cols per plane
         unsigned *bleach_max = nullptr;            //                    per-plane key of max(img_filter)
@@ -372,6 +375,9 @@ struct b2s_plan {
     int n_row_groups = 0;
     int *d_row_src = nullptr, *d_row_start = nullptr, *d_row_targets = nullptr, *d_colmap = nullptr;
     float *d_lut = nullptr;
+    double taps64[4][B2S_MAX_TAPS] = {};            // f64 path: dec_lo, dec_hi, rec_lo, rec_hi in double
+    double *d_notch_mat[2][B2S_MAX_LEVELS + 1][2] = {};   // f64 path: n x n response matrices (b2s_plan_set_notch_matrix)
+    size_t f64_plane_doubles = 0;
     double *d_clip_pp = nullptr;                   // bleach_per_plane: (min, med, max) per plane of the coming b2s_run
     float *d_padv_pp = nullptr;                     //                   constant-padding value per plane (or null)
     int64_t n_levels = 0, cap_levels = 0;
@@ -474,6 +480,7 @@ int build_tables(b2s_plan *pl)
         t.dec_hi[k] = (float)dec_hi[k];
         t.rec_lo[k] = (float)rec_lo[k];
         t.rec_hi[k] = (float)rec_hi[k];
+        pl->taps64[0][k] = dec_lo[k]; pl->taps64[1][k] = dec_hi[k]; pl->taps64[2][k] = rec_lo[k]; pl->taps64[3][k] = rec_hi[k];
     }
     // numpy.pad as index tables (core.py:1100-1110)
     {
@@ -519,8 +526,9 @@ int build_tables(b2s_plan *pl)
             CU(ctx, cudaDeviceSynchronize());
         }
     }
-    // per-level FFT plans + notch tables (np_notch, core.py:637-667, numpy float32 branch)
-    for (int pass = 0; pass < g.n_passes; ++pass) {
+    // per-level FFT plans + notch tables (np_notch, core.py:637-667, numpy float32 branch); the float64 path applies the
+    // notch as a dense matrix the caller uploads (b2s_plan_set_notch_matrix)
+    for (int pass = 0; pass < (g.f64 ? 0 : g.n_passes); ++pass) {
         for (int l = 1; l <= g.levels; ++l) {
             for (int axis = 0; axis < (p.bidirectional ? 2 : 1); ++axis) {
                 const int n = axis == 0 ? g.mx[l] : g.my[l];
@@ -578,14 +586,18 @@ int alloc_slot(b2s_plan *pl, int si)
     b2s_plan::Slot &s = pl->slot[si];
     const size_t B = pl->B;
     int rc;
+    if (g.f64) {
+        pl->f64_plane_doubles = b2s_f64_workspace_doubles(g.PH, g.PW, g.levels, g.my, g.mx);
+        if ((rc = dev_alloc(pl, (void **)&s.f64_work, sizeof(double) * pl->f64_plane_doubles * B))) return rc;
+    }
     if (g.log_image) {
         if ((rc = dev_alloc(pl, (void **)&s.padded, sizeof(float) * pl->plane_stride[0] * B))) return rc;
-        for (int l = 1; l <= g.levels; ++l)
+        for (int l = 1; l <= (g.f64 ? 0 : g.levels); ++l)
             for (int k = 0; k < 4; ++k)
                 if ((rc = dev_alloc(pl, (void **)&s.sub[l][k], sizeof(float) * pl->plane_stride[l] * B))) return rc;
         if (g.n_passes > 0 && p.pad_mode >= B2S_PAD_LINEAR_RAMP &&
             (rc = dev_alloc(pl, (void **)&s.pad_flags, sizeof(unsigned) * 4 * B))) return rc;
-        pl->dwt_scratch_stride = g.n_passes > 0 ? b2s_dwt_scratch_floats(pl->taps.F, g.PH, g.PW) : 0;
+        pl->dwt_scratch_stride = (g.n_passes > 0 && !g.f64) ? b2s_dwt_scratch_floats(pl->taps.F, g.PH, g.PW) : 0;
         if (pl->dwt_scratch_stride &&
             (rc = dev_alloc(pl, (void **)&s.dwt_scratch, sizeof(float) * pl->dwt_scratch_stride * B))) return rc;
     }
@@ -672,7 +684,7 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
     int cur_dt = p.in_dtype;
     // uniform-plane check (core.py:1232): min / max keys of the raw input.  When the prologue reads the raw input itself
     // (no pre-op in between) it accumulates them on the way; otherwise one vectorised pass does.
-    const bool fuse_minmax = p.process_img && g.log_image && !(p.gaussian && !p.reference_quirks) &&
+    const bool fuse_minmax = p.process_img && g.log_image && !g.f64 && !(p.gaussian && !p.reference_quirks) &&
                              g.work_rows == g.in_rows && g.work_cols == g.in_cols && (!(p.process_img && p.has_flat) || g.fuse_flat);
     if (p.process_img) {
         CU(ctx, cudaMemsetAsync(s.mm, 0xff, sizeof(unsigned) * 2 * nb, st));
@@ -705,7 +717,29 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
     }
 
     B2sImg padded = img_of(pl, s.padded, 0);
-    if (g.log_image) {
+    if (g.f64) {   // integer pixels, no log: float64 pad -> wavedec2 -> notch -> waverec2, rint / clip into `padded`
+        ClassTimer t(ctx, st, B2S_K_OTHER, 2 + g.n_passes * (1 + g.levels * (6 + (p.bidirectional ? 2 : 1))));
+        B2sF64Args f;
+        memset(&f, 0, sizeof f);
+        f.in = cur; f.in_dtype = cur_dt; f.rows = g.work_rows; f.cols = g.work_cols;
+        f.pad_mode = p.pad_mode; f.base_pad = g.base_pad;
+        f.pad_value = p.pad_mode == B2S_PAD_CONSTANT ? p.pad_constant : 0.0;
+        f.PH = g.PH; f.PW = g.PW; f.levels = g.levels;
+        for (int l = 0; l <= g.levels; ++l) { f.my[l] = g.my[l]; f.mx[l] = g.mx[l]; }
+        f.F = pl->taps.F;
+        f.dec_lo = pl->taps64[0]; f.dec_hi = pl->taps64[1]; f.rec_lo = pl->taps64[2]; f.rec_hi = pl->taps64[3];
+        f.n_passes = g.n_passes; f.bidirectional = p.bidirectional;
+        for (int pass = 0; pass < g.n_passes; ++pass)
+            for (int l = 1; l <= g.levels; ++l)
+                for (int ax = 0; ax < (p.bidirectional ? 2 : 1); ++ax) {
+                    if (!pl->d_notch_mat[pass][l][ax])
+                        return fail(ctx, B2S_ERR_INVALID, "float64 destripe: b2s_plan_set_notch_matrix was not called for pass %d, level %d, axis %d", pass, l, ax);
+                    f.notch[pass][l][ax] = pl->d_notch_mat[pass][l][ax];
+                }
+        f.work = s.f64_work; f.plane_doubles = pl->f64_plane_doubles;
+        f.out = padded;
+        b2s_launch_f64_destripe(f, nb, st);
+    } else if (g.log_image) {
         {
             ClassTimer t(ctx, st, B2S_K_PROLOGUE, 1);
             B2sPrologueArgs a;
@@ -1136,6 +1170,28 @@ int b2s_plan_set_aa_weights(b2s_plan *pl, int axis, const double *w, int n)
     return B2S_OK;
 }
 
+int b2s_plan_wants_notch_matrix(const b2s_plan *pl) { return pl && pl->g.f64 ? 1 : 0; }
+
+int b2s_plan_set_notch_matrix(b2s_plan *pl, int pass, int level, int axis, const double *R, int n)
+{
+    if (!pl || !R) return B2S_ERR_INVALID;
+    b2s_context *ctx = pl->ctx;
+    const Geometry &gm = pl->g;
+    if (!gm.f64) return fail(ctx, B2S_ERR_INVALID, "b2s_plan_set_notch_matrix: the plan does not run in float64");
+    if (pass < 0 || pass >= gm.n_passes || level < 1 || level > gm.levels || axis < 0 || axis > (pl->p.bidirectional ? 1 : 0))
+        return fail(ctx, B2S_ERR_INVALID, "b2s_plan_set_notch_matrix: no such matrix (pass %d, level %d, axis %d)", pass, level, axis);
+    const int len = axis == 0 ? gm.mx[level] : gm.my[level];
+    if (n != len) return fail(ctx, B2S_ERR_INVALID, "b2s_plan_set_notch_matrix: %d x %d given, sub-band side is %d", n, n, len);
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    if (!pl->d_notch_mat[pass][level][axis]) {
+        int rc = dev_alloc(pl, (void **)&pl->d_notch_mat[pass][level][axis], sizeof(double) * (size_t)n * n);
+        if (rc) return rc;
+    }
+    CU(ctx, cudaMemcpy(pl->d_notch_mat[pass][level][axis], R, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+    return B2S_OK;
+}
+
 int b2s_plan_set_bleach_levels(b2s_plan *pl, const double *clip, const float *pad_value, int64_t n_planes)
 {
     if (!pl || !clip || n_planes <= 0) return B2S_ERR_INVALID;
@@ -1166,6 +1222,7 @@ int b2s_plan_set_notch(b2s_plan *pl, int pass, int level, int axis, const float 
         return fail(ctx, B2S_ERR_INVALID, "b2s_plan_set_notch: no such table (pass %d, level %d, axis %d)", pass, level, axis);
     const int len = axis == 0 ? gm.mx[level] : gm.my[level];
     if (n != len) return fail(ctx, B2S_ERR_INVALID, "b2s_plan_set_notch: table has %d entries, sub-band side is %d", n, len);
+    if (gm.f64) return fail(ctx, B2S_ERR_INVALID, "b2s_plan_set_notch: a float64 plan takes b2s_plan_set_notch_matrix");
     CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaDeviceSynchronize());
     CU(ctx, cudaMemcpy(pl->d_notch[pass][level][axis], g, sizeof(float) * n, cudaMemcpyHostToDevice));

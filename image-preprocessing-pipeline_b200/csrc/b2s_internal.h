@@ -109,6 +109,26 @@ int b2s_pad_fill_supported(int mode, int rows, int cols);
 void b2s_launch_pad_fill(int mode, const B2sImg &padded, int base_pad, int rows, int cols, unsigned *flags, int n_planes,
                          cudaStream_t s);
 
+// f64path.cu ------------------------------------------------------------------------------------------------------
+// integer pixels with log1p_normalization_needed=False: the reference runs pad -> wavedec2 -> notch -> waverec2 in float64
+struct B2sF64Args {
+    const void *in;                // work-size integer planes (u8 / u16), contiguous
+    int in_dtype, rows, cols;
+    int pad_mode, base_pad;
+    double pad_value;
+    int PH, PW, levels;
+    int my[B2S_MAX_LEVELS + 1], mx[B2S_MAX_LEVELS + 1];
+    int F;
+    const double *dec_lo, *dec_hi, *rec_lo, *rec_hi;   // host pointers, F doubles each
+    int n_passes, bidirectional;
+    const double *notch[2][B2S_MAX_LEVELS + 1][2];      // device: response matrices of irfft(rfft(x) * g), n x n, [k][c]
+    double *work;                  // b2s_f64_workspace_doubles() doubles per plane
+    size_t plane_doubles;
+    B2sImg out;                    // float32 padded image: rint / clip of the reconstruction (the common epilogue reads it)
+};
+size_t b2s_f64_workspace_doubles(int PH, int PW, int levels, const int *my, const int *mx);
+void b2s_launch_f64_destripe(const B2sF64Args &a, int n_planes, cudaStream_t s);
+
 // stats.cu ---------------------------------------------------------------------------------------------------------
 // exact intensity histogram of uint8 / uint16 planes, ADDED into `hist` (65 536 uint64 counters, per plane or one for all)
 void b2s_launch_histogram(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned long long *hist, int per_plane,

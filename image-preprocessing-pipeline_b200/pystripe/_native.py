@@ -61,7 +61,7 @@ class PlanInfo(C.Structure):
 
 EXPORTS = (
     "b2s_version", "b2s_params_default", "b2s_create", "b2s_destroy", "b2s_last_error", "b2s_device_sm_count",
-    "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_plan_set_bleach_levels", "b2s_plan_set_aa_weights", "b2s_run",
+    "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_plan_wants_notch_matrix", "b2s_plan_set_notch_matrix", "b2s_plan_set_bleach_levels", "b2s_plan_set_aa_weights", "b2s_run",
     "b2s_host_alloc", "b2s_host_free", "b2s_launch_count", "b2s_timing_enable", "b2s_timing_read",
     "b2s_debug_read", "b2s_debug_math",
     "b2s_resize_aa", "b2s_isotropic_xy", "b2s_isotropic_z", "b2s_isotropic_convert", "b2s_is_uniform", "b2s_histogram",
@@ -104,6 +104,8 @@ def lib():
             L.b2s_plan_set_notch.argtypes = [vp, i32, i32, i32, vp, i32]
             L.b2s_plan_set_aa_weights.argtypes = [vp, i32, vp, i32]
             L.b2s_plan_set_bleach_levels.argtypes = [vp, vp, vp, i64]
+            L.b2s_plan_wants_notch_matrix.argtypes = [vp]
+            L.b2s_plan_set_notch_matrix.argtypes = [vp, i32, i32, i32, vp, i32]
             L.b2s_isotropic_xy.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
             L.b2s_resize_aa.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
             L.b2s_isotropic_z.argtypes = [vp, vp, i32, i64, i32, vp, vp]
@@ -357,6 +359,15 @@ class Plan:
         """upload a host-evaluated np_notch table (float32) for (pass, 1-based level, axis 0 = cH / 1 = cV)."""
         g = np.ascontiguousarray(g, dtype=np.float32)
         self.ctx.check(lib().b2s_plan_set_notch(self._h, pass_idx, level, axis, C.c_void_p(g.ctypes.data), int(g.size)))
+
+    @property
+    def wants_notch_matrix(self) -> bool:
+        """the plan runs the destripe in float64 (integer pixels without log1p) and takes dense notch matrices."""
+        return bool(lib().b2s_plan_wants_notch_matrix(self._h))
+
+    def set_notch_matrix(self, pass_idx: int, level: int, axis: int, R: np.ndarray):
+        R = np.ascontiguousarray(R, dtype=np.float64)
+        self.ctx.check(lib().b2s_plan_set_notch_matrix(self._h, pass_idx, level, axis, C.c_void_p(R.ctypes.data), int(R.shape[0])))
 
     def set_bleach_levels(self, clip: np.ndarray, pad_value: np.ndarray = None):
         """per-plane (clip_min, clip_med, clip_max) [n, 3] float64 and optional constant-padding values [n] float32 for the

@@ -413,12 +413,29 @@ def _upload_numpy_notch_tables(plan, s1, s2):
     if info.n_passes == 0:
         return
     sigmas = (s1,) if info.n_passes == 1 else (s1, s2)
+    f64 = plan.wants_notch_matrix
+
+    def response(n, g):
+        """the float64 path (integer pixels, no log1p): np_filter_coefficient as a matrix — row k = irfft(rfft(e_k) * g),
+        evaluated by scipy.fftpack in float64 exactly as core.py:749-754 would on a float64 coefficient array."""
+        from scipy.fftpack import irfft, rfft
+        spec = rfft(np.eye(n, dtype=np.float64), axis=-1)
+        spec *= g
+        return irfft(spec, axis=-1)
     for pi, sg in enumerate(sigmas):
         for lvl in range(1, info.levels + 1):
             rows, cols = info.level_rows[lvl - 1], info.level_cols[lvl - 1]
-            plan.set_notch(pi, lvl, 0, np_notch(cols, rows * (sg / info.padded_height)))
+            g0 = np_notch(cols, rows * (sg / info.padded_height))
+            if f64:
+                plan.set_notch_matrix(pi, lvl, 0, response(cols, g0))
+            else:
+                plan.set_notch(pi, lvl, 0, g0)
             if plan.params.bidirectional:
-                plan.set_notch(pi, lvl, 1, np_notch(rows, cols * (sg / info.padded_width)))
+                g1 = np_notch(rows, cols * (sg / info.padded_width))
+                if f64:
+                    plan.set_notch_matrix(pi, lvl, 1, response(rows, g1))
+                else:
+                    plan.set_notch(pi, lvl, 1, g1)
 
 
 def clear_plan_cache():

@@ -158,6 +158,12 @@ int b2s_plan_set_flat(b2s_plan *plan, const float *flat, int is_device);
  * with numpy exactly as scipy does (numpy's exp is not libm's). */
 int b2s_plan_set_aa_weights(b2s_plan *plan, int axis, const double *weights, int n);
 int b2s_plan_set_notch(b2s_plan *plan, int pass, int level, int axis, const float *g, int n);
+/* replaces: np_filter_coefficient (core.py:749-754) for the one case the reference runs in float64 — integer pixels with
+ * log1p_normalization_needed=False (pywt and scipy promote the integer image to double): irfft(rfft(x) * g) is applied as
+ * the dense real n x n matrix it is.  R[k * n + c] = response at position c to a unit sample at position k, evaluated by the
+ * caller with scipy.fftpack in float64 (host pointer).  b2s_plan_wants_notch_matrix tells whether a plan runs that way. */
+int b2s_plan_wants_notch_matrix(const b2s_plan *plan);
+int b2s_plan_set_notch_matrix(b2s_plan *plan, int pass, int level, int axis, const double *R, int n);
 /* replaces: the per-image clip levels of filter_streaks when bleach_correction_clip_min / _med / _max are None
  * (core.py:1066-1077: lb, mb, ub = threshold_multiotsu(log1p(img), classes=4)).  clip: n_planes x 3 doubles (min, med, max as
  * numpy.clip compares them, after the clip_min >= log1p(1) rule of core.py:529-531); pad_value: n_planes floats,

@@ -229,13 +229,7 @@ def _gpu_case(kind, img, kw):
 def test_golden_vectors_from_the_reference():
     gold = np.load(ROOT / "tests" / "golden" / "pystripe_golden.npz")
     for name, kind, img, kw in cases.all_cases():
-        if kw.get("log1p_normalization_needed") is False and img.dtype.kind in "ui":
-            # the reference runs this combination in float64 and truncates inside filter_subband (core.py:939):
-            # declared unsupported by the GPU path rather than approximated
-            with pytest.raises(NotImplementedError):
-                _gpu_case(kind, img, kw)
-            continue
-        got = _gpu_case(kind, img, kw)
+        got = _gpu_case(kind, img, kw)       # incl. fs_nolog: integer pixels without log1p run in float64 (csrc/f64path.cu)
         if gold[name].dtype.kind == "f":
             ref = gold[name]
             assert got.dtype == ref.dtype and np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max(), name
@@ -545,6 +539,25 @@ def test_bleach_clip_levels_from_multiotsu_per_plane(kw):
     out = core.process_img(stack, dark=100, **base)
     assert not out[1].any()
     assert np.array_equal(out[0], orc.process_img(stack[0].copy(), dark=100, **base))
+
+
+@pytest.mark.parametrize("kw", [dict(sigma=(24, 24), wavelet="db3"), dict(sigma=(16, 48), wavelet="db6", padding_mode="reflect"),
+                                dict(sigma=(20, 20), wavelet="db9", bidirectional=True, padding_mode="symmetric")])
+def test_integer_pixels_without_log1p_run_in_float64(kw):
+    """log1p_normalization_needed=False on uint16 / uint8 pixels: pywt and scipy promote to float64 and every pass ends with
+    `.astype(d_type)` (truncation, core.py:939).  The GPU evaluates the same chain in float64 without mirroring the operation
+    order: identical integers except within ~1e-9 of an integer boundary."""
+    from pystripe import core
+    for dtype, shape in ((np.uint16, (150, 211)), (np.uint8, (96, 128))):
+        img = synth.plane(31, shape)
+        img = (img >> 4).astype(np.uint8) if dtype == np.uint8 else img
+        stack = np.stack([img, img[::-1].copy()])
+        got = core.filter_streaks(stack, log1p_normalization_needed=False, **kw)
+        for z in range(2):
+            ref = orc.filter_streaks(stack[z], log1p_normalization_needed=False, **kw)
+            _cmp_int(f"nolog_int/{kw}/{dtype.__name__}/{z}", got[z], ref)
+    out = core.process_img(stack, log1p_normalization_needed=False, dark=3, convert_to_8bit=False, **kw)
+    assert np.array_equal(out[0], orc.process_img(stack[0].copy(), log1p_normalization_needed=False, dark=3, **kw))
 
 
 def test_bleach_argument_errors():
