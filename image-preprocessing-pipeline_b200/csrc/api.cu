@@ -258,6 +258,8 @@ int compute_geometry(b2s_context *ctx, const b2s_params &p, Geometry &g)
     if (g.f64 && (p.bleach || g.n_passes == 0 || p.pad_mode > B2S_PAD_CONSTANT))
         return fail(ctx, B2S_ERR_UNSUPPORTED,
                     "log1p_normalization_needed=False on an integer image: only the destripe with a copying padding mode is implemented");
+    if (p.mask && (p.mask_close < 1 || p.mask_open < 1))
+        return fail(ctx, B2S_ERR_INVALID, "enable_masking: close_steps and open_steps must be at least 1 (cv2 rejects an empty structuring element)");
 
     // final conversion, core.py:1361-1369
     if (!p.process_img) {
@@ -359,6 +361,8 @@ struct b2s_plan {
         double *bleach_scratch = nullptr;          // bleach correction: forward low-pass output, rows x (cols + 12) per plane
         float *bleach_filt = nullptr;              //                    img_filter, rows x cols per plane
         unsigned *bleach_max = nullptr;            //                    per-plane key of max(img_filter)
+        unsigned char *mask_a = nullptr, *mask_b = nullptr, *mask_c = nullptr;   // enable_masking: mask, scratch, flood reach (bytes per pixel)
+        int *mask_flag = nullptr, *mask_hflag = nullptr;                         //                 flood-fill "changed" flag (device / page-locked)
         void *h_in = nullptr, *h_out = nullptr;    // pinned staging
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
@@ -381,6 +385,8 @@ struct b2s_plan {
     double *d_clip_pp = nullptr;                   // bleach_per_plane: (min, med, max) per plane of the coming b2s_run
     float *d_padv_pp = nullptr;                     //                   constant-padding value per plane (or null)
     int64_t n_levels = 0, cap_levels = 0;
+    double *d_mask_thr_pp = nullptr;   // enable_masking with per-plane thresholds (multi-Otsu clip_med)
+    int64_t n_mask_thr = 0, cap_mask_thr = 0;
     int *d_rz_idx = nullptr;                        // new_size: [iy0 | iy1 | ix0 | ix1]
     double *d_rz_w = nullptr;                       //           [wy0 | wy1 | wx0 | wx1]
     double *d_aa_w[2] = {nullptr, nullptr};         // anti-aliasing Gaussian weights per axis (2 r + 1), caller-supplied
@@ -602,6 +608,12 @@ int alloc_slot(b2s_plan *pl, int si)
             (rc = dev_alloc(pl, (void **)&s.dwt_scratch, sizeof(float) * pl->dwt_scratch_stride * B))) return rc;
     }
     const size_t in_elems = (size_t)g.in_rows * g.in_cols, work_elems = (size_t)g.work_rows * g.work_cols;
+    if (p.mask && g.log_image) {
+        for (unsigned char **m : {&s.mask_a, &s.mask_b, &s.mask_c})
+            if ((rc = dev_alloc(pl, (void **)m, work_elems * B))) return rc;
+        if ((rc = dev_alloc(pl, (void **)&s.mask_flag, sizeof(int)))) return rc;
+        if (!pl->dry && !s.mask_hflag) CU(pl->ctx, cudaMallocHost((void **)&s.mask_hflag, sizeof(int)));
+    }
     if (p.bleach) {
         if ((rc = dev_alloc(pl, (void **)&s.bleach_scratch, sizeof(double) * (size_t)g.work_rows * (g.work_cols + 12) * B))) return rc;
         if ((rc = dev_alloc(pl, (void **)&s.bleach_filt, sizeof(float) * work_elems * B))) return rc;
@@ -738,6 +750,15 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
                 }
         f.work = s.f64_work; f.plane_doubles = pl->f64_plane_doubles;
         f.out = padded;
+        if (p.mask) {   // core.py:1079-1080 on the integer image
+            ClassTimer tm(ctx, st, B2S_K_OTHER, 12);
+            b2s_launch_mask_threshold_int(cur, cur_dt, (size_t)g.work_rows * g.work_cols, p.mask_threshold,
+                                          p.mask_per_plane ? pl->d_mask_thr_pp + z0 : nullptr, s.mask_a, nb, st);
+            const int rc = b2s_launch_img_mask(s.mask_a, s.mask_b, s.mask_c, g.work_rows, g.work_cols, p.mask_close, p.mask_open,
+                                               s.mask_flag, s.mask_hflag, nb, st);
+            if (rc) return fail(ctx, rc, "enable_masking: get_img_mask failed (rows of %d pixels)", g.work_cols);
+            f.mask = s.mask_a;
+        }
         b2s_launch_f64_destripe(f, nb, st);
     } else if (g.log_image) {
         {
@@ -762,6 +783,15 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
             a.lut = (cur_dt != B2S_F32 && !a.flat && p.log1p) ? pl->d_lut : nullptr;
             a.minmax = fuse_minmax ? s.mm : nullptr;
             b2s_launch_prologue(a, nb, st);
+            if (p.mask) {   // core.py:1079-1080: img *= get_img_mask(img, clip_med) on the (log) image, ahead of numpy.pad
+                ctx->launches += 12;
+                b2s_launch_mask_threshold_f32(padded, g.base_pad, g.work_rows, g.work_cols, p.mask_threshold,
+                                              p.mask_per_plane ? pl->d_mask_thr_pp + z0 : nullptr, s.mask_a, nb, st);
+                const int rc = b2s_launch_img_mask(s.mask_a, s.mask_b, s.mask_c, g.work_rows, g.work_cols, p.mask_close, p.mask_open,
+                                                   s.mask_flag, s.mask_hflag, nb, st);
+                if (rc) return fail(ctx, rc, "enable_masking: get_img_mask failed (rows of %d pixels)", g.work_cols);
+                b2s_launch_mask_apply(padded, s.mask_a, g.base_pad, g.work_rows, g.work_cols, p.pad_mode, nb, st);
+            }
             if (g.n_passes > 0 && p.pad_mode >= B2S_PAD_LINEAR_RAMP) {   // pad areas computed from the image (numpy.pad stat modes)
                 ctx->launches += p.pad_mode == B2S_PAD_EMPTY ? 0 : (p.pad_mode == B2S_PAD_LINEAR_RAMP ? 4 : 2);
                 b2s_launch_pad_fill(p.pad_mode, padded, g.base_pad, g.work_rows, g.work_cols, s.pad_flags, nb, st);
@@ -1123,6 +1153,7 @@ void b2s_plan_destroy(b2s_plan *pl)
     for (auto &s : pl->slot) {
         if (s.h_in) cudaFreeHost(s.h_in);
         if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.mask_hflag) cudaFreeHost(s.mask_hflag);
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.done) cudaEventDestroy(s.done);
     }
@@ -1213,6 +1244,24 @@ int b2s_plan_set_bleach_levels(b2s_plan *pl, const double *clip, const float *pa
     return B2S_OK;
 }
 
+int b2s_plan_set_mask_thresholds(b2s_plan *pl, const double *thr, int64_t n_planes)
+{
+    if (!pl || !thr || n_planes <= 0) return B2S_ERR_INVALID;
+    b2s_context *ctx = pl->ctx;
+    if (!pl->p.mask || !pl->p.mask_per_plane)
+        return fail(ctx, B2S_ERR_INVALID, "b2s_plan_set_mask_thresholds: the plan was not created with mask_per_plane");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    if (n_planes > pl->cap_mask_thr) {
+        int rc = dev_alloc(pl, (void **)&pl->d_mask_thr_pp, sizeof(double) * (size_t)n_planes);
+        if (rc) return rc;
+        pl->cap_mask_thr = n_planes;
+    }
+    CU(ctx, cudaMemcpy(pl->d_mask_thr_pp, thr, sizeof(double) * (size_t)n_planes, cudaMemcpyHostToDevice));
+    pl->n_mask_thr = n_planes;
+    return B2S_OK;
+}
+
 int b2s_plan_set_notch(b2s_plan *pl, int pass, int level, int axis, const float *g, int n)
 {
     if (!pl || !g) return B2S_ERR_INVALID;
@@ -1241,6 +1290,9 @@ int b2s_run(b2s_plan *pl, const void *in, void *out, int64_t n_planes, int in_is
     if (pl->p.bleach && pl->p.bleach_per_plane && pl->n_levels < n_planes)
         return fail(ctx, B2S_ERR_INVALID, "bleach_per_plane: b2s_plan_set_bleach_levels supplied %lld planes, the run has %lld",
                     (long long)pl->n_levels, (long long)n_planes);
+    if (pl->p.mask && pl->p.mask_per_plane && g.log_image && pl->n_mask_thr < n_planes)
+        return fail(ctx, B2S_ERR_INVALID, "mask_per_plane: b2s_plan_set_mask_thresholds supplied %lld planes, the run has %lld",
+                    (long long)pl->n_mask_thr, (long long)n_planes);
 
     if (in_is_device && out_is_device) {
         cudaStream_t st = (cudaStream_t)stream;
@@ -1602,6 +1654,37 @@ int b2s_isotropic_convert(b2s_context *ctx, const float *d_in, int64_t n, int mo
     b2s_launch_convert_f32(d_in, n, mode, shift, d_out, (cudaStream_t)stream);
     ctx->launches += 1;
     CU(ctx, cudaGetLastError());
+    return B2S_OK;
+}
+
+int b2s_img_mask(b2s_context *ctx, const void *img, int dtype, int rows, int cols, int n_planes, double threshold, int close_steps,
+                 int open_steps, unsigned char *mask, void *stream)
+{
+    if (!ctx || !img || !mask || rows <= 0 || cols <= 0 || n_planes <= 0) return B2S_ERR_INVALID;
+    if (close_steps < 1 || open_steps < 1) return fail(ctx, B2S_ERR_INVALID, "b2s_img_mask: close_steps and open_steps must be at least 1");
+    if (dtype != B2S_U8 && dtype != B2S_U16 && dtype != B2S_F32) return fail(ctx, B2S_ERR_INVALID, "b2s_img_mask: unknown dtype");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)rows * cols * n_planes;
+    unsigned char *tmp = nullptr;
+    int *h_flag = nullptr;
+    auto release = [&]() { if (tmp) cudaFreeAsync(tmp, st); if (h_flag) cudaFreeHost(h_flag); };
+    struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
+    if (cudaMallocAsync((void **)&tmp, 2 * n + 16, st) != cudaSuccess) return fail(ctx, B2S_ERR_NOMEM, "cudaMallocAsync failed");
+    CU(ctx, cudaMallocHost((void **)&h_flag, sizeof(int)));
+    if (dtype == B2S_F32) {
+        B2sImg im;
+        im.ptr = const_cast<float *>(reinterpret_cast<const float *>(img));
+        im.plane_stride = (size_t)rows * cols; im.pitch = cols; im.rows = rows; im.cols = cols;
+        b2s_launch_mask_threshold_f32(im, 0, rows, cols, threshold, nullptr, mask, n_planes, st);
+    } else {
+        b2s_launch_mask_threshold_int(img, dtype, (size_t)rows * cols, threshold, nullptr, mask, n_planes, st);
+    }
+    int *d_flag = reinterpret_cast<int *>(tmp + ((2 * n + 3) & ~(size_t)3));
+    const int rc = b2s_launch_img_mask(mask, tmp, tmp + n, rows, cols, close_steps, open_steps, d_flag, h_flag, n_planes, st);
+    ctx->launches += 12;
+    if (rc) return fail(ctx, rc, "b2s_img_mask failed (rows of %d pixels)", cols);
+    CU(ctx, cudaStreamSynchronize(st));
     return B2S_OK;
 }
 

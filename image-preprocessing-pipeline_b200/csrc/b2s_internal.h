@@ -125,9 +125,21 @@ struct B2sF64Args {
     double *work;                  // b2s_f64_workspace_doubles() doubles per plane
     size_t plane_doubles;
     B2sImg out;                    // float32 padded image: rint / clip of the reconstruction (the common epilogue reads it)
+    const unsigned char *mask;     // optional get_img_mask result (rows x cols bytes per plane): img *= mask ahead of the padding
 };
 size_t b2s_f64_workspace_doubles(int PH, int PW, int levels, const int *my, const int *mx);
 void b2s_launch_f64_destripe(const B2sF64Args &a, int n_planes, cudaStream_t s);
+
+// mask.cu ----------------------------------------------------------------------------------------------------------
+// get_img_mask (core.py:475-489): `mask` holds img > threshold on entry, the closed / opened / hole-filled mask on return
+int b2s_launch_img_mask(unsigned char *mask, unsigned char *tmp, unsigned char *reach, int rows, int cols, int close_k, int open_k,
+                        int *d_flag, int *h_flag, int n_planes, cudaStream_t s);
+void b2s_launch_mask_threshold_f32(const B2sImg &padded, int base_pad, int rows, int cols, double thr, const double *thr_pp,
+                                   unsigned char *mask, int n_planes, cudaStream_t s);
+void b2s_launch_mask_threshold_int(const void *in, int dtype, size_t n_per_plane, double thr, const double *thr_pp,
+                                   unsigned char *mask, int n_planes, cudaStream_t s);
+void b2s_launch_mask_apply(const B2sImg &padded, const unsigned char *mask, int base_pad, int rows, int cols, int pad_mode,
+                           int n_planes, cudaStream_t s);
 
 // stats.cu ---------------------------------------------------------------------------------------------------------
 // exact intensity histogram of uint8 / uint16 planes, ADDED into `hist` (65 536 uint64 counters, per plane or one for all)

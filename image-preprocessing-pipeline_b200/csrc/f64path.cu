@@ -41,7 +41,7 @@ __device__ __forceinline__ int sym_ext(int i, int n)   // pywt MODE_SYMMETRIC (h
 struct Taps64 { int F; double dec_lo[B2S_MAX_TAPS], dec_hi[B2S_MAX_TAPS], rec_lo[B2S_MAX_TAPS], rec_hi[B2S_MAX_TAPS]; };
 
 __global__ void k_f64_pad(const void *in, int dtype, int rows, int cols, int mode, int base, double fill, double *out, int PH,
-                          int PW, size_t out_stride)
+                          int PW, size_t out_stride, const unsigned char *mask)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= PW) return;
@@ -52,6 +52,7 @@ __global__ void k_f64_pad(const void *in, int dtype, int rows, int cols, int mod
         const size_t idx = plane * (size_t)rows * cols + (size_t)sy * cols + sx;
         v = dtype == B2S_U16 ? (double)reinterpret_cast<const unsigned short *>(in)[idx]
                              : (double)reinterpret_cast<const unsigned char *>(in)[idx];
+        if (mask && !mask[idx]) v = 0.0;       // img *= mask (core.py:1080) on the integer image
     }
     out[plane * out_stride + (size_t)y * PW + x] = v;
 }
@@ -210,7 +211,7 @@ void b2s_launch_f64_destripe(const B2sF64Args &a, int n_planes, cudaStream_t s)
     double *W = a.work;
     const dim3 blk(256);
     k_f64_pad<<<dim3((a.PW + 255) / 256, a.PH, n_planes), blk, 0, s>>>(a.in, a.in_dtype, a.rows, a.cols, a.pad_mode, a.base_pad,
-                                                                      a.pad_value, W + o_pad, a.PH, a.PW, st);
+                                                                      a.pad_value, W + o_pad, a.PH, a.PW, st, a.mask);
     for (int pass = 0; pass < a.n_passes; ++pass) {
         for (int l = 1; l <= a.levels; ++l) {   // sub order: 0 = cA, 1 = cH (rows hi, cols lo), 2 = cV (rows lo, cols hi), 3 = cD
             const int ny = a.my[l - 1], nx = a.mx[l - 1], my = a.my[l], mx = a.mx[l];

@@ -44,6 +44,8 @@ class Params(C.Structure):
         ("bleach_clip_min", C.c_double), ("bleach_clip_med", C.c_double), ("bleach_clip_max", C.c_double),
         ("pad_constant", C.c_double),
         ("aa_radius_y", C.c_int32), ("aa_radius_x", C.c_int32),
+        ("mask", C.c_int32), ("mask_close", C.c_int32), ("mask_open", C.c_int32), ("mask_per_plane", C.c_int32),
+        ("mask_threshold", C.c_double),
         ("max_batch", C.c_int32), ("debug_stop_after", C.c_int32), ("exact", C.c_int32),
     ]
 
@@ -61,10 +63,10 @@ class PlanInfo(C.Structure):
 
 EXPORTS = (
     "b2s_version", "b2s_params_default", "b2s_create", "b2s_destroy", "b2s_last_error", "b2s_device_sm_count",
-    "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_plan_wants_notch_matrix", "b2s_plan_set_notch_matrix", "b2s_plan_set_bleach_levels", "b2s_plan_set_aa_weights", "b2s_run",
+    "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_plan_wants_notch_matrix", "b2s_plan_set_notch_matrix", "b2s_plan_set_bleach_levels", "b2s_plan_set_mask_thresholds", "b2s_plan_set_aa_weights", "b2s_run",
     "b2s_host_alloc", "b2s_host_free", "b2s_launch_count", "b2s_timing_enable", "b2s_timing_read",
     "b2s_debug_read", "b2s_debug_math",
-    "b2s_resize_aa", "b2s_isotropic_xy", "b2s_isotropic_z", "b2s_isotropic_convert", "b2s_is_uniform", "b2s_histogram",
+    "b2s_resize_aa", "b2s_isotropic_xy", "b2s_isotropic_z", "b2s_isotropic_convert", "b2s_is_uniform", "b2s_histogram", "b2s_img_mask",
 )
 
 _lib = None
@@ -104,12 +106,14 @@ def lib():
             L.b2s_plan_set_notch.argtypes = [vp, i32, i32, i32, vp, i32]
             L.b2s_plan_set_aa_weights.argtypes = [vp, i32, vp, i32]
             L.b2s_plan_set_bleach_levels.argtypes = [vp, vp, vp, i64]
+            L.b2s_plan_set_mask_thresholds.argtypes = [vp, vp, i64]
             L.b2s_plan_wants_notch_matrix.argtypes = [vp]
             L.b2s_plan_set_notch_matrix.argtypes = [vp, i32, i32, i32, vp, i32]
             L.b2s_isotropic_xy.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
             L.b2s_resize_aa.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
             L.b2s_isotropic_z.argtypes = [vp, vp, i32, i64, i32, vp, vp]
             L.b2s_isotropic_convert.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+            L.b2s_img_mask.argtypes = [vp, vp, i32, i32, i32, i32, C.c_double, i32, i32, vp, vp]
             L.b2s_histogram.argtypes = [vp, vp, i32, i32, i64, i32, vp, i32, i32, vp]
             L.b2s_is_uniform.argtypes = [vp, vp, i32, i64, vp, vp]
             L.b2s_run.argtypes = [vp, vp, vp, i64, i32, i32, vp]
@@ -376,6 +380,11 @@ class Plan:
         pv = None if pad_value is None else np.ascontiguousarray(pad_value, dtype=np.float32)
         self.ctx.check(lib().b2s_plan_set_bleach_levels(self._h, C.c_void_p(clip.ctypes.data),
                                                         C.c_void_p(pv.ctypes.data) if pv is not None else None, clip.shape[0]))
+
+    def set_mask_thresholds(self, thr: np.ndarray):
+        """per-plane get_img_mask thresholds [n] float64 for the next run of a plan created with mask_per_plane."""
+        thr = np.ascontiguousarray(thr, dtype=np.float64).reshape(-1)
+        self.ctx.check(lib().b2s_plan_set_mask_thresholds(self._h, C.c_void_p(thr.ctypes.data), thr.shape[0]))
 
     def set_aa_weights(self, axis: int, w: np.ndarray):
         """upload the anti-aliasing Gaussian of skimage.transform.resize along one axis (2 * radius + 1 float64 weights)."""

@@ -200,7 +200,6 @@ def _unsupported(name):
 
 
 hist_match = _unsupported("hist_match")                    # core.py:426
-get_img_mask = _unsupported("get_img_mask")                # core.py:475
 correct_bleaching = _unsupported("correct_bleaching")      # core.py:501
 otsu_threshold = _unsupported("otsu_threshold")            # core.py:562
 foreground_fraction = _unsupported("foreground_fraction")  # core.py:586
@@ -285,7 +284,7 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
               artifact_length=150, background_window_size=200, percentile=0.25, lightsheet_vs_background=2.0,
               convert_to_16bit=False, convert_to_8bit=False, bit_shift_to_right=8, rotate=0, flip=False,
               out_code=None, max_batch=None, stop_after=0, exact=None, new_size=None, bleach=None, pad_constant=0.0, aa=(None, None),
-              _acquire=False):
+              mask=None, _acquire=False):
     """Cached plan for one (device, shape, dtype, parameter set).  `_acquire=True` marks the plan in use until
     `_release_plan` (eviction and the out-of-memory retry only close idle plans); a plan serialises its own runs
     with `plan.lock`, so two threads that ask for the same parameters share tables and workspace safely."""
@@ -321,7 +320,7 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
            method, float(dark or 0), bool(lightsheet), artifact_length, background_window_size, percentile,
            lightsheet_vs_background, bool(convert_to_16bit), bool(convert_to_8bit), bit_shift_to_right, rotate,
            bool(flip), out_code, max_batch, stop_after, exact, REFERENCE_QUIRKS, new_size, bleach, tuple(None if a is None else a[0] for a in aa),
-           float(pad_constant) if (destripe and mode == 'constant') else 0.0)
+           float(pad_constant) if (destripe and mode == 'constant') else 0.0, mask)
     with _plans_lock:
         plan = _plans.get(key)
         if plan is not None:
@@ -363,6 +362,8 @@ def _get_plan(device, shape, in_code, *, process, sigma, level, wavelet, thresho
             (p.bleach_b0, p.bleach_b1, p.bleach_a1, p.bleach_zi,
              p.bleach_clip_min, p.bleach_clip_med, p.bleach_clip_max, p.bleach, p.bleach_per_plane) = bleach
         p.pad_constant = float(pad_constant)
+        if mask is not None:
+            p.mask, (p.mask_threshold, p.mask_close, p.mask_open, p.mask_per_plane) = 1, mask
         p.aa_radius_y = 0 if aa[0] is None else int(aa[0][0])
         p.aa_radius_x = 0 if aa[1] is None else int(aa[1][0])
         p.max_batch = int(max_batch or MAX_BATCH)
@@ -452,18 +453,27 @@ def pinned_empty(shape, dtype, device: int = None) -> ndarray:
     return _native.context(dev).pooled_empty(tuple(shape), dtype)
 
 
-def _run_with_levels(plan, arr, bleach, clip_min, clip_med, clip_max, padding_mode, skip_uniform):
-    """run the plan; when bleach clip levels are per plane (multi-Otsu), compute and upload them first, atomically with the
-    run (the plan may be shared with another thread)."""
-    if bleach is None or not bleach[-1]:
+def _run_with_levels(plan, arr, bleach, clip_min, clip_med, clip_max, padding_mode, skip_uniform, mask=None):
+    """run the plan; when bleach clip levels or the mask threshold are per plane (multi-Otsu), compute and upload them first,
+    atomically with the run (the plan may be shared with another thread)."""
+    per_plane_bleach = bleach is not None and bool(bleach[-1])
+    per_plane_mask = mask is not None and bool(mask[-1])
+    if not per_plane_bleach and not per_plane_mask:
         return _run(plan, arr)
     if _code_of(arr) == _native.F32:
-        raise NotImplementedError("bleach clip levels left to threshold_multiotsu need integer pixels (uint8 / uint16): the "
+        raise NotImplementedError("clip levels left to threshold_multiotsu need integer pixels (uint8 / uint16): the "
                                   "levels come from the exact intensity histogram")
     constant = isinstance(padding_mode, str) and padding_mode.lower() == 'constant'
-    levels, pads = _otsu_levels(arr, clip_min, clip_med, clip_max, constant, skip_uniform)
+    if constant and not per_plane_bleach and clip_min is None and plan.info.n_passes > 0:
+        raise NotImplementedError("enable_masking without clip levels and without bleach correction makes the reference pad "
+                                  "with log1p(multi-Otsu clip_min) per image (core.py:1066-1077, 1101-1105): not implemented "
+                                  "for padding_mode='constant'")
+    levels, pads, meds = _otsu_levels(arr, clip_min, clip_med, clip_max, constant, skip_uniform, check=per_plane_bleach)
     with plan.lock:
-        plan.set_bleach_levels(levels, pads)
+        if per_plane_bleach:
+            plan.set_bleach_levels(levels, pads)
+        if per_plane_mask:
+            plan.set_mask_thresholds(meds)
         return _run(plan, arr)
 
 
@@ -510,9 +520,6 @@ def _bleach_plan_args(frequency, clip_min, clip_med, clip_max, max_method, enabl
     pad_constant = 0.0
     if clip_min is not None:                                            # core.py:1101-1105
         pad_constant = float(np.float32(np.log1p(clip_min)))
-    if enable_masking:
-        raise NotImplementedError("enable_masking (get_img_mask: morphology + flood fill, core.py:475-490) is not part "
-                                  "of the GPU hot path (SURVEY.md §8f N3)")
     if frequency is None:
         return None, pad_constant
     assert isinstance(frequency, (float, float32, np.float64)) and frequency > 0     # core.py:521
@@ -544,16 +551,18 @@ def _clip_levels(clip_min, clip_med, clip_max):
     return as_clip_sees(clip_min), float(np.float32(clip_med)), as_clip_sees(clip_max)
 
 
-def _otsu_levels(arr, clip_min, clip_med, clip_max, constant_padding: bool, skip_uniform: bool):
+def _otsu_levels(arr, clip_min, clip_med, clip_max, constant_padding: bool, skip_uniform: bool, check: bool = True):
     """Per-plane clip levels when some are left to multi-Otsu (core.py:1066-1077): exact per-plane histograms on the GPU
-    (b2s_histogram), thresholds on the host from the bins (pystripe/stack_stats.py), then the same checks as explicit levels.
-    Returns ([n, 3] float64 levels, [n] float32 constant-padding values or None)."""
+    (b2s_histogram), thresholds on the host from the bins (pystripe/stack_stats.py), then the same checks as explicit levels
+    (`check`: correct_bleaching's, when the levels feed it).
+    Returns ([n, 3] float64 levels, [n] float32 constant-padding values or None, [n] float64 clip_med as get_img_mask sees it)."""
     from . import stack_stats
     a3 = arr if arr.ndim == 3 else arr[None]
     h = stack_stats.histogram(a3, per_plane=True)
     h = h.cpu().numpy() if _native._is_torch(h) else h
     levels = np.empty((h.shape[0], 3), np.float64)
     pads = np.zeros(h.shape[0], np.float32) if constant_padding else None
+    meds = np.zeros(h.shape[0], np.float64)
     for z in range(h.shape[0]):
         if skip_uniform and np.count_nonzero(h[z]) <= 1:               # process_img returns zeros for such a plane (core.py:1232)
             levels[z] = (1.0, 2.0, 3.0)
@@ -562,10 +571,22 @@ def _otsu_levels(arr, clip_min, clip_med, clip_max, constant_padding: bool, skip
         cmin = lb if clip_min is None else clip_min
         cmed = mb if clip_med is None else clip_med
         cmax = ub if clip_max is None else clip_max
-        levels[z] = _clip_levels(cmin, cmed, cmax)
+        meds[z] = _mask_threshold(cmed, np.float32)
+        levels[z] = _clip_levels(cmin, cmed, cmax) if check else (cmin, cmed, cmax)
         if constant_padding:
             pads[z] = np.float32(np.log1p(cmin))                       # core.py:1101-1105
-    return levels, pads
+    return levels, pads, meds
+
+
+def _mask_threshold(threshold, image_dtype) -> float:
+    """`img > threshold` (core.py:479) as numpy evaluates it: a Python scalar is weak (rounded to float32 against the float32
+    log image), a numpy scalar promotes with the image dtype; against an integer image every comparison is exact.  The
+    kernel compares in double, which holds all of these exactly."""
+    if np.dtype(image_dtype) == np.float32:
+        if isinstance(threshold, np.generic) and np.result_type(np.float32, threshold.dtype) != np.float32:
+            return float(threshold)
+        return float(np.float32(threshold))
+    return float(threshold)
 
 
 def filter_streaks(
@@ -593,8 +614,8 @@ def filter_streaks(
 
     img: (H, W) or (Z, H, W); numpy array (host round trip) or CUDA torch tensor (zero-copy, current stream).
     `gpu_semaphore`, `crossover` are accepted and ignored (the thresholded dual-band variant is unreachable in the
-    reference, core.py:1113-1117).  Bleach correction (core.py:501-559) runs on the GPU for explicit clip levels and the
-    non-max method; masking and multi-Otsu clip levels raise NotImplementedError.
+    reference, core.py:1113-1117).  Bleach correction (core.py:501-559, both methods, explicit or multi-Otsu clip levels) and
+    masking (get_img_mask, core.py:475-489) run on the GPU.
     """
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
@@ -604,12 +625,20 @@ def filter_streaks(
                                              bleach_correction_clip_med, bleach_correction_clip_max,
                                              bleach_correction_max_method, enable_masking)
     arr, restore = _as_supported(img)
+    mask = None
+    if enable_masking and close_steps is not None and open_steps is not None:        # core.py:1079-1080
+        if bleach_correction_clip_med is None and not log1p_normalization_needed:
+            raise NotImplementedError("enable_masking with the threshold left to threshold_multiotsu on an image that is not "
+                                      "log-normalised (skimage's exact integer histogram path) is not implemented")
+        seen = np.float32 if (log1p_normalization_needed or _code_of(arr) == _native.F32) else np.uint16
+        mask = (0.0 if bleach_correction_clip_med is None else _mask_threshold(bleach_correction_clip_med, seen),
+                int(close_steps), int(open_steps), int(bleach_correction_clip_med is None))
     plan = _get_plan(_device_of(arr), arr.shape[-2:], _code_of(arr), process=0, sigma=sigma, level=level,
                      wavelet=wavelet, threshold=threshold, padding_mode=padding_mode, bidirectional=bidirectional,
-                     log1p=log1p_normalization_needed, bleach=bleach, pad_constant=pad_constant, _acquire=True)
+                     log1p=log1p_normalization_needed, bleach=bleach, pad_constant=pad_constant, mask=mask, _acquire=True)
     try:
         out = _run_with_levels(plan, arr, bleach, bleach_correction_clip_min, bleach_correction_clip_med,
-                               bleach_correction_clip_max, padding_mode, skip_uniform=False)
+                               bleach_correction_clip_max, padding_mode, skip_uniform=False, mask=mask)
     finally:
         _release_plan(plan)
     if verbose:
@@ -913,6 +942,31 @@ def resize_to_tile(img: ndarray, tile_size: Tuple[int, int]) -> ndarray:
             C.c_void_p(wx.ctypes.data if wx is not None else None), aa[1][0] if aa[1] else 0,
             C.c_void_p(out.data_ptr()), 1, C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
         return out.cpu().numpy()
+
+
+def get_img_mask(img, threshold, close_steps: int = 50, open_steps: int = 500, flood_fill_flag: int = 4):
+    """core.py:475-489 on the GPU (b2s_img_mask): `img > threshold`, cv2 MORPH_CLOSE with ones(close_steps, close_steps),
+    MORPH_OPEN with ones(open_steps, open_steps), then the background no corner pixel reaches through 4-connected background
+    is added back.  img: (H, W) or (Z, H, W), numpy array or CUDA tensor; returns a bool array / tensor of the same shape."""
+    if flood_fill_flag != 4:
+        raise NotImplementedError("get_img_mask: only the 4-connected flood fill the reference uses is implemented")
+    import ctypes as C
+    import torch
+    arr, _ = _as_supported(img)
+    dev = _device_of(arr)
+    with torch.cuda.device(dev):
+        t = arr.contiguous() if _native._is_torch(arr) else torch.from_numpy(np.ascontiguousarray(arr)).cuda(dev)
+        shape = tuple(t.shape)
+        rows, cols = shape[-2:]
+        n = 1 if t.dim() == 2 else int(shape[0])
+        out = torch.empty(shape, dtype=torch.uint8, device=t.device)
+        seen = np.float32 if _code_of(arr) == _native.F32 else np.uint16
+        ctx = _native.context(dev)
+        ctx.check(_native.lib().b2s_img_mask(ctx._h, C.c_void_p(t.data_ptr()), _code_of(arr), rows, cols, n,
+                                             _mask_threshold(threshold, seen), int(close_steps), int(open_steps),
+                                             C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
+        out = out.bool()
+        return out if _native._is_torch(arr) else out.cpu().numpy()
 
 
 # --------------------------------------------------------------------------------------------------------------

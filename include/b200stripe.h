@@ -102,6 +102,16 @@ typedef struct b2s_params {
                                      gaussian_filter(sigma = (in/out - 1) / 2, mode='mirror', truncate 4) ahead of the zoom):
                                      kernel radius int(4 sigma + 0.5) per axis, 0 = no filter along that axis; the 2r+1
                                      weights are uploaded with b2s_plan_set_aa_weights                              */
+    /* --- masking inside filter_streaks (core.py:475-489, 1079-1080) ------------------------------------ */
+    int32_t mask;                 /* enable_masking with close_steps / open_steps given: img *= get_img_mask(img, threshold)
+                                     on the (log) image ahead of the padding: img > threshold, cv2 MORPH_CLOSE with ones(close,
+                                     close), MORPH_OPEN with ones(open, open), holes that no corner reaches filled (four
+                                     4-connected cv2.floodFill)                                                    */
+    int32_t mask_close, mask_open;/* close_steps, open_steps (>= 1)                                                 */
+    int32_t mask_per_plane;       /* 1: one threshold per plane through b2s_plan_set_mask_thresholds before every b2s_run
+                                     (bleach_correction_clip_med left to multi-Otsu, core.py:1066-1075)            */
+    double mask_threshold;        /* bleach_correction_clip_med as numpy compares it with the image (the caller rounds a weak
+                                     Python scalar to float32 against a float32 image); the kernel compares in double */
     /* --- execution ------------------------------------------------------------------------------------ */
     int32_t max_batch;            /* planes processed per launch group (workspace is sized for this)         */
     int32_t debug_stop_after;     /* b2s_stage; 0 in production                                             */
@@ -169,6 +179,10 @@ int b2s_plan_set_notch_matrix(b2s_plan *plan, int pass, int level, int axis, con
  * numpy.clip compares them, after the clip_min >= log1p(1) rule of core.py:529-531); pad_value: n_planes floats,
  * log1p(clip_min) for padding_mode='constant' (core.py:1101-1105), or NULL.  Plane z of the next b2s_run uses entry z. */
 int b2s_plan_set_bleach_levels(b2s_plan *plan, const double *clip, const float *pad_value, int64_t n_planes);
+/* replaces: the threshold of get_img_mask when enable_masking is set and bleach_correction_clip_med is None
+ * (core.py:1066-1075, 1079-1080: mb of threshold_multiotsu, per image).  thr: n_planes doubles; plane z of the next b2s_run
+ * uses entry z.  Plans created with mask_per_plane only. */
+int b2s_plan_set_mask_thresholds(b2s_plan *plan, const double *thr, int64_t n_planes);
 
 /*
  * replaces: process_img(img, ...) / filter_streaks(img, ...) applied to n_planes independent planes
@@ -237,6 +251,12 @@ int b2s_isotropic_z(b2s_context *ctx, const float *d_in, int n_in, int64_t plane
  * d_out: uint16 (mode 1) or uint8. */
 int b2s_isotropic_convert(b2s_context *ctx, const float *d_in, int64_t n, int mode, int shift, void *d_out, void *stream);
 
+/* replaces: get_img_mask(img, threshold, close_steps, open_steps, flood_fill_flag=4) (pystripe/core.py:475-489) on n_planes
+ * independent planes: img > threshold, cv2.morphologyEx MORPH_CLOSE with ones(close, close), MORPH_OPEN with ones(open, open),
+ * background that no corner pixel reaches through 4-connected background added back (the four cv2.floodFill calls).
+ * img, mask: DEVICE pointers (rows x cols per plane; mask bytes 0 / 1).  Synchronises the stream. */
+int b2s_img_mask(b2s_context *ctx, const void *img, int dtype, int rows, int cols, int n_planes, double threshold, int close_steps,
+                 int open_steps, unsigned char *mask, void *stream);
 /* replaces: the pixel pass of `estimate_img_related_params` (process_images.py:594-659), which feeds log1p of a plane to
  * skimage.filters.threshold_multiotsu and to a masked percentile (:320-331).  Both are functions of the intensity
  * histogram: this entry ADDS the exact histogram of n_planes planes of uint8 / uint16 pixels (plane_elems each) into

@@ -185,11 +185,44 @@ def sosfiltfilt_order1_restated(x, sos, zi0):
     return y[..., edge:-edge]
 
 
+def _box_morph(mask, k, erode):
+    """cv2.dilate / cv2.erode with ones((k, k)) and the default anchor (k // 2, k // 2): the window covers the offsets
+    [-(k // 2), k - 1 - k // 2] on both axes for both operations; outside the image dilate sees 0 and erode sees 1
+    (cv2.morphologyDefaultBorderValue).  Separable window counts through cumulative sums."""
+    lo, hi = -(k // 2), k - 1 - k // 2
+    m = mask.astype(np.int64)
+    for axis in (1, 0):
+        n = m.shape[axis]
+        pre = np.concatenate([np.zeros_like(np.take(m, [0], axis=axis)), np.cumsum(m, axis=axis)], axis=axis)
+        idx = np.arange(n)
+        a, b = np.clip(idx + lo, 0, n), np.clip(idx + hi + 1, 0, n)
+        b = np.maximum(a, b)
+        ones = np.take(pre, b, axis=axis) - np.take(pre, a, axis=axis)
+        length = (b - a).reshape((-1, 1) if axis == 0 else (1, -1))
+        m = (ones == length).astype(np.int64) if erode else (ones > 0).astype(np.int64)
+    return m.astype(np.uint8)
+
+
+def get_img_mask(img, threshold, close_steps=50, open_steps=500):
+    """core.py:475-489: threshold, MORPH_CLOSE (dilate, erode), MORPH_OPEN (erode, dilate), then the four 4-connected
+    floodFill calls from the corners of the inverted mask: background components that hold no corner pixel are holes and
+    join the mask.  (cv2 itself is the check: tests/test_oracle.py.)"""
+    from scipy import ndimage
+    mask = (img > threshold).astype(np.uint8)
+    mask = _box_morph(_box_morph(mask, close_steps, False), close_steps, True)
+    mask = _box_morph(_box_morph(mask, open_steps, True), open_steps, False).astype(bool)
+    lab, _ = ndimage.label(~mask)                       # default structure: 4-connectivity
+    corner = {int(lab[y, x]) for y in (0, -1) for x in (0, -1)} - {0}
+    holes = (lab > 0) & ~np.isin(lab, list(corner))
+    return mask | holes
+
+
 def filter_streaks(img, sigma=(250, 250), level=0, wavelet='db9', crossover=10, threshold=None,
                    padding_mode="wrap", bidirectional=False, log1p_normalization_needed=True,
                    return_log_domain=False, bleach_correction_frequency=None, bleach_correction_clip_min=None,
-                   bleach_correction_clip_med=None, bleach_correction_clip_max=None, bleach_correction_max_method=False):
-    """core.py:982-1159 without masking (multi-Otsu clip levels through the restated threshold_multiotsu below)."""
+                   bleach_correction_clip_med=None, bleach_correction_clip_max=None, bleach_correction_max_method=False,
+                   enable_masking=False, close_steps=50, open_steps=500):
+    """core.py:982-1159 (multi-Otsu clip levels through the restated threshold_multiotsu below)."""
     if not isinstance(sigma, (tuple, list)):
         sigma = (sigma,) * 2
     s1, s2 = sigma
@@ -198,8 +231,9 @@ def filter_streaks(img, sigma=(250, 250), level=0, wavelet='db9', crossover=10, 
     d_type = img.dtype
     if log1p_normalization_needed:
         img = log1p_f32(img.astype(np.float32))
-    if bleach_correction_frequency is not None and (bleach_correction_clip_min is None or bleach_correction_clip_med is None
-                                                    or bleach_correction_clip_max is None):     # core.py:1066-1077
+    if (bleach_correction_frequency is not None and (bleach_correction_clip_min is None or bleach_correction_clip_med is None
+                                                     or bleach_correction_clip_max is None)) or \
+            (enable_masking and bleach_correction_clip_med is None):                             # core.py:1066-1077
         lb, mb, ub = threshold_multiotsu(img, classes=4)
         if bleach_correction_clip_min is None:
             bleach_correction_clip_min = lb
@@ -207,6 +241,9 @@ def filter_streaks(img, sigma=(250, 250), level=0, wavelet='db9', crossover=10, 
             bleach_correction_clip_med = mb
         if bleach_correction_clip_max is None:
             bleach_correction_clip_max = ub
+    if enable_masking and close_steps is not None and open_steps is not None:      # core.py:1079-1080
+        img = img.copy() if not log1p_normalization_needed else img
+        img *= get_img_mask(img, bleach_correction_clip_med, close_steps=close_steps, open_steps=open_steps)
     if not s1 == s2 == 0:                                                          # core.py:1081 (no padding otherwise)
         shape = img.shape
         base_pad, pad_y, pad_x = padded_geometry(shape, sigma, padding_mode)

@@ -14,6 +14,22 @@ def normalize_flat(flat):
     return f / f.max()
 
 
+MASK_LOG_THRESHOLD = 6.8          # log1p(900) ~ 6.80
+
+
+def mask_plane(shape=(150, 180), seed=21):
+    """a plane with a dim background (< 900), a bright ring (hole inside) and a bright block touching one border."""
+    img = (synth.plane(seed, shape) // 8).astype(np.uint16)
+    img = np.minimum(img, 700)
+    y, x = np.mgrid[0:shape[0], 0:shape[1]]
+    r = np.hypot(y - 70, x - 80)
+    ring = (r > 22) & (r < 45)
+    img[ring] += 2500
+    img[100:150, 0:40] += 1800
+    img[10:14, 150:170] += 3000          # a thin streak the opening removes
+    return img
+
+
 def all_cases():
     """yields (name, kind, img, kwargs).  kind in {"filter_streaks", "process_img"}; '_flat' = flat-field array."""
     rng = np.random.default_rng(7)
@@ -51,6 +67,19 @@ def all_cases():
                                              bleach_correction_max_method=True, **bl)
     yield "fs_bleach_max_method_zero_rows_odd", fs, zeros_in[:95, :127], dict(sigma=(0, 0), bleach_correction_max_method=True, **bl)
     yield "fs_bleach_only_sigma0_odd", fs, zeros_in[:95, :127], dict(sigma=(0, 0), **bl)
+    # masking (core.py:475-489, 1079-1080): the threshold is compared with the LOG image; a bright ring leaves a hole that
+    # no corner reaches, a dim corner patch keeps background connected to a corner
+    yield "fs_mask_explicit_reflect", fs, mask_plane(), dict(sigma=(16, 16), wavelet="db4", padding_mode="reflect", enable_masking=True,
+                                                              bleach_correction_clip_med=MASK_LOG_THRESHOLD, close_steps=5, open_steps=9)
+    yield "fs_mask_even_kernels_constant", fs, mask_plane(), dict(sigma=(8, 24), wavelet="db2", padding_mode="constant", enable_masking=True,
+                                                                   bleach_correction_clip_min=3.0, bleach_correction_clip_med=MASK_LOG_THRESHOLD,
+                                                                   bleach_correction_clip_max=9.0, close_steps=6, open_steps=12)
+    yield "fs_mask_nolog_int", fs, mask_plane(), dict(sigma=(16, 16), wavelet="db4", padding_mode="reflect", enable_masking=True,
+                                                       log1p_normalization_needed=False, bleach_correction_clip_med=900, close_steps=5,
+                                                       open_steps=9)
+    yield "fs_mask_sigma0_bleach", fs, mask_plane(), dict(sigma=(0, 0), enable_masking=True, close_steps=5, open_steps=9, **dict(bl, bleach_correction_clip_med=MASK_LOG_THRESHOLD, bleach_correction_clip_max=9.5))
+    yield "fs_mask_default_steps_small_tile", fs, mask_plane(), dict(sigma=(16, 16), wavelet="db4", enable_masking=True,
+                                                                      bleach_correction_clip_med=MASK_LOG_THRESHOLD)
     pi = "process_img"
     img = synth.plane(3, (96, 128))
     yield "pi_bleach_only_flat_16bit", pi, img, dict(sigma=(0, 0), dark=100, convert_to_16bit=True,

@@ -505,7 +505,7 @@ def test_bleach_correction_goldens_bit_exact():
         REPORT["bleach/" + name] = {"exact_fraction": float(same.mean())}
         assert same.all(), (name, float(same.mean()), float(np.abs(got.astype(np.float64) - ref).max()))
         n += 1
-    assert n == 10
+    assert n == 11
 
 
 @pytest.mark.parametrize("shape,freq", [((700, 900), 1 / 700.0), ((257, 2051), 1 / 2048.0)])
@@ -541,6 +541,57 @@ def test_bleach_clip_levels_from_multiotsu_per_plane(kw):
     assert np.array_equal(out[0], orc.process_img(stack[0].copy(), dark=100, **base))
 
 
+def test_get_img_mask_matches_the_oracle():
+    """get_img_mask (core.py:475-489) on the GPU: threshold, box close / open (even and odd kernels, kernels larger than the
+    plane), corner flood fills — every mask identical to the oracle's (itself pinned against cv2)."""
+    import torch
+    from scipy import ndimage
+    from pystripe import core
+    rng = np.random.default_rng(5)
+    for t in range(12):
+        h, w = (int(v) for v in rng.integers(40, 400, 2))
+        f = ndimage.gaussian_filter(rng.random((3, h, w)), (0, 4, 4)).astype(np.float32)
+        thr = float(np.quantile(f, rng.uniform(0.3, 0.7)))
+        c, o = int(rng.integers(1, 14)), int(rng.integers(1, 40))
+        got = core.get_img_mask(f, thr, c, o)
+        assert got.dtype == bool and got.shape == f.shape
+        for z in range(3):
+            assert np.array_equal(got[z], orc.get_img_mask(f[z], np.float32(thr), c, o)), (t, z, h, w, c, o)
+    ring = cases.mask_plane()
+    assert np.array_equal(core.get_img_mask(ring, 900, 5, 9), orc.get_img_mask(ring, 900, 5, 9))
+    assert np.array_equal(core.get_img_mask(ring, 900), orc.get_img_mask(ring, 900))                # 50 / 500 on a small plane
+    big = np.zeros((1200, 1500), np.uint16)
+    big[100:1100, 200:1300] = 1000
+    big[400:700, 500:900] = 0                                                                        # a hole
+    big[0:30, 0:30] = 1000
+    spiral = core.get_img_mask(torch.from_numpy(big).cuda(), 500)                                    # the reference's defaults
+    assert spiral.is_cuda and np.array_equal(spiral.cpu().numpy(), orc.get_img_mask(big, 500))
+    with pytest.raises(NotImplementedError):
+        core.get_img_mask(ring, 900, flood_fill_flag=8)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(sigma=(16, 16), wavelet="db6", close_steps=4, open_steps=7, bleach_correction_frequency=1 / 64.0),     # Otsu: levels + threshold
+    dict(sigma=(12, 12), wavelet="db3", padding_mode="symmetric", close_steps=3, open_steps=5),                # Otsu threshold only
+    dict(sigma=(16, 16), wavelet="db4", padding_mode="maximum", close_steps=5, open_steps=9, bleach_correction_clip_med=6.8),
+    dict(sigma=(16, 16), wavelet="db4", padding_mode="linear_ramp", close_steps=5, open_steps=9, bleach_correction_clip_med=np.float64(6.8)),
+    dict(sigma=(8, 8), wavelet="db2", padding_mode="wrap", close_steps=None, open_steps=9, bleach_correction_clip_med=6.8),   # no mask
+])
+def test_enable_masking_per_plane(kw):
+    """filter_streaks(enable_masking=True): img *= get_img_mask(img, clip_med) on the log image ahead of numpy.pad
+    (core.py:1079-1080); clip_med left to multi-Otsu gives every plane of a batch its own threshold."""
+    from pystripe import core
+    a = cases.mask_plane()
+    b = cases.mask_plane(seed=22)[::-1].copy()
+    b[b > 2000] += 700
+    stack = np.stack([a, b])
+    got = core.filter_streaks(stack, enable_masking=True, **kw)
+    for z in range(2):
+        ref = orc.filter_streaks(stack[z], enable_masking=True, **kw)
+        _cmp_int(f"mask/{kw}/{z}", got[z], ref)
+        assert kw.get("close_steps") is None or (ref == 0).mean() > 0.3
+
+
 @pytest.mark.parametrize("kw", [dict(sigma=(24, 24), wavelet="db3"), dict(sigma=(16, 48), wavelet="db6", padding_mode="reflect"),
                                 dict(sigma=(20, 20), wavelet="db9", bidirectional=True, padding_mode="symmetric")])
 def test_integer_pixels_without_log1p_run_in_float64(kw):
@@ -568,5 +619,7 @@ def test_bleach_argument_errors():
     with pytest.raises(AssertionError):               # core.py:524-527
         core.filter_streaks(img, sigma=(8, 8), bleach_correction_frequency=0.01, bleach_correction_clip_min=5.0,
                             bleach_correction_clip_med=4.0, bleach_correction_clip_max=6.0)
-    with pytest.raises(NotImplementedError):
-        core.filter_streaks(img, sigma=(8, 8), enable_masking=True)
+    with pytest.raises(NotImplementedError):          # the threshold would come from skimage's exact integer histogram path
+        core.filter_streaks(img, sigma=(8, 8), enable_masking=True, log1p_normalization_needed=False)
+    with pytest.raises(NotImplementedError):          # per-image log1p(multi-Otsu clip_min) as the constant-padding value
+        core.filter_streaks(img, sigma=(8, 8), enable_masking=True, padding_mode="constant")

@@ -254,8 +254,13 @@ def test_bleach_plan_args_host_logic():
     # per-plane levels: multi-Otsu values for the missing ones, the same checks and float32 / float64 rules as explicit levels
     lv = core._clip_levels(np.float32(0.5), np.float32(5.0), 6.5)
     assert lv == (float(np.log1p(1)), 5.0, float(np.float32(6.5)))
-    with pytest.raises(NotImplementedError):
-        core._bleach_plan_args(None, None, None, None, False, True)
+    assert core._bleach_plan_args(None, None, None, None, False, True) == (None, 0.0)   # masking alone: no bleach data
+    # get_img_mask's `img > threshold` as numpy evaluates it: weak Python scalars round to float32 against the log image,
+    # a float64 numpy scalar promotes the comparison, integer images compare exactly
+    assert core._mask_threshold(6.8, np.float32) == float(np.float32(6.8)) != 6.8
+    assert core._mask_threshold(np.float64(6.8), np.float32) == 6.8
+    assert core._mask_threshold(np.float32(6.8), np.float32) == float(np.float32(6.8))
+    assert core._mask_threshold(900, np.uint16) == 900.0 and core._mask_threshold(900.5, np.uint16) == 900.5
     with pytest.raises(AssertionError):
         core._bleach_plan_args(0.01, 5.0, 4.0, 6.0, False, False)
     with pytest.raises(AssertionError):

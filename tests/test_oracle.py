@@ -162,6 +162,38 @@ def test_oracle_matches_golden_vectors():
     assert n == len(meta)
 
 
+def test_get_img_mask_restatement_matches_opencv():
+    """oracle.get_img_mask (window counts + scipy.ndimage.label) against the cv2 calls of core.py:479-487, including even
+    kernels (asymmetric window), kernels larger than the image and holes that no corner reaches."""
+    cv2 = pytest.importorskip("cv2")
+    from scipy import ndimage
+
+    def with_cv2(img, thr, c, o):
+        mask = (img > thr).astype(np.uint8)
+        mask = cv2.morphologyEx(mask, cv2.MORPH_CLOSE, np.ones((c, c), np.uint8))
+        mask = cv2.morphologyEx(mask, cv2.MORPH_OPEN, np.ones((o, o), np.uint8)).astype(bool)
+        inv = np.logical_not(mask).astype(np.uint8)
+        h, w = img.shape
+        for pt in ((0, 0), (0, h - 1), (w - 1, 0), (w - 1, h - 1)):
+            cv2.floodFill(inv, None, pt, 0, flags=4)
+        return mask | inv.astype(bool)
+    rng = np.random.default_rng(3)
+    holes = 0
+    for t in range(60):
+        h, w = (int(v) for v in rng.integers(20, 140, 2))
+        img = ndimage.gaussian_filter(rng.random((h, w)), rng.uniform(1, 6))
+        thr = np.quantile(img, rng.uniform(0.2, 0.8))
+        c, o = int(rng.integers(1, 12)), int(rng.integers(1, 25))
+        a, b = orc.get_img_mask(img, thr, c, o), with_cv2(img, thr, c, o)
+        assert np.array_equal(a, b), (t, h, w, c, o)
+        holes += int((b & ~(img > thr)).any())
+    assert holes > 5
+    ring = cases.mask_plane()
+    assert np.array_equal(orc.get_img_mask(ring, 900, 5, 9), with_cv2(ring, 900, 5, 9))
+    assert orc.get_img_mask(ring, 900, 5, 9)[70, 80] and not orc.get_img_mask(ring, 900, 5, 9)[0, 0]
+    assert np.array_equal(orc.get_img_mask(ring, 900, 50, 500), with_cv2(ring, 900, 50, 500))
+
+
 @pytest.mark.skipif(not ref_runner.available(), reason="/root/reference only exists in the build container")
 def test_oracle_matches_reference_verbatim():
     r = subprocess.run([sys.executable, "-m", "oracle.ref_check"], cwd=ROOT, capture_output=True, text=True, timeout=600)
