@@ -1657,6 +1657,48 @@ int b2s_isotropic_convert(b2s_context *ctx, const float *d_in, int64_t n, int mo
     return B2S_OK;
 }
 
+int64_t b2s_deflate_bound(int dtype, int rows, int cols, int n_planes, int rows_per_strip)
+{
+    if (rows <= 0 || cols <= 0 || n_planes <= 0 || rows_per_strip <= 0 || dtype < 0 || dtype > 2) return B2S_ERR_INVALID;
+    const size_t plane_bytes = (size_t)rows * cols * dtype_size(dtype);
+    return (int64_t)b2s_deflate_bound_bytes(plane_bytes, (rows + rows_per_strip - 1) / rows_per_strip, n_planes);
+}
+
+int b2s_deflate_strips(b2s_context *ctx, const void *d_planes, int dtype, int rows, int cols, int n_planes, int rows_per_strip,
+                       void *d_out, int64_t out_capacity, uint32_t *d_sizes, uint64_t *d_offsets, int64_t *total_bytes, void *stream)
+{
+    if (!ctx || !d_planes || !d_out || !d_sizes || !d_offsets || !total_bytes) return B2S_ERR_INVALID;
+    if (rows <= 0 || cols <= 0 || n_planes <= 0 || rows_per_strip <= 0 || dtype < 0 || dtype > 2)
+        return fail(ctx, B2S_ERR_INVALID, "b2s_deflate_strips: bad geometry");
+    if (((uintptr_t)d_out & 3) != 0 || out_capacity < 64) return fail(ctx, B2S_ERR_INVALID, "b2s_deflate_strips: the output must be 4-byte aligned");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t row_bytes = (size_t)cols * dtype_size(dtype), plane_bytes = row_bytes * rows;
+    const int spp = (rows + rows_per_strip - 1) / rows_per_strip;
+    const size_t n = (size_t)spp * n_planes;
+    unsigned *tmp = nullptr;
+    auto release = [&]() { if (tmp) cudaFreeAsync(tmp, st); };
+    struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
+    if (cudaMallocAsync((void **)&tmp, sizeof(unsigned) * (n * 513 + 4), st) != cudaSuccess) return fail(ctx, B2S_ERR_NOMEM, "cudaMallocAsync failed");
+    int *d_over = reinterpret_cast<int *>(tmp + n * 513);
+    CU(ctx, cudaMemsetAsync(d_over, 0, sizeof(int), st));
+    const size_t usable = ((size_t)out_capacity - 8) & ~(size_t)3;
+    CU(ctx, cudaMemsetAsync(d_out, 0, (size_t)out_capacity, st));       // the bit writer ORs into shared boundary words
+    b2s_launch_deflate(d_planes, plane_bytes, row_bytes, rows, rows_per_strip, n_planes, tmp, d_sizes,
+                       reinterpret_cast<unsigned long long *>(d_offsets), d_out, usable, d_over, st);
+    ctx->launches += 4;
+    int over = 0;
+    unsigned long long total = 0;
+    CU(ctx, cudaMemcpyAsync(&over, d_over, sizeof over, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaMemcpyAsync(&total, d_offsets + n, sizeof total, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    CU(ctx, cudaGetLastError());
+    if (over) return fail(ctx, B2S_ERR_NOMEM, "b2s_deflate_strips: %llu compressed bytes do not fit the %lld-byte output (b2s_deflate_bound)",
+                          total, (long long)out_capacity);
+    *total_bytes = (int64_t)total;
+    return B2S_OK;
+}
+
 int b2s_img_mask(b2s_context *ctx, const void *img, int dtype, int rows, int cols, int n_planes, double threshold, int close_steps,
                  int open_steps, unsigned char *mask, void *stream)
 {

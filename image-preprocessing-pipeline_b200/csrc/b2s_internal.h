@@ -141,6 +141,12 @@ void b2s_launch_mask_threshold_int(const void *in, int dtype, size_t n_per_plane
 void b2s_launch_mask_apply(const B2sImg &padded, const unsigned char *mask, int base_pad, int rows, int cols, int pad_mode,
                            int n_planes, cudaStream_t s);
 
+// deflate.cu -------------------------------------------------------------------------------------------------------
+// one zlib stream (literal-only dynamic Huffman block) per strip of rows_per_strip rows, packed back to back into `out`
+size_t b2s_deflate_bound_bytes(size_t plane_bytes, int strips_per_plane, int n_planes);
+void b2s_launch_deflate(const void *in, size_t plane_bytes, size_t row_bytes, int rows, int rows_per_strip, int n_planes, unsigned *tmp,
+                        unsigned *sizes, unsigned long long *offsets, void *out, size_t capacity, int *overflow, cudaStream_t s);
+
 // stats.cu ---------------------------------------------------------------------------------------------------------
 // exact intensity histogram of uint8 / uint16 planes, ADDED into `hist` (65 536 uint64 counters, per plane or one for all)
 void b2s_launch_histogram(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned long long *hist, int per_plane,

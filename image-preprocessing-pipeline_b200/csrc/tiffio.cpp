@@ -501,6 +501,71 @@ int write_all(int fd, const void *p, size_t n, const char *path)
     return 0;
 }
 
+// layout: header | strip data | offsets array | counts array | IFD
+int write_tiff_layout(const char *path, int32_t height, int32_t width, int32_t dtype, int64_t rps,
+                      const std::vector<std::pair<const uint8_t *, size_t>> &pieces, int compression)
+{
+    const int es = dtype_size(dtype);
+    const int64_t n_strips = (int64_t)pieces.size();
+    std::vector<uint32_t> offs(n_strips), cnts(n_strips);
+    uint64_t pos = 8;
+    for (int64_t s = 0; s < n_strips; ++s) {
+        offs[s] = (uint32_t)pos;
+        cnts[s] = (uint32_t)pieces[s].second;
+        pos += pieces[s].second;
+        if (pos > 0xFFF00000ull) return fail(B2SIO_ERR_UNSUPPORTED, "%s: file would exceed the classic TIFF limit", path);
+    }
+    if (pos & 1) ++pos;
+    const uint32_t data_end = (uint32_t)pos;
+    Out tail;
+    uint32_t offs_at = 0, cnts_at = 0;
+    if (n_strips > 1) {
+        offs_at = data_end;
+        for (uint32_t v : offs) tail.u32(v);
+        cnts_at = data_end + (uint32_t)tail.b.size();
+        for (uint32_t v : cnts) tail.u32(v);
+    }
+    const uint32_t ifd_at = data_end + (uint32_t)tail.b.size();
+    struct Ent { uint16_t tag, type; uint32_t count, value; };
+    std::vector<Ent> ents = {
+        {256, 4, 1, (uint32_t)width}, {257, 4, 1, (uint32_t)height}, {258, 3, 1, (uint32_t)(8 * es)},
+        {259, 3, 1, (uint32_t)compression}, {262, 3, 1, 1},
+        {273, 4, (uint32_t)n_strips, n_strips > 1 ? offs_at : offs[0]}, {277, 3, 1, 1}, {278, 4, 1, (uint32_t)rps},
+        {279, 4, (uint32_t)n_strips, n_strips > 1 ? cnts_at : cnts[0]}, {284, 3, 1, 1}, {339, 3, 1, (uint32_t)(dtype == 2 ? 3 : 1)},
+    };
+    tail.u16((uint16_t)ents.size());
+    for (const Ent &e : ents) { tail.u16(e.tag); tail.u16(e.type); tail.u32(e.count); tail.u32(e.value); }
+    tail.u32(0);
+    Out head;
+    head.b = {'I', 'I'};
+    head.u16(42);
+    head.u32(ifd_at);
+
+    const std::string tmp = std::string(path) + ".b2s~";
+    const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0777);
+    if (fd < 0) return fail(B2SIO_ERR_IO, "open(%s): %s", tmp.c_str(), strerror(errno));
+    int rc = write_all(fd, head.b.data(), head.b.size(), path);
+    // consecutive pieces that are adjacent in memory go out in one write
+    for (int64_t s = 0; s < n_strips && !rc;) {
+        const uint8_t *p0 = pieces[s].first;
+        size_t run = pieces[s].second;
+        int64_t e = s + 1;
+        while (e < n_strips && pieces[e].first == p0 + run) run += pieces[e++].second;
+        rc = write_all(fd, p0, run, path);
+        s = e;
+    }
+    if (!rc && data_end != offs.back() + cnts.back()) {   // the directory starts on a word boundary
+        const uint8_t z = 0;
+        rc = write_all(fd, &z, 1, path);
+    }
+    if (!rc) rc = write_all(fd, tail.b.data(), tail.b.size(), path);
+    fchmod(fd, 0777);   // the reference chmods its output to 0o777 (core.py:311-314)
+    if (::close(fd) != 0 && !rc) rc = fail(B2SIO_ERR_IO, "close(%s): %s", tmp.c_str(), strerror(errno));
+    if (!rc && ::rename(tmp.c_str(), path) != 0) rc = fail(B2SIO_ERR_IO, "rename(%s): %s", path, strerror(errno));
+    if (rc) ::unlink(tmp.c_str());
+    return rc;
+}
+
 int write_tiff(const char *path, const void *src, int32_t height, int32_t width, int32_t dtype, int level, int n_threads)
 {
     const bool use_zstd = level > 100;
@@ -537,60 +602,13 @@ int write_tiff(const char *path, const void *src, int32_t height, int32_t width,
         });
         if (err.load()) return fail(B2SIO_ERR_IO, "%s: deflate failed", path);
     }
-    // layout: header | strip data | offsets array | counts array | IFD
-    std::vector<uint32_t> offs(n_strips), cnts(n_strips);
-    uint64_t pos = 8;
+    std::vector<std::pair<const uint8_t *, size_t>> pieces((size_t)n_strips);
     for (int64_t s = 0; s < n_strips; ++s) {
         const int64_t y0 = s * rps, rows = std::min(rps, height - y0);
-        offs[s] = (uint32_t)pos;
-        cnts[s] = level > 0 ? (uint32_t)comp[s].size() : (uint32_t)((size_t)rows * row_bytes);
-        pos += cnts[s];
-        if (pos > 0xFFF00000ull) return fail(B2SIO_ERR_UNSUPPORTED, "%s: file would exceed the classic TIFF limit", path);
+        if (level > 0) pieces[s] = {comp[s].data(), comp[s].size()};
+        else pieces[s] = {in + (size_t)y0 * row_bytes, (size_t)rows * row_bytes};
     }
-    if (pos & 1) ++pos;
-    const uint32_t data_end = (uint32_t)pos;
-    Out tail;
-    uint32_t offs_at = 0, cnts_at = 0;
-    if (n_strips > 1) {
-        offs_at = data_end;
-        for (uint32_t v : offs) tail.u32(v);
-        cnts_at = data_end + (uint32_t)tail.b.size();
-        for (uint32_t v : cnts) tail.u32(v);
-    }
-    const uint32_t ifd_at = data_end + (uint32_t)tail.b.size();
-    struct Ent { uint16_t tag, type; uint32_t count, value; };
-    std::vector<Ent> ents = {
-        {256, 4, 1, (uint32_t)width}, {257, 4, 1, (uint32_t)height}, {258, 3, 1, (uint32_t)(8 * es)},
-        {259, 3, 1, (uint32_t)(use_zstd ? 50000 : (level > 0 ? 8 : 1))}, {262, 3, 1, 1},
-        {273, 4, (uint32_t)n_strips, n_strips > 1 ? offs_at : offs[0]}, {277, 3, 1, 1}, {278, 4, 1, (uint32_t)rps},
-        {279, 4, (uint32_t)n_strips, n_strips > 1 ? cnts_at : cnts[0]}, {284, 3, 1, 1}, {339, 3, 1, (uint32_t)(dtype == 2 ? 3 : 1)},
-    };
-    tail.u16((uint16_t)ents.size());
-    for (const Ent &e : ents) { tail.u16(e.tag); tail.u16(e.type); tail.u32(e.count); tail.u32(e.value); }
-    tail.u32(0);
-    Out head;
-    head.b = {'I', 'I'};
-    head.u16(42);
-    head.u32(ifd_at);
-
-    const std::string tmp = std::string(path) + ".b2s~";
-    const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0777);
-    if (fd < 0) return fail(B2SIO_ERR_IO, "open(%s): %s", tmp.c_str(), strerror(errno));
-    int rc = write_all(fd, head.b.data(), head.b.size(), path);
-    if (!rc) {
-        if (level > 0) { for (int64_t s = 0; s < n_strips && !rc; ++s) rc = write_all(fd, comp[s].data(), comp[s].size(), path); }
-        else rc = write_all(fd, in, total, path);
-    }
-    if (!rc && data_end != offs.back() + cnts.back()) {   // the directory starts on a word boundary
-        const uint8_t z = 0;
-        rc = write_all(fd, &z, 1, path);
-    }
-    if (!rc) rc = write_all(fd, tail.b.data(), tail.b.size(), path);
-    fchmod(fd, 0777);   // the reference chmods its output to 0o777 (core.py:311-314)
-    if (::close(fd) != 0 && !rc) rc = fail(B2SIO_ERR_IO, "close(%s): %s", tmp.c_str(), strerror(errno));
-    if (!rc && ::rename(tmp.c_str(), path) != 0) rc = fail(B2SIO_ERR_IO, "rename(%s): %s", path, strerror(errno));
-    if (rc) ::unlink(tmp.c_str());
-    return rc;
+    return write_tiff_layout(path, height, width, dtype, rps, pieces, use_zstd ? 50000 : (level > 0 ? 8 : 1));
 }
 
 }  // namespace
@@ -653,6 +671,29 @@ int b2sio_write_tiff_batch(const char *const *paths, int n_files, const void *sr
     const int per_file = n_files > 0 ? std::max(1, n_threads / std::max(1, n_files)) : 1;
     parallel_for(n_files, n_threads, [&](int64_t i) {
         status[i] = write_tiff(paths[i], (const char *)src + (size_t)i * plane_stride_bytes, height, width, dtype, deflate_level, per_file);
+        if (status[i]) ++failed;
+    });
+    return failed.load();
+}
+
+int b2sio_write_tiff_strips_batch(const char *const *paths, int n_files, const void *data, const uint64_t *strip_offsets,
+                                  const uint32_t *strip_sizes, int32_t strips_per_file, int32_t rows_per_strip, int32_t height,
+                                  int32_t width, int32_t dtype, int32_t compression, int n_threads, int32_t *status)
+{
+    if (!paths || n_files < 0 || !data || !strip_offsets || !strip_sizes || !status || strips_per_file <= 0 || rows_per_strip <= 0 ||
+        height <= 0 || width <= 0 || dtype < 0 || dtype > 2 ||
+        (int64_t)strips_per_file != ((int64_t)height + rows_per_strip - 1) / rows_per_strip)
+        return fail(B2SIO_ERR_INVALID, "bad argument");
+    std::atomic<int> failed{0};
+    parallel_for(n_files, n_threads, [&](int64_t i) {
+        status[i] = 0;
+        if (!paths[i]) return;                     // a slot without a file (a plane that is not written)
+        std::vector<std::pair<const uint8_t *, size_t>> pieces((size_t)strips_per_file);
+        for (int32_t s = 0; s < strips_per_file; ++s) {
+            const size_t k = (size_t)i * strips_per_file + s;
+            pieces[s] = {(const uint8_t *)data + strip_offsets[k], (size_t)strip_sizes[k]};
+        }
+        status[i] = write_tiff_layout(paths[i], height, width, dtype, rows_per_strip, pieces, compression);
         if (status[i]) ++failed;
     });
     return failed.load();

@@ -15,7 +15,7 @@ LIB_PATH = Path(os.environ.get("B2SIO_LIB", _PKG.parent / "lib" / "libb2sio.so")
 
 OK, ERR_IO, ERR_FORMAT, ERR_UNSUPPORTED, ERR_SHAPE, ERR_INVALID = 0, -1, -2, -3, -4, -5
 EXPORTS = ("b2sio_version", "b2sio_last_error", "b2sio_probe", "b2sio_read", "b2sio_read_batch", "b2sio_write_tiff",
-           "b2sio_write_tiff_batch", "b2sio_write_raw")
+           "b2sio_write_tiff_batch", "b2sio_write_tiff_strips_batch", "b2sio_write_raw")
 _CODES = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}
 _DTYPES = {0: np.uint8, 1: np.uint16, 2: np.float32}
 
@@ -49,6 +49,8 @@ def lib():
         L.b2sio_write_tiff.argtypes = [cp, vp, i32, i32, i32, C.c_int, C.c_int]
         L.b2sio_write_tiff_batch.argtypes = [C.POINTER(cp), C.c_int, vp, C.c_size_t, i32, i32, i32, C.c_int, C.c_int,
                                              C.POINTER(i32)]
+        L.b2sio_write_tiff_strips_batch.argtypes = [C.POINTER(cp), C.c_int, vp, vp, vp, i32, i32, i32, i32, i32, i32, C.c_int,
+                                                    C.POINTER(i32)]
         L.b2sio_write_raw.argtypes = [cp, vp, i32, i32]
         _lib = L
     return _lib
@@ -138,6 +140,28 @@ def write_tiff_batch(paths, planes, compression=("ADOBE_DEFLATE", 1), threads=No
     status = (C.c_int32 * max(n, 1))()
     lib().b2sio_write_tiff_batch(arr, n, planes.ctypes.data, planes.strides[0], planes.shape[1], planes.shape[2],
                                  _CODES[planes.dtype], _level(compression), int(threads or default_threads()), status)
+    return list(status[:n])
+
+
+def is_deflate_level_1(compression) -> bool:
+    """the reference's default output scheme, compression=('ADOBE_DEFLATE', 1) (or 'DEFLATE' / 'ZLIB' at level <= 1): the one the
+    GPU encoder (b2s_deflate_strips) stands in for."""
+    if not isinstance(compression, (tuple, list)) or len(compression) < 2 or compression[1] is None:
+        return False
+    return str(compression[0]).upper() in ("ADOBE_DEFLATE", "DEFLATE", "ZLIB", "8") and int(compression[1]) == 1
+
+
+def write_tiff_strips_batch(paths, data, strip_offsets, strip_sizes, rows_per_strip, shape, dtype, compression_tag=8, threads=None):
+    """TIFF files from strips compressed elsewhere: `data` uint8 array holding the streams, strip_offsets (n, strips) uint64 and
+    strip_sizes (n, strips) uint32 per file; paths[i] None skips slot i.  Returns the per-file status list."""
+    n = len(paths)
+    strip_offsets = np.ascontiguousarray(strip_offsets, dtype=np.uint64).reshape(n, -1)
+    strip_sizes = np.ascontiguousarray(strip_sizes, dtype=np.uint32).reshape(n, -1)
+    arr = (C.c_char_p * max(n, 1))(*[None if p is None else os.fsencode(p) for p in paths])
+    status = (C.c_int32 * max(n, 1))()
+    lib().b2sio_write_tiff_strips_batch(arr, n, data.ctypes.data, strip_offsets.ctypes.data, strip_sizes.ctypes.data,
+                                        strip_sizes.shape[1], int(rows_per_strip), int(shape[0]), int(shape[1]),
+                                        _CODES[np.dtype(dtype)], int(compression_tag), int(threads or default_threads()), status)
     return list(status[:n])
 
 

@@ -66,7 +66,7 @@ EXPORTS = (
     "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_plan_wants_notch_matrix", "b2s_plan_set_notch_matrix", "b2s_plan_set_bleach_levels", "b2s_plan_set_mask_thresholds", "b2s_plan_set_aa_weights", "b2s_run",
     "b2s_host_alloc", "b2s_host_free", "b2s_launch_count", "b2s_timing_enable", "b2s_timing_read",
     "b2s_debug_read", "b2s_debug_math",
-    "b2s_resize_aa", "b2s_isotropic_xy", "b2s_isotropic_z", "b2s_isotropic_convert", "b2s_is_uniform", "b2s_histogram", "b2s_img_mask",
+    "b2s_resize_aa", "b2s_isotropic_xy", "b2s_isotropic_z", "b2s_isotropic_convert", "b2s_is_uniform", "b2s_histogram", "b2s_img_mask", "b2s_deflate_bound", "b2s_deflate_strips",
 )
 
 _lib = None
@@ -113,6 +113,9 @@ def lib():
             L.b2s_resize_aa.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]
             L.b2s_isotropic_z.argtypes = [vp, vp, i32, i64, i32, vp, vp]
             L.b2s_isotropic_convert.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+            L.b2s_deflate_bound.argtypes = [i32, i32, i32, i32, i32]
+            L.b2s_deflate_bound.restype = i64
+            L.b2s_deflate_strips.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i64, vp, vp, C.POINTER(i64), vp]
             L.b2s_img_mask.argtypes = [vp, vp, i32, i32, i32, i32, C.c_double, i32, i32, vp, vp]
             L.b2s_histogram.argtypes = [vp, vp, i32, i32, i64, i32, vp, i32, i32, vp]
             L.b2s_is_uniform.argtypes = [vp, vp, i32, i64, vp, vp]

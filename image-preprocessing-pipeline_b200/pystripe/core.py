@@ -1346,7 +1346,8 @@ def batch_filter(
                       bleach_correction_clip_max, bleach_correction_max_method, False)
     shared = _BatchShared(jobs=jobs, batch=batch, group=group, progress=progress, kw=kw, d_type=d_type, tile_size=tile_size,
                           compression=compression, timeout=timeout, io_threads=read_threads, write_threads=write_threads,
-                          print_input_file_names=print_input_file_names)
+                          print_input_file_names=print_input_file_names,
+                          gpu_deflate=_io.is_deflate_level_1(compression) and os.environ.get("B200STRIPE_GPU_DEFLATE", "1") != "0")
     return_code = 0
     pipelines = [_BatchPipeline(g, shared) for g in gpus]
     try:
@@ -1374,6 +1375,75 @@ def batch_filter(
 def _batch_buffer(device, shape, dtype):
     """page-locked, recycled buffer a batch of tiles is decoded into (the plan reads it over PCIe without staging)."""
     return _native.context(device).pooled_empty(shape, dtype)
+
+
+class _DeflatedPlanes:
+    """result planes of one batch as the GPU left them: the zlib streams of their TIFF strips in one page-locked byte array
+    (b2s_deflate_strips), with the offset and size of every stream."""
+
+    def __init__(self, data, offsets, sizes, rows_per_strip, shape, dtype):
+        self.data, self.offsets, self.sizes, self.rows_per_strip, self.shape, self.dtype = data, offsets, sizes, rows_per_strip, shape, dtype
+
+    def inflate(self, i) -> ndarray:
+        """plane i decoded on the host (the writer's fallback when a file cannot be laid out natively)."""
+        import zlib
+        raw = b"".join(zlib.decompress(self.data[int(o):int(o) + int(n)].tobytes()) for o, n in zip(self.offsets[i], self.sizes[i]))
+        return np.frombuffer(raw, dtype=self.dtype).reshape(self.shape)
+
+
+def _to_device(buf, device):
+    """the decoded (page-locked) batch as a CUDA tensor (hook: the host-logic tests run without a GPU)."""
+    import torch
+    return torch.from_numpy(buf).cuda(device, non_blocking=True)
+
+
+def _to_host(res):
+    return res.cpu().numpy() if _native._is_torch(res) else np.asarray(res)
+
+
+def _deflatable(res) -> bool:
+    if not _native._is_torch(res):
+        return False
+    import torch
+    return res.is_cuda and res.dim() == 3 and res.dtype in (torch.uint8, torch.uint16)
+
+
+def deflate_rows_per_strip(shape, itemsize) -> int:
+    """strips of whole rows, about 64 KB of samples each (one CTA compresses one strip)."""
+    return int(max(1, min(shape[0], 65536 // max(1, shape[1] * itemsize))))
+
+
+def gpu_deflate(planes) -> _DeflatedPlanes:
+    """the deflate step of imsave_tif (core.py:275-334, compression=('ADOBE_DEFLATE', 1)) on the GPU: planes is a CUDA tensor
+    (n, H, W) of uint8 / uint16; every strip becomes one zlib stream, and only the compressed bytes cross PCIe."""
+    import ctypes as C
+    import torch
+    if planes.dim() == 2:
+        planes = planes[None]
+    planes = planes.contiguous()
+    n, rows, cols = (int(v) for v in planes.shape)
+    code = _code_of(planes)
+    np_dtype = {_native.U8: np.uint8, _native.U16: np.uint16, _native.F32: np.float32}[code]
+    rps = deflate_rows_per_strip((rows, cols), np.dtype(np_dtype).itemsize)
+    spp = -(-rows // rps)
+    dev = planes.device.index
+    ctx = _native.context(dev)
+    with torch.cuda.device(dev):
+        cap = int(_native.lib().b2s_deflate_bound(code, rows, cols, n, rps))
+        d_out = torch.empty(cap, dtype=torch.uint8, device=planes.device)
+        d_sizes = torch.empty(n * spp, dtype=torch.int32, device=planes.device)
+        d_offs = torch.empty(n * spp + 1, dtype=torch.int64, device=planes.device)
+        total = C.c_int64(0)
+        ctx.check(_native.lib().b2s_deflate_strips(ctx._h, C.c_void_p(planes.data_ptr()), code, rows, cols, n, rps,
+                                                   C.c_void_p(d_out.data_ptr()), cap, C.c_void_p(d_sizes.data_ptr()),
+                                                   C.c_void_p(d_offs.data_ptr()), C.byref(total),
+                                                   C.c_void_p(torch.cuda.current_stream(planes.device).cuda_stream)))
+        # page-locked block of the bound's size class (equal for every batch of the run: recycled, not re-allocated)
+        host = ctx.pooled_empty((cap,), np.uint8)[:int(total.value)]
+        torch.from_numpy(host).copy_(d_out[:int(total.value)])
+        sizes = d_sizes.cpu().numpy().view(np.uint32).reshape(n, spp)
+        offs = d_offs[:-1].cpu().numpy().view(np.uint64).reshape(n, spp)
+    return _DeflatedPlanes(host, offs, sizes, rps, (rows, cols), np.dtype(np_dtype))
 
 
 class _BatchShared:
@@ -1566,8 +1636,14 @@ class _BatchPipeline:
             jobs, buf, valid = item
             try:
                 with use_device(self.device):
-                    res = process_img(buf, tile_size=buf.shape[1:], d_type=sh.d_type if sh.d_type is not None else buf.dtype,
-                                      _max_batch=sh.batch, **sh.kw)
+                    if sh.gpu_deflate and buf.dtype in (np.uint8, np.uint16):
+                        # device-resident batch: the result is deflated where it was computed, D2H carries compressed bytes
+                        res = process_img(_to_device(buf, self.device), tile_size=buf.shape[1:],
+                                          d_type=sh.d_type if sh.d_type is not None else buf.dtype, _max_batch=sh.batch, **sh.kw)
+                        res = gpu_deflate(res) if _deflatable(res) else _to_host(res)
+                    else:
+                        res = process_img(buf, tile_size=buf.shape[1:], d_type=sh.d_type if sh.d_type is not None else buf.dtype,
+                                          _max_batch=sh.batch, **sh.kw)
             except Exception as inst:                                    # every per-batch failure is reported, none is fatal
                 for job, ok in zip(jobs, valid):
                     if ok:
@@ -1601,12 +1677,20 @@ class _BatchPipeline:
             if item is None:
                 break
             jobs, res, valid = item
-            res = np.asarray(res)
+            if not isinstance(res, _DeflatedPlanes):
+                res = np.asarray(res)
             try:
                 for d in {j[1].parent for j in jobs}:
                     d.mkdir(parents=True, exist_ok=True)
                 todo = [i for i, ok in enumerate(valid) if ok]
-                if todo and res.ndim == 3 and _io.can_write(res[0], sh.compression) and res.flags.c_contiguous:
+                if todo and isinstance(res, _DeflatedPlanes):
+                    status = _io.write_tiff_strips_batch([jobs[i][1] if valid[i] else None for i in range(len(jobs))], res.data,
+                                                         res.offsets[:len(jobs)], res.sizes[:len(jobs)], res.rows_per_strip,
+                                                         res.shape, res.dtype, 8, threads=sh.write_threads)
+                    for i in todo:
+                        if status[i] and imsave_tif(jobs[i][1], res.inflate(i), compression=sh.compression):
+                            sh.stop.set()
+                elif todo and res.ndim == 3 and _io.can_write(res[0], sh.compression) and res.flags.c_contiguous:
                     if len(todo) == len(jobs):
                         status = _io.write_tiff_batch([j[1] for j in jobs], res, sh.compression, threads=sh.write_threads)
                     else:

@@ -251,6 +251,16 @@ int b2s_isotropic_z(b2s_context *ctx, const float *d_in, int n_in, int64_t plane
  * d_out: uint16 (mode 1) or uint8. */
 int b2s_isotropic_convert(b2s_context *ctx, const float *d_in, int64_t n, int mode, int shift, void *d_out, void *stream);
 
+/* replaces: the deflate step of imsave_tif — tifffile.imwrite(..., compression=('ADOBE_DEFLATE', 1)), pystripe/core.py:275-334
+ * (batch_filter's default output, core.py:1817) — on the device, so that D2H and the file write carry compressed bytes.
+ * Every strip of rows_per_strip rows of every plane becomes one zlib stream (RFC 1950) holding one literal-only dynamic-Huffman
+ * deflate block (RFC 1951); the streams are packed back to back into d_out in (plane, strip) order.  d_planes, d_out, d_sizes
+ * (n_planes x strips uint32: bytes per stream) and d_offsets (n_planes x strips + 1 uint64: start of each stream, total last)
+ * are DEVICE pointers; d_out must be 4-byte aligned with b2s_deflate_bound() bytes.  Synchronises the stream and returns the
+ * packed size in *total_bytes.  b2sio_write_tiff_strips_batch (include/b2sio.h) lays such streams out as TIFF files. */
+int64_t b2s_deflate_bound(int dtype, int rows, int cols, int n_planes, int rows_per_strip);
+int b2s_deflate_strips(b2s_context *ctx, const void *d_planes, int dtype, int rows, int cols, int n_planes, int rows_per_strip,
+                       void *d_out, int64_t out_capacity, uint32_t *d_sizes, uint64_t *d_offsets, int64_t *total_bytes, void *stream);
 /* replaces: get_img_mask(img, threshold, close_steps, open_steps, flood_fill_flag=4) (pystripe/core.py:475-489) on n_planes
  * independent planes: img > threshold, cv2.morphologyEx MORPH_CLOSE with ones(close, close), MORPH_OPEN with ones(open, open),
  * background that no corner pixel reaches through 4-connected background added back (the four cv2.floodFill calls).

@@ -76,6 +76,14 @@ int b2sio_write_tiff(const char *path, const void *src, int32_t height, int32_t 
 int b2sio_write_tiff_batch(const char *const *paths, int n_files, const void *src, size_t plane_stride_bytes,
                            int32_t height, int32_t width, int32_t dtype, int deflate_level, int n_threads, int32_t *status);
 
+/* replaces: the same per-file writes when the strips were already deflated on the GPU (b2s_deflate_strips, include/b200stripe.h):
+ * file i consists of strips_per_file streams, stream s at (const char *)data + strip_offsets[i * strips_per_file + s] with
+ * strip_sizes[...] bytes; `compression` is the TIFF tag 259 value of the streams (8 = Adobe deflate).  paths[i] == NULL skips
+ * slot i.  Returns the number of files that failed; status[i] per file. */
+int b2sio_write_tiff_strips_batch(const char *const *paths, int n_files, const void *data, const uint64_t *strip_offsets,
+                                  const uint32_t *strip_sizes, int32_t strips_per_file, int32_t rows_per_strip, int32_t height,
+                                  int32_t width, int32_t dtype, int32_t compression, int n_threads, int32_t *status);
+
 /* replaces: raw_imsave (raw.py:44-68): 8-byte header (width, height as native uint32) + uint16 samples */
 int b2sio_write_raw(const char *path, const void *src, int32_t height, int32_t width);
 

@@ -15,6 +15,7 @@ def host_only(monkeypatch):
     monkeypatch.setattr(core, "_batch_buffer", lambda device, shape, dtype: np.empty(shape, dtype))
     monkeypatch.setattr(core, "_visible_gpus", lambda: [0])
     monkeypatch.setattr(core, "use_device", lambda d: __import__("contextlib").nullcontext())
+    monkeypatch.setattr(core, "_to_device", lambda buf, device: buf)       # the device-resident leg of the default compression
     for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
 
@@ -44,6 +45,42 @@ def test_batches_are_decoded_processed_and_written(tmp_path, host_only, monkeypa
     assert sorted(s[0] for s in seen) == [3, 4, 4]                     # 11 planes in batches of 4
     for name, img in planes.items():
         assert np.array_equal(core.imread_tif_raw_png(tmp_path / "out" / name), img // 2)
+
+
+def test_gpu_deflated_results_are_laid_out_as_tiff_files(tmp_path, host_only, monkeypatch):
+    """the default output scheme ('ADOBE_DEFLATE', 1): the compute stage hands the writer zlib streams per strip
+    (core.gpu_deflate on the device; here the same layout produced with zlib) and the native writer lays them out as TIFF."""
+    import zlib
+    planes = _write_stack(tmp_path / "in", 7, shape=(37, 40))
+    monkeypatch.setattr(core, "process_img", lambda stack, **kw: (stack + 1).astype(np.uint16))
+    monkeypatch.setattr(core, "_deflatable", lambda res: True)
+    made = []
+
+    def host_deflate(res):
+        n, rows, cols = res.shape
+        rps = 8                                                           # 5 strips, the last one short
+        streams = [[zlib.compress(res[i, r:r + rps].tobytes(), 1) for r in range(0, rows, rps)] for i in range(n)]
+        sizes = np.array([[len(s) for s in row] for row in streams], np.uint32)
+        offsets = (np.cumsum(sizes.ravel(), dtype=np.uint64) - sizes.ravel()).reshape(sizes.shape)
+        made.append(n)
+        return core._DeflatedPlanes(np.frombuffer(b"".join(b"".join(row) for row in streams), np.uint8), offsets, sizes, rps,
+                                    (rows, cols), np.dtype(np.uint16))
+    monkeypatch.setattr(core, "gpu_deflate", host_deflate)
+    assert core.batch_filter(tmp_path / "in", tmp_path / "out", workers=4, threads_per_gpu=4, sigma=(8, 8), wavelet="db2") == 0
+    assert sum(made) == 7
+    from PIL import Image
+    for name, img in planes.items():
+        assert _io.probe(tmp_path / "out" / name)[2].compression == 8
+        assert np.array_equal(_io.read(tmp_path / "out" / name), img + 1)
+        with Image.open(tmp_path / "out" / name) as im:
+            assert np.array_equal(np.array(im), img + 1)
+    d = host_deflate(np.stack([planes["img_0000.tif"], planes["img_0001.tif"]]))
+    assert np.array_equal(d.inflate(1), planes["img_0001.tif"])
+    # another compression level keeps the host encoder
+    made.clear()
+    assert core.batch_filter(tmp_path / "in", tmp_path / "out6", workers=4, threads_per_gpu=4, sigma=(8, 8), wavelet="db2",
+                             compression=("ADOBE_DEFLATE", 6)) == 0
+    assert not made and np.array_equal(_io.read(tmp_path / "out6" / "img_0003.tif"), planes["img_0003.tif"] + 1)
 
 
 def test_a_failing_batch_is_reported_and_the_rest_still_runs(tmp_path, host_only, monkeypatch):
