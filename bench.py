@@ -73,7 +73,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch-filter", action="store_true", help="skip the file-based e2e leg")
     ap.add_argument("--cpu-planes", type=int, default=0, help="planes in the CPU sample (default: 2 per core; 1 per core for configs 4, 5)")
-    ap.add_argument("--files", type=int, default=0, help="files in the batch_filter leg (default 384)")
+    ap.add_argument("--files", type=int, default=0, help="files in the batch_filter leg (default 1024 / ranks)")
     ap.add_argument("--fast", action="store_true", help="allow FMA contraction (exact=0); not the parity configuration")
     a = ap.parse_args()
     if a.planes <= 0:
@@ -368,7 +368,7 @@ def run_b200(a):
 def batch_filter_leg(a, cfg, core, _io, base, flat, local, world, barrier, max_over_ranks):
     """core.batch_filter over `n` uncompressed TIFF tiles on tmpfs -> TIFF tiles on tmpfs.  Every rank owns its own
     folder and GPU (B200STRIPE_DEVICES), so N ranks run N independent batch_filter calls at once."""
-    n = a.files or max(96, 384 // world)       # tmpfs holds the inputs and the outputs of every rank
+    n = a.files or max(128, 1024 // world)     # tmpfs holds the inputs and the outputs of every rank
     tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") else None
     work = Path(tempfile.mkdtemp(prefix=f"b2s_bench_r{local}_", dir=tmp_root))
     saved = {k: os.environ.pop(k, None) for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK")}   # one process = one independent farm
@@ -388,7 +388,6 @@ def batch_filter_leg(a, cfg, core, _io, base, flat, local, world, barrier, max_o
             flist = [src / f"img_{z:05d}.tif" for z in range(files)]
 
             def once():
-                shutil.rmtree(dst, ignore_errors=True)
                 with open(os.devnull, "w") as null:
                     old = sys.stdout
                     sys.stdout = null
@@ -398,7 +397,9 @@ def batch_filter_leg(a, cfg, core, _io, base, flat, local, world, barrier, max_o
                     finally:
                         sys.stdout = old
                 assert rc == 0, f"batch_filter returned {rc}"
+            shutil.rmtree(dst, ignore_errors=True)
             once()                                               # warm-up: plan, pinned pools, the device encoder's buffers
+            shutil.rmtree(dst, ignore_errors=True)               # (deleting the previous outputs is not part of the job)
             barrier()
             t0 = time.perf_counter()
             once()

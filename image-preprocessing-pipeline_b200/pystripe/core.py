@@ -1337,6 +1337,9 @@ def batch_filter(
     per_pipe = max(2, workers // len(gpus))
     read_threads = max(1, per_pipe // 3)
     write_threads = per_pipe          # mild over-subscription: the reader blocks on its bounded queue most of the time
+    gpu_deflate = _io.is_deflate_level_1(compression) and os.environ.get("B200STRIPE_GPU_DEFLATE", "1") != "0"
+    if gpu_deflate:                   # the files receive streams compressed on the GPU: decoding is the host's main job
+        read_threads, write_threads = per_pipe, max(2, per_pipe // 2)
     print(f"{PrintColors.GREEN}{date_time_now()}: {PrintColors.ENDC}"
           f"using {workers} decode/encode threads and {len(gpus)} GPU(s). {num_images} images need to be processed.",
           flush=True)
@@ -1347,7 +1350,7 @@ def batch_filter(
     shared = _BatchShared(jobs=jobs, batch=batch, group=group, progress=progress, kw=kw, d_type=d_type, tile_size=tile_size,
                           compression=compression, timeout=timeout, io_threads=read_threads, write_threads=write_threads,
                           print_input_file_names=print_input_file_names,
-                          gpu_deflate=_io.is_deflate_level_1(compression) and os.environ.get("B200STRIPE_GPU_DEFLATE", "1") != "0")
+                          gpu_deflate=gpu_deflate)
     return_code = 0
     pipelines = [_BatchPipeline(g, shared) for g in gpus]
     try:
@@ -1397,6 +1400,16 @@ def _to_device(buf, device):
     return torch.from_numpy(buf).cuda(device, non_blocking=True)
 
 
+def _own_stream(device):
+    """context: a CUDA stream of this thread's own on `device` (hook, like _to_device)."""
+    import contextlib
+    import torch
+    stack = contextlib.ExitStack()
+    stack.enter_context(torch.cuda.device(device))
+    stack.enter_context(torch.cuda.stream(torch.cuda.Stream(device)))
+    return stack
+
+
 def _to_host(res):
     return res.cpu().numpy() if _native._is_torch(res) else np.asarray(res)
 
@@ -1438,8 +1451,10 @@ def gpu_deflate(planes) -> _DeflatedPlanes:
                                                    C.c_void_p(d_out.data_ptr()), cap, C.c_void_p(d_sizes.data_ptr()),
                                                    C.c_void_p(d_offs.data_ptr()), C.byref(total),
                                                    C.c_void_p(torch.cuda.current_stream(planes.device).cuda_stream)))
-        # page-locked block of the bound's size class (equal for every batch of the run: recycled, not re-allocated)
-        host = ctx.pooled_empty((cap,), np.uint8)[:int(total.value)]
+        # page-locked block in one of eight size classes below the bound: batches of a run land in the same class or two, so
+        # the blocks are recycled instead of re-allocated (cudaMallocHost costs ~0.4 s per GB)
+        step = max(1 << 21, -(-cap // 8))
+        host = ctx.pooled_empty((-(-int(total.value) // step) * step,), np.uint8)[:int(total.value)]
         torch.from_numpy(host).copy_(d_out[:int(total.value)])
         sizes = d_sizes.cpu().numpy().view(np.uint32).reshape(n, spp)
         offs = d_offs[:-1].cpu().numpy().view(np.uint64).reshape(n, spp)
@@ -1491,8 +1506,12 @@ class _BatchPipeline:
         from queue import Queue as _Q
         self.device, self.sh = device, shared
         self.q_ready, self.q_write = _Q(maxsize=2), _Q(maxsize=2)
+        # the device-resident leg (GPU deflate) runs upload -> kernels -> deflate -> download back to back per group: two
+        # compute threads on their own CUDA streams overlap one group's copies with the other's kernels
+        self.n_compute = max(1, int(os.environ.get("B200STRIPE_COMPUTE_THREADS", "2"))) if getattr(shared, "gpu_deflate", False) else 1
+        self._compute_left = self.n_compute
         self.threads = [threading.Thread(target=self._guard, args=(f,), daemon=True)
-                        for f in (self._reader, self._compute, self._writer)]
+                        for f in [self._reader] + [self._compute] * self.n_compute + [self._writer]]
         self.pool = ThreadPoolExecutor(max_workers=max(2, shared.write_threads))
 
     def start(self):
@@ -1625,10 +1644,18 @@ class _BatchPipeline:
 
     # ---- stage 2: the GPU
     def _compute(self):
+        if self.n_compute > 1:
+            with _own_stream(self.device):
+                return self._compute_loop()
+        return self._compute_loop()
+
+    def _compute_loop(self):
         sh = self.sh
         while True:
             item = self.q_ready.get()
             if item is None or sh.stop.is_set():
+                if item is None:
+                    self._put(self.q_ready, None)                        # the sibling compute threads stop too
                 break
             if len(item) == 1:
                 self._slow_file(item[0])
@@ -1653,7 +1680,11 @@ class _BatchPipeline:
             del buf
             if not self._put(self.q_write, (jobs, res, valid)):
                 return
-        self._put(self.q_write, None)
+        with sh.lock:
+            self._compute_left -= 1
+            last = self._compute_left == 0
+        if last:
+            self._put(self.q_write, None)
 
     def _slow_file(self, job):
         sh = self.sh
