@@ -546,27 +546,12 @@ struct FinalArgs {
     int out_rows, out_cols;
 };
 
-__global__ void __launch_bounds__(256) k_lightsheet_final(const FinalArgs a)
+// img - min(img, min(ls, bg * weight)) (lightsheet_correct.py:89-100) and the final conversion of the value (core.py:1361-1369,
+// 397-423; dark was applied before the lightsheet step)
+__device__ __forceinline__ void final_store(const FinalArgs &a, size_t p, size_t oidx, unsigned ls, unsigned bg, bool zero_plane)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
-    if (j >= a.out_cols) return;
-    const size_t plane = blockIdx.z;
-    const size_t oidx = plane * (size_t)a.out_rows * a.out_cols + (size_t)i * a.out_cols + j;
-    const bool zero_plane = a.uniform_mm && a.uniform_mm[2 * plane] == ~a.uniform_mm[2 * plane + 1];
     double v = 0.0;
     if (!zero_plane) {
-        const int R = a.rows, C = a.cols;
-        int y, x;
-        switch (a.rot) {
-        case 1: y = j; x = C - 1 - i; break;
-        case 2: y = R - 1 - i; x = C - 1 - j; break;
-        case 3: y = R - 1 - j; x = i; break;
-        default: y = i; x = j; break;
-        }
-        if (a.flip) y = R - 1 - y;
-        const size_t p = plane * (size_t)R * C + (size_t)y * C + x;
-        const unsigned ls = zoom_u16(a.ls + plane * a.ls_size, a.ls_cols, a.ls_y, a.ls_x, y, x);
-        const unsigned bg = zoom_u16(a.bg + plane * a.bg_size, a.bg_cols, a.bg_y, a.bg_x, y, x);
         if (a.dtype != B2S_F32) {
             const unsigned px = a.dtype == B2S_U16 ? reinterpret_cast<const unsigned short *>(a.img)[p]
                                                    : reinterpret_cast<const unsigned char *>(a.img)[p];
@@ -586,7 +571,6 @@ __global__ void __launch_bounds__(256) k_lightsheet_final(const FinalArgs a)
             v = (double)__fsub_rn(px, (float)m);                     // float32 array -= float32
         }
     }
-    // final conversion (core.py:1361-1369, 397-423); dark was applied before the lightsheet step
     if (a.final_mode == 3) { reinterpret_cast<float *>(a.out)[oidx] = (float)v; return; }
     unsigned u;
     if (a.final_mode == 2) {
@@ -602,6 +586,103 @@ __global__ void __launch_bounds__(256) k_lightsheet_final(const FinalArgs a)
     }
     if (a.out_dtype == B2S_U8) reinterpret_cast<unsigned char *>(a.out)[oidx] = (unsigned char)u;
     else reinterpret_cast<unsigned short *>(a.out)[oidx] = (unsigned short)u;
+}
+
+// general form: one thread per output pixel, both zooms evaluated from the grids (any rotation)
+__global__ void __launch_bounds__(256) k_lightsheet_final(const FinalArgs a)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= a.out_cols) return;
+    const size_t plane = blockIdx.z;
+    const size_t oidx = plane * (size_t)a.out_rows * a.out_cols + (size_t)i * a.out_cols + j;
+    const bool zero_plane = a.uniform_mm && a.uniform_mm[2 * plane] == ~a.uniform_mm[2 * plane + 1];
+    const int R = a.rows, C = a.cols;
+    int y, x;
+    switch (a.rot) {
+    case 1: y = j; x = C - 1 - i; break;
+    case 2: y = R - 1 - i; x = C - 1 - j; break;
+    case 3: y = R - 1 - j; x = i; break;
+    default: y = i; x = j; break;
+    }
+    if (a.flip) y = R - 1 - y;
+    const size_t p = plane * (size_t)R * C + (size_t)y * C + x;
+    unsigned ls = 0, bg = 0;
+    if (!zero_plane) {
+        ls = zoom_u16(a.ls + plane * a.ls_size, a.ls_cols, a.ls_y, a.ls_x, y, x);
+        bg = zoom_u16(a.bg + plane * a.bg_size, a.bg_cols, a.bg_y, a.bg_x, y, x);
+    }
+    final_store(a, p, oidx, ls, bg, zero_plane);
+}
+
+// rotation 0 / 180: an output row is an image row, so the row part of both zooms — (g * wy) for the two grid rows — is shared
+// by the whole row: kFR rows per CTA keep those products in shared memory, a thread loads its column tables once and then
+// only multiplies by wx and adds, in scipy's order (((g00 wy0) wx0 + (g01 wy0) wx1) + (g10 wy1) wx0) + (g11 wy1) wx1.
+constexpr int kFR = 8, kFGridMax = 64;
+__global__ void __launch_bounds__(256) k_lightsheet_final_rows(const FinalArgs a)
+{
+    __shared__ double sA[2][kFR][kFGridMax], sB[2][kFR][kFGridMax];
+    __shared__ int s_y[kFR];
+    __shared__ unsigned char s_zero[2][kFR];
+    const size_t plane = blockIdx.z;
+    const int R = a.rows, C = a.cols;
+    const int i0 = blockIdx.y * kFR;
+    const bool zero_plane = a.uniform_mm && a.uniform_mm[2 * plane] == ~a.uniform_mm[2 * plane + 1];
+    if (threadIdx.x < kFR) {
+        const int i = min(i0 + (int)threadIdx.x, a.out_rows - 1);
+        int y = a.rot == 2 ? R - 1 - i : i;
+        if (a.flip) y = R - 1 - y;
+        s_y[threadIdx.x] = y;
+        s_zero[0][threadIdx.x] = a.ls_y.zero[y];
+        s_zero[1][threadIdx.x] = a.bg_y.zero[y];
+    }
+    __syncthreads();
+    for (int gsel = 0; gsel < 2; ++gsel) {
+        const ZoomAxis &zy = gsel ? a.bg_y : a.ls_y;
+        const int gcols = gsel ? a.bg_cols : a.ls_cols;
+        const unsigned short *g = gsel ? a.bg + plane * a.bg_size : a.ls + plane * a.ls_size;
+        for (int idx = threadIdx.x; idx < kFR * gcols; idx += 256) {
+            const int r = idx / gcols, c = idx - r * gcols;
+            const int y = s_y[r];
+            sA[gsel][r][c] = (double)g[(size_t)zy.i0[y] * gcols + c] * zy.w0[y];
+            sB[gsel][r][c] = (double)g[(size_t)zy.i1[y] * gcols + c] * zy.w1[y];
+        }
+    }
+    __syncthreads();
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= a.out_cols) return;
+    const int x = a.rot == 2 ? C - 1 - j : j;
+    int x0[2], x1[2];
+    double w0[2], w1[2];
+    bool zx[2];
+#pragma unroll
+    for (int gsel = 0; gsel < 2; ++gsel) {
+        const ZoomAxis &z = gsel ? a.bg_x : a.ls_x;
+        zx[gsel] = z.zero[x];
+        x0[gsel] = z.i0[x]; x1[gsel] = z.i1[x];
+        w0[gsel] = z.w0[x]; w1[gsel] = z.w1[x];
+    }
+#pragma unroll
+    for (int r = 0; r < kFR; ++r) {
+        const int i = i0 + r;
+        if (i >= a.out_rows) break;
+        unsigned val[2] = {0u, 0u};
+        if (!zero_plane) {
+#pragma unroll
+            for (int gsel = 0; gsel < 2; ++gsel) {
+                if (zx[gsel] || s_zero[gsel][r]) continue;
+                double t = sA[gsel][r][x0[gsel]] * w0[gsel];
+                t = t + sA[gsel][r][x1[gsel]] * w1[gsel];
+                t = t + sB[gsel][r][x0[gsel]] * w0[gsel];
+                t = t + sB[gsel][r][x1[gsel]] * w1[gsel];
+                t = t > 0.0 ? t + 0.5 : 0.0;
+                if (t > 65535.0) t = 65535.0;
+                val[gsel] = (unsigned)t;
+            }
+        }
+        const size_t p = plane * (size_t)R * C + (size_t)s_y[r] * C + x;
+        const size_t oidx = plane * (size_t)a.out_rows * a.out_cols + (size_t)i * a.out_cols + j;
+        final_store(a, p, oidx, val[0], val[1], zero_plane);
+    }
 }
 
 AxisGeom axis_geom(int size, int selem, int spacing, int step)
@@ -742,5 +823,8 @@ void b2s_launch_lightsheet(const B2sLightsheet *L, const void *mid, unsigned sho
     f.weight = L->weight; f.weight_is_int = L->weight_is_int;
     f.final_mode = e.final_mode; f.shift = e.shift; f.out_dtype = e.out_dtype; f.flip = e.flip; f.rot = e.rot;
     f.uniform_mm = e.uniform_mm; f.out = e.out; f.out_rows = e.out_rows; f.out_cols = e.out_cols;
-    k_lightsheet_final<<<dim3((e.out_cols + 255) / 256, e.out_rows, n_planes), 256, 0, s>>>(f);
+    if ((e.rot == 0 || e.rot == 2) && f.ls_cols <= kFGridMax && f.bg_cols <= kFGridMax)
+        k_lightsheet_final_rows<<<dim3((e.out_cols + 255) / 256, (e.out_rows + kFR - 1) / kFR, n_planes), 256, 0, s>>>(f);
+    else
+        k_lightsheet_final<<<dim3((e.out_cols + 255) / 256, e.out_rows, n_planes), 256, 0, s>>>(f);
 }
