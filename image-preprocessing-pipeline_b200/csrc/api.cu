@@ -379,6 +379,8 @@ struct b2s_plan {
     int n_row_groups = 0;
     int *d_row_src = nullptr, *d_row_start = nullptr, *d_row_targets = nullptr, *d_colmap = nullptr;
     float *d_lut = nullptr;
+    float *d_epi_thr = nullptr;     // fast epilogue: thresholds of the plan's log value -> integer map (pointwise.cu)
+    int epi_kmax = 0;
     double taps64[4][B2S_MAX_TAPS] = {};            // f64 path: dec_lo, dec_hi, rec_lo, rec_hi in double
     double *d_notch_mat[2][B2S_MAX_LEVELS + 1][2] = {};   // f64 path: n x n response matrices (b2s_plan_set_notch_matrix)
     size_t f64_plane_doubles = 0;
@@ -530,6 +532,21 @@ int build_tables(b2s_plan *pl)
             if (rc) return rc;
             b2s_launch_log1p_lut(pl->d_lut, 65536, 0);
             CU(ctx, cudaDeviceSynchronize());
+        }
+    }
+    {
+        static const bool no_tab = getenv("B2S_EPILOGUE_TABLE") && atoi(getenv("B2S_EPILOGUE_TABLE")) == 0;
+        const double dark = p.process_img ? p.dark : 0.0;
+        const bool f32_exact = !(dark > 0.0 && g.int_path && dark != std::floor(dark)) && dark < 16777216.0;
+        const bool rotated = p.process_img && p.rotate != 0;
+        if (g.log_image && p.log1p && !g.f64 && f32_exact && !rotated && g.final_mode != 3 && !no_tab && !pl->dry) {
+            int rc = dev_alloc(pl, (void **)&pl->d_epi_thr, sizeof(float) * 65536 + sizeof(int));
+            if (rc) return rc;
+            B2sEpiFn f;
+            f.int_path = g.int_path; f.darkf = (float)dark; f.hi_w = g.work_dtype == B2S_U8 ? 255.f : 65535.f;
+            int *d_kmax = reinterpret_cast<int *>(pl->d_epi_thr + 65536);
+            b2s_launch_epi_thresholds(pl->d_epi_thr, f, d_kmax, 0);
+            CU(ctx, cudaMemcpy(&pl->epi_kmax, d_kmax, sizeof(int), cudaMemcpyDeviceToHost));
         }
     }
     // per-level FFT plans + notch tables (np_notch, core.py:637-667, numpy float32 branch); the float64 path applies the
@@ -878,6 +895,8 @@ int enqueue_batch(b2s_plan *pl, b2s_plan::Slot &s, const void *d_in, void *d_out
         e.out = d_out;
         e.out_rows = g.out_rows;
         e.out_cols = g.out_cols;
+        e.epi_thr = pl->d_epi_thr;
+        e.epi_kmax = pl->epi_kmax;
         // the image as the reference holds it after the dark subtraction (same dtype), unrotated
         B2sEpilogueArgs m = e;
         const bool mid_int = g.work_dtype != B2S_F32;
@@ -1809,6 +1828,35 @@ int b2s_debug_math(b2s_context *ctx, int which, const float *in, float *out, int
     CU(ctx, cudaMemcpy(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost));
     cudaFree(d_in);
     cudaFree(d_out);
+    return B2S_OK;
+}
+
+int b2s_debug_expm1_table_check(b2s_context *ctx, int int_path, double dark, int work_dtype, uint64_t first, uint64_t count,
+                                uint64_t *mismatches)
+{
+    if (!ctx || !mismatches || first + count > (1ull << 32)) return B2S_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    float *thr = nullptr;
+    unsigned long long *d_bad = nullptr;
+    CU(ctx, cudaMalloc(&thr, sizeof(float) * 65536 + sizeof(int)));
+    CU(ctx, cudaMalloc(&d_bad, sizeof(unsigned long long)));
+    CU(ctx, cudaMemset(d_bad, 0, sizeof(unsigned long long)));
+    B2sEpiFn f;
+    f.int_path = int_path; f.darkf = (float)dark; f.hi_w = work_dtype == B2S_U8 ? 255.f : 65535.f;
+    int *d_kmax = reinterpret_cast<int *>(thr + 65536);
+    b2s_launch_epi_thresholds(thr, f, d_kmax, 0);
+    int kmax = 0;
+    cudaError_t e = cudaMemcpy(&kmax, d_kmax, sizeof kmax, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) {
+        b2s_launch_epi_table_check(thr, f, kmax, first, count, d_bad, 0);
+        ctx->launches += 3;
+        unsigned long long bad = 0;
+        e = cudaMemcpy(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost);
+        *mismatches = bad;
+    }
+    cudaFree(thr);
+    cudaFree(d_bad);
+    CU(ctx, e);
     return B2S_OK;
 }
 

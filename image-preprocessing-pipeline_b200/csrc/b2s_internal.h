@@ -64,8 +64,18 @@ struct B2sEpilogueArgs {
     const unsigned *uniform_mm; // optional per-plane {min key, ~max key}: equal => all pixels equal => write zeros (core.py:1232)
     void *out;
     int out_rows, out_cols;
+    const float *epi_thr;  // optional: thresholds of the plan's log value -> integer map (b2s_launch_epi_thresholds); fast epilogue only
+    int epi_kmax;          // the largest integer that map produces
 };
 void b2s_launch_epilogue(const B2sEpilogueArgs &a, int n_planes, cudaStream_t s);
+// the fast epilogue's map from a log value to an integer in [0, 65535]: expm1 -> [rint, clip to the work dtype] -> dark -> clip
+struct B2sEpiFn { int int_path; float darkf; float hi_w; };
+// thr[k] (65 536 floats) = the smallest float v that map sends to k or above (thr[0] = -inf, NaN above the largest value,
+// which lands in *d_kmax): the epilogue finds the integer from an approximate exponential and two table entries
+void b2s_launch_epi_thresholds(float *thr, const B2sEpiFn &f, int *d_kmax, cudaStream_t s);
+// exhaustive check over float bit patterns [first, first + count): table lookup == direct evaluation; mismatches are counted
+void b2s_launch_epi_table_check(const float *thr, const B2sEpiFn &f, int kmax, unsigned long long first, unsigned long long count,
+                                unsigned long long *mismatches, cudaStream_t s);
 
 // new_size (skimage.transform.resize, order 1, core.py:1356-1359) fused with the final conversion / orientation
 struct B2sResizeArgs {

@@ -259,6 +259,55 @@ __global__ void __launch_bounds__(256) k_epilogue_rows(B2sEpilogueArgs a)
 }
 
 // The common destripe epilogue (log domain, every value exact in float32, no rotation) with its branches resolved at
+// ---- expm1 -> [rint, clip] -> dark -> clip -> integer, through thresholds ------------------------------------------------
+// Whatever the flags, the fast epilogue turns a log value v into an integer G(v) in [0, 65535] (core.py:1150-1158, 1324-1330,
+// 397-423): G = trunc(clip(darksub(INT ? clip(rint(expm1f(v))) : expm1f(v)))).  Every step is monotone and so is the mirrored
+// expm1f (checked exhaustively: b2s_debug_expm1_table_check over all 2^32 bit patterns, tests/test_gpu_parity.py), so G(v) is
+// the number of thresholds thr[1..kmax] at or below v.  An approximate exponential lands within one of it; two table entries
+// decide.  The table belongs to the plan (it depends on int_path, the work dtype's range and dark).
+__device__ __forceinline__ float epi_direct(float v, const B2sEpiFn f)
+{
+    float vf = b2s_expm1f_dev(v);
+    if (f.int_path) vf = fminf(fmaxf(rintf(vf), 0.f), f.hi_w);
+    if (f.darkf > 0.f) vf = vf > f.darkf ? __fsub_rn(vf, f.darkf) : 0.f;
+    const float c = vf < 0.f ? 0.f : (vf > 65535.f ? 65535.f : vf);
+    return (float)(unsigned)c;                                          // NaN -> 0
+}
+__device__ __forceinline__ float epi_table(float v, const float *__restrict__ thr, float darkf, int kmax)
+{
+    float ap = __expf(v) - 1.0f;
+    ap = ap > darkf ? ap - darkf : 0.f;                                 // darkf = 0: max(ap, 0); NaN -> 0
+    int k = min(__float2int_rn(fminf(ap, 65535.f)), kmax);
+    const float dn = __ldg(thr + k), up = __ldg(thr + min(k + 1, 65535));   // thr[0] = -inf, thr[k > kmax] = NaN
+    k += (k < kmax && v >= up) ? 1 : 0;
+    k -= (v < dn) ? 1 : 0;
+    return (float)k;
+}
+__global__ void k_epi_thresholds(float *thr, const B2sEpiFn f)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 65536) return;
+    if (k == 0) { thr[0] = __int_as_float(0xff800000); return; }
+    unsigned lo = 0u, hi = 0x7f800000u;                                 // G(+0) = 0 < k; G(+inf) = the largest value there is
+    if (epi_direct(__uint_as_float(hi), f) < (float)k) { thr[k] = __int_as_float(0x7fc00000); return; }   // never reached
+    while (hi - lo > 1) {
+        const unsigned mid = lo + ((hi - lo) >> 1);
+        if (epi_direct(__uint_as_float(mid), f) >= (float)k) hi = mid; else lo = mid;
+    }
+    thr[k] = __uint_as_float(hi);
+}
+__global__ void k_epi_table_check(const float *thr, const B2sEpiFn f, int kmax, unsigned long long first, unsigned long long count,
+                                  unsigned long long *mismatches)
+{
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float v = __uint_as_float((unsigned)(first + i));
+        if (epi_table(v, thr, f.darkf, kmax) != epi_direct(v, f)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+__global__ void k_epi_kmax(const B2sEpiFn f, int *kmax) { *kmax = (int)epi_direct(__int_as_float(0x7f800000), f); }
+
 // compile time and the branch-free expm1 hot path: crop -> expm1 -> [rint, clip] -> dark -> final conversion, 4 pixels per
 // thread.  Same arithmetic as k_epilogue_rows, which keeps every other combination.
 template <bool INT, bool TO8, bool U8>
@@ -287,18 +336,24 @@ __global__ void __launch_bounds__(256) k_epilogue_fast(const B2sEpilogueArgs a)
         const float darkf = (float)a.dark;
         const int shift = a.shift;
         float e[4];
-        bool bad = false;
+        const bool tab = a.epi_thr != nullptr;
+        if (tab) {   // e = G(v): rint / clip / dark / clip already applied
 #pragma unroll
-        for (int k = 0; k < 4; ++k) e[k] = b2s_expm1f_hot(v[k], bad);
-        if (bad) {   // (unrolled: dynamic indexing would push e[] / v[] into local memory)
+            for (int k = 0; k < 4; ++k) e[k] = epi_table(v[k], a.epi_thr, darkf, a.epi_kmax);
+        } else {
+            bool bad = false;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) e[k] = b2s_expm1f_dev(v[k]);
+            for (int k = 0; k < 4; ++k) e[k] = b2s_expm1f_hot(v[k], bad);
+            if (bad) {   // (unrolled: dynamic indexing would push e[] / v[] into local memory)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) e[k] = b2s_expm1f_dev(v[k]);
+            }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float vf = e[k];
-            if (INT) vf = fminf(fmaxf(rintf(vf), 0.f), hi_w);   // core.py:1153-1158
-            if (darkf > 0.f) vf = vf > darkf ? __fsub_rn(vf, darkf) : 0.f;
+            if (INT && !tab) vf = fminf(fmaxf(rintf(vf), 0.f), hi_w);   // core.py:1153-1158
+            if (darkf > 0.f && !tab) vf = vf > darkf ? __fsub_rn(vf, darkf) : 0.f;
             if (TO8) {
                 const float c = vf < 0.f ? 0.f : (vf > 65535.f ? 65535.f : vf);
                 unsigned w = (unsigned)c;
@@ -813,6 +868,16 @@ void b2s_launch_convert_f32(const float *in, int64_t n, int mode, int shift, voi
     k_convert_f32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, n, mode, shift, out);
 }
 
+void b2s_launch_epi_thresholds(float *thr, const B2sEpiFn &f, int *d_kmax, cudaStream_t s)
+{
+    k_epi_thresholds<<<256, 256, 0, s>>>(thr, f);
+    k_epi_kmax<<<1, 1, 0, s>>>(f, d_kmax);
+}
+void b2s_launch_epi_table_check(const float *thr, const B2sEpiFn &f, int kmax, unsigned long long first, unsigned long long count,
+                                unsigned long long *mismatches, cudaStream_t s)
+{
+    k_epi_table_check<<<148 * 16, 256, 0, s>>>(thr, f, kmax, first, count, mismatches);
+}
 void b2s_launch_log1p_lut(float *lut, int n, cudaStream_t s) { k_log1p_lut<<<(n + 255) / 256, 256, 0, s>>>(lut, n); }
 
 void b2s_launch_minmax(const void *in, int dtype, size_t plane_elems, int n_planes, unsigned *mm, cudaStream_t s)

@@ -65,7 +65,7 @@ EXPORTS = (
     "b2s_version", "b2s_params_default", "b2s_create", "b2s_destroy", "b2s_last_error", "b2s_device_sm_count",
     "b2s_plan_create", "b2s_plan_destroy", "b2s_plan_query", "b2s_plan_geometry", "b2s_resize_table", "b2s_plan_set_flat", "b2s_plan_set_notch", "b2s_plan_wants_notch_matrix", "b2s_plan_set_notch_matrix", "b2s_plan_set_bleach_levels", "b2s_plan_set_mask_thresholds", "b2s_plan_set_aa_weights", "b2s_run",
     "b2s_host_alloc", "b2s_host_free", "b2s_launch_count", "b2s_timing_enable", "b2s_timing_read",
-    "b2s_debug_read", "b2s_debug_math",
+    "b2s_debug_read", "b2s_debug_math", "b2s_debug_expm1_table_check",
     "b2s_resize_aa", "b2s_isotropic_xy", "b2s_isotropic_z", "b2s_isotropic_convert", "b2s_is_uniform", "b2s_histogram", "b2s_img_mask", "b2s_deflate_bound", "b2s_deflate_strips",
 )
 
@@ -128,6 +128,7 @@ def lib():
             L.b2s_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), i32]
             L.b2s_debug_read.argtypes = [vp, i32, i32, i32, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
             L.b2s_debug_math.argtypes = [vp, i32, vp, vp, i64]
+            L.b2s_debug_expm1_table_check.argtypes = [vp, i32, C.c_double, i32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
             _lib = L
     return _lib
 

@@ -280,6 +280,11 @@ int b2s_histogram(b2s_context *ctx, const void *in, int in_is_device, int dtype,
 int b2s_is_uniform(b2s_context *ctx, const void *d_in, int dtype, int64_t n, int32_t *uniform, void *stream);
 
 int b2s_debug_math(b2s_context *ctx, int which /*0 log1pf, 1 expm1f*/, const float *in, float *out, int64_t n);
+/* the fast epilogue maps a log value to its output integer — expm1f, [rint + clip of the integer path], dark, clip — through
+ * 65 535 thresholds and an approximate exponential: compares that with the direct evaluation for the float bit patterns
+ * [first, first + count) (all 2^32 in the GPU tests) for one combination of int_path / dark / work dtype */
+int b2s_debug_expm1_table_check(b2s_context *ctx, int int_path, double dark, int work_dtype, uint64_t first, uint64_t count,
+                                uint64_t *mismatches);
 
 #ifdef __cplusplus
 }

@@ -541,6 +541,20 @@ def test_bleach_clip_levels_from_multiotsu_per_plane(kw):
     assert np.array_equal(out[0], orc.process_img(stack[0].copy(), dark=100, **base))
 
 
+@pytest.mark.parametrize("int_path,dark,work", [(1, 0.0, 1), (0, 100.0, 1), (1, 100.0, 1), (1, 7.0, 0), (0, 0.0, 1)])
+def test_epilogue_threshold_table_is_exhaustively_exact(int_path, dark, work):
+    """the fast epilogue's log value -> integer map (expm1f, [rint + clip], dark, clip) comes from 65 535 thresholds + an
+    approximate exponential (pointwise.cu): identical to the direct evaluation of the fdlibm mirror for EVERY float32 bit
+    pattern (2^32 of them, NaNs and infinities included), which also proves the mirror monotone where it matters."""
+    import ctypes as C
+    from pystripe import _native
+    ctx = _native.context(0)
+    bad = C.c_uint64(123)
+    for first in range(0, 1 << 32, 1 << 30):
+        ctx.check(_native.lib().b2s_debug_expm1_table_check(ctx._h, int_path, dark, work, first, 1 << 30, C.byref(bad)))
+        assert bad.value == 0, (hex(first), bad.value)
+
+
 def test_get_img_mask_matches_the_oracle():
     """get_img_mask (core.py:475-489) on the GPU: threshold, box close / open (even and odd kernels, kernels larger than the
     plane), corner flood fills — every mask identical to the oracle's (itself pinned against cv2)."""
