@@ -1759,6 +1759,14 @@ B2sXfftPlan *b2s_xfft_create(int n)
         }
         if (G) break;
     }
+    if (n_blue) {   // experiments: B2S_XFFT_G_BLUE forces the rows per CTA of a Bluestein plan when its work set fits
+        static const int forced = getenv("B2S_XFFT_G_BLUE") ? atoi(getenv("B2S_XFFT_G_BLUE")) : 0;
+        if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) {
+            const int keep = b.inst;
+            b.inst = 1;
+            if (xfft_smem(n, forced, b, a.gt_max) <= (size_t)220 * 1024) G = forced; else b.inst = keep;
+        }
+    }
     if (!G) { cudaFree(pl->d_tab); delete pl; return nullptr; }
     a.G = G;
     a.lgG = 0;

@@ -1649,10 +1649,31 @@ class _BatchPipeline:
                 return self._compute_loop()
         return self._compute_loop()
 
+    def _get(self, q):
+        """blocking get that gives up when the pipeline is stopping (the sentinel of a dead producer may not have fitted the
+        bounded queue): returns None then, like the sentinel."""
+        while True:
+            try:
+                return q.get(timeout=0.2)
+            except Empty:
+                if self.sh.stop.is_set():
+                    return None
+
     def _compute_loop(self):
         sh = self.sh
+        try:
+            self._compute_items()
+        finally:                                                         # also when this thread dies: the last one out tells the writer
+            with sh.lock:
+                self._compute_left -= 1
+                last = self._compute_left == 0
+            if last:
+                self._put(self.q_write, None)
+
+    def _compute_items(self):
+        sh = self.sh
         while True:
-            item = self.q_ready.get()
+            item = self._get(self.q_ready)
             if item is None or sh.stop.is_set():
                 if item is None:
                     self._put(self.q_ready, None)                        # the sibling compute threads stop too
@@ -1680,11 +1701,6 @@ class _BatchPipeline:
             del buf
             if not self._put(self.q_write, (jobs, res, valid)):
                 return
-        with sh.lock:
-            self._compute_left -= 1
-            last = self._compute_left == 0
-        if last:
-            self._put(self.q_write, None)
 
     def _slow_file(self, job):
         sh = self.sh
@@ -1704,7 +1720,7 @@ class _BatchPipeline:
     def _writer(self):
         sh = self.sh
         while True:
-            item = self.q_write.get()
+            item = self._get(self.q_write)
             if item is None:
                 break
             jobs, res, valid = item
