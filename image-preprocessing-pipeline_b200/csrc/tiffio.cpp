@@ -473,12 +473,99 @@ int read_raw(const Mapped &m, const char *path, void *dst, int32_t height, int32
     return 0;
 }
 
+// .png: greyscale, 8 or 16 bits, not interlaced (the tiles the reference reads through imageio's PNG-FI plugin,
+// core.py:209-210).  One zlib stream over the IDAT chunks, scanline filters None / Sub / Up / Average / Paeth (PNG 1.2 §6),
+// 16-bit samples big-endian.  Colour, palette, alpha or interlaced files are left to the caller's general reader.
+struct Png { int64_t width = 0, height = 0; int depth = 0; };
+int png_header(const Mapped &m, const char *path, Png &png)
+{
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (m.size < 33 || memcmp(m.p, sig, 8) != 0) return fail(B2SIO_ERR_FORMAT, "%s: not a PNG file", path);
+    Reader r{m.p, m.size, false};
+    if (r.u32(8) != 13 || memcmp(m.p + 12, "IHDR", 4) != 0) return fail(B2SIO_ERR_FORMAT, "%s: IHDR is not the first chunk", path);
+    png.width = r.u32(16); png.height = r.u32(20); png.depth = m.p[24];
+    const int colour = m.p[25], interlace = m.p[28];
+    if (png.width <= 0 || png.height <= 0) return fail(B2SIO_ERR_FORMAT, "%s: empty image", path);
+    if (colour != 0 || interlace != 0 || (png.depth != 8 && png.depth != 16))
+        return fail(B2SIO_ERR_UNSUPPORTED, "%s: colour type %d, depth %d, interlace %d (greyscale 8 / 16 bit, not interlaced, is decoded here)",
+                    path, colour, png.depth, interlace);
+    return 0;
+}
+
+int read_png(const Mapped &m, const char *path, void *dst, int32_t height, int32_t width, int32_t dtype)
+{
+    Png png;
+    if (int rc = png_header(m, path, png)) return rc;
+    const int es = png.depth / 8;
+    if (png.height != height || png.width != width || dtype != (es == 2 ? 1 : 0))
+        return fail(B2SIO_ERR_SHAPE, "%s: %lld x %lld, %d bits, expected %d x %d dtype %d", path, (long long)png.height, (long long)png.width,
+                    png.depth, height, width, dtype);
+    const size_t row_bytes = (size_t)width * es, stride = row_bytes + 1;
+    std::vector<uint8_t> raw(stride * (size_t)height);
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit(&zs) != Z_OK) return fail(B2SIO_ERR_IO, "%s: inflateInit failed", path);
+    zs.next_out = raw.data();
+    zs.avail_out = (uInt)std::min<size_t>(raw.size(), 0xFFFFFFFFu);
+    if (raw.size() > 0xFFFFFFFFull) { inflateEnd(&zs); return fail(B2SIO_ERR_UNSUPPORTED, "%s: image too large for this decoder", path); }
+    Reader r{m.p, m.size, false};
+    size_t pos = 8;
+    int zrc = Z_OK;
+    bool end = false;
+    while (!end && pos + 12 <= m.size) {
+        const uint32_t len = r.u32(pos);
+        const uint8_t *type = m.p + pos + 4;
+        if (pos + 12 + (size_t)len > m.size) { inflateEnd(&zs); return fail(B2SIO_ERR_FORMAT, "%s: truncated chunk", path); }
+        if (memcmp(type, "IDAT", 4) == 0 && zrc == Z_OK) {
+            zs.next_in = const_cast<Bytef *>(m.p + pos + 8);
+            zs.avail_in = len;
+            zrc = inflate(&zs, Z_NO_FLUSH);
+            if (zrc != Z_OK && zrc != Z_STREAM_END) { inflateEnd(&zs); return fail(B2SIO_ERR_FORMAT, "%s: inflate failed (%d)", path, zrc); }
+        } else if (memcmp(type, "IEND", 4) == 0) end = true;
+        pos += 12 + (size_t)len;
+    }
+    const size_t got = raw.size() - zs.avail_out;
+    inflateEnd(&zs);
+    if (got != raw.size()) return fail(B2SIO_ERR_FORMAT, "%s: %zu of %zu bytes of scanlines", path, got, raw.size());
+    // undo the scanline filters in place, then copy out (16 bit: big-endian -> native)
+    const size_t bpp = (size_t)es;
+    for (int64_t y = 0; y < height; ++y) {
+        uint8_t *cur = raw.data() + (size_t)y * stride + 1;
+        const uint8_t *up = y ? cur - stride : nullptr;
+        const int ft = cur[-1];
+        switch (ft) {
+        case 0: break;
+        case 1: for (size_t i = bpp; i < row_bytes; ++i) cur[i] = (uint8_t)(cur[i] + cur[i - bpp]); break;
+        case 2: if (up) for (size_t i = 0; i < row_bytes; ++i) cur[i] = (uint8_t)(cur[i] + up[i]); break;
+        case 3:
+            for (size_t i = 0; i < row_bytes; ++i) {
+                const int a = i >= bpp ? cur[i - bpp] : 0, b = up ? up[i] : 0;
+                cur[i] = (uint8_t)(cur[i] + ((a + b) >> 1));
+            }
+            break;
+        case 4:
+            for (size_t i = 0; i < row_bytes; ++i) {
+                const int a = i >= bpp ? cur[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
+                const int pp = a + b - c, pa = abs(pp - a), pb = abs(pp - b), pc = abs(pp - c);
+                cur[i] = (uint8_t)(cur[i] + (pa <= pb && pa <= pc ? a : (pb <= pc ? b : c)));
+            }
+            break;
+        default: return fail(B2SIO_ERR_FORMAT, "%s: scanline filter %d", path, ft);
+        }
+        uint8_t *d = (uint8_t *)dst + (size_t)y * row_bytes;
+        if (es == 1 || !host_is_le()) memcpy(d, cur, row_bytes);
+        else for (int64_t x = 0; x < width; ++x) { d[2 * x] = cur[2 * x + 1]; d[2 * x + 1] = cur[2 * x]; }
+    }
+    return 0;
+}
+
 int read_any(const char *path, void *dst, int32_t height, int32_t width, int32_t dtype, int n_threads)
 {
     if (!path || !dst || height <= 0 || width <= 0 || dtype < 0 || dtype > 2) return fail(B2SIO_ERR_INVALID, "bad argument");
     Mapped m;
     if (int rc = m.open_file(path)) return rc;
     if (ends_with_ci(path, ".raw")) return read_raw(m, path, dst, height, width, dtype, n_threads);
+    if (ends_with_ci(path, ".png")) return read_png(m, path, dst, height, width, dtype);
     return read_tiff(m, path, dst, height, width, dtype, n_threads);
 }
 
@@ -629,6 +716,13 @@ int b2sio_probe(const char *path, b2sio_info *info)
         bool be;
         if (int rc = raw_header(m, path, h, w, be)) return rc;
         info->height = (int32_t)h; info->width = (int32_t)w; info->dtype = 1; info->big_endian = be; info->n_chunks = 1;
+        return 0;
+    }
+    if (ends_with_ci(path, ".png")) {
+        Png png;
+        if (int rc = png_header(m, path, png)) return rc;
+        info->height = (int32_t)png.height; info->width = (int32_t)png.width; info->dtype = png.depth == 16 ? 1 : 0;
+        info->compression = 8; info->big_endian = 1; info->n_chunks = 1;
         return 0;
     }
     Tiff t;

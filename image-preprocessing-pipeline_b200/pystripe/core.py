@@ -816,14 +816,15 @@ def imread_tif_raw_png(path: Path, dtype: str = None, shape: Tuple[int, int] = N
 
 
 def _decode_image(path: Path):
-    if path.suffix.lower() in ('.tif', '.tiff'):
+    if path.suffix.lower() in ('.tif', '.tiff', '.png'):
         try:                                        # native codec (libb2sio): strips / tiles decoded on several threads
             return _io.read(path)
-        except _io.CodecError as e:
+        except _io.CodecError as e:                 # (greyscale PNG only: colour / interlaced files go to Pillow below)
             if e.code == _io.ERR_IO:
                 raise OSError(str(e))
         except OSError:
             pass                                    # library not built: fall through to the Python decoders
+    if path.suffix.lower() in ('.tif', '.tiff'):
         try:
             import tifffile
             return tifffile.imread(path)
@@ -1558,7 +1559,7 @@ class _BatchPipeline:
         if sh.tile_size is not None and sh.d_type is not None and np.dtype(sh.d_type).kind in "uf":
             return tuple(int(v) for v in sh.tile_size), np.dtype(sh.d_type)
         for f, _, z in group:
-            if z is None and f.suffix.lower() in ('.tif', '.tiff', '.raw'):
+            if z is None and f.suffix.lower() in ('.tif', '.tiff', '.raw', '.png'):
                 try:
                     shape, dtype, _ = _io.probe(f)
                     return shape, dtype
@@ -1576,7 +1577,7 @@ class _BatchPipeline:
             fast, slow = [], []
             for job in group:
                 f, _, z = job
-                ok = shape is not None and z is None and f.suffix.lower() in ('.tif', '.tiff', '.raw') and \
+                ok = shape is not None and z is None and f.suffix.lower() in ('.tif', '.tiff', '.raw', '.png') and \
                     np.dtype(dtype) in (np.uint8, np.uint16, np.float32)
                 (fast if ok else slow).append(job)
             if fast:

@@ -11,8 +11,9 @@
  * Plain C ABI, no CUDA: this library only touches host memory.  Host binding: pystripe/_io.py (ctypes).
  * Supported TIFF subset (what light-sheet tile stacks are): classic and BigTIFF, II / MM byte order, one sample per
  * pixel, 8 / 16-bit unsigned or 32-bit float, strips or tiles, compression none (1), LZW (5), deflate (8, 32946), ZSTD (50000),
- * predictor none or horizontal differencing (2); the first IFD is the image.  Anything else returns
- * B2SIO_ERR_UNSUPPORTED and the Python host falls back to Pillow for that file, as the reference does.
+ * predictor none or horizontal differencing (2); the first IFD is the image.  PNG (core.py:209-210): greyscale, 8 or 16 bits,
+ * not interlaced, every scanline filter.  Anything else returns B2SIO_ERR_UNSUPPORTED and the Python host falls back to
+ * Pillow for that file, as the reference does.
  */
 #ifndef B2SIO_H
 #define B2SIO_H

@@ -84,6 +84,27 @@ def test_gpu_deflated_results_are_laid_out_as_tiff_files(tmp_path, host_only, mo
     assert not made and np.array_equal(_io.read(tmp_path / "out6" / "img_0003.tif"), planes["img_0003.tif"] + 1)
 
 
+def test_png_stacks_take_the_batch_path(tmp_path, host_only, monkeypatch):
+    """greyscale PNG tiles (core.py:209-210) are decoded by the native codec into the batch buffer like TIFF tiles."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    (tmp_path / "in").mkdir()
+    planes = {}
+    for z in range(5):
+        img = rng.integers(0, 60000, (33, 47)).astype(np.uint16)
+        Image.fromarray(img).save(tmp_path / "in" / f"p_{z:03d}.png")
+        planes[f"p_{z:03d}.tif"] = img
+    batches = []
+    monkeypatch.setattr(core, "process_img", lambda stack, **kw: (batches.append(stack.shape[0]), stack)[1])
+    slow = []
+    monkeypatch.setattr(core._BatchPipeline, "_slow_file", lambda self, job: slow.append(job))
+    assert core.batch_filter(tmp_path / "in", tmp_path / "out", workers=4, threads_per_gpu=4, sigma=(8, 8), wavelet="db2",
+                             compression=None) == 0
+    assert sum(batches) == 5 and not slow
+    for name, img in planes.items():
+        assert np.array_equal(_io.read(tmp_path / "out" / name), img)
+
+
 def test_a_failing_batch_is_reported_and_the_rest_still_runs(tmp_path, host_only, monkeypatch):
     """MemoryError / AssertionError used to kill the feeder thread and batch_filter still returned 0."""
     _write_stack(tmp_path / "in", 9)

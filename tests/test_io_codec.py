@@ -171,6 +171,62 @@ def test_raw_tiles_both_byte_orders(tmp_path):
     assert arr.dtype == np.uint16 and arr.dtype.isnative and np.array_equal(arr, img)
 
 
+def test_reads_greyscale_png(tmp_path):
+    """8 / 16-bit greyscale PNG (the reference reads them through imageio, core.py:209-210): every scanline filter, written
+    by Pillow and by OpenCV; colour files are refused (the caller's general reader takes them)."""
+    from PIL import Image
+    cv2 = pytest.importorskip("cv2")
+    for dtype in (np.uint8, np.uint16):
+        img = _tile(211, 307, dtype, seed=6)
+        p = tmp_path / "a.png"
+        Image.fromarray(img).save(p, format="PNG")                 # Pillow picks filters per row (adaptive)
+        shape, dt, info = _io.probe(p)
+        assert shape == img.shape and dt == np.dtype(dtype) and info.n_chunks == 1
+        assert np.array_equal(_io.read(p), img)
+        for strategy in (cv2.IMWRITE_PNG_STRATEGY_DEFAULT, cv2.IMWRITE_PNG_STRATEGY_FILTERED, cv2.IMWRITE_PNG_STRATEGY_RLE):
+            cv2.imwrite(str(p), img, [cv2.IMWRITE_PNG_STRATEGY, strategy, cv2.IMWRITE_PNG_COMPRESSION, 3])
+            assert np.array_equal(_io.read(p), img)
+    # hand-built file that uses each filter type once per five rows, IDAT split over several chunks
+    import struct
+    import zlib
+    img = _tile(23, 31, np.uint16, seed=7)
+    be = img.astype(">u2").view(np.uint8).reshape(23, 62).astype(np.int32)
+    rows = []
+    for y in range(23):
+        ft = y % 5
+        cur = be[y]
+        up = be[y - 1] if y else np.zeros(62, np.int32)
+        left = np.concatenate([np.zeros(2, np.int32), cur[:-2]])
+        upleft = np.concatenate([np.zeros(2, np.int32), up[:-2]])
+        if ft == 0:
+            enc = cur
+        elif ft == 1:
+            enc = cur - left
+        elif ft == 2:
+            enc = cur - up
+        elif ft == 3:
+            enc = cur - ((left + up) >> 1)
+        else:
+            pp = left + up - upleft
+            pa, pb, pc = abs(pp - left), abs(pp - up), abs(pp - upleft)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, up, upleft))
+            enc = cur - pred
+        rows.append(bytes([ft]) + (enc & 0xff).astype(np.uint8).tobytes())
+    z = zlib.compress(b"".join(rows), 6)
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 31, 23, 16, 0, 0, 0, 0)) + \
+        chunk(b"IDAT", z[:40]) + chunk(b"tEXt", b"k\0v") + chunk(b"IDAT", z[40:]) + chunk(b"IEND", b"")
+    p = tmp_path / "filters.png"
+    p.write_bytes(png)
+    assert np.array_equal(_io.read(p), img)
+    Image.fromarray(np.dstack([_tile(20, 20, np.uint8)] * 3)).save(tmp_path / "rgb.png")
+    with pytest.raises(_io.CodecError) as e:
+        _io.read(tmp_path / "rgb.png")
+    assert e.value.code == _io.ERR_UNSUPPORTED
+
+
 def test_batch_reports_per_file_status(tmp_path):
     imgs = np.stack([_tile(64, 80, np.uint16, seed=s) for s in range(5)])
     paths = [tmp_path / f"s{i}.tif" for i in range(5)]
