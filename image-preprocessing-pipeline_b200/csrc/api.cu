@@ -1084,6 +1084,14 @@ int b2s_create(int device, b2s_context **out)
     if (prop.major < 10)
         return fail(ctx, B2S_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
                     prop.minor);
+    {   // temporaries of the stream-ordered entries (histogram, mask, deflate) stay in the pool between calls (up to 1 GiB)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = 1ull << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     return B2S_OK;
 }
 

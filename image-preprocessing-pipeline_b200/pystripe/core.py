@@ -1401,13 +1401,22 @@ def _to_device(buf, device):
     return torch.from_numpy(buf).cuda(device, non_blocking=True)
 
 
-def _own_stream(device):
-    """context: a CUDA stream of this thread's own on `device` (hook, like _to_device)."""
+_compute_streams = {}
+
+
+def _own_stream(device, index=0):
+    """context: this compute thread's own CUDA stream on `device` (hook, like _to_device).  The stream objects live as long
+    as the process: torch's caching allocator keys its free blocks by stream, so a fresh stream per call would re-allocate
+    every batch-sized tensor."""
     import contextlib
     import torch
+    with _plans_lock:
+        st = _compute_streams.get((device, index))
+        if st is None:
+            st = _compute_streams[(device, index)] = torch.cuda.Stream(device)
     stack = contextlib.ExitStack()
     stack.enter_context(torch.cuda.device(device))
-    stack.enter_context(torch.cuda.stream(torch.cuda.Stream(device)))
+    stack.enter_context(torch.cuda.stream(st))
     return stack
 
 
@@ -1511,8 +1520,12 @@ class _BatchPipeline:
         # compute threads on their own CUDA streams overlap one group's copies with the other's kernels
         self.n_compute = max(1, int(os.environ.get("B200STRIPE_COMPUTE_THREADS", "2"))) if getattr(shared, "gpu_deflate", False) else 1
         self._compute_left = self.n_compute
+        import functools
+        computes = [functools.partial(self._compute, k) for k in range(self.n_compute)]
+        for c in computes:
+            c.__name__ = "_compute"
         self.threads = [threading.Thread(target=self._guard, args=(f,), daemon=True)
-                        for f in [self._reader] + [self._compute] * self.n_compute + [self._writer]]
+                        for f in [self._reader] + computes + [self._writer]]
         self.pool = ThreadPoolExecutor(max_workers=max(2, shared.write_threads))
 
     def start(self):
@@ -1644,9 +1657,9 @@ class _BatchPipeline:
         return valid
 
     # ---- stage 2: the GPU
-    def _compute(self):
+    def _compute(self, index=0):
         if self.n_compute > 1:
-            with _own_stream(self.device):
+            with _own_stream(self.device, index):
                 return self._compute_loop()
         return self._compute_loop()
 

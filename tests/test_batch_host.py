@@ -16,7 +16,7 @@ def host_only(monkeypatch):
     monkeypatch.setattr(core, "_visible_gpus", lambda: [0])
     monkeypatch.setattr(core, "use_device", lambda d: __import__("contextlib").nullcontext())
     monkeypatch.setattr(core, "_to_device", lambda buf, device: buf)       # the device-resident leg of the default compression
-    monkeypatch.setattr(core, "_own_stream", lambda device: __import__("contextlib").nullcontext())
+    monkeypatch.setattr(core, "_own_stream", lambda device, index=0: __import__("contextlib").nullcontext())
     for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
 

@@ -42,7 +42,7 @@ def _worker(rank, world, port, src, dst):
     core.use_device = lambda d: __import__("contextlib").nullcontext()
     core._batch_buffer = lambda device, shape, dtype: np.empty(shape, dtype)   # pinned memory needs the GPU
     core._to_device = lambda buf, device: buf
-    core._own_stream = lambda device: __import__("contextlib").nullcontext()
+    core._own_stream = lambda device, index=0: __import__("contextlib").nullcontext()
     rc = core.batch_filter(Path(src), Path(dst), workers=2, threads_per_gpu=3, sigma=(8, 8), wavelet="db2")
     t = torch.tensor([sum(seen), rc], dtype=torch.int64)
     dist.all_reduce(t)                            # bookkeeping only (tests): total planes processed, sum of return codes
