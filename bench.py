@@ -505,7 +505,7 @@ def roofline(a, ctx, info, run, d_in, P, ms_max):
             "note": "exact mode issues a separate multiply and add per tap / butterfly term (2 lane-ops per MAC): instruction issue "
                     "and the FP32 pipe, not HBM, bound the DWT and notch kernels; kernel_frac = the dominant kernel's modelled "
                     "lane-ops (DWT: taps; notch: the O(radix^2) phases of scipy's generic radices only) / its time / peak"}
-    roof = {"bound": "hbm", "binding_in_practice": "instruction issue / FP32 pipe (ncu: profiles/r02_main_kernels.md)",
+    roof = {"bound": "hbm", "binding_in_practice": "instruction issue / FP32 pipe (ncu: profiles/r02_final_main_kernels.md)",
             "kernel": f"{kname}@level{lvl}" if lvl else kname, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "fp32": fp32,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
