@@ -594,6 +594,7 @@ int write_tiff_layout(const char *path, int32_t height, int32_t width, int32_t d
 {
     const int es = dtype_size(dtype);
     const int64_t n_strips = (int64_t)pieces.size();
+    if (n_strips == 0) return fail(B2SIO_ERR_INVALID, "%s: no strips to write", path);
     std::vector<uint32_t> offs(n_strips), cnts(n_strips);
     uint64_t pos = 8;
     for (int64_t s = 0; s < n_strips; ++s) {

@@ -1395,6 +1395,11 @@ class _DeflatedPlanes:
         return np.frombuffer(raw, dtype=self.dtype).reshape(self.shape)
 
 
+# the device-resident leg keeps a group's input, result and deflate buffers in HBM (about 3.2 x the group per compute thread):
+# groups of whole stitched slices stay on the host-staged path
+_DEVICE_GROUP_LIMIT = int(float(os.environ.get("B200STRIPE_DEVICE_GROUP_GB", "4")) * 2 ** 30)
+
+
 def _to_device(buf, device):
     """the decoded (page-locked) batch as a CUDA tensor (hook: the host-logic tests run without a GPU)."""
     import torch
@@ -1698,7 +1703,7 @@ class _BatchPipeline:
             jobs, buf, valid = item
             try:
                 with use_device(self.device):
-                    if sh.gpu_deflate and buf.dtype in (np.uint8, np.uint16):
+                    if sh.gpu_deflate and buf.dtype in (np.uint8, np.uint16) and buf.nbytes <= _DEVICE_GROUP_LIMIT:
                         # device-resident batch: the result is deflated where it was computed, D2H carries compressed bytes
                         res = process_img(_to_device(buf, self.device), tile_size=buf.shape[1:],
                                           d_type=sh.d_type if sh.d_type is not None else buf.dtype, _max_batch=sh.batch, **sh.kw)
