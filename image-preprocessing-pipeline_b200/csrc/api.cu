@@ -1,4 +1,5 @@
 // C ABI (include/b200stripe.h): contexts, plans (geometry, tables, workspace) and the batched run loop.
+#include <emmintrin.h>
 #include <sched.h>
 
 #include <atomic>
@@ -1028,6 +1029,29 @@ HostPool *host_pool(b2s_context *ctx)
     return ctx->pool;
 }
 
+// Staging copy with non-temporal stores: the destination (a pinned staging buffer, or the caller's result array) is not read
+// again by this core, so write-allocate traffic — one extra DRAM read per written line with ordinary stores below glibc's
+// non-temporal threshold — is pure loss on a path bounded by host memory bandwidth.  B2S_HOST_NT=0 restores memcpy.
+void stream_copy(void *dst, const void *src, size_t n)
+{
+    static const bool nt = !(getenv("B2S_HOST_NT") && atoi(getenv("B2S_HOST_NT")) == 0);
+    if (!nt || n < 4096) { memcpy(dst, src, n); return; }
+    char *d = (char *)dst;
+    const char *s = (const char *)src;
+    const size_t head = (16 - ((uintptr_t)d & 15)) & 15;
+    if (head) { memcpy(d, s, head); d += head; s += head; n -= head; }
+    const size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks; ++i) {
+        const __m128i a = _mm_loadu_si128((const __m128i *)(s)), b = _mm_loadu_si128((const __m128i *)(s + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i *)(s + 32)), e = _mm_loadu_si128((const __m128i *)(s + 48));
+        _mm_stream_si128((__m128i *)(d), a); _mm_stream_si128((__m128i *)(d + 16), b);
+        _mm_stream_si128((__m128i *)(d + 32), c); _mm_stream_si128((__m128i *)(d + 48), e);
+        s += 64; d += 64;
+    }
+    _mm_sfence();
+    if (n & 63) memcpy(d, s, n & 63);
+}
+
 // memcpy split over the pool; `grp` counts the chunks still running
 void copy_async(HostPool *pool, TaskGroup *grp, void *dst, const void *src, size_t bytes)
 {
@@ -1038,7 +1062,7 @@ void copy_async(HostPool *pool, TaskGroup *grp, void *dst, const void *src, size
     grp->add(parts);
     for (int i = 0; i < parts; ++i) {
         const size_t o = std::min(bytes, per * i), e = std::min(bytes, per * (i + 1));
-        pool->submit([=] { if (e > o) memcpy((char *)dst + o, (const char *)src + o, e - o); grp->done(); });
+        pool->submit([=] { if (e > o) stream_copy((char *)dst + o, (const char *)src + o, e - o); grp->done(); });
     }
 }
 
