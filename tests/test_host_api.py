@@ -265,3 +265,12 @@ def test_bleach_plan_args_host_logic():
         core._bleach_plan_args(0.01, 5.0, 4.0, 6.0, False, False)
     with pytest.raises(AssertionError):
         core._bleach_plan_args(1, 4.0, 5.0, 6.0, False, False)                   # int frequency, as the reference asserts
+
+
+def test_integration_stub_mirrors_the_parameter_struct():
+    """the ctypes stub shown to reference maintainers lists struct b2s_params field for field."""
+    import re
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    block = doc[doc.index("class B2SParams"):doc.index("_PAD = ")]
+    shown = re.findall(r'\("([a-z_0-9]+)", C\.', block)
+    assert shown == [f[0] for f in _native.Params._fields_]
