@@ -273,4 +273,4 @@ def test_integration_stub_mirrors_the_parameter_struct():
     doc = (ROOT / "INTEGRATION.md").read_text()
     block = doc[doc.index("class B2SParams"):doc.index("_PAD = ")]
     shown = re.findall(r'\("([a-z_0-9]+)", C\.', block)
-    assert shown == [f[0] for f in _native.Params._fields_]
+    assert shown == [f[0] for f in _lib().Params._fields_]
